@@ -1,0 +1,1000 @@
+/*
+ * maple_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of the SPR-likelihood hot path of the reference MAPLEv0.7.5.4.py,
+ * operating on the packed genome-list format of maple_b200/genome_list.py.  It exists only
+ * so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * can check and time the CUDA path against an independent CPU implementation.  The product
+ * path (maple_b200/) never links, imports or calls anything in this directory.
+ *
+ * Parity pin: every function here is checked against (inputs -> output) vectors recorded from
+ * the unmodified reference running in the build container (tests/golden/NAME.json.gz, generated
+ * by tests/golden/make_golden.py; checked by tests/test_oracle_golden.py).
+ *
+ * Reference lines (all in /root/reference/MAPLEv0.7.5.4.py):
+ *   getPartialVec 4073-4141 | simplify 3697-3717 | shorten 3721-3745
+ *   mergeVectors 4446-4859 | appendProbNode 6505-6785
+ *   estimateBranchLengthWithDerivative 5040-5358 | areVectorsDifferent 5419-5472
+ *   passGenomeListThroughBranch 3749-3877 | rootVector 4916-4996 | findProbRoot 4865-4912
+ *
+ * Floating point: compiled with -ffp-contract=off so that a*b+c rounds twice like CPython.
+ * All four co-walks use the fact that the packed format stores an explicit end position for
+ * every entry: the next segment boundary is always min(end1,end2) (the reference's
+ * "pos+1 or min(entry1[1],entry2[1])" case split collapses to that).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    int32_t lRef;
+    int32_t U;        /* usingErrorRate */
+    int32_t errSS;    /* errorRateSiteSpecific */
+    int32_t rateVar;  /* useRateVariation */
+    double Q[16];     /* mutMatrixGlobal, row-major Q[i][j] */
+    double pi[4];     /* rootFreqs */
+    double errorRate; /* errorRateGlobal */
+    double totError;
+    double thresholdProb;
+    double thresholdDiffForUpdate;
+    double thresholdFoldChangeUpdate;
+    double minBLenSensitivity;
+    const double *siteRates;  /* [lRef] or NULL */
+    const double *errorRates; /* [lRef] or NULL */
+    const double *cumRate;    /* cumulativeRate [lRef+1] */
+    const double *cumErr;     /* cumulativeErrorRate [lRef+1] or NULL */
+    const int32_t *cumBases;  /* cumulativeBases [(lRef+1)*4] or NULL (findProbRoot only) */
+    const double *piLogErrCum; /* rootFreqsLogErrorCumulative [lRef+1] or NULL */
+} OrModel;
+
+#define MINIMUM_CARRY_OVER (DBL_MIN * 1e50) /* reference :3623 */
+
+typedef struct {
+    const uint32_t *key;
+    const double *pay;
+    int type, nl, flag, nuc, end;
+    double l0, l1;
+    const double *vec;
+} Cur;
+
+static inline void cur_next(Cur *c) {
+    uint32_t k = *c->key++;
+    c->type = (int)(k & 7u);
+    c->nl = (int)((k >> 3) & 3u);
+    c->flag = (int)((k >> 5) & 1u);
+    c->nuc = (int)((k >> 6) & 3u);
+    c->end = (int)(k >> 8);
+    c->l0 = c->l1 = 0.0;
+    if (c->nl >= 1) c->l0 = *c->pay++;
+    if (c->nl == 2) c->l1 = *c->pay++;
+    c->vec = NULL;
+    if (c->type == 6) {
+        c->vec = c->pay;
+        c->pay += 4;
+    }
+}
+
+static inline void cur_init(Cur *c, const uint32_t *key, const double *pay) {
+    c->key = key;
+    c->pay = pay;
+    cur_next(c);
+}
+
+static inline const double *site_Q(const OrModel *m, int pos, double *buf) {
+    if (!m->rateVar) return m->Q;
+    double r = m->siteRates[pos];
+    for (int i = 0; i < 16; i++) buf[i] = m->Q[i] * r; /* mutMatrices[pos][j][k]=Q[j][k]*siteRates[pos], :6367 */
+    return buf;
+}
+
+static inline double site_eps(const OrModel *m, int pos) {
+    return (m->U && m->errSS) ? m->errorRates[pos] : m->errorRate;
+}
+
+static inline void uniform4(double *o) { o[0] = o[1] = o[2] = o[3] = 0.25; }
+
+/* python's builtin sum() over a 4-list of floats.  CPython >= 3.12 (the interpreter the golden
+ * vectors were recorded with) uses Neumaier compensated summation for floats; pypy3 and older
+ * CPython add left to right.  -DMAPLE_NAIVE_SUM selects the latter.  The two differ by at most
+ * one ulp of the normalised vectors. */
+static inline double py_sum4(const double *v) {
+#ifdef MAPLE_NAIVE_SUM
+    return ((v[0] + v[1]) + v[2]) + v[3];
+#else
+    double f = v[0], c = 0.0;
+    for (int i = 1; i < 4; i++) {
+        double x = v[i], t = f + x;
+        if (fabs(f) >= fabs(x)) c += (f - t) + x;
+        else c += (x - t) + f;
+        f = t;
+    }
+    if (c != 0.0 && isfinite(c)) f += c;
+    return f;
+#endif
+}
+
+/* getPartialVec, i12==6 (:4085-4109) */
+static void gv_vec(const double *Q, double t, const double *v, int up, double *o) {
+    if (t == 0.0) {
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
+        return;
+    }
+    double r[4];
+    for (int i = 0; i < 4; i++) {
+        double tot = 0.0;
+        for (int j = 0; j < 4; j++) tot += (up ? Q[j * 4 + i] : Q[i * 4 + j]) * v[j];
+        tot *= t;
+        tot += v[i];
+        if (tot < 0) { uniform4(o); return; }
+        r[i] = tot;
+    }
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+}
+
+/* getPartialVec, i12<4 (:4110-4141); flag must already include "usingErrorRate and" */
+static void gv_nuc(const double *Q, double eps, int x, double t, int up, int flag, double *o) {
+    if (flag) {
+        double nv[4];
+        for (int i = 0; i < 4; i++) nv[i] = eps * 0.33333;
+        nv[x] = 1.0 - eps;
+        if (t == 0.0) { o[0] = nv[0]; o[1] = nv[1]; o[2] = nv[2]; o[3] = nv[3]; return; }
+        double r[4];
+        for (int j = 0; j < 4; j++) {
+            double tot = 0.0;
+            for (int i = 0; i < 4; i++) tot += Q[j * 4 + i] * nv[i];
+            tot *= t;
+            tot += nv[j];
+            if (tot < 0) { uniform4(o); return; }
+            r[j] = tot;
+        }
+        o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = r[3];
+        return;
+    }
+    if (t == 0.0) {
+        o[0] = o[1] = o[2] = o[3] = 0.0;
+        o[x] += 1.0;
+        return;
+    }
+    for (int i = 0; i < 4; i++) o[i] = (up ? Q[x * 4 + i] : Q[i * 4 + x]) * t;
+    o[x] += 1.0;
+    if (o[x] < 0) uniform4(o);
+}
+
+/* ------------------------------------------------------------------ appendProbNode */
+double or_append(const OrModel *m, const uint32_t *kP, const double *pP, const uint32_t *kC, const double *pC,
+                 int isTipC, double bLen) {
+    const int lRef = m->lRef, U = m->U;
+    Cur e1, e2;
+    cur_init(&e1, kP, pP);
+    cur_init(&e2, kC, pC);
+    int pos = 0;
+    double F = 1.0, contrib = bLen;
+    double Lk = bLen * (-(double)lRef);
+    if (U && isTipC) Lk += m->totError;
+    double Qb[16], t2[4], t3[4];
+    for (;;) {
+        int newPos = e1.end < e2.end ? e1.end : e2.end;
+        if (e2.type != 5 && e1.type != 5) {
+            if (e1.type != e2.type || e1.type == 6) { /* :6586-6599 */
+                contrib = bLen;
+                if (e1.type < 5) {
+                    if (e1.nl == 1) contrib += e1.l0;
+                    else if (e1.nl == 2) contrib += e1.l1;
+                } else if (e1.nl == 1) contrib += e1.l0;
+                if (e2.nl == 1) contrib += e2.l0;
+            }
+            if (e1.type == 4) {
+                if (e2.type == 4) {
+                    /* R / R: nothing */
+                } else if (e2.type == 6) { /* :6611-6638 */
+                    const double *Q = site_Q(m, pos, Qb);
+                    int i1 = e2.nuc;
+                    if (e2.vec[i1] > 0.02) F *= e2.vec[i1];
+                    else {
+                        double tot;
+                        if (e1.nl == 2) {
+                            int flag1 = U && e1.flag;
+                            double eps = site_eps(m, pos);
+                            tot = 0.0;
+                            gv_vec(Q, contrib, e2.vec, 0, t3);
+                            gv_nuc(Q, eps, i1, e1.l0, 0, flag1, t2);
+                            for (int i = 0; i < 4; i++) tot += t3[i] * t2[i] * m->pi[i];
+                            tot /= m->pi[i1];
+                        } else if (contrib != 0.0) {
+                            gv_vec(Q, contrib, e2.vec, 0, t3);
+                            tot = t3[i1];
+                        } else tot = e2.vec[i1];
+                        F *= tot;
+                    }
+                } else { /* R / different nucleotide :6640-6663 */
+                    int flag2 = U && (isTipC || (e2.nl > 0 && e2.flag));
+                    const double *Q = site_Q(m, pos, Qb);
+                    if (e1.nl == 2) {
+                        int flag1 = U && e1.flag;
+                        int i1 = e2.nuc, i2 = e2.type;
+                        double eps = site_eps(m, pos);
+                        gv_nuc(Q, eps, i2, contrib, 0, flag2, t3);
+                        gv_nuc(Q, eps, i1, e1.l0, 0, flag1, t2);
+                        double tot = 0.0;
+                        for (int i = 0; i < 4; i++) tot += t3[i] * t2[i] * m->pi[i];
+                        F *= tot / m->pi[i1];
+                    } else if (flag2) {
+                        double eps = site_eps(m, pos);
+                        F *= fmin(0.25, Q[e2.nuc * 4 + e2.type] * contrib) + eps * 0.33333;
+                    } else if (contrib != 0.0) {
+                        F *= fmin(0.25, Q[e2.nuc * 4 + e2.type] * contrib);
+                    } else return -INFINITY;
+                }
+            } else if (e1.type == 6) { /* :6674-6703 */
+                const double *Q = site_Q(m, pos, Qb);
+                if (e2.type == 6) {
+                    double tot = 0.0;
+                    if (contrib != 0.0) {
+                        gv_vec(Q, contrib, e2.vec, 0, t3);
+                        for (int j = 0; j < 4; j++) tot += e1.vec[j] * t3[j];
+                    } else
+                        for (int j = 0; j < 4; j++) tot += e1.vec[j] * e2.vec[j];
+                    F *= tot;
+                } else {
+                    int i2 = (e2.type == 4) ? e1.nuc : e2.type;
+                    if (e1.vec[i2] > 0.02) F *= e1.vec[i2];
+                    else {
+                        int fl = U && (isTipC || (e2.nl > 0 && e2.flag));
+                        double eps = fl ? site_eps(m, pos) : 0.0;
+                        gv_nuc(Q, eps, i2, contrib, 0, fl, t3);
+                        double tot = 0.0;
+                        for (int j = 0; j < 4; j++) tot += e1.vec[j] * t3[j];
+                        F *= tot;
+                    }
+                }
+            } else { /* e1 is a non-reference nucleotide :6713-6761 */
+                if (e2.type != e1.type) {
+                    int flag1 = U && e1.nl > 0 && e1.flag;
+                    const double *Q = site_Q(m, pos, Qb);
+                    int i1 = e1.type;
+                    if (e2.type < 5) {
+                        int i2 = (e2.type == 4) ? e1.nuc : e2.type;
+                        int flag2 = U && (isTipC || (e2.nl > 0 && e2.flag));
+                        if (e1.nl == 2) {
+                            double eps = site_eps(m, pos);
+                            gv_nuc(Q, eps, i2, contrib, 0, flag2, t3);
+                            gv_nuc(Q, eps, i1, e1.l0, 0, flag1, t2);
+                            double tot = 0.0;
+                            for (int j = 0; j < 4; j++) tot += m->pi[j] * t3[j] * t2[j];
+                            F *= tot / m->pi[i1];
+                        } else if (flag1 || flag2) {
+                            double eps = site_eps(m, pos);
+                            F *= (fmin(0.25, Q[i1 * 4 + i2] * contrib) + (double)(flag1 + flag2) * 0.33333 * eps);
+                        } else if (contrib != 0.0) {
+                            F *= fmin(0.25, Q[i1 * 4 + i2] * contrib);
+                        } else return -INFINITY;
+                    } else { /* nucleotide / O */
+                        double eps = site_eps(m, pos);
+                        if (e2.vec[i1] > 0.02) F *= e2.vec[i1];
+                        else if (e1.nl == 2) {
+                            gv_nuc(Q, eps, i1, e1.l0, 0, flag1, t2);
+                            gv_vec(Q, contrib, e2.vec, 0, t3);
+                            double tot = 0.0;
+                            for (int i = 0; i < 4; i++) tot += t2[i] * t3[i] * m->pi[i];
+                            F *= (tot / m->pi[i1]);
+                        } else if (contrib != 0.0) {
+                            gv_vec(Q, contrib, e2.vec, 0, t3);
+                            F *= t3[i1];
+                        } else F *= e2.vec[i1];
+                    }
+                }
+            }
+        }
+        pos = newPos;
+        if (pos == lRef) break;
+        if (e1.end == pos) cur_next(&e1);
+        if (e2.end == pos) cur_next(&e2);
+        if (F <= MINIMUM_CARRY_OVER) { /* :6772-6783 */
+            if (F < DBL_MIN) return -INFINITY;
+            Lk += log(F);
+            F = 1.0;
+        }
+    }
+    if (!(F > 0.0)) return -INFINITY; /* python would raise on log(0); the caller treats it as no placement */
+    return Lk + log(F);
+}
+
+/* ------------------------------------------------------------------ output writer */
+typedef struct {
+    uint32_t *key;
+    double *pay;
+    int nk, np;
+} Out;
+
+static inline void out_put(Out *o, int type, int nl, int flag, int nuc, int end, double l0, double l1, const double *vec) {
+    o->key[o->nk++] = (uint32_t)(type & 7) | ((uint32_t)(nl & 3) << 3) | ((uint32_t)(flag ? 1 : 0) << 5) |
+                      ((uint32_t)(nuc & 3) << 6) | ((uint32_t)end << 8);
+    if (nl >= 1) o->pay[o->np++] = l0;
+    if (nl == 2) o->pay[o->np++] = l1;
+    if (type == 6) {
+        o->pay[o->np++] = vec[0]; o->pay[o->np++] = vec[1]; o->pay[o->np++] = vec[2]; o->pay[o->np++] = vec[3];
+    }
+}
+
+/* simplify (:3697-3717): 4 = collapses to the local reference, 0-3 = to that nucleotide, 6 = stays O */
+static int simplify4(const double *v, int refA, double thr) {
+    double maxP = 0.0;
+    int maxI = 0, numA = 0;
+    for (int i = 0; i < 4; i++) {
+        if (v[i] > maxP) { maxP = v[i]; maxI = i; }
+        if (v[i] > thr) numA++;
+    }
+    if (numA == 1) return maxI == refA ? 4 : maxI;
+    return 6;
+}
+
+/* ------------------------------------------------------------------ mergeVectors
+ * returns 0 = list written, 1 = None (incompatible at zero distance / zero product).
+ * flags: bit0 isUpDown, bit1 returnLK.  Output capacity: nk <= n1+n2, np <= 6*(n1+n2). */
+int or_merge(const OrModel *m, const uint32_t *k1, const double *p1, double bLen1, int fromTip1, const uint32_t *k2,
+             const double *p2, double bLen2, int fromTip2, int flags, int numMinor1, int numMinor2, uint32_t *outKey,
+             double *outPay, int32_t *outNk, int32_t *outNp, double *outLk) {
+    const int lRef = m->lRef, U = m->U, isUpDown = flags & 1, returnLK = (flags >> 1) & 1;
+    Cur e1, e2;
+    cur_init(&e1, k1, p1);
+    cur_init(&e2, k2, p2);
+    Out o = {outKey, outPay, 0, 0};
+    int pos = 0;
+    double totalFactor = 1.0, cumulPartLk = 0.0, cumErrorRate = 0.0;
+    double Qb[16], nv[4], nv2[4];
+    const double *cr = m->cumRate, *ce = m->cumErr;
+    if (returnLK) { /* :4487-4494 */
+        cumulPartLk = (bLen1 + bLen2) * (-(double)lRef);
+        if (U) {
+            if (fromTip1 || numMinor1) cumulPartLk += m->totError * (1 + numMinor1);
+            if (fromTip2 || numMinor2) cumulPartLk += m->totError * (1 + numMinor2);
+        }
+    }
+    for (;;) {
+        int newPos = e1.end < e2.end ? e1.end : e2.end;
+        if (e1.type == 5 || e2.type == 5) {
+            if (e1.type == 5 && e2.type == 5) {
+                out_put(&o, 5, 0, 0, 0, newPos, 0, 0, NULL);
+            } else if (e1.type == 5) {
+                if (e2.type < 5) { /* copy entry2, adding bLen2 :4501-4548 */
+                    int t = e2.type, nuc = e2.nuc;
+                    if (isUpDown) {
+                        if (U) {
+                            if (e2.nl == 0) {
+                                if (bLen2 != 0.0 || fromTip2) out_put(&o, t, 2, fromTip2, nuc, newPos, bLen2, 0.0, NULL);
+                                else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                            } else out_put(&o, t, 2, e2.nl == 1 ? e2.flag : (e2.l1 != 0.0), nuc, newPos, e2.l0 + bLen2, 0.0, NULL);
+                        } else {
+                            if (e2.nl > 0) out_put(&o, t, 2, 0, nuc, newPos, e2.l0 + bLen2, 0.0, NULL);
+                            else if (bLen2 != 0.0) out_put(&o, t, 2, 0, nuc, newPos, bLen2, 0.0, NULL);
+                            else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                        }
+                    } else {
+                        if (U) {
+                            if (e2.nl == 0) {
+                                if (bLen2 != 0.0 || fromTip2) out_put(&o, t, 1, fromTip2, nuc, newPos, bLen2, 0, NULL);
+                                else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                            } else out_put(&o, t, 1, e2.nl == 1 ? e2.flag : (e2.l1 != 0.0), nuc, newPos, e2.l0 + bLen2, 0, NULL);
+                        } else {
+                            if (e2.nl > 0) out_put(&o, t, 1, 0, nuc, newPos, e2.l0 + bLen2, 0, NULL);
+                            else if (bLen2 != 0.0) out_put(&o, t, 1, 0, nuc, newPos, bLen2, 0, NULL);
+                            else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                        }
+                    }
+                } else { /* N / O :4550-4576 */
+                    if (isUpDown) {
+                        const double *Q = site_Q(m, pos, Qb);
+                        double totB = bLen2;
+                        if (e2.nl == 1) totB += e2.l0;
+                        gv_vec(Q, totB, e2.vec, 0, nv);
+                        for (int i = 0; i < 4; i++) nv[i] *= m->pi[i];
+                        double s = py_sum4(nv);
+                        for (int i = 0; i < 4; i++) nv[i] /= s;
+                        out_put(&o, 6, 0, 0, e2.nuc, newPos, 0, 0, nv);
+                    } else {
+                        if (e2.nl == 1) out_put(&o, 6, 1, 0, e2.nuc, newPos, e2.l0 + bLen2, 0, e2.vec);
+                        else if (bLen2 != 0.0) out_put(&o, 6, 1, 0, e2.nuc, newPos, bLen2, 0, e2.vec);
+                        else out_put(&o, 6, 0, 0, e2.nuc, newPos, 0, 0, e2.vec);
+                    }
+                }
+            } else { /* entry2 is N, entry1 informative :4590-4668 */
+                if (e1.type < 5) {
+                    int t = e1.type, nuc = e1.nuc;
+                    if (isUpDown) {
+                        if (U) {
+                            if (e1.nl == 0) {
+                                if (bLen1 != 0.0) out_put(&o, t, 1, 0, nuc, newPos, bLen1, 0, NULL);
+                                else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                            } else if (e1.nl == 1) out_put(&o, t, 1, e1.flag, nuc, newPos, e1.l0 + bLen1, 0, NULL);
+                            else out_put(&o, t, 2, e1.flag, nuc, newPos, e1.l0, e1.l1 + bLen1, NULL);
+                        } else {
+                            if (e1.nl == 0) {
+                                if (bLen1 != 0.0) out_put(&o, t, 1, 0, nuc, newPos, bLen1, 0, NULL);
+                                else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                            } else if (e1.nl == 1) out_put(&o, t, 1, 0, nuc, newPos, e1.l0 + bLen1, 0, NULL);
+                            else out_put(&o, t, 2, 0, nuc, newPos, e1.l0, e1.l1 + bLen1, NULL);
+                        }
+                    } else {
+                        if (U) {
+                            if (e1.nl == 0) {
+                                if (bLen1 != 0.0 || fromTip1) out_put(&o, t, 1, fromTip1, nuc, newPos, bLen1, 0, NULL);
+                                else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                            } else out_put(&o, t, 1, e1.nl == 1 ? e1.flag : (e1.l1 != 0.0), nuc, newPos, e1.l0 + bLen1, 0, NULL);
+                        } else {
+                            if (e1.nl > 0) out_put(&o, t, 1, 0, nuc, newPos, e1.l0 + bLen1, 0, NULL);
+                            else if (bLen1 != 0.0) out_put(&o, t, 1, 0, nuc, newPos, bLen1, 0, NULL);
+                            else out_put(&o, t, 0, 0, nuc, newPos, 0, 0, NULL);
+                        }
+                    }
+                } else { /* O / N :4644-4668 */
+                    if (isUpDown && ((e1.nl == 1 && e1.l0 > 0) || bLen1 != 0.0)) {
+                        const double *Q = site_Q(m, pos, Qb);
+                        double totB = bLen1;
+                        if (e1.nl == 1) totB += e1.l0;
+                        gv_vec(Q, totB, e1.vec, 1, nv);
+                        double s = py_sum4(nv);
+                        for (int i = 0; i < 4; i++) nv[i] /= s;
+                        out_put(&o, 6, 0, 0, e1.nuc, newPos, 0, 0, nv);
+                    } else {
+                        if (e1.nl == 1) out_put(&o, 6, 1, 0, e1.nuc, newPos, e1.l0 + bLen1, 0, e1.vec);
+                        else if (bLen1 != 0.0) out_put(&o, 6, 1, 0, e1.nuc, newPos, bLen1, 0, e1.vec);
+                        else out_put(&o, 6, 0, 0, e1.nuc, newPos, 0, 0, e1.vec);
+                    }
+                }
+            }
+            if (returnLK) { /* :4578-4587 / :4670-4679 */
+                cumulPartLk += (bLen1 + bLen2) * (cr[pos] - cr[newPos]);
+                if (U) {
+                    if (fromTip1 || fromTip2) {
+                        if (m->errSS) cumErrorRate = ce[newPos] - ce[pos];
+                        else cumErrorRate = m->errorRate * (newPos - pos);
+                    }
+                    if (fromTip1) cumulPartLk += cumErrorRate;
+                    if (fromTip2) cumulPartLk += cumErrorRate;
+                }
+            }
+        } else { /* both informative :4682-4826 */
+            double totLen1 = bLen1;
+            if (e1.type == 6) {
+                if (e1.nl == 1) totLen1 += e1.l0;
+            } else if (e1.nl >= 1) {
+                totLen1 += e1.l0;
+                if (e1.nl == 2) totLen1 += e1.l1;
+            }
+            double totLen2 = bLen2;
+            if (e2.nl >= 1) totLen2 += e2.l0;
+            int flag1 = U && e1.type != 6 && ((e1.nl > 0 && e1.flag) || fromTip1);
+            int flag2 = U && e2.type != 6 && ((e2.nl > 0 && e2.flag) || fromTip2);
+            int refNuc = -1;
+            if (returnLK) {
+                if (e1.type == 4 && e2.type == 4) { /* :4704-4714 */
+                    if (totLen2 > bLen2 || totLen1 > bLen1) {
+                        cumulPartLk += (totLen2 - bLen2 + totLen1 - bLen1) * (cr[newPos] - cr[pos]);
+                        if (U) {
+                            if (((!fromTip1) && flag1) || ((!fromTip2) && flag2)) {
+                                if (m->errSS) cumErrorRate = ce[pos] - ce[newPos];
+                                else cumErrorRate = m->errorRate * (pos - newPos);
+                                if ((!fromTip1) && flag1) cumulPartLk += cumErrorRate;
+                                if ((!fromTip2) && flag2) cumulPartLk += cumErrorRate;
+                            }
+                        }
+                    }
+                } else { /* :4715-4730 */
+                    refNuc = (e1.type != 4) ? e1.nuc : e2.nuc;
+                    const double *Q = site_Q(m, pos, Qb);
+                    cumulPartLk -= Q[refNuc * 4 + refNuc] * (bLen2 + bLen1);
+                    if (U && ((e1.type != e2.type) || e1.type == 6) && (fromTip1 || fromTip2)) {
+                        cumErrorRate = m->errSS ? m->errorRates[pos] : m->errorRate;
+                        if (fromTip1) cumulPartLk += cumErrorRate;
+                        if (fromTip2) cumulPartLk += cumErrorRate;
+                    }
+                }
+            }
+            if (e2.type == e1.type && e2.type < 5) { /* identical :4732-4751 */
+                if (e1.type == 4) out_put(&o, 4, 0, 0, 0, newPos, 0, 0, NULL);
+                else {
+                    out_put(&o, e1.type, 0, 0, e1.nuc, newPos, 0, 0, NULL);
+                    if (returnLK) {
+                        const double *Q = site_Q(m, pos, Qb);
+                        cumulPartLk += Q[e1.type * 4 + e1.type] * (totLen1 + totLen2);
+                        if (U) {
+                            if (((!fromTip1) && flag1) || ((!fromTip2) && flag2)) {
+                                cumErrorRate = m->errSS ? m->errorRates[pos] : m->errorRate;
+                                if ((!fromTip1) && flag1) cumulPartLk -= cumErrorRate;
+                                if ((!fromTip2) && flag2) cumulPartLk -= cumErrorRate;
+                            }
+                        }
+                    }
+                }
+            } else if (totLen1 == 0.0 && totLen2 == 0.0 && e1.type < 5 && e2.type < 5 && !flag1 && !flag2) {
+                return 1; /* :4753-4758 */
+            } else { /* :4759-4826 */
+                double eps = site_eps(m, pos);
+                const double *Q = site_Q(m, pos, Qb);
+                int i1, i2;
+                if (e1.type == 4) { refNuc = e2.nuc; i1 = refNuc; }
+                else { refNuc = e1.nuc; i1 = e1.type; }
+                if (i1 <= 4) {
+                    if (totLen1 != 0.0 || flag1) {
+                        if (isUpDown && e1.nl == 2) {
+                            gv_nuc(Q, eps, i1, e1.l0, 0, flag1, nv);
+                            for (int i = 0; i < 4; i++) nv[i] *= m->pi[i];
+                            if (e1.l1 + bLen1 != 0.0) {
+                                double tmp[4];
+                                gv_vec(Q, e1.l1 + bLen1, nv, 1, tmp);
+                                memcpy(nv, tmp, sizeof tmp);
+                            }
+                        } else gv_nuc(Q, eps, i1, totLen1, isUpDown, flag1, nv);
+                    } else {
+                        nv[0] = nv[1] = nv[2] = nv[3] = 0.0;
+                        nv[i1] = 1.0;
+                    }
+                } else gv_vec(Q, totLen1, e1.vec, isUpDown, nv);
+                i2 = (e2.type == 4) ? refNuc : e2.type;
+                if (i2 == 6) gv_vec(Q, totLen2, e2.vec, 0, nv2);
+                else if (totLen2 != 0.0 || flag2) gv_nuc(Q, eps, i2, totLen2, 0, flag2, nv2);
+                else {
+                    nv2[0] = nv2[1] = nv2[2] = nv2[3] = 0.0;
+                    nv2[i2] = 1.0;
+                }
+                for (int j = 0; j < 4; j++) nv[j] *= nv2[j];
+                double totSum = py_sum4(nv);
+                if (totSum == 0.0) return 1;
+                for (int i = 0; i < 4; i++) nv[i] /= totSum;
+                int state = simplify4(nv, refNuc, m->thresholdProb);
+                if (state == 6) out_put(&o, 6, 0, 0, refNuc, newPos, 0, 0, nv);
+                else if (state == 4) out_put(&o, 4, 0, 0, 0, newPos, 0, 0, NULL);
+                else out_put(&o, state, 0, 0, refNuc, newPos, 0, 0, NULL);
+                if (returnLK) totalFactor *= totSum;
+            }
+        }
+        pos = newPos;
+        if (returnLK && totalFactor <= MINIMUM_CARRY_OVER) { /* :4830-4839 */
+            if (totalFactor < DBL_MIN) return 2;
+            cumulPartLk += log(totalFactor);
+            totalFactor = 1.0;
+        }
+        if (pos == lRef) break;
+        if (e1.end == pos) cur_next(&e1);
+        if (e2.end == pos) cur_next(&e2);
+    }
+    *outNk = o.nk;
+    *outNp = o.np;
+    if (returnLK && outLk) *outLk = cumulPartLk + log(totalFactor);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ shorten (:3721-3745), out of place */
+void or_shorten(const OrModel *m, const uint32_t *k, const double *p, uint32_t *outKey, double *outPay, int32_t *outNk,
+                int32_t *outNp) {
+    const int lRef = m->lRef;
+    const double thr = m->thresholdProb;
+    Cur c;
+    cur_init(&c, k, p);
+    Out o = {outKey, outPay, 0, 0};
+    /* The reference keeps comparing against `entryOld`, which is NOT refreshed after a pop: the
+     * anchor of a run is its first entry, while the entry that survives is the last one. */
+    Cur anchor = c, pending = c;
+    while (pending.end != lRef) {
+        cur_next(&c);
+        int mergeable = 0;
+        if (c.type == 4 && anchor.type == 4 && c.nl == anchor.nl) {
+            if (c.nl == 0) mergeable = 1;
+            else if (fabs(c.l0 - anchor.l0) > thr) mergeable = 0;
+            else if (c.nl == 2 && fabs(c.l1 - anchor.l1) > thr) mergeable = 0;
+            else mergeable = (!m->U) || (c.flag == anchor.flag);
+        }
+        if (!mergeable) {
+            out_put(&o, pending.type, pending.nl, pending.flag, pending.nuc, pending.end, pending.l0, pending.l1, pending.vec);
+            anchor = c;
+        }
+        pending = c;
+    }
+    out_put(&o, pending.type, pending.nl, pending.flag, pending.nuc, pending.end, pending.l0, pending.l1, pending.vec);
+    *outNk = o.nk;
+    *outNp = o.np;
+}
+
+/* ------------------------------------------------------------------ estimateBranchLengthWithDerivative
+ * returns 0 = value in *out, 1 = python False.  scratch: ais[n1+n2] */
+int or_blen(const OrModel *m, const uint32_t *kP, const double *pP, const uint32_t *kC, const double *pC, int fromTipC,
+            double *ais, double *out) {
+    const int lRef = m->lRef, U = m->U;
+    const double *pi = m->pi;
+    Cur e1, e2;
+    cur_init(&e1, kP, pP);
+    cur_init(&e2, kC, pC);
+    int pos = 0, nA = 0, nZeros = 0;
+    double c1 = -(double)lRef;
+    double Qb[16];
+    const double *cr = m->cumRate;
+    for (;;) {
+        int end = e1.end < e2.end ? e1.end : e2.end;
+        if (e2.type == 5 || e1.type == 5) {
+            c1 += (cr[pos] - cr[end]);
+        } else if (e1.type == 4 && e2.type == 4) {
+        } else {
+            const double *Q = site_Q(m, pos, Qb);
+            if (e1.type == 4) c1 -= Q[e2.nuc * 4 + e2.nuc];
+            else c1 -= Q[e1.nuc * 4 + e1.nuc];
+            int flag1 = U && e1.type != 6 && e1.nl > 0 && e1.flag;
+            int flag2 = U && e2.type != 6 && (fromTipC || (e2.nl > 0 && e2.flag));
+            double eps = site_eps(m, pos);
+            double contrib = 0.0;
+            if (e1.type < 5) {
+                if (e1.nl == 1) contrib = e1.l0;
+                else if (e1.nl == 2) contrib = e1.l1;
+            } else if (e1.nl == 1) contrib = e1.l0;
+            if (e2.nl >= 1) contrib += e2.l0;
+            double coeff0 = 0.0, coeff1 = 0.0;
+            int mode = 0; /* 1: coeff0/coeff1 pair; 2: single a-value; 0: nothing */
+            int valid = 1;
+            if (e1.type == 4 || (e1.type < 4 && e2.type != e1.type)) {
+                /* parent state x: for R it is the local reference carried by the child entry */
+                int x = (e1.type == 4) ? e2.nuc : e1.type;
+                if (e2.type == 6) { /* :5128-5155, :5253-5278 */
+                    const double *v = e2.vec;
+                    mode = 1;
+                    if (e1.nl == 2) {
+                        coeff0 = pi[x] * v[x];
+                        coeff1 = 0.0;
+                        for (int i = 0; i < 4; i++) {
+                            coeff0 += pi[i] * Q[i * 4 + x] * e1.l0 * v[i];
+                            coeff1 += Q[x * 4 + i] * v[i];
+                        }
+                        coeff1 *= pi[x];
+                        if (contrib != 0.0) coeff0 += coeff1 * contrib;
+                        if (flag1) {
+                            coeff0 -= 1.33333 * eps * pi[x] * v[x];
+                            for (int i = 0; i < 4; i++) coeff0 += pi[i] * v[i] * 0.33333 * eps;
+                        }
+                    } else {
+                        coeff0 = v[x];
+                        coeff1 = 0.0;
+                        for (int j = 0; j < 4; j++) coeff1 += Q[x * 4 + j] * v[j];
+                        if (contrib != 0.0) coeff0 += coeff1 * contrib;
+                    }
+                } else { /* child is a different single nucleotide (or R under a nucleotide parent) */
+                    int c = (e2.type == 4) ? e1.nuc : e2.type;
+                    mode = 2;
+                    if (e1.nl == 2) { /* :5158-5172, :5230-5242 */
+                        coeff0 = pi[c] * Q[c * 4 + x] * e1.l0;
+                        if (contrib != 0.0) coeff0 += pi[x] * Q[x * 4 + c] * contrib;
+                        if (flag2) coeff0 += pi[x] * 0.33333 * eps;
+                        if (flag1) coeff0 += pi[c] * 0.33333 * eps;
+                        coeff1 = pi[x] * Q[x * 4 + c];
+                        if (coeff1 != 0.0) coeff0 = coeff0 / coeff1;
+                        else valid = 0;
+                    } else {
+                        coeff0 = contrib;
+                        if (flag2) {
+                            /* the R-parent branch guards against a zero rate (:5176), the nucleotide-parent one does not (:5246) */
+                            if (e1.type == 4 && Q[x * 4 + c] == 0.0) valid = 0;
+                            else coeff0 += eps * 0.33333 / Q[x * 4 + c];
+                        }
+                    }
+                }
+            } else if (e1.type == 6) { /* :5188-5215 */
+                const double *a = e1.vec;
+                mode = 1;
+                if (e2.type == 6) {
+                    const double *b = e2.vec;
+                    coeff0 = a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
+                    coeff1 = 0.0;
+                    for (int i = 0; i < 4; i++)
+                        for (int j = 0; j < 4; j++) coeff1 += a[i] * b[j] * Q[i * 4 + j];
+                    if (contrib != 0.0) coeff0 += coeff1 * contrib;
+                } else {
+                    int i2 = (e2.type == 4) ? e1.nuc : e2.type;
+                    coeff0 = a[i2];
+                    coeff1 = 0.0;
+                    for (int i = 0; i < 4; i++) coeff1 += a[i] * Q[i * 4 + i2];
+                    if (contrib != 0.0) coeff0 += coeff1 * contrib;
+                    if (flag2) coeff0 += eps * 0.33333;
+                }
+            } else { /* same non-reference nucleotide on both sides :5220-5221 */
+                c1 += Q[e1.type * 4 + e1.type];
+            }
+            if (mode == 1) {
+                if (coeff1 < 0.0) c1 += coeff1 / coeff0;
+                else if (coeff1 != 0.0) ais[nA++] = coeff0 / coeff1;
+            } else if (mode == 2 && valid) {
+                if (coeff0 != 0.0) ais[nA++] = coeff0;
+                else nZeros++;
+            }
+        }
+        pos = end;
+        if (pos == lRef) break;
+        if (e1.end == pos) cur_next(&e1);
+        if (e2.end == pos) cur_next(&e2);
+    }
+    /* :5298-5358 */
+    c1 = -c1;
+    int n = nA + nZeros;
+    *out = 0.0;
+    if (n == 0) return 1;
+    double minAis = 0.0, maxAis = 0.0;
+    if (nA) {
+        minAis = maxAis = ais[0];
+        for (int i = 1; i < nA; i++) {
+            if (ais[i] < minAis) minAis = ais[i];
+            if (ais[i] > maxAis) maxAis = ais[i];
+        }
+    }
+    if (nZeros) minAis = fmin(0.0, minAis);
+    if (minAis < 0.0) { *out = 0.1; return 0; }
+    const double sens = m->minBLenSensitivity;
+    double tDown = fmin(0.1, n / c1 - minAis);
+    if (tDown <= 0.0) return 1;
+    double vDown = nZeros ? nZeros / tDown : 0.0;
+    for (int i = 0; i < nA; i++) vDown += 1.0 / (ais[i] + tDown);
+    double tUp = fmin(0.1, n / c1 - maxAis);
+    if (tUp >= 0.1) { *out = 0.1; return 0; }
+    if (tUp <= sens) tUp = (minAis != 0.0) ? 0.0 : sens;
+    double vUp = nZeros ? nZeros / tUp : 0.0;
+    for (int i = 0; i < nA; i++) vUp += 1.0 / (ais[i] + tUp);
+    if (vDown > c1 + sens || vUp < c1 - sens) {
+        if (vUp < c1 - sens && tUp == 0.0) return 1;
+        if (vDown > c1 + sens && tDown >= 0.1) { *out = 0.1; return 0; }
+    }
+    while (tDown - tUp > sens) {
+        double tMid = (tUp + tDown) / 2;
+        double vMid = nZeros ? nZeros / tMid : 0.0;
+        for (int i = 0; i < nA; i++) vMid += 1.0 / (ais[i] + tMid);
+        if (vMid > c1) tUp = tMid;
+        else tDown = tMid;
+    }
+    *out = tUp;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ areVectorsDifferent (:5419-5472) */
+int or_differ(const OrModel *m, const uint32_t *k1, const double *p1, const uint32_t *k2, const double *p2) {
+    if (!k2) return 1;
+    const int lRef = m->lRef, U = m->U;
+    const double thr = m->thresholdProb;
+    Cur e1, e2;
+    cur_init(&e1, k1, p1);
+    cur_init(&e2, k2, p2);
+    for (;;) {
+        if (e1.type != e2.type) return 1;
+        if (e1.nl != e2.nl) return 1; /* tuple lengths are a function of (type, nLens) for a fixed U */
+        if (e1.type < 5) {
+            if (e1.nl >= 1) {
+                if (fabs(e1.l0 - e2.l0) > thr) return 1;
+                if (e1.nl == 2 && fabs(e1.l1 - e2.l1) > thr) return 1;
+                if (U && e1.flag != e2.flag) return 1; /* abs(True-False)=1 > thresholdProb */
+            }
+        } else if (e1.type == 6) {
+            if (e1.nl == 1 && fabs(e1.l0 - e2.l0) > thr) return 1;
+            for (int i = 0; i < 4; i++) {
+                double a = e1.vec[i], b = e2.vec[i];
+                double d = fabs(a - b);
+                if (d != 0.0) {
+                    if (a == 0.0 || b == 0.0) return 1;
+                    if (d > m->thresholdDiffForUpdate ||
+                        (d > thr && ((d / a > m->thresholdFoldChangeUpdate) || (d / b > m->thresholdFoldChangeUpdate))))
+                        return 1;
+                }
+            }
+        }
+        int pos = e1.end < e2.end ? e1.end : e2.end;
+        if (pos == lRef) break;
+        if (e1.end == pos) cur_next(&e1);
+        if (e2.end == pos) cur_next(&e2);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ passGenomeListThroughBranch (:3749-3877)
+ * mut: nMut triples (pos1based, upNuc, downNuc) sorted by position.  Output capacity nk <= n + 2*nMut. */
+void or_pass_branch(const OrModel *m, const uint32_t *k, const double *p, const int32_t *mut, int nMut, int dirIsUp,
+                    uint32_t *outKey, double *outPay, int32_t *outNk, int32_t *outNp) {
+    const int lRef = m->lRef;
+    Cur c;
+    cur_init(&c, k, p);
+    Out o = {outKey, outPay, 0, 0};
+    int iM = 0, lastPos = 0;
+    for (;;) {
+        if (c.type == 5) {
+            out_put(&o, 5, 0, 0, 0, c.end, 0, 0, NULL);
+            lastPos = c.end;
+            while (iM < nMut && mut[3 * iM] <= lastPos) iM++;
+        } else if (c.type < 4) {
+            lastPos += 1;
+            if (iM < nMut && mut[3 * iM] <= lastPos) {
+                int target = dirIsUp ? mut[3 * iM + 1] : mut[3 * iM + 2];
+                iM++;
+                if (c.type == target) out_put(&o, 4, c.nl, c.flag, 0, lastPos, c.l0, c.l1, NULL);
+                else out_put(&o, c.type, c.nl, c.flag, target, lastPos, c.l0, c.l1, NULL);
+            } else out_put(&o, c.type, c.nl, c.flag, c.nuc, lastPos, c.l0, c.l1, NULL);
+        } else if (c.type == 4) {
+            while (iM < nMut && mut[3 * iM] <= c.end) {
+                if (mut[3 * iM] > lastPos + 1) {
+                    lastPos = mut[3 * iM] - 1;
+                    out_put(&o, 4, c.nl, c.flag, 0, lastPos, c.l0, c.l1, NULL);
+                }
+                lastPos += 1;
+                int nucToPass = dirIsUp ? mut[3 * iM + 2] : mut[3 * iM + 1];
+                int newEl = dirIsUp ? mut[3 * iM + 1] : mut[3 * iM + 2];
+                iM++;
+                out_put(&o, nucToPass, c.nl, c.flag, newEl, lastPos, c.l0, c.l1, NULL);
+            }
+            if (lastPos < c.end) {
+                lastPos = c.end;
+                out_put(&o, 4, c.nl, c.flag, 0, lastPos, c.l0, c.l1, NULL);
+            }
+        } else {
+            lastPos += 1;
+            if (iM < nMut && mut[3 * iM] <= lastPos) {
+                int newEl = dirIsUp ? mut[3 * iM + 1] : mut[3 * iM + 2];
+                iM++;
+                out_put(&o, 6, c.nl, 0, newEl, lastPos, c.l0, 0, c.vec);
+            } else out_put(&o, 6, c.nl, 0, c.nuc, lastPos, c.l0, 0, c.vec);
+        }
+        if (lastPos == lRef) break;
+        cur_next(&c);
+    }
+    *outNk = o.nk;
+    *outNp = o.np;
+}
+
+/* ------------------------------------------------------------------ rootVector (:4916-4996) for a list that is already
+ * expressed relative to the reference genome (no MAT mutations between node and root); NOT shortened here. */
+void or_root_vector(const OrModel *m, const uint32_t *k, const double *p, double bLen, int isFromTip, uint32_t *outKey,
+                    double *outPay, int32_t *outNk, int32_t *outNp) {
+    const int lRef = m->lRef, U = m->U;
+    Cur c;
+    cur_init(&c, k, p);
+    Out o = {outKey, outPay, 0, 0};
+    int pos = 0;
+    double Qb[16], nv[4];
+    for (;;) {
+        if (c.type == 5) out_put(&o, 5, 0, 0, 0, c.end, 0, 0, NULL);
+        else if (c.type == 6) {
+            double totB = bLen;
+            if (c.nl == 1) totB += c.l0;
+            if (totB != 0.0) {
+                const double *Q = site_Q(m, pos, Qb);
+                gv_vec(Q, totB, c.vec, 0, nv);
+                for (int i = 0; i < 4; i++) nv[i] *= m->pi[i];
+            } else
+                for (int i = 0; i < 4; i++) nv[i] = c.vec[i] * m->pi[i];
+            double s = py_sum4(nv);
+            for (int i = 0; i < 4; i++) nv[i] /= s;
+            out_put(&o, 6, 0, 0, c.nuc, c.end, 0, 0, nv);
+        } else if (U) {
+            int flag1 = (c.nl > 0 && c.flag) || isFromTip;
+            if (c.nl >= 1) out_put(&o, c.type, 2, flag1, c.nuc, c.end, c.l0 + bLen, 0.0, NULL);
+            else if (bLen != 0.0 || flag1) out_put(&o, c.type, 2, flag1, c.nuc, c.end, bLen, 0.0, NULL);
+            else out_put(&o, c.type, 0, 0, c.nuc, c.end, 0, 0, NULL);
+        } else {
+            if (c.nl == 1) out_put(&o, c.type, 2, 0, c.nuc, c.end, c.l0 + bLen, 0.0, NULL);
+            else if (bLen != 0.0) out_put(&o, c.type, 2, 0, c.nuc, c.end, bLen, 0.0, NULL);
+            else out_put(&o, c.type, 0, 0, c.nuc, c.end, 0, 0, NULL);
+        }
+        pos = c.end;
+        if (pos == lRef) break;
+        cur_next(&c);
+    }
+    *outNk = o.nk;
+    *outNp = o.np;
+}
+
+/* ------------------------------------------------------------------ findProbRoot (:4865-4912), list relative to the reference */
+double or_prob_root(const OrModel *m, const uint32_t *k, const double *p) {
+    const int lRef = m->lRef, U = m->U;
+    Cur c;
+    cur_init(&c, k, p);
+    double logLK = 0.0, logFactor = 1.0;
+    int pos = 0;
+    double piLog[4];
+    for (int i = 0; i < 4; i++) piLog[i] = log(m->pi[i]);
+    for (;;) {
+        if (U && c.type < 5 && c.nl > 0 && c.flag) {
+            if (c.type == 4) logLK += m->piLogErrCum[c.end] - m->piLogErrCum[pos];
+            else {
+                double eps = m->errSS ? m->errorRates[pos] : m->errorRate;
+                logFactor *= (m->pi[c.type] * (1.0 - 1.33333 * eps) + 0.33333 * eps);
+            }
+        } else if (c.type == 4) {
+            for (int i = 0; i < 4; i++)
+                logLK += piLog[i] * (double)(m->cumBases[c.end * 4 + i] - m->cumBases[pos * 4 + i]);
+        } else if (c.type < 4) logLK += piLog[c.type];
+        else if (c.type == 6) {
+            double tot = 0.0;
+            for (int i = 0; i < 4; i++) tot += m->pi[i] * c.vec[i];
+            logFactor *= tot;
+        }
+        pos = c.end;
+        if (logFactor <= MINIMUM_CARRY_OVER) {
+            if (logFactor < DBL_MIN) return -INFINITY;
+            logLK += log(logFactor);
+            logFactor = 1.0;
+        }
+        if (pos == lRef) break;
+        cur_next(&c);
+    }
+    logLK += log(logFactor);
+    return logLK;
+}
+
+/* ------------------------------------------------------------------ batch drivers (OpenMP over host cores) */
+void or_append_batch(const OrModel *m, const uint32_t *key, const double *pay, const int64_t *keyStart,
+                     const int64_t *payStart, int64_t n, const int32_t *pIdx, const int32_t *cIdx, const uint8_t *isTip,
+                     const double *bLen, double *out) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++) {
+        int p = pIdx[i], c = cIdx[i];
+        out[i] = or_append(m, key + keyStart[p], pay + payStart[p], key + keyStart[c], pay + payStart[c], isTip[i], bLen[i]);
+    }
+}
+
+void or_merge_batch(const OrModel *m, const uint32_t *key, const double *pay, const int64_t *keyStart,
+                    const int64_t *payStart, int64_t n, const int32_t *idx1, const double *bLen1, const uint8_t *tip1,
+                    const int32_t *idx2, const double *bLen2, const uint8_t *tip2, const uint8_t *flags,
+                    const int32_t *numMinor1, const int32_t *numMinor2, uint32_t *outKey, double *outPay,
+                    const int64_t *outKeyStart, const int64_t *outPayStart, int32_t *outNk, int32_t *outNp, double *outLk,
+                    int32_t *outStatus) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        int a = idx1[i], b = idx2[i];
+        double lk = 0.0;
+        outNk[i] = outNp[i] = 0;
+        outStatus[i] = or_merge(m, key + keyStart[a], pay + payStart[a], bLen1[i], tip1[i], key + keyStart[b],
+                                pay + payStart[b], bLen2[i], tip2[i], flags[i], numMinor1 ? numMinor1[i] : 0,
+                                numMinor2 ? numMinor2[i] : 0, outKey + outKeyStart[i], outPay + outPayStart[i],
+                                &outNk[i], &outNp[i], &lk);
+        if (outLk) outLk[i] = lk;
+    }
+}
+
+void or_blen_batch(const OrModel *m, const uint32_t *key, const double *pay, const int64_t *keyStart,
+                   const int64_t *payStart, const int32_t *nkeys, int64_t n, const int32_t *pIdx, const int32_t *cIdx,
+                   const uint8_t *fromTip, double *out, int32_t *outStatus) {
+#pragma omp parallel
+    {
+        double *ais = NULL;
+        int cap = 0;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t i = 0; i < n; i++) {
+            int p = pIdx[i], c = cIdx[i];
+            int need = nkeys[p] + nkeys[c] + 1;
+            if (need > cap) {
+                free(ais);
+                cap = need * 2;
+                ais = (double *)malloc(sizeof(double) * cap);
+            }
+            outStatus[i] = or_blen(m, key + keyStart[p], pay + payStart[p], key + keyStart[c], pay + payStart[c],
+                                   fromTip[i], ais, &out[i]);
+        }
+        free(ais);
+    }
+}
+
+void or_differ_batch(const OrModel *m, const uint32_t *key, const double *pay, const int64_t *keyStart,
+                     const int64_t *payStart, int64_t n, const int32_t *idx1, const int32_t *idx2, uint8_t *out) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++) {
+        int a = idx1[i], b = idx2[i];
+        out[i] = (uint8_t)or_differ(m, key + keyStart[a], pay + payStart[a], keyStart[b] < 0 ? NULL : key + keyStart[b],
+                                    keyStart[b] < 0 ? NULL : pay + payStart[b]);
+    }
+}
+
+int or_num_threads(void) {
+    int n = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+#endif
+    return n;
+}

@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""Generate golden fixtures by RUNNING the unmodified reference (MAPLEv0.7.5.4.py).
+
+This script only runs in the build container (it needs /root/reference); the fixtures it
+writes under tests/golden/*.json.gz are committed and are what the tests read.  Nothing
+here copies reference source: the reference script is executed with runpy as __main__,
+with multiprocessing.Pool replaced by an in-process stand-in so that the frozen tree and
+the model that the reference hands to startTopologyUpdatesParallel (MAPLEv0.7.5.4.py:12289)
+can be snapshotted, and the module-level likelihood functions can be wrapped by recorders.
+
+What is recorded per config (see CONFIGS):
+  * env:    lRef, reference string, rootFreqs, flags, thresholds (module globals at the
+            time of the first Pool.map, i.e. what forked workers would inherit)
+  * model:  mutMatrixGlobal, errorRateGlobal, siteRates / errorRates when in use
+  * tree:   up/children/dist/mutations/minor counts/dirty/replacements/coreNum and the four
+            genome-list families, snapshotted BEFORE the searches run
+  * calls:  sampled (inputs -> output) of appendProbNode, mergeVectors,
+            estimateBranchLengthWithDerivative, areVectorsDifferent,
+            passGenomeListThroughBranch, rootVector, findProbRoot, shorten
+  * searches: every findBestParentTopology call of the first parallel round
+            (args -> bestNode, bestScore, branch lengths, #phase-1 candidates)
+  * proposed: the proposedMoves list returned by startTopologyUpdatesParallel per core
+  * treeLK: calculateTreeLikelihood of the frozen tree, final LK of the run
+
+Usage:  python tests/golden/make_golden.py [config ...]
+"""
+import gzip
+import io
+import json
+import os
+import runpy
+import sys
+import contextlib
+import multiprocessing
+
+REF = "/root/reference/MAPLEv0.7.5.4.py"
+EX = "/root/reference/example_files/"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CONFIGS = {
+    # name: (input file, max seqs (None = all), extra argv, per-function sample cap)
+    "ex_unrest": (EX + "MAPLE_alignment_example.txt", None, ["--model", "UNREST"], 400),
+    "ex_gtr": (EX + "MAPLE_alignment_example.txt", None, ["--model", "GTR"], 150),
+    "ex_jc": (EX + "MAPLE_alignment_example.txt", None, ["--model", "JC"], 150),
+    "ex_unrest_rv": (EX + "MAPLE_alignment_example.txt", None, ["--model", "UNREST", "--rateVariation"], 250),
+    "ex_unrest_rv_sse": (EX + "MAPLE_alignment_example.txt", None,
+                         ["--model", "UNREST", "--rateVariation", "--estimateSiteSpecificErrorRate"], 400),
+    "ex_unrest_err": (EX + "MAPLE_alignment_example.txt", None, ["--model", "UNREST", "--estimateErrorRate"], 250),
+    "ay_unrest_300": (EX + "sameRef_AY.4.2.2.maple.gz", 300, ["--model", "UNREST"], 300),
+    "ay_unrest_deep_200": (EX + "sameRef_AY.4.2.2.maple.gz", 200,
+                           ["--model", "UNREST", "--deeperSearchForLongBranches"], 100),
+}
+
+FUNCS = ["appendProbNode", "mergeVectors", "estimateBranchLengthWithDerivative", "areVectorsDifferent",
+         "passGenomeListThroughBranch", "rootVector", "findProbRoot", "shorten"]
+
+
+def truncate_input(path, max_seqs, out):
+    op = gzip.open if path.endswith(".gz") else open
+    n = -1  # the reference record counts as the first '>'
+    with op(path, "rt") as f, open(out, "w") as g:
+        for line in f:
+            if line.startswith(">"):
+                n += 1
+                if max_seqs is not None and n > max_seqs:
+                    break
+            g.write(line)
+    return out
+
+
+class ListTable:
+    """Interns genome lists by content so that the fixture stores each distinct list once."""
+
+    def __init__(self):
+        self.index = {}
+        self.lists = []
+
+    @staticmethod
+    def canon(gl):
+        out = []
+        for e in gl:
+            ee = []
+            for x in e:
+                if isinstance(x, (list, tuple)):
+                    ee.append(tuple(float(v) for v in x))
+                elif isinstance(x, bool):
+                    ee.append(bool(x))
+                else:
+                    ee.append(x)
+            out.append(tuple(ee))
+        return tuple(out)
+
+    def add(self, gl):
+        if gl is None:
+            return None
+        c = self.canon(gl)
+        i = self.index.get(c)
+        if i is None:
+            i = len(self.lists)
+            self.index[c] = i
+            self.lists.append(c)
+        return i
+
+
+def jsonable_list(c):
+    return [[list(x) if isinstance(x, tuple) else x for x in e] for e in c]
+
+
+class Recorder:
+    def __init__(self, G, cap):
+        self.G = G
+        self.cap = cap
+        self.table = ListTable()
+        self.calls = {f: [] for f in FUNCS}
+        self.count = {f: 0 for f in FUNCS}
+        self.searches = []
+        self.phase1 = 0
+        self.orig = {}
+
+    def keep(self, f, special):
+        self.count[f] += 1
+        n = self.count[f]
+        if special and len(self.calls[f]) < 3 * self.cap:
+            return True
+        # dense at the start, then geometric thinning
+        if len(self.calls[f]) >= self.cap:
+            return False
+        return n <= self.cap // 2 or n % 37 == 0
+
+    def install(self):
+        G, T = self.G, self.table
+        rec = self
+
+        o_app = G["appendProbNode"]
+
+        def appendProbNode(P, C, isTipC, bLen, **kw):
+            r = o_app(P, C, isTipC, bLen, **kw)
+            ln = sys._getframe(1).f_lineno
+            if ln in (7011, 7223):
+                rec.phase1 += 1
+            if rec.keep("appendProbNode", r == float("-inf")):
+                ip, ic = T.add(P), T.add(C)
+                rec.calls["appendProbNode"].append({"P": ip, "C": ic, "isTipC": bool(isTipC), "bLen": bLen, "out": r, "line": ln})
+            return r
+
+        o_mer = G["mergeVectors"]
+
+        def mergeVectors(v1, b1, t1, v2, b2, t2, returnLK=False, isUpDown=False, numMinor1=0, numMinor2=0, **kw):
+            r = o_mer(v1, b1, t1, v2, b2, t2, returnLK=returnLK, isUpDown=isUpDown, numMinor1=numMinor1, numMinor2=numMinor2, **kw)
+            if rec.keep("mergeVectors", r is None or returnLK):
+                i1, i2 = T.add(v1), T.add(v2)
+                if returnLK:
+                    out, lk = T.add(r[0]), r[1]
+                else:
+                    out, lk = T.add(r), None
+                rec.calls["mergeVectors"].append({"v1": i1, "b1": b1, "t1": bool(t1), "v2": i2, "b2": b2, "t2": bool(t2),
+                                                  "returnLK": bool(returnLK), "isUpDown": bool(isUpDown),
+                                                  "numMinor1": numMinor1, "numMinor2": numMinor2, "out": out, "lk": lk,
+                                                  "line": sys._getframe(1).f_lineno})
+            return r
+
+        o_bl = G["estimateBranchLengthWithDerivative"]
+
+        def estimateBranchLengthWithDerivative(P, C, fromTipC=False, **kw):
+            r = o_bl(P, C, fromTipC=fromTipC, **kw)
+            if rec.keep("estimateBranchLengthWithDerivative", r is False or r == 0.1):
+                ip, ic = T.add(P), T.add(C)
+                rec.calls["estimateBranchLengthWithDerivative"].append(
+                    {"P": ip, "C": ic, "fromTipC": bool(fromTipC), "out": (None if r is False else r)})
+            return r
+
+        o_df = G["areVectorsDifferent"]
+
+        def areVectorsDifferent(v1, v2):
+            r = o_df(v1, v2)
+            if rec.keep("areVectorsDifferent", False):
+                i1, i2 = T.add(v1), T.add(v2)
+                rec.calls["areVectorsDifferent"].append({"v1": i1, "v2": i2, "out": bool(r)})
+            return r
+
+        o_ps = G["passGenomeListThroughBranch"]
+
+        def passGenomeListThroughBranch(v, mutations, dirIsUp=False):
+            r = o_ps(v, mutations, dirIsUp=dirIsUp)
+            if rec.keep("passGenomeListThroughBranch", False):
+                i1 = T.add(v)
+                rec.calls["passGenomeListThroughBranch"].append(
+                    {"v": i1, "mutations": [list(m) for m in mutations], "dirIsUp": bool(dirIsUp), "out": T.add(r)})
+            return r
+
+        o_rv = G["rootVector"]
+
+        def rootVector(v, bLen, isFromTip, tree, node, **kw):
+            r = o_rv(v, bLen, isFromTip, tree, node, **kw)
+            # only root-relative calls without MAT mutations on the path are self-contained
+            n, clean = node, True
+            while n is not None:
+                if tree.mutations[n]:
+                    clean = False
+                n = tree.up[n]
+            if clean and rec.keep("rootVector", False):
+                i1 = T.add(v)
+                rec.calls["rootVector"].append({"v": i1, "bLen": bLen, "isFromTip": bool(isFromTip), "out": T.add(r)})
+            return r
+
+        o_sh = G["shorten"]
+
+        def shorten(v):
+            before = T.canon(v)
+            o_sh(v)
+            if rec.keep("shorten", False):
+                rec.calls["shorten"].append({"v": T.add(before), "out": T.add(v)})
+
+        o_fb = G["findBestParentTopology"]
+
+        def findBestParentTopology(tree, node, child, bestLKdiff, removedBLen, **kw):
+            before = rec.phase1
+            r = o_fb(tree, node, child, bestLKdiff, removedBLen, **kw)
+            rec.searches.append({"node": node, "child": child, "bestLKdiff": bestLKdiff, "removedBLen": removedBLen,
+                                 "strict": bool(kw.get("strictTopologyStopRules")), "fails": kw.get("allowedFailsTopology"),
+                                 "thr": kw.get("thresholdLogLKtopology"),
+                                 "bestNode": r[0], "bestScore": r[1], "blens": list(r[2]), "phase1": rec.phase1 - before})
+            return r
+
+        new = {"appendProbNode": appendProbNode, "mergeVectors": mergeVectors,
+               "estimateBranchLengthWithDerivative": estimateBranchLengthWithDerivative,
+               "areVectorsDifferent": areVectorsDifferent, "passGenomeListThroughBranch": passGenomeListThroughBranch,
+               "rootVector": rootVector, "shorten": shorten, "findBestParentTopology": findBestParentTopology}
+        for k, v in new.items():
+            self.orig[k] = G[k]
+            G[k] = v
+
+    def uninstall(self):
+        for k, v in self.orig.items():
+            self.G[k] = v
+        self.orig = {}
+
+
+def snapshot_tree(tree, root, T):
+    n = len(tree.up)
+    return {
+        "root": root,
+        "up": list(tree.up),
+        "children": [list(c) if c else [] for c in tree.children],
+        "dist": [float(d) if d else 0.0 for d in tree.dist],
+        "mutations": [[list(m) for m in (mm or [])] for mm in tree.mutations],
+        "numMinor": [len(m) if m else 0 for m in tree.minorSequences],
+        "dirty": [bool(d) for d in tree.dirty],
+        "replacements": list(tree.replacements),
+        "coreNum": list(getattr(tree, "coreNum", [None] * n)),
+        "probVect": [T.add(v) for v in tree.probVect],
+        "probVectUpRight": [T.add(v) for v in tree.probVectUpRight],
+        "probVectUpLeft": [T.add(v) for v in tree.probVectUpLeft],
+        "probVectTotUp": [T.add(v) for v in tree.probVectTotUp],
+    }
+
+
+ENV_KEYS = ["lRef", "rootFreqs", "usingErrorRate", "errorRateSiteSpecific", "useRateVariation",
+            "thresholdLogLKoptimizationTopology", "thresholdLogLKconsecutivePlacement", "deeperSearchForLongBranches",
+            "BLenThresholdDeeperSearch", "effectivelyNon0BLen", "minBLenSensitivity", "thresholdProb",
+            "thresholdDiffForUpdate", "thresholdFoldChangeUpdate", "maxReplacements", "doNotImproveTopology",
+            "defaultBLen", "oneMutBLen", "HnZ", "aBayesPlus", "model", "minimumCarryOver", "globalTotRate",
+            "thresholdTopologyPlacement", "supportFor0Branches", "doTimeTree"]
+
+
+class Harvest:
+    def __init__(self, name, cap):
+        self.name = name
+        self.cap = cap
+        self.rounds = []
+        self.first = None
+
+    def pool_map(self, func, inputs):
+        G = func.__globals__
+        inputs = list(inputs)
+        tree, root = inputs[0][0], inputs[0][1]
+        if self.first is None:
+            rec = Recorder(G, self.cap)
+            env = {k: G[k] for k in ENV_KEYS}
+            env["ref"] = G["ref"]
+            (_, _, _, strict, fails, thr, thrPlace, mutRate, errorRateGlobal, mutMatrixGlobal, errorRates, mutMatrices,
+             cumulativeRate, cumulativeErrorRate) = inputs[0]
+            siteRates = G.get("siteRates") if G["useRateVariation"] else None
+            # the device side recomputes mutMatrices / cumulative tables from these; check that this is lossless
+            if mutMatrices is not None and G["useRateVariation"]:
+                for p in range(0, G["lRef"], 997):
+                    for i in range(4):
+                        for j in range(4):
+                            assert mutMatrices[p][i][j] == mutMatrixGlobal[i][j] * siteRates[p]
+            cr = [0.0]
+            refIdx = G["refIndeces"]
+            for i in range(G["lRef"]):
+                cr.append(cr[-1] + mutMatrixGlobal[refIdx[i]][refIdx[i]] * (siteRates[i] if siteRates else 1.0))
+            if siteRates:
+                assert cr == list(cumulativeRate), "cumulativeRate is not recomputable bit-exactly"
+            else:
+                cr2 = [0.0]
+                for i in range(G["lRef"]):
+                    cr2.append(cr2[-1] + mutMatrixGlobal[refIdx[i]][refIdx[i]])
+                assert cr2 == list(cumulativeRate), "cumulativeRate (no rate variation) is not recomputable"
+            if errorRates is not None and G["usingErrorRate"] and G["errorRateSiteSpecific"]:
+                ce = [0.0]
+                for i in range(G["lRef"]):
+                    ce.append(ce[-1] + errorRates[i])
+                assert ce == list(cumulativeErrorRate)
+            model = {"mutMatrixGlobal": [list(r) for r in mutMatrixGlobal], "errorRateGlobal": errorRateGlobal,
+                     "siteRates": list(siteRates) if siteRates else None,
+                     "errorRates": list(errorRates) if (errorRates is not None and G["errorRateSiteSpecific"]) else None,
+                     "totError": G.get("totError") if G["usingErrorRate"] else None}
+            params = {"strict": bool(strict), "fails": fails, "thr": thr, "thrPlace": thrPlace, "numCores": len(inputs)}
+            snap = snapshot_tree(tree, root, rec.table)
+            treeLK = G["calculateTreeLikelihood"](tree, root)
+            rec.install()
+            try:
+                results = [func(x) for x in inputs]
+            finally:
+                rec.uninstall()
+            self.first = {"env": env, "model": model, "params": params, "tree": snap, "treeLK": treeLK,
+                          "calls": rec.calls, "callCounts": rec.count, "searches": rec.searches,
+                          "proposed": [[list(m) for m in r] for r in results], "phase1Total": rec.phase1,
+                          "lists": [jsonable_list(c) for c in rec.table.lists]}
+            print("[golden] %s: harvested %d lists, %d searches, %d phase-1 candidates, counts %s" % (
+                self.name, len(rec.table.lists), len(rec.searches), rec.phase1, rec.count), file=sys.stderr)
+            return [list(r) for r in results]
+        return [func(x) for x in inputs]
+
+
+def run_config(name):
+    path, max_seqs, extra, cap = CONFIGS[name]
+    tmp_in = "/tmp/golden_%s_input.txt" % name
+    truncate_input(path, max_seqs, tmp_in)
+    out_prefix = "/tmp/golden_%s_out" % name
+    hv = Harvest(name, cap)
+
+    class FakePool:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def map(self, func, inputs):
+            return hv.pool_map(func, inputs)
+
+    real_pool = multiprocessing.Pool
+    multiprocessing.Pool = FakePool
+    argv = sys.argv
+    sys.argv = [REF, "--input", tmp_in, "--output", out_prefix, "--overwrite", "--numCores", "2"] + extra
+    crashed = None
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(REF, run_name="__main__")
+    except SystemExit:  # the reference ends with exit()
+        pass
+    except Exception as e:  # --model JC dies in the EM after round 1 (reference behaviour)
+        crashed = repr(e)
+    finally:
+        sys.argv = argv
+        multiprocessing.Pool = real_pool
+    assert hv.first is not None, "reference never reached the parallel SPR round: " + buf.getvalue()[-2000:]
+    finalLK = None
+    if crashed is None and os.path.isfile(out_prefix + "_LK.txt"):
+        with open(out_prefix + "_LK.txt") as f:
+            finalLK = float(f.read().split()[0])
+    fx = hv.first
+    fx["config"] = {"name": name, "input": os.path.basename(path), "max_seqs": max_seqs, "argv": extra,
+                    "reference": "MAPLEv0.7.5.4.py", "interpreter": "CPython %d.%d" % sys.version_info[:2],
+                    "crashedAfterHarvest": crashed}
+    fx["finalLK"] = finalLK
+    out = os.path.join(HERE, name + ".json.gz")
+    with gzip.open(out, "wt", compresslevel=9) as f:
+        json.dump(fx, f, separators=(",", ":"))
+    print("[golden] wrote %s (%.1f kB), treeLK=%r finalLK=%r crashed=%r" % (
+        out, os.path.getsize(out) / 1e3, fx["treeLK"], finalLK, crashed), file=sys.stderr)
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CONFIGS)
+    for n in names:
+        run_config(n)

@@ -1,0 +1,24 @@
+"""Load the committed golden fixtures (tests/golden/*.json.gz, written by make_golden.py)."""
+import functools
+import glob
+import gzip
+import json
+import os
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
+
+
+def _as_tuples(gl):
+    return [tuple(e) for e in gl]
+
+
+@functools.lru_cache(maxsize=None)
+def load_golden(name):
+    with gzip.open(os.path.join(GOLDEN_DIR, name + ".json.gz"), "rt") as f:
+        fx = json.load(f)
+    fx["lists"] = [_as_tuples(gl) for gl in fx["lists"]]
+    return fx

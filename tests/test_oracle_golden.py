@@ -1,0 +1,85 @@
+"""The CPU oracle (oracle/maple_oracle.c) against vectors recorded from the unmodified reference.
+
+Bit-exact for everything that involves no transcendental (merged lists, branch lengths, list
+comparisons, re-referencing); log-likelihood scalars within 1e-9 absolute (libm log vs CPython's
+math.log differ by at most an ulp of each term).
+"""
+import math
+
+import pytest
+
+from golden_io import golden_names, load_golden
+from maple_b200.genome_list import lists_equal
+from maple_b200.model import MapleModel
+from oracle.oracle import Oracle
+
+NAMES = golden_names()
+LK_TOL = 1e-9
+
+
+@pytest.fixture(scope="module", params=NAMES)
+def fx(request):
+    g = load_golden(request.param)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    return g, Oracle(model, with_root_tables=True)
+
+
+def test_append(fx):
+    g, orc = fx
+    L = g["lists"]
+    calls = g["calls"]["appendProbNode"]
+    assert calls
+    ninf = 0
+    for c in calls:
+        got = orc.append(L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"])
+        if c["out"] == float("-inf"):
+            assert got == float("-inf")
+            ninf += 1
+        else:
+            assert abs(got - c["out"]) <= LK_TOL, (c, got)
+
+
+def test_merge(fx):
+    g, orc = fx
+    L = g["lists"]
+    calls = g["calls"]["mergeVectors"]
+    assert calls
+    for c in calls:
+        got = orc.merge(L[c["v1"]], c["b1"], c["t1"], L[c["v2"]], c["b2"], c["t2"], returnLK=c["returnLK"],
+                        isUpDown=c["isUpDown"], numMinor1=c["numMinor1"], numMinor2=c["numMinor2"])
+        exp = None if c["out"] is None else L[c["out"]]
+        if c["returnLK"]:
+            got, lk = got
+            assert abs(lk - c["lk"]) <= LK_TOL
+        assert lists_equal(got, exp), (c, got, exp)
+
+
+def test_blen(fx):
+    g, orc = fx
+    L = g["lists"]
+    for c in g["calls"]["estimateBranchLengthWithDerivative"]:
+        got = orc.blen(L[c["P"]], L[c["C"]], c["fromTipC"])
+        assert got == c["out"], (c, got)
+
+
+def test_differ(fx):
+    g, orc = fx
+    L = g["lists"]
+    for c in g["calls"]["areVectorsDifferent"]:
+        v2 = None if c["v2"] is None else L[c["v2"]]
+        assert orc.differ(L[c["v1"]], v2) == c["out"]
+
+
+def test_pass_branch(fx):
+    g, orc = fx
+    L = g["lists"]
+    for c in g["calls"]["passGenomeListThroughBranch"]:
+        got = orc.pass_branch(L[c["v"]], c["mutations"], c["dirIsUp"])
+        assert lists_equal(got, L[c["out"]]), (c, got, L[c["out"]])
+
+
+def test_shorten(fx):
+    g, orc = fx
+    L = g["lists"]
+    for c in g["calls"]["shorten"]:
+        assert lists_equal(orc.shorten(L[c["v"]]), L[c["out"]])
