@@ -116,12 +116,15 @@ class Recorder:
         self.searches = []
         self.phase1 = 0
         self.orig = {}
+        self.nspecial = {}
 
     def keep(self, f, special):
         self.count[f] += 1
         n = self.count[f]
-        if special and len(self.calls[f]) < 3 * self.cap:
-            return True
+        if special:
+            self.nspecial[f] = self.nspecial.get(f, 0) + 1
+            if self.nspecial[f] <= self.cap // 4:
+                return True
         # dense at the start, then geometric thinning
         if len(self.calls[f]) >= self.cap:
             return False
@@ -310,6 +313,35 @@ class Harvest:
             params = {"strict": bool(strict), "fails": fails, "thr": thr, "thrPlace": thrPlace, "numCores": len(inputs)}
             snap = snapshot_tree(tree, root, rec.table)
             treeLK = G["calculateTreeLikelihood"](tree, root)
+            # explicit vectors for the functions the searches do not exercise: the per-node merges of
+            # calculateTreeLikelihood (returnLK=True, :9756), findProbRoot (:4865) and rootVector (:4916)
+            T = rec.table
+            nodes, stack = [], [root]
+            while stack:
+                nd = stack.pop()
+                nodes.append(nd)
+                stack.extend(tree.children[nd])
+            for nd in nodes:
+                ch = tree.children[nd]
+                if not ch or len(rec.calls["mergeVectors"]) >= 160:
+                    continue
+                if tree.mutations[ch[0]] or tree.mutations[ch[1]]:
+                    continue
+                tip = [len(tree.children[c]) == 0 and len(tree.minorSequences[c]) == 0 for c in ch]
+                nm = [len(tree.minorSequences[c]) for c in ch]
+                out, lk = G["mergeVectors"](tree.probVect[ch[0]], tree.dist[ch[0]], tip[0], tree.probVect[ch[1]],
+                                            tree.dist[ch[1]], tip[1], returnLK=True, numMinor1=nm[0], numMinor2=nm[1])
+                rec.calls["mergeVectors"].append({"v1": T.add(tree.probVect[ch[0]]), "b1": tree.dist[ch[0]], "t1": bool(tip[0]),
+                                                  "v2": T.add(tree.probVect[ch[1]]), "b2": tree.dist[ch[1]], "t2": bool(tip[1]),
+                                                  "returnLK": True, "isUpDown": False, "numMinor1": nm[0], "numMinor2": nm[1],
+                                                  "out": T.add(out), "lk": lk, "line": 9756})
+            for nd in nodes[:60]:
+                v = tree.probVect[nd]
+                rec.calls["findProbRoot"].append({"v": T.add(v), "out": G["findProbRoot"](v)})
+                tip = len(tree.children[nd]) == 0 and len(tree.minorSequences[nd]) == 0
+                for bl in (0.0, tree.dist[nd] if tree.dist[nd] else 1e-5):
+                    r = G["rootVector"](v, bl, tip, tree, root)
+                    rec.calls["rootVector"].append({"v": T.add(v), "bLen": bl, "isFromTip": bool(tip), "out": T.add(r)})
             rec.install()
             try:
                 results = [func(x) for x in inputs]

@@ -83,3 +83,49 @@ def test_shorten(fx):
     L = g["lists"]
     for c in g["calls"]["shorten"]:
         assert lists_equal(orc.shorten(L[c["v"]]), L[c["out"]])
+
+
+def test_root_vector(fx):
+    g, orc = fx
+    L = g["lists"]
+    calls = g["calls"]["rootVector"]
+    assert calls
+    for c in calls:
+        # the reference shortens the rootVector result before returning it (:4994)
+        got = orc.shorten(orc.root_vector(L[c["v"]], c["bLen"], c["isFromTip"]))
+        assert lists_equal(got, L[c["out"]]), (c, got, L[c["out"]])
+
+
+def test_prob_root(fx):
+    g, orc = fx
+    L = g["lists"]
+    calls = g["calls"]["findProbRoot"]
+    assert calls
+    for c in calls:
+        got = orc.prob_root(L[c["v"]])
+        assert abs(got - c["out"]) <= LK_TOL * max(1.0, abs(c["out"]) * 1e-4), (c, got)
+
+
+def test_tree_likelihood_from_parts(fx):
+    """calculateTreeLikelihood (:9721-9779) = sum of per-node merge LKs + findProbRoot(root list)."""
+    g, orc = fx
+    L = g["lists"]
+    t = g["tree"]
+
+    def lower(c):  # child list re-expressed relative to the parent's local reference (:9750-9755)
+        v = L[t["probVect"][c]]
+        return orc.pass_branch(v, t["mutations"][c], True) if t["mutations"][c] else v
+
+    total = 0.0
+    stack = [t["root"]]
+    while stack:
+        n = stack.pop()
+        ch = t["children"][n]
+        if ch:
+            stack.extend(ch)
+            tip = [len(t["children"][c]) == 0 and t["numMinor"][c] == 0 for c in ch]
+            out, lk = orc.merge(lower(ch[0]), t["dist"][ch[0]], tip[0], lower(ch[1]), t["dist"][ch[1]],
+                                tip[1], returnLK=True, numMinor1=t["numMinor"][ch[0]], numMinor2=t["numMinor"][ch[1]])
+            total += lk
+    total += orc.prob_root(lower(t["root"]))  # :9772-9775
+    assert abs(total - g["treeLK"]) <= 1e-6, (total, g["treeLK"])
