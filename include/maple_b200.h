@@ -1,0 +1,111 @@
+/*
+ * maple_b200.h -- C ABI of the B200-native SPR-likelihood kernels.
+ *
+ * The reference (NicolaDM/MAPLE, MAPLEv0.7.5.4.py) has no FFI; its seam for this path is the
+ * set of module-level Python functions it already ships across a process boundary
+ * (SURVEY.md section 8b).  Each entry point below names the reference function it replaces.
+ * A maintainer binds these with ctypes; device buffers are owned by the
+ * caller (e.g. torch.cuda tensors) and passed as raw pointers + lengths.
+ *
+ * Conventions: every function returns 0 on success or a negative MAPLE_E_* code and never
+ * throws; maple_last_error() gives a message for the last failure on that context.  A context
+ * is thread-compatible, not thread-safe.  `stream` is a cudaStream_t passed as void* (NULL =
+ * default stream); launches are asynchronous with respect to the host unless stated.
+ *
+ * Packed genome lists (maple_b200/genome_list.py; reference tuple spec MAPLEv0.7.5.4.py:378-390):
+ *   key stream  uint32 per entry: bits 0-2 type (0-3 ACGT, 4 R, 5 N, 6 O) | 3-4 nLens | 5 flag |
+ *               6-7 local-reference nucleotide | 8-31 end position (1-based, inclusive)
+ *   pay stream  float64: per entry nLens branch lengths, then the 4-vector of an O entry
+ *   list i      starts at key[key_start[i]], pay[pay_start[i]]; key_start[i] < 0 encodes None
+ */
+#ifndef MAPLE_B200_H
+#define MAPLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct maple_ctx maple_ctx;
+
+#define MAPLE_OK 0
+#define MAPLE_E_ARG (-1)    /* bad argument */
+#define MAPLE_E_CUDA (-2)   /* CUDA runtime error (message in maple_last_error) */
+#define MAPLE_E_STATE (-3)  /* model / lists not set */
+#define MAPLE_E_NOGPU (-4)  /* no usable CUDA device: there is no CPU fallback */
+
+/* model flags (module globals of the reference: usingErrorRate, errorRateSiteSpecific, useRateVariation) */
+#define MAPLE_F_USING_ERROR_RATE 1
+#define MAPLE_F_ERROR_SITE_SPECIFIC 2
+#define MAPLE_F_RATE_VARIATION 4
+
+/* merge flags (keyword arguments of mergeVectors) */
+#define MAPLE_MERGE_UPDOWN 1    /* isUpDown=True */
+#define MAPLE_MERGE_RETURN_LK 2 /* returnLK=True */
+
+int maple_version(void);
+const char* maple_last_error(const maple_ctx* ctx);
+
+/* Reference-derived constants (MAPLEv0.7.5.4.py:3606-3693): lRef, rootFreqs; flags = MAPLE_F_*.
+ * Fails with MAPLE_E_NOGPU when the device is not available. */
+int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double rootFreqs[4], int32_t flags);
+int maple_ctx_destroy(maple_ctx* ctx);
+
+/* The model arrays startTopologyUpdatesParallel receives in its input tuple (:9581):
+ * mutMatrixGlobal Q[16] row-major, siteRates[lRef] (mutMatrices[pos] = Q*siteRates[pos], :6367) or
+ * NULL, errorRateGlobal, errorRates[lRef] or NULL, cumulativeRate[lRef+1],
+ * cumulativeErrorRate[lRef+1] or NULL, totError (:6385/:6390).  HOST pointers; copied. */
+int maple_ctx_set_model(maple_ctx* ctx, const double Q[16], const double* siteRates, double errorRate,
+                        const double* errorRates, const double* cumulativeRate, const double* cumulativeErrorRate,
+                        double totError);
+
+/* thresholdProb (:51), thresholdDiffForUpdate (:61), thresholdFoldChangeUpdate (:62),
+ * minBLenSensitivity already multiplied by 1/lRef (:3618). */
+int maple_ctx_set_thresholds(maple_ctx* ctx, double thresholdProb, double thresholdDiffForUpdate,
+                             double thresholdFoldChangeUpdate, double minBLenSensitivity);
+
+/* Bind the arena the batch calls index into (DEVICE pointers, caller-owned, must outlive the calls). */
+int maple_lists_bind(maple_ctx* ctx, const uint32_t* key, const double* pay, const int64_t* key_start,
+                     const int64_t* pay_start, int64_t nLists);
+
+/* appendProbNode(probVectP, probVectC, isTipC, bLen) -> float (:6505) for n (P,C) pairs.
+ * DEVICE pointers.  out[i] = log-likelihood cost or -inf. */
+int maple_append_prob_batch(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32_t* cIdx, const uint8_t* isTipC,
+                            const double* bLen, double* out, void* stream);
+
+/* Same call with HOST buffers: copies the four argument arrays to the device, runs the kernel,
+ * copies the scores back and synchronises.  This is the end-to-end form of the call. */
+int maple_append_prob_batch_host(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32_t* cIdx,
+                                 const uint8_t* isTipC, const double* bLen, double* out);
+
+/* mergeVectors(probVect1,bLen1,fromTip1,probVect2,bLen2,fromTip2,returnLK,isUpDown,numMinor1,numMinor2)
+ * (:4446) for n pairs.  flags[i] = MAPLE_MERGE_*.  Result i is written at out_key[out_key_start[i]],
+ * out_pay[out_pay_start[i]] (caller sizes the slots: at most nkeys1+nkeys2 keys and 6x that many
+ * doubles); out_nkeys/out_npay receive the sizes, out_status 0 = list, 1 = None (:4758, :4812),
+ * 2 = likelihood underflow (the reference raises).  numMinor1/2, out_lk may be NULL unless
+ * MAPLE_MERGE_RETURN_LK is used.  shorten != 0 applies shorten() (:3721) to each result in place,
+ * as the reference's callers do before storing a list (:5542, :6201, :6267). */
+int maple_merge_batch(maple_ctx* ctx, int64_t n, const int32_t* idx1, const double* bLen1, const uint8_t* fromTip1,
+                      const int32_t* idx2, const double* bLen2, const uint8_t* fromTip2, const uint8_t* flags,
+                      const int32_t* numMinor1, const int32_t* numMinor2, uint32_t* out_key, double* out_pay,
+                      const int64_t* out_key_start, const int64_t* out_pay_start, int32_t* out_nkeys, int32_t* out_npay,
+                      double* out_lk, int32_t* out_status, int32_t shorten, void* stream);
+
+/* estimateBranchLengthWithDerivative(probVectP, probVectC, fromTipC) (:5040) for n pairs.
+ * scratch: device doubles, pair i may use scratch[scratch_start[i] ...] with room for
+ * nkeys(P)+nkeys(C) values.  out_status 0 = out[i] holds the length, 1 = python False. */
+int maple_blen_batch(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32_t* cIdx, const uint8_t* fromTipC,
+                     double* scratch, const int64_t* scratch_start, double* out, int32_t* out_status, void* stream);
+
+/* areVectorsDifferent(probVect1, probVect2) (:5419); a None second list counts as different. */
+int maple_vectors_differ_batch(maple_ctx* ctx, int64_t n, const int32_t* idx1, const int32_t* idx2, uint8_t* out,
+                               void* stream);
+
+/* Kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
+int64_t maple_launch_count(const maple_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAPLE_B200_H */

@@ -1,0 +1,35 @@
+"""In-tree build of the CUDA library (sm_100a only).  nvcc cross-compiles without a GPU."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libmaple_b200.so")
+SOURCES = ["maple_b200.cu"]
+HEADERS = ["glist.cuh", "likelihood.cuh", os.path.join("..", "..", "include", "maple_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # no FMA contraction: a*b+c rounds twice, like the CPython reference
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS if os.path.exists(os.path.join(CSRC, f)))
+
+
+def build_extension(force: bool = False, verbose: bool = False) -> str:
+    if force or _stale():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_extension(force=True, verbose=True))

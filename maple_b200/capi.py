@@ -1,0 +1,56 @@
+"""ctypes binding of include/maple_b200.h.  There is no CPU fallback: if the CUDA library is not
+built, or no GPU is present, the first call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmaple_b200.so")
+
+MAPLE_F_USING_ERROR_RATE, MAPLE_F_ERROR_SITE_SPECIFIC, MAPLE_F_RATE_VARIATION = 1, 2, 4
+MAPLE_MERGE_UPDOWN, MAPLE_MERGE_RETURN_LK = 1, 2
+
+_P, _I64, _I32, _D = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+
+SIGNATURES = {
+    "maple_version": (C.c_int, []),
+    "maple_last_error": (C.c_char_p, [_P]),
+    "maple_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int, _I32, C.POINTER(_D), _I32]),
+    "maple_ctx_destroy": (C.c_int, [_P]),
+    "maple_ctx_set_model": (C.c_int, [_P, C.POINTER(_D), _P, _D, _P, _P, _P, _D]),
+    "maple_ctx_set_thresholds": (C.c_int, [_P, _D, _D, _D, _D]),
+    "maple_lists_bind": (C.c_int, [_P, _P, _P, _P, _P, _I64]),
+    "maple_append_prob_batch": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P]),
+    "maple_append_prob_batch_host": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    "maple_merge_batch": (C.c_int, [_P, _I64] + [_P] * 17 + [_I32, _P]),
+    "maple_blen_batch": (C.c_int, [_P, _I64] + [_P] * 7 + [_P]),
+    "maple_vectors_differ_batch": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+    "maple_launch_count": (_I64, [_P]),
+}
+
+_lib = None
+
+
+class MapleError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise MapleError("CUDA library %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                             "maple_b200 has no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(ctx, rc, what):
+    if rc != 0:
+        msg = load().maple_last_error(ctx)
+        raise MapleError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))

@@ -1,0 +1,371 @@
+// Batch kernels + C ABI (include/maple_b200.h) for the SPR-likelihood hot path, sm_100a.
+//
+// Thread mapping: one thread per (list, list) pair, threads of a warp take consecutive pairs of
+// the batch (callers order batches so that neighbours share the child list and walk similar
+// parent lists).  The 4x4 rate matrix, root frequencies and scalars are staged in shared memory
+// once per CTA; per-site rate / error tables (239 kB each at lRef 29903) are read through the
+// read-only path at the few informative sites only and stay L2-resident.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/maple_b200.h"
+#include "likelihood.cuh"
+
+using namespace maple;
+
+struct maple_ctx {
+    int device = 0;
+    DevModel model{};
+    bool haveModel = false, haveLists = false;
+    double *dSiteRates = nullptr, *dErrorRates = nullptr, *dCumRate = nullptr, *dCumErr = nullptr;
+    const uint32_t* key = nullptr;
+    const double* pay = nullptr;
+    const int64_t *keyStart = nullptr, *payStart = nullptr;
+    int64_t nLists = 0;
+    int64_t launches = 0;
+    int numSMs = 148;
+    // staging for the host-buffer entry point
+    void* hostStage = nullptr;
+    size_t hostStageBytes = 0;
+    void* devStage = nullptr;
+    size_t devStageBytes = 0;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                \
+            return MAPLE_E_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+constexpr int kThreads = 128;
+
+struct Arena {
+    const uint32_t* key;
+    const double* pay;
+    const int64_t* keyStart;
+    const int64_t* payStart;
+};
+
+__device__ __forceinline__ void stage_model(DevModel& sm, const DevModel& gm) {
+    // 32-bit words of the parameter struct -> shared memory
+    const int nWords = sizeof(DevModel) / 4;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&gm);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm);
+    for (int i = threadIdx.x; i < nWords; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads) k_append(const __grid_constant__ DevModel gm, Arena A, int64_t n, const int32_t* __restrict__ pIdx,
+                                                     const int32_t* __restrict__ cIdx, const uint8_t* __restrict__ isTip,
+                                                     const double* __restrict__ bLen, double* __restrict__ out) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = pIdx[i], c = cIdx[i];
+        const int64_t kp = __ldg(A.keyStart + p), kc = __ldg(A.keyStart + c);
+        out[i] = dev_append<true>(sm, A.key + kp, A.pay + __ldg(A.payStart + p), A.key + kc, A.pay + __ldg(A.payStart + c),
+                                  isTip[i] != 0, bLen[i]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_merge(const __grid_constant__ DevModel gm, Arena A, int64_t n, const int32_t* __restrict__ idx1,
+                                                    const double* __restrict__ bLen1, const uint8_t* __restrict__ tip1,
+                                                    const int32_t* __restrict__ idx2, const double* __restrict__ bLen2,
+                                                    const uint8_t* __restrict__ tip2, const uint8_t* __restrict__ flags,
+                                                    const int32_t* __restrict__ nm1, const int32_t* __restrict__ nm2, uint32_t* outKey,
+                                                    double* outPay, const int64_t* __restrict__ outKeyStart,
+                                                    const int64_t* __restrict__ outPayStart, int32_t* __restrict__ outNk,
+                                                    int32_t* __restrict__ outNp, double* __restrict__ outLk, int32_t* __restrict__ outStatus,
+                                                    int doShorten) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = idx1[i], b = idx2[i];
+        Writer w;
+        w.init(outKey + outKeyStart[i], outPay + outPayStart[i]);
+        double lk = 0.0;
+        int st = dev_merge<true>(sm, A.key + __ldg(A.keyStart + a), A.pay + __ldg(A.payStart + a), bLen1[i], tip1[i] != 0,
+                                 A.key + __ldg(A.keyStart + b), A.pay + __ldg(A.payStart + b), bLen2[i], tip2[i] != 0, flags[i],
+                                 nm1 ? nm1[i] : 0, nm2 ? nm2[i] : 0, w, &lk);
+        if (st == 0 && doShorten) {
+            Writer w2;
+            w2.init(w.key, w.pay);
+            dev_shorten<false>(sm, w.key, w.pay, w2);  // in place: the writer never overtakes the reader
+            w = w2;
+        }
+        outNk[i] = st == 0 ? w.nk : 0;
+        outNp[i] = st == 0 ? w.np : 0;
+        outStatus[i] = st;
+        if (outLk) outLk[i] = lk;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_blen(const __grid_constant__ DevModel gm, Arena A, int64_t n, const int32_t* __restrict__ pIdx,
+                                                   const int32_t* __restrict__ cIdx, const uint8_t* __restrict__ fromTip, double* scratch,
+                                                   const int64_t* __restrict__ scratchStart, double* __restrict__ out,
+                                                   int32_t* __restrict__ outStatus) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = pIdx[i], c = cIdx[i];
+        double v = 0.0;
+        outStatus[i] = dev_blen<true>(sm, A.key + __ldg(A.keyStart + p), A.pay + __ldg(A.payStart + p), A.key + __ldg(A.keyStart + c),
+                                      A.pay + __ldg(A.payStart + c), fromTip[i] != 0, scratch + scratchStart[i], &v);
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_differ(const __grid_constant__ DevModel gm, Arena A, int64_t n, const int32_t* __restrict__ idx1,
+                                                     const int32_t* __restrict__ idx2, uint8_t* __restrict__ out) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = idx1[i], b = idx2[i];
+        const int64_t kb = __ldg(A.keyStart + b);
+        out[i] = dev_differ<true>(sm, A.key + __ldg(A.keyStart + a), A.pay + __ldg(A.payStart + a), kb < 0 ? nullptr : A.key + kb,
+                                  kb < 0 ? nullptr : A.pay + __ldg(A.payStart + b))
+                     ? 1
+                     : 0;
+    }
+}
+
+// grid: whole waves of CTAs (multiples of the SM count), capped by the work
+static int grid_for(const maple_ctx* ctx, int64_t n, int ctasPerSM) {
+    int64_t need = (n + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)ctx->numSMs * ctasPerSM;
+    if (need >= cap) return (int)cap;
+    return (int)(need < 1 ? 1 : need);
+}
+
+extern "C" {
+
+int maple_version(void) { return 100; }
+
+const char* maple_last_error(const maple_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double rootFreqs[4], int32_t flags) {
+    if (!out || !rootFreqs || lRef <= 0 || lRef >= (1 << 24)) {
+        g_err = "maple_ctx_create: bad argument (lRef must be in 1..2^24-1)";
+        return MAPLE_E_ARG;
+    }
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev <= device) {
+        g_err = std::string("maple_ctx_create: no usable CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return MAPLE_E_NOGPU;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_err = "maple_ctx_create: cudaSetDevice failed";
+        return MAPLE_E_NOGPU;
+    }
+    maple_ctx* ctx = new maple_ctx();
+    ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
+    memset(&ctx->model, 0, sizeof(DevModel));
+    ctx->model.lRef = lRef;
+    ctx->model.U = (flags & MAPLE_F_USING_ERROR_RATE) ? 1 : 0;
+    ctx->model.errSS = (flags & MAPLE_F_ERROR_SITE_SPECIFIC) ? 1 : 0;
+    ctx->model.rateVar = (flags & MAPLE_F_RATE_VARIATION) ? 1 : 0;
+    for (int i = 0; i < 4; i++) ctx->model.pi[i] = rootFreqs[i];
+    ctx->model.thresholdProb = 1e-8;
+    ctx->model.thresholdDiffForUpdate = 1e-5;
+    ctx->model.thresholdFoldChangeUpdate = 1.01;
+    ctx->model.minBLenSensitivity = 0.001 / lRef;
+    *out = ctx;
+    return MAPLE_OK;
+}
+
+int maple_ctx_destroy(maple_ctx* ctx) {
+    if (!ctx) return MAPLE_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->dSiteRates);
+    cudaFree(ctx->dErrorRates);
+    cudaFree(ctx->dCumRate);
+    cudaFree(ctx->dCumErr);
+    cudaFree(ctx->devStage);
+    if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
+    delete ctx;
+    return MAPLE_OK;
+}
+
+static int upload(maple_ctx* ctx, double** dst, const double* src, size_t n) {
+    if (!*dst) CK(cudaMalloc((void**)dst, n * sizeof(double)));
+    CK(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_model(maple_ctx* ctx, const double Q[16], const double* siteRates, double errorRate, const double* errorRates,
+                        const double* cumulativeRate, const double* cumulativeErrorRate, double totError) {
+    if (!ctx || !Q || !cumulativeRate) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevModel& m = ctx->model;
+    if (m.rateVar && !siteRates) { ctx->err = "set_model: rate variation needs siteRates"; return MAPLE_E_ARG; }
+    if (m.U && m.errSS && (!errorRates || !cumulativeErrorRate)) { ctx->err = "set_model: site-specific errors need errorRates and cumulativeErrorRate"; return MAPLE_E_ARG; }
+    for (int i = 0; i < 16; i++) m.Q[i] = Q[i];
+    m.errorRate = errorRate;
+    m.totError = totError;
+    int rc;
+    const size_t L = (size_t)m.lRef;
+    if (m.rateVar) { if ((rc = upload(ctx, &ctx->dSiteRates, siteRates, L))) return rc; }
+    if (m.U && m.errSS) {
+        if ((rc = upload(ctx, &ctx->dErrorRates, errorRates, L))) return rc;
+        if ((rc = upload(ctx, &ctx->dCumErr, cumulativeErrorRate, L + 1))) return rc;
+    }
+    if ((rc = upload(ctx, &ctx->dCumRate, cumulativeRate, L + 1))) return rc;
+    m.siteRates = ctx->dSiteRates;
+    m.errorRates = ctx->dErrorRates;
+    m.cumRate = ctx->dCumRate;
+    m.cumErr = ctx->dCumErr;
+    ctx->haveModel = true;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_thresholds(maple_ctx* ctx, double thresholdProb, double thresholdDiffForUpdate, double thresholdFoldChangeUpdate,
+                             double minBLenSensitivity) {
+    if (!ctx) return MAPLE_E_ARG;
+    ctx->model.thresholdProb = thresholdProb;
+    ctx->model.thresholdDiffForUpdate = thresholdDiffForUpdate;
+    ctx->model.thresholdFoldChangeUpdate = thresholdFoldChangeUpdate;
+    ctx->model.minBLenSensitivity = minBLenSensitivity;
+    return MAPLE_OK;
+}
+
+int maple_lists_bind(maple_ctx* ctx, const uint32_t* key, const double* pay, const int64_t* key_start, const int64_t* pay_start,
+                     int64_t nLists) {
+    if (!ctx || !key || !pay || !key_start || !pay_start || nLists <= 0) return MAPLE_E_ARG;
+    ctx->key = key;
+    ctx->pay = pay;
+    ctx->keyStart = key_start;
+    ctx->payStart = pay_start;
+    ctx->nLists = nLists;
+    ctx->haveLists = true;
+    return MAPLE_OK;
+}
+
+static int ready(maple_ctx* ctx) {
+    if (!ctx) return MAPLE_E_ARG;
+    if (!ctx->haveModel || !ctx->haveLists) {
+        ctx->err = "model or lists not set (maple_ctx_set_model / maple_lists_bind)";
+        return MAPLE_E_STATE;
+    }
+    return MAPLE_OK;
+}
+
+int maple_append_prob_batch(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32_t* cIdx, const uint8_t* isTipC,
+                            const double* bLen, double* out, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !pIdx || !cIdx || !isTipC || !bLen || !out) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_append<<<grid_for(ctx, n, 16), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, pIdx, cIdx, isTipC, bLen, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+static int ensure_stage(maple_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->hostStageBytes) {
+        if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
+        ctx->hostStage = nullptr;
+        CK(cudaMallocHost(&ctx->hostStage, bytes));
+        ctx->hostStageBytes = bytes;
+    }
+    if (bytes > ctx->devStageBytes) {
+        cudaFree(ctx->devStage);
+        ctx->devStage = nullptr;
+        CK(cudaMalloc(&ctx->devStage, bytes));
+        ctx->devStageBytes = bytes;
+    }
+    return MAPLE_OK;
+}
+
+int maple_append_prob_batch_host(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32_t* cIdx, const uint8_t* isTipC,
+                                 const double* bLen, double* out) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !pIdx || !cIdx || !isTipC || !bLen || !out) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // layout of one staging block: bLen[n] f64 | out[n] f64 | pIdx[n] i32 | cIdx[n] i32 | isTip[n] u8
+    const size_t N = (size_t)n;
+    const size_t oB = 0, oO = oB + 8 * N, oP = oO + 8 * N, oC = oP + 4 * N, oT = oC + 4 * N, total = oT + ((N + 15) / 16) * 16;
+    if ((rc = ensure_stage(ctx, total))) return rc;
+    char* h = (char*)ctx->hostStage;
+    char* d = (char*)ctx->devStage;
+    memcpy(h + oB, bLen, 8 * N);
+    memcpy(h + oP, pIdx, 4 * N);
+    memcpy(h + oC, cIdx, 4 * N);
+    memcpy(h + oT, isTipC, N);
+    cudaStream_t s = 0;
+    CK(cudaMemcpyAsync(d + oB, h + oB, 8 * N, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + oP, h + oP, total - oP, cudaMemcpyHostToDevice, s));
+    rc = maple_append_prob_batch(ctx, n, (const int32_t*)(d + oP), (const int32_t*)(d + oC), (const uint8_t*)(d + oT),
+                                 (const double*)(d + oB), (double*)(d + oO), s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h + oO, d + oO, 8 * N, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(out, h + oO, 8 * N);
+    return MAPLE_OK;
+}
+
+int maple_merge_batch(maple_ctx* ctx, int64_t n, const int32_t* idx1, const double* bLen1, const uint8_t* fromTip1, const int32_t* idx2,
+                      const double* bLen2, const uint8_t* fromTip2, const uint8_t* flags, const int32_t* numMinor1,
+                      const int32_t* numMinor2, uint32_t* out_key, double* out_pay, const int64_t* out_key_start,
+                      const int64_t* out_pay_start, int32_t* out_nkeys, int32_t* out_npay, double* out_lk, int32_t* out_status,
+                      int32_t shorten, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !idx1 || !bLen1 || !fromTip1 || !idx2 || !bLen2 || !fromTip2 || !flags || !out_key || !out_pay || !out_key_start ||
+        !out_pay_start || !out_nkeys || !out_npay || !out_status)
+        return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_merge<<<grid_for(ctx, n, 8), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, idx1, bLen1, fromTip1, idx2, bLen2, fromTip2, flags,
+                                                                       numMinor1, numMinor2, out_key, out_pay, out_key_start,
+                                                                       out_pay_start, out_nkeys, out_npay, out_lk, out_status, shorten);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_blen_batch(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32_t* cIdx, const uint8_t* fromTipC, double* scratch,
+                     const int64_t* scratch_start, double* out, int32_t* out_status, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !pIdx || !cIdx || !fromTipC || !scratch || !scratch_start || !out || !out_status) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_blen<<<grid_for(ctx, n, 8), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, pIdx, cIdx, fromTipC, scratch, scratch_start, out,
+                                                                      out_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_vectors_differ_batch(maple_ctx* ctx, int64_t n, const int32_t* idx1, const int32_t* idx2, uint8_t* out, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !idx1 || !idx2 || !out) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_differ<<<grid_for(ctx, n, 16), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, idx1, idx2, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int64_t maple_launch_count(const maple_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
