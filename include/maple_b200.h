@@ -102,6 +102,21 @@ int maple_blen_batch(maple_ctx* ctx, int64_t n, const int32_t* pIdx, const int32
 int maple_vectors_differ_batch(maple_ctx* ctx, int64_t n, const int32_t* idx1, const int32_t* idx2, uint8_t* out,
                                void* stream);
 
+/* rootVector(probVect, bLen, isFromTip, ...) (:4916) for lists that are expressed relative to the
+ * reference genome (no MAT mutations between the node and the root).  Output slots as in
+ * maple_merge_batch (at most nkeys keys, 6x doubles); shorten != 0 applies shorten() as :4994 does. */
+int maple_root_vector_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, const double* bLen, const uint8_t* isFromTip,
+                            uint32_t* out_key, double* out_pay, const int64_t* out_key_start, const int64_t* out_pay_start,
+                            int32_t* out_nkeys, int32_t* out_npay, int32_t shorten, void* stream);
+
+/* Gather-copy n whole lists between arenas (DEVICE pointers): list i goes from
+ * src_key[src_key_start[i]] / src_pay[src_pay_start[i]] (nkeys[i] keys, npay[i] doubles) to the dst
+ * offsets.  Used to append batch results to the resident tree arena (what the reference does by
+ * assigning tree.probVect[node] = newList, e.g. :6200, :6275, :6309). */
+int maple_lists_copy(maple_ctx* ctx, int64_t n, const uint32_t* src_key, const double* src_pay, const int64_t* src_key_start,
+                     const int64_t* src_pay_start, const int32_t* nkeys, const int32_t* npay, uint32_t* dst_key, double* dst_pay,
+                     const int64_t* dst_key_start, const int64_t* dst_pay_start, void* stream);
+
 /* Kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 int64_t maple_launch_count(const maple_ctx* ctx);
 

@@ -26,6 +26,8 @@ SIGNATURES = {
     "maple_merge_batch": (C.c_int, [_P, _I64] + [_P] * 17 + [_I32, _P]),
     "maple_blen_batch": (C.c_int, [_P, _I64] + [_P] * 7 + [_P]),
     "maple_vectors_differ_batch": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+    "maple_root_vector_batch": (C.c_int, [_P, _I64] + [_P] * 9 + [_I32, _P]),
+    "maple_lists_copy": (C.c_int, [_P, _I64] + [_P] * 10 + [_P]),
     "maple_launch_count": (_I64, [_P]),
 }
 

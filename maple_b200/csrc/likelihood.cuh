@@ -765,4 +765,50 @@ __device__ bool dev_differ(const DevModel& m, const uint32_t* k1, const double* 
     return false;
 }
 
+// ------------------------------------------------------------------------------------------------
+// rootVector (:4916-4996) for a list already expressed relative to the reference genome (the
+// MAT re-referencing around it, :4928-4940 and :4990-4993, is done by the caller); not shortened.
+template <bool LD>
+__device__ void dev_root_vector(const DevModel& m, const uint32_t* k, const double* p, double bLen, bool isFromTip, Writer& o) {
+    const int lRef = m.lRef;
+    const bool U = m.U != 0;
+    Cursor<LD> c;
+    c.init(k, p);
+    int pos = 0;
+    for (;;) {
+        if (c.type == T_N) o.put0(T_N, 0, c.end);
+        else if (c.type == T_O) {
+            double a[4], nv[4];
+            c.vec(a);
+            double totB = bLen;
+            if (c.nl == 1) totB += c.l0();
+            if (totB != 0.0) {
+                const SiteQ q(m, pos);
+                gv_vec(q, totB, a, false, nv);
+#pragma unroll
+                for (int i = 0; i < 4; i++) nv[i] *= m.pi[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) nv[i] = a[i] * m.pi[i];
+            }
+            const double s = py_sum4(nv);
+#pragma unroll
+            for (int i = 0; i < 4; i++) nv[i] /= s;
+            o.put(T_O, 0, 0, c.nuc, c.end, 0.0, 0.0, nv);
+        } else if (U) {
+            const bool flag1 = (c.nl > 0 && c.flag) || isFromTip;
+            if (c.nl >= 1) o.put(c.type, 2, flag1, c.nuc, c.end, c.l0() + bLen, 0.0, nullptr);
+            else if (bLen != 0.0 || flag1) o.put(c.type, 2, flag1, c.nuc, c.end, bLen, 0.0, nullptr);
+            else o.put0(c.type, c.nuc, c.end);
+        } else {
+            if (c.nl == 1) o.put(c.type, 2, 0, c.nuc, c.end, c.l0() + bLen, 0.0, nullptr);
+            else if (bLen != 0.0) o.put(c.type, 2, 0, c.nuc, c.end, bLen, 0.0, nullptr);
+            else o.put0(c.type, c.nuc, c.end);
+        }
+        pos = c.end;
+        if (pos == lRef) break;
+        c.next();
+    }
+}
+
 }  // namespace maple

@@ -25,9 +25,7 @@ struct maple_ctx {
     int64_t nLists = 0;
     int64_t launches = 0;
     int numSMs = 148;
-    // staging for the host-buffer entry point
-    void* hostStage = nullptr;
-    size_t hostStageBytes = 0;
+    // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
     std::string err;
@@ -136,6 +134,51 @@ __global__ void __launch_bounds__(kThreads) k_differ(const __grid_constant__ Dev
     }
 }
 
+__global__ void __launch_bounds__(kThreads) k_root_vector(const __grid_constant__ DevModel gm, Arena A, int64_t n, const int32_t* __restrict__ idx,
+                                                          const double* __restrict__ bLen, const uint8_t* __restrict__ fromTip, uint32_t* outKey,
+                                                          double* outPay, const int64_t* __restrict__ outKeyStart,
+                                                          const int64_t* __restrict__ outPayStart, int32_t* __restrict__ outNk,
+                                                          int32_t* __restrict__ outNp, int doShorten) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = idx[i];
+        Writer w;
+        w.init(outKey + outKeyStart[i], outPay + outPayStart[i]);
+        dev_root_vector<true>(sm, A.key + __ldg(A.keyStart + a), A.pay + __ldg(A.payStart + a), bLen[i], fromTip[i] != 0, w);
+        if (doShorten) {
+            Writer w2;
+            w2.init(w.key, w.pay);
+            dev_shorten<false>(sm, w.key, w.pay, w2);
+            w = w2;
+        }
+        outNk[i] = w.nk;
+        outNp[i] = w.np;
+    }
+}
+
+// gather-copy of whole lists between arenas: one warp per list, coalesced
+__global__ void __launch_bounds__(256) k_lists_copy(int64_t n, const uint32_t* __restrict__ srcKey, const double* __restrict__ srcPay,
+                                                    const int64_t* __restrict__ srcKeyStart, const int64_t* __restrict__ srcPayStart,
+                                                    const int32_t* __restrict__ nk, const int32_t* __restrict__ np, uint32_t* __restrict__ dstKey,
+                                                    double* __restrict__ dstPay, const int64_t* __restrict__ dstKeyStart,
+                                                    const int64_t* __restrict__ dstPayStart) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nWarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nWarps) {
+        const int64_t sk = srcKeyStart[i], dk = dstKeyStart[i];
+        if (sk < 0 || dk < 0) continue;
+        const int k = nk[i], p = np[i];
+        const uint32_t* s1 = srcKey + sk;
+        uint32_t* d1 = dstKey + dk;
+        for (int j = lane; j < k; j += 32) d1[j] = s1[j];
+        const double* s2 = srcPay + srcPayStart[i];
+        double* d2 = dstPay + dstPayStart[i];
+        for (int j = lane; j < p; j += 32) d2[j] = s2[j];
+    }
+}
+
 // grid: whole waves of CTAs (multiples of the SM count), capped by the work
 static int grid_for(const maple_ctx* ctx, int64_t n, int ctasPerSM) {
     int64_t need = (n + kThreads - 1) / kThreads;
@@ -190,7 +233,6 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->dCumRate);
     cudaFree(ctx->dCumErr);
     cudaFree(ctx->devStage);
-    if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
     delete ctx;
     return MAPLE_OK;
 }
@@ -273,17 +315,12 @@ int maple_append_prob_batch(maple_ctx* ctx, int64_t n, const int32_t* pIdx, cons
 }
 
 static int ensure_stage(maple_ctx* ctx, size_t bytes) {
-    if (bytes > ctx->hostStageBytes) {
-        if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
-        ctx->hostStage = nullptr;
-        CK(cudaMallocHost(&ctx->hostStage, bytes));
-        ctx->hostStageBytes = bytes;
-    }
     if (bytes > ctx->devStageBytes) {
         cudaFree(ctx->devStage);
         ctx->devStage = nullptr;
-        CK(cudaMalloc(&ctx->devStage, bytes));
-        ctx->devStageBytes = bytes;
+        ctx->devStageBytes = 0;
+        CK(cudaMalloc(&ctx->devStage, bytes + bytes / 4));
+        ctx->devStageBytes = bytes + bytes / 4;
     }
     return MAPLE_OK;
 }
@@ -295,25 +332,22 @@ int maple_append_prob_batch_host(maple_ctx* ctx, int64_t n, const int32_t* pIdx,
     if (n == 0) return MAPLE_OK;
     if (n < 0 || !pIdx || !cIdx || !isTipC || !bLen || !out) return MAPLE_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    // layout of one staging block: bLen[n] f64 | out[n] f64 | pIdx[n] i32 | cIdx[n] i32 | isTip[n] u8
+    // device staging block: bLen[n] f64 | out[n] f64 | pIdx[n] i32 | cIdx[n] i32 | isTip[n] u8.  The copies go
+    // straight from / to the caller's buffers (DMA when they are page-locked, driver-staged otherwise).
     const size_t N = (size_t)n;
     const size_t oB = 0, oO = oB + 8 * N, oP = oO + 8 * N, oC = oP + 4 * N, oT = oC + 4 * N, total = oT + ((N + 15) / 16) * 16;
     if ((rc = ensure_stage(ctx, total))) return rc;
-    char* h = (char*)ctx->hostStage;
     char* d = (char*)ctx->devStage;
-    memcpy(h + oB, bLen, 8 * N);
-    memcpy(h + oP, pIdx, 4 * N);
-    memcpy(h + oC, cIdx, 4 * N);
-    memcpy(h + oT, isTipC, N);
     cudaStream_t s = 0;
-    CK(cudaMemcpyAsync(d + oB, h + oB, 8 * N, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d + oP, h + oP, total - oP, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + oB, bLen, 8 * N, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + oP, pIdx, 4 * N, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + oC, cIdx, 4 * N, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d + oT, isTipC, N, cudaMemcpyHostToDevice, s));
     rc = maple_append_prob_batch(ctx, n, (const int32_t*)(d + oP), (const int32_t*)(d + oC), (const uint8_t*)(d + oT),
                                  (const double*)(d + oB), (double*)(d + oO), s);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h + oO, d + oO, 8 * N, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out, d + oO, 8 * N, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    memcpy(out, h + oO, 8 * N);
     return MAPLE_OK;
 }
 
@@ -361,6 +395,42 @@ int maple_vectors_differ_batch(maple_ctx* ctx, int64_t n, const int32_t* idx1, c
     CK(cudaSetDevice(ctx->device));
     Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
     k_differ<<<grid_for(ctx, n, 16), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, idx1, idx2, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_root_vector_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, const double* bLen, const uint8_t* isFromTip, uint32_t* out_key,
+                            double* out_pay, const int64_t* out_key_start, const int64_t* out_pay_start, int32_t* out_nkeys,
+                            int32_t* out_npay, int32_t shorten, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !idx || !bLen || !isFromTip || !out_key || !out_pay || !out_key_start || !out_pay_start || !out_nkeys || !out_npay)
+        return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_root_vector<<<grid_for(ctx, n, 8), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, idx, bLen, isFromTip, out_key, out_pay,
+                                                                             out_key_start, out_pay_start, out_nkeys, out_npay, shorten);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_lists_copy(maple_ctx* ctx, int64_t n, const uint32_t* src_key, const double* src_pay, const int64_t* src_key_start,
+                     const int64_t* src_pay_start, const int32_t* nkeys, const int32_t* npay, uint32_t* dst_key, double* dst_pay,
+                     const int64_t* dst_key_start, const int64_t* dst_pay_start, void* stream) {
+    if (!ctx) return MAPLE_E_ARG;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !src_key || !src_pay || !src_key_start || !src_pay_start || !nkeys || !npay || !dst_key || !dst_pay || !dst_key_start ||
+        !dst_pay_start)
+        return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int64_t blocks = (n * 32 + 255) / 256;
+    int64_t cap = (int64_t)ctx->numSMs * 8;
+    k_lists_copy<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(n, src_key, src_pay, src_key_start, src_pay_start,
+                                                                                      nkeys, npay, dst_key, dst_pay, dst_key_start,
+                                                                                      dst_pay_start);
     ctx->launches++;
     CK(cudaGetLastError());
     return MAPLE_OK;

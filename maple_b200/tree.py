@@ -1,0 +1,230 @@
+"""Device-resident mirror of the reference's Tree (MAPLEv0.7.5.4.py:331-376) and of
+reCalculateAllGenomeLists (:6013-6347) as level-synchronous batches of the merge kernel.
+
+Host side keeps the reference's struct-of-arrays (node = int index): up, children, dist, plus
+isTip = "no children and no minor sequences" (the flag every likelihood call takes) and numMinor.
+The four genome-list families live in ONE arena in HBM; list id = family * nNodes + node with
+family 0 = probVect (lower), 1 = probVectUpRight, 2 = probVectUpLeft, 3 = probVectTotUp.
+
+This module does not handle MAT local references (mutations[node] lists, :3749): trees built here
+express every list relative to the reference genome (the reference's --noLocalRef behaviour).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import capi
+from .engine import MapleEngine, MergeResult, _dp
+from .genome_list import PackedLists, pack_lists, decode_stream
+
+FAM_LOWER, FAM_UPRIGHT, FAM_UPLEFT, FAM_TOTUP = 0, 1, 2, 3
+
+
+class ListArena:
+    """Growable arena of packed lists in HBM, addressed by list id."""
+
+    def __init__(self, engine: MapleEngine, nLists: int, key_capacity: int, pay_capacity: int):
+        self.eng = engine
+        dev = engine.device
+        self.n = nLists
+        self.key = torch.zeros(max(key_capacity, 16), dtype=torch.int32, device=dev)
+        self.pay = torch.zeros(max(pay_capacity, 16), dtype=torch.float64, device=dev)
+        self.key_start = torch.full((nLists,), -1, dtype=torch.int64, device=dev)
+        self.pay_start = torch.full((nLists,), -1, dtype=torch.int64, device=dev)
+        self.nkeys = torch.zeros(nLists, dtype=torch.int32, device=dev)
+        self.npay = torch.zeros(nLists, dtype=torch.int32, device=dev)
+        self.key_tail = 0
+        self.pay_tail = 0
+        self.lRef, self.U = engine.model.lRef, int(engine.model.usingErrorRate)
+        self._bind()
+
+    def _bind(self):
+        self.eng.lists = self
+        rc = self.eng.lib.maple_lists_bind(self.eng.ctx, _dp(self.key), _dp(self.pay), _dp(self.key_start), _dp(self.pay_start), self.n)
+        capi.check(self.eng.ctx, rc, "maple_lists_bind")
+
+    def _reserve(self, nk: int, npay: int):
+        grew = False
+        if self.key_tail + nk + 8 > self.key.numel():
+            new = torch.zeros(int((self.key_tail + nk) * 1.5) + 1024, dtype=torch.int32, device=self.key.device)
+            new[: self.key_tail] = self.key[: self.key_tail]
+            self.key, grew = new, True
+        if self.pay_tail + npay + 8 > self.pay.numel():
+            new = torch.zeros(int((self.pay_tail + npay) * 1.5) + 1024, dtype=torch.float64, device=self.pay.device)
+            new[: self.pay_tail] = self.pay[: self.pay_tail]
+            self.pay, grew = new, True
+        if grew:
+            self._bind()
+
+    def store(self, list_ids: torch.Tensor, src_key, src_pay, src_key_start, src_pay_start, nkeys, npay, status=None):
+        """Append the given source lists to the arena and point list_ids at them (status != 0 -> None)."""
+        ok = torch.ones_like(nkeys, dtype=torch.bool) if status is None else (status == 0)
+        nk = torch.where(ok, nkeys, torch.zeros_like(nkeys)).long()
+        npy = torch.where(ok, npay, torch.zeros_like(npay)).long()
+        k_al = (nk + 3) // 4 * 4
+        p_al = (npy + 1) // 2 * 2
+        tot_k, tot_p = int(k_al.sum().item()), int(p_al.sum().item())
+        self._reserve(tot_k, tot_p)
+        dks = self.key_tail + torch.cumsum(k_al, 0) - k_al
+        dps = self.pay_tail + torch.cumsum(p_al, 0) - p_al
+        dks = torch.where(ok, dks, torch.full_like(dks, -1))
+        n = list_ids.numel()
+        rc = self.eng.lib.maple_lists_copy(self.eng.ctx, n, _dp(src_key), _dp(src_pay), _dp(src_key_start), _dp(src_pay_start),
+                                           _dp(nk.int()), _dp(npy.int()), _dp(self.key), _dp(self.pay), _dp(dks), _dp(dps),
+                                           self.eng._stream())
+        capi.check(self.eng.ctx, rc, "maple_lists_copy")
+        self.key_start[list_ids] = dks
+        self.pay_start[list_ids] = torch.where(ok, dps, torch.full_like(dps, -1))
+        self.nkeys[list_ids] = nk.int()
+        self.npay[list_ids] = npy.int()
+        self.key_tail += tot_k
+        self.pay_tail += tot_p
+
+    def store_packed(self, list_ids, packed: PackedLists):
+        dev = self.key.device
+        self.store(torch.as_tensor(list_ids, dtype=torch.int64, device=dev),
+                   torch.from_numpy(packed.key.view(np.int32)).to(dev), torch.from_numpy(packed.pay).to(dev),
+                   torch.from_numpy(packed.key_start).to(dev), torch.from_numpy(packed.pay_start).to(dev),
+                   torch.from_numpy(packed.nkeys).to(dev), torch.from_numpy(packed.npay).to(dev),
+                   torch.from_numpy((packed.key_start < 0).astype(np.int32)).to(dev))
+
+    def get(self, list_id: int):
+        ks = int(self.key_start[list_id].item())
+        if ks < 0:
+            return None
+        nk, npay = int(self.nkeys[list_id].item()), int(self.npay[list_id].item())
+        ps = int(self.pay_start[list_id].item())
+        key = self.key[ks: ks + nk].cpu().numpy().view(np.uint32)
+        pay = self.pay[ps: ps + npay + 1].cpu().numpy()
+        return decode_stream(key, pay, 0, 0, self.lRef, self.U, nk)
+
+    def to_host(self) -> PackedLists:
+        return PackedLists(self.key[: max(self.key_tail, 4)].cpu().numpy().view(np.uint32), self.pay[: max(self.pay_tail, 2)].cpu().numpy(),
+                           self.key_start.cpu().numpy(), self.pay_start.cpu().numpy(), self.nkeys.cpu().numpy(),
+                           self.npay.cpu().numpy(), self.lRef, self.U)
+
+    def used_bytes(self) -> int:
+        return self.key_tail * 4 + self.pay_tail * 8 + self.n * (8 + 8 + 4 + 4)
+
+
+class DeviceTree:
+    def __init__(self, engine: MapleEngine, up, child0, child1, dist, root: int, isTip=None, numMinor=None):
+        self.eng = engine
+        self.n = len(up)
+        self.up = np.ascontiguousarray(up, np.int32)
+        self.child0 = np.ascontiguousarray(child0, np.int32)
+        self.child1 = np.ascontiguousarray(child1, np.int32)
+        self.dist = np.ascontiguousarray(dist, np.float64)
+        self.root = int(root)
+        self.numMinor = np.zeros(self.n, np.int32) if numMinor is None else np.ascontiguousarray(numMinor, np.int32)
+        self.isTip = ((self.child0 < 0) & (self.numMinor == 0)).astype(np.uint8) if isTip is None else np.ascontiguousarray(isTip, np.uint8)
+        self._levels()
+        dev = engine.device
+        self.d_up = torch.from_numpy(self.up).to(dev)
+        self.d_child0 = torch.from_numpy(self.child0).to(dev)
+        self.d_child1 = torch.from_numpy(self.child1).to(dev)
+        self.d_dist = torch.from_numpy(self.dist).to(dev)
+        self.d_isTip = torch.from_numpy(self.isTip).to(dev)
+        self.arena: Optional[ListArena] = None
+
+    def lid(self, fam: int, node):
+        return fam * self.n + node
+
+    def _levels(self):
+        n = self.n
+        depth = np.full(n, -1, np.int32)
+        order = [self.root]
+        depth[self.root] = 0
+        for nd in order:
+            for c in (self.child0[nd], self.child1[nd]):
+                if c >= 0:
+                    depth[c] = depth[nd] + 1
+                    order.append(int(c))
+        self.preorder = np.array(order, np.int32)
+        height = np.zeros(n, np.int32)
+        for nd in reversed(order):
+            if self.child0[nd] >= 0:
+                height[nd] = 1 + max(height[self.child0[nd]], height[self.child1[nd]])
+        self.depth, self.height = depth, height
+        live = depth >= 0
+        self.by_height = [np.nonzero(live & (height == h))[0].astype(np.int64) for h in range(int(height[self.root]) + 1)]
+        self.by_depth = [np.nonzero(depth == d)[0].astype(np.int64) for d in range(int(depth.max()) + 1)]
+
+    # ------------------------------------------------------------------ reCalculateAllGenomeLists (:6013-6347)
+    def recalculate_all_lists(self, tip_nodes, tip_lists_packed: PackedLists, key_capacity: Optional[int] = None):
+        """Build all four list families on the device from the tip lists.
+
+        First pass (post-order, :6031-6216): lower lists by batches of equal node height.
+        Root (:6225-6245): rootVector of each child's lower list.  Second pass (pre-order,
+        :6247-6345): probVectTotUp / UpRight / UpLeft by batches of equal depth.  Every stored list
+        is shortened, as the reference does at :6201, :6267, :6308, :6330 and inside rootVector.
+        """
+        eng, n, dev = self.eng, self.n, self.eng.device
+        nk_tips = int(tip_lists_packed.nkeys.sum())
+        cap_k = key_capacity or max(1 << 16, int(nk_tips * 12))
+        self.arena = ListArena(eng, 4 * n, cap_k, cap_k)
+        A = self.arena
+        A.store_packed(np.asarray(tip_nodes, np.int64) + FAM_LOWER * n, tip_lists_packed)
+        t64 = lambda a: torch.as_tensor(a, dtype=torch.int64, device=dev)  # noqa: E731
+        dist, isTip = self.d_dist, self.d_isTip
+        c0, c1 = self.d_child0.long(), self.d_child1.long()
+
+        def merge_store(list_ids, i1, b1, t1, i2, b2, t2, updown):
+            r = eng.merge_batch(i1.int(), b1, t1, i2.int(), b2, t2, torch.full((i1.numel(),), 1 if updown else 0, dtype=torch.uint8, device=dev),
+                                shorten=True)
+            if bool((r.status != 0).any().item()):
+                bad = int((r.status != 0).nonzero()[0].item())
+                raise capi.MapleError("inconsistent genome lists (mergeVectors returned None) at list id %d; the reference would "
+                                      "re-estimate zero branch lengths here (:6179-6198), which this builder does not do" % int(list_ids[bad]))
+            A.store(list_ids, r.key, r.pay, r.key_start, r.pay_start, r.nkeys, r.npay, r.status)
+
+        for h in range(1, len(self.by_height)):
+            nodes = t64(self.by_height[h])
+            if nodes.numel() == 0:
+                continue
+            a, b = c0[nodes], c1[nodes]
+            merge_store(nodes + FAM_LOWER * n, a + FAM_LOWER * n, dist[a], isTip[a], b + FAM_LOWER * n, dist[b], isTip[b], False)
+        root = self.root
+        if self.child0[root] >= 0:
+            ch = t64([self.child1[root], self.child0[root]])  # UpRight from child 1, UpLeft from child 0
+            cap = (A.nkeys[ch + FAM_LOWER * n].long() + 3) // 4 * 4 + 4
+            ks = torch.cumsum(cap, 0) - cap
+            ps = ks * 6
+            ok_ = torch.empty(int(cap.sum().item()) + 4, dtype=torch.int32, device=dev)
+            op_ = torch.empty(int(cap.sum().item()) * 6 + 4, dtype=torch.float64, device=dev)
+            nk = torch.empty(2, dtype=torch.int32, device=dev)
+            npay = torch.empty(2, dtype=torch.int32, device=dev)
+            rc = eng.lib.maple_root_vector_batch(eng.ctx, 2, _dp((ch + FAM_LOWER * n).int()), _dp(dist[ch].contiguous()),
+                                                 _dp(isTip[ch].contiguous()), _dp(ok_), _dp(op_), _dp(ks), _dp(ps), _dp(nk), _dp(npay), 1,
+                                                 eng._stream())
+            capi.check(eng.ctx, rc, "maple_root_vector_batch")
+            A.store(t64([root + FAM_UPRIGHT * n, root + FAM_UPLEFT * n]), ok_, op_, ks, ps, nk, npay)
+        for d in range(1, len(self.by_depth)):
+            nodes = t64(self.by_depth[d])
+            par = self.d_up.long()[nodes]
+            is0 = c0[par] == nodes
+            vectUp = torch.where(is0, par + FAM_UPRIGHT * n, par + FAM_UPLEFT * n)
+            dn = dist[nodes]
+            pos = dn > 0  # :6262 `if dist[node]`
+            if bool(pos.any().item()):
+                m = nodes[pos]
+                merge_store(m + FAM_TOTUP * n, vectUp[pos], dn[pos] / 2, torch.zeros_like(isTip[m]), m + FAM_LOWER * n, dn[pos] / 2,
+                            isTip[m], True)
+            internal = c0[nodes] >= 0
+            if bool(internal.any().item()):
+                m, vu = nodes[internal], vectUp[internal]
+                a, b = c0[m], c1[m]
+                z = torch.zeros_like(isTip[m])
+                ids = torch.cat([m + FAM_UPRIGHT * n, m + FAM_UPLEFT * n])
+                merge_store(ids, torch.cat([vu, vu]), torch.cat([dist[m], dist[m]]), torch.cat([z, z]),
+                            torch.cat([b + FAM_LOWER * n, a + FAM_LOWER * n]), torch.cat([dist[b], dist[a]]),
+                            torch.cat([isTip[b], isTip[a]]), True)
+        return A
+
+    def lists_of(self, node: int):
+        A = self.arena
+        return [A.get(self.lid(f, node)) for f in range(4)]
