@@ -73,14 +73,16 @@ class ListArena:
         dps = self.pay_tail + torch.cumsum(p_al, 0) - p_al
         dks = torch.where(ok, dks, torch.full_like(dks, -1))
         n = list_ids.numel()
+        # NOTE: every tensor whose pointer is passed must stay referenced until the call returns
+        nk32, np32 = nk.int(), npy.int()
         rc = self.eng.lib.maple_lists_copy(self.eng.ctx, n, _dp(src_key), _dp(src_pay), _dp(src_key_start), _dp(src_pay_start),
-                                           _dp(nk.int()), _dp(npy.int()), _dp(self.key), _dp(self.pay), _dp(dks), _dp(dps),
+                                           _dp(nk32), _dp(np32), _dp(self.key), _dp(self.pay), _dp(dks), _dp(dps),
                                            self.eng._stream())
         capi.check(self.eng.ctx, rc, "maple_lists_copy")
         self.key_start[list_ids] = dks
         self.pay_start[list_ids] = torch.where(ok, dps, torch.full_like(dps, -1))
-        self.nkeys[list_ids] = nk.int()
-        self.npay[list_ids] = npy.int()
+        self.nkeys[list_ids] = nk32
+        self.npay[list_ids] = np32
         self.key_tail += tot_k
         self.pay_tail += tot_p
 
@@ -198,9 +200,9 @@ class DeviceTree:
             op_ = torch.empty(int(cap.sum().item()) * 6 + 4, dtype=torch.float64, device=dev)
             nk = torch.empty(2, dtype=torch.int32, device=dev)
             npay = torch.empty(2, dtype=torch.int32, device=dev)
-            rc = eng.lib.maple_root_vector_batch(eng.ctx, 2, _dp((ch + FAM_LOWER * n).int()), _dp(dist[ch].contiguous()),
-                                                 _dp(isTip[ch].contiguous()), _dp(ok_), _dp(op_), _dp(ks), _dp(ps), _dp(nk), _dp(npay), 1,
-                                                 eng._stream())
+            ids32, bl_, tip_ = (ch + FAM_LOWER * n).int(), dist[ch].contiguous(), isTip[ch].contiguous()
+            rc = eng.lib.maple_root_vector_batch(eng.ctx, 2, _dp(ids32), _dp(bl_), _dp(tip_), _dp(ok_), _dp(op_), _dp(ks), _dp(ps),
+                                                 _dp(nk), _dp(npay), 1, eng._stream())
             capi.check(eng.ctx, rc, "maple_root_vector_batch")
             A.store(t64([root + FAM_UPRIGHT * n, root + FAM_UPLEFT * n]), ok_, op_, ks, ps, nk, npay)
         for d in range(1, len(self.by_depth)):
