@@ -27,6 +27,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -997,4 +998,628 @@ int or_num_threads(void) {
     }
 #endif
     return n;
+}
+
+/* ==================================================================================================
+ * SPR search: the per-node body of startTopologyUpdatesParallel (:9615-9711) and findBestParentTopology
+ * (:6817-7724) with evaluatePlacement (:6790-6806), for the default feature set (no time tree, no HnZ, no SPRTA).
+ *
+ * Phase 2 of the reference (:7460-7639) re-visits every entry of bestNodes whose score >= originalLK - threshold.
+ * Entries are only appended when score > (>=) bestLKdiff - threshold and bestLKdiff never drops below originalLK,
+ * so EVERY entry qualifies; and an entry's evaluation depends on nothing but the lists it carries.  The phase-2
+ * evaluation is therefore done here at the moment the entry would be appended, keeping the running arg-max in
+ * discovery order (ties: the later entry wins, :7635) -- same results, no list has to outlive the walk.
+ * ================================================================================================== */
+typedef struct {
+    int32_t nNodes, root;
+    const int32_t *up, *child0, *child1; /* -1 = none */
+    const double *dist;
+    const uint8_t *isTip;     /* no children and no minor sequences */
+    const int32_t *mutStart;  /* [nNodes+1] CSR into mut, or NULL when no node carries MAT mutations */
+    const int32_t *mut;       /* triples (pos1, upNuc, downNuc) */
+    const uint32_t *key;      /* list id = family*nNodes + node; 0 lower, 1 upRight, 2 upLeft, 3 totUp */
+    const double *pay;
+    const int64_t *keyStart, *payStart;
+    const int32_t *nkeys;
+} OrTree;
+
+typedef struct {
+    int32_t strictTopologyStopRules, allowedFailsTopology, deeperSearchForLongBranches, reserved;
+    double thresholdLogLKtopology, thresholdTopologyPlacement, thresholdLogLKoptimizationTopology;
+    double thresholdLogLKconsecutivePlacement, effectivelyNon0BLen, BLenThresholdDeeperSearch, defaultBLen;
+} OrSearchParams;
+
+typedef struct {
+    int32_t placement; /* proposed re-attachment node or -1 */
+    int32_t bestNode;  /* findBestParentTopology's bestNode (-1 when the search did not run) */
+    int32_t status;    /* 0 ok, 1 search not needed, 2 aborted (the reference's try/except -> placement None), 3 scratch overflow */
+    int32_t phase1;    /* candidate placements scored by the phase-1 appendProbNode calls (:7011 / :7223) */
+    double improvement, bestCurrentLK, bestScore, bLenTop, bLenBottom, bLenAppend;
+} OrSearchResult;
+
+typedef struct {
+    const uint32_t *k;
+    const double *p;
+    int nk;
+} LRef;
+
+/* The reference's tree is not quite frozen during a search round: a child of the root with a zero-length branch
+ * has probVectTotUp == None until the first search that reaches it from below with needsUpdating computes and STORES
+ * it (:7198-7200).  Before that, searches arriving with converged partials skip the node (:7207); afterwards they
+ * score it -- so the reference's proposals depend on the order of searches within a worker.  `LazyTot` holds those
+ * (at most two) lists.  mode 0 = lazy like the reference (single-threaded, caller's order), mode 1 = pre-filled
+ * before any search (order-independent; what the device path does). */
+typedef struct {
+    int node[2], filled[2], nk[2];
+    uint32_t *key[2];
+    double *pay[2];
+} LazyTot;
+
+typedef struct {
+    uint32_t *key;
+    double *pay;
+    size_t capK, capP, topK, topP;
+    int overflow;
+    double *ais;
+    size_t capA;
+    LazyTot *lazy;
+} Scratch;
+
+typedef struct {
+    int t1, direction, needsUpdating, failedPasses;
+    LRef passed, removed;
+    int removedScratch; /* the removed list lives in scratch (may be shortened in place) */
+    double distance, lastLK;
+    size_t markK, markP;
+} StackE;
+
+#define OR_STACK_MAX 4096
+
+static LRef lref_null(void) { LRef r = {NULL, NULL, 0}; return r; }
+
+static LRef tree_list(const OrTree *t, int fam, int node) {
+    int64_t id = (int64_t)fam * t->nNodes + node;
+    LRef r;
+    if (t->keyStart[id] < 0) return lref_null();
+    r.k = t->key + t->keyStart[id];
+    r.p = t->pay + t->payStart[id];
+    r.nk = t->nkeys[id];
+    return r;
+}
+
+static LRef totup_list(const OrTree *t, const Scratch *s, int node) {
+    LRef r = tree_list(t, 3, node);
+    if (r.k || !s->lazy) return r;
+    for (int i = 0; i < 2; i++)
+        if (s->lazy->node[i] == node && s->lazy->filled[i]) {
+            r.k = s->lazy->key[i];
+            r.p = s->lazy->pay[i];
+            r.nk = s->lazy->nk[i];
+        }
+    return r;
+}
+
+static void lazy_fill(const OrModel *m, const OrTree *t, Scratch *s, int node, LRef vectUp) {
+    LazyTot *z = s->lazy;
+    if (!z) return;
+    for (int i = 0; i < 2; i++)
+        if (z->node[i] == node && !z->filled[i]) {
+            LRef pv = tree_list(t, 0, node);
+            size_t cap = (size_t)vectUp.nk + pv.nk + 4;
+            z->key[i] = (uint32_t *)malloc(sizeof(uint32_t) * cap);
+            z->pay[i] = (double *)malloc(sizeof(double) * 6 * cap);
+            int32_t nk = 0, np = 0;
+            int st = or_merge(m, vectUp.k, vectUp.p, t->dist[node] / 2, 0, pv.k, pv.p, t->dist[node] / 2, 0, 1, 0, 0, z->key[i], z->pay[i], &nk, &np, NULL);
+            if (st == 0) { z->filled[i] = 1; z->nk[i] = nk; }
+        }
+}
+
+static int sc_reserve(Scratch *s, size_t nk) {
+    size_t k = (nk + 3) & ~(size_t)3;
+    if (s->topK + k > s->capK || s->topP + 6 * k > s->capP) { s->overflow = 1; return 0; }
+    return 1;
+}
+
+static LRef sc_commit(Scratch *s, int nk, int np) {
+    LRef r = {s->key + s->topK, s->pay + s->topP, nk};
+    s->topK += ((size_t)nk + 3) & ~(size_t)3;
+    s->topP += ((size_t)np + 1) & ~(size_t)1;
+    return r;
+}
+
+static int n_mut(const OrTree *t, int node) { return t->mutStart ? t->mutStart[node + 1] - t->mutStart[node] : 0; }
+
+/* passGenomeListThroughBranch into scratch */
+static LRef s_pass(const OrModel *m, const OrTree *t, Scratch *s, LRef v, int node, int dirIsUp) {
+    int nm = n_mut(t, node);
+    if (!sc_reserve(s, (size_t)v.nk + 2 * (size_t)nm + 2)) return lref_null();
+    int32_t nk = 0, np = 0;
+    or_pass_branch(m, v.k, v.p, t->mut + 3 * (size_t)t->mutStart[node], nm, dirIsUp, s->key + s->topK, s->pay + s->topP, &nk, &np);
+    return sc_commit(s, nk, np);
+}
+
+static LRef s_merge(const OrModel *m, Scratch *s, LRef a, double b1, int t1, LRef b, double b2, int t2, int upDown) {
+    if (!sc_reserve(s, (size_t)a.nk + b.nk)) return lref_null();
+    int32_t nk = 0, np = 0;
+    int st = or_merge(m, a.k, a.p, b1, t1, b.k, b.p, b2, t2, upDown ? 1 : 0, 0, 0, s->key + s->topK, s->pay + s->topP, &nk, &np, NULL);
+    if (st != 0) return lref_null();
+    return sc_commit(s, nk, np);
+}
+
+static void s_shorten_inplace(const OrModel *m, LRef *v) {
+    int32_t nk = 0, np = 0;
+    or_shorten(m, v->k, v->p, (uint32_t *)v->k, (double *)v->p, &nk, &np);
+    v->nk = nk;
+}
+
+/* rootVector(probVect, bLen, isFromTip, tree, node) for node == root (:4916-4996) */
+static LRef s_root_vector(const OrModel *m, const OrTree *t, Scratch *s, LRef v, double bLen, int isFromTip) {
+    int root = t->root;
+    if (n_mut(t, root)) v = s_pass(m, t, s, v, root, 1);
+    if (!v.k || !sc_reserve(s, (size_t)v.nk)) return lref_null();
+    int32_t nk = 0, np = 0;
+    or_root_vector(m, v.k, v.p, bLen, isFromTip, s->key + s->topK, s->pay + s->topP, &nk, &np);
+    LRef r = sc_commit(s, nk, np);
+    if (n_mut(t, root)) r = s_pass(m, t, s, r, root, 0);
+    if (r.k) s_shorten_inplace(m, &r);
+    return r;
+}
+
+static LRef s_copy(Scratch *s, LRef v) {
+    if (!sc_reserve(s, (size_t)v.nk)) return lref_null();
+    /* payload size is implied by the keys */
+    size_t np = 0;
+    for (int i = 0; i < v.nk; i++) {
+        uint32_t k = v.k[i];
+        np += ((k >> 3) & 3u) + (((k & 7u) == 6) ? 4 : 0);
+    }
+    memcpy(s->key + s->topK, v.k, sizeof(uint32_t) * v.nk);
+    memcpy(s->pay + s->topP, v.p, sizeof(double) * np);
+    return sc_commit(s, v.nk, (int)np);
+}
+
+static double s_blen(const OrModel *m, Scratch *s, LRef P, LRef C, int fromTipC) {
+    size_t need = (size_t)P.nk + C.nk + 1;
+    if (need > s->capA) { s->overflow = 1; return 0.0; }
+    double out = 0.0;
+    or_blen(m, P.k, P.p, C.k, C.p, fromTipC, s->ais, &out); /* python False and 0.0 are both "zero length" to the callers */
+    return out;
+}
+
+/* evaluatePlacement (:6790-6806); returns 0 ok, 1 when the reference would raise (a None list reaches the next call) */
+static int eval_placement(const OrModel *m, const OrSearchParams *sp, Scratch *s, LRef midTot, LRef downVect, LRef upVect,
+                          double distance, LRef removed, int isRemovedTip, int fromTip1, double *cost, double *bBottom,
+                          double *bTop, double *bAppend) {
+    size_t mk = s->topK, mp = s->topP;
+    double bestAppending = s_blen(m, s, midTot, removed, isRemovedTip);
+    LRef midLower = s_merge(m, s, downVect, distance / 2, fromTip1, removed, bestAppending, isRemovedTip, 0);
+    if (!midLower.k) return 1;
+    double bestTop = s_blen(m, s, upVect, midLower, 0);
+    LRef midTop = s_merge(m, s, upVect, bestTop, 0, removed, bestAppending, isRemovedTip, 1);
+    if (!midTop.k) {
+        if (s->overflow) return 1;
+        bestTop = sp->defaultBLen * 0.1;
+        midTop = s_merge(m, s, upVect, bestTop, 0, removed, bestAppending, isRemovedTip, 1);
+        if (!midTop.k) return 1;
+    }
+    double bestBottom = s_blen(m, s, midTop, downVect, fromTip1);
+    LRef newMid = s_merge(m, s, upVect, bestTop, 0, downVect, bestBottom, fromTip1, 1);
+    if (!newMid.k) return 1;
+    *cost = or_append(m, newMid.k, newMid.p, removed.k, removed.p, isRemovedTip, bestAppending);
+    *bBottom = bestBottom;
+    *bTop = bestTop;
+    *bAppend = bestAppending;
+    s->topK = mk;
+    s->topP = mp;
+    return s->overflow;
+}
+
+typedef struct {
+    double bestScore;
+    int bestNode;
+    double bTop, bBottom, bAppend;
+} Phase2;
+
+/* one bestNodes entry, evaluated eagerly (:7460-7639 without HnZ / time / SPRTA) */
+static int phase2_entry(const OrModel *m, const OrSearchParams *sp, Scratch *s, int t1, LRef midTot, LRef downVect, LRef upVect,
+                        double distance, LRef removed, int isRemovedTip, int fromTip1, Phase2 *ph) {
+    double cost, bB, bT, bA;
+    if (eval_placement(m, sp, s, midTot, downVect, upVect, distance, removed, isRemovedTip, fromTip1, &cost, &bB, &bT, &bA)) return 1;
+    double initialCost = or_append(m, upVect.k, upVect.p, downVect.k, downVect.p, fromTip1, distance);
+    double newPartialCost = or_append(m, upVect.k, upVect.p, downVect.k, downVect.p, fromTip1, bB + bT);
+    double optimizedScore = cost + newPartialCost - initialCost;
+    if (optimizedScore >= ph->bestScore) {
+        ph->bestNode = t1;
+        ph->bestScore = optimizedScore;
+        ph->bTop = bT;
+        ph->bBottom = bB;
+        ph->bAppend = bA;
+    }
+    return 0;
+}
+
+static int find_best_parent_topology(const OrModel *m, const OrTree *t, const OrSearchParams *sp, Scratch *s, int node, int child,
+                                     double bestLKdiff, double removedBLen, Phase2 *ph, int *phase1) {
+    const int32_t *up = t->up;
+    const double *dist = t->dist;
+    const double eff = sp->effectivelyNon0BLen;
+#define CH(n, i) ((i) == 0 ? t->child0[n] : t->child1[n])
+    StackE *stack = (StackE *)malloc(sizeof(StackE) * OR_STACK_MAX);
+    int sp_n = 0, rc = 0;
+    const int pruned = CH(node, child), sibling = CH(node, 1 - child);
+    int bestNodeInit = sibling;
+    /* the removed list is copied to scratch: the reference may shorten it in place (:7087) */
+    LRef removedRel = s_copy(s, tree_list(t, 0, pruned));
+    if (n_mut(t, pruned)) removedRel = s_pass(m, t, s, removedRel, pruned, 1);
+    LRef bestRemoved = removedRel;
+    if (n_mut(t, bestNodeInit)) bestRemoved = s_pass(m, t, s, bestRemoved, bestNodeInit, 0);
+    const int isRemovedTip = t->isTip[pruned];
+    const double originalLK = bestLKdiff;
+    ph->bestNode = bestNodeInit;
+    ph->bestScore = originalLK;
+    if (up[node] >= 0) {
+        int childUp;
+        LRef vectUpUp;
+        if (t->child0[up[node]] == node) { childUp = 1; vectUpUp = tree_list(t, 1, up[node]); }
+        else { childUp = 2; vectUpUp = tree_list(t, 2, up[node]); }
+        LRef probVect1 = tree_list(t, 0, bestNodeInit);
+        if (n_mut(t, bestNodeInit)) probVect1 = s_pass(m, t, s, probVect1, bestNodeInit, 1);
+        LRef removedRel1 = removedRel;
+        if (n_mut(t, node)) {
+            probVect1 = s_pass(m, t, s, probVect1, node, 1);
+            removedRel1 = s_pass(m, t, s, removedRel, node, 1);
+        }
+        StackE e;
+        memset(&e, 0, sizeof e);
+        e.t1 = up[node]; e.direction = childUp; e.needsUpdating = 1; e.passed = probVect1;
+        e.distance = dist[bestNodeInit] + dist[node]; e.lastLK = bestLKdiff; e.failedPasses = 0; e.removed = removedRel1; e.removedScratch = 1;
+        e.markK = s->topK; e.markP = s->topP;
+        stack[sp_n++] = e;
+        if (n_mut(t, node)) vectUpUp = s_pass(m, t, s, vectUpUp, node, 0);
+        removedRel1 = removedRel;
+        if (n_mut(t, bestNodeInit)) {
+            vectUpUp = s_pass(m, t, s, vectUpUp, bestNodeInit, 0);
+            removedRel1 = s_pass(m, t, s, removedRel, bestNodeInit, 0);
+        }
+        e.t1 = bestNodeInit; e.direction = 0; e.passed = vectUpUp; e.removed = removedRel1;
+        e.markK = s->topK; e.markP = s->topP;
+        stack[sp_n++] = e;
+        ph->bTop = dist[node]; ph->bBottom = dist[bestNodeInit]; ph->bAppend = removedBLen;
+    } else {
+        if (t->child0[bestNodeInit] >= 0) {
+            int child1 = t->child0[bestNodeInit], child2 = t->child1[bestNodeInit];
+            for (int which = 0; which < 2; which++) {
+                int target = which == 0 ? child1 : child2, other = which == 0 ? child2 : child1;
+                LRef vectUp1 = tree_list(t, 0, other);
+                if (n_mut(t, other)) vectUp1 = s_pass(m, t, s, vectUp1, other, 1);
+                vectUp1 = s_root_vector(m, t, s, vectUp1, dist[other], t->isTip[other]);
+                LRef removedRel1 = bestRemoved;
+                if (n_mut(t, target)) {
+                    removedRel1 = s_pass(m, t, s, bestRemoved, target, 0);
+                    vectUp1 = s_pass(m, t, s, vectUp1, target, 0);
+                }
+                StackE e;
+                memset(&e, 0, sizeof e);
+                e.t1 = target; e.direction = 0; e.needsUpdating = 1; e.passed = vectUp1; e.distance = dist[target];
+                e.lastLK = bestLKdiff; e.failedPasses = 0; e.removed = removedRel1; e.removedScratch = 1;
+                e.markK = s->topK; e.markP = s->topP;
+                stack[sp_n++] = e;
+            }
+        }
+        ph->bTop = 0.0; ph->bBottom = dist[bestNodeInit]; ph->bAppend = removedBLen;
+    }
+    if (s->overflow) { rc = 3; goto done; }
+
+    while (sp_n > 0) {
+        StackE E = stack[--sp_n];
+        s->topK = E.markK;
+        s->topP = E.markP;
+        const int t1 = E.t1, direction = E.direction;
+        int needsUpdating = E.needsUpdating, failedPasses = E.failedPasses;
+        LRef passed = E.passed, removed = E.removed;
+        double distance = E.distance, lastLK = E.lastLK, midProb;
+        if (direction == 0) {
+            if (!(up[t1] == node || up[t1] < 0) && (dist[t1] > eff || up[up[t1]] < 0)) {
+                LRef midTot;
+                if (needsUpdating) {
+                    midTot = s_merge(m, s, passed, distance / 2, 0, tree_list(t, 0, t1), distance / 2, t->isTip[t1], 1);
+                    if (s->overflow) { rc = 3; goto done; }
+                    if (!midTot.k) continue;
+                    LRef stored = totup_list(t, s, t1);
+                    if (!or_differ(m, midTot.k, midTot.p, stored.k, stored.p)) needsUpdating = 0;
+                } else {
+                    midTot = totup_list(t, s, t1);
+                    distance = dist[t1];
+                }
+                if (!midTot.k) continue;
+                LRef vectUp = lref_null();
+                if (sp->deeperSearchForLongBranches && distance > sp->BLenThresholdDeeperSearch) {
+                    LRef midBottom = tree_list(t, 0, t1);
+                    vectUp = (t1 == t->child0[up[t1]]) ? tree_list(t, 1, up[t1]) : tree_list(t, 2, up[t1]);
+                    if (n_mut(t, t1)) vectUp = s_pass(m, t, s, vectUp, t1, 0);
+                    double bB, bT, bA;
+                    if (eval_placement(m, sp, s, midTot, midBottom, vectUp, distance, removed, isRemovedTip, t->isTip[t1], &midProb, &bB, &bT, &bA)) {
+                        rc = s->overflow ? 3 : 2;
+                        goto done;
+                    }
+                } else {
+                    midProb = or_append(m, midTot.k, midTot.p, removed.k, removed.p, isRemovedTip, removedBLen);
+                    (*phase1)++;
+                }
+                if (getenv("MAPLE_ORACLE_TRACE")) fprintf(stderr, "cand %d dir %d nu %d midProb %.17g fails %d lastLK %.17g best %.17g\n", t1, direction, needsUpdating, midProb, failedPasses, lastLK, bestLKdiff);
+                if (midProb > bestLKdiff - sp->thresholdLogLKoptimizationTopology) { /* :7071 */
+                    LRef upV, downV, mt;
+                    double dd;
+                    if (needsUpdating) { upV = passed; downV = tree_list(t, 0, t1); dd = distance; mt = midTot; }
+                    else {
+                        upV = (t1 == t->child0[up[t1]]) ? tree_list(t, 1, up[t1]) : tree_list(t, 2, up[t1]);
+                        if (n_mut(t, t1)) upV = s_pass(m, t, s, upV, t1, 0);
+                        downV = tree_list(t, 0, t1); dd = dist[t1]; mt = totup_list(t, s, t1);
+                    }
+                    if (phase2_entry(m, sp, s, t1, mt, downV, upV, dd, removed, isRemovedTip, t->isTip[t1], ph)) {
+                        rc = s->overflow ? 3 : 2;
+                        goto done;
+                    }
+                }
+                if (midProb > bestLKdiff) {
+                    bestLKdiff = midProb;
+                    failedPasses = 0;
+                    if (E.removedScratch) s_shorten_inplace(m, &removed); /* :7087 */
+                } else if (midProb < (lastLK - sp->thresholdLogLKconsecutivePlacement)) failedPasses++;
+            } else midProb = lastLK;
+
+            int traverse = 0;
+            if (sp->strictTopologyStopRules) {
+                if (failedPasses <= sp->allowedFailsTopology && midProb > (bestLKdiff - sp->thresholdLogLKtopology) && t->child0[t1] >= 0) traverse = 1;
+            } else if (failedPasses <= sp->allowedFailsTopology || midProb > (bestLKdiff - sp->thresholdLogLKtopology)) {
+                if (t->child0[t1] >= 0) traverse = 1;
+            }
+            if (traverse) {
+                for (int which = 0; which < 2; which++) { /* child 0 is pushed first, so child 1 is explored first */
+                    int child1 = CH(t1, which), otherChild = CH(t1, 1 - which);
+                    LRef vUp;
+                    if (needsUpdating) {
+                        LRef otherPV = tree_list(t, 0, otherChild);
+                        if (n_mut(t, otherChild)) otherPV = s_pass(m, t, s, otherPV, otherChild, 1);
+                        vUp = s_merge(m, s, passed, distance, 0, otherPV, dist[otherChild], t->isTip[otherChild], 1);
+                        if (s->overflow) { rc = 3; goto done; }
+                    } else vUp = which == 0 ? tree_list(t, 1, t1) : tree_list(t, 2, t1);
+                    if (vUp.k) {
+                        LRef removed1 = removed;
+                        int rs = E.removedScratch;
+                        if (n_mut(t, child1)) { removed1 = s_pass(m, t, s, removed, child1, 0); rs = 1; }
+                        if (needsUpdating && n_mut(t, child1)) vUp = s_pass(m, t, s, vUp, child1, 0);
+                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                        StackE e;
+                        memset(&e, 0, sizeof e);
+                        e.t1 = child1; e.direction = 0; e.needsUpdating = needsUpdating; e.passed = needsUpdating ? vUp : lref_null();
+                        e.distance = dist[child1]; e.lastLK = midProb; e.failedPasses = failedPasses; e.removed = removed1; e.removedScratch = rs;
+                        e.markK = s->topK; e.markP = s->topP;
+                        stack[sp_n++] = e;
+                    }
+                }
+            }
+        } else { /* crawling up from child to parent (:7179-7429) */
+            const int otherChild = CH(t1, 2 - direction);
+            LRef midBottom = lref_null(), vectUp = lref_null();
+            if (up[t1] >= 0 && (dist[t1] > eff || up[up[t1]] < 0)) {
+                LRef midTot;
+                if (needsUpdating) {
+                    LRef otherPV = tree_list(t, 0, otherChild);
+                    if (n_mut(t, otherChild)) otherPV = s_pass(m, t, s, otherPV, otherChild, 1);
+                    midBottom = s_merge(m, s, passed, distance, 0, otherPV, dist[otherChild], t->isTip[otherChild], 0);
+                    if (s->overflow) { rc = 3; goto done; }
+                    if (!midBottom.k) continue;
+                    vectUp = (t1 == t->child0[up[t1]]) ? tree_list(t, 1, up[t1]) : tree_list(t, 2, up[t1]);
+                    if (n_mut(t, t1)) vectUp = s_pass(m, t, s, vectUp, t1, 0);
+                    midTot = s_merge(m, s, vectUp, dist[t1] / 2, 0, midBottom, dist[t1] / 2, 0, 1);
+                    if (s->overflow) { rc = 3; goto done; }
+                    if (!totup_list(t, s, t1).k) lazy_fill(m, t, s, t1, vectUp); /* :7198-7200 */
+                    if (!midTot.k) continue;
+                    LRef stored = totup_list(t, s, t1);
+                    if (!or_differ(m, midTot.k, midTot.p, stored.k, stored.p)) needsUpdating = 0;
+                } else midTot = totup_list(t, s, t1);
+                if (!midTot.k) continue;
+                if (sp->deeperSearchForLongBranches && dist[t1] > sp->BLenThresholdDeeperSearch) {
+                    if (!needsUpdating) {
+                        midBottom = tree_list(t, 0, t1);
+                        vectUp = (t1 == t->child0[up[t1]]) ? tree_list(t, 1, up[t1]) : tree_list(t, 2, up[t1]);
+                        if (n_mut(t, t1)) vectUp = s_pass(m, t, s, vectUp, t1, 0);
+                    }
+                    double bB, bT, bA;
+                    if (eval_placement(m, sp, s, midTot, midBottom, vectUp, dist[t1], removed, isRemovedTip, 0, &midProb, &bB, &bT, &bA)) {
+                        rc = s->overflow ? 3 : 2;
+                        goto done;
+                    }
+                } else {
+                    midProb = or_append(m, midTot.k, midTot.p, removed.k, removed.p, isRemovedTip, removedBLen);
+                    (*phase1)++;
+                }
+                if (getenv("MAPLE_ORACLE_TRACE")) fprintf(stderr, "cand %d dir %d nu %d midProb %.17g fails %d lastLK %.17g best %.17g\n", t1, direction, needsUpdating, midProb, failedPasses, lastLK, bestLKdiff);
+                if (midProb >= (bestLKdiff - sp->thresholdLogLKoptimizationTopology)) { /* :7293 */
+                    LRef upV, downV, mt;
+                    if (needsUpdating) { upV = vectUp; downV = midBottom; mt = midTot; }
+                    else {
+                        upV = (t1 == t->child0[up[t1]]) ? tree_list(t, 1, up[t1]) : tree_list(t, 2, up[t1]);
+                        if (n_mut(t, t1)) upV = s_pass(m, t, s, upV, t1, 0);
+                        downV = tree_list(t, 0, t1); mt = totup_list(t, s, t1);
+                    }
+                    if (phase2_entry(m, sp, s, t1, mt, downV, upV, dist[t1], removed, isRemovedTip, t->isTip[t1], ph)) {
+                        rc = s->overflow ? 3 : 2;
+                        goto done;
+                    }
+                }
+                if (midProb > bestLKdiff) { bestLKdiff = midProb; failedPasses = 0; }
+                else if (midProb < (lastLK - sp->thresholdLogLKconsecutivePlacement)) failedPasses++;
+            } else midProb = lastLK;
+
+            int keep = 0;
+            if (sp->strictTopologyStopRules) {
+                if (failedPasses <= sp->allowedFailsTopology && midProb > (bestLKdiff - sp->thresholdLogLKtopology)) keep = 1;
+            } else if (failedPasses <= sp->allowedFailsTopology || midProb > (bestLKdiff - sp->thresholdLogLKtopology)) keep = 1;
+            if (keep) {
+                if (up[t1] >= 0) {
+                    int upChild;
+                    LRef vectUpUp = lref_null(), vUp;
+                    if (t1 == t->child0[up[t1]]) { upChild = 0; if (needsUpdating) vectUpUp = tree_list(t, 1, up[t1]); }
+                    else { upChild = 1; if (needsUpdating) vectUpUp = tree_list(t, 2, up[t1]); }
+                    if (needsUpdating) {
+                        if (n_mut(t, t1)) vectUpUp = s_pass(m, t, s, vectUpUp, t1, 0);
+                        vUp = s_merge(m, s, vectUpUp, dist[t1], 0, passed, distance, 0, 1);
+                        if (s->overflow) { rc = 3; goto done; }
+                    } else vUp = direction == 1 ? tree_list(t, 2, t1) : tree_list(t, 1, t1);
+                    if (!vUp.k) continue;
+                    {
+                        LRef removed1 = removed;
+                        int rs = E.removedScratch;
+                        if (n_mut(t, otherChild)) { removed1 = s_pass(m, t, s, removed, otherChild, 0); rs = 1; }
+                        if (needsUpdating && n_mut(t, otherChild)) vUp = s_pass(m, t, s, vUp, otherChild, 0);
+                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                        StackE e;
+                        memset(&e, 0, sizeof e);
+                        e.t1 = otherChild; e.direction = 0; e.needsUpdating = needsUpdating; e.passed = needsUpdating ? vUp : lref_null();
+                        e.distance = dist[otherChild]; e.lastLK = midProb; e.failedPasses = failedPasses; e.removed = removed1; e.removedScratch = rs;
+                        e.markK = s->topK; e.markP = s->topP;
+                        stack[sp_n++] = e;
+                    }
+                    if (needsUpdating && !midBottom.k) {
+                        LRef otherPV = tree_list(t, 0, otherChild);
+                        if (n_mut(t, otherChild)) otherPV = s_pass(m, t, s, otherPV, otherChild, 1);
+                        midBottom = s_merge(m, s, passed, distance, 0, otherPV, dist[otherChild], t->isTip[otherChild], 0);
+                        if (s->overflow) { rc = 3; goto done; }
+                        if (!midBottom.k) continue;
+                    }
+                    {
+                        LRef removed1 = removed;
+                        int rs = E.removedScratch;
+                        if (n_mut(t, t1)) { removed1 = s_pass(m, t, s, removed, t1, 1); rs = 1; }
+                        if (needsUpdating && n_mut(t, t1)) midBottom = s_pass(m, t, s, midBottom, t1, 1);
+                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                        StackE e;
+                        memset(&e, 0, sizeof e);
+                        e.t1 = up[t1]; e.direction = upChild + 1; e.needsUpdating = needsUpdating; e.passed = needsUpdating ? midBottom : lref_null();
+                        e.distance = dist[t1]; e.lastLK = midProb; e.failedPasses = failedPasses; e.removed = removed1; e.removedScratch = rs;
+                        e.markK = s->topK; e.markP = s->topP;
+                        stack[sp_n++] = e;
+                    }
+                } else { /* t1 is the root (:7406-7429) */
+                    LRef vUp = lref_null();
+                    if (needsUpdating) {
+                        vUp = s_root_vector(m, t, s, passed, distance, 0);
+                        if (n_mut(t, otherChild)) vUp = s_pass(m, t, s, vUp, otherChild, 0);
+                    }
+                    LRef removed1 = removed;
+                    int rs = E.removedScratch;
+                    if (n_mut(t, otherChild)) { removed1 = s_pass(m, t, s, removed, otherChild, 0); rs = 1; }
+                    if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                    StackE e;
+                    memset(&e, 0, sizeof e);
+                    e.t1 = otherChild; e.direction = 0; e.needsUpdating = needsUpdating; e.passed = vUp;
+                    e.distance = dist[otherChild]; e.lastLK = midProb; e.failedPasses = failedPasses; e.removed = removed1; e.removedScratch = rs;
+                    e.markK = s->topK; e.markP = s->topP;
+                    stack[sp_n++] = e;
+                }
+            }
+        }
+    }
+done:
+    free(stack);
+    return rc;
+#undef CH
+}
+
+/* the per-node body of startTopologyUpdatesParallel (:9619-9711) */
+void or_search_node(const OrModel *m, const OrTree *t, const OrSearchParams *sp, int node, Scratch *s, OrSearchResult *r) {
+    memset(r, 0, sizeof *r);
+    r->placement = -1;
+    r->bestNode = -1;
+    r->status = 1;
+    if (t->up[node] < 0) return;
+    s->topK = s->topP = 0;
+    s->overflow = 0;
+    const int parent = t->up[node];
+    const int child = (t->child0[parent] == node) ? 0 : 1;
+    LRef vectUp = child == 0 ? tree_list(t, 1, parent) : tree_list(t, 2, parent);
+    if (n_mut(t, node)) vectUp = s_pass(m, t, s, vectUp, node, 0);
+    const double bestCurrenBLen = t->dist[node];
+    LRef own = tree_list(t, 0, node);
+    const double bestCurrentLK = or_append(m, vectUp.k, vectUp.p, own.k, own.p, t->isTip[node], bestCurrenBLen);
+    r->bestCurrentLK = bestCurrentLK;
+    if (!(bestCurrentLK < sp->thresholdTopologyPlacement || t->dist[node] != 0.0)) return;
+    Phase2 ph;
+    memset(&ph, 0, sizeof ph);
+    int phase1 = 0;
+    s->topK = s->topP = 0;
+    int rc = find_best_parent_topology(m, t, sp, s, parent, child, bestCurrentLK, bestCurrenBLen, &ph, &phase1);
+    r->phase1 = phase1;
+    r->status = rc;
+    if (rc != 0) return;
+    r->bestNode = ph.bestNode;
+    r->bestScore = ph.bestScore;
+    r->bLenTop = ph.bTop;
+    r->bLenBottom = ph.bBottom;
+    r->bLenAppend = ph.bAppend;
+    if (ph.bestScore + sp->thresholdTopologyPlacement > bestCurrentLK) { /* :9681-9702 */
+        int updated = 1, topNode = t->up[node];
+        if (ph.bestNode == topNode) updated = 0;
+        while (t->dist[topNode] == 0.0 && t->up[topNode] >= 0) topNode = t->up[topNode];
+        if (ph.bestNode == topNode && ph.bBottom == 0.0) updated = 0;
+        int sibling = child == 0 ? t->child1[parent] : t->child0[parent];
+        if (ph.bestNode == sibling) updated = 0;
+        if (t->up[ph.bestNode] == sibling && ph.bTop == 0.0) updated = 0;
+        if (updated) {
+            r->improvement = ph.bestScore - bestCurrentLK;
+            r->placement = ph.bestNode;
+        }
+    }
+}
+
+void or_search_batch(const OrModel *m, const OrTree *t, const OrSearchParams *sp, int64_t n, const int32_t *nodes,
+                     int64_t scratchKeys, int32_t lazyMode, OrSearchResult *out) {
+    LazyTot lazy;
+    memset(&lazy, 0, sizeof lazy);
+    lazy.node[0] = lazy.node[1] = -1;
+    if (t->child0[t->root] >= 0) {
+        int ch[2] = {t->child0[t->root], t->child1[t->root]};
+        for (int i = 0; i < 2; i++)
+            if (t->dist[ch[i]] == 0.0 && t->keyStart[3 * (int64_t)t->nNodes + ch[i]] < 0) lazy.node[i] = ch[i];
+    }
+    if (lazyMode == 1) { /* pre-fill */
+        Scratch s0;
+        memset(&s0, 0, sizeof s0);
+        s0.capK = (size_t)scratchKeys; s0.capP = 6 * s0.capK;
+        s0.key = (uint32_t *)malloc(sizeof(uint32_t) * s0.capK);
+        s0.pay = (double *)malloc(sizeof(double) * s0.capP);
+        s0.lazy = &lazy;
+        for (int i = 0; i < 2; i++)
+            if (lazy.node[i] >= 0) {
+                int c = lazy.node[i];
+                LRef vectUp = (c == t->child0[t->root]) ? tree_list(t, 1, t->root) : tree_list(t, 2, t->root);
+                if (n_mut(t, c)) vectUp = s_pass(m, t, &s0, vectUp, c, 0);
+                if (vectUp.k) lazy_fill(m, t, &s0, c, vectUp);
+            }
+        free(s0.key);
+        free(s0.pay);
+    }
+#pragma omp parallel if (lazyMode == 1)
+    {
+        Scratch s;
+        memset(&s, 0, sizeof s);
+        s.capK = (size_t)scratchKeys;
+        s.capP = 6 * s.capK;
+        s.capA = s.capK;
+        s.key = (uint32_t *)malloc(sizeof(uint32_t) * s.capK);
+        s.pay = (double *)malloc(sizeof(double) * s.capP);
+        s.ais = (double *)malloc(sizeof(double) * s.capA);
+        s.lazy = &lazy;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t i = 0; i < n; i++) or_search_node(m, t, sp, nodes[i], &s, &out[i]);
+        free(s.key);
+        free(s.pay);
+        free(s.ais);
+    }
+    for (int i = 0; i < 2; i++) {
+        free(lazy.key[i]);
+        free(lazy.pay[i]);
+    }
 }

@@ -33,6 +33,31 @@ class OrModel(C.Structure):
     ]
 
 
+class OrTree(C.Structure):
+    _fields_ = [("nNodes", C.c_int32), ("root", C.c_int32), ("up", C.c_void_p), ("child0", C.c_void_p), ("child1", C.c_void_p),
+                ("dist", C.c_void_p), ("isTip", C.c_void_p), ("mutStart", C.c_void_p), ("mut", C.c_void_p), ("key", C.c_void_p),
+                ("pay", C.c_void_p), ("keyStart", C.c_void_p), ("payStart", C.c_void_p), ("nkeys", C.c_void_p)]
+
+
+class OrSearchParams(C.Structure):
+    _fields_ = [("strictTopologyStopRules", C.c_int32), ("allowedFailsTopology", C.c_int32),
+                ("deeperSearchForLongBranches", C.c_int32), ("reserved", C.c_int32),
+                ("thresholdLogLKtopology", C.c_double), ("thresholdTopologyPlacement", C.c_double),
+                ("thresholdLogLKoptimizationTopology", C.c_double), ("thresholdLogLKconsecutivePlacement", C.c_double),
+                ("effectivelyNon0BLen", C.c_double), ("BLenThresholdDeeperSearch", C.c_double), ("defaultBLen", C.c_double)]
+
+
+class OrSearchResult(C.Structure):
+    _fields_ = [("placement", C.c_int32), ("bestNode", C.c_int32), ("status", C.c_int32), ("phase1", C.c_int32),
+                ("improvement", C.c_double), ("bestCurrentLK", C.c_double), ("bestScore", C.c_double), ("bLenTop", C.c_double),
+                ("bLenBottom", C.c_double), ("bLenAppend", C.c_double)]
+
+
+SEARCH_RESULT_DTYPE = np.dtype([("placement", np.int32), ("bestNode", np.int32), ("status", np.int32), ("phase1", np.int32),
+                                ("improvement", np.float64), ("bestCurrentLK", np.float64), ("bestScore", np.float64),
+                                ("bLenTop", np.float64), ("bLenBottom", np.float64), ("bLenAppend", np.float64)])
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -70,6 +95,8 @@ def lib():
         L.or_blen_batch.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 5
         L.or_differ_batch.restype = None
         L.or_differ_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 3
+        L.or_search_batch.restype = None
+        L.or_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         L.or_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -218,6 +245,30 @@ class Oracle:
         idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
         out = np.zeros(n, np.uint8)
         self.L.or_differ_batch(self.mp, _p(pl.key), _p(pl.pay), _p(pl.key_start), _p(pl.pay_start), n, _p(idx1), _p(idx2), _p(out))
+        return out
+
+    def search_batch(self, tree: dict, lists, params: dict, nodes, scratch_keys: int = 1 << 20, lazy_mode: int = 1):
+        """tree: host arrays up/child0/child1 (int32, -1 = none), dist, isTip, root, optional mutStart/mut;
+        lists: PackedLists with list id = family*nNodes + node.  Returns a structured array (SEARCH_RESULT_DTYPE).
+        lazy_mode 0: the reference's order-dependent lazy probVectTotUp fill (:7198-7200), single thread, `nodes` in the
+        reference's order; lazy_mode 1: pre-filled, all host cores (the semantics of the device path)."""
+        n = len(tree["up"])
+        keep = {k: np.ascontiguousarray(tree[k], dt) for k, dt in (("up", np.int32), ("child0", np.int32), ("child1", np.int32),
+                                                                   ("dist", np.float64), ("isTip", np.uint8))}
+        t = OrTree()
+        t.nNodes, t.root = n, int(tree["root"])
+        t.up, t.child0, t.child1, t.dist, t.isTip = (_p(keep[k]) for k in ("up", "child0", "child1", "dist", "isTip"))
+        if tree.get("mutStart") is not None:
+            keep["mutStart"] = np.ascontiguousarray(tree["mutStart"], np.int32)
+            keep["mut"] = np.ascontiguousarray(tree["mut"], np.int32)
+            t.mutStart, t.mut = _p(keep["mutStart"]), _p(keep["mut"])
+        t.key, t.pay, t.keyStart, t.payStart, t.nkeys = _p(lists.key), _p(lists.pay), _p(lists.key_start), _p(lists.pay_start), _p(lists.nkeys)
+        sp = OrSearchParams()
+        for k, v in params.items():
+            setattr(sp, k, v)
+        nodes = np.ascontiguousarray(nodes, np.int32)
+        out = np.zeros(len(nodes), dtype=SEARCH_RESULT_DTYPE)
+        self.L.or_search_batch(self.mp, C.addressof(t), C.addressof(sp), len(nodes), _p(nodes), int(scratch_keys), int(lazy_mode), _p(out))
         return out
 
     def num_threads(self):
