@@ -117,6 +117,51 @@ int maple_lists_copy(maple_ctx* ctx, int64_t n, const uint32_t* src_key, const d
                      const int64_t* src_pay_start, const int32_t* nkeys, const int32_t* npay, uint32_t* dst_key, double* dst_pay,
                      const int64_t* dst_key_start, const int64_t* dst_pay_start, void* stream);
 
+/* ---- device-resident SPR search: the seam the reference ships across its process boundary ----------------
+ * startTopologyUpdatesParallel(inputTuple) (:9580-9716): on a frozen tree, for every listed node run
+ * appendProbNode(current placement) (:9646) and findBestParentTopology (:6817) and report the proposal. */
+
+/* Stop rules / thresholds of the input tuple and the module globals a forked worker inherits. */
+typedef struct {
+    int32_t strictTopologyStopRules;    /* inputTuple[3] */
+    int32_t allowedFailsTopology;       /* inputTuple[4] */
+    int32_t deeperSearchForLongBranches; /* global, --deeperSearchForLongBranches */
+    int32_t reserved;
+    double thresholdLogLKtopology;      /* inputTuple[5] */
+    double thresholdTopologyPlacement;  /* inputTuple[6] */
+    double thresholdLogLKoptimizationTopology; /* global; adaptive in the main process (:11770-11773) */
+    double thresholdLogLKconsecutivePlacement; /* global (:63) */
+    double effectivelyNon0BLen;         /* 1/(10 lRef) (:3615) */
+    double BLenThresholdDeeperSearch;   /* (log lRef + 5)/lRef (:3624) */
+    double defaultBLen;                 /* --defaultBLen (:88) */
+} maple_search_params;
+
+/* One record per searched node. */
+typedef struct {
+    int32_t placement;   /* proposedMoves entry: re-attachment node, or -1 for no proposal */
+    int32_t bestNode;    /* findBestParentTopology's bestNode (-1: search not run) */
+    int32_t status;      /* 0 searched; 1 not needed (:9674); 2 aborted where the reference's try/except swallows an
+                            exception (:9703); 3 per-search scratch exhausted (re-run with more scratch) */
+    int32_t phase1;      /* SPR candidate placements scored by the phase-1 appendProbNode calls (:7011, :7223) */
+    double improvement;  /* bestLKdiff - bestCurrentLK (:9701) */
+    double bestCurrentLK, bestScore, bLenTop, bLenBottom, bLenAppend; /* bestBranchLengths (:7638) */
+} maple_search_result;
+
+/* Tree arrays (DEVICE pointers, caller-owned; node = int index like the reference's Tree, :331-376):
+ * up/child0/child1 with -1 for none, dist, isTip = no children and no minorSequences, optional MAT mutation lists
+ * as CSR (mutStart[nNodes+1], mut = triples pos1,upNuc,downNuc) or NULL, and nkeys[4*nNodes] = entries per list.
+ * The bound arena must hold 4*nNodes lists: id = family*nNodes + node, family 0 probVect, 1 probVectUpRight,
+ * 2 probVectUpLeft, 3 probVectTotUp. */
+int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t* up, const int32_t* child0, const int32_t* child1,
+                    const double* dist, const uint8_t* isTip, const int32_t* mutStart, const int32_t* mut, const int32_t* nkeys);
+
+/* Search the n listed nodes (DEVICE int32) on the frozen tree; out = n records (DEVICE).  scratch_keys_per_search:
+ * entries of per-search list scratch (0 = default 8192); max_concurrent_searches caps the resident threads (0 = fill
+ * the GPU).  Deterministic: a node's record does not depend on which other nodes are in the batch. */
+int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t n, const int32_t* nodes,
+                           maple_search_result* out, int32_t scratch_keys_per_search, int32_t max_concurrent_searches,
+                           void* stream);
+
 /* Kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 int64_t maple_launch_count(const maple_ctx* ctx);
 

@@ -28,8 +28,22 @@ SIGNATURES = {
     "maple_vectors_differ_batch": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "maple_root_vector_batch": (C.c_int, [_P, _I64] + [_P] * 9 + [_I32, _P]),
     "maple_lists_copy": (C.c_int, [_P, _I64] + [_P] * 10 + [_P]),
+    "maple_tree_bind": (C.c_int, [_P, _I32, _I32] + [_P] * 8),
+    "maple_spr_search_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P]),
     "maple_launch_count": (_I64, [_P]),
 }
+
+class SearchParams(C.Structure):
+    """maple_search_params (include/maple_b200.h)."""
+    _fields_ = [("strictTopologyStopRules", _I32), ("allowedFailsTopology", _I32), ("deeperSearchForLongBranches", _I32),
+                ("reserved", _I32), ("thresholdLogLKtopology", _D), ("thresholdTopologyPlacement", _D),
+                ("thresholdLogLKoptimizationTopology", _D), ("thresholdLogLKconsecutivePlacement", _D),
+                ("effectivelyNon0BLen", _D), ("BLenThresholdDeeperSearch", _D), ("defaultBLen", _D)]
+
+
+# maple_search_result as a numpy record
+SEARCH_RESULT_FIELDS = [("placement", "i4"), ("bestNode", "i4"), ("status", "i4"), ("phase1", "i4"), ("improvement", "f8"),
+                        ("bestCurrentLK", "f8"), ("bestScore", "f8"), ("bLenTop", "f8"), ("bLenBottom", "f8"), ("bLenAppend", "f8")]
 
 _lib = None
 

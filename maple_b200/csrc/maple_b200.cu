@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include "../../include/maple_b200.h"
 #include "likelihood.cuh"
+#include "search.cuh"
 
 using namespace maple;
 
@@ -25,6 +26,13 @@ struct maple_ctx {
     int64_t nLists = 0;
     int64_t launches = 0;
     int numSMs = 148;
+    // tree bound for the search (device pointers, caller-owned)
+    DevTree tree{};
+    bool haveTree = false;
+    // per-thread scratch of the search kernel (owned by the context)
+    void* searchScratch = nullptr;
+    size_t searchScratchBytes = 0;
+    unsigned long long* searchCounter = nullptr;
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
@@ -179,6 +187,32 @@ __global__ void __launch_bounds__(256) k_lists_copy(int64_t n, const uint32_t* _
     }
 }
 
+constexpr int kSearchThreads = 64;
+
+// one SPR search per thread; threads pull the next pruned node from a global counter (searches differ ~10x in length)
+__global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+                                                               const __grid_constant__ SearchParams sp, int64_t n,
+                                                               const int32_t* __restrict__ nodes, SearchResult* __restrict__ out, uint32_t* scrKey,
+                                                               double* scrPay, double* scrAis, StackE* scrStack, unsigned capK, unsigned capP,
+                                                               unsigned capA, int stackCap, unsigned long long* counter) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    ScratchD s;
+    s.key = scrKey + tid * capK;
+    s.pay = scrPay + tid * capP;
+    s.ais = scrAis + tid * capA;
+    s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
+    StackE* stack = scrStack + tid * (size_t)stackCap;
+    for (;;) {
+        const unsigned long long i = atomicAdd(counter, 1ULL);
+        if (i >= (unsigned long long)n) break;
+        SearchResult r;
+        search_node(sm, T, sp, nodes[i], s, stack, stackCap, r);
+        out[i] = r;
+    }
+}
+
 // grid: whole waves of CTAs (multiples of the SM count), capped by the work
 static int grid_for(const maple_ctx* ctx, int64_t n, int ctasPerSM) {
     int64_t need = (n + kThreads - 1) / kThreads;
@@ -233,6 +267,8 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->dCumRate);
     cudaFree(ctx->dCumErr);
     cudaFree(ctx->devStage);
+    cudaFree(ctx->searchScratch);
+    cudaFree(ctx->searchCounter);
     delete ctx;
     return MAPLE_OK;
 }
@@ -431,6 +467,68 @@ int maple_lists_copy(maple_ctx* ctx, int64_t n, const uint32_t* src_key, const d
     k_lists_copy<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(n, src_key, src_pay, src_key_start, src_pay_start,
                                                                                       nkeys, npay, dst_key, dst_pay, dst_key_start,
                                                                                       dst_pay_start);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t* up, const int32_t* child0, const int32_t* child1,
+                    const double* dist, const uint8_t* isTip, const int32_t* mutStart, const int32_t* mut, const int32_t* nkeys) {
+    if (!ctx || nNodes <= 0 || root < 0 || root >= nNodes || !up || !child0 || !child1 || !dist || !isTip || !nkeys) return MAPLE_E_ARG;
+    if (!ctx->haveLists || ctx->nLists < 4 * (int64_t)nNodes) {
+        ctx->err = "maple_tree_bind: bind an arena with 4*nNodes lists first (list id = family*nNodes + node)";
+        return MAPLE_E_STATE;
+    }
+    DevTree& t = ctx->tree;
+    t.nNodes = nNodes; t.root = root; t.up = up; t.child0 = child0; t.child1 = child1; t.dist = dist; t.isTip = isTip;
+    t.mutStart = mutStart; t.mut = mut; t.nkeys = nkeys;
+    ctx->haveTree = true;
+    return MAPLE_OK;
+}
+
+int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t n, const int32_t* nodes, maple_search_result* out,
+                           int32_t scratch_keys_per_search, int32_t max_concurrent_searches, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!ctx->haveTree) { ctx->err = "maple_spr_search_batch: no tree bound (maple_tree_bind)"; return MAPLE_E_STATE; }
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !p || !nodes || !out) return MAPLE_E_ARG;
+    static_assert(sizeof(maple_search_result) == sizeof(SearchResult), "result record layout");
+    static_assert(sizeof(maple_search_params) == sizeof(SearchParams), "params layout");
+    CK(cudaSetDevice(ctx->device));
+    SearchParams sp;
+    memcpy(&sp, p, sizeof sp);
+    DevTree T = ctx->tree;
+    T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
+    const unsigned capK = (unsigned)((scratch_keys_per_search > 0 ? scratch_keys_per_search : 8192) + 3) & ~3u;
+    const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
+    const int stackCap = 512;
+    int blocksPerSM = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
+    if (blocksPerSM < 1) blocksPerSM = 1;
+    int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
+    if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches;
+    if (threads > n) threads = n;
+    int blocks = (int)((threads + kSearchThreads - 1) / kSearchThreads);
+    threads = (int64_t)blocks * kSearchThreads;
+    const size_t perThread = (size_t)capK * 4 + (size_t)capP * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
+    const size_t need = perThread * (size_t)threads + 256;
+    if (need > ctx->searchScratchBytes) {
+        cudaFree(ctx->searchScratch);
+        ctx->searchScratch = nullptr;
+        ctx->searchScratchBytes = 0;
+        CK(cudaMalloc(&ctx->searchScratch, need));
+        ctx->searchScratchBytes = need;
+    }
+    if (!ctx->searchCounter) CK(cudaMalloc((void**)&ctx->searchCounter, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    char* base = (char*)ctx->searchScratch;
+    double* scrPay = (double*)base;
+    double* scrAis = (double*)(base + (size_t)threads * capP * 8);
+    StackE* scrStack = (StackE*)(base + (size_t)threads * (capP + capA) * 8);
+    uint32_t* scrKey = (uint32_t*)(base + (size_t)threads * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+    k_spr_search<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay, scrAis,
+                                                                     scrStack, capK, capP, capA, stackCap, ctx->searchCounter);
     ctx->launches++;
     CK(cudaGetLastError());
     return MAPLE_OK;

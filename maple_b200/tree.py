@@ -227,6 +227,55 @@ class DeviceTree:
                             torch.cat([isTip[b], isTip[a]]), True)
         return A
 
+    # ------------------------------------------------------------------ construction from existing lists
+    @classmethod
+    def from_lists(cls, engine: MapleEngine, up, child0, child1, dist, root, isTip, lists: PackedLists, mutStart=None, mut=None,
+                   numMinor=None):
+        """A tree whose four list families already exist (list id = family*nNodes + node), e.g. a snapshot of the
+        reference's Tree.  mutStart/mut: MAT mutation lists (mutations[node], :336) in CSR form."""
+        t = cls(engine, up, child0, child1, dist, root, isTip=isTip, numMinor=numMinor)
+        assert len(lists) == 4 * t.n
+        t.arena = ListArena(engine, 4 * t.n, int(lists.key.size) + 64, int(lists.pay.size) + 64)
+        t.arena.store_packed(np.arange(4 * t.n, dtype=np.int64), lists)
+        if mutStart is not None and int(np.asarray(mutStart)[-1]) > 0:
+            t.mutStart = np.ascontiguousarray(mutStart, np.int32)
+            t.mut = np.ascontiguousarray(mut, np.int32).reshape(-1, 3)
+        return t
+
+    # ------------------------------------------------------------------ SPR search round (startTopologyUpdatesParallel, :9580)
+    def prepare_search(self):
+        """Fill probVectTotUp of zero-length children of the root (the reference does it lazily and order-dependently
+        inside the round, :7198-7200), then hand the tree arrays to the search kernel."""
+        eng, n, dev, A = self.eng, self.n, self.eng.device, self.arena
+        root = self.root
+        if self.child0[root] >= 0:
+            for c, fam in ((int(self.child0[root]), FAM_UPRIGHT), (int(self.child1[root]), FAM_UPLEFT)):
+                if self.dist[c] == 0.0 and int(A.key_start[FAM_TOTUP * n + c].item()) < 0 and int(A.key_start[fam * n + root].item()) >= 0:
+                    r = eng.merge_batch([fam * n + root], [0.0], [0], [FAM_LOWER * n + c], [0.0], [0], [capi.MAPLE_MERGE_UPDOWN])
+                    A.store(torch.as_tensor([FAM_TOTUP * n + c], dtype=torch.int64, device=dev), r.key, r.pay, r.key_start, r.pay_start,
+                            r.nkeys, r.npay, r.status)
+        mutStart = getattr(self, "mutStart", None)
+        self._d_mutStart = None if mutStart is None else torch.from_numpy(mutStart).to(dev)
+        self._d_mut = None if mutStart is None else torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
+        rc = eng.lib.maple_tree_bind(eng.ctx, n, root, _dp(self.d_up), _dp(self.d_child0), _dp(self.d_child1), _dp(self.d_dist),
+                                     _dp(self.d_isTip), _dp(self._d_mutStart), _dp(self._d_mut), _dp(A.nkeys))
+        capi.check(eng.ctx, rc, "maple_tree_bind")
+
+    def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0):
+        """Run the searches of the listed nodes; returns a device tensor of raw records [n, 64 bytes] viewed as uint8
+        and a helper to read it as a numpy record array."""
+        eng, dev = self.eng, self.eng.device
+        nodes = torch.as_tensor(nodes, dtype=torch.int32, device=dev).contiguous()
+        out = torch.zeros((nodes.numel(), 64), dtype=torch.uint8, device=dev)
+        rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), nodes.numel(), _dp(nodes), _dp(out), int(scratch_keys),
+                                            int(max_concurrent), eng._stream())
+        capi.check(eng.ctx, rc, "maple_spr_search_batch")
+        return out
+
+    @staticmethod
+    def search_records(out: torch.Tensor) -> np.ndarray:
+        return out.cpu().numpy().view(np.dtype(capi.SEARCH_RESULT_FIELDS)).reshape(-1)
+
     def lists_of(self, node: int):
         A = self.arena
         return [A.get(self.lid(f, node)) for f in range(4)]

@@ -1116,7 +1116,7 @@ static void lazy_fill(const OrModel *m, const OrTree *t, Scratch *s, int node, L
 
 static int sc_reserve(Scratch *s, size_t nk) {
     size_t k = (nk + 3) & ~(size_t)3;
-    if (s->topK + k > s->capK || s->topP + 6 * k > s->capP) { s->overflow = 1; return 0; }
+    if (s->topK + k > s->capK || s->topP + 6 * k > s->capP) { s->overflow = 3; return 0; }
     return 1;
 }
 
@@ -1139,6 +1139,7 @@ static LRef s_pass(const OrModel *m, const OrTree *t, Scratch *s, LRef v, int no
 }
 
 static LRef s_merge(const OrModel *m, Scratch *s, LRef a, double b1, int t1, LRef b, double b2, int t2, int upDown) {
+    if (!a.k || !b.k) { if (!s->overflow) s->overflow = 2; return lref_null(); } /* the reference would raise -> search aborted */
     if (!sc_reserve(s, (size_t)a.nk + b.nk)) return lref_null();
     int32_t nk = 0, np = 0;
     int st = or_merge(m, a.k, a.p, b1, t1, b.k, b.p, b2, t2, upDown ? 1 : 0, 0, 0, s->key + s->topK, s->pay + s->topP, &nk, &np, NULL);
@@ -1179,8 +1180,9 @@ static LRef s_copy(Scratch *s, LRef v) {
 }
 
 static double s_blen(const OrModel *m, Scratch *s, LRef P, LRef C, int fromTipC) {
+    if (!P.k || !C.k) { if (!s->overflow) s->overflow = 2; return 0.0; }
     size_t need = (size_t)P.nk + C.nk + 1;
-    if (need > s->capA) { s->overflow = 1; return 0.0; }
+    if (need > s->capA) { s->overflow = 3; return 0.0; }
     double out = 0.0;
     or_blen(m, P.k, P.p, C.k, C.p, fromTipC, s->ais, &out); /* python False and 0.0 are both "zero length" to the callers */
     return out;
@@ -1190,6 +1192,7 @@ static double s_blen(const OrModel *m, Scratch *s, LRef P, LRef C, int fromTipC)
 static int eval_placement(const OrModel *m, const OrSearchParams *sp, Scratch *s, LRef midTot, LRef downVect, LRef upVect,
                           double distance, LRef removed, int isRemovedTip, int fromTip1, double *cost, double *bBottom,
                           double *bTop, double *bAppend) {
+    if (!midTot.k || !downVect.k || !upVect.k) return 1;
     size_t mk = s->topK, mp = s->topP;
     double bestAppending = s_blen(m, s, midTot, removed, isRemovedTip);
     LRef midLower = s_merge(m, s, downVect, distance / 2, fromTip1, removed, bestAppending, isRemovedTip, 0);
@@ -1308,7 +1311,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
         }
         ph->bTop = 0.0; ph->bBottom = dist[bestNodeInit]; ph->bAppend = removedBLen;
     }
-    if (s->overflow) { rc = 3; goto done; }
+    if (s->overflow) { rc = s->overflow; goto done; }
 
     while (sp_n > 0) {
         StackE E = stack[--sp_n];
@@ -1323,7 +1326,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                 LRef midTot;
                 if (needsUpdating) {
                     midTot = s_merge(m, s, passed, distance / 2, 0, tree_list(t, 0, t1), distance / 2, t->isTip[t1], 1);
-                    if (s->overflow) { rc = 3; goto done; }
+                    if (s->overflow) { rc = s->overflow; goto done; }
                     if (!midTot.k) continue;
                     LRef stored = totup_list(t, s, t1);
                     if (!or_differ(m, midTot.k, midTot.p, stored.k, stored.p)) needsUpdating = 0;
@@ -1339,7 +1342,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                     if (n_mut(t, t1)) vectUp = s_pass(m, t, s, vectUp, t1, 0);
                     double bB, bT, bA;
                     if (eval_placement(m, sp, s, midTot, midBottom, vectUp, distance, removed, isRemovedTip, t->isTip[t1], &midProb, &bB, &bT, &bA)) {
-                        rc = s->overflow ? 3 : 2;
+                        rc = s->overflow ? s->overflow : 2;
                         goto done;
                     }
                 } else {
@@ -1357,7 +1360,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                         downV = tree_list(t, 0, t1); dd = dist[t1]; mt = totup_list(t, s, t1);
                     }
                     if (phase2_entry(m, sp, s, t1, mt, downV, upV, dd, removed, isRemovedTip, t->isTip[t1], ph)) {
-                        rc = s->overflow ? 3 : 2;
+                        rc = s->overflow ? s->overflow : 2;
                         goto done;
                     }
                 }
@@ -1382,14 +1385,14 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                         LRef otherPV = tree_list(t, 0, otherChild);
                         if (n_mut(t, otherChild)) otherPV = s_pass(m, t, s, otherPV, otherChild, 1);
                         vUp = s_merge(m, s, passed, distance, 0, otherPV, dist[otherChild], t->isTip[otherChild], 1);
-                        if (s->overflow) { rc = 3; goto done; }
+                        if (s->overflow) { rc = s->overflow; goto done; }
                     } else vUp = which == 0 ? tree_list(t, 1, t1) : tree_list(t, 2, t1);
                     if (vUp.k) {
                         LRef removed1 = removed;
                         int rs = E.removedScratch;
                         if (n_mut(t, child1)) { removed1 = s_pass(m, t, s, removed, child1, 0); rs = 1; }
                         if (needsUpdating && n_mut(t, child1)) vUp = s_pass(m, t, s, vUp, child1, 0);
-                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = s->overflow ? s->overflow : 3; goto done; }
                         StackE e;
                         memset(&e, 0, sizeof e);
                         e.t1 = child1; e.direction = 0; e.needsUpdating = needsUpdating; e.passed = needsUpdating ? vUp : lref_null();
@@ -1408,12 +1411,12 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                     LRef otherPV = tree_list(t, 0, otherChild);
                     if (n_mut(t, otherChild)) otherPV = s_pass(m, t, s, otherPV, otherChild, 1);
                     midBottom = s_merge(m, s, passed, distance, 0, otherPV, dist[otherChild], t->isTip[otherChild], 0);
-                    if (s->overflow) { rc = 3; goto done; }
+                    if (s->overflow) { rc = s->overflow; goto done; }
                     if (!midBottom.k) continue;
                     vectUp = (t1 == t->child0[up[t1]]) ? tree_list(t, 1, up[t1]) : tree_list(t, 2, up[t1]);
                     if (n_mut(t, t1)) vectUp = s_pass(m, t, s, vectUp, t1, 0);
                     midTot = s_merge(m, s, vectUp, dist[t1] / 2, 0, midBottom, dist[t1] / 2, 0, 1);
-                    if (s->overflow) { rc = 3; goto done; }
+                    if (s->overflow) { rc = s->overflow; goto done; }
                     if (!totup_list(t, s, t1).k) lazy_fill(m, t, s, t1, vectUp); /* :7198-7200 */
                     if (!midTot.k) continue;
                     LRef stored = totup_list(t, s, t1);
@@ -1428,7 +1431,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                     }
                     double bB, bT, bA;
                     if (eval_placement(m, sp, s, midTot, midBottom, vectUp, dist[t1], removed, isRemovedTip, 0, &midProb, &bB, &bT, &bA)) {
-                        rc = s->overflow ? 3 : 2;
+                        rc = s->overflow ? s->overflow : 2;
                         goto done;
                     }
                 } else {
@@ -1445,7 +1448,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                         downV = tree_list(t, 0, t1); mt = totup_list(t, s, t1);
                     }
                     if (phase2_entry(m, sp, s, t1, mt, downV, upV, dist[t1], removed, isRemovedTip, t->isTip[t1], ph)) {
-                        rc = s->overflow ? 3 : 2;
+                        rc = s->overflow ? s->overflow : 2;
                         goto done;
                     }
                 }
@@ -1466,7 +1469,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                     if (needsUpdating) {
                         if (n_mut(t, t1)) vectUpUp = s_pass(m, t, s, vectUpUp, t1, 0);
                         vUp = s_merge(m, s, vectUpUp, dist[t1], 0, passed, distance, 0, 1);
-                        if (s->overflow) { rc = 3; goto done; }
+                        if (s->overflow) { rc = s->overflow; goto done; }
                     } else vUp = direction == 1 ? tree_list(t, 2, t1) : tree_list(t, 1, t1);
                     if (!vUp.k) continue;
                     {
@@ -1474,7 +1477,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                         int rs = E.removedScratch;
                         if (n_mut(t, otherChild)) { removed1 = s_pass(m, t, s, removed, otherChild, 0); rs = 1; }
                         if (needsUpdating && n_mut(t, otherChild)) vUp = s_pass(m, t, s, vUp, otherChild, 0);
-                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = s->overflow ? s->overflow : 3; goto done; }
                         StackE e;
                         memset(&e, 0, sizeof e);
                         e.t1 = otherChild; e.direction = 0; e.needsUpdating = needsUpdating; e.passed = needsUpdating ? vUp : lref_null();
@@ -1486,7 +1489,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                         LRef otherPV = tree_list(t, 0, otherChild);
                         if (n_mut(t, otherChild)) otherPV = s_pass(m, t, s, otherPV, otherChild, 1);
                         midBottom = s_merge(m, s, passed, distance, 0, otherPV, dist[otherChild], t->isTip[otherChild], 0);
-                        if (s->overflow) { rc = 3; goto done; }
+                        if (s->overflow) { rc = s->overflow; goto done; }
                         if (!midBottom.k) continue;
                     }
                     {
@@ -1494,7 +1497,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                         int rs = E.removedScratch;
                         if (n_mut(t, t1)) { removed1 = s_pass(m, t, s, removed, t1, 1); rs = 1; }
                         if (needsUpdating && n_mut(t, t1)) midBottom = s_pass(m, t, s, midBottom, t1, 1);
-                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                        if (sp_n >= OR_STACK_MAX || s->overflow) { rc = s->overflow ? s->overflow : 3; goto done; }
                         StackE e;
                         memset(&e, 0, sizeof e);
                         e.t1 = up[t1]; e.direction = upChild + 1; e.needsUpdating = needsUpdating; e.passed = needsUpdating ? midBottom : lref_null();
@@ -1511,7 +1514,7 @@ static int find_best_parent_topology(const OrModel *m, const OrTree *t, const Or
                     LRef removed1 = removed;
                     int rs = E.removedScratch;
                     if (n_mut(t, otherChild)) { removed1 = s_pass(m, t, s, removed, otherChild, 0); rs = 1; }
-                    if (sp_n >= OR_STACK_MAX || s->overflow) { rc = 3; goto done; }
+                    if (sp_n >= OR_STACK_MAX || s->overflow) { rc = s->overflow ? s->overflow : 3; goto done; }
                     StackE e;
                     memset(&e, 0, sizeof e);
                     e.t1 = otherChild; e.direction = 0; e.needsUpdating = needsUpdating; e.passed = vUp;
@@ -1543,6 +1546,7 @@ void or_search_node(const OrModel *m, const OrTree *t, const OrSearchParams *sp,
     if (n_mut(t, node)) vectUp = s_pass(m, t, s, vectUp, node, 0);
     const double bestCurrenBLen = t->dist[node];
     LRef own = tree_list(t, 0, node);
+    if (!vectUp.k || !own.k) { r->status = 2; return; }
     const double bestCurrentLK = or_append(m, vectUp.k, vectUp.p, own.k, own.p, t->isTip[node], bestCurrenBLen);
     r->bestCurrentLK = bestCurrentLK;
     if (!(bestCurrentLK < sp->thresholdTopologyPlacement || t->dist[node] != 0.0)) return;

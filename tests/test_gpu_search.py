@@ -1,0 +1,94 @@
+"""Device-resident SPR search against (a) every search the reference ran on its frozen trees (golden fixtures) and
+(b) the CPU oracle's search on synthetic trees -- needs a GPU.
+
+Bar: identical best node, branch lengths, phase-1 candidate counts and proposed moves; scores within 1e-9."""
+import numpy as np
+import pytest
+
+from golden_io import golden_names, load_golden
+from maple_b200.model import MapleModel
+from tree_fixture import search_params as fixture_params, searched_nodes, tree_arrays, tree_lists
+
+pytestmark = pytest.mark.gpu
+
+
+def _capi_params(d):
+    from maple_b200 import capi
+    p = capi.SearchParams()
+    for k, v in d.items():
+        setattr(p, k, v)
+    return p
+
+
+def _compare(rec, ref, nodes):
+    assert np.array_equal(rec["status"], ref["status"]), [(int(n), int(a), int(b)) for n, a, b in zip(nodes, rec["status"], ref["status"]) if a != b][:5]
+    for f in ("placement", "bestNode", "phase1"):
+        assert np.array_equal(rec[f], ref[f]), (f, [(int(n), int(a), int(b)) for n, a, b in zip(nodes, rec[f], ref[f]) if a != b][:5])
+    for f in ("bLenTop", "bLenBottom", "bLenAppend"):
+        assert np.array_equal(rec[f], ref[f]), f
+    for f in ("bestCurrentLK", "bestScore", "improvement"):
+        a, b = rec[f], ref[f]
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        assert np.max(np.abs(a[fin] - b[fin]), initial=0.0) <= 1e-9, f
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_search_vs_reference_goldens(name):
+    from maple_b200.engine import MapleEngine
+    from maple_b200.tree import DeviceTree
+    from oracle.oracle import Oracle
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    eng = MapleEngine(model, 0)
+    ta, lists = tree_arrays(g), tree_lists(g)
+    tree = DeviceTree.from_lists(eng, ta["up"], ta["child0"], ta["child1"], ta["dist"], ta["root"], ta["isTip"], lists,
+                                 ta["mutStart"], ta["mut"], ta["numMinor"])
+    nodes = np.array(searched_nodes(g), np.int32)
+    tree.prepare_search()
+    rec = tree.search_records(tree.spr_search(nodes, _capi_params(fixture_params(g))))
+    # (b) identical to the oracle with the same (pre-filled) probVectTotUp policy
+    ref = Oracle(model).search_batch(ta, lists, fixture_params(g), nodes, lazy_mode=1)
+    _compare(rec, ref, nodes)
+    # (a) identical to the reference wherever its order-dependent lazy fill (:7198-7200) plays no role
+    lazy = Oracle(model).search_batch(ta, lists, fixture_params(g), nodes, lazy_mode=0)
+    same = np.array([a == b for a, b in zip(lazy, ref)])
+    by_node = {int(n): r for n, r in zip(nodes, rec)}
+    t = g["tree"]
+    checked = 0
+    for s in g["searches"]:
+        pruned = t["children"][s["node"]][s["child"]]
+        if not same[list(nodes).index(pruned)]:
+            continue
+        r = by_node[pruned]
+        assert r["status"] == 0 and r["bestNode"] == s["bestNode"] and r["phase1"] == s["phase1"]
+        assert [r["bLenTop"], r["bLenBottom"], r["bLenAppend"]] == [float(x) for x in s["blens"]]
+        assert r["bestScore"] == s["bestScore"] or abs(r["bestScore"] - s["bestScore"]) <= 1e-9
+        checked += 1
+    assert checked >= 0.8 * len(g["searches"])
+
+
+@pytest.mark.parametrize("rv,err,strict", [(False, False, True), (True, False, False), (True, True, False)])
+def test_search_vs_oracle_synthetic(rv, err, strict):
+    import math
+    from maple_b200.engine import MapleEngine
+    from maple_b200.genome_list import pack_lists
+    from maple_b200.search import dirty_nodes, search_params, start_topology_updates_parallel
+    from maple_b200.synthetic import generate
+    from maple_b200.tree import DeviceTree
+    from oracle.oracle import Oracle
+    d = generate(400, lRef=6000, mean_diffs=8.0, rate_variation=rv, error_model=err, site_specific_errors=err, seed=11)
+    eng = MapleEngine(d.model, 0)
+    tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+    tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+    lRef = d.model.lRef
+    p = search_params(lRef, strict, 2 if strict else 4, (6.0 if strict else 14.0) * math.log(lRef))
+    nodes = dirty_nodes(tree)
+    moves, rec = start_topology_updates_parallel(tree, p, nodes)
+    host = tree.arena.to_host()
+    ta = {"up": d.up, "child0": d.child0, "child1": d.child1, "dist": d.dist, "isTip": tree.isTip, "root": d.root}
+    pd = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] != "reserved"}
+    ref = Oracle(d.model).search_batch(ta, host, pd, nodes, lazy_mode=1)
+    _compare(rec, ref, nodes)
+    assert rec["phase1"].sum() > 20 * len(nodes)
+    assert (rec["status"] == 0).sum() > 0.9 * len(nodes)
