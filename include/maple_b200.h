@@ -160,6 +160,7 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
  * the GPU).  Deterministic: a node's record does not depend on which other nodes are in the batch. */
 int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t n, const int32_t* nodes,
                            maple_search_result* out, int32_t scratch_keys_per_search, int32_t max_concurrent_searches,
+                           int64_t* out_cycles /* optional DEVICE int64[n]: SM clock cycles each search took; NULL to skip */,
                            void* stream);
 
 /* Kernel launches issued by this context so far (bench.py reports it as gpu_launches). */

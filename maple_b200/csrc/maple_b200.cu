@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
                                                                const __grid_constant__ SearchParams sp, int64_t n,
                                                                const int32_t* __restrict__ nodes, SearchResult* __restrict__ out, uint32_t* scrKey,
                                                                double* scrPay, double* scrAis, StackE* scrStack, unsigned capK, unsigned capP,
-                                                               unsigned capA, int stackCap, unsigned long long* counter) {
+                                                               unsigned capA, int stackCap, unsigned long long* counter, long long* outCycles) {
     __shared__ DevModel sm;
     stage_model(sm, gm);
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -208,8 +208,10 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
         const unsigned long long i = atomicAdd(counter, 1ULL);
         if (i >= (unsigned long long)n) break;
         SearchResult r;
+        const long long c0 = clock64();
         search_node(sm, T, sp, nodes[i], s, stack, stackCap, r);
         out[i] = r;
+        if (outCycles) outCycles[i] = clock64() - c0;
     }
 }
 
@@ -487,7 +489,7 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
 }
 
 int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t n, const int32_t* nodes, maple_search_result* out,
-                           int32_t scratch_keys_per_search, int32_t max_concurrent_searches, void* stream) {
+                           int32_t scratch_keys_per_search, int32_t max_concurrent_searches, int64_t* out_cycles, void* stream) {
     int rc = ready(ctx);
     if (rc) return rc;
     if (!ctx->haveTree) { ctx->err = "maple_spr_search_batch: no tree bound (maple_tree_bind)"; return MAPLE_E_STATE; }
@@ -528,7 +530,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     StackE* scrStack = (StackE*)(base + (size_t)threads * (capP + capA) * 8);
     uint32_t* scrKey = (uint32_t*)(base + (size_t)threads * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
     k_spr_search<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay, scrAis,
-                                                                     scrStack, capK, capP, capA, stackCap, ctx->searchCounter);
+                                                                     scrStack, capK, capP, capA, stackCap, ctx->searchCounter, (long long*)out_cycles);
     ctx->launches++;
     CK(cudaGetLastError());
     return MAPLE_OK;

@@ -96,7 +96,10 @@ def _depths(up: np.ndarray, root: int, c0, c1) -> np.ndarray:
 
 
 def generate(nSeq: int, lRef: int = 29903, mean_diffs: float = 10.0, rate_variation: bool = False, error_model: bool = False,
-             site_specific_errors: bool = False, seed: int = 1) -> SyntheticData:
+             site_specific_errors: bool = False, seed: int = 1, ml_like_blens: bool = False) -> SyntheticData:
+    """ml_like_blens: replace the simulated branch lengths by (substitutions on the branch)/lRef, i.e. zero for
+    branches without a substitution -- the shape of the trees MAPLE itself estimates (large multifurcations of
+    zero-length branches), instead of the simulator's strictly positive lengths."""
     ref = make_reference(lRef, seed)
     ridx = ref_indices(ref).astype(np.int64)
     pi = np.bincount(ridx, minlength=4) / float(lRef)
@@ -136,6 +139,9 @@ def generate(nSeq: int, lRef: int = 29903, mean_diffs: float = 10.0, rate_variat
                 else:
                     g[int(s)] = new
         genomes[nd] = g
+    if ml_like_blens:
+        dist = nmut.astype(np.float64) / float(lRef)
+        dist[root] = 0.0
     for nd in order:  # internal genomes are no longer needed once their children exist
         if c0[nd] >= 0:
             genomes[nd] = None

@@ -157,14 +157,29 @@ class DeviceTree:
         self.by_depth = [np.nonzero(depth == d)[0].astype(np.int64) for d in range(int(depth.max()) + 1)]
 
     # ------------------------------------------------------------------ reCalculateAllGenomeLists (:6013-6347)
-    def recalculate_all_lists(self, tip_nodes, tip_lists_packed: PackedLists, key_capacity: Optional[int] = None):
+    def recalculate_all_lists(self, tip_nodes, tip_lists_packed: PackedLists, key_capacity: Optional[int] = None, max_restarts: int = 8):
         """Build all four list families on the device from the tip lists.
 
         First pass (post-order, :6031-6216): lower lists by batches of equal node height.
         Root (:6225-6245): rootVector of each child's lower list.  Second pass (pre-order,
         :6247-6345): probVectTotUp / UpRight / UpLeft by batches of equal depth.  Every stored list
         is shortened, as the reference does at :6201, :6267, :6308, :6330 and inside rootVector.
+
+        Inconsistent zero-length branches (mergeVectors returns None, :4753-4758): the reference gives the two
+        branches involved the length oneMutBLen/2 on first set-up (:6181-6183) or re-estimates them (updateBLen);
+        here they get oneMutBLen/2 and the affected pass is redone (lower pass: on the spot; upper pass: restart).
         """
+        for _ in range(max_restarts):
+            if self._recalculate_once(tip_nodes, tip_lists_packed, key_capacity):
+                return self.arena
+        raise capi.MapleError("genome lists still inconsistent after %d restarts" % max_restarts)
+
+    def _bump(self, nodes: torch.Tensor):
+        half = 0.5 / self.eng.model.lRef  # oneMutBLen/2
+        self.d_dist[nodes] = half
+        self.dist[nodes.cpu().numpy()] = half
+
+    def _recalculate_once(self, tip_nodes, tip_lists_packed: PackedLists, key_capacity: Optional[int]) -> bool:
         eng, n, dev = self.eng, self.n, self.eng.device
         nk_tips = int(tip_lists_packed.nkeys.sum())
         cap_k = key_capacity or max(1 << 16, int(nk_tips * 12))
@@ -172,24 +187,33 @@ class DeviceTree:
         A = self.arena
         A.store_packed(np.asarray(tip_nodes, np.int64) + FAM_LOWER * n, tip_lists_packed)
         t64 = lambda a: torch.as_tensor(a, dtype=torch.int64, device=dev)  # noqa: E731
-        dist, isTip = self.d_dist, self.d_isTip
+        isTip = self.d_isTip
         c0, c1 = self.d_child0.long(), self.d_child1.long()
 
         def merge_store(list_ids, i1, b1, t1, i2, b2, t2, updown):
+            """returns the mask of pairs whose merge came back None (those list ids stay None)"""
             r = eng.merge_batch(i1.int(), b1, t1, i2.int(), b2, t2, torch.full((i1.numel(),), 1 if updown else 0, dtype=torch.uint8, device=dev),
                                 shorten=True)
-            if bool((r.status != 0).any().item()):
-                bad = int((r.status != 0).nonzero()[0].item())
-                raise capi.MapleError("inconsistent genome lists (mergeVectors returned None) at list id %d; the reference would "
-                                      "re-estimate zero branch lengths here (:6179-6198), which this builder does not do" % int(list_ids[bad]))
             A.store(list_ids, r.key, r.pay, r.key_start, r.pay_start, r.nkeys, r.npay, r.status)
+            return r.status != 0
 
         for h in range(1, len(self.by_height)):
             nodes = t64(self.by_height[h])
             if nodes.numel() == 0:
                 continue
             a, b = c0[nodes], c1[nodes]
-            merge_store(nodes + FAM_LOWER * n, a + FAM_LOWER * n, dist[a], isTip[a], b + FAM_LOWER * n, dist[b], isTip[b], False)
+            dist = self.d_dist
+            bad = merge_store(nodes + FAM_LOWER * n, a + FAM_LOWER * n, dist[a], isTip[a], b + FAM_LOWER * n, dist[b], isTip[b], False)
+            if bool(bad.any().item()):
+                nb, ab, bb = nodes[bad], a[bad], b[bad]
+                if bool(((dist[ab] != 0) | (dist[bb] != 0)).any().item()):
+                    raise capi.MapleError("mergeVectors returned None for branches of positive length (the reference raises too, :6196-6198)")
+                self._bump(torch.cat([ab, bb]))
+                dist = self.d_dist
+                bad2 = merge_store(nb + FAM_LOWER * n, ab + FAM_LOWER * n, dist[ab], isTip[ab], bb + FAM_LOWER * n, dist[bb], isTip[bb], False)
+                if bool(bad2.any().item()):
+                    raise capi.MapleError("None vector when merging two vectors despite updating branch lengths (:6193-6195)")
+        dist = self.d_dist
         root = self.root
         if self.child0[root] >= 0:
             ch = t64([self.child1[root], self.child0[root]])  # UpRight from child 1, UpLeft from child 0
@@ -205,27 +229,38 @@ class DeviceTree:
                                                  _dp(nk), _dp(npay), 1, eng._stream())
             capi.check(eng.ctx, rc, "maple_root_vector_batch")
             A.store(t64([root + FAM_UPRIGHT * n, root + FAM_UPLEFT * n]), ok_, op_, ks, ps, nk, npay)
+        clean = True
         for d in range(1, len(self.by_depth)):
             nodes = t64(self.by_depth[d])
             par = self.d_up.long()[nodes]
             is0 = c0[par] == nodes
             vectUp = torch.where(is0, par + FAM_UPRIGHT * n, par + FAM_UPLEFT * n)
+            have = A.key_start[vectUp] >= 0  # a parent whose upper list is None (being repaired) is skipped this time
+            nodes, vectUp = nodes[have], vectUp[have]
             dn = dist[nodes]
             pos = dn > 0  # :6262 `if dist[node]`
             if bool(pos.any().item()):
                 m = nodes[pos]
-                merge_store(m + FAM_TOTUP * n, vectUp[pos], dn[pos] / 2, torch.zeros_like(isTip[m]), m + FAM_LOWER * n, dn[pos] / 2,
-                            isTip[m], True)
+                bad = merge_store(m + FAM_TOTUP * n, vectUp[pos], dn[pos] / 2, torch.zeros_like(isTip[m]), m + FAM_LOWER * n, dn[pos] / 2,
+                                  isTip[m], True)
+                if bool(bad.any().item()):
+                    raise capi.MapleError("probVectTotUp merge returned None on a branch of positive length")
             internal = c0[nodes] >= 0
             if bool(internal.any().item()):
                 m, vu = nodes[internal], vectUp[internal]
                 a, b = c0[m], c1[m]
                 z = torch.zeros_like(isTip[m])
                 ids = torch.cat([m + FAM_UPRIGHT * n, m + FAM_UPLEFT * n])
-                merge_store(ids, torch.cat([vu, vu]), torch.cat([dist[m], dist[m]]), torch.cat([z, z]),
-                            torch.cat([b + FAM_LOWER * n, a + FAM_LOWER * n]), torch.cat([dist[b], dist[a]]),
-                            torch.cat([isTip[b], isTip[a]]), True)
-        return A
+                other = torch.cat([b, a])
+                bad = merge_store(ids, torch.cat([vu, vu]), torch.cat([dist[m], dist[m]]), torch.cat([z, z]),
+                                  other + FAM_LOWER * n, torch.cat([dist[b], dist[a]]), torch.cat([isTip[b], isTip[a]]), True)
+                if bool(bad.any().item()):
+                    mm, oo = torch.cat([m, m])[bad], other[bad]
+                    if bool(((dist[mm] != 0) | (dist[oo] != 0)).any().item()):
+                        raise capi.MapleError("upper-list merge returned None for branches of positive length (:6300-6302)")
+                    self._bump(torch.cat([mm, oo]))  # the reference re-estimates these two lengths (updateBLen, :6289-6299)
+                    clean = False
+        return clean
 
     # ------------------------------------------------------------------ construction from existing lists
     @classmethod
@@ -261,14 +296,14 @@ class DeviceTree:
                                      _dp(self.d_isTip), _dp(self._d_mutStart), _dp(self._d_mut), _dp(A.nkeys))
         capi.check(eng.ctx, rc, "maple_tree_bind")
 
-    def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0):
+    def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0, cycles=None):
         """Run the searches of the listed nodes; returns a device tensor of raw records [n, 64 bytes] viewed as uint8
         and a helper to read it as a numpy record array."""
         eng, dev = self.eng, self.eng.device
         nodes = torch.as_tensor(nodes, dtype=torch.int32, device=dev).contiguous()
         out = torch.zeros((nodes.numel(), 64), dtype=torch.uint8, device=dev)
         rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), nodes.numel(), _dp(nodes), _dp(out), int(scratch_keys),
-                                            int(max_concurrent), eng._stream())
+                                            int(max_concurrent), _dp(cycles), eng._stream())
         capi.check(eng.ctx, rc, "maple_spr_search_batch")
         return out
 

@@ -1,0 +1,42 @@
+"""Ad-hoc timing of the device SPR search on a synthetic tree (not the bench)."""
+import math, sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+from maple_b200.engine import MapleEngine
+from maple_b200.genome_list import pack_lists
+from maple_b200.search import dirty_nodes, search_params
+from maple_b200.synthetic import generate
+from maple_b200.tree import DeviceTree
+
+nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+t0 = time.time()
+ml = len(sys.argv) > 2 and sys.argv[2] == 'ml'
+d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=ml)
+eng = MapleEngine(d.model, 0)
+tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, 0))
+torch.cuda.synchronize()
+print("setup %.1fs nodes %d arena %.1f MB" % (time.time() - t0, tree.n, tree.arena.used_bytes() / 1e6), flush=True)
+nodes = dirty_nodes(tree)
+tree.prepare_search()
+L = math.log(d.model.lRef)
+for name, strict, fails, thr in (("fast", True, 2, 6.0 * L), ("deep", False, 4, 14.0 * L)):
+    p = search_params(d.model.lRef, strict, fails, thr)
+    for rep in range(2):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cyc = torch.zeros(len(nodes), dtype=torch.int64, device=eng.device)
+        out = tree.spr_search(nodes, p, cycles=cyc)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+    rec = tree.search_records(out)
+    st = np.bincount(rec["status"], minlength=4)
+    ph = rec["phase1"].sum()
+    print("%s: %.1f ms, searches %d, status %s, phase1 %d (%.1f/search, max %d), %.3g cand/s, proposals %d" % (
+        name, ms, len(nodes), st.tolist(), ph, ph / len(nodes), rec["phase1"].max(), ph / ms * 1e3, (rec["placement"] >= 0).sum()), flush=True)
+    c = cyc.cpu().numpy().astype(np.float64)
+    print("   cycles/search: mean %.3g p50 %.3g p99 %.3g max %.3g | sum/56832 threads = %.1f ms @1.9GHz, longest = %.1f ms | cycles per candidate %.0f | corr(phase1,cycles)=%.2f" % (
+        c.mean(), np.percentile(c, 50), np.percentile(c, 99), c.max(), c.sum() / 56832 / 1.9e6, c.max() / 1.9e6, c.sum() / max(ph, 1),
+        np.corrcoef(rec["phase1"], c)[0, 1]), flush=True)
