@@ -1,22 +1,24 @@
 #!/usr/bin/env python3
-"""Benchmark of the SPR placement-cost hot path on B200 (contract: see the task's bench.py section).
+"""Benchmark of the SPR search hot path on B200 (contract: the task's bench.py section).
 
-Workload (config.workload): synthetic 29,903-bp reference, N_SEQ sequences (~10 differences each),
-UNREST + per-site rate variation (BASELINE.json configs[2] shape); the tree's four genome-list
-families are built on the device; one STEP scores, for every non-root node of the tree (the subtree
-an SPR move would prune), every branch within RADIUS hops of its parent against the stored
-mid-branch lists -- appendProbNode(probVectTotUp[t], probVect[s], isTip[s], dist[s]), the phase-1 call of
-findBestParentTopology (MAPLEv0.7.5.4.py:7011/7223) -- i.e. one SPR candidate placement per pair.
+Workload (config.workload): synthetic 29,903-bp reference, NSEQ (default 100,000) sequences ~10 differences each,
+UNREST + per-site rate variation (BASELINE.json configs[2] shape).  The tree is the simulated one with
+MAPLE-like branch lengths (substitutions/lRef, zero-length branches where nothing happened); its four genome-list
+families are built on the device.  One STEP = one full SPR search round on that frozen tree, i.e. what the
+reference does in Pool.map(startTopologyUpdatesParallel, ...) (MAPLEv0.7.5.4.py:12283-12312): for every non-root
+node the current placement cost, then findBestParentTopology with the deep-search stop rules (allowedFails 4,
+threshold 14*ln lRef, non-strict) including all merges, branch-length optimisations and phase-2 refinements.
 
-value : candidate placements / s, arguments and lists resident in HBM when the timed region starts
-e2e   : the same through the host-buffer C-ABI call (arguments in pinned host memory, copies and the
-        read-back of the scores inside the timed region)
---impl reference : the CPU restatement of the reference algorithm (oracle/, OpenMP over all host cores)
-        on a bounded sample of the same pairs.  The reference itself is a pure-Python script that
-        cannot travel to the GPU box; its CPython/pypy3 rates measured while surveying are in BASELINE.md.
+metric : SPR candidate placements scored per second = phase-1 appendProbNode calls (:7011/:7223) / search time
+value  : node list already on the device (lists, tree and model are always device-resident)
+e2e    : node ids in pinned host memory -> device, search, 64-byte result records -> host, every step
+--impl reference : the CPU restatement of the reference algorithm (oracle/maple_oracle.c, OpenMP over all host
+         cores) running the same searches on a bounded sample of the nodes.  The reference itself is a pure-Python
+         script that cannot travel to the GPU box; BASELINE.md has its CPython rates measured while surveying.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -33,12 +35,12 @@ UNIT = "placements/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nseq", type=int, default=int(os.environ.get("MAPLE_BENCH_NSEQ", 100000)))
-    ap.add_argument("--radius", type=int, default=int(os.environ.get("MAPLE_BENCH_RADIUS", 13)))
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000)
+    ap.add_argument("--round", default=os.environ.get("MAPLE_BENCH_ROUND", "deep"), choices=["fast", "deep"])
+    ap.add_argument("--cpu-searches", type=int, default=1500, help="searches in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -56,7 +58,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
         except Exception:
@@ -76,71 +78,88 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         sm.sort()
-        busy = [x for x in sm if x > 0]
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_problem(args, device_index, seed):
+def round_params(args, lRef):
+    from maple_b200.search import search_params
+    L = math.log(lRef)
+    if args.round == "fast":  # the reference's first, fast round (:222-225, :12149-12153)
+        return search_params(lRef, True, 2, 6.0 * L)
+    return search_params(lRef, False, 4, 14.0 * L)  # its deep rounds (:53-55, :12155-12159)
+
+
+def workload_name(args):
+    return ("synthetic 29903-bp, %d seqs ~10 diffs, UNREST+rateVariation, MAPLE-like branch lengths; one full SPR search round "
+            "(%s stop rules) over every non-root node of the frozen tree" % (args.nseq, args.round))
+
+
+def build_problem(args, device_index):
     import torch
     from maple_b200.engine import MapleEngine
     from maple_b200.genome_list import pack_lists
+    from maple_b200.search import dirty_nodes
     from maple_b200.synthetic import generate
     from maple_b200.tree import DeviceTree
-    from maple_b200.workloads import neighbourhood_pairs, algorithmic_bytes
     t0 = time.time()
-    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, seed=seed)
+    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, seed=1, ml_like_blens=True)
     eng = MapleEngine(d.model, device_index)
     tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
-    tips = pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate)
-    tree.recalculate_all_lists(d.tip_nodes, tips)
-    s, p, c, tip, bl = neighbourhood_pairs(tree, args.radius)
+    tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+    tree.prepare_search()
+    nodes = dirty_nodes(tree)
     torch.cuda.synchronize()
-    info = {"setup_s": round(time.time() - t0, 1), "nodes": tree.n, "pairs": int(p.numel()), "searches": int(torch.unique(s).numel()),
-            "arena_bytes": tree.arena.used_bytes(), "alg_bytes": algorithmic_bytes(tree, s, p, c),
-            "mean_parent_entries": float(tree.arena.nkeys[p.long()].float().mean().item()),
-            "mean_child_entries": float(tree.arena.nkeys[c.long()].float().mean().item())}
-    return d, eng, tree, (s, p, c, tip, bl), info
+    return d, eng, tree, nodes, round(time.time() - t0, 1)
+
+
+def oracle_tree(d, tree):
+    return {"up": d.up, "child0": d.child0, "child1": d.child1, "dist": tree.dist, "isTip": tree.isTip, "root": d.root}
+
+
+def params_dict(p):
+    return {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] != "reserved"}
+
+
+def cpu_sample(nodes, k):
+    """every (len/k)-th node of the pre-order node list: an unbiased spread over the tree"""
+    import numpy as np
+    if k >= len(nodes):
+        return nodes
+    return nodes[np.linspace(0, len(nodes) - 1, k).astype(np.int64)]
 
 
 def run_reference(args):
-    """CPU arm: the oracle port of the path over all host cores, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np
-    import torch
     from oracle.oracle import Oracle
-    dev = 0
-    d, eng, tree, (s, p, c, tip, bl), info = build_problem(args, dev, seed=1)
+    d, eng, tree, nodes, setup_s = build_problem(args, 0)  # the lists the CPU arm searches are the ones the GPU arm uses
     host = tree.arena.to_host()
-    n = min(args.cpu_sample, int(p.numel()))
-    # the sample is a contiguous run of whole searches from the middle of the batch
-    start = (int(p.numel()) - n) // 2
-    sl = slice(start, start + n)
-    pa, ca, ta, ba = (x[sl].cpu().numpy() for x in (p, c, tip, bl))
+    p = round_params(args, d.model.lRef)
+    sample = cpu_sample(nodes, args.cpu_searches)
     orc = Oracle(d.model)
-    for _ in range(max(1, min(args.warmup, 2))):
-        orc.append_batch(host, pa[: n // 8], ca[: n // 8], ta[: n // 8], ba[: n // 8])
+    ta, pd = oracle_tree(d, tree), params_dict(p)
+    for _ in range(max(1, min(args.warmup, 1))):
+        orc.search_batch(ta, host, pd, sample[: max(16, len(sample) // 8)], lazy_mode=1)
     t0 = time.perf_counter()
+    tot = 0
     for _ in range(args.steps):
-        orc.append_batch(host, pa, ca, ta, ba)
-    dt = (time.perf_counter() - t0) / args.steps
+        rec = orc.search_batch(ta, host, pd, sample, lazy_mode=1)
+        tot += int(rec["phase1"].sum())
+    dt = time.perf_counter() - t0
     cores = orc.num_threads()
-    val = n / dt
+    val = tot / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "nseq": args.nseq, "radius": args.radius, "pairs_per_step": n},
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "nseq": args.nseq, "round": args.round, "searches_per_step": int(len(sample)),
+                       "placements_per_step": tot // args.steps},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d consecutive candidate pairs (whole searches) of the %d-pair step, oracle/maple_oracle.c "
-                                       "with OpenMP on %d threads" % (n, int(p.numel()), cores)},
+                             "sample": "%d of the %d searches of one round (evenly spread over the tree), oracle/maple_oracle.c "
+                                       "search with OpenMP on %d threads" % (len(sample), len(nodes), cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
-
-
-def workload_name(args):
-    return ("synthetic 29903-bp, %d seqs ~10 diffs, UNREST+rateVariation; phase-1 SPR candidate scoring over stored "
-            "mid-branch lists, radius %d" % (args.nseq, args.radius))
 
 
 def main():
@@ -150,6 +169,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
+    from maple_b200 import capi
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -158,31 +178,25 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    d, eng, tree, (s, p, c, tip, bl), info = build_problem(args, local, seed=1)
+    d, eng, tree, nodes, setup_s = build_problem(args, local)
     dev = eng.device
-    # strong scaling: searches (pruned nodes) are dealt round-robin to ranks like coreNum[node]==corNum (:9619)
-    if world > 1:
-        mine = (s.long() % world) == rank
-        s, p, c, tip, bl = s[mine], p[mine].contiguous(), c[mine].contiguous(), tip[mine].contiguous(), bl[mine].contiguous()
-    n = int(p.numel())
-    out = torch.empty(n, dtype=torch.float64, device=dev)
-    n_total = torch.tensor([n], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(n_total)
-    n_total = int(n_total.item())
-    # per-search best candidate (what a search reports); dense [nNodes] so that ranks can all-reduce it
-    best = torch.full((tree.n,), float("-inf"), dtype=torch.float64, device=dev)
-    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # > 126 MB L2
+    p = round_params(args, d.model.lRef)
+    # strong scaling: every rank holds the whole tree; searches are dealt round-robin like coreNum[node]==corNum (:9619)
+    mine = nodes[rank::world] if world > 1 else nodes
+    per_rank = (len(nodes) + world - 1) // world
+    d_nodes = torch.as_tensor(mine, dtype=torch.int32, device=dev)
+    gathered = torch.zeros((world * per_rank, 64), dtype=torch.uint8, device=dev) if world > 1 else None
 
-    def step():
-        eng.append_prob_batch(p, c, tip, bl, out=out)
-        best.fill_(float("-inf"))
-        best.scatter_reduce_(0, s.long(), out, reduce="amax")
-        if world > 1:
-            dist.all_reduce(best, op=dist.ReduceOp.MAX)
+    def step(src_nodes):
+        out = tree.spr_search(src_nodes, p, scratch_keys=16384)
+        if world > 1:  # one collective per round: everybody gets every proposal
+            pad = torch.zeros((per_rank, 64), dtype=torch.uint8, device=dev)
+            pad[: out.shape[0]] = out
+            dist.all_gather_into_tensor(gathered, pad)
+        return out
 
     for _ in range(args.warmup):
-        step()
+        out = step(d_nodes)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -190,8 +204,9 @@ def main():
     if rank == 0:
         sampler.start()
         t_wait = time.time()
-        while not sampler.rows and time.time() - t_wait < 5.0:  # nvidia-smi takes a moment to emit its first line
+        while not sampler.rows and time.time() - t_wait < 5.0:
             time.sleep(0.05)
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # > 126 MB L2
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(args.steps)]
     l0 = eng.launches
@@ -199,12 +214,12 @@ def main():
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations
         ev[k][0].record()
-        eng.append_prob_batch(p, c, tip, bl, out=out)
+        out = tree.spr_search(d_nodes, p, scratch_keys=16384)
         ev[k][1].record()
-        best.fill_(float("-inf"))
-        best.scatter_reduce_(0, s.long(), out, reduce="amax")
         if world > 1:
-            dist.all_reduce(best, op=dist.ReduceOp.MAX)
+            pad = torch.zeros((per_rank, 64), dtype=torch.uint8, device=dev)
+            pad[: out.shape[0]] = out
+            dist.all_gather_into_tensor(gathered, pad)
         ev[k][2].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -212,93 +227,94 @@ def main():
     launches = eng.launches - l0
     step_ms = sum(a.elapsed_time(z) for a, _, z in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / args.steps
-    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    rec = tree.search_records(out)
+    cand = torch.tensor([int(rec["phase1"].sum()), int((rec["status"] == 0).sum()), int((rec["status"] == 3).sum()),
+                         int((rec["placement"] >= 0).sum())], dtype=torch.int64, device=dev)
+    tmax = torch.tensor([step_ms], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = n_total * args.steps / (total_ms / 1e3)
+        dist.all_reduce(cand)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    cand_total, searched, overflowed, proposals = (int(x) for x in cand.tolist())
+    total_ms = float(tmax.item())
+    value = cand_total * args.steps / (total_ms / 1e3)
 
-    # ---- e2e: host buffers through the C-ABI host call, copies inside the timed region
-    hp = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (p, c, tip, bl)]
-    for h, x in zip(hp, (p, c, tip, bl)):
-        h.copy_(x)
-    hout = torch.empty(n, dtype=torch.float64, pin_memory=True)
-    hnp = [h.numpy() for h in hp]
-    for _ in range(2):
-        eng.append_prob_batch_host(*hnp, out=hout.numpy())
+    # ---- e2e: node ids from pinned host memory, records back to the host, every step
+    h_nodes = torch.empty(len(mine), dtype=torch.int32, pin_memory=True)
+    h_nodes.copy_(torch.from_numpy(np.ascontiguousarray(mine)))
+    h_out = torch.empty((len(mine), 64), dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 2))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.append_prob_batch_host(*hnp, out=hout.numpy())
-        _ = float(hout[0])
-    torch.cuda.synchronize()
+        dn = h_nodes.to(dev, non_blocking=True)
+        o = step(dn)
+        h_out.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+        _ = int(h_out[0, 0])
     e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_val = n_total / float(e2e_dt.item())
-    if rank == 0:
-        # keep the GPU busy with the timed kernel a little longer so that the 100 ms sampler sees it under load
-        t_busy = time.time()
-        while time.time() - t_busy < 1.0:
-            eng.append_prob_batch(p, c, tip, bl, out=out)
-            torch.cuda.synchronize()
+    e2e_val = cand_total / float(e2e_dt.item())
     clocks = sampler.stop() if rank == 0 else None
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.destroy_process_group()
         return
+
+    # algorithmic bytes of one round: every scored candidate reads the stored mid-branch list of its branch and
+    # writes nothing; every search reads its removed list once and writes one 64-byte record
+    A, n = tree.arena, tree.n
+    tot_lists = slice(3 * n, 4 * n)
+    have = A.key_start[tot_lists] >= 0
+    mean_tot_bytes = float((A.nkeys[tot_lists][have].double() * 4 + A.npay[tot_lists][have].double() * 8).mean().item()) + 16
+    low = slice(0, n)
+    mean_low_bytes = float((A.nkeys[low].double() * 4 + A.npay[low].double() * 8).mean().item()) + 16
+    alg_bytes = cand_total / world * mean_tot_bytes + (searched / world) * (mean_low_bytes + 64)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = info["alg_bytes"] / world / (kern_ms / 1e3) / 1e9
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "nseq": args.nseq, "radius": args.radius, "pairs_per_step": n_total,
-                   "searches_per_step": info["searches"], "nodes": info["nodes"], "arena_MB": round(info["arena_bytes"] / 1e6, 1),
-                   "mean_parent_entries": round(info["mean_parent_entries"], 2), "mean_child_entries": round(info["mean_child_entries"], 2),
-                   "l2": "flushed between timed iterations (160 MB memset)", "parallelism": "searches dealt round-robin to %d GPU(s); "
-                   "one all-reduce(max) of the dense per-node best score" % world},
+        "config": {"workload": workload_name(args), "nseq": args.nseq, "round": args.round, "nodes": tree.n,
+                   "searches_per_step": searched, "placements_per_step": cand_total, "proposals": proposals,
+                   "scratch_overflows": overflowed, "arena_MB": round(tree.arena.used_bytes() / 1e6, 1), "setup_s": setup_s,
+                   "l2": "flushed between timed iterations (160 MB memset)",
+                   "parallelism": "whole tree on every GPU; searches dealt round-robin to %d GPU(s); one NCCL all-gather of the "
+                                  "64-byte result records per round" % world},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 17, "d2h_bytes_per_step": n * 8,
-                "note": "maple_append_prob_batch_host: pinned host argument arrays in, scores out, per rank"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_append", "kernel_ms": kern_ms,
-                     "alg_bytes_per_launch": info["alg_bytes"] // world,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(len(mine) * 4), "d2h_bytes_per_step": int(len(mine) * 64),
+                "note": "pinned host node ids in, result records out, per rank"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_spr_search_fsm", "kernel_ms": kern_ms, "alg_bytes_per_launch": int(alg_bytes),
+                     "mean_mid_branch_list_bytes": round(mean_tot_bytes, 1),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle.oracle import Oracle
         host = tree.arena.to_host()
-        ns = min(args.cpu_sample, n)
-        start = (n - ns) // 2
-        sl = slice(start, start + ns)
-        pa, ca, ta, ba = (x[sl].cpu().numpy() for x in (p, c, tip, bl))
+        sample = cpu_sample(nodes, args.cpu_searches)
         orc = Oracle(d.model)
-        orc.append_batch(host, pa[: ns // 8], ca[: ns // 8], ta[: ns // 8], ba[: ns // 8])
-        reps, t0 = 0, time.perf_counter()
-        while reps < 3 or time.perf_counter() - t0 < 10.0:
-            ref = orc.append_batch(host, pa, ca, ta, ba)
-            reps += 1
-            if time.perf_counter() - t0 > 30.0:
-                break
-        cdt = (time.perf_counter() - t0) / reps
-        got = out[sl].cpu().numpy()
-        fin = np.isfinite(ref)
-        line["cpu_baseline"] = {"value": ns / cdt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                                "sample": "%d consecutive candidate pairs of the step x %d repeats, oracle/maple_oracle.c (C, OpenMP)"
-                                          % (ns, reps),
-                                "max_abs_diff_vs_gpu": float(np.max(np.abs(got[fin] - ref[fin]))) if fin.any() else 0.0,
-                                "inf_pattern_equal": bool(np.array_equal(np.isfinite(got), fin))}
+        ta, pd = oracle_tree(d, tree), params_dict(p)
+        orc.search_batch(ta, host, pd, sample[: max(16, len(sample) // 8)], lazy_mode=1)
+        t0 = time.perf_counter()
+        ref = orc.search_batch(ta, host, pd, sample, lazy_mode=1)
+        cdt = time.perf_counter() - t0
+        pos = {int(nd): i for i, nd in enumerate(nodes)}
+        got = rec[[pos[int(nd)] for nd in sample]]
+        same = all(np.array_equal(got[f], ref[f]) for f in ("placement", "bestNode", "status", "phase1", "bLenTop", "bLenBottom", "bLenAppend"))
+        fin = np.isfinite(ref["bestScore"])
+        line["cpu_baseline"] = {"value": float(ref["phase1"].sum()) / cdt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                                "sample": "%d of the %d searches of the round (evenly spread), %d placements, oracle/maple_oracle.c "
+                                          "search (C, OpenMP)" % (len(sample), len(nodes), int(ref["phase1"].sum())),
+                                "gpu_matches_oracle_on_sample": bool(same),
+                                "max_abs_score_diff": float(np.max(np.abs(got["bestScore"][fin] - ref["bestScore"][fin]), initial=0.0))}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

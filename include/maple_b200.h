@@ -163,6 +163,10 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                            int64_t* out_cycles /* optional DEVICE int64[n]: SM clock cycles each search took; NULL to skip */,
                            void* stream);
 
+/* Which search kernel maple_spr_search_batch launches: 0 (default) = warp-converged state machine, 1 = the
+ * straight-line one-search-per-thread kernel (kept for A/B measurements; same results). */
+int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
+
 /* Kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 int64_t maple_launch_count(const maple_ctx* ctx);
 

@@ -12,6 +12,7 @@
 #include "../../include/maple_b200.h"
 #include "likelihood.cuh"
 #include "search.cuh"
+#include "search_fsm.cuh"
 
 using namespace maple;
 
@@ -33,6 +34,7 @@ struct maple_ctx {
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
+    int searchVariant = 0;  // 0 = warp-converged state machine (default), 1 = straight-line one-search-per-thread kernel
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
@@ -212,6 +214,102 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
         search_node(sm, T, sp, nodes[i], s, stack, stackCap, r);
         out[i] = r;
         if (outCycles) outCycles[i] = clock64() - c0;
+    }
+}
+
+// The same searches as k_spr_search, one per lane, but as resumable state machines (search_fsm.cuh): every loop
+// iteration each lane advances its control code to the next co-walk request, then the warp runs each kind of
+// co-walk once for all lanes that requested it.
+__global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+                                                                   const __grid_constant__ SearchParams sp, int64_t n,
+                                                                   const int32_t* __restrict__ nodes, SearchResult* __restrict__ out,
+                                                                   uint32_t* scrKey, double* scrPay, double* scrAis, StackE* scrStack,
+                                                                   unsigned capK, unsigned capP, unsigned capA, int stackCap,
+                                                                   unsigned long long* counter, long long* outCycles) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    ScratchD s;
+    s.key = scrKey + tid * capK;
+    s.pay = scrPay + tid * capP;
+    s.ais = scrAis + tid * capA;
+    s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
+    StackE* stack = scrStack + tid * (size_t)stackCap;
+    Fsm f;
+    f.op = OP_NONE;
+    f.pc = 0;
+    int stage = 0;  // 0 idle, 1 current-placement append pending, 2 search running, 3 no more work
+    unsigned long long i = 0;
+    int node = -1;
+    double bestCurrentLK = 0.0;
+    long long c0 = 0;
+    SearchResult r;
+    for (;;) {
+        // ---------------- control (divergent, cheap)
+        if (stage == 2) {
+            fsm_step(f, sm, T, sp, s, stack, stackCap);
+        } else if (stage == 1) {
+            bestCurrentLK = f.resD;
+            r.bestCurrentLK = bestCurrentLK;
+            if (!(bestCurrentLK < sp.thresholdTopologyPlacement || T.dist[node] != 0.0)) {  // :9674
+                f.rc = 1;
+                f.op = OP_DONE;
+            } else {
+                const int parent = T.up[node];
+                f.pc = 0;
+                f.parent = parent;
+                f.child = (T.child0[parent] == node) ? 0 : 1;
+                f.bestLKdiff = bestCurrentLK;
+                f.removedBLen = T.dist[node];
+                f.phase1 = 0;
+                f.rc = 0;
+                s.topK = s.topP = 0;
+                stage = 2;
+                fsm_step(f, sm, T, sp, s, stack, stackCap);
+            }
+        }
+        while (stage != 3 && (stage == 0 || f.op == OP_DONE)) {
+            if (stage != 0) {  // a search (or its pre-check) just ended
+                if (stage == 2) fsm_finish(f, T, sp, node, bestCurrentLK, r);
+                else r.status = f.rc;
+                out[i] = r;
+                if (outCycles) outCycles[i] = clock64() - c0;
+                stage = 0;
+            }
+            i = atomicAdd(counter, 1ULL);
+            if (i >= (unsigned long long)n) { stage = 3; f.op = OP_NONE; break; }
+            node = nodes[i];
+            c0 = clock64();
+            r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
+            r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+            f.op = OP_NONE;
+            if (T.up[node] < 0) { out[i] = r; continue; }
+            s.topK = s.topP = 0;
+            s.err = 0;
+            const int parent = T.up[node];
+            LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
+            if (n_mut(T, node)) vectUp = s_pass(sm, T, s, vectUp, node, false);
+            const LRef own = tree_list(T, 0, node);
+            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[i] = r; continue; }
+            f.a1 = vectUp; f.a2 = own; f.at1 = T.isTip[node] != 0; f.ab1 = T.dist[node];
+            f.op = OP_APPEND;
+            stage = 1;
+        }
+        // ---------------- co-walks, one kind at a time, lanes converged
+        __syncwarp();
+        if (f.op == OP_APPEND) f.resD = f_append(sm, f.a1, f.a2, f.at1 != 0, f.ab1);
+        __syncwarp();
+        if (f.op == OP_MERGE) {
+            Writer w;
+            w.init(s.key + s.topK, s.pay + s.topP);
+            if (f_merge(sm, f.a1, f.ab1, f.at1 != 0, f.a2, f.ab2, f.at2 != 0, f.aflags, w) == 0) f.resL = sc_commit(s, w.nk, w.np);
+            else f.resL = lnull();
+        }
+        __syncwarp();
+        if (f.op == OP_BLEN) f.resD = f_blen(sm, f.a1, f.a2, f.at1 != 0, s.ais);
+        __syncwarp();
+        if (f.op == OP_DIFFER) f.resB = f_differ(sm, f.a1, f.a2) ? 1 : 0;
+        if (__all_sync(0xffffffffu, stage == 3)) break;
     }
 }
 
@@ -506,7 +604,8 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
     const int stackCap = 512;
     int blocksPerSM = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
+    if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search_fsm, kSearchThreads, 0));
     if (blocksPerSM < 1) blocksPerSM = 1;
     int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
     if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches;
@@ -529,10 +628,22 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     double* scrAis = (double*)(base + (size_t)threads * capP * 8);
     StackE* scrStack = (StackE*)(base + (size_t)threads * (capP + capA) * 8);
     uint32_t* scrKey = (uint32_t*)(base + (size_t)threads * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
-    k_spr_search<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay, scrAis,
-                                                                     scrStack, capK, capP, capA, stackCap, ctx->searchCounter, (long long*)out_cycles);
+    if (ctx->searchVariant == 1)
+        k_spr_search<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
+                                                                         scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
+                                                                         (long long*)out_cycles);
+    else
+        k_spr_search_fsm<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
+                                                                             scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
+                                                                             (long long*)out_cycles);
     ctx->launches++;
     CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
+    if (!ctx || variant < 0 || variant > 1) return MAPLE_E_ARG;
+    ctx->searchVariant = variant;
     return MAPLE_OK;
 }
 

@@ -1,0 +1,424 @@
+// Warp-converged form of the device SPR search (same algorithm and results as search.cuh).
+//
+// search.cuh runs one search per thread as straight-line code; on the GPU the 32 lanes of a warp are then almost
+// always inside DIFFERENT functions (one in appendProbNode, one in mergeVectors, one popping its stack...), so a warp
+// issues for one lane at a time (measured: ~1.3e6 SM cycles per candidate placement).  Here every lane still owns
+// one search, but the search is a resumable state machine: a lane runs its (cheap, divergent) control code until it
+// needs one of the four heavy co-walks, parks the request, and the warp then executes each kind of co-walk ONCE for
+// all lanes that asked for it -- the lanes of a warp are converged inside appendProbNode / mergeVectors /
+// estimateBranchLength / areVectorsDifferent, which is where the time goes.
+//
+// The control flow is search.cuh's find_best_parent_topology written as a coroutine: `pc` is the resume point, all
+// state that lives across a co-walk sits in the Fsm struct, and YIELD_* are the suspension points.
+#pragma once
+#include "search.cuh"
+
+namespace maple {
+
+enum FsmOp { OP_NONE = 0, OP_APPEND = 1, OP_MERGE = 2, OP_BLEN = 3, OP_DIFFER = 4, OP_DONE = 5 };
+
+struct Fsm {
+    int pc, op;
+    // request / reply registers of the co-walks
+    LRef a1, a2;
+    double ab1, ab2, resD;
+    LRef resL;
+    int at1, at2, aflags, resB;
+    // search level
+    int parent, child, pruned, sibling, isRemovedTip, phase1, spN, rc;
+    double removedBLen, bestLKdiff;
+    Phase2 ph;
+    // current stack entry
+    int t1, direction, needsUpdating, failedPasses, otherChild, which;
+    LRef passed, removed, midTot, midBottom, vectUp, vUp;
+    double distance, lastLK, midProb;
+    // evaluatePlacement / phase-2 sub-machine
+    LRef eMidTot, eDown, eUp, eRemoved, midLower, midTop, newMid;
+    double eDist, bestAppending, bestTop, bestBottom, cost, initialCost;
+    int eFromTip1, eT1, evalRet;
+    unsigned mk, mp;
+};
+
+#define FSM_FAIL(code)          \
+    do {                        \
+        f.rc = (code);          \
+        f.op = OP_DONE;         \
+        return;                 \
+    } while (0)
+
+#define FSM_CHECK_ERR()                  \
+    do {                                 \
+        if (s.err) FSM_FAIL(s.err);      \
+    } while (0)
+
+// co-walk requests.  LABEL must be a unique positive integer literal.
+#define YIELD_APPEND(LABEL, P_, C_, TIP_, BL_)                                   \
+    do {                                                                         \
+        f.a1 = (P_); f.a2 = (C_); f.at1 = (TIP_) ? 1 : 0; f.ab1 = (BL_);         \
+        if (!f.a1.k || !f.a2.k) FSM_FAIL(2);                                     \
+        f.op = OP_APPEND; f.pc = LABEL; return;                                  \
+        case LABEL:;                                                             \
+    } while (0)
+
+#define YIELD_MERGE(LABEL, A_, B1_, T1_, B_, B2_, T2_, UPDOWN_)                                              \
+    do {                                                                                                     \
+        f.a1 = (A_); f.ab1 = (B1_); f.at1 = (T1_) ? 1 : 0; f.a2 = (B_); f.ab2 = (B2_); f.at2 = (T2_) ? 1 : 0; \
+        f.aflags = (UPDOWN_) ? 1 : 0;                                                                        \
+        if (!f.a1.k || !f.a2.k) { if (!s.err) s.err = 2; FSM_FAIL(s.err); }                                  \
+        if (!sc_reserve(s, unsigned(f.a1.nk) + unsigned(f.a2.nk))) FSM_FAIL(3);                              \
+        f.op = OP_MERGE; f.pc = LABEL; return;                                                               \
+        case LABEL:;                                                                                         \
+    } while (0)
+
+#define YIELD_BLEN(LABEL, P_, C_, TIP_)                                                      \
+    do {                                                                                     \
+        f.a1 = (P_); f.a2 = (C_); f.at1 = (TIP_) ? 1 : 0;                                    \
+        if (!f.a1.k || !f.a2.k) FSM_FAIL(2);                                                 \
+        if (unsigned(f.a1.nk) + unsigned(f.a2.nk) + 1u > s.capA) FSM_FAIL(3);                \
+        f.op = OP_BLEN; f.pc = LABEL; return;                                                \
+        case LABEL:;                                                                         \
+    } while (0)
+
+#define YIELD_DIFFER(LABEL, A_, B_)                         \
+    do {                                                    \
+        f.a1 = (A_); f.a2 = (B_);                           \
+        if (!f.a1.k) FSM_FAIL(2);                           \
+        f.op = OP_DIFFER; f.pc = LABEL; return;             \
+        case LABEL:;                                        \
+    } while (0)
+
+#define FSM_PUSH(T1, DIR, NU, PASSED, DISTANCE, LASTLK, FAILS, REMOVED)                                 \
+    do {                                                                                               \
+        FSM_CHECK_ERR();                                                                               \
+        if (f.spN >= stackCap) FSM_FAIL(3);                                                            \
+        StackE& e_ = stack[f.spN++];                                                                   \
+        e_.t1 = (T1); e_.direction = (signed char)(DIR); e_.needsUpdating = (signed char)(NU);          \
+        e_.passed = (PASSED); e_.distance = (DISTANCE); e_.lastLK = (LASTLK); e_.failedPasses = (FAILS); \
+        e_.removed = (REMOVED); e_.markK = s.topK; e_.markP = s.topP;                                  \
+    } while (0)
+
+// Runs the search of f until it needs a co-walk (f.op says which) or finishes (f.op == OP_DONE, f.rc = status).
+__device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack, int stackCap) {
+    const int32_t* up = t.up;
+    const double* dist = t.dist;
+    const double eff = sp.effectivelyNon0BLen;
+    f.op = OP_NONE;
+#define CH(n, i) ((i) == 0 ? t.child0[n] : t.child1[n])
+    switch (f.pc) {
+        case 0: {
+            f.spN = 0;
+            f.pruned = CH(f.parent, f.child);
+            f.sibling = CH(f.parent, 1 - f.child);
+            f.removed = s_copy(s, tree_list(t, 0, f.pruned));  // search-level "removedRel"; copied: may be shortened in place (:7087)
+            if (n_mut(t, f.pruned)) f.removed = s_pass(m, t, s, f.removed, f.pruned, true);
+            f.vUp = f.removed;  // bestRemoved
+            if (n_mut(t, f.sibling)) f.vUp = s_pass(m, t, s, f.vUp, f.sibling, false);
+            if (!f.removed.k) FSM_FAIL(s.err ? s.err : 2);
+            f.isRemovedTip = t.isTip[f.pruned] != 0;
+            f.ph.bestNode = f.sibling;
+            f.ph.bestScore = f.bestLKdiff;  // originalLK
+            if (up[f.parent] >= 0) {
+                const int node = f.parent, sib = f.sibling;
+                int childUp;
+                LRef vectUpUp;
+                if (t.child0[up[node]] == node) { childUp = 1; vectUpUp = tree_list(t, 1, up[node]); }
+                else { childUp = 2; vectUpUp = tree_list(t, 2, up[node]); }
+                LRef probVect1 = tree_list(t, 0, sib);
+                if (n_mut(t, sib)) probVect1 = s_pass(m, t, s, probVect1, sib, true);
+                LRef removedRel1 = f.removed;
+                if (n_mut(t, node)) {
+                    probVect1 = s_pass(m, t, s, probVect1, node, true);
+                    removedRel1 = s_pass(m, t, s, f.removed, node, true);
+                }
+                FSM_PUSH(up[node], childUp, 1, probVect1, dist[sib] + dist[node], f.bestLKdiff, 0, removedRel1);
+                if (n_mut(t, node)) vectUpUp = s_pass(m, t, s, vectUpUp, node, false);
+                removedRel1 = f.removed;
+                if (n_mut(t, sib)) {
+                    vectUpUp = s_pass(m, t, s, vectUpUp, sib, false);
+                    removedRel1 = s_pass(m, t, s, f.removed, sib, false);
+                }
+                FSM_PUSH(sib, 0, 1, vectUpUp, dist[sib] + dist[node], f.bestLKdiff, 0, removedRel1);
+                f.ph.bTop = dist[node]; f.ph.bBottom = dist[sib]; f.ph.bAppend = f.removedBLen;
+            } else {
+                const int sib = f.sibling;
+                if (t.child0[sib] >= 0) {
+                    const int c1 = t.child0[sib], c2 = t.child1[sib];
+                    for (int which = 0; which < 2; which++) {
+                        const int target = which == 0 ? c1 : c2, other = which == 0 ? c2 : c1;
+                        LRef vectUp1 = tree_list(t, 0, other);
+                        if (n_mut(t, other)) vectUp1 = s_pass(m, t, s, vectUp1, other, true);
+                        vectUp1 = s_root_vector(m, t, s, vectUp1, dist[other], t.isTip[other] != 0);
+                        LRef removedRel1 = f.vUp;
+                        if (n_mut(t, target)) {
+                            removedRel1 = s_pass(m, t, s, f.vUp, target, false);
+                            vectUp1 = s_pass(m, t, s, vectUp1, target, false);
+                        }
+                        FSM_PUSH(target, 0, 1, vectUp1, dist[target], f.bestLKdiff, 0, removedRel1);
+                    }
+                }
+                f.ph.bTop = 0.0; f.ph.bBottom = dist[sib]; f.ph.bAppend = f.removedBLen;
+            }
+            FSM_CHECK_ERR();
+        }
+        // fall through into the main loop
+        while (f.spN > 0) {
+            {
+                const StackE& E = stack[--f.spN];
+                s.topK = E.markK;
+                s.topP = E.markP;
+                f.t1 = E.t1; f.direction = E.direction; f.needsUpdating = E.needsUpdating; f.failedPasses = E.failedPasses;
+                f.passed = E.passed; f.removed = E.removed; f.distance = E.distance; f.lastLK = E.lastLK;
+            }
+            if (f.needsUpdating && !f.passed.k) FSM_FAIL(s.err ? s.err : 2);
+            if (f.direction == 0) {
+                if (!(up[f.t1] == f.parent || up[f.t1] < 0) && (dist[f.t1] > eff || up[up[f.t1]] < 0)) {
+                    if (f.needsUpdating) {
+                        YIELD_MERGE(1, f.passed, f.distance / 2, false, tree_list(t, 0, f.t1), f.distance / 2, t.isTip[f.t1] != 0, true);
+                        f.midTot = f.resL;
+                        if (!f.midTot.k) continue;
+                        f.a2 = tree_list(t, 3, f.t1);
+                        if (f.a2.k) {
+                            YIELD_DIFFER(2, f.midTot, f.a2);
+                            if (!f.resB) f.needsUpdating = 0;
+                        }
+                    } else {
+                        f.midTot = tree_list(t, 3, f.t1);
+                        f.distance = dist[f.t1];
+                    }
+                    if (!f.midTot.k) continue;
+                    if (sp.deeperSearchForLongBranches && f.distance > sp.BLenThresholdDeeperSearch) {
+                        f.eMidTot = f.midTot; f.eDown = tree_list(t, 0, f.t1); f.eUp = up_list_for(m, t, s, f.t1); f.eDist = f.distance;
+                        f.eFromTip1 = t.isTip[f.t1] != 0; f.evalRet = 1;
+                        goto L_EVAL;
+                    L_EVAL_RET1:
+                        f.midProb = f.cost;
+                    } else {
+                        YIELD_APPEND(3, f.midTot, f.removed, f.isRemovedTip, f.removedBLen);
+                        f.midProb = f.resD;
+                        f.phase1++;
+                    }
+                    if (f.midProb > f.bestLKdiff - sp.thresholdLogLKoptimizationTopology) {  // :7071
+                        if (f.needsUpdating) { f.eUp = f.passed; f.eDist = f.distance; f.eMidTot = f.midTot; }
+                        else { f.eUp = up_list_for(m, t, s, f.t1); f.eDist = dist[f.t1]; f.eMidTot = tree_list(t, 3, f.t1); }
+                        f.eDown = tree_list(t, 0, f.t1);
+                        f.eFromTip1 = t.isTip[f.t1] != 0; f.evalRet = 2;
+                        goto L_EVAL;
+                    L_EVAL_RET2:;
+                    }
+                    if (f.midProb > f.bestLKdiff) {
+                        f.bestLKdiff = f.midProb;
+                        f.failedPasses = 0;
+                        f_shorten_inplace(m, f.removed);  // :7087
+                    } else if (f.midProb < (f.lastLK - sp.thresholdLogLKconsecutivePlacement)) f.failedPasses++;
+                } else f.midProb = f.lastLK;
+
+                {
+                    bool traverse = false;
+                    if (sp.strictTopologyStopRules) {
+                        if (f.failedPasses <= sp.allowedFailsTopology && f.midProb > (f.bestLKdiff - sp.thresholdLogLKtopology) && t.child0[f.t1] >= 0)
+                            traverse = true;
+                    } else if (f.failedPasses <= sp.allowedFailsTopology || f.midProb > (f.bestLKdiff - sp.thresholdLogLKtopology)) {
+                        if (t.child0[f.t1] >= 0) traverse = true;
+                    }
+                    if (!traverse) continue;
+                }
+                for (f.which = 0; f.which < 2; f.which++) {  // child 0 is pushed first, so child 1 is explored first
+                    f.otherChild = CH(f.t1, 1 - f.which);
+                    if (f.needsUpdating) {
+                        f.a2 = tree_list(t, 0, f.otherChild);
+                        if (n_mut(t, f.otherChild)) f.a2 = s_pass(m, t, s, f.a2, f.otherChild, true);
+                        YIELD_MERGE(4, f.passed, f.distance, false, f.a2, dist[f.otherChild], t.isTip[f.otherChild] != 0, true);
+                        f.vUp = f.resL;
+                    } else f.vUp = f.which == 0 ? tree_list(t, 1, f.t1) : tree_list(t, 2, f.t1);
+                    if (f.vUp.k) {
+                        const int c1 = CH(f.t1, f.which);
+                        LRef removed1 = f.removed;
+                        if (n_mut(t, c1)) removed1 = s_pass(m, t, s, f.removed, c1, false);
+                        if (f.needsUpdating && n_mut(t, c1)) f.vUp = s_pass(m, t, s, f.vUp, c1, false);
+                        FSM_PUSH(c1, 0, f.needsUpdating, f.needsUpdating ? f.vUp : lnull(), dist[c1], f.midProb, f.failedPasses, removed1);
+                    }
+                }
+            } else {  // crawling up from child to parent (:7179-7429)
+                f.otherChild = CH(f.t1, 2 - f.direction);
+                f.midBottom = lnull();
+                f.vectUp = lnull();
+                if (up[f.t1] >= 0 && (dist[f.t1] > eff || up[up[f.t1]] < 0)) {
+                    if (f.needsUpdating) {
+                        f.a2 = tree_list(t, 0, f.otherChild);
+                        if (n_mut(t, f.otherChild)) f.a2 = s_pass(m, t, s, f.a2, f.otherChild, true);
+                        YIELD_MERGE(5, f.passed, f.distance, false, f.a2, dist[f.otherChild], t.isTip[f.otherChild] != 0, false);
+                        f.midBottom = f.resL;
+                        if (!f.midBottom.k) continue;
+                        f.vectUp = up_list_for(m, t, s, f.t1);
+                        YIELD_MERGE(6, f.vectUp, dist[f.t1] / 2, false, f.midBottom, dist[f.t1] / 2, false, true);
+                        f.midTot = f.resL;
+                        if (!f.midTot.k) continue;
+                        f.a2 = tree_list(t, 3, f.t1);
+                        if (f.a2.k) {
+                            YIELD_DIFFER(7, f.midTot, f.a2);
+                            if (!f.resB) f.needsUpdating = 0;
+                        }
+                    } else f.midTot = tree_list(t, 3, f.t1);
+                    if (!f.midTot.k) continue;
+                    if (sp.deeperSearchForLongBranches && dist[f.t1] > sp.BLenThresholdDeeperSearch) {
+                        if (!f.needsUpdating) {
+                            f.midBottom = tree_list(t, 0, f.t1);
+                            f.vectUp = up_list_for(m, t, s, f.t1);
+                        }
+                        f.eMidTot = f.midTot; f.eDown = f.midBottom; f.eUp = f.vectUp; f.eDist = dist[f.t1]; f.eFromTip1 = 0; f.evalRet = 3;
+                        goto L_EVAL;
+                    L_EVAL_RET3:
+                        f.midProb = f.cost;
+                    } else {
+                        YIELD_APPEND(8, f.midTot, f.removed, f.isRemovedTip, f.removedBLen);
+                        f.midProb = f.resD;
+                        f.phase1++;
+                    }
+                    if (f.midProb >= (f.bestLKdiff - sp.thresholdLogLKoptimizationTopology)) {  // :7293
+                        if (f.needsUpdating) { f.eUp = f.vectUp; f.eDown = f.midBottom; f.eMidTot = f.midTot; }
+                        else { f.eUp = up_list_for(m, t, s, f.t1); f.eDown = tree_list(t, 0, f.t1); f.eMidTot = tree_list(t, 3, f.t1); }
+                        f.eDist = dist[f.t1];
+                        f.eFromTip1 = t.isTip[f.t1] != 0; f.evalRet = 4;
+                        goto L_EVAL;
+                    L_EVAL_RET4:;
+                    }
+                    if (f.midProb > f.bestLKdiff) { f.bestLKdiff = f.midProb; f.failedPasses = 0; }
+                    else if (f.midProb < (f.lastLK - sp.thresholdLogLKconsecutivePlacement)) f.failedPasses++;
+                } else f.midProb = f.lastLK;
+
+                {
+                    bool keep = false;
+                    if (sp.strictTopologyStopRules) {
+                        if (f.failedPasses <= sp.allowedFailsTopology && f.midProb > (f.bestLKdiff - sp.thresholdLogLKtopology)) keep = true;
+                    } else if (f.failedPasses <= sp.allowedFailsTopology || f.midProb > (f.bestLKdiff - sp.thresholdLogLKtopology)) keep = true;
+                    if (!keep) continue;
+                }
+                if (up[f.t1] >= 0) {
+                    if (f.needsUpdating) {
+                        f.a1 = up_list_for(m, t, s, f.t1);
+                        YIELD_MERGE(9, f.a1, dist[f.t1], false, f.passed, f.distance, false, true);
+                        f.vUp = f.resL;
+                    } else f.vUp = f.direction == 1 ? tree_list(t, 2, f.t1) : tree_list(t, 1, f.t1);
+                    if (!f.vUp.k) continue;
+                    {
+                        LRef removed1 = f.removed;
+                        if (n_mut(t, f.otherChild)) removed1 = s_pass(m, t, s, f.removed, f.otherChild, false);
+                        if (f.needsUpdating && n_mut(t, f.otherChild)) f.vUp = s_pass(m, t, s, f.vUp, f.otherChild, false);
+                        FSM_PUSH(f.otherChild, 0, f.needsUpdating, f.needsUpdating ? f.vUp : lnull(), dist[f.otherChild], f.midProb, f.failedPasses,
+                                 removed1);
+                    }
+                    if (f.needsUpdating && !f.midBottom.k) {
+                        f.a2 = tree_list(t, 0, f.otherChild);
+                        if (n_mut(t, f.otherChild)) f.a2 = s_pass(m, t, s, f.a2, f.otherChild, true);
+                        YIELD_MERGE(10, f.passed, f.distance, false, f.a2, dist[f.otherChild], t.isTip[f.otherChild] != 0, false);
+                        f.midBottom = f.resL;
+                        if (!f.midBottom.k) continue;
+                    }
+                    {
+                        const int upChild = (f.t1 == t.child0[up[f.t1]]) ? 0 : 1;
+                        LRef removed1 = f.removed;
+                        if (n_mut(t, f.t1)) removed1 = s_pass(m, t, s, f.removed, f.t1, true);
+                        if (f.needsUpdating && n_mut(t, f.t1)) f.midBottom = s_pass(m, t, s, f.midBottom, f.t1, true);
+                        FSM_PUSH(up[f.t1], upChild + 1, f.needsUpdating, f.needsUpdating ? f.midBottom : lnull(), dist[f.t1], f.midProb,
+                                 f.failedPasses, removed1);
+                    }
+                } else {  // t1 is the root (:7406-7429)
+                    f.vUp = lnull();
+                    if (f.needsUpdating) {
+                        f.vUp = s_root_vector(m, t, s, f.passed, f.distance, false);
+                        if (n_mut(t, f.otherChild)) f.vUp = s_pass(m, t, s, f.vUp, f.otherChild, false);
+                    }
+                    LRef removed1 = f.removed;
+                    if (n_mut(t, f.otherChild)) removed1 = s_pass(m, t, s, f.removed, f.otherChild, false);
+                    FSM_PUSH(f.otherChild, 0, f.needsUpdating, f.vUp, dist[f.otherChild], f.midProb, f.failedPasses, removed1);
+                }
+            }
+            continue;
+
+            // ---- evaluatePlacement (:6790-6806) [+ the rest of a phase-2 entry (:7510-7512, :7635-7639) for evalRet 2 and 4]
+        L_EVAL:
+            if (!f.eMidTot.k || !f.eDown.k || !f.eUp.k) FSM_FAIL(s.err ? s.err : 2);
+            f.mk = s.topK;
+            f.mp = s.topP;
+            YIELD_BLEN(20, f.eMidTot, f.removed, f.isRemovedTip);
+            f.bestAppending = f.resD;
+            YIELD_MERGE(21, f.eDown, f.eDist / 2, f.eFromTip1, f.removed, f.bestAppending, f.isRemovedTip, false);
+            f.midLower = f.resL;
+            if (!f.midLower.k) FSM_FAIL(s.err ? s.err : 2);
+            YIELD_BLEN(22, f.eUp, f.midLower, false);
+            f.bestTop = f.resD;
+            YIELD_MERGE(23, f.eUp, f.bestTop, false, f.removed, f.bestAppending, f.isRemovedTip, true);
+            f.midTop = f.resL;
+            if (!f.midTop.k) {
+                FSM_CHECK_ERR();
+                f.bestTop = sp.defaultBLen * 0.1;
+                YIELD_MERGE(24, f.eUp, f.bestTop, false, f.removed, f.bestAppending, f.isRemovedTip, true);
+                f.midTop = f.resL;
+                if (!f.midTop.k) FSM_FAIL(s.err ? s.err : 2);
+            }
+            YIELD_BLEN(25, f.midTop, f.eDown, f.eFromTip1);
+            f.bestBottom = f.resD;
+            YIELD_MERGE(26, f.eUp, f.bestTop, false, f.eDown, f.bestBottom, f.eFromTip1, true);
+            f.newMid = f.resL;
+            if (!f.newMid.k) FSM_FAIL(s.err ? s.err : 2);
+            YIELD_APPEND(27, f.newMid, f.removed, f.isRemovedTip, f.bestAppending);
+            f.cost = f.resD;
+            s.topK = f.mk;
+            s.topP = f.mp;
+            FSM_CHECK_ERR();
+            if (f.evalRet == 1) goto L_EVAL_RET1;
+            if (f.evalRet == 3) goto L_EVAL_RET3;
+            YIELD_APPEND(28, f.eUp, f.eDown, f.eFromTip1, f.eDist);
+            f.initialCost = f.resD;
+            YIELD_APPEND(29, f.eUp, f.eDown, f.eFromTip1, f.bestBottom + f.bestTop);
+            {
+                const double optimizedScore = f.cost + f.resD - f.initialCost;
+                if (optimizedScore >= f.ph.bestScore) {
+                    f.ph.bestNode = f.t1;
+                    f.ph.bestScore = optimizedScore;
+                    f.ph.bTop = f.bestTop;
+                    f.ph.bBottom = f.bestBottom;
+                    f.ph.bAppend = f.bestAppending;
+                }
+            }
+            if (f.evalRet == 2) goto L_EVAL_RET2;
+            goto L_EVAL_RET4;
+        }
+            f.rc = 0;
+            f.op = OP_DONE;
+            return;
+        default:
+            f.rc = 2;
+            f.op = OP_DONE;
+            return;
+    }
+#undef CH
+}
+
+// After a search finished: startTopologyUpdatesParallel's acceptance logic (:9681-9702)
+__device__ void fsm_finish(const Fsm& f, const DevTree& t, const SearchParams& sp, int node, double bestCurrentLK, SearchResult& r) {
+    r.phase1 = f.phase1;
+    r.status = f.rc;
+    if (f.rc != 0) return;
+    r.bestNode = f.ph.bestNode;
+    r.bestScore = f.ph.bestScore;
+    r.bLenTop = f.ph.bTop;
+    r.bLenBottom = f.ph.bBottom;
+    r.bLenAppend = f.ph.bAppend;
+    if (f.ph.bestScore + sp.thresholdTopologyPlacement > bestCurrentLK) {
+        bool updated = true;
+        int topNode = t.up[node];
+        if (f.ph.bestNode == topNode) updated = false;
+        while (t.dist[topNode] == 0.0 && t.up[topNode] >= 0) topNode = t.up[topNode];
+        if (f.ph.bestNode == topNode && f.ph.bBottom == 0.0) updated = false;
+        const int sibling = f.child == 0 ? t.child1[f.parent] : t.child0[f.parent];
+        if (f.ph.bestNode == sibling) updated = false;
+        if (t.up[f.ph.bestNode] == sibling && f.ph.bTop == 0.0) updated = false;
+        if (updated) {
+            r.improvement = f.ph.bestScore - bestCurrentLK;
+            r.placement = f.ph.bestNode;
+        }
+    }
+}
+
+}  // namespace maple

@@ -117,6 +117,10 @@ class MapleEngine:
             return a.to(device=self.device, dtype=dtype).contiguous()
         return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
 
+    def set_search_variant(self, variant: int):
+        """0 = warp-converged state-machine search kernel (default), 1 = straight-line kernel (A/B measurements)."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_search_variant(self.ctx, int(variant)), "maple_ctx_set_search_variant")
+
     @property
     def launches(self) -> int:
         return int(self.lib.maple_launch_count(self.ctx))

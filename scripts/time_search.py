@@ -20,7 +20,14 @@ print("setup %.1fs nodes %d arena %.1f MB" % (time.time() - t0, tree.n, tree.are
 nodes = dirty_nodes(tree)
 tree.prepare_search()
 L = math.log(d.model.lRef)
-for name, strict, fails, thr in (("fast", True, 2, 6.0 * L), ("deep", False, 4, 14.0 * L)):
+variants = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
+rounds = sys.argv[4].split(",") if len(sys.argv) > 4 else ["fast", "deep"]
+for variant in variants:
+  eng.set_search_variant(variant)
+  for name, strict, fails, thr in (("fast", True, 2, 6.0 * L), ("deep", False, 4, 14.0 * L)):
+    if name not in rounds:
+        continue
+    name = "v%d %s" % (variant, name)
     p = search_params(d.model.lRef, strict, fails, thr)
     for rep in range(2):
         torch.cuda.synchronize()
