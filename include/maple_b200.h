@@ -149,11 +149,13 @@ typedef struct {
 
 /* Tree arrays (DEVICE pointers, caller-owned; node = int index like the reference's Tree, :331-376):
  * up/child0/child1 with -1 for none, dist, isTip = no children and no minorSequences, optional MAT mutation lists
- * as CSR (mutStart[nNodes+1], mut = triples pos1,upNuc,downNuc) or NULL, and nkeys[4*nNodes] = entries per list.
+ * as CSR (mutStart[nNodes+1], mut = triples pos1,upNuc,downNuc) or NULL, nkeys[4*nNodes] = entries per list and
+ * npay[4*nNodes] = payload doubles per list (npay may be NULL: lists are then never staged in shared memory).
  * The bound arena must hold 4*nNodes lists: id = family*nNodes + node, family 0 probVect, 1 probVectUpRight,
  * 2 probVectUpLeft, 3 probVectTotUp. */
 int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t* up, const int32_t* child0, const int32_t* child1,
-                    const double* dist, const uint8_t* isTip, const int32_t* mutStart, const int32_t* mut, const int32_t* nkeys);
+                    const double* dist, const uint8_t* isTip, const int32_t* mutStart, const int32_t* mut, const int32_t* nkeys,
+                    const int32_t* npay);
 
 /* Search the n listed nodes (DEVICE int32) on the frozen tree; out = n records (DEVICE).  scratch_keys_per_search:
  * entries of per-search list scratch (0 = default 8192); max_concurrent_searches caps the resident threads (0 = fill
@@ -163,9 +165,18 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                            int64_t* out_cycles /* optional DEVICE int64[n]: SM clock cycles each search took; NULL to skip */,
                            void* stream);
 
-/* Which search kernel maple_spr_search_batch launches: 0 (default) = warp-converged state machine, 1 = the
- * straight-line one-search-per-thread kernel (kept for A/B measurements; same results). */
+/* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state
+ * machine, with subtrees whose lists are all stored ones scanned by the whole warp; 1 = the straight-line
+ * one-search-per-thread kernel; 2 = the state machine without warp scans (1, 2: kept for A/B measurements; same results). */
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
+
+/* Subtrees of at least minNodes nodes are scanned by the whole warp (default 8; 0 = never).  Tuning only: results do not
+ * depend on it. */
+int maple_ctx_set_scan_min_size(maple_ctx* ctx, int32_t minNodes);
+
+/* Profiling counters of the search kernel (32 uint64, meaning in DESIGN.md / scripts/time_search.py): enable != 0
+ * switches collection on for later launches; out != NULL receives and resets the counters (synchronises). */
+int maple_search_stats(maple_ctx* ctx, int32_t enable, uint64_t* out);
 
 /* Kernel launches issued by this context so far (bench.py reports it as gpu_launches). */
 int64_t maple_launch_count(const maple_ctx* ctx);

@@ -28,9 +28,11 @@ SIGNATURES = {
     "maple_vectors_differ_batch": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "maple_root_vector_batch": (C.c_int, [_P, _I64] + [_P] * 9 + [_I32, _P]),
     "maple_lists_copy": (C.c_int, [_P, _I64] + [_P] * 10 + [_P]),
-    "maple_tree_bind": (C.c_int, [_P, _I32, _I32] + [_P] * 8),
+    "maple_tree_bind": (C.c_int, [_P, _I32, _I32] + [_P] * 9),
     "maple_spr_search_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P]),
     "maple_ctx_set_search_variant": (C.c_int, [_P, _I32]),
+    "maple_ctx_set_scan_min_size": (C.c_int, [_P, _I32]),
+    "maple_search_stats": (C.c_int, [_P, _I32, _P]),
     "maple_launch_count": (_I64, [_P]),
 }
 

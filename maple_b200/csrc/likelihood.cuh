@@ -134,6 +134,135 @@ __device__ __forceinline__ double sel4(const double* v, int i) {
     return r;
 }
 
+// One informative site of appendProbNode (:6586-6761): multiplies F by the site's factor; false = the reference returns -inf.
+template <class Cur>
+__device__ __forceinline__ bool append_site(const DevModel& m, const Cur& e1, const Cur& e2, int pos, double bLen, bool isTipC, bool U,
+                                            double& F) {
+    // an informative site: one side at least is a single-site entry
+    double contrib = bLen;  // :6586-6599
+    if (e1.type < 5) {
+        if (e1.nl == 1) contrib += e1.l0();
+        else if (e1.nl == 2) contrib += e1.l1();
+    } else if (e1.nl == 1) contrib += e1.l0();
+    if (e2.nl == 1) contrib += e2.l0();
+    const SiteQ q(m, pos);
+    double t2[4], t3[4], a[4];
+    if (e1.type == T_R) {
+        if (e2.type == T_O) {  // :6611-6638
+            const int i1 = e2.nuc;
+            e2.vec(a);
+            const double ai = sel4(a, i1);
+            if (ai > 0.02) F *= ai;
+            else {
+                double tot;
+                if (e1.nl == 2) {
+                    const bool flag1 = U && e1.flag;
+                    const double eps = site_eps(m, pos);
+                    tot = 0.0;
+                    gv_vec(q, contrib, a, false, t3);
+                    gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) tot += t3[i] * t2[i] * m.pi[i];
+                    tot /= m.pi[i1];
+                } else if (contrib != 0.0) {
+                    gv_vec(q, contrib, a, false, t3);
+                    tot = sel4(t3, i1);
+                } else tot = ai;
+                F *= tot;
+            }
+        } else {  // R / different nucleotide :6640-6663
+            const bool flag2 = U && (isTipC || (e2.nl > 0 && e2.flag));
+            if (e1.nl == 2) {
+                const bool flag1 = U && e1.flag;
+                const int i1 = e2.nuc, i2 = e2.type;
+                const double eps = site_eps(m, pos);
+                gv_nuc(q, eps, i2, contrib, false, flag2, t3);
+                gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
+                double tot = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) tot += t3[i] * t2[i] * m.pi[i];
+                F *= tot / m.pi[i1];
+            } else if (flag2) {
+                const double eps = site_eps(m, pos);
+                F *= fmin(0.25, q.at(e2.nuc, e2.type) * contrib) + eps * 0.33333;
+            } else if (contrib != 0.0) {
+                F *= fmin(0.25, q.at(e2.nuc, e2.type) * contrib);
+            } else return false;
+        }
+    } else if (e1.type == T_O) {  // :6674-6703
+        e1.vec(a);
+        if (e2.type == T_O) {
+            double b[4];
+            e2.vec(b);
+            double tot = 0.0;
+            if (contrib != 0.0) {
+                gv_vec(q, contrib, b, false, t3);
+#pragma unroll
+                for (int j = 0; j < 4; j++) tot += a[j] * t3[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) tot += a[j] * b[j];
+            }
+            F *= tot;
+        } else {
+            const int i2 = (e2.type == T_R) ? e1.nuc : e2.type;
+            const double ai = sel4(a, i2);
+            if (ai > 0.02) F *= ai;
+            else {
+                const bool fl = U && (isTipC || (e2.nl > 0 && e2.flag));
+                const double eps = fl ? site_eps(m, pos) : 0.0;
+                gv_nuc(q, eps, i2, contrib, false, fl, t3);
+                double tot = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) tot += a[j] * t3[j];
+                F *= tot;
+            }
+        }
+    } else {  // e1 is a non-reference nucleotide, e2 differs :6713-6761
+        const bool flag1 = U && e1.nl > 0 && e1.flag;
+        const int i1 = e1.type;
+        if (e2.type < 5) {
+            const int i2 = (e2.type == T_R) ? e1.nuc : e2.type;
+            const bool flag2 = U && (isTipC || (e2.nl > 0 && e2.flag));
+            if (e1.nl == 2) {
+                const double eps = site_eps(m, pos);
+                gv_nuc(q, eps, i2, contrib, false, flag2, t3);
+                gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
+                double tot = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) tot += m.pi[j] * t3[j] * t2[j];
+                F *= tot / m.pi[i1];
+            } else if (flag1 || flag2) {
+                const double eps = site_eps(m, pos);
+                F *= (fmin(0.25, q.at(i1, i2) * contrib) + (double)(int(flag1) + int(flag2)) * 0.33333 * eps);
+            } else if (contrib != 0.0) {
+                F *= fmin(0.25, q.at(i1, i2) * contrib);
+            } else return false;
+        } else {  // nucleotide / O
+            e2.vec(a);
+            const double ai = sel4(a, i1);
+            if (ai > 0.02) F *= ai;
+            else if (e1.nl == 2) {
+                const double eps = site_eps(m, pos);
+                gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
+                gv_vec(q, contrib, a, false, t3);
+                double tot = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) tot += t2[i] * t3[i] * m.pi[i];
+                F *= (tot / m.pi[i1]);
+            } else if (contrib != 0.0) {
+                gv_vec(q, contrib, a, false, t3);
+                F *= sel4(t3, i1);
+            } else F *= ai;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ bool append_informative(int t1, int t2) {
+    return t1 != T_N && t2 != T_N && !(t1 == T_R && t2 == T_R) && !(t1 < 4 && t1 == t2);
+}
+
 // ------------------------------------------------------------------------------------------------
 // appendProbNode (:6505-6785)
 template <bool LD>
@@ -150,127 +279,50 @@ __device__ double dev_append(const DevModel& m, const uint32_t* kP, const double
     if (U && isTipC) Lk += m.totError;
     for (;;) {
         const int newPos = min(e1.end, e2.end);
-        if (e1.type != T_N && e2.type != T_N && !(e1.type == T_R && e2.type == T_R) && !(e1.type < 4 && e1.type == e2.type)) {
-            // an informative site: one side at least is a single-site entry
-            double contrib = bLen;  // :6586-6599
-            if (e1.type < 5) {
-                if (e1.nl == 1) contrib += e1.l0();
-                else if (e1.nl == 2) contrib += e1.l1();
-            } else if (e1.nl == 1) contrib += e1.l0();
-            if (e2.nl == 1) contrib += e2.l0();
-            const SiteQ q(m, pos);
-            double t2[4], t3[4], a[4];
-            if (e1.type == T_R) {
-                if (e2.type == T_O) {  // :6611-6638
-                    const int i1 = e2.nuc;
-                    e2.vec(a);
-                    const double ai = sel4(a, i1);
-                    if (ai > 0.02) F *= ai;
-                    else {
-                        double tot;
-                        if (e1.nl == 2) {
-                            const bool flag1 = U && e1.flag;
-                            const double eps = site_eps(m, pos);
-                            tot = 0.0;
-                            gv_vec(q, contrib, a, false, t3);
-                            gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
-#pragma unroll
-                            for (int i = 0; i < 4; i++) tot += t3[i] * t2[i] * m.pi[i];
-                            tot /= m.pi[i1];
-                        } else if (contrib != 0.0) {
-                            gv_vec(q, contrib, a, false, t3);
-                            tot = sel4(t3, i1);
-                        } else tot = ai;
-                        F *= tot;
-                    }
-                } else {  // R / different nucleotide :6640-6663
-                    const bool flag2 = U && (isTipC || (e2.nl > 0 && e2.flag));
-                    if (e1.nl == 2) {
-                        const bool flag1 = U && e1.flag;
-                        const int i1 = e2.nuc, i2 = e2.type;
-                        const double eps = site_eps(m, pos);
-                        gv_nuc(q, eps, i2, contrib, false, flag2, t3);
-                        gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
-                        double tot = 0.0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) tot += t3[i] * t2[i] * m.pi[i];
-                        F *= tot / m.pi[i1];
-                    } else if (flag2) {
-                        const double eps = site_eps(m, pos);
-                        F *= fmin(0.25, q.at(e2.nuc, e2.type) * contrib) + eps * 0.33333;
-                    } else if (contrib != 0.0) {
-                        F *= fmin(0.25, q.at(e2.nuc, e2.type) * contrib);
-                    } else return -INFINITY;
-                }
-            } else if (e1.type == T_O) {  // :6674-6703
-                e1.vec(a);
-                if (e2.type == T_O) {
-                    double b[4];
-                    e2.vec(b);
-                    double tot = 0.0;
-                    if (contrib != 0.0) {
-                        gv_vec(q, contrib, b, false, t3);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) tot += a[j] * t3[j];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) tot += a[j] * b[j];
-                    }
-                    F *= tot;
-                } else {
-                    const int i2 = (e2.type == T_R) ? e1.nuc : e2.type;
-                    const double ai = sel4(a, i2);
-                    if (ai > 0.02) F *= ai;
-                    else {
-                        const bool fl = U && (isTipC || (e2.nl > 0 && e2.flag));
-                        const double eps = fl ? site_eps(m, pos) : 0.0;
-                        gv_nuc(q, eps, i2, contrib, false, fl, t3);
-                        double tot = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) tot += a[j] * t3[j];
-                        F *= tot;
-                    }
-                }
-            } else {  // e1 is a non-reference nucleotide, e2 differs :6713-6761
-                const bool flag1 = U && e1.nl > 0 && e1.flag;
-                const int i1 = e1.type;
-                if (e2.type < 5) {
-                    const int i2 = (e2.type == T_R) ? e1.nuc : e2.type;
-                    const bool flag2 = U && (isTipC || (e2.nl > 0 && e2.flag));
-                    if (e1.nl == 2) {
-                        const double eps = site_eps(m, pos);
-                        gv_nuc(q, eps, i2, contrib, false, flag2, t3);
-                        gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
-                        double tot = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) tot += m.pi[j] * t3[j] * t2[j];
-                        F *= tot / m.pi[i1];
-                    } else if (flag1 || flag2) {
-                        const double eps = site_eps(m, pos);
-                        F *= (fmin(0.25, q.at(i1, i2) * contrib) + (double)(int(flag1) + int(flag2)) * 0.33333 * eps);
-                    } else if (contrib != 0.0) {
-                        F *= fmin(0.25, q.at(i1, i2) * contrib);
-                    } else return -INFINITY;
-                } else {  // nucleotide / O
-                    e2.vec(a);
-                    const double ai = sel4(a, i1);
-                    if (ai > 0.02) F *= ai;
-                    else if (e1.nl == 2) {
-                        const double eps = site_eps(m, pos);
-                        gv_nuc(q, eps, i1, e1.l0(), false, flag1, t2);
-                        gv_vec(q, contrib, a, false, t3);
-                        double tot = 0.0;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) tot += t2[i] * t3[i] * m.pi[i];
-                        F *= (tot / m.pi[i1]);
-                    } else if (contrib != 0.0) {
-                        gv_vec(q, contrib, a, false, t3);
-                        F *= sel4(t3, i1);
-                    } else F *= ai;
-                }
-            }
+        if (append_informative(e1.type, e2.type)) {
+            if (!append_site(m, e1, e2, pos, bLen, isTipC, U, F)) return -INFINITY;
         }
         pos = newPos;
+        if (pos == lRef) break;
+        if (e1.end == pos) e1.next();
+        if (e2.end == pos) e2.next();
+        if (F <= kMinCarryOver) {  // :6772-6783
+            if (F < DBL_MIN) return -INFINITY;
+            Lk += log(F);
+            F = 1.0;
+        }
+    }
+    if (!(F > 0.0)) return -INFINITY;
+    return Lk + log(F);
+}
+
+// appendProbNode again, same arithmetic in the same order, arranged for a warp whose lanes score different pairs at
+// once: every lane first walks (cheap loop) to its next informative site, then the lanes evaluate one site each
+// together, so the long site code runs once per "k-th site of every lane" instead of once per segment of any lane.
+template <bool LD>
+__device__ double dev_append_sitewise(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC,
+                                      bool isTipC, double bLen) {
+    const int lRef = m.lRef;
+    const bool U = m.U != 0;
+    Cursor<LD> e1, e2;
+    e1.init(kP, pP);
+    e2.init(kC, pC);
+    int pos = 0;
+    double F = 1.0;
+    double Lk = bLen * (-(double)lRef);
+    if (U && isTipC) Lk += m.totError;
+    for (;;) {
+        bool site = false;
+        for (;;) {  // segments that contribute nothing leave F untouched, so the carry-over test has nothing to do
+            if (append_informative(e1.type, e2.type)) { site = true; break; }
+            pos = min(e1.end, e2.end);
+            if (pos == lRef) break;
+            if (e1.end == pos) e1.next();
+            if (e2.end == pos) e2.next();
+        }
+        if (!site) break;
+        if (!append_site(m, e1, e2, pos, bLen, isTipC, U, F)) return -INFINITY;
+        pos = min(e1.end, e2.end);
         if (pos == lRef) break;
         if (e1.end == pos) e1.next();
         if (e2.end == pos) e2.next();

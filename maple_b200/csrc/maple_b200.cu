@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/maple_b200.h"
 #include "likelihood.cuh"
@@ -30,11 +31,16 @@ struct maple_ctx {
     // tree bound for the search (device pointers, caller-owned)
     DevTree tree{};
     bool haveTree = false;
+    int32_t* treeDerived = nullptr;  // order | pre | size | depth (int32[nNodes] each) then mutBelow (uint8[nNodes]); owned
+    int treeHeight = 0;
+    unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
+    bool statsOn = false;
+    int scanMinSize = 8;             // subtrees of at least this many nodes are scanned by the whole warp (0 = never)
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
-    int searchVariant = 0;  // 0 = warp-converged state machine (default), 1 = straight-line one-search-per-thread kernel
+    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
@@ -225,8 +231,22 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_
                                                                    const int32_t* __restrict__ nodes, SearchResult* __restrict__ out,
                                                                    uint32_t* scrKey, double* scrPay, double* scrAis, StackE* scrStack,
                                                                    unsigned capK, unsigned capP, unsigned capA, int stackCap,
-                                                                   unsigned long long* counter, long long* outCycles) {
+                                                                   unsigned long long* counter, long long* outCycles, int scanMinSize,
+                                                                   unsigned long long* stats) {
     __shared__ DevModel sm;
+    __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
+    unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
+    if (stats) {
+        for (int i = threadIdx.x; i < (kSearchThreads / 32) * kNumSearchStats; i += blockDim.x) (&wst[0][0])[i] = 0ULL;
+        st = wst[threadIdx.x >> 5];
+        __syncthreads();
+    }
+    const bool l0 = (threadIdx.x & 31) == 0;
+    extern __shared__ uint4 dynSmem[];
+    ScanSmem& W = reinterpret_cast<ScanSmem*>(dynSmem)[threadIdx.x >> 5];
+    long long tk = clock64();
+#define STAT_T(i) do { if (st) { const long long now_ = clock64(); if (l0) st[i] += (unsigned long long)(now_ - tk); tk = now_; } } while (0)
+#define STAT_N(i, v) do { if (st && l0) st[i] += (unsigned long long)(v); } while (0)
     stage_model(sm, gm);
     const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     ScratchD s;
@@ -247,7 +267,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_
     for (;;) {
         // ---------------- control (divergent, cheap)
         if (stage == 2) {
-            fsm_step(f, sm, T, sp, s, stack, stackCap);
+            fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
         } else if (stage == 1) {
             bestCurrentLK = f.resD;
             r.bestCurrentLK = bestCurrentLK;
@@ -265,7 +285,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_
                 f.rc = 0;
                 s.topK = s.topP = 0;
                 stage = 2;
-                fsm_step(f, sm, T, sp, s, stack, stackCap);
+                fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
             }
         }
         while (stage != 3 && (stage == 0 || f.op == OP_DONE)) {
@@ -297,8 +317,17 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_
         }
         // ---------------- co-walks, one kind at a time, lanes converged
         __syncwarp();
+        STAT_T(0);
+        if (stats) {
+            const unsigned b1 = __ballot_sync(0xffffffffu, f.op == OP_APPEND), b2 = __ballot_sync(0xffffffffu, f.op == OP_MERGE),
+                           b3 = __ballot_sync(0xffffffffu, f.op == OP_BLEN), b4 = __ballot_sync(0xffffffffu, f.op == OP_DIFFER);
+            STAT_N(8, __popc(b1)); STAT_N(9, __popc(b2)); STAT_N(10, __popc(b3)); STAT_N(11, __popc(b4));
+            STAT_N(12, b1 != 0); STAT_N(13, b2 != 0); STAT_N(14, b3 != 0); STAT_N(15, b4 != 0); STAT_N(16, 1);
+            tk = clock64();
+        }
         if (f.op == OP_APPEND) f.resD = f_append(sm, f.a1, f.a2, f.at1 != 0, f.ab1);
         __syncwarp();
+        STAT_T(1);
         if (f.op == OP_MERGE) {
             Writer w;
             w.init(s.key + s.topK, s.pay + s.topP);
@@ -306,11 +335,29 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_
             else f.resL = lnull();
         }
         __syncwarp();
+        STAT_T(2);
         if (f.op == OP_BLEN) f.resD = f_blen(sm, f.a1, f.a2, f.at1 != 0, s.ais);
         __syncwarp();
+        STAT_T(3);
         if (f.op == OP_DIFFER) f.resB = f_differ(sm, f.a1, f.a2) ? 1 : 0;
+        __syncwarp();
+        STAT_T(4);
+        // ---------------- subtree scans: the whole warp works for one lane's search at a time
+        for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1)
+            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, st);
+        STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
     }
+    if (stats) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kNumSearchStats; i += blockDim.x) {
+            unsigned long long v = 0;
+            for (int w = 0; w < kSearchThreads / 32; w++) v += wst[w][i];
+            if (v) atomicAdd(stats + i, v);
+        }
+    }
+#undef STAT_T
+#undef STAT_N
 }
 
 // grid: whole waves of CTAs (multiples of the SM count), capped by the work
@@ -369,6 +416,8 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->devStage);
     cudaFree(ctx->searchScratch);
     cudaFree(ctx->searchCounter);
+    cudaFree(ctx->treeDerived);
+    cudaFree(ctx->searchStats);
     delete ctx;
     return MAPLE_OK;
 }
@@ -573,7 +622,7 @@ int maple_lists_copy(maple_ctx* ctx, int64_t n, const uint32_t* src_key, const d
 }
 
 int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t* up, const int32_t* child0, const int32_t* child1,
-                    const double* dist, const uint8_t* isTip, const int32_t* mutStart, const int32_t* mut, const int32_t* nkeys) {
+                    const double* dist, const uint8_t* isTip, const int32_t* mutStart, const int32_t* mut, const int32_t* nkeys, const int32_t* npay) {
     if (!ctx || nNodes <= 0 || root < 0 || root >= nNodes || !up || !child0 || !child1 || !dist || !isTip || !nkeys) return MAPLE_E_ARG;
     if (!ctx->haveLists || ctx->nLists < 4 * (int64_t)nNodes) {
         ctx->err = "maple_tree_bind: bind an arena with 4*nNodes lists first (list id = family*nNodes + node)";
@@ -581,7 +630,54 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
     }
     DevTree& t = ctx->tree;
     t.nNodes = nNodes; t.root = root; t.up = up; t.child0 = child0; t.child1 = child1; t.dist = dist; t.isTip = isTip;
-    t.mutStart = mutStart; t.mut = mut; t.nkeys = nkeys;
+    t.mutStart = mutStart; t.mut = mut; t.nkeys = nkeys; t.npay = npay;
+    // Derived arrays for the warp-cooperative subtree scans: the order in which findBestParentTopology walks down a
+    // subtree (children pushed 0 then 1, so child 1 is explored first, :7112-7170), subtree sizes and depths.
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)nNodes;
+    std::vector<int32_t> hUp(n), hC0(n), hC1(n), hMs;
+    CK(cudaMemcpy(hUp.data(), up, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hC0.data(), child0, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hC1.data(), child1, n * 4, cudaMemcpyDeviceToHost));
+    if (mutStart) {
+        hMs.resize(n + 1);
+        CK(cudaMemcpy(hMs.data(), mutStart, (n + 1) * 4, cudaMemcpyDeviceToHost));
+    }
+    std::vector<int32_t> der(4 * n + (n + 3) / 4, 0);
+    int32_t *order = der.data(), *pre = order + n, *size = pre + n, *depth = size + n;
+    uint8_t* mutBelow = reinterpret_cast<uint8_t*>(depth + n);
+    for (size_t i = 0; i < n; i++) { pre[i] = -1; size[i] = 1; }
+    std::vector<int32_t> st;
+    st.push_back(root);
+    depth[root] = 0;
+    size_t cnt = 0;
+    int height = 0;
+    while (!st.empty()) {
+        const int32_t v = st.back();
+        st.pop_back();
+        if (cnt >= n || pre[v] >= 0) { ctx->err = "maple_tree_bind: up/child arrays do not describe a tree"; return MAPLE_E_ARG; }
+        pre[v] = (int32_t)cnt;
+        order[cnt++] = v;
+        if (depth[v] > height) height = depth[v];
+        if (hC0[v] >= 0) {
+            if (hC0[v] >= nNodes || hC1[v] < 0 || hC1[v] >= nNodes) { ctx->err = "maple_tree_bind: bad child index"; return MAPLE_E_ARG; }
+            depth[hC0[v]] = depth[hC1[v]] = depth[v] + 1;
+            st.push_back(hC0[v]);
+            st.push_back(hC1[v]);
+        }
+    }
+    for (size_t i = cnt; i-- > 1;) {  // children come after their parent in pre-order
+        const int32_t v = order[i], p = hUp[v];
+        size[p] += size[v];
+        if (mutBelow[v] || (mutStart && hMs[v + 1] > hMs[v])) mutBelow[p] = 1;
+    }
+    cudaFree(ctx->treeDerived);
+    ctx->treeDerived = nullptr;
+    CK(cudaMalloc((void**)&ctx->treeDerived, der.size() * 4));
+    CK(cudaMemcpy(ctx->treeDerived, der.data(), der.size() * 4, cudaMemcpyHostToDevice));
+    t.order = ctx->treeDerived; t.pre = t.order + n; t.size = t.pre + n; t.depth = t.size + n;
+    t.mutBelow = reinterpret_cast<const uint8_t*>(t.depth + n);
+    ctx->treeHeight = height;
     ctx->haveTree = true;
     return MAPLE_OK;
 }
@@ -602,10 +698,15 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
     const unsigned capK = (unsigned)((scratch_keys_per_search > 0 ? scratch_keys_per_search : 8192) + 3) & ~3u;
     const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
-    const int stackCap = 512;
+    const int stackCap = ctx->treeHeight + 16 > 512 ? ((2 * ctx->treeHeight + 16 + 63) & ~63) : 512;
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search_fsm, kSearchThreads, 0));
+    const size_t fsmSmem = (kSearchThreads / 32) * sizeof(ScanSmem);
+    if (ctx->searchVariant != 1) {
+        CK(cudaFuncSetAttribute(k_spr_search_fsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
+        CK(cudaFuncSetAttribute(k_spr_search_fsm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search_fsm, kSearchThreads, fsmSmem));
+    }
     if (blocksPerSM < 1) blocksPerSM = 1;
     int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
     if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches;
@@ -633,17 +734,40 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                                                                          scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
                                                                          (long long*)out_cycles);
     else
-        k_spr_search_fsm<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
+        k_spr_search_fsm<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
                                                                              scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
-                                                                             (long long*)out_cycles);
+                                                                             (long long*)out_cycles, (T.order && ctx->searchVariant == 0) ? ctx->scanMinSize : 0,
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     return MAPLE_OK;
 }
 
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
-    if (!ctx || variant < 0 || variant > 1) return MAPLE_E_ARG;
+    if (!ctx || variant < 0 || variant > 2) return MAPLE_E_ARG;
     ctx->searchVariant = variant;
+    return MAPLE_OK;
+}
+
+int maple_search_stats(maple_ctx* ctx, int32_t enable, uint64_t* out) {
+    if (!ctx) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->searchStats) {
+        CK(cudaMalloc((void**)&ctx->searchStats, kNumSearchStats * 8));
+        CK(cudaMemset(ctx->searchStats, 0, kNumSearchStats * 8));
+    }
+    if (out) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(out, ctx->searchStats, kNumSearchStats * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(ctx->searchStats, 0, kNumSearchStats * 8));
+    }
+    ctx->statsOn = enable != 0;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_scan_min_size(maple_ctx* ctx, int32_t minNodes) {
+    if (!ctx || minNodes < 0) return MAPLE_E_ARG;
+    ctx->scanMinSize = minNodes;
     return MAPLE_OK;
 }
 

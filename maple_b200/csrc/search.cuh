@@ -32,6 +32,13 @@ struct DevTree {
     const double* pay;
     const int64_t *keyStart, *payStart;
     const int32_t* nkeys;
+    const int32_t* npay;      // payload doubles per list, or nullptr (then lists are read where they lie)
+    // derived by maple_tree_bind for the warp-cooperative subtree scans (search_fsm.cuh); order == nullptr disables them
+    const int32_t* order;     // [nNodes] nodes in the search's own pre-order: a node, then the subtree of child 1, then of child 0
+    const int32_t* pre;       // position of a node in `order` (-1: not reachable from the root)
+    const int32_t* size;      // nodes in the subtree of a node (itself included)
+    const int32_t* depth;     // edges between the root and a node
+    const uint8_t* mutBelow;  // some node strictly below carries MAT mutations
 };
 
 struct SearchParams {

@@ -15,7 +15,9 @@
 
 namespace maple {
 
-enum FsmOp { OP_NONE = 0, OP_APPEND = 1, OP_MERGE = 2, OP_BLEN = 3, OP_DIFFER = 4, OP_DONE = 5 };
+constexpr int kNumSearchStats = 32;
+
+enum FsmOp { OP_NONE = 0, OP_APPEND = 1, OP_MERGE = 2, OP_BLEN = 3, OP_DIFFER = 4, OP_DONE = 5, OP_SCAN = 6 };
 
 struct Fsm {
     int pc, op;
@@ -37,6 +39,14 @@ struct Fsm {
     double eDist, bestAppending, bestTop, bestBottom, cost, initialCost;
     int eFromTip1, eT1, evalRet;
     unsigned mk, mp;
+    // subtree scan (warp_scan_job): phase-2 entries it found, waiting to be evaluated
+    int qN, qi, scanNewBest;
+    unsigned qRes;
+};
+
+struct PathE {  // per-depth state of a subtree scan: what a node hands to its children (lastLK, failedPasses)
+    double lk;
+    int failed, pad;
 };
 
 #define FSM_FAIL(code)          \
@@ -98,7 +108,8 @@ struct Fsm {
     } while (0)
 
 // Runs the search of f until it needs a co-walk (f.op says which) or finishes (f.op == OP_DONE, f.rc = status).
-__device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack, int stackCap) {
+__device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack, int stackCap,
+                         int scanMinSize) {
     const int32_t* up = t.up;
     const double* dist = t.dist;
     const double eff = sp.effectivelyNon0BLen;
@@ -170,6 +181,30 @@ __device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const Sear
                 f.passed = E.passed; f.removed = E.removed; f.distance = E.distance; f.lastLK = E.lastLK;
             }
             if (f.needsUpdating && !f.passed.k) FSM_FAIL(s.err ? s.err : 2);
+            if (f.direction == 0 && !f.needsUpdating && scanMinSize > 0 && t.size[f.t1] >= scanMinSize && !t.mutBelow[f.t1] &&
+                !sp.deeperSearchForLongBranches) {
+                // The passed partials have converged to the stored ones: everything below t1 is scored against stored
+                // lists only, so the whole warp walks this subtree together (warp_scan_job) and hands back the new
+                // running best, the number of candidates scored and the phase-2 entries it met, in discovery order.
+                f.op = OP_SCAN;
+                f.pc = 30;
+                return;
+                case 30:;
+                FSM_CHECK_ERR();
+                if (f.scanNewBest) f_shorten_inplace(m, f.removed);  // :7087
+                f.qRes = (unsigned(f.qN) + 3u) & ~3u;
+                s.capK -= f.qRes;  // the queue sits at the top end of the key scratch
+                for (f.qi = 0; f.qi < f.qN; f.qi++) {
+                    f.t1 = int(s.key[s.capK + f.qRes - 1u - unsigned(f.qi)]);
+                    f.eUp = up_list_for(m, t, s, f.t1); f.eDist = dist[f.t1]; f.eMidTot = tree_list(t, 3, f.t1);
+                    f.eDown = tree_list(t, 0, f.t1);
+                    f.eFromTip1 = t.isTip[f.t1] != 0; f.evalRet = 5;
+                    goto L_EVAL;
+                L_EVAL_RET5:;
+                }
+                s.capK += f.qRes;
+                continue;
+            }
             if (f.direction == 0) {
                 if (!(up[f.t1] == f.parent || up[f.t1] < 0) && (dist[f.t1] > eff || up[up[f.t1]] < 0)) {
                     if (f.needsUpdating) {
@@ -382,6 +417,7 @@ __device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const Sear
                 }
             }
             if (f.evalRet == 2) goto L_EVAL_RET2;
+            if (f.evalRet == 5) goto L_EVAL_RET5;
             goto L_EVAL_RET4;
         }
             f.rc = 0;
@@ -393,6 +429,235 @@ __device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const Sear
             return;
     }
 #undef CH
+}
+
+
+// ---- warp-cooperative subtree scan -----------------------------------------------------------------------------
+// Lane `src` popped a stack entry (t1, direction 0, needsUpdating False) whose subtree carries no MAT mutations.  From
+// there on the reference's walk (:6975-7170) only reads STORED lists: at every node below, the candidate score is
+// appendProbNode(probVectTotUp[node], removedPartials, ...) and whether a node is scored at all was decided when its
+// parent was processed.  In the search's pre-order (DevTree::order) the subtree is a contiguous range, a pruned
+// subtree is a contiguous sub-range, and what a node inherits from its parent (lastLK, failedPasses) is a per-depth
+// value.  So the warp takes a window of the range holding up to 32 nodes that need a score, copies their mid-branch
+// lists (and once per job the removed list) into shared memory, scores them one per lane -- all lanes inside
+// appendProbNode at once, walking shared memory -- then replays the reference's sequential bookkeeping over the window
+// in order: running best, failure counters, stop rule, jumping over the ranges the stop rule prunes.  Scores of nodes
+// that turn out to be pruned are discarded; nothing the reference would not have scored is counted or kept.
+constexpr int kWinMax = 96;      // nodes per window
+constexpr int kPathSm = 40;      // per-depth states kept in shared memory (deeper ones go to global scratch)
+constexpr int kCKeys = 64;       // removed list staged in shared memory when it has at most this many entries ...
+constexpr int kCPay = 96;        // ... and this many payload doubles
+constexpr int kPoolBytes = 9216; // mid-branch lists of one batch
+struct ScanSmem {
+    double winScore[kWinMax];
+    double cPay[kCPay];
+    PathE path[kPathSm];
+    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax];
+    uint32_t cKey[kCKeys];
+    uint4 pool[kPoolBytes / 16];
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += x;
+    }
+    return v;
+}
+
+__device__ __noinline__ double f_append_sitewise(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC,
+                                                 bool isTipC, double bLen) {
+    return dev_append_sitewise<false>(m, kP, pP, kC, pC, isTipC, bLen);
+}
+
+__device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack,
+                              int stackCap, ScanSmem& W, unsigned long long* st) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int R = __shfl_sync(FULL, f.t1, src);
+    const int prunedParent = __shfl_sync(FULL, f.parent, src);
+    double best = __shfl_sync(FULL, f.bestLKdiff, src);
+    const double lastLK0 = __shfl_sync(FULL, f.lastLK, src);
+    const int failed0 = __shfl_sync(FULL, f.failedPasses, src);
+    const double removedBLen = __shfl_sync(FULL, f.removedBLen, src);
+    const bool isRemovedTip = __shfl_sync(FULL, f.isRemovedTip, src) != 0;
+    const uint32_t* remK = reinterpret_cast<const uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(f.removed.k), src));
+    const double* remP = reinterpret_cast<const double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(f.removed.p), src));
+    // deep per-depth state lives in the unused part of lane src's DFS stack; the phase-2 queue grows down from the top of its key scratch
+    PathE* gpath = reinterpret_cast<PathE*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(stack + f.spN), src));
+    const int pathCap = int((size_t)(stackCap - __shfl_sync(FULL, f.spN, src)) * sizeof(StackE) / sizeof(PathE));
+    uint32_t* qTop = reinterpret_cast<uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(s.key + s.capK), src));
+    const int qCap = int(__shfl_sync(FULL, s.capK - s.topK, src)) - 8;
+    const double eff = sp.effectivelyNon0BLen;
+    const int64_t nN = t.nNodes;
+    int phase1 = 0, qN = 0, newBest = 0, err = 0;
+    int pos = t.pre[R];
+    const int end = pos + t.size[R], d0 = t.depth[R];
+    long long tk = st ? clock64() : 0;
+    if (st && lane == 0) { st[17] += 1; st[18] += (unsigned long long)(end - pos); }
+    __syncwarp();  // the previous job's shared-memory reads are over
+    // ---- the removed list: the same for every candidate of the job
+    {
+        int nk = 0;  // entries up to the one that ends at lRef
+        for (int base = 0; base < kCKeys && nk == 0; base += 32) {
+            const uint32_t k = remK[base + lane];  // reading past the end stays inside the owner's scratch / the arena slack
+            const unsigned hit = __ballot_sync(FULL, int(k >> 8) == m.lRef);
+            if (hit) nk = base + __ffs(hit);
+        }
+        int np = kCPay + 1;
+        if (nk) {
+            int mine = 0;
+            for (int i = lane; i < nk; i += 32) {
+                const uint32_t k = remK[i];
+                mine += int((k >> 3) & 3u) + (((k & 7u) == 6u) ? 4 : 0);
+            }
+            np = __shfl_sync(FULL, warp_incl_scan(mine, lane), 31);
+        }
+        if (nk && np <= kCPay) {
+            for (int i = lane; i < nk; i += 32) W.cKey[i] = remK[i];
+            for (int i = lane; i < np; i += 32) W.cPay[i] = remP[i];
+            remK = W.cKey;
+            remP = W.cPay;
+        }
+    }
+    if (pathCap < 2) err = 3;
+    else if (lane == 0) W.path[0] = PathE{lastLK0, failed0, 0};
+    __syncwarp();
+    while (pos < end && !err) {
+        // ---- window: nodes pos .. pos+nWin-1, at most 32 of them need a score
+        int nWin = 0, nScore = 0;
+        int myW = -1;  // window position this lane scores
+        for (int sweep = 0; sweep < kWinMax / 32 && pos + nWin < end && nScore < 32; sweep++) {
+            const int w = nWin + lane, idx = pos + w;
+            int info = 0;  // bit0 eligible, bit1 has probVectTotUp, bit2 was pushed (parent's upper list exists), bit3 internal, bits 8.. relative depth
+            if (idx < end) {
+                const int node = t.order[idx];
+                const int up = t.up[node];
+                const bool elig = !(up == prunedParent || up < 0) && (t.dist[node] > eff || t.up[up] < 0);
+                const bool hasTot = t.keyStart[3 * nN + node] >= 0;
+                const bool pushed = node == R || t.keyStart[(t.child0[up] == node ? 1 : 2) * nN + up] >= 0;
+                info = (elig ? 1 : 0) | (hasTot ? 2 : 0) | (pushed ? 4 : 0) | (t.child0[node] >= 0 ? 8 : 0) | ((t.depth[node] - d0) << 8);
+                W.winInfo[w] = info;
+                W.winSize[w] = t.size[node];
+                W.winNode[w] = node;
+            }
+            const unsigned need = __ballot_sync(FULL, (info & 7) == 7);
+            const int room = 32 - nScore;
+            int take = min(32, end - pos - nWin);  // nodes of this sweep that join the window
+            if (__popc(need) > room) {             // cut right after the node that fills the last lane
+                unsigned x = need;
+                for (int i = 1; i < room; i++) x &= x - 1;
+                take = __ffs(x);                   // position (1-based) of the room-th set bit
+            }
+            const unsigned mine = need & (take >= 32 ? FULL : ((1u << take) - 1u));
+            // the k-th node that needs a score goes to lane nScore + k
+            for (unsigned x = mine; x; x &= x - 1) {
+                const int b = __ffs(x) - 1;
+                if (lane == nScore + __popc(mine & ((1u << b) - 1u))) myW = nWin + b;
+            }
+            nScore += __popc(mine);
+            nWin += take;
+        }
+        __syncwarp();
+        // ---- copy the lists to shared memory (16-byte loads, all in flight together) and score, one candidate per lane
+        {
+            const uint32_t* kP = nullptr;
+            const double* pP = nullptr;
+            int bytes = 0, nk4 = 0, np2 = 0;
+            if (myW >= 0) {
+                const int64_t id = 3 * nN + W.winNode[myW];
+                kP = t.key + t.keyStart[id];
+                pP = t.pay + t.payStart[id];
+                if (t.npay && ((reinterpret_cast<uintptr_t>(kP) | reinterpret_cast<uintptr_t>(pP)) & 15) == 0) {
+                    nk4 = (t.nkeys[id] + 3) >> 2;
+                    np2 = (t.npay[id] + 1) >> 1;
+                    bytes = (nk4 + np2) * 16;
+                }
+            }
+            const int endOff = warp_incl_scan(bytes, lane);
+            if (bytes && endOff <= kPoolBytes) {
+                uint4* dk = W.pool + ((endOff - bytes) >> 4);
+                uint4* dp = dk + nk4;
+                const uint4* gk = reinterpret_cast<const uint4*>(kP);
+                const uint4* gp = reinterpret_cast<const uint4*>(pP);
+#pragma unroll 4
+                for (int i = 0; i < nk4; i++) dk[i] = gk[i];
+#pragma unroll 4
+                for (int i = 0; i < np2; i++) dp[i] = gp[i];
+                kP = reinterpret_cast<const uint32_t*>(dk);
+                pP = reinterpret_cast<const double*>(dp);
+            }
+            if (st) {
+                const long long now = clock64();
+                if (lane == 0) { st[23] += (unsigned long long)(now - tk); st[19] += 1; st[20] += nScore; st[24] += nWin; }
+                tk = now;
+            }
+            if (myW >= 0) W.winScore[myW] = f_append_sitewise(m, kP, pP, remK, remP, isRemovedTip, removedBLen);
+        }
+        __syncwarp();
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) st[6] += (unsigned long long)(now - tk);
+            tk = now;
+        }
+        // ---- replay, every lane the same
+        int j = 0;
+        while (j < nWin) {
+            const int inf = W.winInfo[j];
+            const int rel = inf >> 8;
+            bool descend = false;
+            if (inf & 4) {
+                PathE pe;
+                if (rel < kPathSm) pe = W.path[rel];
+                else pe = gpath[rel];
+                double midProb = pe.lk;
+                int failed = pe.failed;
+                bool alive = true;
+                if (inf & 1) {
+                    if (!(inf & 2)) alive = false;  // no probVectTotUp: the reference moves on without visiting the children
+                    else {
+                        midProb = W.winScore[j];
+                        phase1++;
+                        if (midProb > best - sp.thresholdLogLKoptimizationTopology) {  // :7071
+                            if (qN >= qCap) err = 3;
+                            else qTop[-1 - qN] = uint32_t(W.winNode[j]);
+                            qN++;
+                        }
+                        if (midProb > best) { best = midProb; failed = 0; newBest = 1; }
+                        else if (midProb < (pe.lk - sp.thresholdLogLKconsecutivePlacement)) failed++;
+                    }
+                }
+                if (alive && (inf & 8)) {
+                    if (sp.strictTopologyStopRules) descend = failed <= sp.allowedFailsTopology && midProb > (best - sp.thresholdLogLKtopology);
+                    else descend = failed <= sp.allowedFailsTopology || midProb > (best - sp.thresholdLogLKtopology);
+                    if (descend) {
+                        if (rel + 1 >= pathCap) { err = 3; descend = false; }
+                        else if (rel + 1 < kPathSm) W.path[rel + 1] = PathE{midProb, failed, 0};  // every lane stores the same value
+                        else gpath[rel + 1] = PathE{midProb, failed, 0};
+                    }
+                }
+            }
+            j += descend ? 1 : W.winSize[j];
+            if (err) break;
+        }
+        pos += j;
+        __syncwarp();
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) st[7] += (unsigned long long)(now - tk);
+            tk = now;
+        }
+    }
+    __syncwarp();
+    if (st && lane == 0) { st[21] += (unsigned long long)phase1; st[22] += (unsigned long long)qN; }
+    if (lane == src) {
+        f.bestLKdiff = best;
+        f.phase1 += phase1;
+        f.qN = qN;
+        f.scanNewBest = newBest;
+        if (err) s.err = err;
+    }
 }
 
 // After a search finished: startTopologyUpdatesParallel's acceptance logic (:9681-9702)

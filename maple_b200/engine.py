@@ -121,6 +121,15 @@ class MapleEngine:
         """0 = warp-converged state-machine search kernel (default), 1 = straight-line kernel (A/B measurements)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_search_variant(self.ctx, int(variant)), "maple_ctx_set_search_variant")
 
+    def set_scan_min_size(self, n: int):
+        capi.check(self.ctx, self.lib.maple_ctx_set_scan_min_size(self.ctx, int(n)), "maple_ctx_set_scan_min_size")
+
+    def search_stats(self, enable: bool = True, read: bool = True):
+        """Profiling counters of the search kernel (see scripts/time_search.py for their meaning)."""
+        out = (C.c_uint64 * 32)() if read else None
+        capi.check(self.ctx, self.lib.maple_search_stats(self.ctx, 1 if enable else 0, out), "maple_search_stats")
+        return None if out is None else list(out)
+
     @property
     def launches(self) -> int:
         return int(self.lib.maple_launch_count(self.ctx))

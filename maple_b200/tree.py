@@ -293,7 +293,7 @@ class DeviceTree:
         self._d_mutStart = None if mutStart is None else torch.from_numpy(mutStart).to(dev)
         self._d_mut = None if mutStart is None else torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
         rc = eng.lib.maple_tree_bind(eng.ctx, n, root, _dp(self.d_up), _dp(self.d_child0), _dp(self.d_child1), _dp(self.d_dist),
-                                     _dp(self.d_isTip), _dp(self._d_mutStart), _dp(self._d_mut), _dp(A.nkeys))
+                                     _dp(self.d_isTip), _dp(self._d_mutStart), _dp(self._d_mut), _dp(A.nkeys), _dp(A.npay))
         capi.check(eng.ctx, rc, "maple_tree_bind")
 
     def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0, cycles=None):

@@ -30,6 +30,8 @@ for variant in variants:
     name = "v%d %s" % (variant, name)
     p = search_params(d.model.lRef, strict, fails, thr)
     for rep in range(2):
+        if rep == 1 and variant != 1:
+            eng.search_stats(True, True)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -39,6 +41,15 @@ for variant in variants:
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
     rec = tree.search_records(out)
+    if variant != 1:
+        S = eng.search_stats(False, True)
+        wc = float(sum(S[0:6])) or 1.0
+        print("   warp cycles: control %.1f%% append %.1f%% merge %.1f%% blen %.1f%% differ %.1f%% scan %.1f%% (scan: window+stage %.1f%% score %.1f%% replay %.1f%%) | "
+              "iterations %.3g; lanes/op-iteration: append %.1f merge %.1f blen %.1f differ %.1f | op counts a %.3g m %.3g b %.3g d %.3g" % (
+                  100 * S[0] / wc, 100 * S[1] / wc, 100 * S[2] / wc, 100 * S[3] / wc, 100 * S[4] / wc, 100 * S[5] / wc, 100 * S[23] / wc, 100 * S[6] / wc, 100 * S[7] / wc,
+                  S[16], S[8] / max(S[12], 1), S[9] / max(S[13], 1), S[10] / max(S[14], 1), S[11] / max(S[15], 1), S[8], S[9], S[10], S[11]), flush=True)
+        print("   scan jobs %d, nodes in their ranges %.3g, batches %.3g, lanes scored %.3g (%.1f / batch, window %.1f nodes), counted %.3g, phase-2 entries queued %d" % (
+            S[17], S[18], S[19], S[20], S[20] / max(S[19], 1), S[24] / max(S[19], 1), S[21], S[22]), flush=True)
     st = np.bincount(rec["status"], minlength=4)
     ph = rec["phase1"].sum()
     print("%s: %.1f ms, searches %d, status %s, phase1 %d (%.1f/search, max %d), %.3g cand/s, proposals %d" % (
