@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmaple_b200.so")
 SOURCES = ["maple_b200.cu"]
-HEADERS = ["glist.cuh", "likelihood.cuh", os.path.join("..", "..", "include", "maple_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "maple_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # no FMA contraction: a*b+c rounds twice, like the CPython reference

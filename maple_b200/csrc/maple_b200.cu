@@ -6,6 +6,7 @@
 // once per CTA; per-site rate / error tables (239 kB each at lRef 29903) are read through the
 // read-only path at the few informative sites only and stay L2-resident.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -35,12 +36,13 @@ struct maple_ctx {
     int treeHeight = 0;
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
+    int fsmMinBlocks = 8;            // resident CTAs per SM the state-machine kernel is compiled for (6, 8 or 10: register budget)
     int scanMinSize = 8;             // subtrees of at least this many nodes are scanned by the whole warp (0 = never)
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
-    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only
+    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans with the parallel-rounds replay, 4 = 3 + cross-check when stats are on
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
@@ -197,6 +199,47 @@ __global__ void __launch_bounds__(256) k_lists_copy(int64_t n, const uint32_t* _
 
 constexpr int kSearchThreads = 64;
 
+// one thread per pre-order position: the ScanNode records of the bound tree and arena for this launch's effectivelyNon0BLen
+__global__ void __launch_bounds__(256) k_scan_prepare(const __grid_constant__ DevTree T, double eff, ScanNode* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T.nNodes) return;
+    ScanNode r;
+    const int node = T.order[i];
+    r.node = node;
+    r.keyOff = r.payOff = r.cnt = r.flags = 0;
+    if (node < 0 || T.pre[node] != i) {  // positions past the reachable nodes
+        r.node = -1; r.parentPos = -1; r.size = 1; r.depth = 0;
+        out[i] = r;
+        return;
+    }
+    const int up = T.up[node];
+    const int64_t nN = T.nNodes;
+    r.parentPos = up >= 0 ? T.pre[up] : -1;
+    r.size = T.size[node];
+    r.depth = T.depth[node];
+    uint32_t fl = 0;
+    if (up >= 0 && (T.dist[node] > eff || T.up[up] < 0)) fl |= SN_ELIG;
+    if (up >= 0 && T.keyStart[(T.child0[up] == node ? 1 : 2) * nN + up] >= 0) fl |= SN_PUSHED;
+    if (T.child0[node] >= 0) fl |= SN_INNER;
+    const int64_t id = 3 * nN + node, ks = T.keyStart[id];
+    if (ks >= 0) {
+        fl |= SN_TOT;
+        const int64_t ps = T.payStart[id];
+        const uintptr_t ak = reinterpret_cast<uintptr_t>(T.key + ks), ap = reinterpret_cast<uintptr_t>(T.pay + ps);
+        if (T.npay && ((ak | ap) & 15) == 0 && (ks >> 2) < (int64_t(1) << 32) && (ps >> 1) < (int64_t(1) << 32)) {
+            const int nk4 = (T.nkeys[id] + 3) >> 2, np2 = (T.npay[id] + 1) >> 1;
+            if (nk4 < 65536 && np2 < 65536) {
+                fl |= SN_STAGE;
+                r.keyOff = uint32_t(ks >> 2);
+                r.payOff = uint32_t(ps >> 1);
+                r.cnt = uint32_t(nk4) | (uint32_t(np2) << 16);
+            }
+        }
+    }
+    r.flags = fl;
+    out[i] = r;
+}
+
 // one SPR search per thread; threads pull the next pruned node from a global counter (searches differ ~10x in length)
 __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                const __grid_constant__ SearchParams sp, int64_t n,
@@ -226,13 +269,14 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
 // The same searches as k_spr_search, one per lane, but as resumable state machines (search_fsm.cuh): every loop
 // iteration each lane advances its control code to the next co-walk request, then the warp runs each kind of
 // co-walk once for all lanes that requested it.
-__global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+template <int MINB>
+__global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                    const __grid_constant__ SearchParams sp, int64_t n,
                                                                    const int32_t* __restrict__ nodes, SearchResult* __restrict__ out,
                                                                    uint32_t* scrKey, double* scrPay, double* scrAis, StackE* scrStack,
                                                                    unsigned capK, unsigned capP, unsigned capA, int stackCap,
                                                                    unsigned long long* counter, long long* outCycles, int scanMinSize,
-                                                                   unsigned long long* stats) {
+                                                                   int replayMode, unsigned long long* stats) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -344,7 +388,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search_fsm(const __grid_
         STAT_T(4);
         // ---------------- subtree scans: the whole warp works for one lane's search at a time
         for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1)
-            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, st);
+            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, replayMode, st, replayMode == 2 ? stats + 32 : nullptr);
         STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
     }
@@ -391,6 +435,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     }
     maple_ctx* ctx = new maple_ctx();
     ctx->device = device;
+    if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
     cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
     memset(&ctx->model, 0, sizeof(DevModel));
     ctx->model.lRef = lRef;
@@ -673,10 +718,11 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
     }
     cudaFree(ctx->treeDerived);
     ctx->treeDerived = nullptr;
-    CK(cudaMalloc((void**)&ctx->treeDerived, der.size() * 4));
+    CK(cudaMalloc((void**)&ctx->treeDerived, der.size() * 4 + 32 + n * sizeof(ScanNode)));
     CK(cudaMemcpy(ctx->treeDerived, der.data(), der.size() * 4, cudaMemcpyHostToDevice));
     t.order = ctx->treeDerived; t.pre = t.order + n; t.size = t.pre + n; t.depth = t.size + n;
     t.mutBelow = reinterpret_cast<const uint8_t*>(t.depth + n);
+    t.scan = reinterpret_cast<const ScanNode*>((reinterpret_cast<uintptr_t>(ctx->treeDerived + der.size()) + 31) & ~uintptr_t(31));
     ctx->treeHeight = height;
     ctx->haveTree = true;
     return MAPLE_OK;
@@ -702,10 +748,15 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     const size_t fsmSmem = (kSearchThreads / 32) * sizeof(ScanSmem);
+    using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
+                               StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, unsigned long long*);
+    FsmKernel fsmKernel = k_spr_search_fsm<8>;  // 128 registers, 16 warps per SM: measured best of the three on the deep round
+    if (ctx->fsmMinBlocks == 6) fsmKernel = k_spr_search_fsm<6>;
+    else if (ctx->fsmMinBlocks == 10) fsmKernel = k_spr_search_fsm<10>;
     if (ctx->searchVariant != 1) {
-        CK(cudaFuncSetAttribute(k_spr_search_fsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
-        CK(cudaFuncSetAttribute(k_spr_search_fsm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search_fsm, kSearchThreads, fsmSmem));
+        CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
+        CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, fsmKernel, kSearchThreads, fsmSmem));
     }
     if (blocksPerSM < 1) blocksPerSM = 1;
     int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
@@ -729,14 +780,20 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     double* scrAis = (double*)(base + (size_t)threads * capP * 8);
     StackE* scrStack = (StackE*)(base + (size_t)threads * (capP + capA) * 8);
     uint32_t* scrKey = (uint32_t*)(base + (size_t)threads * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+    if ((ctx->searchVariant == 0 || ctx->searchVariant >= 3) && T.order && ctx->scanMinSize > 0) {
+        k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, sp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
+        ctx->launches++;
+    }
     if (ctx->searchVariant == 1)
         k_spr_search<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
                                                                          scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
                                                                          (long long*)out_cycles);
     else
-        k_spr_search_fsm<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
+        fsmKernel<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
                                                                              scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
-                                                                             (long long*)out_cycles, (T.order && ctx->searchVariant == 0) ? ctx->scanMinSize : 0,
+                                                                             (long long*)out_cycles,
+                                                                             (T.order && (ctx->searchVariant == 0 || ctx->searchVariant >= 3)) ? ctx->scanMinSize : 0,
+                                                                             ctx->searchVariant == 3 ? 1 : (ctx->searchVariant == 4 && ctx->statsOn) ? 2 : (ctx->searchVariant == 4 ? 1 : 0),
                                                                              ctx->statsOn ? ctx->searchStats : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -744,7 +801,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
 }
 
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
-    if (!ctx || variant < 0 || variant > 2) return MAPLE_E_ARG;
+    if (!ctx || variant < 0 || variant > 4) return MAPLE_E_ARG;
     ctx->searchVariant = variant;
     return MAPLE_OK;
 }
@@ -753,13 +810,13 @@ int maple_search_stats(maple_ctx* ctx, int32_t enable, uint64_t* out) {
     if (!ctx) return MAPLE_E_ARG;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->searchStats) {
-        CK(cudaMalloc((void**)&ctx->searchStats, kNumSearchStats * 8));
-        CK(cudaMemset(ctx->searchStats, 0, kNumSearchStats * 8));
+        CK(cudaMalloc((void**)&ctx->searchStats, (kNumSearchStats + 256) * 8));
+        CK(cudaMemset(ctx->searchStats, 0, (kNumSearchStats + 256) * 8));
     }
     if (out) {
         CK(cudaDeviceSynchronize());
-        CK(cudaMemcpy(out, ctx->searchStats, kNumSearchStats * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemset(ctx->searchStats, 0, kNumSearchStats * 8));
+        CK(cudaMemcpy(out, ctx->searchStats, (kNumSearchStats + 256) * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(ctx->searchStats, 0, (kNumSearchStats + 256) * 8));
     }
     ctx->statsOn = enable != 0;
     return MAPLE_OK;

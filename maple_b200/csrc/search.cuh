@@ -39,7 +39,26 @@ struct DevTree {
     const int32_t* size;      // nodes in the subtree of a node (itself included)
     const int32_t* depth;     // edges between the root and a node
     const uint8_t* mutBelow;  // some node strictly below carries MAT mutations
+    const struct ScanNode* scan;  // [nNodes] per pre-order position, refreshed by k_scan_prepare before every search launch
 };
+
+// Everything a subtree scan needs to know about the node at one pre-order position, in one 32-byte record (two 16-byte loads,
+// consecutive lanes read consecutive records).
+struct ScanNode {
+    int32_t node;
+    int32_t parentPos;  // pre-order position of the parent, -1 for the root
+    int32_t size;       // nodes in the subtree
+    int32_t depth;
+    uint32_t keyOff;    // probVectTotUp list: key offset / 4 and payload offset / 2 in the arena (valid with SN_STAGE)
+    uint32_t payOff;
+    uint32_t cnt;       // 16-byte units: keys | payload << 16
+    uint32_t flags;
+};
+constexpr uint32_t SN_ELIG = 1;    // has a parent and (dist > effectivelyNon0BLen or the parent is the root): gets a score (:6978, :7184)
+constexpr uint32_t SN_TOT = 2;     // probVectTotUp exists
+constexpr uint32_t SN_PUSHED = 4;  // the parent's upper list towards this node exists, so the walk pushes this node (:7120, :7157)
+constexpr uint32_t SN_INNER = 8;   // has children
+constexpr uint32_t SN_STAGE = 16;  // list is 16-byte aligned and small enough for the offsets above
 
 struct SearchParams {
     int strictTopologyStopRules, allowedFailsTopology, deeperSearchForLongBranches, reserved;

@@ -447,15 +447,18 @@ constexpr int kWinMax = 96;      // nodes per window
 constexpr int kPathSm = 40;      // per-depth states kept in shared memory (deeper ones go to global scratch)
 constexpr int kCKeys = 64;       // removed list staged in shared memory when it has at most this many entries ...
 constexpr int kCPay = 96;        // ... and this many payload doubles
-constexpr int kPoolBytes = 9216; // mid-branch lists of one batch
+constexpr int kPoolBytes = 8192; // mid-branch lists of one batch
 struct ScanSmem {
-    double winScore[kWinMax];
+    double winScore[kWinMax];  // candidate score; after the replay: the midProb the node hands to its children
     double cPay[kCPay];
     PathE path[kPathSm];
-    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax];
+    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax], winParent[kWinMax], winOut[kWinMax];
     uint32_t cKey[kCKeys];
     uint4 pool[kPoolBytes / 16];
 };
+// winInfo: bit0 eligible, bit1 has probVectTotUp, bit2 was pushed, bit3 has children, bits 8.. depth relative to the job's root
+// winOut: failedPasses | WO_*
+constexpr int WO_DESCEND = 1 << 20, WO_REACHED = 1 << 21, WO_DONE = 1 << 22, WO_COUNTED = 1 << 23, WO_FAILMASK = (1 << 20) - 1;
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -472,7 +475,8 @@ __device__ __noinline__ double f_append_sitewise(const DevModel& m, const uint32
 }
 
 __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack,
-                              int stackCap, ScanSmem& W, unsigned long long* st) {
+                              int stackCap, ScanSmem& W, int replayMode /* 0 sequential, 1 parallel rounds, 2 both + compare (debug) */,
+                              unsigned long long* st, unsigned long long* dbg) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int R = __shfl_sync(FULL, f.t1, src);
@@ -489,7 +493,6 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
     const int pathCap = int((size_t)(stackCap - __shfl_sync(FULL, f.spN, src)) * sizeof(StackE) / sizeof(PathE));
     uint32_t* qTop = reinterpret_cast<uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(s.key + s.capK), src));
     const int qCap = int(__shfl_sync(FULL, s.capK - s.topK, src)) - 8;
-    const double eff = sp.effectivelyNon0BLen;
     const int64_t nN = t.nNodes;
     int phase1 = 0, qN = 0, newBest = 0, err = 0;
     int pos = t.pre[R];
@@ -524,38 +527,44 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
     if (pathCap < 2) err = 3;
     else if (lane == 0) W.path[0] = PathE{lastLK0, failed0, 0};
     __syncwarp();
+    const int prunedParentPos = t.pre[prunedParent];
     while (pos < end && !err) {
         // ---- window: nodes pos .. pos+nWin-1, at most 32 of them need a score
         int nWin = 0, nScore = 0;
-        int myW = -1;  // window position this lane scores
+        int myW = -1;  // window position this lane scores, and where its list lies
+        uint32_t myKeyOff = 0, myPayOff = 0, myCnt = 0;
+        bool myStage = false;
         for (int sweep = 0; sweep < kWinMax / 32 && pos + nWin < end && nScore < 32; sweep++) {
             const int w = nWin + lane, idx = pos + w;
-            int info = 0;  // bit0 eligible, bit1 has probVectTotUp, bit2 was pushed (parent's upper list exists), bit3 internal, bits 8.. relative depth
+            int info = 0;
+            ScanNode rec;
+            rec.keyOff = rec.payOff = rec.cnt = rec.flags = 0;
             if (idx < end) {
-                const int node = t.order[idx];
-                const int up = t.up[node];
-                const bool elig = !(up == prunedParent || up < 0) && (t.dist[node] > eff || t.up[up] < 0);
-                const bool hasTot = t.keyStart[3 * nN + node] >= 0;
-                const bool pushed = node == R || t.keyStart[(t.child0[up] == node ? 1 : 2) * nN + up] >= 0;
-                info = (elig ? 1 : 0) | (hasTot ? 2 : 0) | (pushed ? 4 : 0) | (t.child0[node] >= 0 ? 8 : 0) | ((t.depth[node] - d0) << 8);
+                const uint4* src4 = reinterpret_cast<const uint4*>(t.scan + idx);
+                const uint4 a4 = __ldg(src4), b4 = __ldg(src4 + 1);
+                rec.node = int(a4.x); rec.parentPos = int(a4.y); rec.size = int(a4.z); rec.depth = int(a4.w);
+                rec.keyOff = b4.x; rec.payOff = b4.y; rec.cnt = b4.z; rec.flags = b4.w;
+                const bool elig = (rec.flags & SN_ELIG) && rec.parentPos != prunedParentPos;
+                const bool pushed = (rec.flags & SN_PUSHED) || rec.node == R;
+                info = (elig ? 1 : 0) | ((rec.flags & SN_TOT) ? 2 : 0) | (pushed ? 4 : 0) | ((rec.flags & SN_INNER) ? 8 : 0) | ((rec.depth - d0) << 8);
                 W.winInfo[w] = info;
-                W.winSize[w] = t.size[node];
-                W.winNode[w] = node;
+                W.winSize[w] = rec.size;
+                W.winNode[w] = rec.node;
+                W.winParent[w] = rec.parentPos - pos;
+                W.winOut[w] = 0;
             }
             const unsigned need = __ballot_sync(FULL, (info & 7) == 7);
             const int room = 32 - nScore;
             int take = min(32, end - pos - nWin);  // nodes of this sweep that join the window
-            if (__popc(need) > room) {             // cut right after the node that fills the last lane
-                unsigned x = need;
-                for (int i = 1; i < room; i++) x &= x - 1;
-                take = __ffs(x);                   // position (1-based) of the room-th set bit
-            }
+            if (__popc(need) > room) take = __fns(need, 0, room) + 1;  // cut right after the node that fills the last lane
             const unsigned mine = need & (take >= 32 ? FULL : ((1u << take) - 1u));
             // the k-th node that needs a score goes to lane nScore + k
-            for (unsigned x = mine; x; x &= x - 1) {
-                const int b = __ffs(x) - 1;
-                if (lane == nScore + __popc(mine & ((1u << b) - 1u))) myW = nWin + b;
-            }
+            const int k = lane - nScore;
+            const bool gets = k >= 0 && k < __popc(mine);
+            const int from = gets ? int(__fns(mine, 0, k + 1)) : lane;
+            const uint32_t ko = __shfl_sync(FULL, rec.keyOff, from), po = __shfl_sync(FULL, rec.payOff, from), cn = __shfl_sync(FULL, rec.cnt, from),
+                           fl = __shfl_sync(FULL, rec.flags, from);
+            if (gets) { myW = nWin + from; myKeyOff = ko; myPayOff = po; myCnt = cn; myStage = (fl & SN_STAGE) != 0; }
             nScore += __popc(mine);
             nWin += take;
         }
@@ -564,15 +573,17 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
         {
             const uint32_t* kP = nullptr;
             const double* pP = nullptr;
-            int bytes = 0, nk4 = 0, np2 = 0;
+            int bytes = 0;
+            const int nk4 = int(myCnt & 0xffffu), np2 = int(myCnt >> 16);
             if (myW >= 0) {
-                const int64_t id = 3 * nN + W.winNode[myW];
-                kP = t.key + t.keyStart[id];
-                pP = t.pay + t.payStart[id];
-                if (t.npay && ((reinterpret_cast<uintptr_t>(kP) | reinterpret_cast<uintptr_t>(pP)) & 15) == 0) {
-                    nk4 = (t.nkeys[id] + 3) >> 2;
-                    np2 = (t.npay[id] + 1) >> 1;
+                if (myStage) {
+                    kP = t.key + 4 * (size_t)myKeyOff;
+                    pP = t.pay + 2 * (size_t)myPayOff;
                     bytes = (nk4 + np2) * 16;
+                } else {
+                    const int64_t id = 3 * nN + W.winNode[myW];
+                    kP = t.key + t.keyStart[id];
+                    pP = t.pay + t.payStart[id];
                 }
             }
             const int endOff = warp_incl_scan(bytes, lane);
@@ -582,9 +593,9 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                 const uint4* gk = reinterpret_cast<const uint4*>(kP);
                 const uint4* gp = reinterpret_cast<const uint4*>(pP);
 #pragma unroll 4
-                for (int i = 0; i < nk4; i++) dk[i] = gk[i];
+                for (int i = 0; i < nk4; i++) dk[i] = __ldg(gk + i);
 #pragma unroll 4
-                for (int i = 0; i < np2; i++) dp[i] = gp[i];
+                for (int i = 0; i < np2; i++) dp[i] = __ldg(gp + i);
                 kP = reinterpret_cast<const uint32_t*>(dk);
                 pP = reinterpret_cast<const double*>(dp);
             }
@@ -601,45 +612,217 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
             if (lane == 0) st[6] += (unsigned long long)(now - tk);
             tk = now;
         }
-        // ---- replay, every lane the same
+        // ---- replay.  Parallel form: assume no node of the window that holds a new running best gets pruned; then the best seen
+        // before each node is a prefix maximum over the window, every node's bookkeeping depends only on its parent's, and the
+        // nodes can be processed parent-before-child in a few rounds.  The assumption is checked afterwards; if it fails (rare:
+        // a pruned branch would have to beat the running best) the window is replayed one node at a time instead.
+        bool parallelOk = replayMode != 0;
         int j = 0;
-        while (j < nWin) {
-            const int inf = W.winInfo[j];
-            const int rel = inf >> 8;
-            bool descend = false;
-            if (inf & 4) {
-                PathE pe;
-                if (rel < kPathSm) pe = W.path[rel];
-                else pe = gpath[rel];
-                double midProb = pe.lk;
-                int failed = pe.failed;
-                bool alive = true;
-                if (inf & 1) {
-                    if (!(inf & 2)) alive = false;  // no probVectTotUp: the reference moves on without visiting the children
-                    else {
-                        midProb = W.winScore[j];
-                        phase1++;
-                        if (midProb > best - sp.thresholdLogLKoptimizationTopology) {  // :7071
-                            if (qN >= qCap) err = 3;
-                            else qTop[-1 - qN] = uint32_t(W.winNode[j]);
-                            qN++;
+        int chkJ = -1, chkCounted = 0;
+        double chkBest = 0.0;
+        const int phase1Before = phase1;
+        if (parallelOk) {
+            // (1) prefix maximum of the scores in window order
+            double bb[kWinMax / 32];  // best before node c*32+lane
+            double carry = best;
+#pragma unroll
+            for (int c = 0; c < kWinMax / 32; c++) {
+                const int w = c * 32 + lane;
+                const bool cnt = w < nWin && (W.winInfo[w] & 7) == 7;
+                double v = cnt ? W.winScore[w] : -INFINITY;  // inclusive maximum over this chunk up to the lane
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double x = __shfl_up_sync(FULL, v, o);
+                    if (lane >= o) v = fmax(v, x);
+                }
+                double ex = __shfl_up_sync(FULL, v, 1);
+                if (lane == 0) ex = -INFINITY;
+                bb[c] = fmax(carry, ex);
+                carry = fmax(carry, __shfl_sync(FULL, v, 31));
+            }
+            // (2) rounds: a node is processed once its parent is
+            unsigned doneMask = 0;  // bit c: node c*32+lane done
+#pragma unroll
+            for (int c = 0; c < kWinMax / 32; c++)
+                if (c * 32 + lane >= nWin) doneMask |= 1u << c;
+            int maxTarget = 0, nCounted = 0, anyNewBest = 0, bad = 0;
+            for (int round = 0; round < kWinMax + 1; round++) {
+                if (__all_sync(FULL, doneMask == (1u << (kWinMax / 32)) - 1u)) break;
+                unsigned ready = 0;  // decided before anything of this round is written
+#pragma unroll
+                for (int c = 0; c < kWinMax / 32; c++) {
+                    if (doneMask & (1u << c)) continue;
+                    const int pw = W.winParent[c * 32 + lane];
+                    if (pw < 0 || (W.winOut[pw] & WO_DONE)) ready |= 1u << c;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < kWinMax / 32; c++) {
+                    if (!(ready & (1u << c))) continue;
+                    const int w = c * 32 + lane;
+                    const int pw = W.winParent[w];
+                    double lastLK;
+                    int failed;
+                    bool reached;
+                    const int inf = W.winInfo[w];
+                    const int rel = inf >> 8;
+                    if (pw < 0) {  // parent before the window: it was reached and it descended, or this window would not have got here
+                        PathE pe;
+                        if (rel < kPathSm) pe = W.path[rel];
+                        else pe = gpath[rel];
+                        lastLK = pe.lk; failed = pe.failed; reached = true;
+                    } else {
+                        const int po = W.winOut[pw];
+                        lastLK = W.winScore[pw];
+                        failed = po & WO_FAILMASK;
+                        reached = (po & WO_REACHED) && (po & WO_DESCEND);
+                    }
+                    int out = WO_DONE;
+                    if (reached) {
+                        out |= WO_REACHED;
+                        double midProb = lastLK;
+                        int target = w + W.winSize[w];
+                        if (inf & 4) {
+                            bool alive = true;
+                            double bestAfter = bb[c];
+                            if (inf & 1) {
+                                if (!(inf & 2)) alive = false;
+                                else {
+                                    midProb = W.winScore[w];
+                                    out |= WO_COUNTED;
+                                    nCounted++;
+                                    if (midProb > bb[c]) { bestAfter = midProb; failed = 0; anyNewBest = 1; }
+                                    else if (midProb < (lastLK - sp.thresholdLogLKconsecutivePlacement)) failed++;
+                                }
+                            }
+                            if (alive && (inf & 8)) {
+                                bool descend;
+                                if (sp.strictTopologyStopRules) descend = failed <= sp.allowedFailsTopology && midProb > (bestAfter - sp.thresholdLogLKtopology);
+                                else descend = failed <= sp.allowedFailsTopology || midProb > (bestAfter - sp.thresholdLogLKtopology);
+                                if (descend) { out |= WO_DESCEND; target = w + 1; }
+                            }
                         }
-                        if (midProb > best) { best = midProb; failed = 0; newBest = 1; }
-                        else if (midProb < (pe.lk - sp.thresholdLogLKconsecutivePlacement)) failed++;
+                        maxTarget = max(maxTarget, target);
+                        if (!(out & WO_COUNTED)) W.winScore[w] = midProb;  // what the children inherit as lastLK (a counted node: its own score)
+                    } else if ((inf & 7) == 7 && W.winScore[w] > bb[c]) bad = 1;  // a pruned node holds a new best: the prefix maxima are wrong
+                    W.winOut[w] = out | (failed & WO_FAILMASK);
+                    doneMask |= 1u << c;
+                }
+                __syncwarp();
+            }
+            parallelOk = !__any_sync(FULL, bad) && __all_sync(FULL, doneMask == (1u << (kWinMax / 32)) - 1u);
+            if (parallelOk && replayMode == 2) {  // debug: keep the parallel outcome aside, let the sequential replay decide
+                int mt = maxTarget, nc = nCounted;
+                double nb = best;
+                for (int c = 0; c < kWinMax / 32; c++) {
+                    const int w = c * 32 + lane;
+                    if (w < nWin && (W.winOut[w] & WO_COUNTED)) nb = fmax(nb, W.winScore[w]);
+                }
+                for (int o = 16; o; o >>= 1) {
+                    mt = max(mt, __shfl_xor_sync(FULL, mt, o));
+                    nc += __shfl_xor_sync(FULL, nc, o);
+                    nb = fmax(nb, __shfl_xor_sync(FULL, nb, o));
+                }
+                chkJ = mt; chkCounted = nc; chkBest = nb;
+                parallelOk = false;
+            }
+            if (parallelOk) {
+                // (3) commit: counts, running best, phase-2 queue in window order, per-depth states for the next windows
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    maxTarget = max(maxTarget, __shfl_xor_sync(FULL, maxTarget, o));
+                    nCounted += __shfl_xor_sync(FULL, nCounted, o);
+                }
+                double newBestVal = best;
+#pragma unroll
+                for (int c = 0; c < kWinMax / 32; c++) {
+                    const int w = c * 32 + lane;
+                    const int out = w < nWin ? W.winOut[w] : 0;
+                    const bool counted = (out & WO_COUNTED) != 0;
+                    const double sc = counted ? W.winScore[w] : -INFINITY;  // a counted node hands down its own score
+                    const bool queued = counted && sc > bb[c] - sp.thresholdLogLKoptimizationTopology;  // :7071
+                    const unsigned qm = __ballot_sync(FULL, queued);
+                    if (queued) {
+                        const int at = qN + __popc(qm & ((1u << lane) - 1u));
+                        if (at < qCap) qTop[-1 - at] = uint32_t(W.winNode[w]);
+                    }
+                    qN += __popc(qm);
+                    newBestVal = fmax(newBestVal, sc);
+                    // the last node of each depth that descends leaves its state for later windows
+                    const bool desc = (out & WO_DESCEND) != 0;
+                    const int rel1 = (W.winInfo[w < nWin ? w : 0] >> 8) + 1;
+                    const unsigned peers = __match_any_sync(FULL, desc ? rel1 : -1 - lane);
+                    if (desc && lane == 31 - __clz(peers)) {
+                        if (rel1 >= pathCap) err = 3;
+                        else if (rel1 < kPathSm) W.path[rel1] = PathE{W.winScore[w], out & WO_FAILMASK, 0};
+                        else gpath[rel1] = PathE{W.winScore[w], out & WO_FAILMASK, 0};
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) newBestVal = fmax(newBestVal, __shfl_xor_sync(FULL, newBestVal, o));
+                if (qN > qCap) err = 3;
+                err = __any_sync(FULL, err == 3) ? 3 : err;
+                if (__any_sync(FULL, anyNewBest)) newBest = 1;
+                best = newBestVal;
+                phase1 += nCounted;
+                j = maxTarget;
+            }
+        }
+        if (!parallelOk) {
+            // sequential replay, every lane the same (the scores of the nodes that need one are still in winScore)
+            if (st && lane == 0) st[25] += 1;
+            j = 0;
+            while (j < nWin) {
+                const int inf = W.winInfo[j];
+                const int rel = inf >> 8;
+                bool descend = false;
+                if (inf & 4) {
+                    PathE pe;
+                    if (rel < kPathSm) pe = W.path[rel];
+                    else pe = gpath[rel];
+                    double midProb = pe.lk;
+                    int failed = pe.failed;
+                    bool alive = true;
+                    if (inf & 1) {
+                        if (!(inf & 2)) alive = false;  // no probVectTotUp: the reference moves on without visiting the children
+                        else {
+                            midProb = W.winScore[j];
+                            phase1++;
+                            if (midProb > best - sp.thresholdLogLKoptimizationTopology) {  // :7071
+                                if (qN >= qCap) err = 3;
+                                else qTop[-1 - qN] = uint32_t(W.winNode[j]);
+                                qN++;
+                            }
+                            if (midProb > best) { best = midProb; failed = 0; newBest = 1; }
+                            else if (midProb < (pe.lk - sp.thresholdLogLKconsecutivePlacement)) failed++;
+                        }
+                    }
+                    if (alive && (inf & 8)) {
+                        if (sp.strictTopologyStopRules) descend = failed <= sp.allowedFailsTopology && midProb > (best - sp.thresholdLogLKtopology);
+                        else descend = failed <= sp.allowedFailsTopology || midProb > (best - sp.thresholdLogLKtopology);
+                        if (descend) {
+                            if (rel + 1 >= pathCap) { err = 3; descend = false; }
+                            else if (rel + 1 < kPathSm) W.path[rel + 1] = PathE{midProb, failed, 0};  // every lane stores the same value
+                            else gpath[rel + 1] = PathE{midProb, failed, 0};
+                        }
                     }
                 }
-                if (alive && (inf & 8)) {
-                    if (sp.strictTopologyStopRules) descend = failed <= sp.allowedFailsTopology && midProb > (best - sp.thresholdLogLKtopology);
-                    else descend = failed <= sp.allowedFailsTopology || midProb > (best - sp.thresholdLogLKtopology);
-                    if (descend) {
-                        if (rel + 1 >= pathCap) { err = 3; descend = false; }
-                        else if (rel + 1 < kPathSm) W.path[rel + 1] = PathE{midProb, failed, 0};  // every lane stores the same value
-                        else gpath[rel + 1] = PathE{midProb, failed, 0};
+                j += descend ? 1 : W.winSize[j];
+                if (err) break;
+            }
+            if (chkJ >= 0 && dbg && (chkJ != j || chkCounted != phase1 - phase1Before || chkBest != best) && lane == 0) {
+                if (atomicAdd(dbg, 1ULL) == 0) {
+                    dbg[1] = (unsigned long long)pos; dbg[2] = (unsigned long long)nWin; dbg[3] = (unsigned long long)chkJ; dbg[4] = (unsigned long long)j;
+                    dbg[5] = (unsigned long long)chkCounted; dbg[6] = (unsigned long long)(phase1 - phase1Before);
+                    dbg[7] = (unsigned long long)__double_as_longlong(chkBest); dbg[8] = (unsigned long long)__double_as_longlong(best);
+                    dbg[9] = (unsigned long long)R; dbg[10] = (unsigned long long)t.pre[R]; dbg[11] = (unsigned long long)nScore;
+                    for (int q = 0; q < nWin && q < 96; q++) {
+                        dbg[16 + 2 * q] = ((unsigned long long)(unsigned)W.winInfo[q]) | ((unsigned long long)(unsigned)W.winOut[q] << 32);
+                        dbg[17 + 2 * q] = ((unsigned long long)(unsigned)W.winParent[q]) | ((unsigned long long)(unsigned)W.winSize[q] << 32);
                     }
                 }
             }
-            j += descend ? 1 : W.winSize[j];
-            if (err) break;
         }
         pos += j;
         __syncwarp();
