@@ -182,17 +182,14 @@ def main():
     dev = eng.device
     p = round_params(args, d.model.lRef)
     # strong scaling: every rank holds the whole tree; searches are dealt round-robin like coreNum[node]==corNum (:9619)
-    mine = nodes[rank::world] if world > 1 else nodes
-    per_rank = (len(nodes) + world - 1) // world
+    from maple_b200.sharding import all_gather_raw, shard_nodes
+    mine = shard_nodes(nodes, rank, world)
     d_nodes = torch.as_tensor(mine, dtype=torch.int32, device=dev)
-    gathered = torch.zeros((world * per_rank, 64), dtype=torch.uint8, device=dev) if world > 1 else None
 
     def step(src_nodes):
         out = tree.spr_search(src_nodes, p, scratch_keys=16384)
         if world > 1:  # one collective per round: everybody gets every proposal
-            pad = torch.zeros((per_rank, 64), dtype=torch.uint8, device=dev)
-            pad[: out.shape[0]] = out
-            dist.all_gather_into_tensor(gathered, pad)
+            all_gather_raw(out, len(nodes), world)
         return out
 
     for _ in range(args.warmup):
@@ -217,9 +214,7 @@ def main():
         out = tree.spr_search(d_nodes, p, scratch_keys=16384)
         ev[k][1].record()
         if world > 1:
-            pad = torch.zeros((per_rank, 64), dtype=torch.uint8, device=dev)
-            pad[: out.shape[0]] = out
-            dist.all_gather_into_tensor(gathered, pad)
+            all_gather_raw(out, len(nodes), world)
         ev[k][2].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -278,6 +273,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    traffic = None  # ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one launch (profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "search_traffic.json")))
+        if tr.get("nseq") == args.nseq and tr.get("round") == args.round and world == 1:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -291,7 +293,7 @@ def main():
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(len(mine) * 4), "d2h_bytes_per_step": int(len(mine) * 64),
                 "note": "pinned host node ids in, result records out, per rank"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "k_spr_search_fsm", "kernel_ms": kern_ms, "alg_bytes_per_launch": int(alg_bytes),
                      "mean_mid_branch_list_bytes": round(mean_tot_bytes, 1),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},

@@ -109,6 +109,20 @@ int maple_root_vector_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, const
                             uint32_t* out_key, double* out_pay, const int64_t* out_key_start, const int64_t* out_pay_start,
                             int32_t* out_nkeys, int32_t* out_npay, int32_t shorten, void* stream);
 
+/* Tables findProbRoot reads (:4865-4912): cumulativeBases[(lRef+1)*4] (:3640-3647) and, under the error model,
+ * rootFreqsLogErrorCumulative[lRef+1] (:6379-6389).  HOST pointers; copied. */
+int maple_ctx_set_root_tables(maple_ctx* ctx, const int32_t* cumulativeBases, const double* rootFreqsLogErrorCumulative);
+
+/* findProbRoot(probVect) (:4865) for n lists expressed relative to the reference genome.  DEVICE pointers. */
+int maple_prob_root_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, double* out, void* stream);
+
+/* passGenomeListThroughBranch(probVect, mutations[node], dirIsUp) (:3749) for n lists: list idx[i] goes through the MAT
+ * mutation list of node mutNode[i] (CSR mutStart / mut triples pos1,upNuc,downNuc as in maple_tree_bind).  Output slots as
+ * in maple_merge_batch; a slot needs nkeys + 2*nMutations + 2 keys. */
+int maple_pass_branch_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, const int32_t* mutNode, const uint8_t* dirIsUp,
+                            const int32_t* mutStart, const int32_t* mut, uint32_t* out_key, double* out_pay, const int64_t* out_key_start,
+                            const int64_t* out_pay_start, int32_t* out_nkeys, int32_t* out_npay, void* stream);
+
 /* Gather-copy n whole lists between arenas (DEVICE pointers): list i goes from
  * src_key[src_key_start[i]] / src_pay[src_pay_start[i]] (nkeys[i] keys, npay[i] doubles) to the dst
  * offsets.  Used to append batch results to the resident tree arena (what the reference does by

@@ -27,6 +27,9 @@ SIGNATURES = {
     "maple_blen_batch": (C.c_int, [_P, _I64] + [_P] * 7 + [_P]),
     "maple_vectors_differ_batch": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "maple_root_vector_batch": (C.c_int, [_P, _I64] + [_P] * 9 + [_I32, _P]),
+    "maple_ctx_set_root_tables": (C.c_int, [_P, _P, _P]),
+    "maple_prob_root_batch": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "maple_pass_branch_batch": (C.c_int, [_P, _I64] + [_P] * 11 + [_P]),
     "maple_lists_copy": (C.c_int, [_P, _I64] + [_P] * 10 + [_P]),
     "maple_tree_bind": (C.c_int, [_P, _I32, _I32] + [_P] * 9),
     "maple_spr_search_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P]),

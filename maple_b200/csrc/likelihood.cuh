@@ -28,6 +28,8 @@ struct DevModel {
     const double* errorRates;  // [lRef] (U && errSS)
     const double* cumRate;     // [lRef+1]
     const double* cumErr;      // [lRef+1] (U && errSS)
+    const int32_t* cumBases;   // cumulativeBases [(lRef+1)*4] (findProbRoot only; maple_ctx_set_root_tables)
+    const double* piLogErrCum; // rootFreqsLogErrorCumulative [lRef+1] (findProbRoot under the error model)
 };
 
 constexpr double kMinCarryOver = DBL_MIN * 1e50;  // :3623
@@ -861,6 +863,51 @@ __device__ void dev_root_vector(const DevModel& m, const uint32_t* k, const doub
         if (pos == lRef) break;
         c.next();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// findProbRoot (:4865-4912) for a list expressed relative to the reference genome
+template <bool LD>
+__device__ double dev_prob_root(const DevModel& m, const uint32_t* k, const double* p) {
+    const int lRef = m.lRef;
+    const bool U = m.U != 0;
+    Cursor<LD> c;
+    c.init(k, p);
+    double logLK = 0.0, logFactor = 1.0;
+    int pos = 0;
+    double piLog[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) piLog[i] = log(m.pi[i]);
+    for (;;) {
+        if (U && c.type < 5 && c.nl > 0 && c.flag) {
+            if (c.type == T_R) logLK += __ldg(m.piLogErrCum + c.end) - __ldg(m.piLogErrCum + pos);
+            else {
+                const double eps = site_eps(m, pos);
+                logFactor *= (sel4(m.pi, c.type) * (1.0 - 1.33333 * eps) + 0.33333 * eps);
+            }
+        } else if (c.type == T_R) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) logLK += piLog[i] * (double)(__ldg(m.cumBases + c.end * 4 + i) - __ldg(m.cumBases + pos * 4 + i));
+        } else if (c.type < 4) logLK += sel4(piLog, c.type);
+        else if (c.type == T_O) {
+            double a[4];
+            c.vec(a);
+            double tot = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) tot += m.pi[i] * a[i];
+            logFactor *= tot;
+        }
+        pos = c.end;
+        if (logFactor <= kMinCarryOver) {
+            if (logFactor < DBL_MIN) return -INFINITY;
+            logLK += log(logFactor);
+            logFactor = 1.0;
+        }
+        if (pos == lRef) break;
+        c.next();
+    }
+    logLK += log(logFactor);
+    return logLK;
 }
 
 }  // namespace maple

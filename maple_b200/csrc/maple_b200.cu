@@ -22,7 +22,8 @@ struct maple_ctx {
     int device = 0;
     DevModel model{};
     bool haveModel = false, haveLists = false;
-    double *dSiteRates = nullptr, *dErrorRates = nullptr, *dCumRate = nullptr, *dCumErr = nullptr;
+    double *dSiteRates = nullptr, *dErrorRates = nullptr, *dCumRate = nullptr, *dCumErr = nullptr, *dPiLogErrCum = nullptr;
+    int32_t* dCumBases = nullptr;
     const uint32_t* key = nullptr;
     const double* pay = nullptr;
     const int64_t *keyStart = nullptr, *payStart = nullptr;
@@ -170,6 +171,34 @@ __global__ void __launch_bounds__(kThreads) k_root_vector(const __grid_constant_
             dev_shorten<false>(sm, w.key, w.pay, w2);
             w = w2;
         }
+        outNk[i] = w.nk;
+        outNp[i] = w.np;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_prob_root(const __grid_constant__ DevModel gm, Arena A, int64_t n, const int32_t* __restrict__ idx,
+                                                        double* __restrict__ out) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = idx[i];
+        out[i] = dev_prob_root<true>(sm, A.key + __ldg(A.keyStart + a), A.pay + __ldg(A.payStart + a));
+    }
+}
+
+// passGenomeListThroughBranch (:3749-3877): list idx[i] through the MAT mutations of node mutNode[i]
+__global__ void __launch_bounds__(kThreads) k_pass_branch(int lRef, Arena A, int64_t n, const int32_t* __restrict__ idx,
+                                                          const int32_t* __restrict__ mutNode, const uint8_t* __restrict__ dirIsUp,
+                                                          const int32_t* __restrict__ mutStart, const int32_t* __restrict__ mut, uint32_t* outKey,
+                                                          double* outPay, const int64_t* __restrict__ outKeyStart,
+                                                          const int64_t* __restrict__ outPayStart, int32_t* __restrict__ outNk,
+                                                          int32_t* __restrict__ outNp) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = idx[i], nd = mutNode[i];
+        Writer w;
+        w.init(outKey + outKeyStart[i], outPay + outPayStart[i]);
+        const int m0 = mutStart[nd], nm = mutStart[nd + 1] - m0;
+        dev_pass_branch(lRef, A.key + A.keyStart[a], A.pay + A.payStart[a], mut + 3 * (size_t)m0, nm, dirIsUp[i] != 0, w);
         outNk[i] = w.nk;
         outNp[i] = w.np;
     }
@@ -458,6 +487,8 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->dErrorRates);
     cudaFree(ctx->dCumRate);
     cudaFree(ctx->dCumErr);
+    cudaFree(ctx->dPiLogErrCum);
+    cudaFree(ctx->dCumBases);
     cudaFree(ctx->devStage);
     cudaFree(ctx->searchScratch);
     cudaFree(ctx->searchCounter);
@@ -647,6 +678,55 @@ int maple_root_vector_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, const
     return MAPLE_OK;
 }
 
+int maple_ctx_set_root_tables(maple_ctx* ctx, const int32_t* cumulativeBases, const double* rootFreqsLogErrorCumulative) {
+    if (!ctx || !cumulativeBases) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevModel& m = ctx->model;
+    const size_t L = (size_t)m.lRef;
+    if (m.U && !rootFreqsLogErrorCumulative) { ctx->err = "set_root_tables: the error model needs rootFreqsLogErrorCumulative"; return MAPLE_E_ARG; }
+    if (!ctx->dCumBases) CK(cudaMalloc((void**)&ctx->dCumBases, (L + 1) * 4 * sizeof(int32_t)));
+    CK(cudaMemcpy(ctx->dCumBases, cumulativeBases, (L + 1) * 4 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (rootFreqsLogErrorCumulative) {
+        int rc = upload(ctx, &ctx->dPiLogErrCum, rootFreqsLogErrorCumulative, L + 1);
+        if (rc) return rc;
+    }
+    m.cumBases = ctx->dCumBases;
+    m.piLogErrCum = ctx->dPiLogErrCum;
+    return MAPLE_OK;
+}
+
+int maple_prob_root_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, double* out, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!ctx->model.cumBases) { ctx->err = "maple_prob_root_batch: root tables not set (maple_ctx_set_root_tables)"; return MAPLE_E_STATE; }
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !idx || !out) return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_prob_root<<<grid_for(ctx, n, 8), kThreads, 0, (cudaStream_t)stream>>>(ctx->model, A, n, idx, out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_pass_branch_batch(maple_ctx* ctx, int64_t n, const int32_t* idx, const int32_t* mutNode, const uint8_t* dirIsUp,
+                            const int32_t* mutStart, const int32_t* mut, uint32_t* out_key, double* out_pay, const int64_t* out_key_start,
+                            const int64_t* out_pay_start, int32_t* out_nkeys, int32_t* out_npay, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !idx || !mutNode || !dirIsUp || !mutStart || !mut || !out_key || !out_pay || !out_key_start || !out_pay_start || !out_nkeys ||
+        !out_npay)
+        return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Arena A{ctx->key, ctx->pay, ctx->keyStart, ctx->payStart};
+    k_pass_branch<<<grid_for(ctx, n, 8), kThreads, 0, (cudaStream_t)stream>>>(ctx->model.lRef, A, n, idx, mutNode, dirIsUp, mutStart, mut, out_key,
+                                                                             out_pay, out_key_start, out_pay_start, out_nkeys, out_npay);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
 int maple_lists_copy(maple_ctx* ctx, int64_t n, const uint32_t* src_key, const double* src_pay, const int64_t* src_key_start,
                      const int64_t* src_pay_start, const int32_t* nkeys, const int32_t* npay, uint32_t* dst_key, double* dst_pay,
                      const int64_t* dst_key_start, const int64_t* dst_pay_start, void* stream) {
@@ -744,7 +824,9 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
     const unsigned capK = (unsigned)((scratch_keys_per_search > 0 ? scratch_keys_per_search : 8192) + 3) & ~3u;
     const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
-    const int stackCap = ctx->treeHeight + 16 > 512 ? ((2 * ctx->treeHeight + 16 + 63) & ~63) : 512;
+    // the DFS keeps at most one pending entry per level on the way up and one per level on the way down; what is left of the
+    // stack doubles as the per-depth state of the subtree scans (5 states per free entry)
+    const int stackCap = (2 * ctx->treeHeight + 32 + 63) & ~63;
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     const size_t fsmSmem = (kSearchThreads / 32) * sizeof(ScanSmem);

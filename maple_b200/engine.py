@@ -100,6 +100,18 @@ class MapleEngine:
         rc = self.lib.maple_ctx_set_thresholds(self.ctx, m.thresholdProb, m.thresholdDiffForUpdate, m.thresholdFoldChangeUpdate,
                                                m.minBLenSensitivity)
         capi.check(self.ctx, rc, "maple_ctx_set_thresholds")
+        self._root_tables = False
+
+    def _ensure_root_tables(self):
+        """cumulativeBases / rootFreqsLogErrorCumulative: only findProbRoot reads them, so they are uploaded on first use."""
+        if self._root_tables:
+            return
+        m = self.model
+        cb = np.ascontiguousarray(m.cumulative_bases(), np.int32)
+        pl = np.ascontiguousarray(m.root_freqs_log_error_cumulative()) if m.usingErrorRate else None
+        rc = self.lib.maple_ctx_set_root_tables(self.ctx, cb.ctypes.data_as(C.c_void_p), None if pl is None else pl.ctypes.data_as(C.c_void_p))
+        capi.check(self.ctx, rc, "maple_ctx_set_root_tables")
+        self._root_tables = True
 
     def bind(self, lists) -> DeviceLists:
         if isinstance(lists, PackedLists):
@@ -208,6 +220,34 @@ class MapleEngine:
         capi.check(self.ctx, rc, "maple_vectors_differ_batch")
         return out
 
+    def prob_root_batch(self, idx) -> torch.Tensor:
+        self._ensure_root_tables()
+        idx = self._t(idx, torch.int32)
+        out = torch.empty(idx.numel(), dtype=torch.float64, device=self.device)
+        rc = self.lib.maple_prob_root_batch(self.ctx, idx.numel(), _dp(idx), _dp(out), self._stream())
+        capi.check(self.ctx, rc, "maple_prob_root_batch")
+        return out
+
+    def pass_branch_batch(self, idx, mutNode, dirIsUp, mutStart: torch.Tensor, mut: torch.Tensor) -> MergeResult:
+        """passGenomeListThroughBranch for n lists; mutStart/mut: CSR mutation lists on the device (int32)."""
+        L = self.lists
+        idx, mutNode, dirIsUp = self._t(idx, torch.int32), self._t(mutNode, torch.int32), self._t(dirIsUp, torch.uint8)
+        n = idx.numel()
+        nm = (mutStart[mutNode.long() + 1] - mutStart[mutNode.long()]).long()
+        cap = (L.nkeys[idx.long()].long() + 2 * nm + 2 + 3) // 4 * 4
+        ks = torch.cumsum(cap, 0) - cap
+        ps = ks * 6
+        total = int(cap.sum().item())
+        out_key = torch.empty(total + 4, dtype=torch.int32, device=self.device)
+        out_pay = torch.empty(total * 6 + 4, dtype=torch.float64, device=self.device)
+        nk = torch.empty(n, dtype=torch.int32, device=self.device)
+        npay = torch.empty(n, dtype=torch.int32, device=self.device)
+        rc = self.lib.maple_pass_branch_batch(self.ctx, n, _dp(idx), _dp(mutNode), _dp(dirIsUp), _dp(mutStart), _dp(mut), _dp(out_key),
+                                              _dp(out_pay), _dp(ks), _dp(ps), _dp(nk), _dp(npay), self._stream())
+        capi.check(self.ctx, rc, "maple_pass_branch_batch")
+        st = torch.zeros(n, dtype=torch.int32, device=self.device)
+        return MergeResult(out_key, out_pay, ks, ps, nk, npay, None, st, L.lRef, L.U)
+
     # ---------------------------------------------------------------- reference-named single calls
     def _bind_pair(self, a, b):
         keep = self.lists
@@ -247,6 +287,22 @@ class MapleEngine:
         try:
             out, st = self.blen_batch([0], [1], [1 if fromTipC else 0])
             return False if int(st.cpu()[0]) == 1 else float(out.cpu()[0])
+        finally:
+            self._restore(keep)
+
+    def findProbRoot(self, probVect) -> float:
+        keep = self._bind_pair(probVect, probVect)
+        try:
+            return float(self.prob_root_batch([0]).cpu()[0])
+        finally:
+            self._restore(keep)
+
+    def passGenomeListThroughBranch(self, probVect, mutations, dirIsUp=False):
+        keep = self._bind_pair(probVect, probVect)
+        try:
+            ms = torch.tensor([0, len(mutations)], dtype=torch.int32, device=self.device)
+            mu = torch.tensor([list(m) for m in mutations] or [[0, 0, 0]], dtype=torch.int32, device=self.device).reshape(-1)
+            return self.pass_branch_batch([0], [0], [1 if dirIsUp else 0], ms, mu).to_lists()[0]
         finally:
             self._restore(keep)
 

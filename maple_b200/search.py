@@ -14,6 +14,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import capi
+from .sharding import moves_from_records
 from .tree import DeviceTree
 
 
@@ -69,6 +70,4 @@ def start_topology_updates_parallel(tree: DeviceTree, params: capi.SearchParams,
         again = tree.search_records(tree.spr_search(nodes[retry], params, grow, max_concurrent=max(64, (1 << 28) // grow)))
         rec[retry] = again
         retry = retry[again["status"] == 3]
-    moves = [(int(n), int(r["placement"]), float(r["improvement"])) for n, r in zip(nodes, rec) if r["placement"] >= 0]
-    moves.sort(key=lambda m: m[2])  # improvementsFound.sort(reverse=False,key=itemgetter(2)) (:12312)
-    return moves, rec
+    return moves_from_records(nodes, rec), rec  # improvementsFound.sort(reverse=False,key=itemgetter(2)) (:12312)

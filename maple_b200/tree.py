@@ -94,6 +94,17 @@ class ListArena:
                    torch.from_numpy(packed.nkeys).to(dev), torch.from_numpy(packed.npay).to(dev),
                    torch.from_numpy((packed.key_start < 0).astype(np.int32)).to(dev))
 
+    def add_ids(self, k: int) -> int:
+        """Make room for k more list ids (all None); returns the first new id."""
+        first, dev = self.n, self.key.device
+        self.key_start = torch.cat([self.key_start, torch.full((k,), -1, dtype=torch.int64, device=dev)])
+        self.pay_start = torch.cat([self.pay_start, torch.full((k,), -1, dtype=torch.int64, device=dev)])
+        self.nkeys = torch.cat([self.nkeys, torch.zeros(k, dtype=torch.int32, device=dev)])
+        self.npay = torch.cat([self.npay, torch.zeros(k, dtype=torch.int32, device=dev)])
+        self.n += k
+        self._bind()
+        return first
+
     def get(self, list_id: int):
         ks = int(self.key_start[list_id].item())
         if ks < 0:
@@ -261,6 +272,46 @@ class DeviceTree:
                     self._bump(torch.cat([mm, oo]))  # the reference re-estimates these two lengths (updateBLen, :6289-6299)
                     clean = False
         return clean
+
+    # ------------------------------------------------------------------ calculateTreeLikelihood (:9721-9779)
+    def tree_likelihood(self) -> float:
+        """Sum over internal nodes of the Lkcontribution of mergeVectors(child0, dist0, isTip0, child1, dist1, isTip1,
+        returnLK=True, numMinor1, numMinor2) (:9756) plus findProbRoot(probVect[root]) (:9775).  The merges only read the
+        STORED lower lists, so all of them run as one batch.  Children that carry MAT mutations are re-referenced first
+        (passGenomeListThroughBranch, :9750-9755), also on the device."""
+        eng, n, dev, A = self.eng, self.n, self.eng.device, self.arena
+        t64 = lambda a: torch.as_tensor(a, dtype=torch.int64, device=dev)  # noqa: E731
+        reach = np.zeros(n, bool)
+        reach[self.preorder] = True
+        internal = t64(np.nonzero(reach & (self.child0 >= 0))[0])
+        ids0 = self.d_child0.long()[internal] + FAM_LOWER * n
+        ids1 = self.d_child1.long()[internal] + FAM_LOWER * n
+        root_id = self.root + FAM_LOWER * n
+        mutStart = getattr(self, "mutStart", None)
+        if mutStart is not None:  # lists that must cross a local-reference branch get a temporary id
+            nmut = np.diff(mutStart)
+            hit = np.nonzero(reach & (nmut > 0))[0]
+            if hit.size:
+                d_ms = torch.from_numpy(mutStart).to(dev)
+                d_mu = torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
+                r = eng.pass_branch_batch(t64(hit) + FAM_LOWER * n, hit, np.ones(hit.size, np.uint8), d_ms, d_mu)
+                first = A.add_ids(hit.size)
+                A.store(torch.arange(first, first + hit.size, device=dev), r.key, r.pay, r.key_start, r.pay_start, r.nkeys, r.npay)
+                remap = torch.arange(4 * n, device=dev)
+                remap[t64(hit) + FAM_LOWER * n] = torch.arange(first, first + hit.size, device=dev)
+                ids0, ids1 = remap[ids0], remap[ids1]
+                root_id = int(remap[root_id].item())
+        total = 0.0
+        if internal.numel():
+            c0, c1 = self.d_child0.long()[internal], self.d_child1.long()[internal]
+            nm = torch.from_numpy(self.numMinor).to(dev)
+            r = eng.merge_batch(ids0.int(), self.d_dist[c0], self.d_isTip[c0], ids1.int(), self.d_dist[c1], self.d_isTip[c1],
+                                torch.full((internal.numel(),), capi.MAPLE_MERGE_RETURN_LK, dtype=torch.uint8, device=dev), nm[c0], nm[c1])
+            if bool((r.status != 0).any().item()):
+                raise capi.MapleError("inconsistent lower genome list creation in tree_likelihood (the reference raises, :9762-9764)")
+            total += float(r.lk.sum().item())
+        total += float(eng.prob_root_batch([root_id]).cpu()[0])
+        return total
 
     # ------------------------------------------------------------------ construction from existing lists
     @classmethod

@@ -12,6 +12,7 @@ nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 rnd = sys.argv[2] if len(sys.argv) > 2 else "deep"
 variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+scratch_keys = int(sys.argv[5]) if len(sys.argv) > 5 else 16384
 d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=True)
 eng = MapleEngine(d.model, 0)
 eng.set_search_variant(variant)
@@ -24,8 +25,8 @@ p = search_params(d.model.lRef, True, 2, 6.0 * L) if rnd == "fast" else search_p
 for _ in range(reps):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    out = tree.spr_search(nodes, p, scratch_keys=16384)
+    out = tree.spr_search(nodes, p, scratch_keys=scratch_keys)
     b.record()
     torch.cuda.synchronize()
     rec = tree.search_records(out)
-    print("%s v%d nseq %d: %.1f ms, phase1 %d, %.3g cand/s" % (rnd, variant, nseq, a.elapsed_time(b), rec["phase1"].sum(), rec["phase1"].sum() / a.elapsed_time(b) * 1e3), flush=True)
+    print("%s v%d nseq %d: %.1f ms, phase1 %d, %.3g cand/s, status %s" % (rnd, variant, nseq, a.elapsed_time(b), rec["phase1"].sum(), rec["phase1"].sum() / a.elapsed_time(b) * 1e3, np.bincount(rec["status"], minlength=4).tolist()), flush=True)

@@ -168,3 +168,39 @@ def test_reference_named_single_calls(env):
     c = g["calls"]["areVectorsDifferent"][0]
     assert eng.areVectorsDifferent(L[c["v1"]], None if c["v2"] is None else L[c["v2"]]) == c["out"]
     eng.bind(packed)
+
+
+def test_prob_root_vs_golden_and_oracle(env):
+    g, eng, packed, orc = env
+    from oracle.oracle import Oracle
+    orc_r = Oracle(eng.model, with_root_tables=True)
+    calls = g["calls"]["findProbRoot"]
+    assert calls
+    idx = np.array([c["v"] for c in calls], np.int32)
+    got = eng.prob_root_batch(idx).cpu().numpy()
+    for c, x in zip(calls, got):
+        assert abs(x - c["out"]) <= 1e-6 * max(1.0, abs(c["out"]) * 1e-4), (c, x)  # same bar as the oracle's own pin
+        assert abs(x - orc_r.prob_root(g["lists"][c["v"]])) <= LK_TOL * max(1.0, abs(c["out"]) * 1e-3)
+    assert abs(eng.findProbRoot(g["lists"][calls[0]["v"]]) - got[0]) == 0.0
+
+
+def test_pass_branch_vs_golden(env):
+    g, eng, packed, orc = env
+    calls = g["calls"]["passGenomeListThroughBranch"]
+    for c in calls[:40]:
+        got = eng.passGenomeListThroughBranch(g["lists"][c["v"]], c["mutations"], c["dirIsUp"])
+        assert lists_equal(got, g["lists"][c["out"]]), c
+
+
+def test_tree_likelihood_vs_reference(env):
+    """calculateTreeLikelihood of the reference's frozen tree (:9721-9779), computed on the device from the stored lists."""
+    g, eng, packed, orc = env
+    from maple_b200.engine import MapleEngine
+    from maple_b200.tree import DeviceTree
+    from tree_fixture import tree_arrays, tree_lists
+    eng2 = MapleEngine(eng.model, 0)
+    ta = tree_arrays(g)
+    tree = DeviceTree.from_lists(eng2, ta["up"], ta["child0"], ta["child1"], ta["dist"], ta["root"], ta["isTip"], tree_lists(g),
+                                 ta["mutStart"], ta["mut"], ta["numMinor"])
+    lk = tree.tree_likelihood()
+    assert abs(lk - g["treeLK"]) <= 1e-6, (lk, g["treeLK"])
