@@ -181,7 +181,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
 
 /* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state
  * machine, with subtrees whose lists are all stored ones scanned by the whole warp; 1 = the straight-line
- * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans with the window bookkeeping replayed in parallel rounds instead of node by node
+ * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans scored with the queued-site form of appendProbNode
  * (1-3: kept for A/B measurements and to test the alternative paths; same results). */
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
 
@@ -189,7 +189,7 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
  * depend on it. */
 int maple_ctx_set_scan_min_size(maple_ctx* ctx, int32_t minNodes);
 
-/* Profiling counters of the search kernel (288 uint64: 32 counters + a debug area, meaning in DESIGN.md / scripts/time_search.py): enable != 0
+/* Profiling counters of the search kernel (32 uint64, meaning in DESIGN.md / scripts/time_search.py): enable != 0
  * switches collection on for later launches; out != NULL receives and resets the counters (synchronises). */
 int maple_search_stats(maple_ctx* ctx, int32_t enable, uint64_t* out);
 

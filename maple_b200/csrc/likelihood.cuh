@@ -323,7 +323,12 @@ __device__ double dev_append_sitewise(const DevModel& m, const uint32_t* kP, con
             if (e2.end == pos) e2.next();
         }
         if (!site) break;
-        if (!append_site(m, e1, e2, pos, bLen, isTipC, U, F)) return -INFINITY;
+        {
+            bool minusInf = false;
+            if (append_site_fast(m, *e1.key, e1.pay, *e2.key, e2.pay, pos, bLen, F, minusInf)) {
+                if (minusInf) return -INFINITY;
+            } else if (!append_site(m, e1, e2, pos, bLen, isTipC, U, F)) return -INFINITY;
+        }
         pos = min(e1.end, e2.end);
         if (pos == lRef) break;
         if (e1.end == pos) e1.next();
@@ -335,6 +340,120 @@ __device__ double dev_append_sitewise(const DevModel& m, const uint32_t* kP, con
         }
     }
     if (!(F > 0.0)) return -INFINITY;
+    return Lk + log(F);
+}
+
+// The cheap outcomes of an informative site, straight from the raw keys (same arithmetic as append_site): two certain
+// states without an across-the-root length (:6657-6663, :6729-6742), and an O entry whose probability for the other side's
+// state is above the 0.02 shortcut (:6615, :6692, :6746).  Returns false when the site needs the general code.
+__device__ __forceinline__ bool append_site_fast(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
+                                                 double bLen, double& F, bool& minusInf) {
+    const int t1 = int(k1 & 7u), t2 = int(k2 & 7u), nl1 = int((k1 >> 3) & 3u), nl2 = int((k2 >> 3) & 3u);
+    const int nuc1 = int((k1 >> 6) & 3u), nuc2 = int((k2 >> 6) & 3u);
+    if (t1 < 5 && t2 < 5) {
+        if (nl1 == 2 || m.U) return false;
+        double contrib = bLen;
+        if (nl1 == 1) contrib += pay1[0];
+        if (nl2 == 1) contrib += pay2[0];
+        if (contrib == 0.0) { minusInf = true; return true; }
+        const int from = t1 == T_R ? nuc2 : t1, to = t2 == T_R ? nuc1 : t2;
+        const SiteQ q(m, pos);
+        F *= fmin(0.25, q.at(from, to) * contrib);
+        return true;
+    }
+    if (t1 < 5 && t2 == T_O) {
+        const double ai = pay2[nl2 + (t1 == T_R ? nuc2 : t1)];
+        if (ai > 0.02) { F *= ai; return true; }
+        return false;
+    }
+    if (t1 == T_O && t2 < 5) {
+        const double ai = pay1[nl1 + (t2 == T_R ? nuc1 : t2)];
+        if (ai > 0.02) { F *= ai; return true; }
+        return false;
+    }
+    return false;
+}
+
+// One queued site of dev_append_q4: returns F times the site's factor, or -1 when the reference returns -inf here.
+__device__ __noinline__ double append_site_ref(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
+                                               double bLen, bool isTipC, double F) {
+    bool minusInf = false;
+    if (append_site_fast(m, k1, pay1, k2, pay2, pos, bLen, F, minusInf)) return minusInf ? -1.0 : F;
+    Cursor<false> e1, e2;
+    e1.key = nullptr; e1.pay = pay1; e1.decode(k1);
+    e2.key = nullptr; e2.pay = pay2; e2.decode(k2);
+    if (!append_site(m, e1, e2, pos, bLen, isTipC, m.U != 0, F)) return -1.0;
+    return F;
+}
+
+// bit (t1*8+t2) set <=> append_informative(t1, t2), for entry types 0..6
+__host__ __device__ constexpr unsigned long long append_informative_mask() {
+    unsigned long long mk = 0;
+    for (int t1 = 0; t1 < 7; t1++)
+        for (int t2 = 0; t2 < 7; t2++)
+            if (t1 != T_N && t2 != T_N && !(t1 == T_R && t2 == T_R) && !(t1 < 4 && t1 == t2)) mk |= 1ull << (t1 * 8 + t2);
+    return mk;
+}
+
+// appendProbNode for a warp whose lanes score different pairs at once (subtree scans): same arithmetic in the same order
+// as dev_append, but the walk and the site arithmetic are separated.  Each lane walks its two key streams with a few
+// integer operations per segment and parks up to four informative sites (raw keys, payload offsets, position) in
+// registers; then the lanes evaluate their parked sites together.  The long site code therefore runs about
+// (sites per pair / 4) times per batch with most lanes active, instead of once per segment with a few.
+template <bool LD>
+__device__ double dev_append_q4(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC, bool isTipC,
+                                double bLen) {
+    constexpr unsigned long long INF = append_informative_mask();
+    const unsigned act = __activemask();  // the lanes scoring in this batch: they walk and evaluate in lock step
+    const int lRef = m.lRef;
+    const uint32_t *q1 = kP, *q2 = kC;
+    uint32_t k1 = LD ? __ldg(q1) : *q1, k2 = LD ? __ldg(q2) : *q2;
+    int o1 = 0, o2 = 0;  // payload offsets of the current entries
+    int pos = 0;
+    double F = 1.0;
+    double Lk = bLen * (-(double)lRef);
+    if (m.U && isTipC) Lk += m.totError;
+    bool done = false, dead = false;  // dead: the reference returned -inf at some site
+    for (;;) {
+        uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0, c1 = 0, c2 = 0, d1 = 0, d2 = 0;
+        int ao1 = 0, ao2 = 0, bo1 = 0, bo2 = 0, co1 = 0, co2 = 0, do1 = 0, do2 = 0, ap = 0, bp = 0, cp = 0, dp = 0;
+        int ns = 0;
+        while (!done) {
+            const int t1 = int(k1 & 7u), t2 = int(k2 & 7u);
+            if ((INF >> (t1 * 8 + t2)) & 1ull) {
+                if (ns == 0) { a1 = k1; a2 = k2; ao1 = o1; ao2 = o2; ap = pos; }
+                else if (ns == 1) { b1 = k1; b2 = k2; bo1 = o1; bo2 = o2; bp = pos; }
+                else if (ns == 2) { c1 = k1; c2 = k2; co1 = o1; co2 = o2; cp = pos; }
+                else { d1 = k1; d2 = k2; do1 = o1; do2 = o2; dp = pos; }
+                ns++;
+            }
+            const int e1 = int(k1 >> 8), e2 = int(k2 >> 8);
+            pos = min(e1, e2);
+            if (pos == lRef) { done = true; break; }
+            if (e1 == pos) { o1 += int((k1 >> 3) & 3u) + (t1 == T_O ? 4 : 0); ++q1; k1 = LD ? __ldg(q1) : *q1; }
+            if (e2 == pos) { o2 += int((k2 >> 3) & 3u) + (t2 == T_O ? 4 : 0); ++q2; k2 = LD ? __ldg(q2) : *q2; }
+            if (ns == 4) break;
+        }
+        __syncwarp(act);
+        for (int q = 0; q < 4; q++) {
+            const bool mine = q < ns && !dead;
+            if (!__any_sync(act, mine)) break;
+            if (mine) {
+                const uint32_t s1 = q == 0 ? a1 : q == 1 ? b1 : q == 2 ? c1 : d1, s2 = q == 0 ? a2 : q == 1 ? b2 : q == 2 ? c2 : d2;
+                const int so1 = q == 0 ? ao1 : q == 1 ? bo1 : q == 2 ? co1 : do1, so2 = q == 0 ? ao2 : q == 1 ? bo2 : q == 2 ? co2 : do2;
+                const int sp = q == 0 ? ap : q == 1 ? bp : q == 2 ? cp : dp;
+                F = append_site_ref(m, s1, pP + so1, s2, pC + so2, sp, bLen, isTipC, F);
+                if (F < 0.0) dead = true;
+                else if (min(int(s1 >> 8), int(s2 >> 8)) != lRef && F <= kMinCarryOver) {  // :6772-6783
+                    if (F < DBL_MIN) dead = true;
+                    else { Lk += log(F); F = 1.0; }
+                }
+            }
+        }
+        if (dead) done = true;
+        if (!__any_sync(act, !done)) break;
+    }
+    if (dead || !(F > 0.0)) return -INFINITY;
     return Lk + log(F);
 }
 

@@ -37,13 +37,14 @@ struct maple_ctx {
     int treeHeight = 0;
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
+    bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
     int fsmMinBlocks = 8;            // resident CTAs per SM the state-machine kernel is compiled for (6, 8 or 10: register budget)
     int scanMinSize = 8;             // subtrees of at least this many nodes are scanned by the whole warp (0 = never)
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
-    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans with the parallel-rounds replay, 4 = 3 + cross-check when stats are on
+    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans scored with the queued-site appendProbNode
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
                                                                    uint32_t* scrKey, double* scrPay, double* scrAis, StackE* scrStack,
                                                                    unsigned capK, unsigned capP, unsigned capA, int stackCap,
                                                                    unsigned long long* counter, long long* outCycles, int scanMinSize,
-                                                                   int replayMode, unsigned long long* stats) {
+                                                                   int scanFlags, int poolBytes, unsigned long long* stats) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     }
     const bool l0 = (threadIdx.x & 31) == 0;
     extern __shared__ uint4 dynSmem[];
-    ScanSmem& W = reinterpret_cast<ScanSmem*>(dynSmem)[threadIdx.x >> 5];
+    const int warpSmem = int(sizeof(ScanSmem) - sizeof(uint4)) + poolBytes;
+    ScanSmem& W = *reinterpret_cast<ScanSmem*>(reinterpret_cast<char*>(dynSmem) + (threadIdx.x >> 5) * warpSmem);
     long long tk = clock64();
 #define STAT_T(i) do { if (st) { const long long now_ = clock64(); if (l0) st[i] += (unsigned long long)(now_ - tk); tk = now_; } } while (0)
 #define STAT_N(i, v) do { if (st && l0) st[i] += (unsigned long long)(v); } while (0)
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
         STAT_T(4);
         // ---------------- subtree scans: the whole warp works for one lane's search at a time
         for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1)
-            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, replayMode, st, replayMode == 2 ? stats + 32 : nullptr);
+            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags & 1, st);
         STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
     }
@@ -465,6 +467,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     maple_ctx* ctx = new maple_ctx();
     ctx->device = device;
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
+    if (const char* e = getenv("MAPLE_SCAN_APPEND")) ctx->scanAppendSitewise = strcmp(e, "q4") != 0;
     cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
     memset(&ctx->model, 0, sizeof(DevModel));
     ctx->model.lRef = lRef;
@@ -829,9 +832,14 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     const int stackCap = (2 * ctx->treeHeight + 32 + 63) & ~63;
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
-    const size_t fsmSmem = (kSearchThreads / 32) * sizeof(ScanSmem);
+    // shared memory: a fixed part per warp plus as much list pool as the targeted CTAs per SM leave (227 KB per SM, 1 KB reserved per CTA)
+    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : ctx->fsmMinBlocks == 10 ? 10 : 8;
+    const int fixedPerWarp = int(sizeof(ScanSmem) - sizeof(uint4));
+    int poolBytes = ((227 * 1024 / ctasWanted - 2048) / (kSearchThreads / 32) - fixedPerWarp) & ~15;
+    if (poolBytes > 12288) poolBytes = 12288;
+    const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
-                               StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, unsigned long long*);
+                               StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*);
     FsmKernel fsmKernel = k_spr_search_fsm<8>;  // 128 registers, 16 warps per SM: measured best of the three on the deep round
     if (ctx->fsmMinBlocks == 6) fsmKernel = k_spr_search_fsm<6>;
     else if (ctx->fsmMinBlocks == 10) fsmKernel = k_spr_search_fsm<10>;
@@ -862,7 +870,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     double* scrAis = (double*)(base + (size_t)threads * capP * 8);
     StackE* scrStack = (StackE*)(base + (size_t)threads * (capP + capA) * 8);
     uint32_t* scrKey = (uint32_t*)(base + (size_t)threads * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
-    if ((ctx->searchVariant == 0 || ctx->searchVariant >= 3) && T.order && ctx->scanMinSize > 0) {
+    if ((ctx->searchVariant == 0 || ctx->searchVariant == 3) && T.order && ctx->scanMinSize > 0) {
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, sp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
     }
@@ -874,8 +882,8 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         fsmKernel<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
                                                                              scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
                                                                              (long long*)out_cycles,
-                                                                             (T.order && (ctx->searchVariant == 0 || ctx->searchVariant >= 3)) ? ctx->scanMinSize : 0,
-                                                                             ctx->searchVariant == 3 ? 1 : (ctx->searchVariant == 4 && ctx->statsOn) ? 2 : (ctx->searchVariant == 4 ? 1 : 0),
+                                                                             (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
+                                                                             (ctx->scanAppendSitewise && ctx->searchVariant != 3) ? 0 : 1, poolBytes,
                                                                              ctx->statsOn ? ctx->searchStats : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -883,7 +891,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
 }
 
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
-    if (!ctx || variant < 0 || variant > 4) return MAPLE_E_ARG;
+    if (!ctx || variant < 0 || variant > 3) return MAPLE_E_ARG;
     ctx->searchVariant = variant;
     return MAPLE_OK;
 }
@@ -892,13 +900,13 @@ int maple_search_stats(maple_ctx* ctx, int32_t enable, uint64_t* out) {
     if (!ctx) return MAPLE_E_ARG;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->searchStats) {
-        CK(cudaMalloc((void**)&ctx->searchStats, (kNumSearchStats + 256) * 8));
-        CK(cudaMemset(ctx->searchStats, 0, (kNumSearchStats + 256) * 8));
+        CK(cudaMalloc((void**)&ctx->searchStats, kNumSearchStats * 8));
+        CK(cudaMemset(ctx->searchStats, 0, kNumSearchStats * 8));
     }
     if (out) {
         CK(cudaDeviceSynchronize());
-        CK(cudaMemcpy(out, ctx->searchStats, (kNumSearchStats + 256) * 8, cudaMemcpyDeviceToHost));
-        CK(cudaMemset(ctx->searchStats, 0, (kNumSearchStats + 256) * 8));
+        CK(cudaMemcpy(out, ctx->searchStats, kNumSearchStats * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(ctx->searchStats, 0, kNumSearchStats * 8));
     }
     ctx->statsOn = enable != 0;
     return MAPLE_OK;

@@ -447,18 +447,15 @@ constexpr int kWinMax = 96;      // nodes per window
 constexpr int kPathSm = 40;      // per-depth states kept in shared memory (deeper ones go to global scratch)
 constexpr int kCKeys = 64;       // removed list staged in shared memory when it has at most this many entries ...
 constexpr int kCPay = 96;        // ... and this many payload doubles
-constexpr int kPoolBytes = 8192; // mid-branch lists of one batch
 struct ScanSmem {
-    double winScore[kWinMax];  // candidate score; after the replay: the midProb the node hands to its children
+    double winScore[kWinMax];  // candidate scores of the nodes that need one
     double cPay[kCPay];
     PathE path[kPathSm];
-    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax], winParent[kWinMax], winOut[kWinMax];
+    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax];
     uint32_t cKey[kCKeys];
-    uint4 pool[kPoolBytes / 16];
+    uint4 pool[1];  // mid-branch lists of one batch: poolBytes of them, the rest of the warp's share of the dynamic shared memory
 };
 // winInfo: bit0 eligible, bit1 has probVectTotUp, bit2 was pushed, bit3 has children, bits 8.. depth relative to the job's root
-// winOut: failedPasses | WO_*
-constexpr int WO_DESCEND = 1 << 20, WO_REACHED = 1 << 21, WO_DONE = 1 << 22, WO_COUNTED = 1 << 23, WO_FAILMASK = (1 << 20) - 1;
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
@@ -473,10 +470,13 @@ __device__ __noinline__ double f_append_sitewise(const DevModel& m, const uint32
                                                  bool isTipC, double bLen) {
     return dev_append_sitewise<false>(m, kP, pP, kC, pC, isTipC, bLen);
 }
+__device__ __noinline__ double f_append_q4(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC,
+                                           bool isTipC, double bLen) {
+    return dev_append_q4<false>(m, kP, pP, kC, pC, isTipC, bLen);
+}
 
 __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack,
-                              int stackCap, ScanSmem& W, int replayMode /* 0 sequential, 1 parallel rounds, 2 both + compare (debug) */,
-                              unsigned long long* st, unsigned long long* dbg) {
+                              int stackCap, ScanSmem& W, int poolBytes, bool queuedAppend, unsigned long long* st) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int R = __shfl_sync(FULL, f.t1, src);
@@ -550,8 +550,6 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                 W.winInfo[w] = info;
                 W.winSize[w] = rec.size;
                 W.winNode[w] = rec.node;
-                W.winParent[w] = rec.parentPos - pos;
-                W.winOut[w] = 0;
             }
             const unsigned need = __ballot_sync(FULL, (info & 7) == 7);
             const int room = 32 - nScore;
@@ -587,7 +585,7 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                 }
             }
             const int endOff = warp_incl_scan(bytes, lane);
-            if (bytes && endOff <= kPoolBytes) {
+            if (bytes && endOff <= poolBytes) {
                 uint4* dk = W.pool + ((endOff - bytes) >> 4);
                 uint4* dp = dk + nk4;
                 const uint4* gk = reinterpret_cast<const uint4*>(kP);
@@ -604,7 +602,9 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                 if (lane == 0) { st[23] += (unsigned long long)(now - tk); st[19] += 1; st[20] += nScore; st[24] += nWin; }
                 tk = now;
             }
-            if (myW >= 0) W.winScore[myW] = f_append_sitewise(m, kP, pP, remK, remP, isRemovedTip, removedBLen);
+            if (myW >= 0)
+                W.winScore[myW] = queuedAppend ? f_append_q4(m, kP, pP, remK, remP, isRemovedTip, removedBLen)
+                                               : f_append_sitewise(m, kP, pP, remK, remP, isRemovedTip, removedBLen);
         }
         __syncwarp();
         if (st) {
@@ -612,172 +612,42 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
             if (lane == 0) st[6] += (unsigned long long)(now - tk);
             tk = now;
         }
-        // ---- replay.  Parallel form: assume no node of the window that holds a new running best gets pruned; then the best seen
-        // before each node is a prefix maximum over the window, every node's bookkeeping depends only on its parent's, and the
-        // nodes can be processed parent-before-child in a few rounds.  The assumption is checked afterwards; if it fails (rare:
-        // a pruned branch would have to beat the running best) the window is replayed one node at a time instead.
-        bool parallelOk = replayMode != 0;
+        // ---- replay: the reference's sequential bookkeeping over the window, every lane the same
         int j = 0;
-        int chkJ = -1, chkCounted = 0;
-        double chkBest = 0.0;
-        const int phase1Before = phase1;
-        if (parallelOk) {
-            // (1) prefix maximum of the scores in window order
-            double bb[kWinMax / 32];  // best before node c*32+lane
-            double carry = best;
-#pragma unroll
-            for (int c = 0; c < kWinMax / 32; c++) {
-                const int w = c * 32 + lane;
-                const bool cnt = w < nWin && (W.winInfo[w] & 7) == 7;
-                double v = cnt ? W.winScore[w] : -INFINITY;  // inclusive maximum over this chunk up to the lane
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double x = __shfl_up_sync(FULL, v, o);
-                    if (lane >= o) v = fmax(v, x);
-                }
-                double ex = __shfl_up_sync(FULL, v, 1);
-                if (lane == 0) ex = -INFINITY;
-                bb[c] = fmax(carry, ex);
-                carry = fmax(carry, __shfl_sync(FULL, v, 31));
-            }
-            // (2) rounds: a node is processed once its parent is
-            unsigned doneMask = 0;  // bit c: node c*32+lane done
-#pragma unroll
-            for (int c = 0; c < kWinMax / 32; c++)
-                if (c * 32 + lane >= nWin) doneMask |= 1u << c;
-            int maxTarget = 0, nCounted = 0, anyNewBest = 0, bad = 0;
-            for (int round = 0; round < kWinMax + 1; round++) {
-                if (__all_sync(FULL, doneMask == (1u << (kWinMax / 32)) - 1u)) break;
-                unsigned ready = 0;  // decided before anything of this round is written
-#pragma unroll
-                for (int c = 0; c < kWinMax / 32; c++) {
-                    if (doneMask & (1u << c)) continue;
-                    const int pw = W.winParent[c * 32 + lane];
-                    if (pw < 0 || (W.winOut[pw] & WO_DONE)) ready |= 1u << c;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int c = 0; c < kWinMax / 32; c++) {
-                    if (!(ready & (1u << c))) continue;
-                    const int w = c * 32 + lane;
-                    const int pw = W.winParent[w];
-                    double lastLK;
-                    int failed;
-                    bool reached;
-                    const int inf = W.winInfo[w];
-                    const int rel = inf >> 8;
-                    if (pw < 0) {  // parent before the window: it was reached and it descended, or this window would not have got here
-                        PathE pe;
-                        if (rel < kPathSm) pe = W.path[rel];
-                        else pe = gpath[rel];
-                        lastLK = pe.lk; failed = pe.failed; reached = true;
-                    } else {
-                        const int po = W.winOut[pw];
-                        lastLK = W.winScore[pw];
-                        failed = po & WO_FAILMASK;
-                        reached = (po & WO_REACHED) && (po & WO_DESCEND);
-                    }
-                    int out = WO_DONE;
-                    if (reached) {
-                        out |= WO_REACHED;
-                        double midProb = lastLK;
-                        int target = w + W.winSize[w];
-                        if (inf & 4) {
-                            bool alive = true;
-                            double bestAfter = bb[c];
-                            if (inf & 1) {
-                                if (!(inf & 2)) alive = false;
-                                else {
-                                    midProb = W.winScore[w];
-                                    out |= WO_COUNTED;
-                                    nCounted++;
-                                    if (midProb > bb[c]) { bestAfter = midProb; failed = 0; anyNewBest = 1; }
-                                    else if (midProb < (lastLK - sp.thresholdLogLKconsecutivePlacement)) failed++;
-                                }
-                            }
-                            if (alive && (inf & 8)) {
-                                bool descend;
-                                if (sp.strictTopologyStopRules) descend = failed <= sp.allowedFailsTopology && midProb > (bestAfter - sp.thresholdLogLKtopology);
-                                else descend = failed <= sp.allowedFailsTopology || midProb > (bestAfter - sp.thresholdLogLKtopology);
-                                if (descend) { out |= WO_DESCEND; target = w + 1; }
-                            }
-                        }
-                        maxTarget = max(maxTarget, target);
-                        if (!(out & WO_COUNTED)) W.winScore[w] = midProb;  // what the children inherit as lastLK (a counted node: its own score)
-                    } else if ((inf & 7) == 7 && W.winScore[w] > bb[c]) bad = 1;  // a pruned node holds a new best: the prefix maxima are wrong
-                    W.winOut[w] = out | (failed & WO_FAILMASK);
-                    doneMask |= 1u << c;
-                }
-                __syncwarp();
-            }
-            parallelOk = !__any_sync(FULL, bad) && __all_sync(FULL, doneMask == (1u << (kWinMax / 32)) - 1u);
-            if (parallelOk && replayMode == 2) {  // debug: keep the parallel outcome aside, let the sequential replay decide
-                int mt = maxTarget, nc = nCounted;
-                double nb = best;
-                for (int c = 0; c < kWinMax / 32; c++) {
-                    const int w = c * 32 + lane;
-                    if (w < nWin && (W.winOut[w] & WO_COUNTED)) nb = fmax(nb, W.winScore[w]);
-                }
-                for (int o = 16; o; o >>= 1) {
-                    mt = max(mt, __shfl_xor_sync(FULL, mt, o));
-                    nc += __shfl_xor_sync(FULL, nc, o);
-                    nb = fmax(nb, __shfl_xor_sync(FULL, nb, o));
-                }
-                chkJ = mt; chkCounted = nc; chkBest = nb;
-                parallelOk = false;
-            }
-            if (parallelOk) {
-                // (3) commit: counts, running best, phase-2 queue in window order, per-depth states for the next windows
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    maxTarget = max(maxTarget, __shfl_xor_sync(FULL, maxTarget, o));
-                    nCounted += __shfl_xor_sync(FULL, nCounted, o);
-                }
-                double newBestVal = best;
-#pragma unroll
-                for (int c = 0; c < kWinMax / 32; c++) {
-                    const int w = c * 32 + lane;
-                    const int out = w < nWin ? W.winOut[w] : 0;
-                    const bool counted = (out & WO_COUNTED) != 0;
-                    const double sc = counted ? W.winScore[w] : -INFINITY;  // a counted node hands down its own score
-                    const bool queued = counted && sc > bb[c] - sp.thresholdLogLKoptimizationTopology;  // :7071
-                    const unsigned qm = __ballot_sync(FULL, queued);
-                    if (queued) {
-                        const int at = qN + __popc(qm & ((1u << lane) - 1u));
-                        if (at < qCap) qTop[-1 - at] = uint32_t(W.winNode[w]);
-                    }
-                    qN += __popc(qm);
-                    newBestVal = fmax(newBestVal, sc);
-                    // the last node of each depth that descends leaves its state for later windows
-                    const bool desc = (out & WO_DESCEND) != 0;
-                    const int rel1 = (W.winInfo[w < nWin ? w : 0] >> 8) + 1;
-                    const unsigned peers = __match_any_sync(FULL, desc ? rel1 : -1 - lane);
-                    if (desc && lane == 31 - __clz(peers)) {
-                        if (rel1 >= pathCap) err = 3;
-                        else if (rel1 < kPathSm) W.path[rel1] = PathE{W.winScore[w], out & WO_FAILMASK, 0};
-                        else gpath[rel1] = PathE{W.winScore[w], out & WO_FAILMASK, 0};
-                    }
-                    __syncwarp();
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) newBestVal = fmax(newBestVal, __shfl_xor_sync(FULL, newBestVal, o));
-                if (qN > qCap) err = 3;
-                err = __any_sync(FULL, err == 3) ? 3 : err;
-                if (__any_sync(FULL, anyNewBest)) newBest = 1;
-                best = newBestVal;
-                phase1 += nCounted;
-                j = maxTarget;
-            }
-        }
-        if (!parallelOk) {
-            // sequential replay, every lane the same (the scores of the nodes that need one are still in winScore)
-            if (st && lane == 0) st[25] += 1;
-            j = 0;
+        {
+            int inf = W.winInfo[0], sz = W.winSize[0];
+            double sc = W.winScore[0];
             while (j < nWin) {
-                const int inf = W.winInfo[j];
                 const int rel = inf >> 8;
+                // both possible successors are fetched before the decision is known
+                const int jA = j + 1, jB = j + sz;
+                int infA = 0, szA = 1, infB = 0, szB = 1;
+                double scA = 0.0, scB = 0.0;
+                if (jA < nWin) { infA = W.winInfo[jA]; szA = W.winSize[jA]; scA = W.winScore[jA]; }
+                if (jB < nWin) { infB = W.winInfo[jB]; szB = W.winSize[jB]; scB = W.winScore[jB]; }
                 bool descend = false;
-                if (inf & 4) {
+                if (rel + 1 < kPathSm) {
+                    // straight-line form of the bookkeeping below (the usual case: the per-depth states are in shared memory)
+                    const PathE pe = W.path[rel];
+                    const bool scored = (inf & 7) == 7, dead = (inf & 3) == 1;  // dead: eligible but no probVectTotUp
+                    const bool nb = scored && sc > best;
+                    const bool queued = scored && sc > best - sp.thresholdLogLKoptimizationTopology;  // :7071
+                    const double mid = scored ? sc : pe.lk;
+                    const int failed = nb ? 0 : pe.failed + ((scored && sc < (pe.lk - sp.thresholdLogLKconsecutivePlacement)) ? 1 : 0);
+                    if (queued) {
+                        if (qN >= qCap) err = 3;
+                        else qTop[-1 - qN] = uint32_t(W.winNode[j]);
+                        qN++;
+                    }
+                    best = nb ? sc : best;
+                    newBest |= nb ? 1 : 0;
+                    phase1 += scored ? 1 : 0;
+                    const bool within = mid > (best - sp.thresholdLogLKtopology);
+                    const bool rule = sp.strictTopologyStopRules ? (failed <= sp.allowedFailsTopology && within)
+                                                                 : (failed <= sp.allowedFailsTopology || within);
+                    descend = (inf & 4) && !dead && (inf & 8) && rule;
+                    W.path[rel + 1] = PathE{mid, failed, 0};  // every lane stores the same value; unused unless this node descends
+                } else if (inf & 4) {
                     PathE pe;
                     if (rel < kPathSm) pe = W.path[rel];
                     else pe = gpath[rel];
@@ -787,7 +657,7 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                     if (inf & 1) {
                         if (!(inf & 2)) alive = false;  // no probVectTotUp: the reference moves on without visiting the children
                         else {
-                            midProb = W.winScore[j];
+                            midProb = sc;
                             phase1++;
                             if (midProb > best - sp.thresholdLogLKoptimizationTopology) {  // :7071
                                 if (qN >= qCap) err = 3;
@@ -803,25 +673,14 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                         else descend = failed <= sp.allowedFailsTopology || midProb > (best - sp.thresholdLogLKtopology);
                         if (descend) {
                             if (rel + 1 >= pathCap) { err = 3; descend = false; }
-                            else if (rel + 1 < kPathSm) W.path[rel + 1] = PathE{midProb, failed, 0};  // every lane stores the same value
+                            else if (rel + 1 < kPathSm) W.path[rel + 1] = PathE{midProb, failed, 0};
                             else gpath[rel + 1] = PathE{midProb, failed, 0};
                         }
                     }
                 }
-                j += descend ? 1 : W.winSize[j];
+                if (descend) { j = jA; inf = infA; sz = szA; sc = scA; }
+                else { j = jB; inf = infB; sz = szB; sc = scB; }
                 if (err) break;
-            }
-            if (chkJ >= 0 && dbg && (chkJ != j || chkCounted != phase1 - phase1Before || chkBest != best) && lane == 0) {
-                if (atomicAdd(dbg, 1ULL) == 0) {
-                    dbg[1] = (unsigned long long)pos; dbg[2] = (unsigned long long)nWin; dbg[3] = (unsigned long long)chkJ; dbg[4] = (unsigned long long)j;
-                    dbg[5] = (unsigned long long)chkCounted; dbg[6] = (unsigned long long)(phase1 - phase1Before);
-                    dbg[7] = (unsigned long long)__double_as_longlong(chkBest); dbg[8] = (unsigned long long)__double_as_longlong(best);
-                    dbg[9] = (unsigned long long)R; dbg[10] = (unsigned long long)t.pre[R]; dbg[11] = (unsigned long long)nScore;
-                    for (int q = 0; q < nWin && q < 96; q++) {
-                        dbg[16 + 2 * q] = ((unsigned long long)(unsigned)W.winInfo[q]) | ((unsigned long long)(unsigned)W.winOut[q] << 32);
-                        dbg[17 + 2 * q] = ((unsigned long long)(unsigned)W.winParent[q]) | ((unsigned long long)(unsigned)W.winSize[q] << 32);
-                    }
-                }
             }
         }
         pos += j;

@@ -138,7 +138,7 @@ class MapleEngine:
 
     def search_stats(self, enable: bool = True, read: bool = True):
         """Profiling counters of the search kernel (see scripts/time_search.py for their meaning)."""
-        out = (C.c_uint64 * 288)() if read else None
+        out = (C.c_uint64 * 32)() if read else None
         capi.check(self.ctx, self.lib.maple_search_stats(self.ctx, 1 if enable else 0, out), "maple_search_stats")
         return None if out is None else list(out)
 
