@@ -181,7 +181,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
 
 /* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state
  * machine, with subtrees whose lists are all stored ones scanned by the whole warp; 1 = the straight-line
- * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans scored with the queued-site form of appendProbNode
+ * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans with the queued-site form of appendProbNode and the node-by-node window replay
  * (1-3: kept for A/B measurements and to test the alternative paths; same results). */
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
 

@@ -298,51 +298,6 @@ __device__ double dev_append(const DevModel& m, const uint32_t* kP, const double
     return Lk + log(F);
 }
 
-// appendProbNode again, same arithmetic in the same order, arranged for a warp whose lanes score different pairs at
-// once: every lane first walks (cheap loop) to its next informative site, then the lanes evaluate one site each
-// together, so the long site code runs once per "k-th site of every lane" instead of once per segment of any lane.
-template <bool LD>
-__device__ double dev_append_sitewise(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC,
-                                      bool isTipC, double bLen) {
-    const int lRef = m.lRef;
-    const bool U = m.U != 0;
-    Cursor<LD> e1, e2;
-    e1.init(kP, pP);
-    e2.init(kC, pC);
-    int pos = 0;
-    double F = 1.0;
-    double Lk = bLen * (-(double)lRef);
-    if (U && isTipC) Lk += m.totError;
-    for (;;) {
-        bool site = false;
-        for (;;) {  // segments that contribute nothing leave F untouched, so the carry-over test has nothing to do
-            if (append_informative(e1.type, e2.type)) { site = true; break; }
-            pos = min(e1.end, e2.end);
-            if (pos == lRef) break;
-            if (e1.end == pos) e1.next();
-            if (e2.end == pos) e2.next();
-        }
-        if (!site) break;
-        {
-            bool minusInf = false;
-            if (append_site_fast(m, *e1.key, e1.pay, *e2.key, e2.pay, pos, bLen, F, minusInf)) {
-                if (minusInf) return -INFINITY;
-            } else if (!append_site(m, e1, e2, pos, bLen, isTipC, U, F)) return -INFINITY;
-        }
-        pos = min(e1.end, e2.end);
-        if (pos == lRef) break;
-        if (e1.end == pos) e1.next();
-        if (e2.end == pos) e2.next();
-        if (F <= kMinCarryOver) {  // :6772-6783
-            if (F < DBL_MIN) return -INFINITY;
-            Lk += log(F);
-            F = 1.0;
-        }
-    }
-    if (!(F > 0.0)) return -INFINITY;
-    return Lk + log(F);
-}
-
 // The cheap outcomes of an informative site, straight from the raw keys (same arithmetic as append_site): two certain
 // states without an across-the-root length (:6657-6663, :6729-6742), and an O entry whose probability for the other side's
 // state is above the 0.02 shortcut (:6615, :6692, :6746).  Returns false when the site needs the general code.
@@ -375,15 +330,19 @@ __device__ __forceinline__ bool append_site_fast(const DevModel& m, uint32_t k1,
 }
 
 // One queued site of dev_append_q4: returns F times the site's factor, or -1 when the reference returns -inf here.
-__device__ __noinline__ double append_site_ref(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
-                                               double bLen, bool isTipC, double F) {
-    bool minusInf = false;
-    if (append_site_fast(m, k1, pay1, k2, pay2, pos, bLen, F, minusInf)) return minusInf ? -1.0 : F;
+__device__ __noinline__ double append_site_general(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
+                                                   double bLen, bool isTipC, double F) {
     Cursor<false> e1, e2;
     e1.key = nullptr; e1.pay = pay1; e1.decode(k1);
     e2.key = nullptr; e2.pay = pay2; e2.decode(k2);
     if (!append_site(m, e1, e2, pos, bLen, isTipC, m.U != 0, F)) return -1.0;
     return F;
+}
+__device__ __forceinline__ double append_site_ref(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
+                                                  double bLen, bool isTipC, double F) {
+    bool minusInf = false;
+    if (append_site_fast(m, k1, pay1, k2, pay2, pos, bLen, F, minusInf)) return minusInf ? -1.0 : F;
+    return append_site_general(m, k1, pay1, k2, pay2, pos, bLen, isTipC, F);
 }
 
 // bit (t1*8+t2) set <=> append_informative(t1, t2), for entry types 0..6
@@ -393,6 +352,50 @@ __host__ __device__ constexpr unsigned long long append_informative_mask() {
         for (int t2 = 0; t2 < 7; t2++)
             if (t1 != T_N && t2 != T_N && !(t1 == T_R && t2 == T_R) && !(t1 < 4 && t1 == t2)) mk |= 1ull << (t1 * 8 + t2);
     return mk;
+}
+
+// appendProbNode again, same arithmetic in the same order, arranged for a warp whose lanes score different pairs at
+// once: every lane first walks to its next informative site -- a loop over the raw keys with a handful of integer
+// operations per segment, payload offsets advanced without touching the payload -- then the lanes evaluate one site
+// each together, so the site code runs once per "k-th site of every lane" instead of once per segment of any lane.
+template <bool LD>
+__device__ double dev_append_sitewise(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC,
+                                      bool isTipC, double bLen) {
+    constexpr unsigned long long INF = append_informative_mask();
+    const int lRef = m.lRef;
+    const uint32_t *q1 = kP, *q2 = kC;
+    uint32_t k1 = LD ? __ldg(q1) : *q1, k2 = LD ? __ldg(q2) : *q2;
+    const double *y1 = pP, *y2 = pC;  // payload of the current entries
+    int pos = 0;
+    double F = 1.0;
+    double Lk = bLen * (-(double)lRef);
+    if (m.U && isTipC) Lk += m.totError;
+    for (;;) {
+        bool site = false;
+        for (;;) {  // segments that contribute nothing leave F untouched, so the carry-over test has nothing to do
+            if ((INF >> ((k1 & 7u) * 8u + (k2 & 7u))) & 1ull) { site = true; break; }
+            const int e1 = int(k1 >> 8), e2 = int(k2 >> 8);
+            pos = min(e1, e2);
+            if (pos == lRef) break;
+            if (e1 == pos) { y1 += ((k1 >> 3) & 3u) + ((k1 & 7u) == 6u ? 4u : 0u); ++q1; k1 = LD ? __ldg(q1) : *q1; }
+            if (e2 == pos) { y2 += ((k2 >> 3) & 3u) + ((k2 & 7u) == 6u ? 4u : 0u); ++q2; k2 = LD ? __ldg(q2) : *q2; }
+        }
+        if (!site) break;
+        F = append_site_ref(m, k1, y1, k2, y2, pos, bLen, isTipC, F);
+        if (F < 0.0) return -INFINITY;
+        const int e1 = int(k1 >> 8), e2 = int(k2 >> 8);
+        pos = min(e1, e2);
+        if (pos == lRef) break;
+        if (e1 == pos) { y1 += ((k1 >> 3) & 3u) + ((k1 & 7u) == 6u ? 4u : 0u); ++q1; k1 = LD ? __ldg(q1) : *q1; }
+        if (e2 == pos) { y2 += ((k2 >> 3) & 3u) + ((k2 & 7u) == 6u ? 4u : 0u); ++q2; k2 = LD ? __ldg(q2) : *q2; }
+        if (F <= kMinCarryOver) {  // :6772-6783
+            if (F < DBL_MIN) return -INFINITY;
+            Lk += log(F);
+            F = 1.0;
+        }
+    }
+    if (!(F > 0.0)) return -INFINITY;
+    return Lk + log(F);
 }
 
 // appendProbNode for a warp whose lanes score different pairs at once (subtree scans): same arithmetic in the same order

@@ -37,14 +37,15 @@ struct maple_ctx {
     int treeHeight = 0;
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
+    bool scanReplaySequential = false;  // A/B: node-by-node window replay instead of the pointer-jumping one
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
-    int fsmMinBlocks = 8;            // resident CTAs per SM the state-machine kernel is compiled for (6, 8 or 10: register budget)
+    int fsmMinBlocks = 6;            // resident CTAs per SM the state-machine kernel is compiled for (6 or 8: register budget)
     int scanMinSize = 8;             // subtrees of at least this many nodes are scanned by the whole warp (0 = never)
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
-    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans scored with the queued-site appendProbNode
+    int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans with the queued-site appendProbNode and the node-by-node replay
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
     size_t devStageBytes = 0;
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
         STAT_T(4);
         // ---------------- subtree scans: the whole warp works for one lane's search at a time
         for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1)
-            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags & 1, st);
+            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags, st);
         STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
     }
@@ -467,6 +468,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     maple_ctx* ctx = new maple_ctx();
     ctx->device = device;
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
+    if (const char* e = getenv("MAPLE_SCAN_REPLAY")) ctx->scanReplaySequential = strcmp(e, "sequential") == 0;
     if (const char* e = getenv("MAPLE_SCAN_APPEND")) ctx->scanAppendSitewise = strcmp(e, "q4") != 0;
     cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
     memset(&ctx->model, 0, sizeof(DevModel));
@@ -833,16 +835,17 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     // shared memory: a fixed part per warp plus as much list pool as the targeted CTAs per SM leave (227 KB per SM, 1 KB reserved per CTA)
-    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : ctx->fsmMinBlocks == 10 ? 10 : 8;
+    const int ctasWanted = ctx->fsmMinBlocks == 8 ? 8 : 6;
     const int fixedPerWarp = int(sizeof(ScanSmem) - sizeof(uint4));
     int poolBytes = ((227 * 1024 / ctasWanted - 2048) / (kSearchThreads / 32) - fixedPerWarp) & ~15;
     if (poolBytes > 12288) poolBytes = 12288;
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*);
-    FsmKernel fsmKernel = k_spr_search_fsm<8>;  // 128 registers, 16 warps per SM: measured best of the three on the deep round
-    if (ctx->fsmMinBlocks == 6) fsmKernel = k_spr_search_fsm<6>;
-    else if (ctx->fsmMinBlocks == 10) fsmKernel = k_spr_search_fsm<10>;
+    // 168 registers, 12 warps per SM: measured best (deep round at 100 k sequences: 3.0 s; the 128-register build spills in the
+    // window replay and takes 4.2 s; MAPLE_FSM_MINB=8 selects it for A/B runs)
+    FsmKernel fsmKernel = k_spr_search_fsm<6>;
+    if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8>;
     if (ctx->searchVariant != 1) {
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -883,7 +886,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                                                                              scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
-                                                                             (ctx->scanAppendSitewise && ctx->searchVariant != 3) ? 0 : 1, poolBytes,
+                                                                             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
                                                                              ctx->statsOn ? ctx->searchStats : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());

@@ -451,7 +451,8 @@ struct ScanSmem {
     double winScore[kWinMax];  // candidate scores of the nodes that need one
     double cPay[kCPay];
     PathE path[kPathSm];
-    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax];
+    int winInfo[kWinMax], winSize[kWinMax], winNode[kWinMax], winParent[kWinMax];
+    int wp[kWinMax], wv[kWinMax], wd[kWinMax];  // pointer-jumping work arrays of the parallel replay
     uint32_t cKey[kCKeys];
     uint4 pool[1];  // mid-branch lists of one batch: poolBytes of them, the rest of the warp's share of the dynamic shared memory
 };
@@ -476,7 +477,8 @@ __device__ __noinline__ double f_append_q4(const DevModel& m, const uint32_t* kP
 }
 
 __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, StackE* stack,
-                              int stackCap, ScanSmem& W, int poolBytes, bool queuedAppend, unsigned long long* st) {
+                              int stackCap, ScanSmem& W, int poolBytes, int scanFlags /* 1: queued-site append, 2: node-by-node replay */,
+                              unsigned long long* st) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int R = __shfl_sync(FULL, f.t1, src);
@@ -550,6 +552,7 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                 W.winInfo[w] = info;
                 W.winSize[w] = rec.size;
                 W.winNode[w] = rec.node;
+                W.winParent[w] = rec.parentPos - pos;
             }
             const unsigned need = __ballot_sync(FULL, (info & 7) == 7);
             const int room = 32 - nScore;
@@ -603,7 +606,7 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
                 tk = now;
             }
             if (myW >= 0)
-                W.winScore[myW] = queuedAppend ? f_append_q4(m, kP, pP, remK, remP, isRemovedTip, removedBLen)
+                W.winScore[myW] = (scanFlags & 1) ? f_append_q4(m, kP, pP, remK, remP, isRemovedTip, removedBLen)
                                                : f_append_sitewise(m, kP, pP, remK, remP, isRemovedTip, removedBLen);
         }
         __syncwarp();
@@ -612,9 +615,225 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
             if (lane == 0) st[6] += (unsigned long long)(now - tk);
             tk = now;
         }
-        // ---- replay: the reference's sequential bookkeeping over the window, every lane the same
+        // ---- replay of the reference's bookkeeping over the window (running best, failure counters, stop rule, jumps).
+        // Parallel form.  What a node hands to its children -- midProb (its own score, or the inherited one when it is not
+        // scored) and failedPasses (reset on a new best, +1 on a consecutive worsening, else inherited) -- are chains over
+        // ancestors, and "reached" is the AND of the ancestors' stop-rule outcomes: three pointer-jumping passes over the
+        // parent links of the window, log2(depth span) rounds each.  The running best before a node is taken as the prefix
+        // maximum of the window's scores, which is right unless a node that the stop rule prunes holds a new best; that is
+        // checked, and such a window (rare) is replayed node by node below instead.
         int j = 0;
-        {
+        bool replayed = false;
+        if (!(scanFlags & 2)) {
+            constexpr int NC = kWinMax / 32;
+            constexpr int FL_NB = 1, FL_DESC = 2, FL_OK = 4;
+            int infc[NC], parc[NC], ptr[NC], fval[NC], flg[NC];
+            double bb[NC];  // running best before node c*32+lane
+            auto scoreOf = [&](int c, int w) { return (infc[c] & 7) == 7 ? W.winScore[w] : -INFINITY; };  // scored nodes keep their score throughout
+            {
+                double carry = best;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const int w = c * 32 + lane;
+                    infc[c] = w < nWin ? W.winInfo[w] : 0;
+                    parc[c] = w < nWin ? W.winParent[w] : -1;
+                    double v = scoreOf(c, w);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double x = __shfl_up_sync(FULL, v, o);
+                        if (lane >= o) v = fmax(v, x);
+                    }
+                    double ex = __shfl_up_sync(FULL, v, 1);
+                    if (lane == 0) ex = -INFINITY;
+                    bb[c] = fmax(carry, ex);
+                    carry = fmax(carry, __shfl_sync(FULL, v, 31));
+                }
+            }
+            auto incoming = [&](int c) {  // what a node whose parent lies before the window inherits
+                const int rel = infc[c] >> 8;
+                return rel < kPathSm ? W.path[rel] : gpath[rel];
+            };
+            // pass 1: midProb handed down = score of the nearest scored ancestor-or-self, else what came in from above the window
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                ptr[c] = -1;
+                if (w < nWin) {
+                    if ((infc[c] & 7) != 7) {
+                        if (parc[c] < 0) W.winScore[w] = incoming(c).lk;
+                        else ptr[c] = parc[c];
+                    }
+                    W.wp[w] = ptr[c];
+                }
+            }
+            __syncwarp();
+            for (int round = 0; round < 8; round++) {
+                if (!__any_sync(FULL, ptr[0] >= 0 || ptr[1] >= 0 || ptr[2] >= 0)) break;
+                int pp[NC];
+                double pv[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (ptr[c] >= 0) { pp[c] = W.wp[ptr[c]]; pv[c] = W.winScore[ptr[c]]; }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (ptr[c] >= 0) {
+                        const int w = c * 32 + lane;
+                        if (pp[c] < 0) { W.winScore[w] = pv[c]; ptr[c] = -1; }
+                        else ptr[c] = pp[c];
+                        W.wp[w] = ptr[c];
+                    }
+                __syncwarp();
+            }
+            // pass 2: failedPasses handed down.  Own effect: SET 0 on a new best, ADD 1 on a consecutive worsening, else ADD 0.
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                fval[c] = 0; flg[c] = 0; ptr[c] = -1;
+                if (w < nWin) {
+                    const bool scored = (infc[c] & 7) == 7;
+                    const double sc = scoreOf(c, w);
+                    double lkIn;
+                    int failedIn = 0;
+                    if (parc[c] >= 0) lkIn = W.winScore[parc[c]];
+                    else { const PathE pe = incoming(c); lkIn = pe.lk; failedIn = pe.failed; }
+                    const bool nb = scored && sc > bb[c];
+                    const int inc = (scored && !nb && sc < (lkIn - sp.thresholdLogLKconsecutivePlacement)) ? 1 : 0;
+                    if (nb) flg[c] = FL_NB;
+                    else if (parc[c] < 0) fval[c] = failedIn + inc;
+                    else { fval[c] = inc; ptr[c] = parc[c]; }
+                    W.wp[w] = ptr[c];
+                    W.wv[w] = fval[c];
+                }
+            }
+            __syncwarp();
+            for (int round = 0; round < 8; round++) {
+                if (!__any_sync(FULL, ptr[0] >= 0 || ptr[1] >= 0 || ptr[2] >= 0)) break;
+                int pp[NC], pf[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (ptr[c] >= 0) { pp[c] = W.wp[ptr[c]]; pf[c] = W.wv[ptr[c]]; }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (ptr[c] >= 0) {
+                        const int w = c * 32 + lane;
+                        fval[c] += pf[c];
+                        ptr[c] = pp[c];
+                        W.wp[w] = ptr[c];
+                        W.wv[w] = fval[c];
+                    }
+                __syncwarp();
+            }
+            // stop rule of every node as if it were reached, then pass 3: reached = every ancestor in the window descends
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                if (w < nWin) {
+                    const int inf = infc[c];
+                    const double mid = W.winScore[w];
+                    const double bestAfter = fmax(bb[c], scoreOf(c, w));
+                    const bool within = mid > (bestAfter - sp.thresholdLogLKtopology);
+                    const bool rule = sp.strictTopologyStopRules ? (fval[c] <= sp.allowedFailsTopology && within)
+                                                                 : (fval[c] <= sp.allowedFailsTopology || within);
+                    const bool d = (inf & 4) && (inf & 3) != 1 && (inf & 8) && rule;
+                    if (d) flg[c] |= FL_DESC;
+                    W.wd[w] = d ? 1 : 0;
+                }
+            }
+            __syncwarp();
+            // ok[w] starts as "my parent descends" (true when the parent lies before the window: this window would not have been
+            // reached otherwise) and absorbs the parent's ok, the grandparent's, ... by pointer jumping
+            int ok[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                ok[c] = 1; ptr[c] = -1;
+                if (w < nWin) {
+                    if (parc[c] >= 0) { ok[c] = W.wd[parc[c]]; ptr[c] = parc[c]; }
+                    W.wp[w] = ptr[c];
+                }
+            }
+            __syncwarp();  // wd has been read: wv (failedPasses, final) stays, wd is reused for ok
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                if (w < nWin) W.wd[w] = ok[c];
+            }
+            __syncwarp();
+            for (int round = 0; round < 8; round++) {
+                if (!__any_sync(FULL, ptr[0] >= 0 || ptr[1] >= 0 || ptr[2] >= 0)) break;
+                int pp[NC], po[NC];
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (ptr[c] >= 0) { pp[c] = W.wp[ptr[c]]; po[c] = W.wd[ptr[c]]; }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (ptr[c] >= 0) {
+                        const int w = c * 32 + lane;
+                        ok[c] &= po[c];
+                        ptr[c] = pp[c];
+                        W.wp[w] = ptr[c];
+                        W.wd[w] = ok[c];
+                    }
+                __syncwarp();
+            }
+            // check the prefix-maximum assumption, then commit
+            bool bad = false;
+            int maxTarget = 0, nCounted = 0, anyNb = 0;
+            double newBestVal = best;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                if (w < nWin) {
+                    const bool scored = (infc[c] & 7) == 7;
+                    if (ok[c]) {
+                        flg[c] |= FL_OK;
+                        maxTarget = max(maxTarget, (flg[c] & FL_DESC) ? w + 1 : w + W.winSize[w]);
+                        if (scored) { nCounted++; newBestVal = fmax(newBestVal, W.winScore[w]); anyNb |= flg[c] & FL_NB; }
+                    } else if (scored && W.winScore[w] > bb[c]) bad = true;
+                }
+            }
+            if (!__any_sync(FULL, bad)) {
+                replayed = true;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    maxTarget = max(maxTarget, __shfl_xor_sync(FULL, maxTarget, o));
+                    nCounted += __shfl_xor_sync(FULL, nCounted, o);
+                    newBestVal = fmax(newBestVal, __shfl_xor_sync(FULL, newBestVal, o));
+                }
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    const int w = c * 32 + lane;
+                    const bool live = (flg[c] & FL_OK) != 0;
+                    const bool queued = live && (infc[c] & 7) == 7 && W.winScore[w] > bb[c] - sp.thresholdLogLKoptimizationTopology;  // :7071
+                    const unsigned qm = __ballot_sync(FULL, queued);
+                    if (queued) {
+                        const int at = qN + __popc(qm & ((1u << lane) - 1u));
+                        if (at < qCap) qTop[-1 - at] = uint32_t(W.winNode[w]);
+                    }
+                    qN += __popc(qm);
+                    // the last node of each depth that descends leaves its state for the windows that follow
+                    const bool dsc = live && (flg[c] & FL_DESC);
+                    const int rel1 = (infc[c] >> 8) + 1;
+                    const unsigned peers = __match_any_sync(FULL, dsc ? rel1 : -1 - lane);
+                    if (dsc && lane == 31 - __clz(peers)) {
+                        if (rel1 >= pathCap) err = 3;
+                        else if (rel1 < kPathSm) W.path[rel1] = PathE{W.winScore[w], fval[c], 0};
+                        else gpath[rel1] = PathE{W.winScore[w], fval[c], 0};
+                    }
+                    __syncwarp();
+                }
+                if (qN > qCap) err = 3;
+                err = __any_sync(FULL, err == 3) ? 3 : err;
+                if (__any_sync(FULL, anyNb)) newBest = 1;
+                best = newBestVal;
+                phase1 += nCounted;
+                j = maxTarget;
+            } else if (st && lane == 0) st[25] += 1;  // the node-by-node replay only reads the scores of scored nodes: untouched above
+        }
+        if (!replayed) {
             int inf = W.winInfo[0], sz = W.winSize[0];
             double sc = W.winScore[0];
             while (j < nWin) {

@@ -48,8 +48,8 @@ for variant in variants:
               "iterations %.3g; lanes/op-iteration: append %.1f merge %.1f blen %.1f differ %.1f | op counts a %.3g m %.3g b %.3g d %.3g" % (
                   100 * S[0] / wc, 100 * S[1] / wc, 100 * S[2] / wc, 100 * S[3] / wc, 100 * S[4] / wc, 100 * S[5] / wc, 100 * S[23] / wc, 100 * S[6] / wc, 100 * S[7] / wc,
                   S[16], S[8] / max(S[12], 1), S[9] / max(S[13], 1), S[10] / max(S[14], 1), S[11] / max(S[15], 1), S[8], S[9], S[10], S[11]), flush=True)
-        print("   scan jobs %d, nodes in their ranges %.3g, batches %.3g, lanes scored %.3g (%.1f / batch, window %.1f nodes), counted %.3g, phase-2 entries queued %d" % (
-            S[17], S[18], S[19], S[20], S[20] / max(S[19], 1), S[24] / max(S[19], 1), S[21], S[22]), flush=True)
+        print("   scan jobs %d, nodes in their ranges %.3g, batches %.3g, lanes scored %.3g (%.1f / batch, window %.1f nodes), counted %.3g, phase-2 entries queued %d, windows replayed node by node %d" % (
+            S[17], S[18], S[19], S[20], S[20] / max(S[19], 1), S[24] / max(S[19], 1), S[21], S[22], S[25]), flush=True)
     st = np.bincount(rec["status"], minlength=4)
     ph = rec["phase1"].sum()
     print("%s: %.1f ms, searches %d, status %s, phase1 %d (%.1f/search, max %d), %.3g cand/s, proposals %d" % (
