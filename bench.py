@@ -187,7 +187,7 @@ def main():
     d_nodes = torch.as_tensor(mine, dtype=torch.int32, device=dev)
 
     def step(src_nodes):
-        out = tree.spr_search(src_nodes, p, scratch_keys=16384)
+        out = tree.spr_search(src_nodes, p)
         if world > 1:  # one collective per round: everybody gets every proposal
             all_gather_raw(out, len(nodes), world)
         return out
@@ -211,7 +211,7 @@ def main():
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations
         ev[k][0].record()
-        out = tree.spr_search(d_nodes, p, scratch_keys=16384)
+        out = tree.spr_search(d_nodes, p)
         ev[k][1].record()
         if world > 1:
             all_gather_raw(out, len(nodes), world)

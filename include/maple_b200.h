@@ -173,7 +173,9 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
 
 /* Search the n listed nodes (DEVICE int32) on the frozen tree; out = n records (DEVICE).  scratch_keys_per_search:
  * entries of per-search list scratch (0 = default 8192); max_concurrent_searches caps the resident threads (0 = fill
- * the GPU).  Deterministic: a node's record does not depend on which other nodes are in the batch. */
+ * the GPU).  A search that exhausts its scratch is re-run on the device by a second small launch with 8x the entries; only if
+ * that is not enough either does its record come back with status 3.  Deterministic: a node's record does not depend on which
+ * other nodes are in the batch. */
 int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t n, const int32_t* nodes,
                            maple_search_result* out, int32_t scratch_keys_per_search, int32_t max_concurrent_searches,
                            int64_t* out_cycles /* optional DEVICE int64[n]: SM clock cycles each search took; NULL to skip */,

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmaple_b200.so")
+LIB_PATH = os.environ.get("MAPLE_B200_LIB") or os.path.join(HERE, "libmaple_b200.so")
 
 MAPLE_F_USING_ERROR_RATE, MAPLE_F_ERROR_SITE_SPECIFIC, MAPLE_F_RATE_VARIATION = 1, 2, 4
 MAPLE_MERGE_UPDOWN, MAPLE_MERGE_RETURN_LK = 1, 2

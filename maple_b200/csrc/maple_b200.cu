@@ -37,6 +37,7 @@ struct maple_ctx {
     int treeHeight = 0;
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
+    int lanesPerWarp = 32;              // searches per warp (1..32)
     bool scanReplaySequential = false;  // A/B: node-by-node window replay instead of the pointer-jumping one
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
     int fsmMinBlocks = 6;            // resident CTAs per SM the state-machine kernel is compiled for (6 or 8: register budget)
@@ -45,6 +46,9 @@ struct maple_ctx {
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
+    void* retryScratch = nullptr;  // node list + scratch of the on-device retry of overflowed searches
+    size_t retryScratchBytes = 0;
+    unsigned long long* retryCounters = nullptr;  // [0] overflowed searches, [1] work counter of the retry launch
     int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans with the queued-site appendProbNode and the node-by-node replay
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
@@ -230,6 +234,16 @@ __global__ void __launch_bounds__(256) k_lists_copy(int64_t n, const uint32_t* _
 
 constexpr int kSearchThreads = 64;
 
+// searches whose per-lane scratch ran out (status 3) are collected for a second launch with a few lanes and 8x the scratch
+__global__ void __launch_bounds__(256) k_collect_overflow(int64_t n, const SearchResult* __restrict__ out, const int32_t* __restrict__ nodes,
+                                                          int32_t* __restrict__ retryNodes, int32_t* __restrict__ retryIdx,
+                                                          unsigned long long* retryCount, int cap) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n || out[i].status != 3) return;
+    const unsigned long long at = atomicAdd(retryCount, 1ULL);
+    if (at < (unsigned long long)cap) { retryNodes[at] = nodes[i]; retryIdx[at] = (int32_t)i; }
+}
+
 // one thread per pre-order position: the ScanNode records of the bound tree and arena for this launch's effectivelyNon0BLen
 __global__ void __launch_bounds__(256) k_scan_prepare(const __grid_constant__ DevTree T, double eff, ScanNode* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,7 +321,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
                                                                    uint32_t* scrKey, double* scrPay, double* scrAis, StackE* scrStack,
                                                                    unsigned capK, unsigned capP, unsigned capA, int stackCap,
                                                                    unsigned long long* counter, long long* outCycles, int scanMinSize,
-                                                                   int scanFlags, int poolBytes, unsigned long long* stats) {
+                                                                   int scanFlags, int poolBytes, unsigned long long* stats,
+                                                                   const unsigned long long* nDev, const int32_t* outIndex, int lanesPerWarp) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -320,11 +335,14 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     extern __shared__ uint4 dynSmem[];
     const int warpSmem = int(sizeof(ScanSmem) - sizeof(uint4)) + poolBytes;
     ScanSmem& W = *reinterpret_cast<ScanSmem*>(reinterpret_cast<char*>(dynSmem) + (threadIdx.x >> 5) * warpSmem);
+    if (nDev) n = (int64_t)min((unsigned long long)n, *nDev);  // retry launch: the list length lives on the device
     long long tk = clock64();
 #define STAT_T(i) do { if (st) { const long long now_ = clock64(); if (l0) st[i] += (unsigned long long)(now_ - tk); tk = now_; } } while (0)
 #define STAT_N(i, v) do { if (st && l0) st[i] += (unsigned long long)(v); } while (0)
     stage_model(sm, gm);
-    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    // scratch is laid out for the lanes that own searches only
+    const int lane_ = int(threadIdx.x & 31);
+    const size_t tid = ((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * (size_t)lanesPerWarp + (lane_ < lanesPerWarp ? lane_ : 0);
     ScratchD s;
     s.key = scrKey + tid * capK;
     s.pay = scrPay + tid * capP;
@@ -334,7 +352,9 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     Fsm f;
     f.op = OP_NONE;
     f.pc = 0;
-    int stage = 0;  // 0 idle, 1 current-placement append pending, 2 search running, 3 no more work
+    // lanes beyond lanesPerWarp own no search: they only lend a hand in the whole-warp subtree scans (fewer searches per warp =
+    // a long search shares its warp's time with fewer others)
+    int stage = (int(threadIdx.x & 31) < lanesPerWarp) ? 0 : 3;  // 0 idle, 1 current-placement append pending, 2 search running, 3 no more work
     unsigned long long i = 0;
     int node = -1;
     double bestCurrentLK = 0.0;
@@ -368,7 +388,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
             if (stage != 0) {  // a search (or its pre-check) just ended
                 if (stage == 2) fsm_finish(f, T, sp, node, bestCurrentLK, r);
                 else r.status = f.rc;
-                out[i] = r;
+                out[outIndex ? outIndex[i] : i] = r;
                 if (outCycles) outCycles[i] = clock64() - c0;
                 stage = 0;
             }
@@ -379,14 +399,14 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
             r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
             r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
             f.op = OP_NONE;
-            if (T.up[node] < 0) { out[i] = r; continue; }
+            if (T.up[node] < 0) { out[outIndex ? outIndex[i] : i] = r; continue; }
             s.topK = s.topP = 0;
             s.err = 0;
             const int parent = T.up[node];
             LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
             if (n_mut(T, node)) vectUp = s_pass(sm, T, s, vectUp, node, false);
             const LRef own = tree_list(T, 0, node);
-            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[i] = r; continue; }
+            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[outIndex ? outIndex[i] : i] = r; continue; }
             f.a1 = vectUp; f.a2 = own; f.at1 = T.isTip[node] != 0; f.ab1 = T.dist[node];
             f.op = OP_APPEND;
             stage = 1;
@@ -468,6 +488,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     maple_ctx* ctx = new maple_ctx();
     ctx->device = device;
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
+    if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 1 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 32; }
     if (const char* e = getenv("MAPLE_SCAN_REPLAY")) ctx->scanReplaySequential = strcmp(e, "sequential") == 0;
     if (const char* e = getenv("MAPLE_SCAN_APPEND")) ctx->scanAppendSitewise = strcmp(e, "q4") != 0;
     cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
@@ -497,6 +518,8 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->devStage);
     cudaFree(ctx->searchScratch);
     cudaFree(ctx->searchCounter);
+    cudaFree(ctx->retryScratch);
+    cudaFree(ctx->retryCounters);
     cudaFree(ctx->treeDerived);
     cudaFree(ctx->searchStats);
     delete ctx;
@@ -841,7 +864,8 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     if (poolBytes > 12288) poolBytes = 12288;
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
-                               StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*);
+                               StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
+                               const unsigned long long*, const int32_t*, int);
     // 168 registers, 12 warps per SM: measured best (deep round at 100 k sequences: 3.0 s; the 128-register build spills in the
     // window replay and takes 4.2 s; MAPLE_FSM_MINB=8 selects it for A/B runs)
     FsmKernel fsmKernel = k_spr_search_fsm<6>;
@@ -854,11 +878,14 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     if (blocksPerSM < 1) blocksPerSM = 1;
     int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
     if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches;
-    if (threads > n) threads = n;
+    if (ctx->searchVariant != 1 && threads > (n + ctx->lanesPerWarp - 1) / ctx->lanesPerWarp * 32) threads = (n + ctx->lanesPerWarp - 1) / ctx->lanesPerWarp * 32;
+    else if (ctx->searchVariant == 1 && threads > n) threads = n;
     int blocks = (int)((threads + kSearchThreads - 1) / kSearchThreads);
     threads = (int64_t)blocks * kSearchThreads;
     const size_t perThread = (size_t)capK * 4 + (size_t)capP * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
-    const size_t need = perThread * (size_t)threads + 256;
+    const int lpw = ctx->searchVariant == 1 ? 32 : ctx->lanesPerWarp;
+    const size_t owners = (size_t)threads / 32 * lpw;  // lanes that own a search (and scratch)
+    const size_t need = perThread * owners + 256;
     if (need > ctx->searchScratchBytes) {
         cudaFree(ctx->searchScratch);
         ctx->searchScratch = nullptr;
@@ -870,9 +897,9 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     char* base = (char*)ctx->searchScratch;
     double* scrPay = (double*)base;
-    double* scrAis = (double*)(base + (size_t)threads * capP * 8);
-    StackE* scrStack = (StackE*)(base + (size_t)threads * (capP + capA) * 8);
-    uint32_t* scrKey = (uint32_t*)(base + (size_t)threads * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+    double* scrAis = (double*)(base + owners * capP * 8);
+    StackE* scrStack = (StackE*)(base + owners * (capP + capA) * 8);
+    uint32_t* scrKey = (uint32_t*)(base + owners * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
     if ((ctx->searchVariant == 0 || ctx->searchVariant == 3) && T.order && ctx->scanMinSize > 0) {
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, sp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
@@ -887,8 +914,41 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr);
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, ctx->lanesPerWarp);
     ctx->launches++;
+    if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
+        // second chance on the device for searches that exhausted their scratch: 128 lanes with 8x the entries
+        const int retryCap = (int)(n < 65536 ? n : 65536);
+        const int lanes2 = 2 * kSearchThreads;
+        const unsigned capK2 = capK * 8, capP2 = 2 * capK2 + 6 * 1024;
+        const size_t per2 = (size_t)capK2 * 4 + (size_t)capP2 * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
+        const size_t need2 = per2 * lanes2 + 256 + (size_t)retryCap * 8 + 64;
+        if (need2 > ctx->retryScratchBytes) {
+            cudaFree(ctx->retryScratch);
+            ctx->retryScratch = nullptr;
+            ctx->retryScratchBytes = 0;
+            CK(cudaMalloc(&ctx->retryScratch, need2));
+            ctx->retryScratchBytes = need2;
+        }
+        if (!ctx->retryCounters) CK(cudaMalloc((void**)&ctx->retryCounters, 2 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->retryCounters, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+        char* b2 = (char*)ctx->retryScratch;
+        int32_t* retryNodes = (int32_t*)b2;
+        int32_t* retryIdx = retryNodes + retryCap;
+        char* s2 = b2 + (((size_t)retryCap * 8 + 63) & ~size_t(63));
+        double* pay2 = (double*)s2;
+        double* ais2 = (double*)(s2 + (size_t)lanes2 * capP2 * 8);
+        StackE* stack2 = (StackE*)(s2 + (size_t)lanes2 * (capP2 + capA) * 8);
+        uint32_t* key2 = (uint32_t*)(s2 + (size_t)lanes2 * ((size_t)(capP2 + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+        k_collect_overflow<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, (const SearchResult*)out, nodes, retryNodes, retryIdx,
+                                                                                         ctx->retryCounters, retryCap);
+        fsmKernel<<<lanes2 / kSearchThreads, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(
+            ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, key2, pay2, ais2, stack2, capK2, capP2, capA, stackCap,
+            ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
+            ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
+            ctx->retryCounters, retryIdx, 32);
+        ctx->launches += 2;
+    }
     CK(cudaGetLastError());
     return MAPLE_OK;
 }

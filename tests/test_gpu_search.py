@@ -95,3 +95,34 @@ def test_search_vs_oracle_synthetic(rv, err, strict, ml, variant):
     ref = Oracle(d.model).search_batch(ta, host, pd, nodes, lazy_mode=1)
     _compare(rec, ref, nodes)
     assert rec["phase1"].sum() > 20 * (rec["status"] == 0).sum() > 0
+
+
+def test_scratch_overflow_is_retried_on_the_device():
+    """With a tiny per-search scratch most searches overflow in the first launch; the library re-runs them with 8x the
+    entries in a second launch.  Whatever comes back as searched (status 0) must be the oracle's result; the rest must say 3."""
+    import math
+    from maple_b200.engine import MapleEngine
+    from maple_b200.genome_list import pack_lists
+    from maple_b200.search import dirty_nodes, search_params
+    from maple_b200.synthetic import generate
+    from maple_b200.tree import DeviceTree
+    from oracle.oracle import Oracle
+    d = generate(300, lRef=6000, mean_diffs=8.0, rate_variation=True, seed=3)
+    eng = MapleEngine(d.model, 0)
+    tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+    tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+    p = search_params(d.model.lRef, False, 4, 14.0 * math.log(d.model.lRef))
+    nodes = dirty_nodes(tree)
+    tree.prepare_search()
+    small = tree.search_records(tree.spr_search(nodes, p, scratch_keys=192))
+    tiny = tree.search_records(tree.spr_search(nodes, p, scratch_keys=24))
+    host = tree.arena.to_host()
+    ta = {"up": d.up, "child0": d.child0, "child1": d.child1, "dist": tree.dist, "isTip": tree.isTip, "root": d.root}
+    pd = {f[0]: getattr(p, f[0]) for f in p._fields_ if f[0] != "reserved"}
+    ref = Oracle(d.model).search_batch(ta, host, pd, nodes, lazy_mode=1)
+    for rec in (small, tiny):
+        assert set(np.unique(rec["status"])) <= {0, 1, 3}
+        ok = rec["status"] != 3
+        assert ok.sum() > 0
+        _compare(rec[ok], ref[ok], nodes[ok])
+    assert (small["status"] == 0).sum() > (tiny["status"] == 0).sum() > 0
