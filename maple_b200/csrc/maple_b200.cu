@@ -37,7 +37,7 @@ struct maple_ctx {
     int treeHeight = 0;
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
-    int lanesPerWarp = 32;              // searches per warp (1..32)
+    int lanesPerWarp = 0;               // searches per warp (1..32); 0 = chosen per launch from the number of searches
     bool scanReplaySequential = false;  // A/B: node-by-node window replay instead of the pointer-jumping one
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
     int fsmMinBlocks = 6;            // resident CTAs per SM the state-machine kernel is compiled for (6 or 8: register budget)
@@ -488,7 +488,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     maple_ctx* ctx = new maple_ctx();
     ctx->device = device;
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
-    if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 1 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 32; }
+    if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 0 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 0; }
     if (const char* e = getenv("MAPLE_SCAN_REPLAY")) ctx->scanReplaySequential = strcmp(e, "sequential") == 0;
     if (const char* e = getenv("MAPLE_SCAN_APPEND")) ctx->scanAppendSitewise = strcmp(e, "q4") != 0;
     cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, device);
@@ -878,12 +878,23 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     if (blocksPerSM < 1) blocksPerSM = 1;
     int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
     if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches;
-    if (ctx->searchVariant != 1 && threads > (n + ctx->lanesPerWarp - 1) / ctx->lanesPerWarp * 32) threads = (n + ctx->lanesPerWarp - 1) / ctx->lanesPerWarp * 32;
-    else if (ctx->searchVariant == 1 && threads > n) threads = n;
+    // Searches per warp.  The subtree scans -- most of the work of a deep round -- are executed by whole warps, so the unit that
+    // has to be kept busy is the warp, not the lane: every resident warp should own searches, and each owning lane should get
+    // a few searches in turn (dynamic balance) rather than one.  With few searches (a shard of a multi-GPU round) this spreads
+    // them over all warps instead of packing 32 into each of a few.
+    int lpw = 32;
+    if (ctx->searchVariant != 1) {
+        lpw = ctx->lanesPerWarp;
+        if (lpw <= 0) {
+            const int64_t warps = threads / 32;
+            lpw = (int)((n + warps * 3 - 1) / (warps * 3));
+            lpw = lpw < 2 ? 2 : lpw > 32 ? 32 : lpw;
+        }
+        if (threads > (n + lpw - 1) / lpw * 32) threads = (n + lpw - 1) / lpw * 32;
+    } else if (threads > n) threads = n;
     int blocks = (int)((threads + kSearchThreads - 1) / kSearchThreads);
     threads = (int64_t)blocks * kSearchThreads;
     const size_t perThread = (size_t)capK * 4 + (size_t)capP * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
-    const int lpw = ctx->searchVariant == 1 ? 32 : ctx->lanesPerWarp;
     const size_t owners = (size_t)threads / 32 * lpw;  // lanes that own a search (and scratch)
     const size_t need = perThread * owners + 256;
     if (need > ctx->searchScratchBytes) {
@@ -914,7 +925,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, ctx->lanesPerWarp);
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw);
     ctx->launches++;
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
         // second chance on the device for searches that exhausted their scratch: 128 lanes with 8x the entries
