@@ -40,7 +40,7 @@ struct maple_ctx {
     int lanesPerWarp = 0;               // searches per warp (1..32); 0 = chosen per launch from the number of searches
     bool scanReplaySequential = false;  // A/B: node-by-node window replay instead of the pointer-jumping one
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
-    int fsmMinBlocks = 6;            // resident CTAs per SM the state-machine kernel is compiled for (6 or 8: register budget)
+    int fsmMinBlocks = 7;            // __launch_bounds__ minimum CTAs per SM of the state-machine kernel (7 -> 128 registers, 6 -> 168)
     int scanMinSize = 8;             // subtrees of at least this many nodes are scanned by the whole warp (0 = never)
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
@@ -858,7 +858,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     // shared memory: a fixed part per warp plus as much list pool as the targeted CTAs per SM leave (227 KB per SM, 1 KB reserved per CTA)
-    const int ctasWanted = ctx->fsmMinBlocks == 8 ? 8 : 6;
+    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : 8;
     const int fixedPerWarp = int(sizeof(ScanSmem) - sizeof(uint4));
     int poolBytes = ((227 * 1024 / ctasWanted - 2048) / (kSearchThreads / 32) - fixedPerWarp) & ~15;
     if (poolBytes > 12288) poolBytes = 12288;
@@ -866,10 +866,14 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
                                const unsigned long long*, const int32_t*, int);
-    // 168 registers, 12 warps per SM: measured best (deep round at 100 k sequences: 3.0 s; the 128-register build spills in the
-    // window replay and takes 4.2 s; MAPLE_FSM_MINB=8 selects it for A/B runs)
+    // Register budget = resident warps.  __launch_bounds__(64, 7) makes ptxas settle on 128 registers with few spills, which lets
+    // 8 CTAs (16 warps) share an SM: 3.1 s for the deep round at 100 k sequences against 4.4 s for the 168-register build
+    // (12 warps) on the same box.  MAPLE_FSM_MINB=6 selects the latter for A/B runs.  (Register allocation of this kernel is
+    // touchy: check `-Xptxas -v` after changing it -- a 128-register build with ~2 kB of spills is as slow as 168 registers.)
+    // Keep the three instantiations: with only <6> and <7> present the same <7> comes out with 2 kB of spills.
     FsmKernel fsmKernel = k_spr_search_fsm<6>;
     if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8>;
+    if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7>;
     if (ctx->searchVariant != 1) {
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -1,0 +1,22 @@
+"""The default search kernel must come out of ptxas as measured: 128 registers (8 CTAs = 16 warps per SM) and well under
+1 kB of spill stores.  The same source with a different set of instantiations has produced 2 kB of spills and a 40 % slower
+kernel, silently -- this test makes that loud.  No GPU needed (reads the ptxas report of the in-tree build)."""
+import os
+
+import pytest
+
+from maple_b200.build import LIB, PTXAS_LOG, build_extension, kernel_resources
+
+
+def test_default_search_kernel_register_allocation():
+    build_extension()
+    if not os.path.isfile(PTXAS_LOG) or os.path.getmtime(PTXAS_LOG) + 5 < os.path.getmtime(LIB):
+        pytest.skip("no ptxas report for the current library (built elsewhere)")
+    res = kernel_resources()
+    default = [v for k, v in res.items() if "k_spr_search_fsmILi7E" in k]
+    assert len(default) == 1, sorted(res)
+    r = default[0]
+    assert r["registers"] == 128, r
+    assert r["spill_stores"] <= 1200 and r["spill_loads"] <= 1200, r
+    wide = [v for k, v in res.items() if "k_spr_search_fsmILi6E" in k]
+    assert wide and wide[0]["registers"] > 128
