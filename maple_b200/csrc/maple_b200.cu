@@ -858,7 +858,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     // shared memory: a fixed part per warp plus as much list pool as the targeted CTAs per SM leave (227 KB per SM, 1 KB reserved per CTA)
-    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : 8;
+    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : ctx->fsmMinBlocks >= 9 ? ctx->fsmMinBlocks : 8;
     const int fixedPerWarp = int(sizeof(ScanSmem) - sizeof(uint4));
     int poolBytes = ((227 * 1024 / ctasWanted - 2048) / (kSearchThreads / 32) - fixedPerWarp) & ~15;
     if (poolBytes > 12288) poolBytes = 12288;
@@ -874,6 +874,8 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     FsmKernel fsmKernel = k_spr_search_fsm<6>;
     if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8>;
     if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7>;
+    if (ctx->fsmMinBlocks == 9) fsmKernel = k_spr_search_fsm<9>;    // 96 registers; shared memory sized for 9 CTAs per SM
+    if (ctx->fsmMinBlocks == 10) fsmKernel = k_spr_search_fsm<10>;  // 96 registers; shared memory sized for 10
     if (ctx->searchVariant != 1) {
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

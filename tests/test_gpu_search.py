@@ -126,3 +126,41 @@ def test_scratch_overflow_is_retried_on_the_device():
         assert ok.sum() > 0
         _compare(rec[ok], ref[ok], nodes[ok])
     assert (small["status"] == 0).sum() > (tiny["status"] == 0).sum() > 0
+
+
+def test_records_do_not_depend_on_the_batch():
+    """Size-independent property of the seam: a node's record is a function of (frozen tree, model, parameters) only --
+    not of which other nodes are searched with it, their order, the scratch size or the kernel variant.  2 000 sequences,
+    deep rules, every node; then shuffled halves, a small scratch (on-device retries) and the straight-line kernel."""
+    import math
+    from maple_b200.engine import MapleEngine
+    from maple_b200.genome_list import pack_lists
+    from maple_b200.search import dirty_nodes, search_params
+    from maple_b200.synthetic import generate
+    from maple_b200.tree import DeviceTree
+    d = generate(2000, rate_variation=True, seed=21, ml_like_blens=True)
+    eng = MapleEngine(d.model, 0)
+    tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+    tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+    p = search_params(d.model.lRef, False, 4, 14.0 * math.log(d.model.lRef))
+    nodes = dirty_nodes(tree)
+    tree.prepare_search()
+    full = tree.search_records(tree.spr_search(nodes, p))
+    assert (full["status"] == 3).sum() == 0 and (full["status"] == 0).sum() > 500
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(nodes))
+    for part in (perm[: len(perm) // 2], perm[len(perm) // 2:]):
+        rec = tree.search_records(tree.spr_search(nodes[part], p))
+        assert rec.tobytes() == full[part].tobytes()
+    small = tree.search_records(tree.spr_search(nodes, p, scratch_keys=1024))
+    ok = small["status"] != 3
+    assert ok.sum() > 0.9 * len(nodes) and small[ok].tobytes() == full[ok].tobytes()
+    eng.set_search_variant(1)
+    sub = perm[:300]
+    rec = tree.search_records(tree.spr_search(nodes[sub], p))
+    eng.set_search_variant(0)
+    assert rec.tobytes() == full[sub].tobytes()
+    # the proposals of a round can be applied in the reference's order: ascending improvement (:12312)
+    from maple_b200.sharding import moves_from_records
+    moves = moves_from_records(nodes, full)
+    assert moves == sorted(moves, key=lambda m: m[2]) and all(m[2] > 0 for m in moves)
