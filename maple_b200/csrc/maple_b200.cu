@@ -858,7 +858,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     // shared memory: a fixed part per warp plus as much list pool as the targeted CTAs per SM leave (227 KB per SM, 1 KB reserved per CTA)
-    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : ctx->fsmMinBlocks >= 9 ? ctx->fsmMinBlocks : 8;
+    const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : 8;
     const int fixedPerWarp = int(sizeof(ScanSmem) - sizeof(uint4));
     int poolBytes = ((227 * 1024 / ctasWanted - 2048) / (kSearchThreads / 32) - fixedPerWarp) & ~15;
     if (poolBytes > 12288) poolBytes = 12288;
@@ -870,12 +870,11 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     // 8 CTAs (16 warps) share an SM: 3.1 s for the deep round at 100 k sequences against 4.4 s for the 168-register build
     // (12 warps) on the same box.  MAPLE_FSM_MINB=6 selects the latter for A/B runs.  (Register allocation of this kernel is
     // touchy: check `-Xptxas -v` after changing it -- a 128-register build with ~2 kB of spills is as slow as 168 registers.)
-    // Keep the three instantiations: with only <6> and <7> present the same <7> comes out with 2 kB of spills.
+    // Keep the three instantiations: with only <6> and <7> present the same <7> comes out with 2 kB of spills.  96-register builds
+    // (<9>, <10>: 10 CTAs per SM, half the list pool) were measured too: 5.5 s against 3.1-3.4 s.
     FsmKernel fsmKernel = k_spr_search_fsm<6>;
     if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8>;
     if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7>;
-    if (ctx->fsmMinBlocks == 9) fsmKernel = k_spr_search_fsm<9>;    // 96 registers; shared memory sized for 9 CTAs per SM
-    if (ctx->fsmMinBlocks == 10) fsmKernel = k_spr_search_fsm<10>;  // 96 registers; shared memory sized for 10
     if (ctx->searchVariant != 1) {
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
