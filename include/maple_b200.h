@@ -181,6 +181,35 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                            int64_t* out_cycles /* optional DEVICE int64[n]: SM clock cycles each search took; NULL to skip */,
                            void* stream);
 
+/* ---- placement of new samples on a frozen tree ------------------------------------------------------------------------
+ * findBestParentForNewSample(tree, root, diffs, sample, computePlacementSupportOnly=False) (:7912-8292) for n samples; the
+ * reference's own batch form of this is process_chunk under joblib (:11190-11287).  Globals the function reads: */
+typedef struct {
+    int32_t strictStopRules;            /* --strictInitialStopRules (:7097-analogue at :8089) */
+    int32_t allowedFails;               /* --allowedFails (:54) */
+    int32_t deeperSearchForLongBranches;
+    int32_t onlyFindIdentical;          /* any error-rate option, --supportFor0Branches or --HnZ: only identical samples are absorbed (:7936) */
+    double thresholdLogLK;              /* after the multiplication by log(lRef) (:3609) */
+    double thresholdLogLKoptimization;  /* idem (:3611) */
+    double thresholdLogLKconsecutivePlacement;
+    double effectivelyNon0BLen, BLenThresholdDeeperSearch, oneMutBLen;
+} maple_place_params;
+
+typedef struct {
+    int32_t bestNode;      /* placement branch (the branch above this node), or the leaf that absorbs the sample */
+    int32_t status;        /* 0 placed; 1 absorbed as a minor sequence of leaf bestNode (the reference returns (node, 1.0, None, diffs),
+                              :7949/:8002); 2 aborted where the reference would raise; 3 per-sample scratch exhausted */
+    int32_t phase1;        /* candidate branches scored in the walk (:8033 / :8050) */
+    int32_t missedMinors;  /* leaves strictly less informative than the sample (:7960, :8004) */
+    double bestScore, bLenTop, bLenBottom, bLenAppend; /* bestBranchLengths; python False is 0.0 */
+} maple_place_result;
+
+/* sampleLists: DEVICE int32[n], ids of the samples' tip genome lists (probVectTerminalNode output, :3882) in the bound arena
+ * (ids >= 4*nNodes); the tree must be bound (maple_tree_bind).  out: DEVICE records.  The tree is not modified: a sample that
+ * the reference would append to minorSequences is reported with status 1. */
+int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, const int32_t* sampleLists, maple_place_result* out,
+                      int32_t scratch_keys_per_sample, void* stream);
+
 /* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state
  * machine, with subtrees whose lists are all stored ones scanned by the whole warp; 1 = the straight-line
  * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans with the queued-site form of appendProbNode and the node-by-node window replay

@@ -33,6 +33,7 @@ SIGNATURES = {
     "maple_lists_copy": (C.c_int, [_P, _I64] + [_P] * 10 + [_P]),
     "maple_tree_bind": (C.c_int, [_P, _I32, _I32] + [_P] * 9),
     "maple_spr_search_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P]),
+    "maple_place_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _P]),
     "maple_ctx_set_search_variant": (C.c_int, [_P, _I32]),
     "maple_ctx_set_scan_min_size": (C.c_int, [_P, _I32]),
     "maple_search_stats": (C.c_int, [_P, _I32, _P]),
@@ -46,6 +47,16 @@ class SearchParams(C.Structure):
                 ("thresholdLogLKoptimizationTopology", _D), ("thresholdLogLKconsecutivePlacement", _D),
                 ("effectivelyNon0BLen", _D), ("BLenThresholdDeeperSearch", _D), ("defaultBLen", _D)]
 
+
+class PlaceParams(C.Structure):
+    """maple_place_params (include/maple_b200.h)."""
+    _fields_ = [("strictStopRules", _I32), ("allowedFails", _I32), ("deeperSearchForLongBranches", _I32), ("onlyFindIdentical", _I32),
+                ("thresholdLogLK", _D), ("thresholdLogLKoptimization", _D), ("thresholdLogLKconsecutivePlacement", _D),
+                ("effectivelyNon0BLen", _D), ("BLenThresholdDeeperSearch", _D), ("oneMutBLen", _D)]
+
+
+PLACE_RESULT_FIELDS = [("bestNode", "i4"), ("status", "i4"), ("phase1", "i4"), ("missedMinors", "i4"), ("bestScore", "f8"),
+                       ("bLenTop", "f8"), ("bLenBottom", "f8"), ("bLenAppend", "f8")]
 
 # maple_search_result as a numpy record
 SEARCH_RESULT_FIELDS = [("placement", "i4"), ("bestNode", "i4"), ("status", "i4"), ("phase1", "i4"), ("improvement", "f8"),

@@ -15,6 +15,7 @@
 #include "likelihood.cuh"
 #include "search.cuh"
 #include "search_fsm.cuh"
+#include "place.cuh"
 
 using namespace maple;
 
@@ -46,6 +47,8 @@ struct maple_ctx {
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
     unsigned long long* searchCounter = nullptr;
+    void* placeScratch = nullptr;  // per-thread scratch of the sample-placement kernel
+    size_t placeScratchBytes = 0;
     void* retryScratch = nullptr;  // node list + scratch of the on-device retry of overflowed searches
     size_t retryScratchBytes = 0;
     unsigned long long* retryCounters = nullptr;  // [0] overflowed searches, [1] work counter of the retry launch
@@ -456,6 +459,34 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
 #undef STAT_N
 }
 
+// one new-sample placement per thread (place.cuh); threads pull samples from a global counter
+__global__ void __launch_bounds__(kSearchThreads) k_place_samples(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+                                                                  const __grid_constant__ PlaceParams pp, int64_t n,
+                                                                  const int32_t* __restrict__ sampleLists, PlaceResult* __restrict__ out,
+                                                                  char* scratch, size_t laneBytes, unsigned capK, unsigned capP, unsigned capA,
+                                                                  int stackCap, int bestCap, unsigned long long* counter) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    char* base = scratch + (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * laneBytes;
+    ScratchD s;
+    s.pay = reinterpret_cast<double*>(base);
+    s.ais = s.pay + capP;
+    PlaceBest* best = reinterpret_cast<PlaceBest*>(s.ais + capA);
+    PlaceStackE* stack = reinterpret_cast<PlaceStackE*>(best + bestCap);
+    s.key = reinterpret_cast<uint32_t*>(stack + stackCap);
+    s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
+    for (;;) {
+        const unsigned long long i = atomicAdd(counter, 1ULL);
+        if (i >= (unsigned long long)n) break;
+        const int64_t id = sampleLists[i];
+        PlaceResult r;
+        const int64_t ks = T.keyStart[id];
+        if (ks < 0) { r.bestNode = -1; r.status = 2; r.phase1 = r.missedMinors = 0; r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0; }
+        else place_sample(sm, T, pp, LRef{T.key + ks, T.pay + T.payStart[id], T.nkeys[id]}, s, stack, stackCap, best, bestCap, r);
+        out[i] = r;
+    }
+}
+
 // grid: whole waves of CTAs (multiples of the SM count), capped by the work
 static int grid_for(const maple_ctx* ctx, int64_t n, int ctasPerSM) {
     int64_t need = (n + kThreads - 1) / kThreads;
@@ -519,6 +550,7 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->searchScratch);
     cudaFree(ctx->searchCounter);
     cudaFree(ctx->retryScratch);
+    cudaFree(ctx->placeScratch);
     cudaFree(ctx->retryCounters);
     cudaFree(ctx->treeDerived);
     cudaFree(ctx->searchStats);
@@ -941,6 +973,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         const size_t need2 = per2 * lanes2 + 256 + (size_t)retryCap * 8 + 64;
         if (need2 > ctx->retryScratchBytes) {
             cudaFree(ctx->retryScratch);
+    cudaFree(ctx->placeScratch);
             ctx->retryScratch = nullptr;
             ctx->retryScratchBytes = 0;
             CK(cudaMalloc(&ctx->retryScratch, need2));
@@ -965,6 +998,49 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
             ctx->retryCounters, retryIdx, 32);
         ctx->launches += 2;
     }
+    CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, const int32_t* sampleLists, maple_place_result* out,
+                      int32_t scratch_keys_per_sample, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!ctx->haveTree) { ctx->err = "maple_place_batch: no tree bound (maple_tree_bind)"; return MAPLE_E_STATE; }
+    if (n == 0) return MAPLE_OK;
+    if (n < 0 || !p || !sampleLists || !out) return MAPLE_E_ARG;
+    static_assert(sizeof(maple_place_result) == sizeof(PlaceResult), "placement record layout");
+    static_assert(sizeof(maple_place_params) == sizeof(PlaceParams), "placement params layout");
+    CK(cudaSetDevice(ctx->device));
+    PlaceParams pp;
+    memcpy(&pp, p, sizeof pp);
+    DevTree T = ctx->tree;
+    T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
+    const unsigned capK = (unsigned)((scratch_keys_per_sample > 0 ? scratch_keys_per_sample : 4096) + 3) & ~3u;
+    const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
+    const int stackCap = ctx->treeHeight + 8, bestCap = 1024;
+    const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
+                              (size_t)capK * 4 + 15) & ~size_t(15);
+    int blocksPerSM = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_place_samples, kSearchThreads, 0));
+    if (blocksPerSM < 1) blocksPerSM = 1;
+    int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
+    if (threads > n) threads = n;
+    const int blocks = (int)((threads + kSearchThreads - 1) / kSearchThreads);
+    const size_t need = laneBytes * (size_t)blocks * kSearchThreads + 256;
+    if (need > ctx->placeScratchBytes) {
+        cudaFree(ctx->placeScratch);
+        ctx->placeScratch = nullptr;
+        ctx->placeScratchBytes = 0;
+        CK(cudaMalloc(&ctx->placeScratch, need));
+        ctx->placeScratchBytes = need;
+    }
+    if (!ctx->searchCounter) CK(cudaMalloc((void**)&ctx->searchCounter, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    k_place_samples<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
+                                                                        (char*)ctx->placeScratch, laneBytes, capK, capP, capA, stackCap, bestCap,
+                                                                        ctx->searchCounter);
+    ctx->launches++;
     CK(cudaGetLastError());
     return MAPLE_OK;
 }

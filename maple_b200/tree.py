@@ -358,6 +358,21 @@ class DeviceTree:
         capi.check(eng.ctx, rc, "maple_spr_search_batch")
         return out
 
+    # ------------------------------------------------------------------ findBestParentForNewSample for a batch (:7912, :11190-11287)
+    def place_samples(self, samples: PackedLists, params: "capi.PlaceParams", scratch_keys: int = 0) -> np.ndarray:
+        """Place every tip genome list of `samples` (probVectTerminalNode output) on the frozen tree; returns records
+        (capi.PLACE_RESULT_FIELDS).  The tree is not modified; prepare_search() must have bound it."""
+        eng, dev, A = self.eng, self.eng.device, self.arena
+        n = len(samples)
+        first = A.add_ids(n)
+        A.store_packed(np.arange(first, first + n, dtype=np.int64), samples)
+        self.prepare_search()  # the arena's tables moved: bind again
+        ids = torch.arange(first, first + n, dtype=torch.int32, device=dev)
+        out = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
+        rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), n, _dp(ids), _dp(out), int(scratch_keys), eng._stream())
+        capi.check(eng.ctx, rc, "maple_place_batch")
+        return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
+
     @staticmethod
     def search_records(out: torch.Tensor) -> np.ndarray:
         return out.cpu().numpy().view(np.dtype(capi.SEARCH_RESULT_FIELDS)).reshape(-1)

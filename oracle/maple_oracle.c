@@ -1627,3 +1627,251 @@ void or_search_batch(const OrModel *m, const OrTree *t, const OrSearchParams *sp
         free(lazy.pay[i]);
     }
 }
+
+/* ==================================================================================================
+ * Placement of a new sample on a frozen tree: findBestParentForNewSample (:7912-8292), default feature set
+ * (computePlacementSupportOnly=False, no HnZ, no time tree), with isMinorSequence (:5919-6004).
+ * ================================================================================================== */
+
+/* isMinorSequence(probVect1, probVect2, onlyFindIdentical): 0 = neither contains the other, 1 = list 2 is identical to or
+ * less informative than list 1, 2 = list 1 is less informative than list 2 */
+int or_is_minor(const OrModel *m, const uint32_t *k1, const double *p1, const uint32_t *k2, const double *p2, int onlyFindIdentical) {
+    const int lRef = m->lRef;
+    Cur e1, e2;
+    cur_init(&e1, k1, p1);
+    cur_init(&e2, k2, p2);
+    int pos = 0, found1bigger = 0, found2bigger = 0;
+    for (;;) {
+        if (e1.type != e2.type) {
+            if (onlyFindIdentical) return 0;
+            else if (e1.type == 5) {
+                if (e2.type == 4) pos = e1.end < e2.end ? e1.end : e2.end;
+                else pos += 1;
+                found2bigger = 1;
+            } else if (e2.type == 5) {
+                if (e1.type == 4) pos = e1.end < e2.end ? e1.end : e2.end;
+                else pos += 1;
+                found1bigger = 1;
+            } else if (e1.type == 6) {
+                int i2 = (e2.type == 4) ? e1.nuc : e2.type;
+                if (e1.vec[i2] > 0.1) found2bigger = 1;
+                else return 0;
+                pos += 1;
+            } else if (e2.type == 6) {
+                int i1 = (e1.type == 4) ? e2.nuc : e1.type;
+                if (e2.vec[i1] > 0.1) found1bigger = 1;
+                else return 0;
+                pos += 1;
+            } else return 0;
+        } else if (e1.type == 6) {
+            for (int j = 0; j < 4; j++) {
+                if (onlyFindIdentical) {
+                    if (e2.vec[j] != e1.vec[j]) return 0;
+                } else if (e2.vec[j] > 0.1 && e1.vec[j] < 0.1) found1bigger = 1;
+                else if (e1.vec[j] > 0.1 && e2.vec[j] < 0.1) found2bigger = 1;
+            }
+            pos += 1;
+        } else {
+            if (e1.type < 4) pos += 1;
+            else pos = e1.end < e2.end ? e1.end : e2.end;
+        }
+        if (found1bigger && found2bigger) return 0;
+        if (pos == lRef) break;
+        if (e1.type < 4 || e1.type == 6 || pos == e1.end) cur_next(&e1);
+        if (e2.type < 4 || e2.type == 6 || pos == e2.end) cur_next(&e2);
+    }
+    if (found1bigger) return found2bigger ? 0 : 1;
+    return found2bigger ? 2 : 1;
+}
+
+typedef struct {
+    int32_t strictStopRules, allowedFails, deeperSearchForLongBranches, onlyFindIdentical; /* onlyFindIdentical: any error-rate option, --supportFor0Branches or --HnZ (:7936) */
+    double thresholdLogLK, thresholdLogLKoptimization, thresholdLogLKconsecutivePlacement;
+    double effectivelyNon0BLen, BLenThresholdDeeperSearch, oneMutBLen;
+} OrPlaceParams;
+
+typedef struct {
+    int32_t bestNode;
+    int32_t status;   /* 0 placed (bestNode, bestScore, lengths); 1 absorbed as a minor sequence of leaf bestNode (:7949, :8002: the
+                         reference returns (node, 1.0, None, diffs)); 2 aborted (the reference would raise); 3 scratch overflow */
+    int32_t phase1;   /* candidate branches scored in the walk (:8033 / :8050) */
+    int32_t missedMinors; /* leaves found strictly less informative than the sample (:7960, :8004) */
+    double bestScore, bLenTop, bLenBottom, bLenAppend; /* python False in bestBranchLengths is 0.0 here */
+} OrPlaceResult;
+
+typedef struct { int t1, failedPasses; double parentLK; LRef diffs; } PlaceStackE;
+typedef struct { int t1; double score; LRef diffs; } PlaceBest;
+
+void or_place_sample(const OrModel *m, const OrTree *t, const OrPlaceParams *pp, const uint32_t *dk, const double *dp, int dnk, Scratch *s,
+                     OrPlaceResult *r) {
+    memset(r, 0, sizeof *r);
+    s->topK = s->topP = 0;
+    s->overflow = 0;
+    const int root = t->root;
+    const double eff = pp->effectivelyNon0BLen, one = pp->oneMutBLen;
+    LRef in = {dk, dp, dnk};
+    LRef diffs = s_copy(s, in); /* shorten() works in place on it (:8065) */
+    if (!diffs.k) { r->status = 3; return; }
+    if (n_mut(t, root)) diffs = s_pass(m, t, s, diffs, root, 0);
+    int bestNode = root;
+    double bTop = 0.0, bBottom = 0.0, bAppend = one; /* (False, False, oneMutBLen) */
+    PlaceStackE *stack = (PlaceStackE *)malloc(sizeof(PlaceStackE) * (size_t)(t->nNodes + 4));
+    PlaceBest *best = NULL;
+    size_t nBest = 0, capBest = 0;
+    int sp = 0;
+#define PLACE_FAIL(code) do { r->status = (code); goto done; } while (0)
+    if (t->child0[root] < 0) {
+        LRef pv = tree_list(t, 0, root);
+        int cmp = or_is_minor(m, pv.k, pv.p, diffs.k, diffs.p, pp->onlyFindIdentical);
+        if (cmp == 1) { r->bestNode = root; r->bestScore = 1.0; PLACE_FAIL(1); }
+        else if (cmp == 2) r->missedMinors++;
+    }
+    {
+        LRef rootVect = s_root_vector(m, t, s, tree_list(t, 0, root), 0.0, 0);
+        if (!rootVect.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+        double bestLKdiff = or_append(m, rootVect.k, rootVect.p, diffs.k, diffs.p, 1, one);
+        const double originalLKdiff = bestLKdiff;
+        if (t->child0[root] >= 0) {
+            int ch[2] = {t->child0[root], t->child1[root]};
+            for (int i = 0; i < 2; i++) {
+                LRef dc = diffs;
+                if (n_mut(t, ch[i])) dc = s_pass(m, t, s, diffs, ch[i], 0);
+                if (!dc.k) PLACE_FAIL(3);
+                stack[sp].t1 = ch[i]; stack[sp].parentLK = bestLKdiff; stack[sp].failedPasses = 0; stack[sp].diffs = dc; sp++;
+            }
+        }
+        while (sp > 0) {
+            PlaceStackE E = stack[--sp];
+            const int t1 = E.t1;
+            int failedPasses = E.failedPasses;
+            LRef d = E.diffs;
+            double LKdiff;
+            if (t->child0[t1] < 0) { /* a leaf: is the new sample identical to / contained in it? (:7975-8005) */
+                LRef pv = tree_list(t, 0, t1);
+                int cmp = or_is_minor(m, pv.k, pv.p, d.k, d.p, pp->onlyFindIdentical);
+                if (cmp == 1) { r->bestNode = t1; r->bestScore = 1.0; PLACE_FAIL(1); }
+                else if (cmp == 2) r->missedMinors++;
+            }
+            if (t->dist[t1] > eff && t->up[t1] >= 0) {
+                double bestTopLength, bestBottomLength, bestAppendingLength;
+                if (pp->deeperSearchForLongBranches && t->dist[t1] > pp->BLenThresholdDeeperSearch) {
+                    const int par = t->up[t1];
+                    LRef upVect = (t1 == t->child0[par]) ? tree_list(t, 1, par) : tree_list(t, 2, par);
+                    if (n_mut(t, t1)) upVect = s_pass(m, t, s, upVect, t1, 0);
+                    const int isTip = t->isTip[t1];
+                    LRef pv = tree_list(t, 0, t1);
+                    const size_t mk = s->topK, mp = s->topP;
+                    bestAppendingLength = one;
+                    LRef midLower = s_merge(m, s, pv, t->dist[t1] / 2, isTip, d, bestAppendingLength, 1, 0);
+                    if (!midLower.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+                    bestTopLength = s_blen(m, s, upVect, midLower, 0);
+                    LRef midTop = s_merge(m, s, upVect, bestTopLength, 0, d, bestAppendingLength, 1, 1);
+                    if (!midTop.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+                    bestBottomLength = s_blen(m, s, midTop, pv, isTip);
+                    LRef newMid = s_merge(m, s, upVect, bestTopLength, 0, pv, bestBottomLength, isTip, 1);
+                    if (!newMid.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+                    LKdiff = or_append(m, newMid.k, newMid.p, d.k, d.p, 1, bestAppendingLength);
+                    if (!n_mut(t, t1)) { s->topK = mk; s->topP = mp; }
+                } else {
+                    LRef tot = tree_list(t, 3, t1);
+                    if (!tot.k) PLACE_FAIL(2);
+                    LKdiff = or_append(m, tot.k, tot.p, d.k, d.p, 1, one);
+                    bestBottomLength = t->dist[t1] / 2;
+                    bestTopLength = t->dist[t1] / 2;
+                    bestAppendingLength = one;
+                }
+                r->phase1++;
+                if (LKdiff >= bestLKdiff) {
+                    s_shorten_inplace(m, &d); /* :8065 */
+                    bestLKdiff = LKdiff;
+                    bestNode = t1;
+                    failedPasses = 0;
+                    if (nBest == capBest) { capBest = capBest ? 2 * capBest : 64; best = (PlaceBest *)realloc(best, sizeof(PlaceBest) * capBest); }
+                    best[nBest].t1 = t1; best[nBest].score = LKdiff; best[nBest].diffs = d; nBest++;
+                    bTop = bestTopLength; bBottom = bestBottomLength / 2; bAppend = bestAppendingLength;
+                } else if (LKdiff > bestLKdiff - pp->thresholdLogLKoptimization) {
+                    if (nBest == capBest) { capBest = capBest ? 2 * capBest : 64; best = (PlaceBest *)realloc(best, sizeof(PlaceBest) * capBest); }
+                    best[nBest].t1 = t1; best[nBest].score = LKdiff; best[nBest].diffs = d; nBest++;
+                }
+                if (LKdiff < (E.parentLK - pp->thresholdLogLKconsecutivePlacement)) failedPasses++;
+            } else LKdiff = E.parentLK;
+            int go;
+            if (pp->strictStopRules) go = failedPasses <= pp->allowedFails && LKdiff > (bestLKdiff - pp->thresholdLogLK);
+            else go = failedPasses <= pp->allowedFails || LKdiff > (bestLKdiff - pp->thresholdLogLK);
+            if (go && t->child0[t1] >= 0) {
+                int ch[2] = {t->child0[t1], t->child1[t1]};
+                for (int i = 0; i < 2; i++) {
+                    LRef dc = d;
+                    if (n_mut(t, ch[i])) dc = s_pass(m, t, s, d, ch[i], 0);
+                    if (!dc.k) PLACE_FAIL(3);
+                    stack[sp].t1 = ch[i]; stack[sp].parentLK = LKdiff; stack[sp].failedPasses = failedPasses; stack[sp].diffs = dc; sp++;
+                }
+            }
+        }
+        /* refinement of every branch within thresholdLogLKoptimization of the best (:8109-8187) */
+        double bestScore = bestLKdiff;
+        for (size_t i = 0; i < nBest; i++) {
+            if (!(best[i].score >= bestLKdiff - pp->thresholdLogLKoptimization)) continue;
+            const int node = best[i].t1, par = t->up[node];
+            LRef d = best[i].diffs;
+            LRef upVect = (node == t->child0[par]) ? tree_list(t, 1, par) : tree_list(t, 2, par);
+            const size_t mk = s->topK, mp = s->topP;
+            if (n_mut(t, node)) upVect = s_pass(m, t, s, upVect, node, 0);
+            const int isTip = t->isTip[node];
+            LRef pv = tree_list(t, 0, node), tot = tree_list(t, 3, node);
+            if (!upVect.k || !pv.k || !tot.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+            const double bestAppendingLength = s_blen(m, s, tot, d, 1);
+            LRef midLower = s_merge(m, s, pv, t->dist[node] / 2, isTip, d, bestAppendingLength, 1, 0);
+            if (!midLower.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+            double bestTopLength = s_blen(m, s, upVect, midLower, 0);
+            LRef midTop = s_merge(m, s, upVect, bestTopLength, 0, d, bestAppendingLength, 1, 1);
+            if (!midTop.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+            double bestBottomLength = s_blen(m, s, midTop, pv, isTip);
+            LRef newMid = s_merge(m, s, upVect, bestTopLength, 0, pv, bestBottomLength, isTip, 1);
+            if (!newMid.k) PLACE_FAIL(s->overflow ? s->overflow : 2);
+            const double appendingCost = or_append(m, newMid.k, newMid.p, d.k, d.p, 1, bestAppendingLength);
+            const double initialCost = or_append(m, upVect.k, upVect.p, pv.k, pv.p, isTip, t->dist[node]);
+            const double newPartialCost = or_append(m, upVect.k, upVect.p, pv.k, pv.p, isTip, bestBottomLength + bestTopLength);
+            const double optimizedScore = appendingCost + newPartialCost - initialCost;
+            if (optimizedScore >= bestScore) {
+                bestNode = node;
+                bestScore = optimizedScore;
+                bTop = bestTopLength; bBottom = bestBottomLength; bAppend = bestAppendingLength;
+            }
+            s->topK = mk;
+            s->topP = mp;
+            if (s->overflow) PLACE_FAIL(s->overflow);
+        }
+        if (bestScore == -INFINITY) bestScore = originalLKdiff;
+        r->bestNode = bestNode;
+        r->bestScore = bestScore;
+        r->bLenTop = bTop; r->bLenBottom = bBottom; r->bLenAppend = bAppend;
+        r->status = s->overflow ? s->overflow : 0;
+    }
+done:
+#undef PLACE_FAIL
+    free(stack);
+    free(best);
+}
+
+/* Samples are independent on a frozen tree (the reference's process_chunk / joblib seam, :11190-11287). */
+void or_place_batch(const OrModel *m, const OrTree *t, const OrPlaceParams *pp, int64_t n, const uint32_t *key, const double *pay,
+                    const int64_t *keyStart, const int64_t *payStart, const int32_t *nkeys, int64_t scratchKeys, OrPlaceResult *out) {
+#pragma omp parallel
+    {
+        Scratch s;
+        memset(&s, 0, sizeof s);
+        s.capK = (size_t)scratchKeys;
+        s.capP = 6 * s.capK;
+        s.capA = s.capK;
+        s.key = (uint32_t *)malloc(sizeof(uint32_t) * s.capK);
+        s.pay = (double *)malloc(sizeof(double) * s.capP);
+        s.ais = (double *)malloc(sizeof(double) * s.capA);
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t i = 0; i < n; i++)
+            or_place_sample(m, t, pp, key + keyStart[i], pay + payStart[i], nkeys[i], &s, &out[i]);
+        free(s.key);
+        free(s.pay);
+        free(s.ais);
+    }
+}

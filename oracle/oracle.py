@@ -98,8 +98,23 @@ def lib():
         L.or_search_batch.restype = None
         L.or_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         L.or_num_threads.restype = C.c_int
+        L.or_is_minor.restype = C.c_int
+        L.or_is_minor.argtypes = [C.c_void_p] * 5 + [C.c_int]
+        L.or_place_batch.restype = None
+        L.or_place_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
         _lib = L
     return _lib
+
+
+class OrPlaceParams(C.Structure):
+    _fields_ = [("strictStopRules", C.c_int32), ("allowedFails", C.c_int32), ("deeperSearchForLongBranches", C.c_int32),
+                ("onlyFindIdentical", C.c_int32), ("thresholdLogLK", C.c_double), ("thresholdLogLKoptimization", C.c_double),
+                ("thresholdLogLKconsecutivePlacement", C.c_double), ("effectivelyNon0BLen", C.c_double),
+                ("BLenThresholdDeeperSearch", C.c_double), ("oneMutBLen", C.c_double)]
+
+
+PLACE_RESULT_DTYPE = np.dtype([("bestNode", "i4"), ("status", "i4"), ("phase1", "i4"), ("missedMinors", "i4"), ("bestScore", "f8"),
+                               ("bLenTop", "f8"), ("bLenBottom", "f8"), ("bLenAppend", "f8")])
 
 
 class Oracle:
@@ -269,6 +284,37 @@ class Oracle:
         nodes = np.ascontiguousarray(nodes, np.int32)
         out = np.zeros(len(nodes), dtype=SEARCH_RESULT_DTYPE)
         self.L.or_search_batch(self.mp, C.addressof(t), C.addressof(sp), len(nodes), _p(nodes), int(scratch_keys), int(lazy_mode), _p(out))
+        return out
+
+    def _tree_struct(self, tree: dict, lists):
+        n = len(tree["up"])
+        keep = {k: np.ascontiguousarray(tree[k], dt) for k, dt in (("up", np.int32), ("child0", np.int32), ("child1", np.int32),
+                                                                   ("dist", np.float64), ("isTip", np.uint8))}
+        t = OrTree()
+        t.nNodes, t.root = n, int(tree["root"])
+        t.up, t.child0, t.child1, t.dist, t.isTip = (_p(keep[k]) for k in ("up", "child0", "child1", "dist", "isTip"))
+        if tree.get("mutStart") is not None:
+            keep["mutStart"] = np.ascontiguousarray(tree["mutStart"], np.int32)
+            keep["mut"] = np.ascontiguousarray(tree["mut"], np.int32)
+            t.mutStart, t.mut = _p(keep["mutStart"]), _p(keep["mut"])
+        t.key, t.pay, t.keyStart, t.payStart, t.nkeys = _p(lists.key), _p(lists.pay), _p(lists.key_start), _p(lists.pay_start), _p(lists.nkeys)
+        return t, keep
+
+    def is_minor(self, v1, v2, onlyFindIdentical=False):
+        """isMinorSequence(probVect1, probVect2, onlyFindIdentical) (:5919)."""
+        a, b = self._one(v1), self._one(v2)
+        return int(self.L.or_is_minor(self.mp, _p(a.key), _p(a.pay), _p(b.key), _p(b.pay), 1 if onlyFindIdentical else 0))
+
+    def place_batch(self, tree: dict, lists, params: dict, samples, scratch_keys: int = 1 << 20):
+        """findBestParentForNewSample (:7912) for every list of `samples` (PackedLists of tip genome lists) on the frozen tree.
+        Returns a structured array (PLACE_RESULT_DTYPE)."""
+        t, keep = self._tree_struct(tree, lists)
+        pp = OrPlaceParams()
+        for k, v in params.items():
+            setattr(pp, k, v)
+        out = np.zeros(len(samples), dtype=PLACE_RESULT_DTYPE)
+        self.L.or_place_batch(self.mp, C.addressof(t), C.addressof(pp), len(samples), _p(samples.key), _p(samples.pay),
+                              _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(out))
         return out
 
     def num_threads(self):

@@ -258,6 +258,74 @@ def snapshot_tree(tree, root, T):
     }
 
 
+def harvest_placements(G, tree, root, T, n_base=14):
+    """findBestParentForNewSample (:7912) on the FROZEN tree for new samples derived from the ones already placed: an exact
+    copy, a copy without its last difference, a copy with one extra substitution, and a mix of two samples.  Every call
+    runs on a deep copy of the tree (the reference appends absorbed samples to minorSequences and may update lists)."""
+    import copy
+    import random
+    rng = random.Random(12345)
+    lRef, ref = G["lRef"], G["ref"]
+    _, data = G["readConciseAlignment"](G["inputFile"])  # the reference clears its own copy after the initial placement (:11816)
+    data = {k: v for k, v in data.items() if v is not None}
+    names = sorted(data)
+    picks = [names[i] for i in sorted(rng.sample(range(len(names)), min(n_base, len(names))))]
+
+    def covered(diffs):
+        c = set()
+        for d in diffs:
+            ln = d[2] if len(d) > 2 else 1
+            c.update(range(d[1], d[1] + ln))
+        return c
+
+    new_samples = []
+    for i, nm in enumerate(picks):
+        d = list(data[nm])
+        new_samples.append(("copy:" + nm, d))
+        if d:
+            new_samples.append(("minus:" + nm, d[:-1]))
+        cov = covered(d)
+        for _ in range(50):
+            pos = rng.randrange(1, lRef + 1)
+            if pos not in cov:
+                alt = rng.choice([b for b in "acgt" if b != ref[pos - 1].lower()])
+                new_samples.append(("plus:" + nm, sorted(d + [(alt, pos)], key=lambda x: x[1])))
+                break
+        other = list(data[picks[(i + 1) % len(picks)]])
+        half = lRef // 2
+        mix = [x for x in d if x[1] + (x[2] if len(x) > 2 else 1) - 1 <= half] + [x for x in other if x[1] > half]
+        new_samples.append(("mix:" + nm, mix))
+    counter = {"n": 0}
+    o_app = G["appendProbNode"]
+
+    def counting_append(P, C, isTipC, bLen, **kw):
+        if sys._getframe(1).f_lineno in (8033, 8050):
+            counter["n"] += 1
+        return o_app(P, C, isTipC, bLen, **kw)
+
+    out = []
+    G["appendProbNode"] = counting_append
+    try:
+        for label, diffs in new_samples:
+            tcopy = copy.deepcopy(tree)
+            partials = G["probVectTerminalNode"](diffs, None, None)
+            before = T.canon(partials)
+            counter["n"] = 0
+            r = G["findBestParentForNewSample"](tcopy, root, partials, "new_" + label, False)
+            minor = r[2] is None
+            out.append({"label": label, "diffs": T.add(before), "bestNode": r[0], "bestScore": r[1], "minor": bool(minor),
+                        "blens": None if minor else [float(x) if x else 0.0 for x in r[2]], "phase1": counter["n"]})
+    finally:
+        G["appendProbNode"] = o_app
+    env = {"strictStopRules": bool(G["strictStopRules"]), "allowedFails": G["allowedFails"], "thresholdLogLK": G["thresholdLogLK"],
+           "thresholdLogLKoptimization": G["thresholdLogLKoptimization"], "oneMutBLen": G["oneMutBLen"],
+           "onlyFindIdentical": bool(G["errorRateSiteSpecificFile"] or G["errorRateFixed"] or G["estimateErrorRate"]
+                                     or G["estimateSiteSpecificErrorRate"] or G["supportFor0Branches"] or G["HnZ"])}
+    print("[golden] placements: %d new samples, %d absorbed as minor sequences, %d candidate branches scored" % (
+        len(out), sum(o["minor"] for o in out), sum(o["phase1"] for o in out)), file=sys.stderr)
+    return out, env
+
+
 ENV_KEYS = ["lRef", "rootFreqs", "usingErrorRate", "errorRateSiteSpecific", "useRateVariation",
             "thresholdLogLKoptimizationTopology", "thresholdLogLKconsecutivePlacement", "deeperSearchForLongBranches",
             "BLenThresholdDeeperSearch", "effectivelyNon0BLen", "minBLenSensitivity", "thresholdProb",
@@ -342,6 +410,7 @@ class Harvest:
                 for bl in (0.0, tree.dist[nd] if tree.dist[nd] else 1e-5):
                     r = G["rootVector"](v, bl, tip, tree, root)
                     rec.calls["rootVector"].append({"v": T.add(v), "bLen": bl, "isFromTip": bool(tip), "out": T.add(r)})
+            placements, place_env = harvest_placements(G, tree, root, T)
             rec.install()
             try:
                 results = [func(x) for x in inputs]
@@ -350,6 +419,7 @@ class Harvest:
             self.first = {"env": env, "model": model, "params": params, "tree": snap, "treeLK": treeLK,
                           "calls": rec.calls, "callCounts": rec.count, "searches": rec.searches,
                           "proposed": [[list(m) for m in r] for r in results], "phase1Total": rec.phase1,
+                          "placements": placements, "placeEnv": place_env,
                           "lists": [jsonable_list(c) for c in rec.table.lists]}
             print("[golden] %s: harvested %d lists, %d searches, %d phase-1 candidates, counts %s" % (
                 self.name, len(rec.table.lists), len(rec.searches), rec.phase1, rec.count), file=sys.stderr)
