@@ -13,8 +13,9 @@ metric : SPR candidate placements scored per second = phase-1 appendProbNode cal
 value  : node list already on the device (lists, tree and model are always device-resident)
 e2e    : node ids in pinned host memory -> device, search, 64-byte result records -> host, every step
 --impl reference : the CPU restatement of the reference algorithm (oracle/maple_oracle.c, OpenMP over all host
-         cores) running the same searches on a bounded sample of the nodes.  The reference itself is a pure-Python
-         script that cannot travel to the GPU box; BASELINE.md has its CPython rates measured while surveying.
+         cores) running the same searches on a bounded sample of the nodes, on the same frozen tree built on the CPU
+         (no GPU, no CUDA library on this path).  The reference itself is a pure-Python script that cannot travel to
+         the GPU box; BASELINE.md has its CPython rates measured while surveying.
 """
 import argparse
 import json
@@ -128,18 +129,39 @@ def cpu_sample(nodes, k):
     return nodes[np.linspace(0, len(nodes) - 1, k).astype(np.int64)]
 
 
+def build_problem_cpu(args):
+    """The same frozen tree as build_problem, built without the CUDA library: the oracle's mergeVectors in level-synchronous
+    batches (oracle/host_tree.py).  Verified equivalent: the oracle's searches on both give identical records."""
+    import numpy as np
+    from maple_b200.synthetic import generate
+    from oracle.host_tree import build_tree_lists
+    from oracle.oracle import Oracle
+    t0 = time.time()
+    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, seed=1, ml_like_blens=True)
+    orc = Oracle(d.model)
+    lists, dist, isTip = build_tree_lists(orc, d.up, d.child0, d.child1, d.dist, d.root, d.tip_nodes, d.tip_lists, d.model.lRef,
+                                          d.model.usingErrorRate)
+    out, stack = [], [int(d.root)]  # the nodes startTopologyUpdatesParallel visits (:9615-9626), in its pre-order
+    while stack:
+        n = stack.pop()
+        if d.child0[n] >= 0:
+            stack.append(int(d.child0[n]))
+            stack.append(int(d.child1[n]))
+        if n != d.root:
+            out.append(n)
+    ta = {"up": d.up, "child0": d.child0, "child1": d.child1, "dist": dist, "isTip": isTip, "root": d.root}
+    return d, orc, ta, lists, np.array(out, np.int32), round(time.time() - t0, 1)
+
+
 def run_reference(args):
+    """CPU arm: no GPU, no CUDA library anywhere on this path."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle.oracle import Oracle
-    d, eng, tree, nodes, setup_s = build_problem(args, 0)  # the lists the CPU arm searches are the ones the GPU arm uses
-    host = tree.arena.to_host()
+    d, orc, ta, host, nodes, setup_s = build_problem_cpu(args)
     p = round_params(args, d.model.lRef)
     sample = cpu_sample(nodes, args.cpu_searches)
-    orc = Oracle(d.model)
-    ta, pd = oracle_tree(d, tree), params_dict(p)
+    pd = params_dict(p)
     for _ in range(max(1, min(args.warmup, 1))):
         orc.search_batch(ta, host, pd, sample[: max(16, len(sample) // 8)], lazy_mode=1)
     t0 = time.perf_counter()
@@ -154,7 +176,9 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "nseq": args.nseq, "round": args.round, "searches_per_step": int(len(sample)),
-                       "placements_per_step": tot // args.steps},
+                       "placements_per_step": tot // args.steps, "setup_s": setup_s,
+                       "note": "tree and lists built on the CPU (oracle/host_tree.py); the reference itself is a Python script "
+                               "that cannot travel to this box, BASELINE.md has its CPython rates"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d of the %d searches of one round (evenly spread over the tree), oracle/maple_oracle.c "
                                        "search with OpenMP on %d threads" % (len(sample), len(nodes), cores)},

@@ -988,6 +988,19 @@ void or_differ_batch(const OrModel *m, const uint32_t *key, const double *pay, c
     }
 }
 
+/* shorten() (:3721) applied in place to every result slot of a merge batch (what the callers that STORE a list do, :6201, :6267) */
+void or_shorten_slots(const OrModel *m, int64_t n, uint32_t *key, double *pay, const int64_t *keyStart, const int64_t *payStart,
+                      int32_t *nk, int32_t *np_, const int32_t *status) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++) {
+        if (status && status[i] != 0) continue;
+        int32_t a = 0, b = 0;
+        or_shorten(m, key + keyStart[i], pay + payStart[i], key + keyStart[i], pay + payStart[i], &a, &b);
+        nk[i] = a;
+        np_[i] = b;
+    }
+}
+
 int or_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

@@ -98,6 +98,8 @@ def lib():
         L.or_search_batch.restype = None
         L.or_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
         L.or_num_threads.restype = C.c_int
+        L.or_shorten_slots.restype = None
+        L.or_shorten_slots.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         L.or_is_minor.restype = C.c_int
         L.or_is_minor.argtypes = [C.c_void_p] * 5 + [C.c_int]
         L.or_place_batch.restype = None
@@ -224,7 +226,7 @@ class Oracle:
                                _p(isTip), _p(bLen), _p(out))
         return out
 
-    def merge_batch(self, pl, idx1, b1, t1, idx2, b2, t2, flags, numMinor1=None, numMinor2=None):
+    def merge_batch(self, pl, idx1, b1, t1, idx2, b2, t2, flags, numMinor1=None, numMinor2=None, shorten=False):
         n = len(idx1)
         idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
         b1, b2 = np.ascontiguousarray(b1, np.float64), np.ascontiguousarray(b2, np.float64)
@@ -244,6 +246,8 @@ class Oracle:
         self.L.or_merge_batch(self.mp, _p(pl.key), _p(pl.pay), _p(pl.key_start), _p(pl.pay_start), n, _p(idx1), _p(b1), _p(t1),
                               _p(idx2), _p(b2), _p(t2), _p(flags), _p(nm1), _p(nm2), _p(ok), _p(op), _p(ks), _p(ps), _p(nk),
                               _p(npay), _p(lk), _p(st))
+        if shorten:
+            self.L.or_shorten_slots(self.mp, n, _p(ok), _p(op), _p(ks), _p(ps), _p(nk), _p(npay), _p(st))
         return {"key": ok, "pay": op, "key_start": ks, "pay_start": ps, "nkeys": nk, "npay": npay, "lk": lk, "status": st}
 
     def blen_batch(self, pl, pIdx, cIdx, fromTip):
