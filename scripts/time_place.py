@@ -1,0 +1,48 @@
+"""Ad hoc: throughput of maple_place_batch (findBestParentForNewSample on a frozen tree) on a synthetic tree.
+New samples = existing tips with one extra substitution each (so they are not simply absorbed as minor sequences)."""
+import math, sys, time
+import numpy as np, torch
+sys.path.insert(0, ".")
+from maple_b200 import capi
+from maple_b200.engine import MapleEngine
+from maple_b200.genome_list import pack_lists
+from maple_b200.synthetic import generate
+from maple_b200.tree import DeviceTree
+
+nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+nnew = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=True)
+eng = MapleEngine(d.model, 0)
+tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, 0))
+tree.prepare_search()
+lRef = d.model.lRef
+rng = np.random.default_rng(3)
+new = []
+for i in rng.choice(len(d.tip_lists), nnew, replace=False):
+    gl, out, pos, done = d.tip_lists[i], [], 0, False
+    for e in gl:  # split the first long R run to insert a substitution in its middle
+        end = e[1] if e[0] in (4, 5) else pos + 1
+        if not done and e[0] == 4 and end - pos > 40:
+            mid = pos + 20
+            ref = int(d.model.refIdx[mid])
+            out += [(4, mid), ((ref + 1 + int(rng.integers(3))) % 4, ref), (4, end)]
+            done = True
+        else:
+            out.append(e)
+        pos = end
+    new.append(out)
+samples = pack_lists(new, lRef, 0)
+L = math.log(lRef)
+p = capi.PlaceParams()
+p.strictStopRules, p.allowedFails, p.deeperSearchForLongBranches, p.onlyFindIdentical = 0, 5, 0, 0
+p.thresholdLogLK, p.thresholdLogLKoptimization, p.thresholdLogLKconsecutivePlacement = 18.0 * L, 1.0 * L, 1.0
+p.effectivelyNon0BLen, p.BLenThresholdDeeperSearch, p.oneMutBLen = 1.0 / (10 * lRef), (L + 5) / lRef, 1.0 / lRef
+for rep in range(2):
+    torch.cuda.synchronize()
+    t0 = time.time()
+    rec = tree.place_samples(samples, p)
+    dt = time.time() - t0
+    print("rep %d: %d samples in %.2f s (incl. upload and re-bind) = %.3g samples/s; %d candidate branches (%.0f / sample) = %.3g placements/s; "
+          "status %s" % (rep, nnew, dt, nnew / dt, rec["phase1"].sum(), rec["phase1"].mean(), rec["phase1"].sum() / dt,
+                         np.bincount(rec["status"], minlength=4).tolist()), flush=True)
