@@ -1018,7 +1018,7 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
     const unsigned capK = (unsigned)((scratch_keys_per_sample > 0 ? scratch_keys_per_sample : 4096) + 3) & ~3u;
     const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
-    const int stackCap = ctx->treeHeight + 8, bestCap = 1024;
+    const int stackCap = ctx->treeHeight + 8, bestCap = (int)(capK / 4 > 1024 ? capK / 4 : 1024);  // bestNodes entries per sample
     const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
                               (size_t)capK * 4 + 15) & ~size_t(15);
     int blocksPerSM = 0;

@@ -368,10 +368,21 @@ class DeviceTree:
         A.store_packed(np.arange(first, first + n, dtype=np.int64), samples)
         self.prepare_search()  # the arena's tables moved: bind again
         ids = torch.arange(first, first + n, dtype=torch.int32, device=dev)
-        out = torch.zeros((n, 48), dtype=torch.uint8, device=dev)
-        rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), n, _dp(ids), _dp(out), int(scratch_keys), eng._stream())
-        capi.check(eng.ctx, rc, "maple_place_batch")
-        return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
+
+        def run(which: torch.Tensor, keys: int) -> np.ndarray:
+            out = torch.zeros((which.numel(), 48), dtype=torch.uint8, device=dev)
+            rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), which.numel(), _dp(which), _dp(out), int(keys), eng._stream())
+            capi.check(eng.ctx, rc, "maple_place_batch")
+            return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
+
+        rec = run(ids, scratch_keys)
+        retry, keys = np.nonzero(rec["status"] == 3)[0], max(int(scratch_keys), 4096)
+        while retry.size and keys < (1 << 22):  # per-sample scratch (lists or the bestNodes table) exhausted: again with 8x
+            keys *= 8
+            again = run(ids[torch.as_tensor(retry, device=dev)].contiguous(), keys)
+            rec[retry] = again
+            retry = retry[again["status"] == 3]
+        return rec
 
     @staticmethod
     def search_records(out: torch.Tensor) -> np.ndarray:
