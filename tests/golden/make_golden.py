@@ -258,6 +258,9 @@ def snapshot_tree(tree, root, T):
     }
 
 
+TIPS_OUT = None
+
+
 def harvest_placements(G, tree, root, T, n_base=14):
     """findBestParentForNewSample (:7912) on the FROZEN tree for new samples derived from the ones already placed: an exact
     copy, a copy without its last difference, a copy with one extra substitution, and a mix of two samples.  Every call
@@ -317,6 +320,14 @@ def harvest_placements(G, tree, root, T, n_base=14):
                         "blens": None if minor else [float(x) if x else 0.0 for x in r[2]], "phase1": counter["n"]})
     finally:
         G["appendProbNode"] = o_app
+    # inputs of the path: the reference's reader on a snippet of the input file, and probVectTerminalNode (:3882) of the
+    # first samples under the flags that are live at this point of the run
+    tips = []
+    for nm in names[:80]:
+        tips.append({"name": nm, "diffs": [list(x) for x in data[nm]], "list": T.add(T.canon(G["probVectTerminalNode"](data[nm], None, None)))})
+    global TIPS_OUT
+    TIPS_OUT = {"tips": tips, "onlyNambiguities": bool(G["onlyNambiguities"]), "usingErrorRate": bool(G["usingErrorRate"]),
+                "errorRateSiteSpecific": bool(G["errorRateSiteSpecific"]), "errorRateGlobal": G.get("errorRateGlobal")}
     env = {"strictStopRules": bool(G["strictStopRules"]), "allowedFails": G["allowedFails"], "thresholdLogLK": G["thresholdLogLK"],
            "thresholdLogLKoptimization": G["thresholdLogLKoptimization"], "oneMutBLen": G["oneMutBLen"],
            "onlyFindIdentical": bool(G["errorRateSiteSpecificFile"] or G["errorRateFixed"] or G["estimateErrorRate"]
@@ -419,7 +430,7 @@ class Harvest:
             self.first = {"env": env, "model": model, "params": params, "tree": snap, "treeLK": treeLK,
                           "calls": rec.calls, "callCounts": rec.count, "searches": rec.searches,
                           "proposed": [[list(m) for m in r] for r in results], "phase1Total": rec.phase1,
-                          "placements": placements, "placeEnv": place_env,
+                          "placements": placements, "placeEnv": place_env, "tipInputs": TIPS_OUT,
                           "lists": [jsonable_list(c) for c in rec.table.lists]}
             print("[golden] %s: harvested %d lists, %d searches, %d phase-1 candidates, counts %s" % (
                 self.name, len(rec.table.lists), len(rec.searches), rec.phase1, rec.count), file=sys.stderr)
