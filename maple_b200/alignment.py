@@ -68,8 +68,11 @@ def read_maple_alignment(path: str, reference: Optional[str] = None) -> Tuple[st
 
 
 def tip_genome_list(diffs: Optional[Sequence[Diff]], refIdx: Sequence[int], lRef: int, usingErrorRate: bool = False,
-                    errorRate: float = 0.0, errorRates: Optional[Sequence[float]] = None, onlyNambiguities: bool = False) -> list:
-    """probVectTerminalNode(diffs, None, None): the lower genome list of a new tip, relative to the reference genome."""
+                    errorRate: float = 0.0, errorRates: Optional[Sequence[float]] = None, onlyNambiguities: bool = False,
+                    numMinSeqs: int = 0) -> list:
+    """probVectTerminalNode(diffs, None, None): the lower genome list of a new tip, relative to the reference genome.
+    numMinSeqs > 0: the tip stands for several identical samples, which under the error model gives its ambiguity vectors
+    no error term (updateProbVectTerminalNode, :3980-4003)."""
     if diffs is None:
         return [(5, lRef)]
     pos = 1
@@ -102,7 +105,9 @@ def tip_genome_list(diffs: Optional[Sequence[Diff]], refIdx: Sequence[int], lRef
                 base = AMBIGUITIES[ch]
                 n_set = sum(bool(x) for x in base)
                 eps = float(errorRates[cur - 1]) if errorRates is not None else float(errorRate)
-                if n_set == 2:
+                if numMinSeqs and n_set in (2, 3):
+                    vec = [0.0 if x == 0 else (0.5 if n_set == 2 else 1.0 / 3) for x in base]
+                elif n_set == 2:
                     vec = [eps * 0.33333 if x == 0 else 0.5 - eps * 0.33333 for x in base]
                 elif n_set == 3:
                     vec = [eps * 0.33333 if x == 0 else (1.0 / 3) - eps / 9 for x in base]

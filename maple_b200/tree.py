@@ -328,6 +328,16 @@ class DeviceTree:
             t.mut = np.ascontiguousarray(mut, np.int32).reshape(-1, 3)
         return t
 
+    @classmethod
+    def from_host_tree(cls, engine: MapleEngine, host_tree, root: int, tip_nodes, tip_lists):
+        """An input tree as set up by maple_b200.newick.load_input_tree: all four list families are built on the device
+        (reCalculateAllGenomeLists, :6431-6441)."""
+        a = host_tree.arrays()
+        t = cls(engine, a["up"], a["child0"], a["child1"], a["dist"], root, isTip=a["isTip"], numMinor=a["numMinor"])
+        m = engine.model
+        t.recalculate_all_lists(np.asarray(tip_nodes, np.int64), pack_lists(tip_lists, m.lRef, m.usingErrorRate))
+        return t
+
     # ------------------------------------------------------------------ SPR search round (startTopologyUpdatesParallel, :9580)
     def prepare_search(self):
         """Fill probVectTotUp of zero-length children of the root (the reference does it lazily and order-dependently

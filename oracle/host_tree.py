@@ -58,12 +58,13 @@ class HostArena:
         self.pt += int(p_al.sum())
 
 
-def build_tree_lists(orc, up, child0, child1, dist, root, tip_nodes, tip_lists, lRef, U, max_restarts=8):
-    """Returns (PackedLists with list id = family*nNodes + node, dist after zero-length repairs, isTip)."""
+def build_tree_lists(orc, up, child0, child1, dist, root, tip_nodes, tip_lists, lRef, U, max_restarts=8, isTip=None):
+    """Returns (PackedLists with list id = family*nNodes + node, dist after zero-length repairs, isTip).
+    isTip: "no children and no minor sequences" per node when the tree carries minor sequences (default: no children)."""
     up, child0, child1 = (np.asarray(a, np.int32) for a in (up, child0, child1))
     dist = np.array(dist, np.float64)
     n = len(up)
-    isTip = (child0 < 0).astype(np.uint8)
+    isTip = (child0 < 0).astype(np.uint8) if isTip is None else np.asarray(isTip, np.uint8)
     depth = np.full(n, -1, np.int32)
     order = [int(root)]
     depth[root] = 0
@@ -152,3 +153,24 @@ def build_tree_lists(orc, up, child0, child1, dist, root, tip_nodes, tip_lists, 
                 A.store(np.array([FAM_TOTUP * n + c]), r["key"], r["pay"], r["key_start"], r["pay_start"], r["nkeys"], r["npay"], r["status"])
     pl = PackedLists(A.key[: max(A.kt, 4) + 8].copy(), A.pay[: max(A.pt, 2) + 8].copy(), A.key_start, A.pay_start, A.nkeys, A.npay, lRef, U)
     return pl, dist, isTip
+
+
+def tree_likelihood(orc, pl, child0, child1, dist, root, isTip, numMinor=None):
+    """calculateTreeLikelihood (:9721-9779) over the stored lower lists: sum of the mergeVectors(returnLK=True) contributions of
+    every internal node reachable from the root, plus findProbRoot of the root's lower list.  `orc` needs its root tables."""
+    n = len(child0)
+    numMinor = np.zeros(n, np.int32) if numMinor is None else np.asarray(numMinor, np.int32)
+    internal, stack = [], [int(root)]
+    while stack:
+        nd = stack.pop()
+        if child0[nd] >= 0:
+            internal.append(nd)
+            stack.extend((int(child0[nd]), int(child1[nd])))
+    total = 0.0
+    if internal:
+        a, b = child0[internal].astype(np.int64), child1[internal].astype(np.int64)
+        r = orc.merge_batch(pl, a + FAM_LOWER * n, dist[a], isTip[a], b + FAM_LOWER * n, dist[b], isTip[b],
+                            np.full(len(a), 2, np.uint8), numMinor[a], numMinor[b])
+        assert not (r["status"] != 0).any(), "inconsistent lower genome lists"
+        total += float(np.sum(r["lk"]))
+    return total + orc.prob_root(pl.get(int(root) + FAM_LOWER * n))

@@ -22,3 +22,13 @@ def load_golden(name):
         fx = json.load(f)
     fx["lists"] = [_as_tuples(gl) for gl in fx["lists"]]
     return fx
+
+
+@functools.lru_cache(maxsize=None)
+def load_extras(name):
+    """tests/golden/extras/<name>.json.gz: Newick strings, re-read trees, the input-tree set-up and the branch-length sweeps
+    recorded from the reference on the same frozen tree (make_golden.py: harvest_extras)."""
+    with gzip.open(os.path.join(GOLDEN_DIR, "extras", name + ".json.gz"), "rt") as f:
+        fx = json.load(f)
+    fx["lists"] = [_as_tuples(gl) for gl in fx["lists"]]
+    return fx
