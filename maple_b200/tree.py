@@ -120,6 +120,27 @@ class ListArena:
                            self.key_start.cpu().numpy(), self.pay_start.cpu().numpy(), self.nkeys.cpu().numpy(),
                            self.npay.cpu().numpy(), self.lRef, self.U)
 
+    def mark(self):
+        """State to come back to with release(): temporary lists (re-referenced copies, trial root vectors) are appended
+        after the mark and dropped again."""
+        return (self.n, self.key_tail, self.pay_tail)
+
+    def release(self, mark):
+        n, self.key_tail, self.pay_tail = mark
+        if n != self.n:
+            self.key_start, self.pay_start = self.key_start[:n].contiguous(), self.pay_start[:n].contiguous()
+            self.nkeys, self.npay = self.nkeys[:n].contiguous(), self.npay[:n].contiguous()
+            self.n = n
+            self._bind()
+
+    def add_lists(self, r) -> torch.Tensor:
+        """Append the lists of a MergeResult under fresh ids; returns the ids (int64, device)."""
+        k = r.nkeys.numel()
+        first = self.add_ids(k)
+        ids = torch.arange(first, first + k, dtype=torch.int64, device=self.key.device)
+        self.store(ids, r.key, r.pay, r.key_start, r.pay_start, r.nkeys, r.npay, r.status)
+        return ids
+
     def used_bytes(self) -> int:
         return self.key_tail * 4 + self.pay_tail * 8 + self.n * (8 + 8 + 4 + 4)
 
@@ -312,6 +333,74 @@ class DeviceTree:
             total += float(r.lk.sum().item())
         total += float(eng.prob_root_batch([root_id]).cpu()[0])
         return total
+
+    # ------------------------------------------------------------------ traverseTreeToOptimizeBranchLengths(fastPass=True) (:8727)
+    def optimize_branch_lengths(self, effectivelyNon0BLen: float, dirty=None):
+        """One sweep over all dirty branches with the genome lists frozen (the reference's fastPass mode, see blen_sweep.py):
+        the root's two branches by a scan of their split (a batch of mergeVectors(returnLK) + findProbRoot), every other
+        branch by ONE maple_blen_batch launch over (upper list of the parent side, lower list of the node); the acceptance
+        rule (:8866-8884) is applied to the returned lengths.  Updates dist on host and device; the lists are NOT refreshed --
+        call recalculate_all_lists (or the per-family updates) afterwards.  Returns (number of updated branches, dirty flags
+        after the sweep)."""
+        from . import blen_sweep
+        eng, n, dev, A = self.eng, self.n, self.eng.device, self.arena
+        t64 = lambda a: torch.as_tensor(a, dtype=torch.int64, device=dev)  # noqa: E731
+        dirty = np.ones(n, bool) if dirty is None else np.array(dirty, bool)
+        root = self.root
+        mutStart = getattr(self, "mutStart", None)
+        nmut = np.zeros(n, np.int64) if mutStart is None else np.diff(mutStart).astype(np.int64)
+        if mutStart is not None:
+            d_ms = torch.from_numpy(mutStart).to(dev)
+            d_mu = torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
+        mark = A.mark()
+
+        def passed(ids: torch.Tensor, through: np.ndarray, dir_up: bool) -> torch.Tensor:
+            """ids with the lists that cross a local-reference branch (mutations[node], :8754-8759, :8824) replaced by
+            temporary re-referenced copies."""
+            hit = np.nonzero(nmut[through] > 0)[0]
+            if hit.size == 0:
+                return ids
+            r = eng.pass_branch_batch(ids[t64(hit)], through[hit], np.full(hit.size, 1 if dir_up else 0, np.uint8), d_ms, d_mu)
+            ids = ids.clone()
+            ids[t64(hit)] = A.add_lists(r)
+            return ids
+
+        try:
+            if self.child0[root] >= 0:
+                c = np.array([self.child0[root], self.child1[root]], np.int64)
+                cand = blen_sweep.root_split_candidates(float(self.dist[c[0]]), float(self.dist[c[1]]), eng.model.lRef, effectivelyNon0BLen)
+                if cand is not None:
+                    low = passed(t64(c) + FAM_LOWER * n, c, True)
+                    k = len(cand[0])
+                    tips = self.d_isTip[t64(c)]
+                    r = eng.merge_batch(low[0].expand(k).int().contiguous(), torch.from_numpy(cand[0]).to(dev), tips[0].expand(k).contiguous(),
+                                        low[1].expand(k).int().contiguous(), torch.from_numpy(cand[1]).to(dev), tips[1].expand(k).contiguous(),
+                                        torch.full((k,), capi.MAPLE_MERGE_RETURN_LK, dtype=torch.uint8, device=dev))
+                    if bool((r.status != 0).any().item()):
+                        raise capi.MapleError("inconsistent root vector while scanning the root's branch lengths (the reference fails too, :8768)")
+                    trial = A.add_lists(r)
+                    if nmut[root] > 0:
+                        trial = passed(trial, np.full(k, root, np.int64), True)
+                    cost = (r.lk + eng.prob_root_batch(trial.int())).cpu().numpy()
+                    b1, b2 = blen_sweep.choose_root_split(cost, cand[0], float(self.dist[c[0]]), float(self.dist[c[1]]))
+                    self.dist[c[0]], self.dist[c[1]] = b1, b2
+            nodes = blen_sweep.sweep_nodes(self.up, self.child0, self.child1, root, dirty)
+            updates = 0
+            if nodes.size:
+                par = self.up[nodes].astype(np.int64)
+                upv = t64(np.where(self.child0[par] == nodes, par + FAM_UPRIGHT * n, par + FAM_UPLEFT * n))
+                if bool((A.key_start[upv] < 0).any().item()):
+                    raise capi.MapleError("a swept node has no upper list on its parent's side: build the lists first")
+                upv = passed(upv, nodes, False)
+                best, st = eng.blen_batch(upv.int(), (t64(nodes) + FAM_LOWER * n).int(), self.d_isTip[t64(nodes)])
+                new, changed, still = blen_sweep.accept(self.dist[nodes], best.cpu().numpy(), st.cpu().numpy() != 0)
+                self.dist[nodes] = new
+                dirty[nodes] = still
+                updates = int(changed.sum())
+            self.d_dist.copy_(torch.from_numpy(self.dist))
+        finally:
+            A.release(mark)
+        return updates, dirty
 
     # ------------------------------------------------------------------ construction from existing lists
     @classmethod

@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE: a stand-in for libmaple_b200.so whose entry points run the CPU oracle on HOST memory, so that the
+host-side orchestration above the C ABI (ListArena, DeviceTree: level-synchronous list building, tree likelihood, branch-length
+sweeps, input-tree set-up) can be exercised in a container without a GPU.  It binds the same call signatures the ctypes table
+in maple_b200/capi.py uses (pointers arrive as c_void_p, here of CPU torch tensors).  Nothing under maple_b200/ knows about
+it; the product path always loads the CUDA library (capi.load) and fails without a device."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from maple_b200.engine import MapleEngine
+from oracle.oracle import Oracle
+
+
+def _arr(ptr, n, dtype):
+    if ptr is None or n == 0:
+        return np.zeros(0, dtype)
+    addr = ptr.value if isinstance(ptr, C.c_void_p) else int(ptr)
+    return np.ctypeslib.as_array((C.c_byte * (n * np.dtype(dtype).itemsize)).from_address(addr)).view(dtype)
+
+
+def _off(ptr, nbytes):
+    return C.c_void_p(ptr.value + int(nbytes))
+
+
+class FakeLib:
+    def __init__(self, orc: Oracle, engine):
+        self.o, self.L, self.mp, self.eng = orc, orc.L, orc.mp, engine
+        self.launches = 0
+
+    # ---- lists
+    def maple_lists_bind(self, ctx, key, pay, ks, ps, n):
+        self.key, self.pay, self.ks, self.ps, self.n = key, pay, ks, ps, n
+        return 0
+
+    def maple_lists_copy(self, ctx, n, skey, spay, sks, sps, nk, npay, dkey, dpay, dks, dps, stream):
+        sks_, sps_, nk_, np_ = _arr(sks, n, np.int64), _arr(sps, n, np.int64), _arr(nk, n, np.int32), _arr(npay, n, np.int32)
+        dks_, dps_ = _arr(dks, n, np.int64), _arr(dps, n, np.int64)
+        for i in range(n):
+            if dks_[i] < 0 or nk_[i] == 0:
+                continue
+            C.memmove(dkey.value + 4 * int(dks_[i]), skey.value + 4 * int(sks_[i]), 4 * int(nk_[i]))
+            if np_[i]:
+                C.memmove(dpay.value + 8 * int(dps_[i]), spay.value + 8 * int(sps_[i]), 8 * int(np_[i]))
+        return 0
+
+    # ---- batches
+    def maple_merge_batch(self, ctx, n, i1, b1, t1, i2, b2, t2, flags, nm1, nm2, ok, op, ks, ps, nk, npay, lk, st, shorten, stream):
+        self.launches += 1
+        self.L.or_merge_batch(self.mp, self.key, self.pay, self.ks, self.ps, n, i1, b1, t1, i2, b2, t2, flags, nm1, nm2, ok, op, ks, ps,
+                              nk, npay, lk, st)
+        if shorten:
+            self.L.or_shorten_slots(self.mp, n, ok, op, ks, ps, nk, npay, st)
+        return 0
+
+    def maple_blen_batch(self, ctx, n, pIdx, cIdx, tip, scratch, ss, out, st, stream):
+        self.launches += 1
+        nkeys = C.c_void_p(self.eng.lists.nkeys.data_ptr())
+        self.L.or_blen_batch(self.mp, self.key, self.pay, self.ks, self.ps, nkeys, n, pIdx, cIdx, tip, out, st)
+        return 0
+
+    def maple_prob_root_batch(self, ctx, n, idx, out, stream):
+        self.launches += 1
+        idx_, out_ = _arr(idx, n, np.int32), _arr(out, n, np.float64)
+        ks, ps = _arr(self.ks, self.n, np.int64), _arr(self.ps, self.n, np.int64)
+        for i in range(n):
+            out_[i] = self.L.or_prob_root(self.mp, _off(self.key, 4 * ks[idx_[i]]), _off(self.pay, 8 * ps[idx_[i]]))
+        return 0
+
+    def maple_ctx_set_root_tables(self, ctx, cb, pl):
+        return 0  # the oracle built with_root_tables=True already holds them
+
+    def maple_root_vector_batch(self, ctx, n, idx, bLen, tip, ok, op, oks, ops, nk, npay, shorten, stream):
+        self.launches += 1
+        idx_, bl_, tip_ = _arr(idx, n, np.int32), _arr(bLen, n, np.float64), _arr(tip, n, np.uint8)
+        oks_, ops_, nk_, np_ = _arr(oks, n, np.int64), _arr(ops, n, np.int64), _arr(nk, n, np.int32), _arr(npay, n, np.int32)
+        ks, ps = _arr(self.ks, self.n, np.int64), _arr(self.ps, self.n, np.int64)
+        for i in range(n):
+            a, b = C.c_int32(0), C.c_int32(0)
+            k, p = _off(ok, 4 * oks_[i]), _off(op, 8 * ops_[i])
+            self.L.or_root_vector(self.mp, _off(self.key, 4 * ks[idx_[i]]), _off(self.pay, 8 * ps[idx_[i]]), float(bl_[i]), int(tip_[i]),
+                                  k, p, C.addressof(a), C.addressof(b))
+            if shorten:
+                self.L.or_shorten(self.mp, k, p, k, p, C.addressof(a), C.addressof(b))
+            nk_[i], np_[i] = a.value, b.value
+        return 0
+
+    def maple_pass_branch_batch(self, ctx, n, idx, mutNode, dirUp, mutStart, mut, ok, op, oks, ops, nk, npay, stream):
+        self.launches += 1
+        idx_, mn_, du_ = _arr(idx, n, np.int32), _arr(mutNode, n, np.int32), _arr(dirUp, n, np.uint8)
+        oks_, ops_, nk_, np_ = _arr(oks, n, np.int64), _arr(ops, n, np.int64), _arr(nk, n, np.int32), _arr(npay, n, np.int32)
+        ks, ps = _arr(self.ks, self.n, np.int64), _arr(self.ps, self.n, np.int64)
+        ms = _arr(mutStart, int(mn_.max()) + 2 if n else 0, np.int32)
+        for i in range(n):
+            a, b = C.c_int32(0), C.c_int32(0)
+            m0, m1 = int(ms[mn_[i]]), int(ms[mn_[i] + 1])
+            self.L.or_pass_branch(self.mp, _off(self.key, 4 * ks[idx_[i]]), _off(self.pay, 8 * ps[idx_[i]]), _off(mut, 12 * m0), m1 - m0,
+                                  int(du_[i]), _off(ok, 4 * oks_[i]), _off(op, 8 * ops_[i]), C.addressof(a), C.addressof(b))
+            nk_[i], np_[i] = a.value, b.value
+        return 0
+
+    def maple_last_error(self, ctx):
+        return b""
+
+    def maple_launch_count(self, ctx):
+        return self.launches
+
+
+class FakeEngine(MapleEngine):
+    """MapleEngine over FakeLib: same python code paths, CPU tensors."""
+
+    def __init__(self, model):  # noqa: super().__init__ needs a CUDA device on purpose
+        self.model = model
+        self.device = torch.device("cpu")
+        self.ctx = None
+        self.lists = None
+        self._root_tables = True
+        self.lib = FakeLib(Oracle(model, with_root_tables=True), self)
+
+    def _stream(self):
+        return None
+
+    def update_model(self):
+        self.lib = FakeLib(Oracle(self.model, with_root_tables=True), self)
