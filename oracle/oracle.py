@@ -65,46 +65,50 @@ def _p(a):
 _lib = None
 
 
+def declare(L):
+    """ctypes signatures of the oracle's entry points (also used for tests/hostsim, which exports the same names)."""
+    L.or_append.restype = C.c_double
+    L.or_append.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_double]
+    L.or_merge.restype = C.c_int
+    L.or_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.or_shorten.restype = None
+    L.or_shorten.argtypes = [C.c_void_p] * 7
+    L.or_blen.restype = C.c_int
+    L.or_blen.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+    L.or_differ.restype = C.c_int
+    L.or_differ.argtypes = [C.c_void_p] * 5
+    L.or_pass_branch.restype = None
+    L.or_pass_branch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+    L.or_root_vector.restype = None
+    L.or_root_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 4
+    L.or_prob_root.restype = C.c_double
+    L.or_prob_root.argtypes = [C.c_void_p] * 3
+    L.or_append_batch.restype = None
+    L.or_append_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 5
+    L.or_merge_batch.restype = None
+    L.or_merge_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 17
+    L.or_blen_batch.restype = None
+    L.or_blen_batch.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 5
+    L.or_differ_batch.restype = None
+    L.or_differ_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 3
+    L.or_search_batch.restype = None
+    L.or_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    L.or_num_threads.restype = C.c_int
+    L.or_shorten_slots.restype = None
+    L.or_shorten_slots.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    L.or_is_minor.restype = C.c_int
+    L.or_is_minor.argtypes = [C.c_void_p] * 5 + [C.c_int]
+    L.or_place_batch.restype = None
+    L.or_place_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
+    return L
+
+
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(LIB_PATH)
-        L.or_append.restype = C.c_double
-        L.or_append.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_double]
-        L.or_merge.restype = C.c_int
-        L.or_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
-                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.or_shorten.restype = None
-        L.or_shorten.argtypes = [C.c_void_p] * 7
-        L.or_blen.restype = C.c_int
-        L.or_blen.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
-        L.or_differ.restype = C.c_int
-        L.or_differ.argtypes = [C.c_void_p] * 5
-        L.or_pass_branch.restype = None
-        L.or_pass_branch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
-        L.or_root_vector.restype = None
-        L.or_root_vector.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int] + [C.c_void_p] * 4
-        L.or_prob_root.restype = C.c_double
-        L.or_prob_root.argtypes = [C.c_void_p] * 3
-        L.or_append_batch.restype = None
-        L.or_append_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 5
-        L.or_merge_batch.restype = None
-        L.or_merge_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 17
-        L.or_blen_batch.restype = None
-        L.or_blen_batch.argtypes = [C.c_void_p] * 6 + [C.c_int64] + [C.c_void_p] * 5
-        L.or_differ_batch.restype = None
-        L.or_differ_batch.argtypes = [C.c_void_p] * 5 + [C.c_int64] + [C.c_void_p] * 3
-        L.or_search_batch.restype = None
-        L.or_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
-        L.or_num_threads.restype = C.c_int
-        L.or_shorten_slots.restype = None
-        L.or_shorten_slots.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
-        L.or_is_minor.restype = C.c_int
-        L.or_is_minor.argtypes = [C.c_void_p] * 5 + [C.c_int]
-        L.or_place_batch.restype = None
-        L.or_place_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
-        _lib = L
+        _lib = declare(C.CDLL(LIB_PATH))
     return _lib
 
 

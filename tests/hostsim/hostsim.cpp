@@ -1,0 +1,207 @@
+// TEST INFRASTRUCTURE: the lane-level device code of maple_b200/csrc compiled for the host (shim/cuda_runtime.h) behind the
+// C oracle's own entry-point names and signatures (oracle/maple_oracle.c), so the python wrapper of the oracle
+// (oracle/oracle.py) can drive either library and the golden-vector tests run unchanged against the kernel SOURCE.
+// Built by tests/hostsim/build.py with g++ -O2 -ffp-contract=off (the CUDA build uses -fmad=false for the same reason:
+// a*b+c must round twice like CPython).  Never loaded by anything under maple_b200/.
+#include "cuda_runtime.h"
+
+#include "place.cuh"
+
+#include <vector>
+
+using namespace maple;
+
+struct OrTree {  // oracle/oracle.py: OrTree
+    int32_t nNodes, root;
+    const int32_t *up, *child0, *child1;
+    const double* dist;
+    const uint8_t* isTip;
+    const int32_t *mutStart, *mut;
+    const uint32_t* key;
+    const double* pay;
+    const int64_t *keyStart, *payStart;
+    const int32_t* nkeys;
+};
+
+static DevTree dev_tree(const OrTree* t) {
+    DevTree T;
+    memset(&T, 0, sizeof T);
+    T.nNodes = t->nNodes; T.root = t->root;
+    T.up = t->up; T.child0 = t->child0; T.child1 = t->child1; T.dist = t->dist; T.isTip = t->isTip;
+    T.mutStart = t->mutStart; T.mut = t->mut;
+    T.key = t->key; T.pay = t->pay; T.keyStart = t->keyStart; T.payStart = t->payStart; T.nkeys = t->nkeys;
+    return T;  // order == nullptr: no warp scans (they do not exist on the host)
+}
+
+static int tree_height(const OrTree* t) {
+    std::vector<int> depth(t->nNodes, 0), stack{t->root};
+    int h = 0;
+    while (!stack.empty()) {
+        const int v = stack.back();
+        stack.pop_back();
+        if (depth[v] > h) h = depth[v];
+        for (int c : {t->child0[v], t->child1[v]})
+            if (c >= 0) { depth[c] = depth[v] + 1; stack.push_back(c); }
+    }
+    return h;
+}
+
+extern "C" {
+
+double or_append(const DevModel* m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC, int isTipC, double bLen) {
+    return dev_append<true>(*m, kP, pP, kC, pC, isTipC != 0, bLen);
+}
+// the two forms the warp scans of the search kernel use per lane (search_fsm.cuh: f_append_sitewise / f_append_q4)
+double hs_append_sitewise(const DevModel* m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC, int isTipC, double bLen) {
+    return dev_append_sitewise<false>(*m, kP, pP, kC, pC, isTipC != 0, bLen);
+}
+double hs_append_q4(const DevModel* m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC, int isTipC, double bLen) {
+    return dev_append_q4<false>(*m, kP, pP, kC, pC, isTipC != 0, bLen);
+}
+
+int or_merge(const DevModel* m, const uint32_t* k1, const double* p1, double bLen1, int fromTip1, const uint32_t* k2, const double* p2,
+             double bLen2, int fromTip2, int flags, int numMinor1, int numMinor2, uint32_t* outKey, double* outPay, int32_t* outNk,
+             int32_t* outNp, double* outLk) {
+    Writer w;
+    w.init(outKey, outPay);
+    double lk = 0.0;
+    const int st = dev_merge<true>(*m, k1, p1, bLen1, fromTip1 != 0, k2, p2, bLen2, fromTip2 != 0, flags, numMinor1, numMinor2, w, &lk);
+    *outNk = st == 0 ? w.nk : 0;
+    *outNp = st == 0 ? w.np : 0;
+    if (outLk) *outLk = lk;
+    return st;
+}
+
+void or_shorten(const DevModel* m, const uint32_t* k, const double* p, uint32_t* outKey, double* outPay, int32_t* outNk, int32_t* outNp) {
+    Writer w;
+    w.init(outKey, outPay);
+    dev_shorten<false>(*m, k, p, w);
+    *outNk = w.nk;
+    *outNp = w.np;
+}
+
+int or_blen(const DevModel* m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC, int fromTipC, double* ais, double* out) {
+    double v = 0.0;
+    const int st = dev_blen<true>(*m, kP, pP, kC, pC, fromTipC != 0, ais, &v);
+    *out = v;
+    return st;
+}
+
+int or_differ(const DevModel* m, const uint32_t* k1, const double* p1, const uint32_t* k2, const double* p2) {
+    return dev_differ<true>(*m, k1, p1, k2, p2) ? 1 : 0;
+}
+
+void or_pass_branch(const DevModel* m, const uint32_t* k, const double* p, const int32_t* mut, int nMut, int dirIsUp, uint32_t* outKey,
+                    double* outPay, int32_t* outNk, int32_t* outNp) {
+    Writer w;
+    w.init(outKey, outPay);
+    dev_pass_branch(m->lRef, k, p, mut, nMut, dirIsUp != 0, w);
+    *outNk = w.nk;
+    *outNp = w.np;
+}
+
+void or_root_vector(const DevModel* m, const uint32_t* k, const double* p, double bLen, int isFromTip, uint32_t* outKey, double* outPay,
+                    int32_t* outNk, int32_t* outNp) {
+    Writer w;
+    w.init(outKey, outPay);
+    dev_root_vector<true>(*m, k, p, bLen, isFromTip != 0, w);
+    *outNk = w.nk;
+    *outNp = w.np;
+}
+
+double or_prob_root(const DevModel* m, const uint32_t* k, const double* p) { return dev_prob_root<true>(*m, k, p); }
+
+int or_is_minor(const DevModel* m, const uint32_t* k1, const double* p1, const uint32_t* k2, const double* p2, int onlyFindIdentical) {
+    return dev_is_minor(m->lRef, LRef{k1, p1, 0}, LRef{k2, p2, 0}, onlyFindIdentical != 0);
+}
+
+// the straight-line search of k_spr_search (search variant 1), one node after the other
+void or_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, int64_t n, const int32_t* nodes, int64_t scratchKeys,
+                     int32_t /*lazyMode: the device semantics are the pre-filled ones*/, SearchResult* out) {
+    const DevTree T = dev_tree(t);
+    const unsigned capK = (unsigned)scratchKeys, capP = 2 * capK + 6 * 1024, capA = 2048;
+    const int stackCap = (2 * tree_height(t) + 32 + 63) & ~63;
+    std::vector<uint32_t> key(capK + 64);
+    std::vector<double> pay(capP + 64), ais(capA);
+    std::vector<StackE> stack(stackCap);
+    ScratchD s;
+    s.key = key.data(); s.pay = pay.data(); s.ais = ais.data();
+    s.capK = capK; s.capP = capP; s.capA = capA; s.topK = s.topP = 0; s.err = 0;
+    for (int64_t i = 0; i < n; i++) search_node(*m, T, *sp, nodes[i], s, stack.data(), stackCap, out[i]);
+}
+
+// k_place_samples, one sample after the other
+void or_place_batch(const DevModel* m, const OrTree* t, const PlaceParams* pp, int64_t n, const uint32_t* key, const double* pay,
+                    const int64_t* keyStart, const int64_t* payStart, const int32_t* nkeys, int64_t scratchKeys, PlaceResult* out) {
+    const DevTree T = dev_tree(t);
+    const unsigned capK = (unsigned)scratchKeys, capP = 2 * capK + 6 * 1024, capA = 2048;
+    const int stackCap = tree_height(t) + 8, bestCap = (int)(capK / 4 > 1024 ? capK / 4 : 1024);
+    std::vector<uint32_t> sk(capK + 64);
+    std::vector<double> spay(capP + 64), ais(capA);
+    std::vector<PlaceStackE> stack(stackCap);
+    std::vector<PlaceBest> best(bestCap);
+    ScratchD s;
+    s.key = sk.data(); s.pay = spay.data(); s.ais = ais.data();
+    s.capK = capK; s.capP = capP; s.capA = capA; s.topK = s.topP = 0; s.err = 0;
+    for (int64_t i = 0; i < n; i++)
+        place_sample(*m, T, *pp, LRef{key + keyStart[i], pay + payStart[i], nkeys[i]}, s, stack.data(), stackCap, best.data(), bestCap, out[i]);
+}
+
+// batch drivers with the oracle's signatures (plain loops: this library is about the source, not about speed)
+void or_append_batch(const DevModel* m, const uint32_t* key, const double* pay, const int64_t* keyStart, const int64_t* payStart, int64_t n,
+                     const int32_t* pIdx, const int32_t* cIdx, const uint8_t* isTip, const double* bLen, double* out) {
+    for (int64_t i = 0; i < n; i++) {
+        const int p = pIdx[i], c = cIdx[i];
+        out[i] = dev_append<true>(*m, key + keyStart[p], pay + payStart[p], key + keyStart[c], pay + payStart[c], isTip[i] != 0, bLen[i]);
+    }
+}
+
+void or_merge_batch(const DevModel* m, const uint32_t* key, const double* pay, const int64_t* keyStart, const int64_t* payStart, int64_t n,
+                    const int32_t* idx1, const double* bLen1, const uint8_t* tip1, const int32_t* idx2, const double* bLen2,
+                    const uint8_t* tip2, const uint8_t* flags, const int32_t* numMinor1, const int32_t* numMinor2, uint32_t* outKey,
+                    double* outPay, const int64_t* outKeyStart, const int64_t* outPayStart, int32_t* outNk, int32_t* outNp, double* outLk,
+                    int32_t* outStatus) {
+    for (int64_t i = 0; i < n; i++) {
+        const int a = idx1[i], b = idx2[i];
+        double lk = 0.0;
+        outStatus[i] = or_merge(m, key + keyStart[a], pay + payStart[a], bLen1[i], tip1[i], key + keyStart[b], pay + payStart[b], bLen2[i],
+                                tip2[i], flags[i], numMinor1 ? numMinor1[i] : 0, numMinor2 ? numMinor2[i] : 0, outKey + outKeyStart[i],
+                                outPay + outPayStart[i], &outNk[i], &outNp[i], &lk);
+        if (outLk) outLk[i] = lk;
+    }
+}
+
+void or_blen_batch(const DevModel* m, const uint32_t* key, const double* pay, const int64_t* keyStart, const int64_t* payStart,
+                   const int32_t* nkeys, int64_t n, const int32_t* pIdx, const int32_t* cIdx, const uint8_t* fromTip, double* out,
+                   int32_t* outStatus) {
+    std::vector<double> ais;
+    for (int64_t i = 0; i < n; i++) {
+        const int p = pIdx[i], c = cIdx[i];
+        ais.assign(nkeys[p] + nkeys[c] + 1, 0.0);
+        outStatus[i] = or_blen(m, key + keyStart[p], pay + payStart[p], key + keyStart[c], pay + payStart[c], fromTip[i], ais.data(), &out[i]);
+    }
+}
+
+void or_differ_batch(const DevModel* m, const uint32_t* key, const double* pay, const int64_t* keyStart, const int64_t* payStart, int64_t n,
+                     const int32_t* idx1, const int32_t* idx2, uint8_t* out) {
+    for (int64_t i = 0; i < n; i++) {
+        const int a = idx1[i], b = idx2[i];
+        out[i] = (uint8_t)or_differ(m, key + keyStart[a], pay + payStart[a], keyStart[b] < 0 ? nullptr : key + keyStart[b],
+                                    keyStart[b] < 0 ? nullptr : pay + payStart[b]);
+    }
+}
+
+void or_shorten_slots(const DevModel* m, int64_t n, uint32_t* key, double* pay, const int64_t* keyStart, const int64_t* payStart, int32_t* nk,
+                      int32_t* np_, const int32_t* status) {
+    for (int64_t i = 0; i < n; i++) {
+        if (status && status[i] != 0) continue;
+        int32_t a = 0, b = 0;
+        or_shorten(m, key + keyStart[i], pay + payStart[i], key + keyStart[i], pay + payStart[i], &a, &b);
+        nk[i] = a;
+        np_[i] = b;
+    }
+}
+
+int or_num_threads(void) { return 1; }
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// TEST INFRASTRUCTURE.  Stand-in for <cuda_runtime.h> that lets g++ compile the lane-level device code of
+// maple_b200/csrc (glist.cuh, likelihood.cuh, search.cuh, place.cuh) for the HOST, one "lane" at a time, so that the very
+// source the kernels are built from can be checked against the reference's golden vectors in a container without a GPU
+// (tests/hostsim/hostsim.cpp).  Warp-level code (search_fsm.cuh) is not covered: it needs the hardware.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <math.h>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __activemask() { return 1u; }
+static inline void __syncwarp(unsigned = 1u) {}
+static inline int __any_sync(unsigned, int p) { return p != 0; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline double min(double a, double b) { return std::fmin(a, b); }
+static inline double max(double a, double b) { return std::fmax(a, b); }
+using std::fabs;
+using std::fmax;
+using std::isfinite;
+using std::log;

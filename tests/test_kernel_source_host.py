@@ -1,0 +1,109 @@
+"""The CUDA source itself against the reference, without a GPU: the lane-level device code (likelihood.cuh, search.cuh,
+place.cuh -- what k_append / k_merge / k_blen / ... / k_spr_search (variant 1) / k_place_samples execute per thread) is compiled
+for the host by tests/hostsim and run through the same golden-vector checks as the oracle, plus oracle comparisons of whole
+searches and placements.  The warp-cooperative code of the default search kernel (search_fsm.cuh) needs the hardware and is
+covered by the -m gpu tests; its two per-lane append forms (site-converged, queued-site) are checked here too."""
+import math
+
+import numpy as np
+import pytest
+
+import test_oracle_golden as og
+from golden_io import golden_names, load_golden
+from hostsim import KernelSourceOnHost
+from maple_b200.genome_list import pack_lists
+from maple_b200.model import MapleModel
+from oracle.oracle import Oracle
+from test_oracle_placement_golden import check_placements, place_params
+from tree_fixture import FAMILIES, search_params, searched_nodes, tree_arrays, tree_lists
+
+NAMES = golden_names()
+
+
+@pytest.fixture(scope="module", params=NAMES)
+def fx(request):
+    g = load_golden(request.param)
+    return g, KernelSourceOnHost(MapleModel.from_reference_snapshot(g["env"], g["model"]), with_root_tables=True)
+
+
+@pytest.mark.parametrize("check", ["test_append", "test_merge", "test_blen", "test_differ", "test_pass_branch", "test_shorten",
+                                   "test_root_vector", "test_prob_root", "test_tree_likelihood_from_parts"])
+def test_primitives_against_reference_vectors(fx, check):
+    getattr(og, check)(fx)  # the oracle's own golden checks, computing with the kernel source
+
+
+@pytest.mark.parametrize("which", ["sitewise", "q4"])
+def test_scan_append_forms_against_reference_vectors(fx, which):
+    g, hs = fx
+    L = g["lists"]
+    n = 0
+    for c in g["calls"]["appendProbNode"]:
+        got = hs.append_variant(which, L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"])
+        if c["out"] == float("-inf"):
+            assert got == float("-inf")
+        else:
+            assert abs(got - c["out"]) <= 1e-9
+        n += 1
+    assert n >= 100
+
+
+def _prefilled_lists(g, orc):
+    """probVectTotUp of zero-length children of the root filled ahead of the round (DeviceTree.prepare_search)."""
+    t, L = g["tree"], g["lists"]
+    fam = {f: [None if j is None else L[j] for j in t[f]] for f in FAMILIES}
+    root = t["root"]
+    if t["children"][root]:
+        for c, up in ((t["children"][root][0], "probVectUpRight"), (t["children"][root][1], "probVectUpLeft")):
+            if t["dist"][c] == 0.0 and fam["probVectTotUp"][c] is None and fam[up][root] is not None:
+                fam["probVectTotUp"][c] = orc.merge(fam[up][root], 0.0, False, fam["probVect"][c], 0.0, False, isUpDown=True)
+    flat = []
+    for f in FAMILIES:
+        flat.extend(fam[f])
+    return pack_lists(flat, g["env"]["lRef"], g["env"]["usingErrorRate"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_straight_line_search_source_matches_oracle_and_reference(name):
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    orc, hs = Oracle(model), KernelSourceOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
+    lists = _prefilled_lists(g, orc)
+    rec = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=8192)
+    ref = orc.search_batch(ta, lists, search_params(g), nodes, lazy_mode=1)
+    for f in ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
+        assert np.array_equal(rec[f], ref[f]), f
+    for f in ("bestCurrentLK", "bestScore", "improvement"):
+        assert np.max(np.abs(rec[f] - ref[f])) <= 1e-9, f
+    # and the reference's own searches wherever its lazy probVectTotUp fill (:7198-7200) plays no role
+    lazy = orc.search_batch(ta, tree_lists(g), search_params(g), nodes, lazy_mode=0)
+    by_node = {int(n): (r, bool(a == b)) for n, r, a, b in zip(nodes, rec, lazy, ref)}
+    t, checked = g["tree"], 0
+    for s in g["searches"]:
+        r, same = by_node[t["children"][s["node"]][s["child"]]]
+        if same:
+            assert r["status"] == 0 and r["bestNode"] == s["bestNode"] and r["phase1"] == s["phase1"]
+            assert [r["bLenTop"], r["bLenBottom"], r["bLenAppend"]] == [float(x) for x in s["blens"]]
+            assert r["bestScore"] == s["bestScore"] or abs(r["bestScore"] - s["bestScore"]) <= 1e-9
+            checked += 1
+    assert checked >= 0.8 * len(g["searches"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_placement_source_matches_reference(name):
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    samples = pack_lists([g["lists"][c["diffs"]] for c in g["placements"]], model.lRef, model.usingErrorRate)
+    hs = KernelSourceOnHost(model)
+    rec = hs.place_batch(tree_arrays(g), _prefilled_lists(g, Oracle(model)), place_params(g), samples, scratch_keys=8192)
+    check_placements(g, rec)
+    assert int(rec["missedMinors"].sum()) >= 0
+
+
+def test_scratch_exhaustion_is_reported_not_overrun():
+    g = load_golden("ex_unrest")
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs = KernelSourceOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
+    rec = hs.search_batch(ta, _prefilled_lists(g, Oracle(model)), search_params(g), nodes, scratch_keys=64)
+    assert (rec["status"] == 3).any() and not math.isnan(float(rec["bestCurrentLK"].sum()))
