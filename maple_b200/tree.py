@@ -40,9 +40,11 @@ class ListArena:
         self.key_tail = 0
         self.pay_tail = 0
         self.lRef, self.U = engine.model.lRef, int(engine.model.usingErrorRate)
+        self.epoch = 0  # bumped whenever the tables or streams move in memory: holders of raw pointers (maple_tree_bind) rebind
         self._bind()
 
     def _bind(self):
+        self.epoch += 1
         self.eng.lists = self
         rc = self.eng.lib.maple_lists_bind(self.eng.ctx, _dp(self.key), _dp(self.pay), _dp(self.key_start), _dp(self.pay_start), self.n)
         capi.check(self.eng.ctx, rc, "maple_lists_bind")
@@ -309,29 +311,31 @@ class DeviceTree:
         ids1 = self.d_child1.long()[internal] + FAM_LOWER * n
         root_id = self.root + FAM_LOWER * n
         mutStart = getattr(self, "mutStart", None)
-        if mutStart is not None:  # lists that must cross a local-reference branch get a temporary id
-            nmut = np.diff(mutStart)
-            hit = np.nonzero(reach & (nmut > 0))[0]
-            if hit.size:
-                d_ms = torch.from_numpy(mutStart).to(dev)
-                d_mu = torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
-                r = eng.pass_branch_batch(t64(hit) + FAM_LOWER * n, hit, np.ones(hit.size, np.uint8), d_ms, d_mu)
-                first = A.add_ids(hit.size)
-                A.store(torch.arange(first, first + hit.size, device=dev), r.key, r.pay, r.key_start, r.pay_start, r.nkeys, r.npay)
-                remap = torch.arange(4 * n, device=dev)
-                remap[t64(hit) + FAM_LOWER * n] = torch.arange(first, first + hit.size, device=dev)
-                ids0, ids1 = remap[ids0], remap[ids1]
-                root_id = int(remap[root_id].item())
-        total = 0.0
-        if internal.numel():
-            c0, c1 = self.d_child0.long()[internal], self.d_child1.long()[internal]
-            nm = torch.from_numpy(self.numMinor).to(dev)
-            r = eng.merge_batch(ids0.int(), self.d_dist[c0], self.d_isTip[c0], ids1.int(), self.d_dist[c1], self.d_isTip[c1],
-                                torch.full((internal.numel(),), capi.MAPLE_MERGE_RETURN_LK, dtype=torch.uint8, device=dev), nm[c0], nm[c1])
-            if bool((r.status != 0).any().item()):
-                raise capi.MapleError("inconsistent lower genome list creation in tree_likelihood (the reference raises, :9762-9764)")
-            total += float(r.lk.sum().item())
-        total += float(eng.prob_root_batch([root_id]).cpu()[0])
+        mark = A.mark()
+        try:
+            if mutStart is not None:  # lists that must cross a local-reference branch get a temporary id
+                nmut = np.diff(mutStart)
+                hit = np.nonzero(reach & (nmut > 0))[0]
+                if hit.size:
+                    d_ms = torch.from_numpy(mutStart).to(dev)
+                    d_mu = torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
+                    tmp = A.add_lists(eng.pass_branch_batch(t64(hit) + FAM_LOWER * n, hit, np.ones(hit.size, np.uint8), d_ms, d_mu))
+                    remap = torch.arange(4 * n, device=dev)
+                    remap[t64(hit) + FAM_LOWER * n] = tmp
+                    ids0, ids1 = remap[ids0], remap[ids1]
+                    root_id = int(remap[root_id].item())
+            total = 0.0
+            if internal.numel():
+                c0, c1 = self.d_child0.long()[internal], self.d_child1.long()[internal]
+                nm = torch.from_numpy(self.numMinor).to(dev)
+                r = eng.merge_batch(ids0.int(), self.d_dist[c0], self.d_isTip[c0], ids1.int(), self.d_dist[c1], self.d_isTip[c1],
+                                    torch.full((internal.numel(),), capi.MAPLE_MERGE_RETURN_LK, dtype=torch.uint8, device=dev), nm[c0], nm[c1])
+                if bool((r.status != 0).any().item()):
+                    raise capi.MapleError("inconsistent lower genome list creation in tree_likelihood (the reference raises, :9762-9764)")
+                total += float(r.lk.sum().item())
+            total += float(eng.prob_root_batch([root_id]).cpu()[0])
+        finally:
+            A.release(mark)  # the re-referenced copies were temporaries
         return total
 
     # ------------------------------------------------------------------ traverseTreeToOptimizeBranchLengths(fastPass=True) (:8727)
@@ -445,11 +449,14 @@ class DeviceTree:
         rc = eng.lib.maple_tree_bind(eng.ctx, n, root, _dp(self.d_up), _dp(self.d_child0), _dp(self.d_child1), _dp(self.d_dist),
                                      _dp(self.d_isTip), _dp(self._d_mutStart), _dp(self._d_mut), _dp(A.nkeys), _dp(A.npay))
         capi.check(eng.ctx, rc, "maple_tree_bind")
+        self._bound_epoch = A.epoch
 
     def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0, cycles=None):
         """Run the searches of the listed nodes; returns a device tensor of raw records [n, 64 bytes] viewed as uint8
         and a helper to read it as a numpy record array."""
         eng, dev = self.eng, self.eng.device
+        if getattr(self, "_bound_epoch", None) != self.arena.epoch:
+            self.prepare_search()  # never bound, or the arena's tables moved since (temporary lists added / released)
         nodes = torch.as_tensor(nodes, dtype=torch.int32, device=dev).contiguous()
         out = torch.zeros((nodes.numel(), 64), dtype=torch.uint8, device=dev)
         rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), nodes.numel(), _dp(nodes), _dp(out), int(scratch_keys),

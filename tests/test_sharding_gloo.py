@@ -86,6 +86,69 @@ def test_two_ranks_agree_with_one():
     assert got[0][2] == got[1][2] == np.ascontiguousarray(one).tobytes()
 
 
+def _place_problem():
+    from maple_b200.genome_list import pack_lists
+    model, ta, packed, params, nodes = _problem()
+    from maple_b200.synthetic import generate
+    d = generate(120, lRef=3000, mean_diffs=8.0, rate_variation=True, seed=7)
+    samples = []
+    for i, v in enumerate(d.tip_lists[:37]):  # new samples: placed tips with one more substitution (every third one unchanged)
+        v = [tuple(e) for e in v]
+        if i % 3:
+            prev = 0
+            for j, e in enumerate(v):
+                end = e[1] if e[0] in (4, 5) else prev + 1
+                if e[0] == 4 and len(e) == 2 and end - prev >= 3 + i:
+                    pos = prev + 2 + i  # 1-based position of the new substitution, inside this R run
+                    ref = int(d.model.refIdx[pos - 1])
+                    v[j:j + 1] = [(4, pos - 1), ((ref + 1 + i % 3) % 4, ref), (4, end)]
+                    break
+                prev = end
+        samples.append(v)
+    pp = {"strictStopRules": 0, "allowedFails": 3, "deeperSearchForLongBranches": 0, "onlyFindIdentical": 0,
+          "thresholdLogLK": params["thresholdLogLKtopology"], "thresholdLogLKoptimization": params["thresholdLogLKoptimizationTopology"],
+          "thresholdLogLKconsecutivePlacement": 0.01, "effectivelyNon0BLen": params["effectivelyNon0BLen"],
+          "BLenThresholdDeeperSearch": params["BLenThresholdDeeperSearch"], "oneMutBLen": 1.0 / d.model.lRef}
+    return model, ta, packed, pp, samples
+
+
+def _place_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from maple_b200.genome_list import pack_lists
+        from oracle.oracle import Oracle
+        model, ta, packed, pp, samples = _place_problem()
+        mine = shard_nodes(np.arange(len(samples)), rank, world)
+        rec = Oracle(model).place_batch(ta, packed, pp, pack_lists([samples[i] for i in mine], model.lRef, model.usingErrorRate))
+        raw = torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8).reshape(len(mine), 48).copy())
+        allrec = gather_records(raw, len(samples), rank, world, fields=capi.PLACE_RESULT_FIELDS)
+        q.put((rank, allrec.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_placement_batch_two_ranks_agree_with_one():
+    """Samples of a placement batch are the sharded unit; same exchange, 48-byte records."""
+    from maple_b200.genome_list import pack_lists
+    from oracle.oracle import Oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_place_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    model, ta, packed, pp, samples = _place_problem()
+    one = Oracle(model).place_batch(ta, packed, pp, pack_lists(samples, model.lRef, model.usingErrorRate))
+    assert got[0][1] == got[1][1] == np.ascontiguousarray(one).tobytes()
+    assert (one["status"] == 0).sum() > 10 and (one["status"] == 1).sum() > 5 and (one["phase1"][one["status"] == 0] > 0).all()
+
+
 def test_shard_nodes_is_the_round_robin_partition():
     nodes = np.arange(11, dtype=np.int32) * 3
     parts = [shard_nodes(nodes, r, 4) for r in range(4)]
