@@ -210,6 +210,12 @@ typedef struct {
 int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, const int32_t* sampleLists, maple_place_result* out,
                       int32_t scratch_keys_per_sample, void* stream);
 
+/* Which kernel maple_place_batch launches: 0 (default) = one sample per thread, the straight-line walk; 1 = one sample per
+ * warp: windows of the pre-order scored one node per lane, leaf comparisons one per lane, refinement entries one per lane
+ * (trees with MAT mutations, --deeperSearchForLongBranches and a few rare shapes run the straight-line walk inside that
+ * kernel).  Same results; a sample that exhausts the per-lane scratch of variant 1 reports status 3 like variant 0. */
+int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant);
+
 /* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state
  * machine, with subtrees whose lists are all stored ones scanned by the whole warp; 1 = the straight-line
  * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans with the queued-site form of appendProbNode and the node-by-node window replay

@@ -34,6 +34,7 @@ SIGNATURES = {
     "maple_tree_bind": (C.c_int, [_P, _I32, _I32] + [_P] * 9),
     "maple_spr_search_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P]),
     "maple_place_batch": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _P]),
+    "maple_ctx_set_place_variant": (C.c_int, [_P, _I32]),
     "maple_ctx_set_search_variant": (C.c_int, [_P, _I32]),
     "maple_ctx_set_scan_min_size": (C.c_int, [_P, _I32]),
     "maple_search_stats": (C.c_int, [_P, _I32, _P]),

@@ -16,6 +16,7 @@
 #include "search.cuh"
 #include "search_fsm.cuh"
 #include "place.cuh"
+#include "place_scan.cuh"
 
 using namespace maple;
 
@@ -52,6 +53,7 @@ struct maple_ctx {
     void* retryScratch = nullptr;  // node list + scratch of the on-device retry of overflowed searches
     size_t retryScratchBytes = 0;
     unsigned long long* retryCounters = nullptr;  // [0] overflowed searches, [1] work counter of the retry launch
+    int placeVariant = 0;   // 0 = one sample per thread (place.cuh), 1 = one sample per warp with windowed scans (place_scan.cuh)
     int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans with the queued-site appendProbNode and the node-by-node replay
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
@@ -251,41 +253,7 @@ __global__ void __launch_bounds__(256) k_collect_overflow(int64_t n, const Searc
 __global__ void __launch_bounds__(256) k_scan_prepare(const __grid_constant__ DevTree T, double eff, ScanNode* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T.nNodes) return;
-    ScanNode r;
-    const int node = T.order[i];
-    r.node = node;
-    r.keyOff = r.payOff = r.cnt = r.flags = 0;
-    if (node < 0 || T.pre[node] != i) {  // positions past the reachable nodes
-        r.node = -1; r.parentPos = -1; r.size = 1; r.depth = 0;
-        out[i] = r;
-        return;
-    }
-    const int up = T.up[node];
-    const int64_t nN = T.nNodes;
-    r.parentPos = up >= 0 ? T.pre[up] : -1;
-    r.size = T.size[node];
-    r.depth = T.depth[node];
-    uint32_t fl = 0;
-    if (up >= 0 && (T.dist[node] > eff || T.up[up] < 0)) fl |= SN_ELIG;
-    if (up >= 0 && T.keyStart[(T.child0[up] == node ? 1 : 2) * nN + up] >= 0) fl |= SN_PUSHED;
-    if (T.child0[node] >= 0) fl |= SN_INNER;
-    const int64_t id = 3 * nN + node, ks = T.keyStart[id];
-    if (ks >= 0) {
-        fl |= SN_TOT;
-        const int64_t ps = T.payStart[id];
-        const uintptr_t ak = reinterpret_cast<uintptr_t>(T.key + ks), ap = reinterpret_cast<uintptr_t>(T.pay + ps);
-        if (T.npay && ((ak | ap) & 15) == 0 && (ks >> 2) < (int64_t(1) << 32) && (ps >> 1) < (int64_t(1) << 32)) {
-            const int nk4 = (T.nkeys[id] + 3) >> 2, np2 = (T.npay[id] + 1) >> 1;
-            if (nk4 < 65536 && np2 < 65536) {
-                fl |= SN_STAGE;
-                r.keyOff = uint32_t(ks >> 2);
-                r.payOff = uint32_t(ps >> 1);
-                r.cnt = uint32_t(nk4) | (uint32_t(np2) << 16);
-            }
-        }
-    }
-    r.flags = fl;
-    out[i] = r;
+    out[i] = make_scan_node(T, eff, i);
 }
 
 // one SPR search per thread; threads pull the next pruned node from a global counter (searches differ ~10x in length)
@@ -484,6 +452,48 @@ __global__ void __launch_bounds__(kSearchThreads) k_place_samples(const __grid_c
         if (ks < 0) { r.bestNode = -1; r.status = 2; r.phase1 = r.missedMinors = 0; r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0; }
         else place_sample(sm, T, pp, LRef{T.key + ks, T.pay + T.payStart[id], T.nkeys[id]}, s, stack, stackCap, best, bestCap, r);
         out[i] = r;
+    }
+}
+
+// one new-sample placement per WARP (place_scan.cuh); warps pull samples from a global counter
+constexpr int kPlaceWarpThreads = 128;
+__global__ void __launch_bounds__(kPlaceWarpThreads) k_place_samples_warp(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+                                                                          const __grid_constant__ PlaceParams pp, int64_t n,
+                                                                          const int32_t* __restrict__ sampleLists, PlaceResult* __restrict__ out,
+                                                                          char* scratch, size_t warpBytes, unsigned laneK, unsigned laneP,
+                                                                          unsigned laneA, int stackCap, int bestCap, unsigned long long* counter) {
+    __shared__ DevModel sm;
+    __shared__ PlaceWarp warps[kPlaceWarpThreads / 32];
+    __shared__ long long ticket[kPlaceWarpThreads / 32];
+    stage_model(sm, gm);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    PlaceWarp& W = warps[wid];
+    char* base = scratch + (blockIdx.x * (size_t)(kPlaceWarpThreads / 32) + wid) * warpBytes;
+    PlaceWarpScratch ws;
+    ws.laneK = laneK; ws.laneP = laneP; ws.laneA = laneA; ws.bestCap = bestCap; ws.stackCap = stackCap;
+    ws.pay = reinterpret_cast<double*>(base);
+    ws.ais = ws.pay + 32 * (size_t)laneP;
+    ws.diffPay = ws.ais + 32 * (size_t)laneA;
+    ws.eval = reinterpret_cast<PlaceEval*>(ws.diffPay + 6 * (size_t)laneK);
+    ws.gpath = reinterpret_cast<PlacePath*>(ws.eval + bestCap);
+    ws.best = reinterpret_cast<PlaceBest*>(ws.gpath + stackCap);
+    ws.stack = reinterpret_cast<PlaceStackE*>(ws.best + bestCap);
+    ws.key = reinterpret_cast<uint32_t*>(ws.stack + stackCap);
+    ws.diffKey = ws.key + 32 * (size_t)laneK;
+    ws.evalRc = reinterpret_cast<int*>(ws.diffKey + laneK);
+    for (;;) {
+        if (lane == 0) ticket[wid] = (long long)atomicAdd(counter, 1ULL);
+        __syncwarp();
+        const long long i = ticket[wid];
+        __syncwarp();
+        if (i >= n) break;
+        const int64_t id = sampleLists[i];
+        const int64_t ks = T.keyStart[id];
+        PlaceResult r;
+        r.bestNode = -1; r.status = 2; r.phase1 = r.missedMinors = 0; r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+        if (ks >= 0) place_sample_warp(sm, T, pp, LRef{T.key + ks, T.pay + T.payStart[id], T.nkeys[id]}, W, ws, r);
+        if (lane == 0) out[i] = r;
+        __syncwarp();
     }
 }
 
@@ -1021,6 +1031,39 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     const int stackCap = ctx->treeHeight + 8, bestCap = (int)(capK / 4 > 1024 ? capK / 4 : 1024);  // bestNodes entries per sample
     const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
                               (size_t)capK * 4 + 15) & ~size_t(15);
+    if (ctx->placeVariant == 1 && T.order) {
+        // one warp per sample: 32 lane slices of scratch (refinement entries run one per lane), the sample list, bestNodes and
+        // its refinement results, per-depth states, and the stack of the straight-line fallback
+        const unsigned laneK = 512, laneP = 6 * 512, laneA = 512;
+        const int bestCapW = (int)(capK / 4 > 1024 ? capK / 4 : 1024);
+        const size_t warpBytes = ((size_t)32 * laneP * 8 + (size_t)32 * laneA * 8 + (size_t)6 * laneK * 8 + (size_t)bestCapW * sizeof(PlaceEval) +
+                                  (size_t)stackCap * sizeof(PlacePath) + (size_t)bestCapW * sizeof(PlaceBest) +
+                                  (size_t)stackCap * sizeof(PlaceStackE) + (size_t)32 * laneK * 4 + (size_t)laneK * 4 + (size_t)bestCapW * 4 + 63) & ~size_t(63);
+        int perSM = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp, kPlaceWarpThreads, 0));
+        if (perSM < 1) perSM = 1;
+        const int warpsPerBlock = kPlaceWarpThreads / 32;
+        int64_t nBlocks = (int64_t)ctx->numSMs * perSM;
+        if (nBlocks * warpsPerBlock > n) nBlocks = (n + warpsPerBlock - 1) / warpsPerBlock;
+        const size_t needW = warpBytes * (size_t)nBlocks * warpsPerBlock + 256;
+        if (needW > ctx->placeScratchBytes) {
+            cudaFree(ctx->placeScratch);
+            ctx->placeScratch = nullptr;
+            ctx->placeScratchBytes = 0;
+            CK(cudaMalloc(&ctx->placeScratch, needW));
+            ctx->placeScratchBytes = needW;
+        }
+        if (!ctx->searchCounter) CK(cudaMalloc((void**)&ctx->searchCounter, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+        k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, pp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
+        ctx->launches++;
+        k_place_samples_warp<<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
+                                                                                          (char*)ctx->placeScratch, warpBytes, laneK, laneP, laneA,
+                                                                                          stackCap, bestCapW, ctx->searchCounter);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return MAPLE_OK;
+    }
     int blocksPerSM = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_place_samples, kSearchThreads, 0));
     if (blocksPerSM < 1) blocksPerSM = 1;
@@ -1042,6 +1085,12 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
                                                                         ctx->searchCounter);
     ctx->launches++;
     CK(cudaGetLastError());
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant) {
+    if (!ctx || variant < 0 || variant > 1) return MAPLE_E_ARG;
+    ctx->placeVariant = variant;
     return MAPLE_OK;
 }
 

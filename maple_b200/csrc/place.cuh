@@ -89,6 +89,37 @@ __device__ __noinline__ int dev_is_minor(int lRef, LRef a, LRef b, bool onlyFind
     return found2bigger ? 2 : 1;
 }
 
+// One entry of the refinement loop (:8109-8187): the three branch lengths of a placement on the branch above `node` are
+// re-optimised and the placement is scored again.  Entries are independent of one another (the loop only keeps the last
+// best one).  Returns 0, or the status the placement ends with (2: the reference would raise, 3: scratch exhausted).
+struct PlaceEval {
+    double score, top, bottom, append;
+};
+
+__device__ int place_refine_entry(const DevModel& m, const DevTree& t, ScratchD& s, int node, LRef d, PlaceEval& e) {
+    const unsigned mk = s.topK, mp = s.topP;
+    const LRef upVect = up_list_for(m, t, s, node);
+    const bool isTip = t.isTip[node] != 0;
+    const LRef pv = tree_list(t, 0, node), tot = tree_list(t, 3, node);
+    if (!upVect.k || !pv.k || !tot.k) return s.err ? s.err : 2;
+    const double bestAppendingLength = s_blen(m, s, tot, d, true);
+    const LRef midLower = s_merge(m, s, pv, t.dist[node] / 2, isTip, d, bestAppendingLength, true, false);
+    if (!midLower.k) return s.err ? s.err : 2;
+    const double bestTopLength = s_blen(m, s, upVect, midLower, false);
+    const LRef midTop = s_merge(m, s, upVect, bestTopLength, false, d, bestAppendingLength, true, true);
+    if (!midTop.k) return s.err ? s.err : 2;
+    const double bestBottomLength = s_blen(m, s, midTop, pv, isTip);
+    const LRef newMid = s_merge(m, s, upVect, bestTopLength, false, pv, bestBottomLength, isTip, true);
+    if (!newMid.k) return s.err ? s.err : 2;
+    const double appendingCost = f_append(m, newMid, d, true, bestAppendingLength);
+    const double initialCost = f_append(m, upVect, pv, isTip, t.dist[node]);
+    const double newPartialCost = f_append(m, upVect, pv, isTip, bestBottomLength + bestTopLength);
+    e.score = appendingCost + newPartialCost - initialCost;
+    e.top = bestTopLength; e.bottom = bestBottomLength; e.append = bestAppendingLength;
+    s.topK = mk; s.topP = mp;
+    return s.err;
+}
+
 __device__ void place_sample(const DevModel& m, const DevTree& t, const PlaceParams& pp, LRef in, ScratchD& s, PlaceStackE* stack, int stackCap,
                              PlaceBest* best, int bestCap, PlaceResult& r) {
     r.bestNode = -1; r.status = 0; r.phase1 = 0; r.missedMinors = 0;
@@ -191,33 +222,14 @@ __device__ void place_sample(const DevModel& m, const DevTree& t, const PlacePar
     double bestScore = bestLKdiff;
     for (int i = 0; i < nBest; i++) {
         if (!(best[i].score >= bestLKdiff - pp.thresholdLogLKoptimization)) continue;
-        const int node = best[i].t1;
-        const LRef d = best[i].diffs;
-        const unsigned mk = s.topK, mp = s.topP;
-        const LRef upVect = up_list_for(m, t, s, node);
-        const bool isTip = t.isTip[node] != 0;
-        const LRef pv = tree_list(t, 0, node), tot = tree_list(t, 3, node);
-        if (!upVect.k || !pv.k || !tot.k) PLACE_FAIL(s.err ? s.err : 2);
-        const double bestAppendingLength = s_blen(m, s, tot, d, true);
-        const LRef midLower = s_merge(m, s, pv, t.dist[node] / 2, isTip, d, bestAppendingLength, true, false);
-        if (!midLower.k) PLACE_FAIL(s.err ? s.err : 2);
-        const double bestTopLength = s_blen(m, s, upVect, midLower, false);
-        const LRef midTop = s_merge(m, s, upVect, bestTopLength, false, d, bestAppendingLength, true, true);
-        if (!midTop.k) PLACE_FAIL(s.err ? s.err : 2);
-        const double bestBottomLength = s_blen(m, s, midTop, pv, isTip);
-        const LRef newMid = s_merge(m, s, upVect, bestTopLength, false, pv, bestBottomLength, isTip, true);
-        if (!newMid.k) PLACE_FAIL(s.err ? s.err : 2);
-        const double appendingCost = f_append(m, newMid, d, true, bestAppendingLength);
-        const double initialCost = f_append(m, upVect, pv, isTip, t.dist[node]);
-        const double newPartialCost = f_append(m, upVect, pv, isTip, bestBottomLength + bestTopLength);
-        const double optimizedScore = appendingCost + newPartialCost - initialCost;
-        if (optimizedScore >= bestScore) {
-            bestNode = node;
-            bestScore = optimizedScore;
-            bTop = bestTopLength; bBottom = bestBottomLength; bAppend = bestAppendingLength;
+        PlaceEval e;
+        const int rc = place_refine_entry(m, t, s, best[i].t1, best[i].diffs, e);
+        if (rc) PLACE_FAIL(rc);
+        if (e.score >= bestScore) {
+            bestNode = best[i].t1;
+            bestScore = e.score;
+            bTop = e.top; bBottom = e.bottom; bAppend = e.append;
         }
-        s.topK = mk; s.topP = mp;
-        if (s.err) PLACE_FAIL(s.err);
     }
 #undef PLACE_FAIL
     if (bestScore == -INFINITY) bestScore = originalLKdiff;

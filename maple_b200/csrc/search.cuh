@@ -59,6 +59,7 @@ constexpr uint32_t SN_TOT = 2;     // probVectTotUp exists
 constexpr uint32_t SN_PUSHED = 4;  // the parent's upper list towards this node exists, so the walk pushes this node (:7120, :7157)
 constexpr uint32_t SN_INNER = 8;   // has children
 constexpr uint32_t SN_STAGE = 16;  // list is 16-byte aligned and small enough for the offsets above
+constexpr uint32_t SN_LONG = 32;   // dist > effectivelyNon0BLen: the branch a new sample is scored against (:8013), whatever its parent
 
 struct SearchParams {
     int strictTopologyStopRules, allowedFailsTopology, deeperSearchForLongBranches, reserved;
@@ -117,6 +118,45 @@ __device__ __forceinline__ LRef sc_commit(ScratchD& s, int nk, int np) {
     LRef r{s.key + s.topK, s.pay + s.topP, nk};
     s.topK += (unsigned(nk) + 3u) & ~3u;
     s.topP += (unsigned(np) + 1u) & ~1u;
+    return r;
+}
+
+// The ScanNode record of pre-order position i for the bound tree and arena (k_scan_prepare: one thread per position).
+__device__ __forceinline__ ScanNode make_scan_node(const DevTree& T, double eff, int i) {
+    ScanNode r;
+    const int node = T.order[i];
+    r.node = node;
+    r.keyOff = r.payOff = r.cnt = r.flags = 0;
+    if (node < 0 || T.pre[node] != i) {  // positions past the reachable nodes
+        r.node = -1; r.parentPos = -1; r.size = 1; r.depth = 0;
+        return r;
+    }
+    const int up = T.up[node];
+    const int64_t nN = T.nNodes;
+    r.parentPos = up >= 0 ? T.pre[up] : -1;
+    r.size = T.size[node];
+    r.depth = T.depth[node];
+    uint32_t fl = 0;
+    if (up >= 0 && (T.dist[node] > eff || T.up[up] < 0)) fl |= SN_ELIG;
+    if (up >= 0 && T.dist[node] > eff) fl |= SN_LONG;
+    if (up >= 0 && T.keyStart[(T.child0[up] == node ? 1 : 2) * nN + up] >= 0) fl |= SN_PUSHED;
+    if (T.child0[node] >= 0) fl |= SN_INNER;
+    const int64_t id = 3 * nN + node, ks = T.keyStart[id];
+    if (ks >= 0) {
+        fl |= SN_TOT;
+        const int64_t ps = T.payStart[id];
+        const uintptr_t ak = reinterpret_cast<uintptr_t>(T.key + ks), ap = reinterpret_cast<uintptr_t>(T.pay + ps);
+        if (T.npay && ((ak | ap) & 15) == 0 && (ks >> 2) < (int64_t(1) << 32) && (ps >> 1) < (int64_t(1) << 32)) {
+            const int nk4 = (T.nkeys[id] + 3) >> 2, np2 = (T.npay[id] + 1) >> 1;
+            if (nk4 < 65536 && np2 < 65536) {
+                fl |= SN_STAGE;
+                r.keyOff = uint32_t(ks >> 2);
+                r.payOff = uint32_t(ps >> 1);
+                r.cnt = uint32_t(nk4) | (uint32_t(np2) << 16);
+            }
+        }
+    }
+    r.flags = fl;
     return r;
 }
 

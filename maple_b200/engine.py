@@ -133,6 +133,11 @@ class MapleEngine:
         """0 = warp-converged state-machine search kernel (default), 1 = straight-line kernel (A/B measurements)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_search_variant(self.ctx, int(variant)), "maple_ctx_set_search_variant")
 
+    def set_place_variant(self, variant: int):
+        """0 = one new sample per thread (default), 1 = one per warp with windowed scans (place_scan.cuh); same results."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_place_variant(self.ctx, int(variant)), "maple_ctx_set_place_variant")
+        self.place_variant = int(variant)
+
     def set_scan_min_size(self, n: int):
         capi.check(self.ctx, self.lib.maple_ctx_set_scan_min_size(self.ctx, int(n)), "maple_ctx_set_scan_min_size")
 

@@ -483,11 +483,18 @@ class DeviceTree:
 
         rec = run(ids, scratch_keys)
         retry, keys = np.nonzero(rec["status"] == 3)[0], max(int(scratch_keys), 4096)
-        while retry.size and keys < (1 << 22):  # per-sample scratch (lists or the bestNodes table) exhausted: again with 8x
-            keys *= 8
-            again = run(ids[torch.as_tensor(retry, device=dev)].contiguous(), keys)
-            rec[retry] = again
-            retry = retry[again["status"] == 3]
+        variant = getattr(eng, "place_variant", 0)
+        try:
+            while retry.size and keys < (1 << 22):  # per-sample scratch (lists or the bestNodes table) exhausted: again with 8x
+                keys *= 8
+                if variant != 0:  # the retries go through the one-sample-per-thread kernel, whose whole scratch scales with `keys`
+                    eng.set_place_variant(0)
+                again = run(ids[torch.as_tensor(retry, device=dev)].contiguous(), keys)
+                rec[retry] = again
+                retry = retry[again["status"] == 3]
+        finally:
+            if variant != 0:
+                eng.set_place_variant(variant)
         return rec
 
     @staticmethod

@@ -5,13 +5,15 @@ import ctypes as C
 import os
 import subprocess
 
-from oracle.oracle import Oracle, _p, declare
+import numpy as np
+
+from oracle.oracle import PLACE_RESULT_DTYPE, Oracle, OrPlaceParams, _p, declare
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "maple_b200", "csrc")
 LIB = os.path.join(HERE, "libhostsim.so")
 SOURCES = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "shim", "cuda_runtime.h")] + [
-    os.path.join(CSRC, f) for f in ("glist.cuh", "likelihood.cuh", "search.cuh", "place.cuh")]
+    os.path.join(CSRC, f) for f in ("glist.cuh", "likelihood.cuh", "search.cuh", "place.cuh", "place_scan.cuh")]
 _lib = None
 
 
@@ -30,6 +32,8 @@ def lib():
         for f in (L.hs_append_sitewise, L.hs_append_q4):
             f.restype = C.c_double
             f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_double]
+        L.hs_place_batch_scan.restype = None
+        L.hs_place_batch_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -46,3 +50,14 @@ class KernelSourceOnHost(Oracle):
         a, b = self._one(P), self._one(C_)
         f = {"sitewise": self.L.hs_append_sitewise, "q4": self.L.hs_append_q4}[which]
         return f(self.mp, _p(a.key), _p(a.pay), _p(b.key), _p(b.pay), int(bool(isTipC)), float(bLen))
+
+    def place_batch_scan(self, tree: dict, lists, params: dict, samples, scratch_keys: int = 4096):
+        """Placement variant 1 (one sample per warp, place_scan.cuh), lanes emulated in turn."""
+        t, keep = self._tree_struct(tree, lists)
+        pp = OrPlaceParams()
+        for k, v in params.items():
+            setattr(pp, k, v)
+        out = np.zeros(len(samples), dtype=PLACE_RESULT_DTYPE)
+        self.L.hs_place_batch_scan(self.mp, C.addressof(t), C.addressof(pp), len(samples), _p(samples.key), _p(samples.pay),
+                                   _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(lists.npay), _p(out))
+        return out

@@ -5,7 +5,7 @@
 // a*b+c must round twice like CPython).  Never loaded by anything under maple_b200/.
 #include "cuda_runtime.h"
 
-#include "place.cuh"
+#include "place_scan.cuh"
 
 #include <vector>
 
@@ -199,6 +199,61 @@ void or_shorten_slots(const DevModel* m, int64_t n, uint32_t* key, double* pay, 
         or_shorten(m, key + keyStart[i], pay + payStart[i], key + keyStart[i], pay + payStart[i], &a, &b);
         nk[i] = a;
         np_[i] = b;
+    }
+}
+
+// k_place_samples_warp (placement variant 1): place_scan.cuh with the lanes of every phase run in turn.  The derived tree
+// arrays are what maple_tree_bind computes on the host, the ScanNode records what k_scan_prepare computes per position.
+void hs_place_batch_scan(const DevModel* m, const OrTree* t, const PlaceParams* pp, int64_t n, const uint32_t* key, const double* pay,
+                         const int64_t* keyStart, const int64_t* payStart, const int32_t* nkeys, int64_t scratchKeys, const int32_t* npay,
+                         PlaceResult* out) {
+    DevTree T = dev_tree(t);
+    const size_t N = (size_t)t->nNodes;
+    std::vector<int32_t> order(N, -1), pre(N, -1), size(N, 1), depth(N, 0), st{t->root};
+    std::vector<uint8_t> mutBelow(N, 0);
+    size_t cnt = 0;
+    int height = 0;
+    while (!st.empty()) {
+        const int v = st.back();
+        st.pop_back();
+        pre[v] = (int32_t)cnt;
+        order[cnt++] = v;
+        if (depth[v] > height) height = depth[v];
+        if (t->child0[v] >= 0) {
+            depth[t->child0[v]] = depth[t->child1[v]] = depth[v] + 1;
+            st.push_back(t->child0[v]);
+            st.push_back(t->child1[v]);
+        }
+    }
+    for (size_t i = cnt; i-- > 1;) {
+        const int v = order[i], p = t->up[v];
+        size[p] += size[v];
+        if (mutBelow[v] || (t->mutStart && t->mutStart[v + 1] > t->mutStart[v])) mutBelow[p] = 1;
+    }
+    for (size_t i = cnt; i < N; i++) order[i] = -1;
+    T.order = order.data(); T.pre = pre.data(); T.size = size.data(); T.depth = depth.data(); T.mutBelow = mutBelow.data();
+    T.npay = npay;
+    std::vector<ScanNode> scan(N);
+    T.scan = scan.data();
+    for (size_t i = 0; i < N; i++) scan[i] = make_scan_node(T, pp->effectivelyNon0BLen, (int)i);
+    PlaceWarpScratch ws;
+    ws.laneK = 512; ws.laneP = 6 * 512; ws.laneA = 512;
+    const unsigned capK = (unsigned)scratchKeys;
+    ws.bestCap = (int)(capK / 4 > 1024 ? capK / 4 : 1024);
+    ws.stackCap = height + 8;
+    std::vector<double> payS(32 * (size_t)ws.laneP), aisS(32 * (size_t)ws.laneA), diffPay(6 * (size_t)ws.laneK);
+    std::vector<uint32_t> keyS(32 * (size_t)ws.laneK + 64), diffKey(ws.laneK + 64);
+    std::vector<PlaceBest> best(ws.bestCap);
+    std::vector<PlaceEval> eval(ws.bestCap);
+    std::vector<int> evalRc(ws.bestCap);
+    std::vector<PlacePath> gpath(ws.stackCap);
+    std::vector<PlaceStackE> stack(ws.stackCap);
+    ws.pay = payS.data(); ws.ais = aisS.data(); ws.key = keyS.data(); ws.best = best.data(); ws.eval = eval.data(); ws.evalRc = evalRc.data();
+    ws.gpath = gpath.data(); ws.stack = stack.data(); ws.diffKey = diffKey.data(); ws.diffPay = diffPay.data();
+    PlaceWarp W;
+    for (int64_t i = 0; i < n; i++) {
+        memset(&W, 0, sizeof W);
+        place_sample_warp(*m, T, *pp, LRef{key + keyStart[i], pay + payStart[i], nkeys[i]}, W, ws, out[i]);
     }
 }
 

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <math.h>
 
+#define MAPLE_HOST_LANES 1  // place_scan.cuh: the lanes of a phase run one after the other
 #define __device__
 #define __host__
 #define __global__
