@@ -37,6 +37,7 @@ struct maple_ctx {
     bool haveTree = false;
     int32_t* treeDerived = nullptr;  // order | pre | size | depth (int32[nNodes] each) then mutBelow (uint8[nNodes]); owned
     int treeHeight = 0;
+    bool treeHasMut = false;  // some reachable node carries MAT mutations
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
     int lanesPerWarp = 0;               // searches per warp (1..32); 0 = chosen per launch from the number of searches
@@ -874,6 +875,7 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
     t.mutBelow = reinterpret_cast<const uint8_t*>(t.depth + n);
     t.scan = reinterpret_cast<const ScanNode*>((reinterpret_cast<uintptr_t>(ctx->treeDerived + der.size()) + 31) & ~uintptr_t(31));
     ctx->treeHeight = height;
+    ctx->treeHasMut = mutStart && (mutBelow[root] || hMs[root + 1] > hMs[root]);
     ctx->haveTree = true;
     return MAPLE_OK;
 }
@@ -1031,7 +1033,8 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     const int stackCap = ctx->treeHeight + 8, bestCap = (int)(capK / 4 > 1024 ? capK / 4 : 1024);  // bestNodes entries per sample
     const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
                               (size_t)capK * 4 + 15) & ~size_t(15);
-    if (ctx->placeVariant == 1 && T.order) {
+    // Variant 1 covers what its scans cover; everything else would run on one lane per warp there, so it goes to variant 0
+    if (ctx->placeVariant == 1 && T.order && !ctx->treeHasMut && !pp.deeperSearchForLongBranches) {
         // one warp per sample: 32 lane slices of scratch (refinement entries run one per lane), the sample list, bestNodes and
         // its refinement results, per-depth states, and the stack of the straight-line fallback
         const unsigned laneK = 512, laneP = 6 * 512, laneA = 512;

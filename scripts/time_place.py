@@ -11,6 +11,7 @@ from maple_b200.tree import DeviceTree
 
 nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 nnew = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]  # 0 = sample per thread, 1 = sample per warp
 d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=True)
 eng = MapleEngine(d.model, 0)
 tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
@@ -38,11 +39,19 @@ p = capi.PlaceParams()
 p.strictStopRules, p.allowedFails, p.deeperSearchForLongBranches, p.onlyFindIdentical = 0, 5, 0, 0
 p.thresholdLogLK, p.thresholdLogLKoptimization, p.thresholdLogLKconsecutivePlacement = 18.0 * L, 1.0 * L, 1.0
 p.effectivelyNon0BLen, p.BLenThresholdDeeperSearch, p.oneMutBLen = 1.0 / (10 * lRef), (L + 5) / lRef, 1.0 / lRef
-for rep in range(2):
-    torch.cuda.synchronize()
-    t0 = time.time()
-    rec = tree.place_samples(samples, p)
-    dt = time.time() - t0
-    print("rep %d: %d samples in %.2f s (incl. upload and re-bind) = %.3g samples/s; %d candidate branches (%.0f / sample) = %.3g placements/s; "
-          "status %s" % (rep, nnew, dt, nnew / dt, rec["phase1"].sum(), rec["phase1"].mean(), rec["phase1"].sum() / dt,
-                         np.bincount(rec["status"], minlength=4).tolist()), flush=True)
+results = {}
+for variant in variants:
+    eng.set_place_variant(variant)
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        rec = tree.place_samples(samples, p)
+        dt = time.time() - t0
+        print("variant %d rep %d: %d samples in %.2f s (incl. upload and re-bind) = %.3g samples/s; %d candidate branches (%.0f / sample) = "
+              "%.3g placements/s; status %s" % (variant, rep, nnew, dt, nnew / dt, rec["phase1"].sum(), rec["phase1"].mean(),
+                                                rec["phase1"].sum() / dt, np.bincount(rec["status"], minlength=4).tolist()), flush=True)
+    results[variant] = rec
+if len(results) == 2:  # the two kernels must agree record by record
+    a, b = results[variants[0]], results[variants[1]]
+    same = all(np.array_equal(a[f], b[f]) for f in ("bestNode", "status", "phase1", "missedMinors", "bLenTop", "bLenBottom", "bLenAppend"))
+    print("variants agree:", same, "max |score diff| =", float(np.nanmax(np.abs(a["bestScore"] - b["bestScore"]))))
