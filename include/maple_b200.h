@@ -213,7 +213,10 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
 /* Which kernel maple_place_batch launches: 0 (default) = one sample per thread, the straight-line walk; 1 = one sample per
  * warp: windows of the pre-order scored one node per lane, leaf comparisons one per lane, refinement entries one per lane
  * (a few rare shapes run the straight-line walk inside that kernel; batches on trees with MAT mutations or with
- * --deeperSearchForLongBranches are launched on variant 0, which is the faster one for them).  Same results; a sample that exhausts the per-lane scratch of variant 1 reports status 3 like variant 0. */
+ * --deeperSearchForLongBranches are launched on variant 0, which is the faster one for them); 2 = variant 1 with MAT trees
+ * covered: lane 0 walks the part of the tree above mutation-carrying nodes, every mutation-free subtree is scanned by the warp
+ * (checked against the reference's recorded placements with its lanes emulated on the host; not yet run on hardware).
+ * Same results; a sample that exhausts its scratch reports status 3 in every variant. */
 int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant);
 
 /* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state

@@ -498,6 +498,47 @@ __global__ void __launch_bounds__(kPlaceWarpThreads) k_place_samples_warp(const 
     }
 }
 
+// the same with MAT trees covered (place_sample_warp_mat): lane 0 walks above mutation-carrying nodes, mutation-free subtrees are scan jobs
+__global__ void __launch_bounds__(kPlaceWarpThreads) k_place_samples_warp_mat(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+                                                                              const __grid_constant__ PlaceParams pp, int64_t n,
+                                                                              const int32_t* __restrict__ sampleLists, PlaceResult* __restrict__ out,
+                                                                              char* scratch, size_t warpBytes, unsigned laneK, unsigned laneP,
+                                                                              unsigned laneA, int stackCap, int bestCap, unsigned long long* counter) {
+    __shared__ DevModel sm;
+    __shared__ PlaceWarpMat warps[kPlaceWarpThreads / 32];
+    __shared__ long long ticket[kPlaceWarpThreads / 32];
+    stage_model(sm, gm);
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    PlaceWarpMat& X = warps[wid];
+    char* base = scratch + (blockIdx.x * (size_t)(kPlaceWarpThreads / 32) + wid) * warpBytes;
+    PlaceWarpScratch ws;
+    ws.laneK = laneK; ws.laneP = laneP; ws.laneA = laneA; ws.bestCap = bestCap; ws.stackCap = stackCap;
+    ws.pay = reinterpret_cast<double*>(base);
+    ws.ais = ws.pay + 32 * (size_t)laneP;
+    ws.diffPay = ws.ais + 32 * (size_t)laneA;
+    ws.eval = reinterpret_cast<PlaceEval*>(ws.diffPay + 6 * (size_t)laneK);
+    ws.gpath = reinterpret_cast<PlacePath*>(ws.eval + bestCap);
+    ws.best = reinterpret_cast<PlaceBest*>(ws.gpath + stackCap);
+    ws.stack = reinterpret_cast<PlaceStackE*>(ws.best + bestCap);
+    ws.key = reinterpret_cast<uint32_t*>(ws.stack + stackCap);
+    ws.diffKey = ws.key + 32 * (size_t)laneK;
+    ws.evalRc = reinterpret_cast<int*>(ws.diffKey + laneK);
+    for (;;) {
+        if (lane == 0) ticket[wid] = (long long)atomicAdd(counter, 1ULL);
+        __syncwarp();
+        const long long i = ticket[wid];
+        __syncwarp();
+        if (i >= n) break;
+        const int64_t id = sampleLists[i];
+        const int64_t ks = T.keyStart[id];
+        PlaceResult r;
+        r.bestNode = -1; r.status = 2; r.phase1 = r.missedMinors = 0; r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+        if (ks >= 0) place_sample_warp_mat(sm, T, pp, LRef{T.key + ks, T.pay + T.payStart[id], T.nkeys[id]}, X, ws, r);
+        if (lane == 0) out[i] = r;
+        __syncwarp();
+    }
+}
+
 // grid: whole waves of CTAs (multiples of the SM count), capped by the work
 static int grid_for(const maple_ctx* ctx, int64_t n, int ctasPerSM) {
     int64_t need = (n + kThreads - 1) / kThreads;
@@ -1034,7 +1075,8 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
                               (size_t)capK * 4 + 15) & ~size_t(15);
     // Variant 1 covers what its scans cover; everything else would run on one lane per warp there, so it goes to variant 0
-    if (ctx->placeVariant == 1 && T.order && !ctx->treeHasMut && !pp.deeperSearchForLongBranches) {
+    const bool warpPlain = ctx->placeVariant == 1 && !ctx->treeHasMut, warpMat = ctx->placeVariant == 2;
+    if ((warpPlain || warpMat) && T.order && !pp.deeperSearchForLongBranches) {
         // one warp per sample: 32 lane slices of scratch (refinement entries run one per lane), the sample list, bestNodes and
         // its refinement results, per-depth states, and the stack of the straight-line fallback
         const unsigned laneK = 512, laneP = 6 * 512, laneA = 512;
@@ -1043,7 +1085,8 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
                                   (size_t)stackCap * sizeof(PlacePath) + (size_t)bestCapW * sizeof(PlaceBest) +
                                   (size_t)stackCap * sizeof(PlaceStackE) + (size_t)32 * laneK * 4 + (size_t)laneK * 4 + (size_t)bestCapW * 4 + 63) & ~size_t(63);
         int perSM = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp, kPlaceWarpThreads, 0));
+        if (warpMat) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp_mat, kPlaceWarpThreads, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp, kPlaceWarpThreads, 0));
         if (perSM < 1) perSM = 1;
         const int warpsPerBlock = kPlaceWarpThreads / 32;
         int64_t nBlocks = (int64_t)ctx->numSMs * perSM;
@@ -1060,9 +1103,14 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
         CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, pp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
-        k_place_samples_warp<<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
-                                                                                          (char*)ctx->placeScratch, warpBytes, laneK, laneP, laneA,
-                                                                                          stackCap, bestCapW, ctx->searchCounter);
+        if (warpMat)
+            k_place_samples_warp_mat<<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
+                                                                                                  (char*)ctx->placeScratch, warpBytes, laneK, laneP,
+                                                                                                  laneA, stackCap, bestCapW, ctx->searchCounter);
+        else
+            k_place_samples_warp<<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
+                                                                                              (char*)ctx->placeScratch, warpBytes, laneK, laneP, laneA,
+                                                                                              stackCap, bestCapW, ctx->searchCounter);
         ctx->launches++;
         CK(cudaGetLastError());
         return MAPLE_OK;
@@ -1092,7 +1140,7 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
 }
 
 int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant) {
-    if (!ctx || variant < 0 || variant > 1) return MAPLE_E_ARG;
+    if (!ctx || variant < 0 || variant > 2) return MAPLE_E_ARG;
     ctx->placeVariant = variant;
     return MAPLE_OK;
 }

@@ -286,4 +286,305 @@ __device__ void place_sample_warp(const DevModel& m, const DevTree& t, const Pla
     WARP_SYNC();
 }
 
+// ---- the same with MAT trees covered -------------------------------------------------------------------------------------
+// On a tree with local references (mutations[node] lists, the reference's default) the sample list is re-referenced whenever
+// the walk crosses a branch that carries mutations (:7969, :8082, :8089), so one list no longer serves the whole tree.  Here lane 0
+// runs the reference's stack-driven walk itself and hands every popped node whose subtree carries no mutations below it (and is
+// worth a window) to the warp as a scan job: the subtree is a contiguous pre-order range scored against ONE list, the one the
+// stack entry carries, exactly as in place_sample_warp; what the job's root inherits (parentLK, failedPasses) comes from the
+// entry.  Nodes outside such subtrees -- the ancestors of mutation-carrying nodes -- are processed by lane 0 in the straight-line
+// form.  shorten() of the current list at a new best (:8065) is applied in place like the reference does; candidate scores and
+// leaf comparisons do not depend on how R runs are split, the refinement does, and by then every list has been shortened if
+// and only if a new best was found while it was the current one, as in the reference.
+// Scratch: the walk allocates re-referenced lists from the bottom of the warp's scratch and never frees them (bestNodes
+// entries point at them); the refinement lanes share what is left above.
+constexpr int kPlaceScanMin = 4;  // subtrees smaller than this stay on lane 0
+
+struct PlaceWarpMat {
+    PlaceWarp w;
+    ScratchD walk;       // lane 0's allocator over the whole scratch
+    PlaceStackE cur;     // the entry being processed
+    int sp, job, jobNewBest;
+};
+
+__device__ void place_sample_warp_mat(const DevModel& m, const DevTree& t, const PlaceParams& pp, LRef in, PlaceWarpMat& X,
+                                      const PlaceWarpScratch& ws, PlaceResult& r) {
+    PlaceWarp& W = X.w;
+    const int root = t.root;
+    const double one = pp.oneMutBLen, eff = pp.effectivelyNon0BLen;
+    // ---- preamble (lane 0): :7929-7971
+    FOR_LANES(lane) {
+        if (lane == 0) {
+            W.state = 0;
+            W.bestNode = root; W.phase1 = 0; W.missed = 0; W.nQ = 0;
+            W.pos = 0; W.nWin = 0; W.minorNode = -1;
+            W.diffs = lnull();
+            X.sp = 0; X.job = 0; X.jobNewBest = 0;
+            X.walk = place_whole_scratch(ws);
+            const bool covered = t.order && !pp.deeperSearchForLongBranches && t.child0[root] >= 0 && in.k;
+            if (!covered) W.state = 2;
+            else {
+                ScratchD& s = X.walk;
+                LRef diffs = s_copy(s, in);
+                if (diffs.k && n_mut(t, root)) diffs = s_pass(m, t, s, diffs, root, false);
+                const LRef rootVect = diffs.k ? s_root_vector(m, t, s, tree_list(t, 0, root), 0.0, false) : lnull();
+                if (!rootVect.k) W.state = s.err == 3 ? 3 : 2;
+                else {
+                    W.best = W.original = f_append(m, rootVect, diffs, true, one);
+                    for (int i = 0; i < 2 && W.state == 0; i++) {
+                        const int c = i == 0 ? t.child0[root] : t.child1[root];
+                        LRef dc = diffs;
+                        if (n_mut(t, c)) dc = s_pass(m, t, s, diffs, c, false);
+                        if (!dc.k || X.sp >= ws.stackCap) { W.state = 3; break; }
+                        PlaceStackE& e = ws.stack[X.sp++];
+                        e.t1 = c; e.parentLK = W.best; e.failedPasses = 0; e.diffs = dc;
+                    }
+                }
+            }
+        }
+    }
+    WARP_SYNC();
+    for (;;) {
+        const int state0 = W.state, sp0 = X.sp;
+        WARP_SYNC();  // every lane has read the loop condition before lane 0 pops
+        if (state0 != 0 || sp0 == 0) break;
+        // ---- lane 0 pops an entry: a scan job for the warp, or one node processed on the spot
+        FOR_LANES(lane) {
+            if (lane == 0) {
+                const PlaceStackE E = ws.stack[--X.sp];
+                X.cur = E;
+                const int t1 = E.t1;
+                X.job = (!(t.mutStart && t.mutBelow[t1]) && t.size[t1] >= kPlaceScanMin) ? 1 : 0;
+                X.jobNewBest = 0;
+                if (X.job) {
+                    W.diffs = E.diffs;
+                    W.path[0] = PlacePath{E.parentLK, E.failedPasses, 0};
+                    W.pos = t.pre[t1];
+                } else {
+                    ScratchD& s = X.walk;
+                    int failedPasses = E.failedPasses;
+                    LRef d = E.diffs;
+                    double LKdiff = E.parentLK;
+                    bool stop = false;
+                    if (t.child0[t1] < 0) {
+                        const int cmp = dev_is_minor(m.lRef, tree_list(t, 0, t1), d, pp.onlyFindIdentical != 0);
+                        if (cmp == 1) { W.state = 1; W.minorNode = t1; stop = true; }
+                        else if (cmp == 2) W.missed++;
+                    }
+                    if (!stop && t.dist[t1] > eff && t.up[t1] >= 0) {
+                        const LRef tot = tree_list(t, 3, t1);
+                        if (!tot.k) { W.state = 2; stop = true; }
+                        else {
+                            LKdiff = p_append_sitewise(m, tot, d, one);
+                            W.phase1++;
+                            const bool nb = LKdiff >= W.best;
+                            if (nb) f_shorten_inplace(m, d);  // :8065, before the entry is recorded
+                            if (nb || LKdiff > W.best - pp.thresholdLogLKoptimization) {
+                                if (W.nQ >= ws.bestCap) { W.state = 3; stop = true; }
+                                else {
+                                    PlaceBest& b = ws.best[W.nQ++];
+                                    b.t1 = t1; b.score = LKdiff; b.diffs = d;
+                                }
+                            }
+                            if (nb) { W.best = LKdiff; W.bestNode = t1; failedPasses = 0; }
+                            if (LKdiff < (E.parentLK - pp.thresholdLogLKconsecutivePlacement)) failedPasses++;
+                        }
+                    }
+                    if (!stop && t.child0[t1] >= 0) {
+                        const bool within = LKdiff > (W.best - pp.thresholdLogLK);
+                        const bool go = pp.strictStopRules ? (failedPasses <= pp.allowedFails && within) : (failedPasses <= pp.allowedFails || within);
+                        if (go) {
+                            for (int i = 0; i < 2; i++) {
+                                const int c = i == 0 ? t.child0[t1] : t.child1[t1];
+                                LRef dc = d;
+                                if (n_mut(t, c)) dc = s_pass(m, t, s, d, c, false);
+                                if (!dc.k || X.sp >= ws.stackCap) { W.state = 3; break; }
+                                PlaceStackE& e = ws.stack[X.sp++];
+                                e.t1 = c; e.parentLK = LKdiff; e.failedPasses = failedPasses; e.diffs = dc;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        WARP_SYNC();
+        if (!X.job) continue;
+        // ---- scan job over the subtree of X.cur.t1 (same phases as place_sample_warp)
+        const int jobRoot = X.cur.t1;
+        const int end = t.pre[jobRoot] + t.size[jobRoot], d0 = t.depth[jobRoot];
+        for (;;) {
+            const int state1 = W.state, pos = W.pos;
+            WARP_SYNC();
+            if (state1 != 0 || pos >= end) break;
+            FOR_LANES(lane) {
+                for (int w = lane; w < kPWin; w += 32) {
+                    const int idx = pos + w;
+                    int info = 0, size = 1, node = -1;
+                    if (idx < end) {
+                        const ScanNode rec = t.scan[idx];
+                        node = rec.node;
+                        size = rec.size;
+                        const bool isLong = (rec.flags & SN_LONG) != 0, tot = (rec.flags & SN_TOT) != 0;
+                        info = ((isLong && tot) ? 1 : 0) | ((rec.flags & SN_INNER) ? 0 : 2) | ((isLong && !tot) ? 4 : 0) | ((rec.depth - d0) << 8);
+                    }
+                    W.winInfo[w] = info; W.winSize[w] = size; W.winNode[w] = node;
+                }
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {
+                if (lane == 0) {
+                    int nWin = min(kPWin, end - pos), k = 0;
+                    for (int w = 0; w < nWin; w++) {
+                        if (W.winInfo[w] & 1) {
+                            if (k == 32) { nWin = w; break; }
+                            W.slot[k++] = w;
+                        }
+                    }
+                    for (; k < 32; k++) W.slot[k] = -1;
+                    W.nWin = nWin;
+                }
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {
+                const int w = W.slot[lane];
+                if (w >= 0) W.winScore[w] = p_append_sitewise(m, tree_list(t, 3, W.winNode[w]), W.diffs, one);
+            }
+            FOR_LANES(lane) {
+                for (int w = lane; w < W.nWin; w += 32)
+                    if (W.winInfo[w] & 2) W.winMinor[w] = dev_is_minor(m.lRef, tree_list(t, 0, W.winNode[w]), W.diffs, pp.onlyFindIdentical != 0);
+            }
+            WARP_SYNC();
+            FOR_LANES(lane) {
+                if (lane == 0) {
+                    int j = 0;
+                    const int nWin = W.nWin;
+                    double best = W.best;
+                    while (j < nWin) {
+                        const int info = W.winInfo[j], rel = info >> 8, node = W.winNode[j];
+                        const PlacePath pe = rel < kPPath ? W.path[rel] : ws.gpath[rel];
+                        int failed = pe.failed;
+                        double LK = pe.lk;
+                        if (info & 2) {
+                            const int cmp = W.winMinor[j];
+                            if (cmp == 1) { W.state = 1; W.minorNode = node; break; }
+                            if (cmp == 2) W.missed++;
+                        }
+                        if (info & 4) { W.state = 2; break; }
+                        if (info & 1) {
+                            LK = W.winScore[j];
+                            W.phase1++;
+                            const bool nb = LK >= best;
+                            if (nb || LK > best - pp.thresholdLogLKoptimization) {
+                                if (W.nQ >= ws.bestCap) { W.state = 3; break; }
+                                PlaceBest& b = ws.best[W.nQ++];
+                                b.t1 = node; b.score = LK; b.diffs = W.diffs;
+                            }
+                            if (nb) { best = LK; W.bestNode = node; failed = 0; X.jobNewBest = 1; }
+                            if (LK < (pe.lk - pp.thresholdLogLKconsecutivePlacement)) failed++;
+                        }
+                        const bool within = LK > (best - pp.thresholdLogLK);
+                        const bool go = pp.strictStopRules ? (failed <= pp.allowedFails && within) : (failed <= pp.allowedFails || within);
+                        if (go && !(info & 2)) {
+                            if (rel + 1 >= ws.stackCap) { W.state = 3; break; }
+                            if (rel + 1 < kPPath) W.path[rel + 1] = PlacePath{LK, failed, 0};
+                            else ws.gpath[rel + 1] = PlacePath{LK, failed, 0};
+                            j += 1;
+                        } else j += W.winSize[j];
+                    }
+                    W.best = best;
+                    W.pos = pos + j;
+                }
+            }
+            WARP_SYNC();
+        }
+        // the list of this job was the current one at a new best: shorten it in place (:8065), once
+        FOR_LANES(lane) {
+            if (lane == 0 && X.jobNewBest) {
+                LRef d = X.cur.diffs;
+                f_shorten_inplace(m, d);
+            }
+        }
+        WARP_SYNC();
+    }
+    if (W.state != 0) {
+        FOR_LANES(lane) {
+            if (lane == 0) {
+                if (W.state == 2) {
+                    ScratchD s = place_whole_scratch(ws);
+                    place_sample(m, t, pp, in, s, ws.stack, ws.stackCap, ws.best, ws.bestCap, r);
+                } else {
+                    r.bestNode = W.state == 1 ? W.minorNode : -1;
+                    r.status = W.state;
+                    r.phase1 = W.state == 1 ? W.phase1 : 0;
+                    r.missedMinors = W.state == 1 ? W.missed : 0;
+                    r.bestScore = W.state == 1 ? 1.0 : 0.0;
+                    r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+                }
+            }
+        }
+        WARP_SYNC();
+        return;
+    }
+    // ---- refinement, one entry per lane, in what the walk left of the scratch
+    const unsigned usedK = (X.walk.topK + 3u) & ~3u, usedP = (X.walk.topP + 1u) & ~1u;
+    const unsigned totalK = 32u * ws.laneK, totalP = 32u * ws.laneP;
+    const unsigned sliceK = usedK < totalK ? ((totalK - usedK) / 32u) & ~3u : 0u, sliceP = usedP < totalP ? ((totalP - usedP) / 32u) & ~1u : 0u;
+    FOR_LANES(lane) {
+        for (int i = lane; i < W.nQ; i += 32) {
+            int rc = -1;
+            if (ws.best[i].score >= W.best - pp.thresholdLogLKoptimization) {
+                ScratchD s;
+                s.key = ws.key + usedK + (size_t)lane * sliceK;
+                s.pay = ws.pay + usedP + (size_t)lane * sliceP;
+                s.ais = ws.ais + (size_t)lane * ws.laneA;
+                s.capK = sliceK; s.capP = sliceP; s.capA = ws.laneA; s.topK = s.topP = 0; s.err = 0;
+                rc = place_refine_entry(m, t, s, ws.best[i].t1, ws.best[i].diffs, ws.eval[i]);
+            }
+            ws.evalRc[i] = rc;
+        }
+    }
+    WARP_SYNC();
+    FOR_LANES(lane) {
+        if (lane == 0) {
+            int bestNode = W.bestNode, status = 0;
+            double bestScore = W.best;
+            double bTop = 0.0, bBottom = 0.0, bAppend = one;
+            if (bestNode != root) {
+                bTop = t.dist[bestNode] / 2;
+                bBottom = t.dist[bestNode] / 2 / 2;
+            }
+            for (int i = 0; i < W.nQ; i++) {
+                int rc = ws.evalRc[i];
+                if (rc < 0) continue;
+                PlaceEval e = ws.eval[i];
+                if (rc == 3) {  // did not fit a lane's slice: everything above the walk's lists
+                    ScratchD s;
+                    s.key = ws.key + usedK; s.pay = ws.pay + usedP; s.ais = ws.ais;
+                    s.capK = totalK - min(usedK, totalK); s.capP = totalP - min(usedP, totalP); s.capA = 32u * ws.laneA; s.topK = s.topP = 0; s.err = 0;
+                    rc = place_refine_entry(m, t, s, ws.best[i].t1, ws.best[i].diffs, e);
+                }
+                if (rc > 0) { status = rc; break; }
+                if (e.score >= bestScore) {
+                    bestNode = ws.best[i].t1;
+                    bestScore = e.score;
+                    bTop = e.top; bBottom = e.bottom; bAppend = e.append;
+                }
+            }
+            r.phase1 = W.phase1;
+            r.missedMinors = W.missed;
+            r.status = status;
+            if (status) {
+                r.bestNode = -1;
+                r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+            } else {
+                if (bestScore == -INFINITY) bestScore = W.original;
+                r.bestNode = bestNode;
+                r.bestScore = bestScore;
+                r.bLenTop = bTop; r.bLenBottom = bBottom; r.bLenAppend = bAppend;
+            }
+        }
+    }
+    WARP_SYNC();
+}
+
 }  // namespace maple

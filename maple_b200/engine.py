@@ -134,7 +134,8 @@ class MapleEngine:
         capi.check(self.ctx, self.lib.maple_ctx_set_search_variant(self.ctx, int(variant)), "maple_ctx_set_search_variant")
 
     def set_place_variant(self, variant: int):
-        """0 = one new sample per thread (default), 1 = one per warp with windowed scans (place_scan.cuh); same results."""
+        """0 = one new sample per thread (default), 1 = one per warp with windowed scans (place_scan.cuh), 2 = the same with MAT
+        trees covered; same results."""
         capi.check(self.ctx, self.lib.maple_ctx_set_place_variant(self.ctx, int(variant)), "maple_ctx_set_place_variant")
         self.place_variant = int(variant)
 

@@ -33,7 +33,7 @@ def lib():
             f.restype = C.c_double
             f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_double]
         L.hs_place_batch_scan.restype = None
-        L.hs_place_batch_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p]
+        L.hs_place_batch_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -51,13 +51,14 @@ class KernelSourceOnHost(Oracle):
         f = {"sitewise": self.L.hs_append_sitewise, "q4": self.L.hs_append_q4}[which]
         return f(self.mp, _p(a.key), _p(a.pay), _p(b.key), _p(b.pay), int(bool(isTipC)), float(bLen))
 
-    def place_batch_scan(self, tree: dict, lists, params: dict, samples, scratch_keys: int = 4096):
-        """Placement variant 1 (one sample per warp, place_scan.cuh), lanes emulated in turn."""
+    def place_batch_scan(self, tree: dict, lists, params: dict, samples, scratch_keys: int = 4096, mat: bool = False):
+        """Placement variant 1 (one sample per warp, place_scan.cuh: place_sample_warp), or with mat=True variant 2
+        (place_sample_warp_mat: MAT trees covered), lanes emulated in turn."""
         t, keep = self._tree_struct(tree, lists)
         pp = OrPlaceParams()
         for k, v in params.items():
             setattr(pp, k, v)
         out = np.zeros(len(samples), dtype=PLACE_RESULT_DTYPE)
         self.L.hs_place_batch_scan(self.mp, C.addressof(t), C.addressof(pp), len(samples), _p(samples.key), _p(samples.pay),
-                                   _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(lists.npay), _p(out))
+                                   _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(lists.npay), int(bool(mat)), _p(out))
         return out
