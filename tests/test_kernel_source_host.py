@@ -43,6 +43,9 @@ def test_scan_append_forms_against_reference_vectors(fx, which):
             assert got == float("-inf")
         else:
             assert abs(got - c["out"]) <= 1e-9
+        # the three forms run the same arithmetic in the same order: the lane path and the warp scans of one search or
+        # placement may mix them without changing a single `>` / `>=` decision
+        assert got == hs.append(L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"])
         n += 1
     assert n >= 100
 
@@ -107,3 +110,31 @@ def test_scratch_exhaustion_is_reported_not_overrun():
     ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
     rec = hs.search_batch(ta, _prefilled_lists(g, Oracle(model)), search_params(g), nodes, scratch_keys=64)
     assert (rec["status"] == 3).any() and not math.isnan(float(rec["bestCurrentLK"].sum()))
+
+
+@pytest.mark.parametrize("rv,err,strict,ml", [(False, False, True, False), (True, False, False, True), (True, True, False, False)])
+def test_straight_line_search_source_matches_oracle_on_synthetic_trees(rv, err, strict, ml):
+    """Same configurations as the device test (tests/test_gpu_search.py), on the host: rate variation, site-specific error model,
+    strict and deep stop rules, ML-like branch lengths."""
+    from maple_b200.synthetic import generate
+    from oracle.host_tree import build_tree_lists
+    d = generate(400, lRef=4000, mean_diffs=8.0, rate_variation=rv, error_model=err, site_specific_errors=err, seed=5, ml_like_blens=ml)
+    model = d.model
+    orc, hs = Oracle(model), KernelSourceOnHost(model)
+    lists, dist, isTip = build_tree_lists(orc, d.up, d.child0, d.child1, d.dist, d.root, d.tip_nodes, d.tip_lists, model.lRef,
+                                          int(model.usingErrorRate))
+    ta = {"up": d.up, "child0": d.child0, "child1": d.child1, "dist": dist, "isTip": isTip, "root": d.root}
+    L = math.log(model.lRef)
+    sp = {"strictTopologyStopRules": int(strict), "allowedFailsTopology": 2 if strict else 4, "deeperSearchForLongBranches": 0,
+          "thresholdLogLKtopology": (2.0 if strict else 14.0) * L, "thresholdTopologyPlacement": -0.1,
+          "thresholdLogLKoptimizationTopology": L, "thresholdLogLKconsecutivePlacement": 1.0,
+          "effectivelyNon0BLen": 1.0 / (10 * model.lRef), "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "defaultBLen": 0.000033}
+    nodes = np.array([i for i in range(len(d.up)) if d.up[i] >= 0], np.int32)
+    rec = hs.search_batch(ta, lists, sp, nodes, scratch_keys=1 << 15)
+    ref = orc.search_batch(ta, lists, sp, nodes, lazy_mode=1)
+    for f in ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
+        assert np.array_equal(rec[f], ref[f]), f
+    for f in ("bestCurrentLK", "bestScore", "improvement"):
+        fin = np.isfinite(ref[f])
+        assert np.array_equal(rec[f][~fin], ref[f][~fin]) and np.max(np.abs(rec[f][fin] - ref[f][fin]), initial=0.0) <= 1e-9, f
+    assert (ref["status"] == 0).sum() > 100 and (ref["placement"] >= 0).sum() > 0 and int(ref["phase1"].sum()) > 20000
