@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(kPlaceWarpThreads) k_place_samples_warp(const 
 }
 
 // the same with MAT trees covered (place_sample_warp_mat): lane 0 walks above mutation-carrying nodes, mutation-free subtrees are scan jobs
+template <bool PAR>
 __global__ void __launch_bounds__(kPlaceWarpThreads) k_place_samples_warp_mat(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                               const __grid_constant__ PlaceParams pp, int64_t n,
                                                                               const int32_t* __restrict__ sampleLists, PlaceResult* __restrict__ out,
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(kPlaceWarpThreads) k_place_samples_warp_mat(co
         const int64_t ks = T.keyStart[id];
         PlaceResult r;
         r.bestNode = -1; r.status = 2; r.phase1 = r.missedMinors = 0; r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
-        if (ks >= 0) place_sample_warp_mat(sm, T, pp, LRef{T.key + ks, T.pay + T.payStart[id], T.nkeys[id]}, X, ws, r);
+        if (ks >= 0) place_sample_warp_mat<PAR>(sm, T, pp, LRef{T.key + ks, T.pay + T.payStart[id], T.nkeys[id]}, X, ws, r);
         if (lane == 0) out[i] = r;
         __syncwarp();
     }
@@ -1075,7 +1076,7 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
                               (size_t)capK * 4 + 15) & ~size_t(15);
     // Variant 1 covers what its scans cover; everything else would run on one lane per warp there, so it goes to variant 0
-    const bool warpPlain = ctx->placeVariant == 1 && !ctx->treeHasMut, warpMat = ctx->placeVariant == 2;
+    const bool warpPlain = ctx->placeVariant == 1 && !ctx->treeHasMut, warpMat = ctx->placeVariant >= 2, warpPar = ctx->placeVariant == 3;
     if ((warpPlain || warpMat) && T.order && !pp.deeperSearchForLongBranches) {
         // one warp per sample: 32 lane slices of scratch (refinement entries run one per lane), the sample list, bestNodes and
         // its refinement results, per-depth states, and the stack of the straight-line fallback
@@ -1085,7 +1086,8 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
                                   (size_t)stackCap * sizeof(PlacePath) + (size_t)bestCapW * sizeof(PlaceBest) +
                                   (size_t)stackCap * sizeof(PlaceStackE) + (size_t)32 * laneK * 4 + (size_t)laneK * 4 + (size_t)bestCapW * 4 + 63) & ~size_t(63);
         int perSM = 0;
-        if (warpMat) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp_mat, kPlaceWarpThreads, 0));
+        if (warpPar) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp_mat<true>, kPlaceWarpThreads, 0));
+        else if (warpMat) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp_mat<false>, kPlaceWarpThreads, 0));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_place_samples_warp, kPlaceWarpThreads, 0));
         if (perSM < 1) perSM = 1;
         const int warpsPerBlock = kPlaceWarpThreads / 32;
@@ -1103,10 +1105,14 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
         CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, pp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
-        if (warpMat)
-            k_place_samples_warp_mat<<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
-                                                                                                  (char*)ctx->placeScratch, warpBytes, laneK, laneP,
-                                                                                                  laneA, stackCap, bestCapW, ctx->searchCounter);
+        if (warpPar)
+            k_place_samples_warp_mat<true><<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(
+                ctx->model, T, pp, n, sampleLists, (PlaceResult*)out, (char*)ctx->placeScratch, warpBytes, laneK, laneP, laneA, stackCap, bestCapW,
+                ctx->searchCounter);
+        else if (warpMat)
+            k_place_samples_warp_mat<false><<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(
+                ctx->model, T, pp, n, sampleLists, (PlaceResult*)out, (char*)ctx->placeScratch, warpBytes, laneK, laneP, laneA, stackCap, bestCapW,
+                ctx->searchCounter);
         else
             k_place_samples_warp<<<(int)nBlocks, kPlaceWarpThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, pp, n, sampleLists, (PlaceResult*)out,
                                                                                               (char*)ctx->placeScratch, warpBytes, laneK, laneP, laneA,
@@ -1140,7 +1146,7 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
 }
 
 int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant) {
-    if (!ctx || variant < 0 || variant > 2) return MAPLE_E_ARG;
+    if (!ctx || variant < 0 || variant > 3) return MAPLE_E_ARG;
     ctx->placeVariant = variant;
     return MAPLE_OK;
 }

@@ -305,8 +305,255 @@ struct PlaceWarpMat {
     ScratchD walk;       // lane 0's allocator over the whole scratch
     PlaceStackE cur;     // the entry being processed
     int sp, job, jobNewBest;
+    // work arrays of the parallel window replay (place_replay_parallel)
+    double bb[kPWin];       // running best before the node, taking every earlier score of the window
+    double lkOut[kPWin];    // LKdiff the node hands to its children
+    double dval[2][kPWin];  // double-buffered values of the scans / pointer jumps
+    int fOut[kPWin];        // failedPasses the node hands to its children
+    int par[kPWin];         // window position of the parent, -1: before the window
+    int ival[2][kPWin], ptr[2][kPWin];
+    int flags[kPWin];       // 1 new best, 2 descends, 4 reached
+    double redD[32];
+    int redI[32], redJ[32], redK[32];
+    int act[8];
+    int cutW, maxTarget, committed, qBase;
 };
 
+// Pointer jumping over the parent links of a window: every node with ptr >= 0 combines its value with its pointer target's and
+// takes over the target's pointer, until all chains end at a resolved node (ptr < 0).  MODE 0: the value of the resolved ancestor
+// (double), 1: sum (int), 2: logical and (int).  Values and pointers are double-buffered; returns the buffer that holds the
+// result, or -1 when 8 rounds were not enough (cannot happen for 96 nodes; the caller then replays serially).
+template <int MODE>
+__device__ int place_jump(PlaceWarpMat& X, int nWin) {
+    FOR_LANES(lane) {
+        if (lane < 8) X.act[lane] = 0;
+    }
+    WARP_SYNC();
+    int cur = 0;
+    for (int round = 0; round < 8; round++) {
+        const int nxt = cur ^ 1;
+        FOR_LANES(lane) {
+            for (int w = lane; w < nWin; w += 32) {
+                const int p = X.ptr[cur][w];
+                if (p < 0) {
+                    X.ptr[nxt][w] = -1;
+                    if (MODE == 0) X.dval[nxt][w] = X.dval[cur][w];
+                    else X.ival[nxt][w] = X.ival[cur][w];
+                } else {
+                    const int pp = X.ptr[cur][p];
+                    if (MODE == 0) X.dval[nxt][w] = X.dval[cur][p];  // meaningful once p is resolved, i.e. when pp < 0
+                    else if (MODE == 1) X.ival[nxt][w] = X.ival[cur][w] + X.ival[cur][p];
+                    else X.ival[nxt][w] = X.ival[cur][w] & X.ival[cur][p];
+                    X.ptr[nxt][w] = pp;
+                    if (pp >= 0) X.act[round] = 1;
+                }
+            }
+        }
+        WARP_SYNC();
+        cur = nxt;
+        if (!X.act[round]) return cur;
+    }
+    return -1;
+}
+
+// The window replay of place_sample_warp in parallel form.  What a node hands to its children -- LKdiff (its own score, or the
+// inherited one when it is not scored) and failedPasses (reset on a new best, +1 on a consecutive worsening, else inherited) --
+// are chains over ancestors, and "reached" is the AND of the ancestors' stop-rule outcomes: three pointer-jumping passes over the
+// window's parent links.  The running best before a node is taken as the prefix maximum of ALL earlier scores of the window, which
+// is right unless a node the walk does not reach holds a score above it; that is checked, and such a window is left to the serial
+// replay (returns false, nothing committed).  Everything after the first reached leaf that absorbs the sample is void.
+__device__ bool place_replay_parallel(const PlaceParams& pp, PlaceWarpMat& X, const PlaceWarpScratch& ws, int pos) {
+    PlaceWarp& W = X.w;
+    const int nWin = W.nWin;
+    // ---- running best before every node: exclusive prefix maximum of the scores (Hillis-Steele over the window)
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) X.dval[0][w] = (W.winInfo[w] & 1) ? W.winScore[w] : -INFINITY;
+    }
+    WARP_SYNC();
+    int cur = 0;
+    for (int o = 1; o < nWin; o <<= 1) {
+        const int nxt = cur ^ 1;
+        FOR_LANES(lane) {
+            for (int w = lane; w < nWin; w += 32) X.dval[nxt][w] = w >= o ? fmax(X.dval[cur][w], X.dval[cur][w - o]) : X.dval[cur][w];
+        }
+        WARP_SYNC();
+        cur = nxt;
+    }
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) X.bb[w] = w > 0 ? fmax(W.best, X.dval[cur][w - 1]) : W.best;
+    }
+    WARP_SYNC();
+    // ---- pass 1: LKdiff handed down = own score, else the nearest scored ancestor's, else what came in from above the window
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) {
+            const int info = W.winInfo[w], rel = info >> 8, p = X.par[w];
+            if (info & 1) { X.ptr[0][w] = -1; X.dval[0][w] = W.winScore[w]; }
+            else if (p < 0) { X.ptr[0][w] = -1; X.dval[0][w] = (rel < kPPath ? W.path[rel] : ws.gpath[rel]).lk; }
+            else { X.ptr[0][w] = p; X.dval[0][w] = 0.0; }
+        }
+    }
+    WARP_SYNC();
+    cur = place_jump<0>(X, nWin);
+    if (cur < 0) return false;
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) X.lkOut[w] = X.dval[cur][w];
+    }
+    WARP_SYNC();
+    // ---- pass 2: failedPasses handed down.  Own effect: SET to the increment on a new best, else ADD the increment
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) {
+            const int info = W.winInfo[w], rel = info >> 8, p = X.par[w];
+            const bool scored = (info & 1) != 0;
+            const PlacePath pe = p < 0 ? (rel < kPPath ? W.path[rel] : ws.gpath[rel]) : PlacePath{X.lkOut[p], 0, 0};
+            const double sc = W.winScore[w];
+            const bool nb = scored && sc >= X.bb[w];
+            const int inc = (scored && sc < (pe.lk - pp.thresholdLogLKconsecutivePlacement)) ? 1 : 0;
+            X.flags[w] = nb ? 1 : 0;
+            if (nb) { X.ptr[0][w] = -1; X.ival[0][w] = inc; }
+            else if (p < 0) { X.ptr[0][w] = -1; X.ival[0][w] = pe.failed + inc; }
+            else { X.ptr[0][w] = p; X.ival[0][w] = inc; }
+        }
+    }
+    WARP_SYNC();
+    cur = place_jump<1>(X, nWin);
+    if (cur < 0) return false;
+    // ---- the stop rule of every node as if it were reached
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) {
+            const int info = W.winInfo[w];
+            const int failed = X.ival[cur][w];
+            X.fOut[w] = failed;
+            const double LK = X.lkOut[w];
+            const double bestAfter = (info & 1) ? fmax(X.bb[w], W.winScore[w]) : X.bb[w];
+            const bool within = LK > (bestAfter - pp.thresholdLogLK);
+            const bool go = pp.strictStopRules ? (failed <= pp.allowedFails && within) : (failed <= pp.allowedFails || within);
+            if (go && !(info & 2)) X.flags[w] |= 2;
+        }
+    }
+    WARP_SYNC();
+    // ---- pass 3: reached = every ancestor inside the window descends (the window's first node always is)
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32) {
+            const int p = X.par[w];
+            X.ptr[0][w] = p;
+            X.ival[0][w] = p < 0 ? 1 : ((X.flags[p] & 2) ? 1 : 0);
+        }
+    }
+    WARP_SYNC();
+    cur = place_jump<2>(X, nWin);
+    if (cur < 0) return false;
+    // ---- the first reached leaf that absorbs the sample, anomalies, and the check of the prefix-maximum assumption
+    FOR_LANES(lane) {
+        int cut = nWin, bad = 0, anomaly = nWin;
+        for (int w = lane; w < nWin; w += 32) {
+            const int info = W.winInfo[w];
+            const bool ok = X.ival[cur][w] != 0;
+            if (ok) {
+                X.flags[w] |= 4;
+                if ((info & 2) && W.winMinor[w] == 1) cut = min(cut, w);
+                if (info & 4) anomaly = min(anomaly, w);
+            } else if ((info & 1) && W.winScore[w] > X.bb[w]) bad = 1;
+        }
+        X.redI[lane] = cut; X.redJ[lane] = bad; X.redK[lane] = anomaly;
+    }
+    WARP_SYNC();
+    FOR_LANES(lane) {
+        if (lane == 0) {
+            int cut = nWin, bad = 0, anomaly = nWin;
+            for (int i = 0; i < 32; i++) { cut = min(cut, X.redI[i]); bad |= X.redJ[i]; anomaly = min(anomaly, X.redK[i]); }
+            X.cutW = cut;
+            // a leaf that absorbs the sample ends the walk before anything else at that node; an anomaly before it sends the
+            // sample to the straight-line walk; a wrong running best anywhere in the window sends the window to the serial replay
+            X.committed = bad ? 0 : 1;
+            if (!bad && anomaly < cut) { W.state = 2; X.committed = 2; }
+        }
+    }
+    WARP_SYNC();
+    if (X.committed == 0) return false;
+    if (X.committed == 2) return true;
+    const int cutW = X.cutW;
+    // ---- commit: counters, the new running best and its node, the position the walk continues at (three nodes per lane, in order)
+    FOR_LANES(lane) {
+        int nScored = 0, nMissed = 0, nQueued = 0, lastNb = -1, target = 0;
+        double mx = -INFINITY;
+        for (int w = 3 * lane; w < 3 * lane + 3 && w < cutW; w++) {
+            const int info = W.winInfo[w], fl = X.flags[w];
+            if (!(fl & 4)) continue;
+            if ((info & 2) && W.winMinor[w] == 2) nMissed++;
+            if (info & 1) {
+                const double sc = W.winScore[w];
+                nScored++;
+                mx = fmax(mx, sc);
+                if (fl & 1) lastNb = w;
+                if ((fl & 1) || sc > X.bb[w] - pp.thresholdLogLKoptimization) nQueued++;
+            }
+            target = max(target, (fl & 2) ? w + 1 : w + W.winSize[w]);
+        }
+        X.redD[lane] = mx;
+        X.redI[lane] = nScored | (nMissed << 16);
+        X.redJ[lane] = nQueued;
+        X.redK[lane] = (lastNb < 0 ? 0xff : lastNb) | (target << 8);  // lastNb < 96; the target can lie far beyond the window
+    }
+    WARP_SYNC();
+    FOR_LANES(lane) {
+        if (lane == 0) {
+            int nScored = 0, nMissed = 0, q = 0, lastNb = -1, target = 0;
+            double mx = W.best;
+            for (int i = 0; i < 32; i++) {
+                mx = fmax(mx, X.redD[i]);
+                nScored += X.redI[i] & 0xffff;
+                nMissed += X.redI[i] >> 16;
+                const int nq = X.redJ[i];
+                X.redJ[i] = q;  // exclusive prefix: where lane i's entries go
+                q += nq;
+                const int ln = X.redK[i] & 0xff, tg = X.redK[i] >> 8;
+                if (ln != 0xff) lastNb = max(lastNb, ln);
+                target = max(target, tg);
+            }
+            if (W.nQ + q > ws.bestCap) { W.state = 3; X.committed = 2; }
+            else {
+                X.qBase = W.nQ;
+                W.nQ += q;
+                W.phase1 += nScored;
+                W.missed += nMissed;
+                W.best = mx;
+                if (lastNb >= 0) { W.bestNode = W.winNode[lastNb]; X.jobNewBest = 1; }
+                X.maxTarget = target;
+                if (cutW < nWin) { W.state = 1; W.minorNode = W.winNode[cutW]; }
+                else W.pos = pos + target;
+            }
+        }
+    }
+    WARP_SYNC();
+    if (X.committed == 2) return true;
+    // ---- bestNodes entries in window order, and the states the windows that follow inherit: those of the nodes whose subtree
+    // reaches beyond the position the walk continues at (the ancestors of the next node; one per depth)
+    const int maxTarget = X.maxTarget;
+    FOR_LANES(lane) {
+        int at = X.qBase + X.redJ[lane];
+        for (int w = 3 * lane; w < 3 * lane + 3 && w < cutW; w++) {
+            const int info = W.winInfo[w], fl = X.flags[w];
+            if (!(fl & 4)) continue;
+            if (info & 1) {
+                const double sc = W.winScore[w];
+                if ((fl & 1) || sc > X.bb[w] - pp.thresholdLogLKoptimization) {
+                    PlaceBest& b = ws.best[at++];
+                    b.t1 = W.winNode[w]; b.score = sc; b.diffs = W.diffs;
+                }
+            }
+            if ((fl & 2) && w + W.winSize[w] > maxTarget) {
+                const int rel1 = (info >> 8) + 1;
+                if (rel1 >= ws.stackCap) W.state = 3;
+                else if (rel1 < kPPath) W.path[rel1] = PlacePath{X.lkOut[w], X.fOut[w], 0};
+                else ws.gpath[rel1] = PlacePath{X.lkOut[w], X.fOut[w], 0};
+            }
+        }
+    }
+    WARP_SYNC();
+    return true;
+}
+
+template <bool PAR>
 __device__ void place_sample_warp_mat(const DevModel& m, const DevTree& t, const PlaceParams& pp, LRef in, PlaceWarpMat& X,
                                       const PlaceWarpScratch& ws, PlaceResult& r) {
     PlaceWarp& W = X.w;
@@ -428,6 +675,7 @@ __device__ void place_sample_warp_mat(const DevModel& m, const DevTree& t, const
                         info = ((isLong && tot) ? 1 : 0) | ((rec.flags & SN_INNER) ? 0 : 2) | ((isLong && !tot) ? 4 : 0) | ((rec.depth - d0) << 8);
                     }
                     W.winInfo[w] = info; W.winSize[w] = size; W.winNode[w] = node;
+                    X.par[w] = idx < end ? max(t.scan[idx].parentPos - pos, -1) : -1;
                 }
             }
             WARP_SYNC();
@@ -454,6 +702,7 @@ __device__ void place_sample_warp_mat(const DevModel& m, const DevTree& t, const
                     if (W.winInfo[w] & 2) W.winMinor[w] = dev_is_minor(m.lRef, tree_list(t, 0, W.winNode[w]), W.diffs, pp.onlyFindIdentical != 0);
             }
             WARP_SYNC();
+            if (PAR && place_replay_parallel(pp, X, ws, pos)) continue;  // else: the reference's loop body over the window, in order (lane 0)
             FOR_LANES(lane) {
                 if (lane == 0) {
                     int j = 0;

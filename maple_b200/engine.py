@@ -135,7 +135,7 @@ class MapleEngine:
 
     def set_place_variant(self, variant: int):
         """0 = one new sample per thread (default), 1 = one per warp with windowed scans (place_scan.cuh), 2 = the same with MAT
-        trees covered; same results."""
+        trees covered, 3 = 2 with the parallel window replay; same results."""
         capi.check(self.ctx, self.lib.maple_ctx_set_place_variant(self.ctx, int(variant)), "maple_ctx_set_place_variant")
         self.place_variant = int(variant)
 

@@ -11,7 +11,7 @@ from maple_b200.tree import DeviceTree
 
 nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 nnew = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
-variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]  # 0 = sample per thread, 1 = sample per warp
+variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]  # 0 = sample per thread, 1 = sample per warp, 2 = + MAT trees, 3 = + parallel window replay
 d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=True)
 eng = MapleEngine(d.model, 0)
 tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
@@ -51,7 +51,7 @@ for variant in variants:
               "%.3g placements/s; status %s" % (variant, rep, nnew, dt, nnew / dt, rec["phase1"].sum(), rec["phase1"].mean(),
                                                 rec["phase1"].sum() / dt, np.bincount(rec["status"], minlength=4).tolist()), flush=True)
     results[variant] = rec
-if len(results) == 2:  # the two kernels must agree record by record
-    a, b = results[variants[0]], results[variants[1]]
+for v in variants[1:]:  # the kernels must agree record by record
+    a, b = results[variants[0]], results[v]
     same = all(np.array_equal(a[f], b[f]) for f in ("bestNode", "status", "phase1", "missedMinors", "bLenTop", "bLenBottom", "bLenAppend"))
-    print("variants agree:", same, "max |score diff| =", float(np.nanmax(np.abs(a["bestScore"] - b["bestScore"]))))
+    print("variants %d and %d agree:" % (variants[0], v), same, "max |score diff| =", float(np.nanmax(np.abs(a["bestScore"] - b["bestScore"]))))

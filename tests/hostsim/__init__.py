@@ -51,14 +51,14 @@ class KernelSourceOnHost(Oracle):
         f = {"sitewise": self.L.hs_append_sitewise, "q4": self.L.hs_append_q4}[which]
         return f(self.mp, _p(a.key), _p(a.pay), _p(b.key), _p(b.pay), int(bool(isTipC)), float(bLen))
 
-    def place_batch_scan(self, tree: dict, lists, params: dict, samples, scratch_keys: int = 4096, mat: bool = False):
+    def place_batch_scan(self, tree: dict, lists, params: dict, samples, scratch_keys: int = 4096, mat: int = 0):
         """Placement variant 1 (one sample per warp, place_scan.cuh: place_sample_warp), or with mat=True variant 2
-        (place_sample_warp_mat: MAT trees covered), lanes emulated in turn."""
+        (place_sample_warp_mat: MAT trees covered) and with mat=2 variant 3 (parallel window replay), lanes emulated in turn."""
         t, keep = self._tree_struct(tree, lists)
         pp = OrPlaceParams()
         for k, v in params.items():
             setattr(pp, k, v)
         out = np.zeros(len(samples), dtype=PLACE_RESULT_DTYPE)
         self.L.hs_place_batch_scan(self.mp, C.addressof(t), C.addressof(pp), len(samples), _p(samples.key), _p(samples.pay),
-                                   _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(lists.npay), int(bool(mat)), _p(out))
+                                   _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(lists.npay), int(mat), _p(out))
         return out

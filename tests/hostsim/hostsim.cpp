@@ -206,7 +206,7 @@ void or_shorten_slots(const DevModel* m, int64_t n, uint32_t* key, double* pay, 
 // arrays are what maple_tree_bind computes on the host, the ScanNode records what k_scan_prepare computes per position.
 void hs_place_batch_scan(const DevModel* m, const OrTree* t, const PlaceParams* pp, int64_t n, const uint32_t* key, const double* pay,
                          const int64_t* keyStart, const int64_t* payStart, const int32_t* nkeys, int64_t scratchKeys, const int32_t* npay,
-                         int32_t matVariant /* 0: place_sample_warp, 1: place_sample_warp_mat */, PlaceResult* out) {
+                         int32_t matVariant /* 0: place_sample_warp, 1: place_sample_warp_mat, 2: the same with the parallel window replay */, PlaceResult* out) {
     DevTree T = dev_tree(t);
     const size_t N = (size_t)t->nNodes;
     std::vector<int32_t> order(N, -1), pre(N, -1), size(N, 1), depth(N, 0), st{t->root};
@@ -254,7 +254,8 @@ void hs_place_batch_scan(const DevModel* m, const OrTree* t, const PlaceParams* 
     for (int64_t i = 0; i < n; i++) {
         memset(&X, 0, sizeof X);
         const LRef in{key + keyStart[i], pay + payStart[i], nkeys[i]};
-        if (matVariant) place_sample_warp_mat(*m, T, *pp, in, X, ws, out[i]);
+        if (matVariant == 2) place_sample_warp_mat<true>(*m, T, *pp, in, X, ws, out[i]);
+        else if (matVariant) place_sample_warp_mat<false>(*m, T, *pp, in, X, ws, out[i]);
         else place_sample_warp(*m, T, *pp, in, X.w, ws, out[i]);
     }
 }

@@ -67,7 +67,8 @@ def test_scan_placement_matches_oracle_on_synthetic_trees(rv, err, strict, nseq)
     ref = orc.place_batch(ta, lists, pp, samples)
     got = hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16)
     _same(got, ref)
-    _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=True), ref)
+    _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=1), ref)
+    _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=2), ref)
     _same(hs.place_batch(ta, lists, pp, samples, scratch_keys=1 << 16), ref)
     assert (ref["status"] == 0).sum() > 20 and (ref["status"] == 1).sum() > 5
     assert ref["phase1"].max() > 96  # more than one window
@@ -88,7 +89,8 @@ def test_scan_placement_on_reference_built_trees_without_mat(name):
     ref = Oracle(model).place_batch(ta, lists, pp, samples)
     hs = KernelSourceOnHost(model)
     _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16), ref)
-    _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=True), ref)
+    _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=1), ref)
+    _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=2), ref)
     if not pp["deeperSearchForLongBranches"]:
         assert (ref["status"] == 0).sum() > 10
 
@@ -102,15 +104,16 @@ def test_scan_variant_falls_back_on_mat_trees_and_matches_reference(name):
     check_placements(g, rec)
 
 
+@pytest.mark.parametrize("mat", [1, 2])
 @pytest.mark.parametrize("name", golden_names())
-def test_mat_covering_variant_matches_reference_on_mat_trees(name):
+def test_mat_covering_variant_matches_reference_on_mat_trees(name, mat):
     """place_sample_warp_mat on the reference's frozen trees WITH their local references: lane 0 walks the part of the tree
     above mutation-carrying nodes, mutation-free subtrees are scan jobs; identical to the 448 recorded placements."""
     g = load_golden(name)
     model = MapleModel.from_reference_snapshot(g["env"], g["model"])
     samples = pack_lists([g["lists"][c["diffs"]] for c in g["placements"]], model.lRef, model.usingErrorRate)
     ta = tree_arrays(g)
-    rec = KernelSourceOnHost(model).place_batch_scan(ta, tree_lists(g), place_params(g), samples, scratch_keys=1 << 16, mat=True)
+    rec = KernelSourceOnHost(model).place_batch_scan(ta, tree_lists(g), place_params(g), samples, scratch_keys=1 << 16, mat=mat)
     check_placements(g, rec)
     ref = Oracle(model).place_batch(ta, tree_lists(g), place_params(g), samples)
     _same(rec, ref)
