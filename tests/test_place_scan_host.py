@@ -139,3 +139,43 @@ def test_parallel_replay_under_aggressive_stop_rules(strict, fails, thr, cons):
     ref = orc.place_batch(ta, lists, pp, samples)
     for mat in (0, 1, 2):
         _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=mat), ref)
+
+
+@pytest.mark.parametrize("deep_child", [0, 1])
+def test_warp_placement_on_a_caterpillar_tree(deep_child):
+    """A ladder of 160 tips: the tree is 159 levels deep, so the per-depth states go past the 48 kept in the warp block into the
+    global array, a window holds an ancestor chain of 96 nodes (the longest the pointer jumping can meet: 7 rounds) when the deep
+    child is explored first, and subtrees are skipped from far above."""
+    from maple_b200.synthetic import generate
+    d = generate(160, lRef=4000, mean_diffs=8.0, rate_variation=True, seed=31)
+    model = d.model
+    n_tips = len(d.tip_lists)
+    # nodes 0..n_tips-1 tips, n_tips.. internals; internal k has the tip k and the next internal (the last one: two tips)
+    n = 2 * n_tips - 1
+    up, c0, c1 = np.full(n, -1, np.int32), np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+    rng = np.random.default_rng(5)
+    dist = np.where(rng.random(n) < 0.3, 0.0, rng.exponential(1.5 / model.lRef, n))
+    for k in range(n_tips - 1):
+        node = n_tips + k
+        deep = n_tips + k + 1 if k < n_tips - 2 else n_tips - 1
+        pair = (k, deep) if deep_child == 1 else (deep, k)
+        c0[node], c1[node] = pair
+        up[pair[0]] = up[pair[1]] = node
+    root = n_tips
+    dist[root] = 0.0
+    orc, hs = Oracle(model), KernelSourceOnHost(model)
+    lists, dist2, isTip = build_tree_lists(orc, up, c0, c1, dist, root, np.arange(n_tips), d.tip_lists, model.lRef, int(model.usingErrorRate))
+    ta = {"up": up, "child0": c0, "child1": c1, "dist": dist2, "isTip": isTip, "root": root}
+    L = math.log(model.lRef)
+    pp = {"strictStopRules": 0, "allowedFails": 6, "deeperSearchForLongBranches": 0, "onlyFindIdentical": 0, "thresholdLogLK": 18.0 * L,
+          "thresholdLogLKoptimization": L, "thresholdLogLKconsecutivePlacement": 0.01, "effectivelyNon0BLen": 1.0 / (10 * model.lRef),
+          "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "oneMutBLen": 1.0 / model.lRef}
+    samples = pack_lists(_mutated(d.tip_lists, model.refIdx, 60), model.lRef, model.usingErrorRate)
+    ref = orc.place_batch(ta, lists, pp, samples)
+    assert ref["phase1"].max() > 150 and (ref["status"] == 0).sum() > 20
+    for mat in (0, 1, 2):
+        _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=mat), ref)
+    pp["strictStopRules"], pp["allowedFails"], pp["thresholdLogLK"] = 1, 1, 2.0 * L
+    ref = orc.place_batch(ta, lists, pp, samples)
+    for mat in (0, 1, 2):
+        _same(hs.place_batch_scan(ta, lists, pp, samples, scratch_keys=1 << 16, mat=mat), ref)
