@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--round", default=os.environ.get("MAPLE_BENCH_ROUND", "deep"), choices=["fast", "deep"])
     ap.add_argument("--cpu-searches", type=int, default=1500, help="searches in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the untimed side measurements reported under 'extra'")
     return ap.parse_args()
 
 
@@ -184,6 +185,22 @@ def run_reference(args):
                                        "search with OpenMP on %d threads" % (len(sample), len(nodes), cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def placement_extra(args):
+    """Side measurement, outside every timed region and in its own processes (a failure there cannot take the headline down):
+    maple_place_batch (findBestParentForNewSample for a batch of new samples on the same frozen tree) with the
+    one-sample-per-thread kernel and the one-sample-per-warp kernels, records compared.  scripts/time_place.py does the work."""
+    out = {}
+    for key, variants in (("thread_vs_warp", "0,1"), ("thread_vs_warp_parallel_replay", "0,3")):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "time_place.py"), str(args.nseq), "4000", variants],
+                               capture_output=True, text=True, timeout=240, cwd=ROOT)
+            got = [ln for ln in r.stdout.splitlines() if ln.startswith("PLACE_JSON ")]
+            out[key] = json.loads(got[-1][len("PLACE_JSON "):]) if got else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as e:  # timeout included
+            out[key] = {"error": repr(e)[:400]}
+    return out
 
 
 def main():
@@ -341,6 +358,8 @@ def main():
                                           "search (C, OpenMP)" % (len(sample), len(nodes), int(ref["phase1"].sum())),
                                 "gpu_matches_oracle_on_sample": bool(same),
                                 "max_abs_score_diff": float(np.max(np.abs(got["bestScore"][fin] - ref["bestScore"][fin]), initial=0.0))}
+    if world == 1 and not args.no_extras and args.nseq >= 20000:
+        line["extra"] = {"placement_batch": placement_extra(args)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
