@@ -7,13 +7,13 @@ import subprocess
 
 import numpy as np
 
-from oracle.oracle import PLACE_RESULT_DTYPE, Oracle, OrPlaceParams, _p, declare
+from oracle.oracle import PLACE_RESULT_DTYPE, SEARCH_RESULT_DTYPE, Oracle, OrPlaceParams, OrSearchParams, _p, declare
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "maple_b200", "csrc")
 LIB = os.path.join(HERE, "libhostsim.so")
 SOURCES = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "shim", "cuda_runtime.h")] + [
-    os.path.join(CSRC, f) for f in ("glist.cuh", "likelihood.cuh", "search.cuh", "place.cuh", "place_scan.cuh")]
+    os.path.join(CSRC, f) for f in ("glist.cuh", "likelihood.cuh", "search.cuh", "search_fsm.cuh", "place.cuh", "place_scan.cuh")]
 _lib = None
 
 
@@ -32,6 +32,8 @@ def lib():
         for f in (L.hs_append_sitewise, L.hs_append_q4):
             f.restype = C.c_double
             f.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_double]
+        L.hs_search_batch_fsm.restype = None
+        L.hs_search_batch_fsm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.hs_place_batch_scan.restype = None
         L.hs_place_batch_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
         _lib = L
@@ -61,4 +63,15 @@ class KernelSourceOnHost(Oracle):
         out = np.zeros(len(samples), dtype=PLACE_RESULT_DTYPE)
         self.L.hs_place_batch_scan(self.mp, C.addressof(t), C.addressof(pp), len(samples), _p(samples.key), _p(samples.pay),
                                    _p(samples.key_start), _p(samples.pay_start), _p(samples.nkeys), int(scratch_keys), _p(lists.npay), int(mat), _p(out))
+        return out
+
+    def search_batch_fsm(self, tree: dict, lists, params: dict, nodes, scratch_keys: int = 8192):
+        """The default search kernel's per-lane state machine (fsm_step / fsm_finish) with the warp scans off, one lane."""
+        t, keep = self._tree_struct(tree, lists)
+        sp = OrSearchParams()
+        for k, v in params.items():
+            setattr(sp, k, v)
+        nodes = np.ascontiguousarray(nodes, np.int32)
+        out = np.zeros(len(nodes), dtype=SEARCH_RESULT_DTYPE)
+        self.L.hs_search_batch_fsm(self.mp, C.addressof(t), C.addressof(sp), len(nodes), _p(nodes), int(scratch_keys), _p(out))
         return out

@@ -6,6 +6,7 @@
 #include "cuda_runtime.h"
 
 #include "place_scan.cuh"
+#include "search_fsm.cuh"
 
 #include <vector>
 
@@ -128,6 +129,63 @@ void or_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp,
     s.key = key.data(); s.pay = pay.data(); s.ais = ais.data();
     s.capK = capK; s.capP = capP; s.capA = capA; s.topK = s.topP = 0; s.err = 0;
     for (int64_t i = 0; i < n; i++) search_node(*m, T, *sp, nodes[i], s, stack.data(), stackCap, out[i]);
+}
+
+// One lane of k_spr_search_fsm (the default search kernel) with the warp scans switched off (search variant 2): the per-lane
+// control code (fsm_step, fsm_finish) and the co-walk service loop of the kernel, one search after the other.
+void hs_search_batch_fsm(const DevModel* m, const OrTree* t, const SearchParams* sp, int64_t n, const int32_t* nodes, int64_t scratchKeys,
+                         SearchResult* out) {
+    const DevTree T = dev_tree(t);
+    const unsigned capK = (unsigned)scratchKeys, capP = 2 * capK + 6 * 1024, capA = 2048;
+    const int stackCap = (2 * tree_height(t) + 32 + 63) & ~63;
+    std::vector<uint32_t> key(capK + 64);
+    std::vector<double> pay(capP + 64), ais(capA);
+    std::vector<StackE> stack(stackCap);
+    ScratchD s;
+    s.key = key.data(); s.pay = pay.data(); s.ais = ais.data();
+    s.capK = capK; s.capP = capP; s.capA = capA; s.topK = s.topP = 0; s.err = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const int node = nodes[i];
+        SearchResult r;
+        r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
+        r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+        out[i] = r;
+        if (T.up[node] < 0) continue;
+        s.topK = s.topP = 0;
+        s.err = 0;
+        const int parent = T.up[node];
+        LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
+        if (n_mut(T, node)) vectUp = s_pass(*m, T, s, vectUp, node, false);
+        const LRef own = tree_list(T, 0, node);
+        if (!vectUp.k || !own.k) { out[i].status = s.err ? s.err : 2; continue; }
+        const double bestCurrentLK = f_append(*m, vectUp, own, T.isTip[node] != 0, T.dist[node]);
+        r.bestCurrentLK = bestCurrentLK;
+        if (!(bestCurrentLK < sp->thresholdTopologyPlacement || T.dist[node] != 0.0)) { r.status = 1; out[i] = r; continue; }  // :9674
+        Fsm f;
+        memset(&f, 0, sizeof f);
+        f.op = OP_NONE; f.pc = 0;
+        f.parent = parent;
+        f.child = (T.child0[parent] == node) ? 0 : 1;
+        f.bestLKdiff = bestCurrentLK;
+        f.removedBLen = T.dist[node];
+        f.phase1 = 0; f.rc = 0;
+        s.topK = s.topP = 0;
+        for (;;) {
+            fsm_step(f, *m, T, *sp, s, stack.data(), stackCap, 0 /* no warp scans */);
+            if (f.op == OP_DONE) break;
+            if (f.op == OP_APPEND) f.resD = f_append(*m, f.a1, f.a2, f.at1 != 0, f.ab1);
+            else if (f.op == OP_MERGE) {
+                Writer w;
+                w.init(s.key + s.topK, s.pay + s.topP);
+                if (f_merge(*m, f.a1, f.ab1, f.at1 != 0, f.a2, f.ab2, f.at2 != 0, f.aflags, w) == 0) f.resL = sc_commit(s, w.nk, w.np);
+                else f.resL = lnull();
+            } else if (f.op == OP_BLEN) f.resD = f_blen(*m, f.a1, f.a2, f.at1 != 0, s.ais);
+            else if (f.op == OP_DIFFER) f.resB = f_differ(*m, f.a1, f.a2) ? 1 : 0;
+            else { f.rc = 2; break; }  // OP_SCAN cannot be requested with scanMinSize == 0
+        }
+        fsm_finish(f, T, *sp, node, bestCurrentLK, r);
+        out[i] = r;
+    }
 }
 
 // k_place_samples, one sample after the other

@@ -28,6 +28,22 @@ static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline double min(double a, double b) { return std::fmin(a, b); }
 static inline double max(double a, double b) { return std::fmax(a, b); }
+// Compile-only stand-ins for the warp intrinsics of search_fsm.cuh: its warp-cooperative scan (warp_scan_job) is never executed
+// on the host (the state machine is driven with scanMinSize = 0, i.e. search variant 2); they only let the file compile so that
+// its lane-level state machine (fsm_step, fsm_finish) can run.
+struct uint4 { unsigned x, y, z, w; };
+struct HostIdx { unsigned x = 0, y = 0, z = 0; };
+static const HostIdx threadIdx, blockIdx;
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __match_any_sync(unsigned, int) { return 1u; }
+static inline unsigned __fns(unsigned, unsigned, int) { return 0u; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline long long clock64() { return 0; }
 using std::fabs;
 using std::fmax;
 using std::isfinite;

@@ -1,8 +1,9 @@
 """The CUDA source itself against the reference, without a GPU: the lane-level device code (likelihood.cuh, search.cuh,
-place.cuh -- what k_append / k_merge / k_blen / ... / k_spr_search (variant 1) / k_place_samples execute per thread) is compiled
-for the host by tests/hostsim and run through the same golden-vector checks as the oracle, plus oracle comparisons of whole
-searches and placements.  The warp-cooperative code of the default search kernel (search_fsm.cuh) needs the hardware and is
-covered by the -m gpu tests; its two per-lane append forms (site-converged, queued-site) are checked here too."""
+place.cuh, and the per-lane state machine of search_fsm.cuh -- what k_append / k_merge / k_blen / ... / k_spr_search (variant 1) /
+k_spr_search_fsm without its warp scans (variant 2) / k_place_samples execute per thread) is compiled for the host by
+tests/hostsim and run through the same golden-vector checks as the oracle, plus oracle comparisons of whole searches and
+placements.  The shuffle-based subtree scan of the default search kernel (warp_scan_job) needs the hardware and is covered by
+the -m gpu tests; its two per-lane append forms (site-converged, queued-site) are checked here too."""
 import math
 
 import numpy as np
@@ -65,14 +66,23 @@ def _prefilled_lists(g, orc):
     return pack_lists(flat, g["env"]["lRef"], g["env"]["usingErrorRate"])
 
 
+def _search(hs, kind, ta, lists, params, nodes, scratch_keys):
+    """kind 'straight': search_node (k_spr_search, variant 1); 'fsm': fsm_step / fsm_finish, the per-lane state machine of the
+    default kernel k_spr_search_fsm, driven like the kernel drives one lane, warp scans off (variant 2)."""
+    if kind == "fsm":
+        return hs.search_batch_fsm(ta, lists, params, nodes, scratch_keys=scratch_keys)
+    return hs.search_batch(ta, lists, params, nodes, scratch_keys=scratch_keys)
+
+
+@pytest.mark.parametrize("kind", ["straight", "fsm"])
 @pytest.mark.parametrize("name", NAMES)
-def test_straight_line_search_source_matches_oracle_and_reference(name):
+def test_straight_line_search_source_matches_oracle_and_reference(name, kind):
     g = load_golden(name)
     model = MapleModel.from_reference_snapshot(g["env"], g["model"])
     orc, hs = Oracle(model), KernelSourceOnHost(model)
     ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
     lists = _prefilled_lists(g, orc)
-    rec = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=8192)
+    rec = _search(hs, kind, ta, lists, search_params(g), nodes, 8192)
     ref = orc.search_batch(ta, lists, search_params(g), nodes, lazy_mode=1)
     for f in ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
         assert np.array_equal(rec[f], ref[f]), f
@@ -112,8 +122,9 @@ def test_scratch_exhaustion_is_reported_not_overrun():
     assert (rec["status"] == 3).any() and not math.isnan(float(rec["bestCurrentLK"].sum()))
 
 
+@pytest.mark.parametrize("kind", ["straight", "fsm"])
 @pytest.mark.parametrize("rv,err,strict,ml", [(False, False, True, False), (True, False, False, True), (True, True, False, False)])
-def test_straight_line_search_source_matches_oracle_on_synthetic_trees(rv, err, strict, ml):
+def test_straight_line_search_source_matches_oracle_on_synthetic_trees(rv, err, strict, ml, kind):
     """Same configurations as the device test (tests/test_gpu_search.py), on the host: rate variation, site-specific error model,
     strict and deep stop rules, ML-like branch lengths."""
     from maple_b200.synthetic import generate
@@ -130,7 +141,7 @@ def test_straight_line_search_source_matches_oracle_on_synthetic_trees(rv, err, 
           "thresholdLogLKoptimizationTopology": L, "thresholdLogLKconsecutivePlacement": 1.0,
           "effectivelyNon0BLen": 1.0 / (10 * model.lRef), "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "defaultBLen": 0.000033}
     nodes = np.array([i for i in range(len(d.up)) if d.up[i] >= 0], np.int32)
-    rec = hs.search_batch(ta, lists, sp, nodes, scratch_keys=1 << 15)
+    rec = _search(hs, kind, ta, lists, sp, nodes, 1 << 15)
     ref = orc.search_batch(ta, lists, sp, nodes, lazy_mode=1)
     for f in ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
         assert np.array_equal(rec[f], ref[f]), f
