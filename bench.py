@@ -187,6 +187,55 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def callers_extra(args, d, eng, tree, d_nodes):
+    """Side measurements on the same device-resident tree, after everything that is timed for the headline and each guarded on its
+    own: the other stop-rule setting of the search, and the callers either side of it: whole-tree log-likelihood
+    (calculateTreeLikelihood as one merge batch), the branch-length sweep with frozen lists (traverseTreeToOptimizeBranchLengths
+    fastPass as one maple_blen_batch launch) and the rebuild of all four list families (reCalculateAllGenomeLists)."""
+    import torch
+    from maple_b200.genome_list import pack_lists
+    out = {"note": "wall clock with a device synchronize on both sides, one run each after one warm-up where it is cheap"}
+
+    def timed(fn, warm=True):
+        if warm:
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        return r, time.perf_counter() - t0
+
+    try:
+        other = "fast" if args.round == "deep" else "deep"
+        p2 = round_params(type("A", (), {"round": other})(), d.model.lRef)
+        o, dt = timed(lambda: tree.spr_search(d_nodes, p2))
+        rec = tree.search_records(o)
+        out["search_round_" + other] = {"placements": int(rec["phase1"].sum()), "seconds": dt, "placements_per_s": float(rec["phase1"].sum()) / dt,
+                                        "searched": int((rec["status"] == 0).sum()), "proposals": int((rec["placement"] >= 0).sum())}
+    except Exception as e:
+        out["search_round_error"] = repr(e)[:300]
+    try:
+        lk, dt = timed(tree.tree_likelihood)
+        out["tree_likelihood"] = {"logLK": lk, "seconds": dt, "internal_nodes": int((tree.child0 >= 0).sum())}
+    except Exception as e:
+        out["tree_likelihood_error"] = repr(e)[:300]
+    try:
+        dist0 = tree.dist.copy()
+        (upd, dirty), dt = timed(lambda: tree.optimize_branch_lengths(1.0 / (10 * d.model.lRef)), warm=False)
+        out["fast_branch_length_sweep"] = {"branches": int(tree.n - 3), "updated": int(upd), "seconds": dt,
+                                           "mean_abs_change_in_mutations": float(abs(tree.dist - dist0).mean() * d.model.lRef)}
+        lists_t0 = time.perf_counter()
+        tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+        torch.cuda.synchronize()
+        out["recalculate_all_lists"] = {"nodes": int(tree.n), "seconds": time.perf_counter() - lists_t0,
+                                        "note": "includes packing the tip lists on the host"}
+        lk2 = tree.tree_likelihood()
+        out["fast_branch_length_sweep"]["logLK_after_sweep_and_rebuild"] = lk2
+    except Exception as e:
+        out["branch_length_sweep_error"] = repr(e)[:300]
+    return out
+
+
 def placement_extra(args):
     """Side measurement, outside every timed region and in its own processes (a failure there cannot take the headline down):
     maple_place_batch (findBestParentForNewSample for a batch of new samples on the same frozen tree) with the
@@ -359,7 +408,8 @@ def main():
                                 "gpu_matches_oracle_on_sample": bool(same),
                                 "max_abs_score_diff": float(np.max(np.abs(got["bestScore"][fin] - ref["bestScore"][fin]), initial=0.0))}
     if world == 1 and not args.no_extras and args.nseq >= 20000:
-        line["extra"] = {"placement_batch": placement_extra(args)}
+        line["extra"] = callers_extra(args, d, eng, tree, d_nodes)
+        line["extra"]["placement_batch"] = placement_extra(args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -12,6 +12,7 @@ express every list relative to the reference genome (the reference's --noLocalRe
 from __future__ import annotations
 
 import ctypes as C
+import itertools
 from typing import List, Optional
 
 import numpy as np
@@ -22,6 +23,7 @@ from .engine import MapleEngine, MergeResult, _dp
 from .genome_list import PackedLists, pack_lists, decode_stream
 
 FAM_LOWER, FAM_UPRIGHT, FAM_UPLEFT, FAM_TOTUP = 0, 1, 2, 3
+_EPOCH = itertools.count(1)  # one sequence for all arenas: a rebuilt arena never repeats an epoch a tree was bound at
 
 
 class ListArena:
@@ -40,11 +42,11 @@ class ListArena:
         self.key_tail = 0
         self.pay_tail = 0
         self.lRef, self.U = engine.model.lRef, int(engine.model.usingErrorRate)
-        self.epoch = 0  # bumped whenever the tables or streams move in memory: holders of raw pointers (maple_tree_bind) rebind
+        self.epoch = 0  # renewed whenever the tables or streams move in memory: holders of raw pointers (maple_tree_bind) rebind
         self._bind()
 
     def _bind(self):
-        self.epoch += 1
+        self.epoch = next(_EPOCH)
         self.eng.lists = self
         rc = self.eng.lib.maple_lists_bind(self.eng.ctx, _dp(self.key), _dp(self.pay), _dp(self.key_start), _dp(self.pay_start), self.n)
         capi.check(self.eng.ctx, rc, "maple_lists_bind")
