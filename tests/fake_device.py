@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from maple_b200.engine import MapleEngine
-from oracle.oracle import Oracle
+from oracle.oracle import Oracle, OrTree
 
 
 def _arr(ptr, n, dtype):
@@ -99,6 +99,52 @@ class FakeLib:
             nk_[i], np_[i] = a.value, b.value
         return 0
 
+    # ---- the search seam and placement batches: the kernel source on the host (tests/hostsim), which sizes its scratch like the
+    # device does (status 3 when it is exhausted) -- so the retry logic of the wrappers can be exercised too
+    def maple_tree_bind(self, ctx, n, root, up, c0, c1, dist, isTip, mutStart, mut, nkeys, npay):
+        self.tree = (n, root, up, c0, c1, dist, isTip, mutStart, mut, nkeys, npay)
+        return 0
+
+    def _or_tree(self):
+        n, root, up, c0, c1, dist, isTip, mutStart, mut, nkeys, npay = self.tree
+        t = OrTree()
+        t.nNodes, t.root = n, root
+        t.up, t.child0, t.child1, t.dist, t.isTip, t.mutStart, t.mut = up, c0, c1, dist, isTip, mutStart, mut
+        t.key, t.pay, t.keyStart, t.payStart, t.nkeys = self.key, self.pay, self.ks, self.ps, nkeys
+        return t
+
+    def _hs(self):
+        from hostsim import lib
+        return lib()
+
+    def maple_ctx_set_place_variant(self, ctx, variant):
+        self.place_variant = variant
+        return 0
+
+    def maple_place_batch(self, ctx, params, n, sampleLists, out, scratch_keys, stream):
+        self.launches += 1
+        ids = _arr(sampleLists, n, np.int32).astype(np.int64)
+        ks, ps = _arr(self.ks, self.n, np.int64), _arr(self.ps, self.n, np.int64)
+        nkeys_all = _arr(self.tree[9], self.n, np.int32)
+        sks, sps, snk = np.ascontiguousarray(ks[ids]), np.ascontiguousarray(ps[ids]), np.ascontiguousarray(nkeys_all[ids])
+        t = self._or_tree()
+        keys = scratch_keys if scratch_keys > 0 else 4096
+        variant = getattr(self, "place_variant", 0)
+        has_mut = self.tree[7] is not None and int(_arr(self.tree[7], self.tree[0] + 1, np.int32)[-1]) > 0
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        if variant == 0 or (variant == 1 and has_mut):
+            self._hs().or_place_batch(self.mp, C.addressof(t), params, n, self.key, self.pay, p(sks), p(sps), p(snk), keys, out)
+        else:
+            self._hs().hs_place_batch_scan(self.mp, C.addressof(t), params, n, self.key, self.pay, p(sks), p(sps), p(snk), keys, self.tree[10],
+                                           variant - 1, out)
+        return 0
+
+    def maple_spr_search_batch(self, ctx, params, n, nodes, out, scratch_keys, max_concurrent, cycles, stream):
+        self.launches += 1
+        t = self._or_tree()
+        self._hs().hs_search_batch_fsm(self.mp, C.addressof(t), params, n, nodes, scratch_keys if scratch_keys > 0 else 8192, out)
+        return 0
+
     def maple_last_error(self, ctx):
         return b""
 
@@ -119,6 +165,10 @@ class FakeEngine(MapleEngine):
 
     def _stream(self):
         return None
+
+    def set_place_variant(self, variant: int):
+        self.lib.maple_ctx_set_place_variant(None, int(variant))
+        self.place_variant = int(variant)
 
     def update_model(self):
         self.lib = FakeLib(Oracle(self.model, with_root_tables=True), self)

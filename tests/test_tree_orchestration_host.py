@@ -62,3 +62,81 @@ def test_fast_sweep_through_device_tree_code(name, which):
     # the frozen tree's likelihood is still the reference's (lists untouched by the sweep)
     if which == "frozen":
         assert abs(tree.tree_likelihood() - g["treeLK"]) <= 1e-6
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+def test_place_samples_wrapper_and_its_retries(variant):
+    """DeviceTree.place_samples over the stand-in library (the kernel source on the host behind it): samples are appended to the
+    arena, the tree is re-bound, and samples whose scratch (here: a bestNodes table of 1 024 entries under very permissive rules) is
+    exhausted come back with status 3 and are re-run with 8x the scratch through variant 0, whatever variant the batch started on."""
+    import math
+    from maple_b200 import capi
+    from maple_b200.genome_list import pack_lists
+    from maple_b200.synthetic import generate
+    from oracle.oracle import Oracle
+    from test_place_scan_host import _mutated
+    d = generate(1500, lRef=4000, mean_diffs=8.0, rate_variation=False, seed=21)
+    model = d.model
+    eng = FakeEngine(model)
+    tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+    tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, model.lRef, 0))
+    L = math.log(model.lRef)
+    pp = {"strictStopRules": 0, "allowedFails": 8, "deeperSearchForLongBranches": 0, "onlyFindIdentical": 0, "thresholdLogLK": 40.0 * L,
+          "thresholdLogLKoptimization": 6.0 * L, "thresholdLogLKconsecutivePlacement": 0.01, "effectivelyNon0BLen": 1.0 / (10 * model.lRef),
+          "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "oneMutBLen": 1.0 / model.lRef}
+    p = capi.PlaceParams()
+    for k, v in pp.items():
+        setattr(p, k, v)
+    samples = pack_lists(_mutated(d.tip_lists, model.refIdx, 24), model.lRef, 0)
+    ta = {"up": tree.up, "child0": tree.child0, "child1": tree.child1, "dist": tree.dist, "isTip": tree.isTip, "root": tree.root}
+    ref = Oracle(model).place_batch(ta, tree.arena.to_host(), pp, samples)
+    eng.set_place_variant(variant)
+    first = []
+    orig = eng.lib.maple_place_batch
+
+    def spy(ctx, params, n, sampleLists, out, scratch_keys, stream):
+        rc = orig(ctx, params, n, sampleLists, out, scratch_keys, stream)
+        first.append((n, scratch_keys, getattr(eng.lib, "place_variant", 0)))
+        return rc
+
+    eng.lib.maple_place_batch = spy
+    rec = tree.place_samples(samples, p)
+    for f in ("bestNode", "status", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
+        assert np.array_equal(rec[f], ref[f]), f
+    assert len(first) >= 2 and first[0][0] == 24 and first[1][0] < 24 and first[1][1] == 8 * 4096  # some samples were re-run with 8x
+    assert first[0][2] == variant and all(c[2] == 0 for c in first[1:])  # the re-runs go through variant 0
+    assert eng.place_variant == variant  # and the batch variant is restored
+
+
+@pytest.mark.parametrize("name", ["ex_unrest", "ay_unrest_300"])
+def test_search_seam_wrapper_on_reference_trees(name):
+    """start_topology_updates_parallel (the drop-in for Pool.map(startTopologyUpdatesParallel) + sort, :12283-12312) over the
+    stand-in library: prepare_search fills the zero-length root children, binds the tree, the searches run (here: the kernel's
+    per-lane state machine on the host), scratch-exhausted searches are re-run with more, and the moves come back sorted as the
+    reference sorts them -- equal to the oracle's, and to the reference's own proposedMoves where its lazy fill plays no role."""
+    from maple_b200 import capi
+    from maple_b200.search import dirty_nodes, start_topology_updates_parallel
+    from oracle.oracle import Oracle
+    from tree_fixture import search_params, searched_nodes
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    a = tree_arrays(g)
+    eng = FakeEngine(model)
+    tree = DeviceTree.from_lists(eng, a["up"], a["child0"], a["child1"], a["dist"], a["root"], a["isTip"], tree_lists(g),
+                                 mutStart=a["mutStart"], mut=a["mut"], numMinor=a["numMinor"])
+    p = capi.SearchParams()
+    for k, v in search_params(g).items():
+        setattr(p, k, v)
+    t = g["tree"]
+    nodes = dirty_nodes(tree, t["dirty"], t["replacements"], g["env"]["maxReplacements"])
+    assert sorted(nodes.tolist()) == sorted(searched_nodes(g))
+    tree.tree_likelihood()  # moves the arena tables (temporary lists): the search must notice and bind again
+    moves, rec = start_topology_updates_parallel(tree, p, nodes, scratch_keys=256)  # small scratch: some searches are re-run
+    ref = Oracle(model).search_batch(a, tree_lists(g), search_params(g), nodes, lazy_mode=1)
+    for f in ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
+        assert np.array_equal(rec[f], ref[f]), f
+    want = sorted(((int(n), int(r["placement"]), float(r["improvement"])) for n, r in zip(nodes, ref) if r["placement"] >= 0), key=lambda m: m[2])
+    assert [m[:2] for m in moves] == [m[:2] for m in want] and all(abs(x[2] - y[2]) <= 1e-9 for x, y in zip(moves, want))
+    assert moves == sorted(moves, key=lambda m: m[2])
+    assert sorted(m[:2] for m in moves) == sorted((m[0], m[1]) for core in g["proposed"] for m in core)  # the reference's own proposedMoves
+    assert (rec["status"] == 0).sum() > 50
