@@ -362,7 +362,8 @@ __device__ int place_jump(PlaceWarpMat& X, int nWin) {
 // window's parent links.  The running best before a node is taken as the prefix maximum of ALL earlier scores of the window, which
 // is right unless a node the walk does not reach holds a score above it; that is checked, and such a window is left to the serial
 // replay (returns false, nothing committed).  Everything after the first reached leaf that absorbs the sample is void.
-__device__ bool place_replay_parallel(const PlaceParams& pp, PlaceWarpMat& X, const PlaceWarpScratch& ws, int pos) {
+__device__ bool place_replay_parallel(const DevModel& m, const DevTree& t, const PlaceParams& pp, PlaceWarpMat& X, const PlaceWarpScratch& ws,
+                                      int pos) {
     PlaceWarp& W = X.w;
     const int nWin = W.nWin;
     // ---- running best before every node: exclusive prefix maximum of the scores (Hillis-Steele over the window)
@@ -442,6 +443,13 @@ __device__ bool place_replay_parallel(const PlaceParams& pp, PlaceWarpMat& X, co
     WARP_SYNC();
     cur = place_jump<2>(X, nWin);
     if (cur < 0) return false;
+    // ---- leaf comparisons (:7975-7984), only for the leaves the walk reaches
+    FOR_LANES(lane) {
+        for (int w = lane; w < nWin; w += 32)
+            if ((W.winInfo[w] & 2) && X.ival[cur][w])
+                W.winMinor[w] = dev_is_minor(m.lRef, tree_list(t, 0, W.winNode[w]), W.diffs, pp.onlyFindIdentical != 0);
+    }
+    WARP_SYNC();
     // ---- the first reached leaf that absorbs the sample, anomalies, and the check of the prefix-maximum assumption
     FOR_LANES(lane) {
         int cut = nWin, bad = 0, anomaly = nWin;
@@ -697,12 +705,14 @@ __device__ void place_sample_warp_mat(const DevModel& m, const DevTree& t, const
                 const int w = W.slot[lane];
                 if (w >= 0) W.winScore[w] = p_append_sitewise(m, tree_list(t, 3, W.winNode[w]), W.diffs, one);
             }
+            WARP_SYNC();
+            if (PAR && place_replay_parallel(m, t, pp, X, ws, pos)) continue;  // it compares only the leaves the walk reaches
+            // the reference's loop body over the window, in order (lane 0), on the comparisons of every leaf of the window
             FOR_LANES(lane) {
                 for (int w = lane; w < W.nWin; w += 32)
                     if (W.winInfo[w] & 2) W.winMinor[w] = dev_is_minor(m.lRef, tree_list(t, 0, W.winNode[w]), W.diffs, pp.onlyFindIdentical != 0);
             }
             WARP_SYNC();
-            if (PAR && place_replay_parallel(pp, X, ws, pos)) continue;  // else: the reference's loop body over the window, in order (lane 0)
             FOR_LANES(lane) {
                 if (lane == 0) {
                     int j = 0;
