@@ -356,6 +356,60 @@ __device__ int place_jump(PlaceWarpMat& X, int nWin) {
     return -1;
 }
 
+// Inclusive prefix sum over the 32 lane values in X.ival[0][0..31] (Hillis-Steele, double-buffered); returns the buffer holding it.
+__device__ int place_lane_scan(PlaceWarpMat& X) {
+    int cur = 0;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nxt = cur ^ 1;
+        FOR_LANES(lane) { X.ival[nxt][lane] = lane >= o ? X.ival[cur][lane] + X.ival[cur][lane - o] : X.ival[cur][lane]; }
+        WARP_SYNC();
+        cur = nxt;
+    }
+    return cur;
+}
+
+// Tree reductions over the per-lane partials redD (max), redI (sum), redJ (max), redK (min), in place; results in element 0.
+// A round only writes elements below its stride and only reads elements at or above it from other lanes.
+__device__ void place_lane_reduce(PlaceWarpMat& X) {
+    for (int o = 16; o > 0; o >>= 1) {
+        FOR_LANES(lane) {
+            if (lane < o) {
+                X.redD[lane] = fmax(X.redD[lane], X.redD[lane + o]);
+                X.redI[lane] += X.redI[lane + o];
+                X.redJ[lane] = max(X.redJ[lane], X.redJ[lane + o]);
+                X.redK[lane] = min(X.redK[lane], X.redK[lane + o]);
+            }
+        }
+        WARP_SYNC();
+    }
+}
+
+// The nodes of the window that need a score, in order, one per lane; the window ends before the 33rd (parallel form of the loop
+// in place_sample_warp).  Three consecutive positions per lane, a prefix sum over the lanes.
+__device__ void place_assign_slots(PlaceWarpMat& X, int nWin0) {
+    PlaceWarp& W = X.w;
+    FOR_LANES(lane) {
+        int c = 0;
+        for (int w = 3 * lane; w < 3 * lane + 3 && w < nWin0; w++) c += W.winInfo[w] & 1;
+        X.ival[0][lane] = c;
+        W.slot[lane] = -1;
+        if (lane == 0) W.nWin = nWin0;
+    }
+    WARP_SYNC();
+    const int cur = place_lane_scan(X);
+    FOR_LANES(lane) {
+        int k = lane > 0 ? X.ival[cur][lane - 1] : 0;
+        for (int w = 3 * lane; w < 3 * lane + 3 && w < nWin0; w++) {
+            if (W.winInfo[w] & 1) {
+                if (k < 32) W.slot[k] = w;
+                else if (k == 32) W.nWin = w;
+                k++;
+            }
+        }
+    }
+    WARP_SYNC();
+}
+
 // The window replay of place_sample_warp in parallel form.  What a node hands to its children -- LKdiff (its own score, or the
 // inherited one when it is not scored) and failedPasses (reset on a new best, +1 on a consecutive worsening, else inherited) --
 // are chains over ancestors, and "reached" is the AND of the ancestors' stop-rule outcomes: three pointer-jumping passes over the
@@ -462,13 +516,13 @@ __device__ bool place_replay_parallel(const DevModel& m, const DevTree& t, const
                 if (info & 4) anomaly = min(anomaly, w);
             } else if ((info & 1) && W.winScore[w] > X.bb[w]) bad = 1;
         }
-        X.redI[lane] = cut; X.redJ[lane] = bad; X.redK[lane] = anomaly;
+        X.redD[lane] = 0.0; X.redI[lane] = bad; X.redJ[lane] = -anomaly; X.redK[lane] = cut;  // sum, max, min of the tree below
     }
     WARP_SYNC();
+    place_lane_reduce(X);
     FOR_LANES(lane) {
         if (lane == 0) {
-            int cut = nWin, bad = 0, anomaly = nWin;
-            for (int i = 0; i < 32; i++) { cut = min(cut, X.redI[i]); bad |= X.redJ[i]; anomaly = min(anomaly, X.redK[i]); }
+            const int cut = X.redK[0], bad = X.redI[0], anomaly = -X.redJ[0];
             X.cutW = cut;
             // a leaf that absorbs the sample ends the walk before anything else at that node; an anomaly before it sends the
             // sample to the straight-line walk; a wrong running best anywhere in the window sends the window to the serial replay
@@ -497,34 +551,26 @@ __device__ bool place_replay_parallel(const DevModel& m, const DevTree& t, const
             }
             target = max(target, (fl & 2) ? w + 1 : w + W.winSize[w]);
         }
-        X.redD[lane] = mx;
-        X.redI[lane] = nScored | (nMissed << 16);
-        X.redJ[lane] = nQueued;
-        X.redK[lane] = (lastNb < 0 ? 0xff : lastNb) | (target << 8);  // lastNb < 96; the target can lie far beyond the window
+        X.redD[lane] = mx;                        // max
+        X.redI[lane] = nScored | (nMissed << 16);  // sum
+        X.redJ[lane] = lastNb;                    // max (-1: none)
+        X.redK[lane] = -target;                   // min, i.e. the largest target
+        X.ival[0][lane] = nQueued;                // prefix sum: where the lane's bestNodes entries go
     }
     WARP_SYNC();
+    place_lane_reduce(X);
+    const int qcur = place_lane_scan(X);
     FOR_LANES(lane) {
         if (lane == 0) {
-            int nScored = 0, nMissed = 0, q = 0, lastNb = -1, target = 0;
-            double mx = W.best;
-            for (int i = 0; i < 32; i++) {
-                mx = fmax(mx, X.redD[i]);
-                nScored += X.redI[i] & 0xffff;
-                nMissed += X.redI[i] >> 16;
-                const int nq = X.redJ[i];
-                X.redJ[i] = q;  // exclusive prefix: where lane i's entries go
-                q += nq;
-                const int ln = X.redK[i] & 0xff, tg = X.redK[i] >> 8;
-                if (ln != 0xff) lastNb = max(lastNb, ln);
-                target = max(target, tg);
-            }
+            const int nScored = X.redI[0] & 0xffff, nMissed = X.redI[0] >> 16, lastNb = X.redJ[0], target = -X.redK[0];
+            const int q = X.ival[qcur][31];
             if (W.nQ + q > ws.bestCap) { W.state = 3; X.committed = 2; }
             else {
                 X.qBase = W.nQ;
                 W.nQ += q;
                 W.phase1 += nScored;
                 W.missed += nMissed;
-                W.best = mx;
+                W.best = fmax(W.best, X.redD[0]);
                 if (lastNb >= 0) { W.bestNode = W.winNode[lastNb]; X.jobNewBest = 1; }
                 X.maxTarget = target;
                 if (cutW < nWin) { W.state = 1; W.minorNode = W.winNode[cutW]; }
@@ -538,7 +584,7 @@ __device__ bool place_replay_parallel(const DevModel& m, const DevTree& t, const
     // reaches beyond the position the walk continues at (the ancestors of the next node; one per depth)
     const int maxTarget = X.maxTarget;
     FOR_LANES(lane) {
-        int at = X.qBase + X.redJ[lane];
+        int at = X.qBase + (lane > 0 ? X.ival[qcur][lane - 1] : 0);
         for (int w = 3 * lane; w < 3 * lane + 3 && w < cutW; w++) {
             const int info = W.winInfo[w], fl = X.flags[w];
             if (!(fl & 4)) continue;
@@ -687,20 +733,23 @@ __device__ void place_sample_warp_mat(const DevModel& m, const DevTree& t, const
                 }
             }
             WARP_SYNC();
-            FOR_LANES(lane) {
-                if (lane == 0) {
-                    int nWin = min(kPWin, end - pos), k = 0;
-                    for (int w = 0; w < nWin; w++) {
-                        if (W.winInfo[w] & 1) {
-                            if (k == 32) { nWin = w; break; }
-                            W.slot[k++] = w;
+            if (PAR) place_assign_slots(X, min(kPWin, end - pos));
+            else {
+                FOR_LANES(lane) {
+                    if (lane == 0) {
+                        int nWin = min(kPWin, end - pos), k = 0;
+                        for (int w = 0; w < nWin; w++) {
+                            if (W.winInfo[w] & 1) {
+                                if (k == 32) { nWin = w; break; }
+                                W.slot[k++] = w;
+                            }
                         }
+                        for (; k < 32; k++) W.slot[k] = -1;
+                        W.nWin = nWin;
                     }
-                    for (; k < 32; k++) W.slot[k] = -1;
-                    W.nWin = nWin;
                 }
+                WARP_SYNC();
             }
-            WARP_SYNC();
             FOR_LANES(lane) {
                 const int w = W.slot[lane];
                 if (w >= 0) W.winScore[w] = p_append_sitewise(m, tree_list(t, 3, W.winNode[w]), W.diffs, one);
