@@ -20,6 +20,13 @@
 // Samples the scan does not cover fall back to place_sample() on lane 0 with the warp's whole scratch: trees with MAT
 // mutations, --deeperSearchForLongBranches, a root without children, a sample list shorten() would change, a scored node
 // without probVectTotUp (the reference raises there).
+//
+// Three entry points, kept apart until each has been timed on hardware:
+//   place_sample_warp            variant 1: MAT-free trees, one-lane window replay -- the form that has run on a B200;
+//   place_sample_warp_mat<false> variant 2: MAT trees covered (lane 0 walks above mutation-carrying nodes, mutation-free subtrees
+//                                are scan jobs), one-lane window replay;
+//   place_sample_warp_mat<true>  variant 3: variant 2 with every per-window step in parallel form (slots by prefix sum, replay by
+//                                prefix maximum + pointer jumping, reductions as trees, leaf comparisons only where reached).
 #pragma once
 #include "place.cuh"
 
