@@ -433,6 +433,53 @@ def harvest_extras(G, tree, root, name):
     return ex
 
 
+def harvest_fuzz(G, tree, root, seed, steps=2500):
+    """A random chain of list operations (tests/fuzz_chain.py) run with the REFERENCE's own functions under the model of this run:
+    digests of every output list and every scalar, for inputs far outside what the run itself produced."""
+    import copy
+    sys.path.insert(0, os.path.dirname(HERE))
+    import fuzz_chain
+
+    class Ref:
+        def merge(self, a, b1, t1, b, b2, t2, lk, updown, nm1, nm2):
+            try:
+                return G["mergeVectors"](a, b1, t1, b, b2, t2, returnLK=lk, isUpDown=updown, numMinor1=nm1, numMinor2=nm2)
+            except Exception as e:  # with returnLK an impossible merge raises Exception("exit") instead of returning None (:4753-4758)
+                if e.args != ("exit",):
+                    raise
+                return None
+
+        def append(self, a, b, tip, bl):
+            return G["appendProbNode"](a, b, tip, bl)
+
+        def blen(self, a, b, tip):
+            r = G["estimateBranchLengthWithDerivative"](a, b, fromTipC=tip)
+            return None if r is False else r
+
+        def differ(self, a, b):
+            return G["areVectorsDifferent"](a, b)
+
+        def root_vector(self, a, bl, tip):
+            return G["rootVector"](a, bl, tip, flat, 0)  # a one-node tree without MAT mutations: the list is taken as it is
+
+        def prob_root(self, a):
+            return G["findProbRoot"](a)
+
+        def shorten(self, a):
+            v = copy.deepcopy(list(a))
+            G["shorten"](v)
+            return v
+
+    import types
+    flat = types.SimpleNamespace(up=[None], mutations=[[]])
+    plain = {"up": tree.up, "mutations": [m or [] for m in tree.mutations]}
+    lower, upper = fuzz_chain.initial_pools(plain, lambda fam, i: getattr(tree, fam)[i])
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        res = fuzz_chain.run_chain(Ref(), lower, upper, G["lRef"], seed, steps)
+    return {"seed": seed, "steps": steps, "results": res}
+
+
 ENV_KEYS = ["lRef", "rootFreqs", "usingErrorRate", "errorRateSiteSpecific", "useRateVariation",
             "thresholdLogLKoptimizationTopology", "thresholdLogLKconsecutivePlacement", "deeperSearchForLongBranches",
             "BLenThresholdDeeperSearch", "effectivelyNon0BLen", "minBLenSensitivity", "thresholdProb",
@@ -519,6 +566,8 @@ class Harvest:
                     rec.calls["rootVector"].append({"v": T.add(v), "bLen": bl, "isFromTip": bool(tip), "out": T.add(r)})
             placements, place_env = harvest_placements(G, tree, root, T)
             self.extras = harvest_extras(G, tree, root, self.name)
+            self.extras["fuzz"] = harvest_fuzz(G, tree, root, seed=sum(map(ord, self.name)))
+            print("[golden] %s fuzz chain: %d steps" % (self.name, len(self.extras["fuzz"]["results"])), file=sys.stderr)
             rec.install()
             try:
                 results = [func(x) for x in inputs]
