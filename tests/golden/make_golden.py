@@ -342,7 +342,9 @@ def _plain_tree(tree, root, T=None):
     collapse of reCalculateAllGenomeLists(firstSetUp=True), :6108)."""
     out = {"root": root, "up": list(tree.up), "children": [None if c is None else list(c) for c in tree.children],
            "dist": [float(d) if d else 0.0 for d in tree.dist], "name": list(tree.name),
-           "minorSequences": [list(m) for m in tree.minorSequences], "dirty": [bool(d) for d in tree.dirty]}
+           "minorSequences": [list(m) for m in tree.minorSequences], "dirty": [bool(d) for d in tree.dirty],
+           "replacements": list(getattr(tree, "replacements", [0] * len(tree.up))),
+           "coreNum": list(getattr(tree, "coreNum", [None] * len(tree.up)))}
     if T is not None:
         for fam in ("probVect", "probVectUpRight", "probVectUpLeft", "probVectTotUp"):
             out[fam] = [T.add(v) for v in getattr(tree, fam)]
@@ -430,7 +432,39 @@ def harvest_extras(G, tree, root, name):
     print("[golden] %s extras: newick %d/%d chars, loaded LK %r, sweep updates fast %d / sequential %d, perturbed %d / %d" % (
         name, len(nw["binary"]), len(nw["multi"]), ex["read"]["binary"]["loadedLK"], sweeps["fastPass"]["updates"],
         sweeps["sequential"]["updates"], sweeps["perturbed_fastPass"]["updates"], sweeps["perturbed_sequential"]["updates"]), file=sys.stderr)
+    ex["_perturbed_tree"] = tp
     return ex
+
+
+def harvest_rounds(G, func, inputs, trees, root):
+    """startTopologyUpdatesParallel (:9580) of the reference under the stop rules the main fixture does not cover: the DEEP rules of the
+    later rounds (module globals strictTopologyStopRules / allowedFailsTopology / thresholdLogLKtopology, :12155-12159) on the frozen
+    tree, and both settings on the copy with perturbed branch lengths (recalculated lists, part of the nodes dirty).  Every search is
+    recorded as in the main fixture; each run gets its own deep copy (the reference fills probVectTotUp lazily while it searches)."""
+    import copy
+    tail = tuple(inputs[0][7:])
+    settings = {"deep": (G["strictTopologyStopRules"], G["allowedFailsTopology"], G["thresholdLogLKtopology"], G["thresholdTopologyPlacement"]),
+                "fast": tuple(inputs[0][3:7])}
+    out = {}
+    buf = io.StringIO()
+    for tname, tr in trees.items():
+        for sname, (strict, fails, thr, thrPlace) in settings.items():
+            if tname == "frozen" and sname == "fast":
+                continue  # the main fixture
+            tc = copy.deepcopy(tr)
+            rec = Recorder(G, 0)
+            rec.install()
+            try:
+                with contextlib.redirect_stdout(buf):
+                    results = [func((tc, root, core, strict, fails, thr, thrPlace) + tail) for core in range(len(inputs))]
+            finally:
+                rec.uninstall()
+            out[tname + "_" + sname] = {"params": {"strict": bool(strict), "fails": fails, "thr": thr, "thrPlace": thrPlace, "numCores": len(inputs)},
+                                        "searches": rec.searches, "proposed": [[list(m) for m in r] for r in results],
+                                        "phase1Total": rec.phase1}
+            print("[golden] round %s/%s: %d searches, %d candidates, %d proposals" % (
+                tname, sname, len(rec.searches), rec.phase1, sum(len(r) for r in results)), file=sys.stderr)
+    return out
 
 
 def harvest_fuzz(G, tree, root, seed, steps=2500):
@@ -566,6 +600,8 @@ class Harvest:
                     rec.calls["rootVector"].append({"v": T.add(v), "bLen": bl, "isFromTip": bool(tip), "out": T.add(r)})
             placements, place_env = harvest_placements(G, tree, root, T)
             self.extras = harvest_extras(G, tree, root, self.name)
+            tp = self.extras.pop("_perturbed_tree")
+            self.extras["rounds"] = harvest_rounds(G, func, inputs, {"frozen": tree, "perturbed": tp}, root)
             self.extras["fuzz"] = harvest_fuzz(G, tree, root, seed=sum(map(ord, self.name)))
             print("[golden] %s fuzz chain: %d steps" % (self.name, len(self.extras["fuzz"]["results"])), file=sys.stderr)
             rec.install()
