@@ -47,6 +47,7 @@ CONFIGS = {
                          ["--model", "UNREST", "--rateVariation", "--estimateSiteSpecificErrorRate"], 400),
     "ex_unrest_err": (EX + "MAPLE_alignment_example.txt", None, ["--model", "UNREST", "--estimateErrorRate"], 250),
     "ay_unrest_300": (EX + "sameRef_AY.4.2.2.maple.gz", 300, ["--model", "UNREST"], 300),
+    "ay_unrest_1000": (EX + "sameRef_AY.4.2.2.maple.gz", 1000, ["--model", "UNREST", "--rateVariation"], 40),
     "ay_unrest_deep_200": (EX + "sameRef_AY.4.2.2.maple.gz", 200,
                            ["--model", "UNREST", "--deeperSearchForLongBranches"], 100),
 }

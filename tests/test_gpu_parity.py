@@ -6,7 +6,7 @@ Bar: merged lists, branch lengths, list comparisons bit-exact; log-likelihood sc
 import numpy as np
 import pytest
 
-from golden_io import golden_names, load_golden
+from golden_io import hw_names as golden_names, load_golden
 from maple_b200.genome_list import lists_equal, pack_lists
 from maple_b200.model import MapleModel
 

@@ -4,7 +4,7 @@ minor-sequence verdict, number of candidate branches and branch lengths identica
 import numpy as np
 import pytest
 
-from golden_io import golden_names, load_golden
+from golden_io import hw_names as golden_names, load_golden
 from maple_b200.genome_list import pack_lists
 from maple_b200.model import MapleModel
 from test_oracle_placement_golden import check_placements, place_params

@@ -5,9 +5,9 @@ Bar: identical best node, branch lengths, phase-1 candidate counts and proposed 
 import numpy as np
 import pytest
 
-from golden_io import golden_names, load_golden
+from golden_io import hw_names as golden_names, load_golden
 from maple_b200.model import MapleModel
-from tree_fixture import search_params as fixture_params, searched_nodes, tree_arrays, tree_lists
+from tree_fixture import compare_with_reference_searches, search_params as fixture_params, searched_nodes, tree_arrays, tree_lists
 
 pytestmark = pytest.mark.gpu
 
@@ -48,26 +48,17 @@ def test_search_vs_reference_goldens(name, variant):
                                  ta["mutStart"], ta["mut"], ta["numMinor"])
     nodes = np.array(searched_nodes(g), np.int32)
     tree.prepare_search()
-    rec = tree.search_records(tree.spr_search(nodes, _capi_params(fixture_params(g))))
+    # the straight-line kernel has no on-device retry of searches that exhaust their scratch: on the 1 000-sequence tree give it
+    # what its longest search needs (the other variants re-run such searches with 8x on their own)
+    big = variant == 1 and len(nodes) > 500
+    rec = tree.search_records(tree.spr_search(nodes, _capi_params(fixture_params(g)), scratch_keys=(1 << 15) if big else 0,
+                                              max_concurrent=4096 if big else 0))
     # (b) identical to the oracle with the same (pre-filled) probVectTotUp policy
     ref = Oracle(model).search_batch(ta, lists, fixture_params(g), nodes, lazy_mode=1)
     _compare(rec, ref, nodes)
-    # (a) identical to the reference wherever its order-dependent lazy fill (:7198-7200) plays no role
+    # (a) the reference's own record of every search whose outcome does not depend on its lazy fill order, and its proposedMoves
     lazy = Oracle(model).search_batch(ta, lists, fixture_params(g), nodes, lazy_mode=0)
-    same = np.array([a == b for a, b in zip(lazy, ref)])
-    by_node = {int(n): r for n, r in zip(nodes, rec)}
-    t = g["tree"]
-    checked = 0
-    for s in g["searches"]:
-        pruned = t["children"][s["node"]][s["child"]]
-        if not same[list(nodes).index(pruned)]:
-            continue
-        r = by_node[pruned]
-        assert r["status"] == 0 and r["bestNode"] == s["bestNode"] and r["phase1"] == s["phase1"]
-        assert [r["bLenTop"], r["bLenBottom"], r["bLenAppend"]] == [float(x) for x in s["blens"]]
-        assert r["bestScore"] == s["bestScore"] or abs(r["bestScore"] - s["bestScore"]) <= 1e-9
-        checked += 1
-    assert checked >= 0.8 * len(g["searches"])
+    compare_with_reference_searches(g, nodes, rec, lazy, ref)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])

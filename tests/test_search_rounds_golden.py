@@ -3,8 +3,8 @@ harvest_rounds): the DEEP stop rules of its later rounds -- the rules bench.py m
 on a copy with perturbed branch lengths, recalculated lists and part of the nodes dirty (28-40 accepted proposals per round).
 The oracle must reproduce every search (best node, branch lengths, candidate count identical, scores within 1e-9, the same
 proposedMoves); the CUDA source on the host (straight-line search and the per-lane state machine of the default kernel) must equal
-the oracle search by search, and the reference in everything but the candidate count of searches that reach a zero-length child
-of the root (one more there, see the test)."""
+the oracle search by search, and the reference's record of every search whose outcome does not depend on the order in which the
+reference fills probVectTotUp of zero-length children of the root (tree_fixture.compare_with_reference_searches)."""
 import numpy as np
 import pytest
 
@@ -13,7 +13,7 @@ from hostsim import KernelSourceOnHost
 from maple_b200.model import MapleModel
 from oracle.oracle import Oracle
 from test_kernel_source_host import _prefilled_lists
-from tree_fixture import search_params, searched_nodes, tree_arrays, tree_lists
+from tree_fixture import compare_with_reference_searches, search_params, searched_nodes, tree_arrays, tree_lists
 
 ROUNDS = ["frozen_deep", "perturbed_deep", "perturbed_fast"]
 
@@ -71,20 +71,5 @@ def test_cuda_source_reproduces_the_round(name, rnd, kind):
         assert np.array_equal(rec[f], ref[f]), f
     for f in ("bestCurrentLK", "bestScore", "improvement"):
         assert np.max(np.abs(rec[f] - ref[f])) <= 1e-9, f
-    # Against the reference itself: the device fills probVectTotUp of a zero-length child of the root before the round, the reference
-    # lazily and order-dependently during it (:7198-7200).  The only trace of that in any recorded round: such a
-    # child counts as one more scored candidate in the searches that reach it; node, lengths and score of every search are the same.
-    by_node = {int(n): r for n, r in zip(nodes, rec)}
-    t, extra = s["tree"], 0
-    for q in s["searches"]:
-        r = by_node[t["children"][q["node"]][q["child"]]]
-        assert r["status"] == 0 and r["bestNode"] == q["bestNode"], (q, r)
-        assert [r["bLenTop"], r["bLenBottom"], r["bLenAppend"]] == [float(x) for x in q["blens"]], (q, r)
-        assert r["bestScore"] == q["bestScore"] or abs(r["bestScore"] - q["bestScore"]) <= 1e-9, (q, r)
-        assert r["phase1"] - q["phase1"] in (0, 1), (q, r)
-        extra += int(r["phase1"] - q["phase1"])
-    root = t["root"]
-    if all(t["dist"][c] > 0 for c in t["children"][root]):
-        assert extra == 0
-    got = sorted((n, int(r["placement"])) for n, r in by_node.items() if r["placement"] >= 0)
-    assert got == sorted((m[0], m[1]) for core in s["proposed"] for m in core)
+    lazy = orc.search_batch(ta, tree_lists(s), search_params(s), nodes, lazy_mode=0)
+    compare_with_reference_searches(s, nodes, rec, lazy, ref)

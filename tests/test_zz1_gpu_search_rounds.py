@@ -1,8 +1,8 @@
 """The device search under the stop rules bench.py measures (the reference's DEEP rounds) and on rearranged trees, against rounds
 recorded from the reference itself (tests/golden/extras 'rounds'): frozen tree with the deep rules, and a copy with perturbed
-branch lengths under both rule sets (28-40 accepted proposals per round).  Bar: every search's best node, branch lengths and score
-as the reference recorded them, the same proposedMoves; the candidate count may be one higher in searches that reach a zero-length
-child of the root (filled before the round here, lazily by the reference: DESIGN section 5); equal to the oracle in everything.
+branch lengths under both rule sets (28-40 accepted proposals per round).  Bar: equal to the oracle in everything; the
+reference's record of every search whose outcome does not depend on its lazy fill order (at least 98 % of them) and the same
+proposedMoves (tree_fixture.compare_with_reference_searches).
 The CPU twin (oracle, and the CUDA source compiled for the host) is tests/test_search_rounds_golden.py.  Written after the GPU
 budget of round 1 was spent: first run on hardware is the round-end test run.  Needs a GPU."""
 import numpy as np
@@ -10,7 +10,7 @@ import pytest
 
 from test_gpu_search import _capi_params, _compare
 from test_search_rounds_golden import ROUNDS, round_shim
-from tree_fixture import search_params, searched_nodes, tree_arrays, tree_lists
+from tree_fixture import compare_with_reference_searches, search_params, searched_nodes, tree_arrays, tree_lists
 
 pytestmark = pytest.mark.gpu
 
@@ -33,14 +33,7 @@ def test_device_reproduces_the_reference_round(name, rnd, variant):
     nodes = np.array(searched_nodes(s), np.int32)
     tree.prepare_search()
     rec = tree.search_records(tree.spr_search(nodes, _capi_params(search_params(s))))
-    _compare(rec, Oracle(model).search_batch(ta, lists, search_params(s), nodes, lazy_mode=1), nodes)
-    by_node = {int(n): r for n, r in zip(nodes, rec)}
-    t = s["tree"]
-    for q in s["searches"]:
-        r = by_node[t["children"][q["node"]][q["child"]]]
-        assert r["status"] == 0 and r["bestNode"] == q["bestNode"], (q, r)
-        assert [r["bLenTop"], r["bLenBottom"], r["bLenAppend"]] == [float(x) for x in q["blens"]], (q, r)
-        assert r["bestScore"] == q["bestScore"] or abs(r["bestScore"] - q["bestScore"]) <= 1e-9, (q, r)
-        assert r["phase1"] - q["phase1"] in (0, 1), (q, r)
-    got = sorted((n, int(r["placement"])) for n, r in by_node.items() if r["placement"] >= 0)
-    assert got == sorted((m[0], m[1]) for core in s["proposed"] for m in core)
+    orc = Oracle(model)
+    pre = orc.search_batch(ta, lists, search_params(s), nodes, lazy_mode=1)
+    _compare(rec, pre, nodes)
+    compare_with_reference_searches(s, nodes, rec, orc.search_batch(ta, lists, search_params(s), nodes, lazy_mode=0), pre)

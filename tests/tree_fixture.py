@@ -57,3 +57,33 @@ def searched_nodes(g):
                     and t["coreNum"][n] == core):
                 out.append(n)
     return out
+
+
+def compare_with_reference_searches(g, nodes, rec, lazy, pre, max_count_diff=3, min_fraction=0.98):
+    """rec: records of the path under test (device, or the CUDA source on the host) for `nodes`, computed with probVectTotUp of the
+    zero-length children of the root filled BEFORE the round; lazy / pre: the oracle's records in the reference's lazy mode and in
+    the pre-filled mode.  The reference fills those lists lazily and order-dependently during the round (:7198-7200).  Over all
+    recorded rounds (5 374 searches) the deviation shows as: a different number of scored candidates in searches that reach such a
+    child (1 306 searches, by at most 3), and in ONE search (ex_gtr, pruned node 53, best node = that child) a refinement of the
+    branch lengths the reference skips; proposedMoves never differ.  So: every search whose outcome does not depend on the fill
+    order must equal the reference's record in node, lengths and score; those are at least 98 % of every round; the proposals must be identical."""
+    import numpy as np
+    fields = ("status", "placement", "bestNode", "bLenTop", "bLenBottom", "bLenAppend", "bestScore", "improvement")
+    t = g["tree"]
+    by_node = {int(n): (r, all(a[f] == b[f] or (a[f] != a[f] and b[f] != b[f]) for f in fields)) for n, r, a, b in zip(nodes, rec, lazy, pre)}
+    checked = 0
+    for s in g["searches"]:
+        r, independent = by_node[t["children"][s["node"]][s["child"]]]
+        if not independent:
+            continue
+        assert r["status"] == 0 and r["bestNode"] == s["bestNode"], (s, r)
+        assert abs(int(r["phase1"]) - s["phase1"]) <= max_count_diff, (s, r)
+        assert [r["bLenTop"], r["bLenBottom"], r["bLenAppend"]] == [float(x) for x in s["blens"]], (s, r)
+        assert r["bestScore"] == s["bestScore"] or abs(r["bestScore"] - s["bestScore"]) <= 1e-9, (s, r)
+        checked += 1
+    assert checked >= min_fraction * len(g["searches"]), (checked, len(g["searches"]))
+    root = t["root"]
+    if all(t["dist"][c] > 0 for c in t["children"][root]):  # no zero-length child of the root: nothing to fill, counts identical
+        assert int(np.sum(rec["phase1"])) == g["phase1Total"]
+    got = sorted((int(n), int(r["placement"])) for n, (r, _) in by_node.items() if r["placement"] >= 0)
+    assert got == sorted((m[0], m[1]) for core in g["proposed"] for m in core)
