@@ -105,7 +105,7 @@ def _check_against(res, want):
 
 @pytest.mark.parametrize("backend", ["oracle", "cuda-source"])
 @pytest.mark.parametrize("name", ["ex_unrest", "ex_gtr", "ex_jc", "ex_unrest_rv", "ex_unrest_rv_sse", "ex_unrest_err", "ay_unrest_300",
-                                  "ay_unrest_deep_200"])
+                                  "ay_unrest_deep_200", "ay_unrest_1000"])
 def test_random_chain_matches_the_reference(name, backend):
     """The same chain was run with the REFERENCE's own functions when the fixtures were made (make_golden.py: harvest_fuzz): 2 500
     operations per configuration on lists the reference's run never produced.  The oracle and the CUDA source must reproduce every
