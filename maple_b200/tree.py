@@ -13,13 +13,13 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 import torch
 
 from . import capi
-from .engine import MapleEngine, MergeResult, _dp
+from .engine import MapleEngine, _dp
 from .genome_list import PackedLists, pack_lists, decode_stream
 
 FAM_LOWER, FAM_UPRIGHT, FAM_UPLEFT, FAM_TOTUP = 0, 1, 2, 3
