@@ -58,14 +58,14 @@ def test_oracle_reproduces_the_reference_round(name, rnd):
 
 @pytest.mark.parametrize("kind", ["straight", "fsm"])
 @pytest.mark.parametrize("rnd", ROUNDS)
-@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_rv_sse", "ex_unrest_err", "ay_unrest_300", "ay_unrest_deep_200"])
+@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_rv_sse", "ex_unrest_err", "ay_unrest_300", "ay_unrest_deep_200", "ay_unrest_1000"])
 def test_cuda_source_reproduces_the_round(name, rnd, kind):
     g, s = round_shim(name, rnd)
     model = MapleModel.from_reference_snapshot(g["env"], g["model"])
     orc, hs = Oracle(model), KernelSourceOnHost(model)
     ta, nodes = tree_arrays(s), np.array(searched_nodes(s), np.int32)
     lists = _prefilled_lists(s, orc)
-    rec = (hs.search_batch_fsm if kind == "fsm" else hs.search_batch)(ta, lists, search_params(s), nodes, scratch_keys=1 << 15)
+    rec = (hs.search_batch_fsm if kind == "fsm" else hs.search_batch)(ta, lists, search_params(s), nodes, scratch_keys=1 << 17)
     ref = orc.search_batch(ta, lists, search_params(s), nodes, lazy_mode=1)
     for f in ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend"):
         assert np.array_equal(rec[f], ref[f]), f
