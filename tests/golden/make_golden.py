@@ -437,6 +437,32 @@ def harvest_extras(G, tree, root, name):
     return ex
 
 
+def harvest_more_placements(G, trees, root):
+    """findBestParentForNewSample under stop rules the main fixture lacks (it has the reference's defaults: strict, 5 fails, 18 ln L):
+    the non-strict form of the same rule, and a tight one (strict, 1 fail, 2 ln L), on the frozen tree and on the copy with perturbed
+    branch lengths.  Same derived samples as the main fixture; own list table."""
+    import math
+    T = ListTable()
+    out = {}
+    L = math.log(G["lRef"])
+    saved = (G["strictStopRules"], G["allowedFails"], G["thresholdLogLK"])
+    global TIPS_OUT
+    tips_saved = TIPS_OUT
+    try:
+        for tname, tr in trees.items():
+            for rname, (strict, fails, thr) in (("default", saved), ("nonstrict", (False, saved[1], saved[2])), ("tight", (True, 1, 2.0 * L))):
+                if tname == "frozen" and rname == "default":
+                    continue  # the main fixture
+                G["strictStopRules"], G["allowedFails"], G["thresholdLogLK"] = strict, fails, thr
+                pl, env = harvest_placements(G, tr, root, T)
+                out[tname + "_" + rname] = {"placements": pl, "placeEnv": env}
+    finally:
+        G["strictStopRules"], G["allowedFails"], G["thresholdLogLK"] = saved
+        TIPS_OUT = tips_saved
+    out["lists"] = [jsonable_list(c) for c in T.lists]
+    return out
+
+
 def harvest_rounds(G, func, inputs, trees, root):
     """startTopologyUpdatesParallel (:9580) of the reference under the stop rules the main fixture does not cover: the DEEP rules of the
     later rounds (module globals strictTopologyStopRules / allowedFailsTopology / thresholdLogLKtopology, :12155-12159) on the frozen
@@ -603,6 +629,7 @@ class Harvest:
             self.extras = harvest_extras(G, tree, root, self.name)
             tp = self.extras.pop("_perturbed_tree")
             self.extras["rounds"] = harvest_rounds(G, func, inputs, {"frozen": tree, "perturbed": tp}, root)
+            self.extras["placements_more"] = harvest_more_placements(G, {"frozen": tree, "perturbed": tp}, root)
             self.extras["fuzz"] = harvest_fuzz(G, tree, root, seed=sum(map(ord, self.name)))
             print("[golden] %s fuzz chain: %d steps" % (self.name, len(self.extras["fuzz"]["results"])), file=sys.stderr)
             rec.install()
