@@ -37,3 +37,25 @@ def test_device_reproduces_the_reference_round(name, rnd, variant):
     pre = orc.search_batch(ta, lists, search_params(s), nodes, lazy_mode=1)
     _compare(rec, pre, nodes)
     compare_with_reference_searches(s, nodes, rec, orc.search_batch(ta, lists, search_params(s), nodes, lazy_mode=0), pre)
+
+
+@pytest.mark.parametrize("key", ["frozen_nonstrict", "frozen_tight", "perturbed_default", "perturbed_nonstrict", "perturbed_tight"])
+@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_err", "ay_unrest_300"])
+def test_device_placements_under_other_rules(name, key):
+    """maple_place_batch (default kernel) against placements recorded from the reference under non-strict and tight stop rules, on
+    frozen and perturbed trees (CPU twin: tests/test_placement_rules_golden.py)."""
+    from maple_b200.engine import MapleEngine
+    from maple_b200.genome_list import pack_lists
+    from maple_b200.model import MapleModel
+    from maple_b200.tree import DeviceTree
+    from test_gpu_placement import _capi_params as place_capi
+    from test_oracle_placement_golden import check_placements, place_params
+    from test_placement_rules_golden import _shim
+    g, tree_shim, s = _shim(name, key)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    eng = MapleEngine(model, 0)
+    ta, lists = tree_arrays(tree_shim), tree_lists(tree_shim)
+    tree = DeviceTree.from_lists(eng, ta["up"], ta["child0"], ta["child1"], ta["dist"], ta["root"], ta["isTip"], lists,
+                                 ta["mutStart"], ta["mut"], ta["numMinor"])
+    samples = pack_lists([[tuple(e) for e in s["lists"][c["diffs"]]] for c in s["placements"]], model.lRef, model.usingErrorRate)
+    check_placements(s, tree.place_samples(samples, place_capi(place_params(s))))
