@@ -139,10 +139,31 @@ class FakeLib:
                                            variant - 1, out)
         return 0
 
+    def maple_ctx_set_search_variant(self, ctx, variant):
+        self.search_variant = variant
+        return 0
+
+    def maple_ctx_set_scan_min_size(self, ctx, n):
+        return 0
+
     def maple_spr_search_batch(self, ctx, params, n, nodes, out, scratch_keys, max_concurrent, cycles, stream):
+        """Variant 1: the straight-line search, no retry.  Other variants: the per-lane state machine, and -- like the device -- a
+        second pass with 8x the scratch for the searches that exhausted theirs."""
         self.launches += 1
         t = self._or_tree()
-        self._hs().hs_search_batch_fsm(self.mp, C.addressof(t), params, n, nodes, scratch_keys if scratch_keys > 0 else 8192, out)
+        keys = scratch_keys if scratch_keys > 0 else 8192
+        if getattr(self, "search_variant", 0) == 1:
+            self._hs().or_search_batch(self.mp, C.addressof(t), params, n, nodes, keys, 1, out)
+            return 0
+        self._hs().hs_search_batch_fsm(self.mp, C.addressof(t), params, n, nodes, keys, out)
+        rec = _arr(out, n * 16, np.int32).reshape(n, 16)  # 64-byte records; status is the third int32
+        again = np.nonzero(rec[:, 2] == 3)[0]
+        if again.size:
+            sub = np.ascontiguousarray(_arr(nodes, n, np.int32)[again])
+            tmp = np.zeros((again.size, 16), np.int32)
+            self._hs().hs_search_batch_fsm(self.mp, C.addressof(t), params, again.size, sub.ctypes.data_as(C.c_void_p), keys * 8,
+                                           tmp.ctypes.data_as(C.c_void_p))
+            rec[again] = tmp
         return 0
 
     def maple_last_error(self, ctx):
