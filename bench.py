@@ -160,6 +160,7 @@ def run_reference(args):
     if rank != 0:
         return
     d, orc, ta, host, nodes, setup_s = build_problem_cpu(args)
+    orc.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core of this process's affinity mask at every N
     p = round_params(args, d.model.lRef)
     sample = cpu_sample(nodes, args.cpu_searches)
     pd = params_dict(p)
@@ -330,7 +331,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         dn = h_nodes.to(dev, non_blocking=True)
@@ -393,6 +394,7 @@ def main():
         host = tree.arena.to_host()
         sample = cpu_sample(nodes, args.cpu_searches)
         orc = Oracle(d.model)
+        orc.use_all_cores()
         ta, pd = oracle_tree(d, tree), params_dict(p)
         orc.search_batch(ta, host, pd, sample[: max(16, len(sample) // 8)], lazy_mode=1)
         t0 = time.perf_counter()

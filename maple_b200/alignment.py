@@ -25,45 +25,57 @@ class AlignmentError(ValueError):
     """The reference prints a message and raises Exception("exit") in these cases (:3527-3539)."""
 
 
+def _records(text: str):
+    """Split a MAPLE/FASTA-like text into (header, body lines) records; reading stops at the first empty line that
+    follows a record, as the reference's reader does (:3515, :3520)."""
+    header, body = None, []
+    for raw in text.split("\n"):
+        if raw.startswith(">"):
+            if header is not None:
+                yield header, body
+            header, body = raw[1:].replace(">", ""), []
+        elif raw == "":
+            if header is not None:
+                break
+        elif header is not None:
+            body.append(raw)
+    if header is not None:
+        yield header, body
+
+
+def _parse_diff(line: str, ref: str, where: str) -> Diff:
+    cols = line.split()
+    if len(cols) < 2:
+        raise AlignmentError("%s: line with only one column: %r (is the reference included at the top of the alignment?)" % (where, line))
+    ch, pos = cols[0].lower(), int(cols[1])
+    if ch not in ("n", "-") and ref[pos - 1] == ch:
+        raise AlignmentError("mutation into the reference nucleotide at position %d (%s): wrong reference?" % (pos, ch))
+    return (ch, pos, int(cols[2])) if len(cols) > 2 else (ch, pos)
+
+
 def read_maple_alignment(path: str, reference: Optional[str] = None) -> Tuple[str, Dict[str, List[Diff]]]:
     """Returns (reference genome in lower case, {sample name: [(char, pos[, length]), ...]}).  With `reference` given the file
-    is expected to hold samples only (the reference's --reference option, extractReference=False)."""
-    op = gzip.open if path.endswith(".gz") else open
-    with op(path, "rt") as f:
-        line = f.readline()
-        if reference is None:
-            line = f.readline()
-            parts = []
-            while line != "" and line[0] != ">":
-                parts.append(line.replace("\n", ""))
-                line = f.readline()
-            ref = "".join(parts).lower()
-        else:
-            ref = reference.lower()
-        data: Dict[str, List[Diff]] = {}
-        n_seqs = 0
-        while line != "" and line != "\n":
-            name = line.replace(">", "").replace("\n", "")
-            seq: List[Diff] = []
-            line = f.readline()
-            pos = 0
-            while line != "" and line != "\n" and line[0] != ">":
-                cols = line.split()
-                if len(cols) > 2:
-                    entry: Diff = (cols[0].lower(), int(cols[1]), int(cols[2]))
-                elif len(cols) < 2:
-                    raise AlignmentError("%s: line with only one column: %r (is the reference included at the top of the alignment?)" % (path, line))
-                else:
-                    entry = (cols[0].lower(), int(cols[1]))
-                if ref[entry[1] - 1] == entry[0] and entry[0] != "n" and entry[0] != "-":
-                    raise AlignmentError("mutation into the reference nucleotide at position %d (%s): wrong reference?" % (entry[1], entry[0]))
-                if entry[1] <= pos:
-                    raise AlignmentError("sample %d (%s): entry %r overlaps the previous one %r" % (n_seqs + 1, name, line.strip(), seq[-1]))
-                seq.append(entry)
-                pos = entry[1] if len(entry) == 2 else entry[1] + entry[2] - 1
-                line = f.readline()
-            data[name] = seq
-            n_seqs += 1
+    is expected to hold samples only (the reference's --reference option, extractReference=False).  Same accepted inputs and
+    the same three rejections as readConciseAlignment (:3527-3539): a one-column line, a substitution into the reference
+    base, an entry that starts inside the previous one."""
+    with (gzip.open if path.endswith(".gz") else open)(path, "rt") as f:
+        records = _records(f.read())
+    if reference is None:
+        first = next(records, None)
+        ref = "".join(first[1]).lower() if first else ""
+    else:
+        ref = reference.lower()
+    data: Dict[str, List[Diff]] = {}
+    for number, (name, lines) in enumerate(records, 1):
+        seq: List[Diff] = []
+        covered = 0  # last position the previous entry covers
+        for line in lines:
+            entry = _parse_diff(line, ref, path)
+            if entry[1] <= covered:
+                raise AlignmentError("sample %d (%s): entry %r overlaps the previous one %r" % (number, name, line.strip(), seq[-1]))
+            covered = entry[1] + (entry[2] - 1 if len(entry) == 3 else 0)
+            seq.append(entry)
+        data[name] = seq
     return ref, data
 
 

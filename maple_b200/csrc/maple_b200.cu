@@ -937,7 +937,9 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     DevTree T = ctx->tree;
     T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
     const unsigned capK = (unsigned)((scratch_keys_per_search > 0 ? scratch_keys_per_search : 8192) + 3) & ~3u;
-    const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
+    // coefficient scratch of the branch-length solver: one value per entry of the two lists, which may be scratch lists, so it
+    // grows with the list scratch (2048 at the default 8192 entries)
+    const unsigned capP = 2 * capK + 6 * 1024, capA = capK / 4 > 2048 ? capK / 4 : 2048;
     // the DFS keeps at most one pending entry per level on the way up and one per level on the way down; what is left of the
     // stack doubles as the per-depth state of the subtree scans (5 states per free entry)
     const int stackCap = (2 * ctx->treeHeight + 32 + 63) & ~63;
@@ -968,7 +970,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     }
     if (blocksPerSM < 1) blocksPerSM = 1;
     int64_t threads = (int64_t)ctx->numSMs * blocksPerSM * kSearchThreads;
-    if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches;
+    if (max_concurrent_searches > 0 && threads > max_concurrent_searches) threads = max_concurrent_searches < 32 ? 32 : max_concurrent_searches;
     // Searches per warp.  The subtree scans -- most of the work of a deep round -- are executed by whole warps, so the unit that
     // has to be kept busy is the warp, not the lane: every resident warp should own searches, and each owning lane should get
     // a few searches in turn (dynamic balance) rather than one.  With few searches (a shard of a multi-GPU round) this spreads
@@ -1022,12 +1024,11 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         // second chance on the device for searches that exhausted their scratch: 128 lanes with 8x the entries
         const int retryCap = (int)(n < 65536 ? n : 65536);
         const int lanes2 = 2 * kSearchThreads;
-        const unsigned capK2 = capK * 8, capP2 = 2 * capK2 + 6 * 1024;
-        const size_t per2 = (size_t)capK2 * 4 + (size_t)capP2 * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
+        const unsigned capK2 = capK * 8, capP2 = 2 * capK2 + 6 * 1024, capA2 = capA * 8;
+        const size_t per2 = (size_t)capK2 * 4 + (size_t)capP2 * 8 + (size_t)capA2 * 8 + (size_t)stackCap * sizeof(StackE);
         const size_t need2 = per2 * lanes2 + 256 + (size_t)retryCap * 8 + 64;
         if (need2 > ctx->retryScratchBytes) {
             cudaFree(ctx->retryScratch);
-    cudaFree(ctx->placeScratch);
             ctx->retryScratch = nullptr;
             ctx->retryScratchBytes = 0;
             CK(cudaMalloc(&ctx->retryScratch, need2));
@@ -1041,12 +1042,12 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         char* s2 = b2 + (((size_t)retryCap * 8 + 63) & ~size_t(63));
         double* pay2 = (double*)s2;
         double* ais2 = (double*)(s2 + (size_t)lanes2 * capP2 * 8);
-        StackE* stack2 = (StackE*)(s2 + (size_t)lanes2 * (capP2 + capA) * 8);
-        uint32_t* key2 = (uint32_t*)(s2 + (size_t)lanes2 * ((size_t)(capP2 + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+        StackE* stack2 = (StackE*)(s2 + (size_t)lanes2 * (capP2 + capA2) * 8);
+        uint32_t* key2 = (uint32_t*)(s2 + (size_t)lanes2 * ((size_t)(capP2 + capA2) * 8 + (size_t)stackCap * sizeof(StackE)));
         k_collect_overflow<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, (const SearchResult*)out, nodes, retryNodes, retryIdx,
                                                                                          ctx->retryCounters, retryCap);
         fsmKernel<<<lanes2 / kSearchThreads, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(
-            ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, key2, pay2, ais2, stack2, capK2, capP2, capA, stackCap,
+            ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, key2, pay2, ais2, stack2, capK2, capP2, capA2, stackCap,
             ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
             ctx->retryCounters, retryIdx, 32);
@@ -1071,7 +1072,7 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     DevTree T = ctx->tree;
     T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
     const unsigned capK = (unsigned)((scratch_keys_per_sample > 0 ? scratch_keys_per_sample : 4096) + 3) & ~3u;
-    const unsigned capP = 2 * capK + 6 * 1024, capA = 2048;
+    const unsigned capP = 2 * capK + 6 * 1024, capA = capK / 2 > 2048 ? capK / 2 : 2048;
     const int stackCap = ctx->treeHeight + 8, bestCap = (int)(capK / 4 > 1024 ? capK / 4 : 1024);  // bestNodes entries per sample
     const size_t laneBytes = ((size_t)capP * 8 + (size_t)capA * 8 + (size_t)bestCap * sizeof(PlaceBest) + (size_t)stackCap * sizeof(PlaceStackE) +
                               (size_t)capK * 4 + 15) & ~size_t(15);
@@ -1080,7 +1081,7 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
     if ((warpPlain || warpMat) && T.order && !pp.deeperSearchForLongBranches) {
         // one warp per sample: 32 lane slices of scratch (refinement entries run one per lane), the sample list, bestNodes and
         // its refinement results, per-depth states, and the stack of the straight-line fallback
-        const unsigned laneK = 512, laneP = 6 * 512, laneA = 512;
+        const unsigned laneK = capK / 8 > 512 ? capK / 8 : 512, laneP = 6 * laneK, laneA = laneK;  // 512 at the default 4096 entries
         const int bestCapW = (int)(capK / 4 > 1024 ? capK / 4 : 1024);
         const size_t warpBytes = ((size_t)32 * laneP * 8 + (size_t)32 * laneA * 8 + (size_t)6 * laneK * 8 + (size_t)bestCapW * sizeof(PlaceEval) +
                                   (size_t)stackCap * sizeof(PlacePath) + (size_t)bestCapW * sizeof(PlaceBest) +

@@ -234,6 +234,26 @@ class MapleEngine:
         capi.check(self.ctx, rc, "maple_prob_root_batch")
         return out
 
+    def root_vector_batch(self, idx, bLen, isFromTip, shorten: bool = True) -> MergeResult:
+        """rootVector(probVect, bLen, isFromTip) (:4916) for n lists of the bound arena; shorten=True returns what the reference
+        returns (it shortens before returning, :4994)."""
+        L = self.lists
+        idx, bLen, isFromTip = self._t(idx, torch.int32), self._t(bLen, torch.float64), self._t(isFromTip, torch.uint8)
+        n = idx.numel()
+        cap = (L.nkeys[idx.long()].long() + 3) // 4 * 4 + 4
+        ks = torch.cumsum(cap, 0) - cap
+        ps = ks * 6
+        total = int(cap.sum().item())
+        out_key = torch.empty(total + 4, dtype=torch.int32, device=self.device)
+        out_pay = torch.empty(total * 6 + 4, dtype=torch.float64, device=self.device)
+        nk = torch.empty(n, dtype=torch.int32, device=self.device)
+        npay = torch.empty(n, dtype=torch.int32, device=self.device)
+        rc = self.lib.maple_root_vector_batch(self.ctx, n, _dp(idx), _dp(bLen), _dp(isFromTip), _dp(out_key), _dp(out_pay), _dp(ks), _dp(ps),
+                                              _dp(nk), _dp(npay), 1 if shorten else 0, self._stream())
+        capi.check(self.ctx, rc, "maple_root_vector_batch")
+        st = torch.zeros(n, dtype=torch.int32, device=self.device)
+        return MergeResult(out_key, out_pay, ks, ps, nk, npay, None, st, L.lRef, L.U)
+
     def pass_branch_batch(self, idx, mutNode, dirIsUp, mutStart: torch.Tensor, mut: torch.Tensor) -> MergeResult:
         """passGenomeListThroughBranch for n lists; mutStart/mut: CSR mutation lists on the device (int32)."""
         L = self.lists
@@ -300,6 +320,13 @@ class MapleEngine:
         keep = self._bind_pair(probVect, probVect)
         try:
             return float(self.prob_root_batch([0]).cpu()[0])
+        finally:
+            self._restore(keep)
+
+    def rootVector(self, probVect, bLen, isFromTip):
+        keep = self._bind_pair(probVect, probVect)
+        try:
+            return self.root_vector_batch([0], [float(bLen) if bLen else 0.0], [1 if isFromTip else 0]).to_lists()[0]
         finally:
             self._restore(keep)
 

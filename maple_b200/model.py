@@ -22,6 +22,11 @@ def ref_indices(ref: str) -> np.ndarray:
     return np.fromiter((_ALLELES.get(ch, 0) for ch in ref), dtype=np.int8, count=len(ref))
 
 
+def ref_valid(ref: str) -> np.ndarray:
+    """True where the reference holds A/C/G/T (the positions cumulativeBases counts, :3640-3647)."""
+    return np.fromiter((ch in _ALLELES for ch in ref), dtype=bool, count=len(ref))
+
+
 def root_freqs_from_ref(ref: str):
     """rootFreqs (:3670-3678): base composition over ACGT characters, divided by lRef."""
     counts = [0, 0, 0, 0]
@@ -54,6 +59,9 @@ class MapleModel:
     cumulativeErrorRate: Optional[np.ndarray] = field(default=None, repr=False)
     totError: float = 0.0
     minBLenSensitivity: float = 0.0
+    # reference positions holding A/C/G/T; ambiguous or N reference characters are indexed as A by refIndeces (:3680-3685)
+    # but are NOT counted in cumulativeBases (:3640-3647).  None = every position is valid.
+    refValid: Optional[np.ndarray] = field(default=None, repr=False)
 
     def __post_init__(self):
         self.refIdx = np.ascontiguousarray(self.refIdx, dtype=np.int8)
@@ -94,10 +102,9 @@ class MapleModel:
     def cumulative_bases(self) -> np.ndarray:
         cb = np.zeros((self.lRef + 1, 4), dtype=np.int32)
         onehot = np.zeros((self.lRef, 4), dtype=np.int32)
-        valid = getattr(self, "_refValid", None)
         onehot[np.arange(self.lRef), self.refIdx.astype(np.int64)] = 1
-        if valid is not None:
-            onehot[~valid] = 0
+        if self.refValid is not None:
+            onehot[~np.asarray(self.refValid, bool)] = 0
         np.cumsum(onehot, axis=0, out=cb[1:])
         return cb
 
@@ -111,6 +118,13 @@ class MapleModel:
             acc = acc + math.log(pi[ridx[i]] * (1.0 - 1.33333 * e) + 0.333333 * e)  # :6384 / :6389
             out[i + 1] = acc
         return out
+
+    @classmethod
+    def from_ref(cls, ref: str, Q, **kw) -> "MapleModel":
+        """Model for a reference genome string: refIndeces, rootFreqs and the validity mask are derived from it
+        (:3640-3685), everything else is passed through."""
+        return cls(lRef=len(ref), refIdx=ref_indices(ref), rootFreqs=np.array(root_freqs_from_ref(ref), dtype=np.float64),
+                   Q=np.array(Q, dtype=np.float64), refValid=ref_valid(ref), **kw)
 
     @classmethod
     def from_reference_snapshot(cls, env: dict, model: dict) -> "MapleModel":
@@ -131,7 +145,7 @@ class MapleModel:
             thresholdDiffForUpdate=env["thresholdDiffForUpdate"],
             thresholdFoldChangeUpdate=env["thresholdFoldChangeUpdate"],
         )
-        m._refValid = np.fromiter((ch in _ALLELES for ch in ref), dtype=bool, count=len(ref))
+        m.refValid = ref_valid(ref)
         # the fixture records minBLenSensitivity already scaled by 1/lRef
         m.minBLenSensitivity = float(env["minBLenSensitivity"])
         return m

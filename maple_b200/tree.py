@@ -472,31 +472,39 @@ class DeviceTree:
         (capi.PLACE_RESULT_FIELDS).  The tree is not modified; prepare_search() must have bound it."""
         eng, dev, A = self.eng, self.eng.device, self.arena
         n = len(samples)
-        first = A.add_ids(n)
-        A.store_packed(np.arange(first, first + n, dtype=np.int64), samples)
-        self.prepare_search()  # the arena's tables moved: bind again
-        ids = torch.arange(first, first + n, dtype=torch.int32, device=dev)
-
-        def run(which: torch.Tensor, keys: int) -> np.ndarray:
-            out = torch.zeros((which.numel(), 48), dtype=torch.uint8, device=dev)
-            rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), which.numel(), _dp(which), _dp(out), int(keys), eng._stream())
-            capi.check(eng.ctx, rc, "maple_place_batch")
-            return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
-
-        rec = run(ids, scratch_keys)
-        retry, keys = np.nonzero(rec["status"] == 3)[0], max(int(scratch_keys), 4096)
-        variant = getattr(eng, "place_variant", 0)
+        mark = A.mark()  # the sample lists are temporaries of this batch: ids and storage are given back below
         try:
-            while retry.size and keys < (1 << 22):  # per-sample scratch (lists or the bestNodes table) exhausted: again with 8x
-                keys *= 8
-                if variant != 0:  # the retries go through the one-sample-per-thread kernel, whose whole scratch scales with `keys`
-                    eng.set_place_variant(0)
-                again = run(ids[torch.as_tensor(retry, device=dev)].contiguous(), keys)
-                rec[retry] = again
-                retry = retry[again["status"] == 3]
+            first = A.add_ids(n)
+            A.store_packed(np.arange(first, first + n, dtype=np.int64), samples)
+            self.prepare_search()  # the arena's tables moved: bind again
+            ids = torch.arange(first, first + n, dtype=torch.int32, device=dev)
+
+            def run(which: torch.Tensor, keys: int) -> np.ndarray:
+                out = torch.zeros((which.numel(), 48), dtype=torch.uint8, device=dev)
+                rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), which.numel(), _dp(which), _dp(out), int(keys), eng._stream())
+                capi.check(eng.ctx, rc, "maple_place_batch")
+                return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
+
+            rec = run(ids, scratch_keys)
+            retry, keys = np.nonzero(rec["status"] == 3)[0], max(int(scratch_keys), 4096)
+            variant = getattr(eng, "place_variant", 0)
+            try:
+                while retry.size and keys < (1 << 22):  # per-sample scratch (lists or the bestNodes table) exhausted: again with 8x
+                    keys *= 8
+                    if variant != 0:  # the retries go through the one-sample-per-thread kernel, whose whole scratch scales with `keys`
+                        eng.set_place_variant(0)
+                    again = run(ids[torch.as_tensor(retry, device=dev)].contiguous(), keys)
+                    rec[retry] = again
+                    retry = retry[again["status"] == 3]
+            finally:
+                if variant != 0:
+                    eng.set_place_variant(variant)
+            if retry.size:
+                raise capi.MapleError("%d samples still exhaust their scratch with %d entries (first: sample %d)" % (retry.size, keys, int(retry[0])))
         finally:
-            if variant != 0:
-                eng.set_place_variant(variant)
+            A.release(mark)
+            if getattr(self, "_bound_epoch", None) != A.epoch:
+                self.prepare_search()
         return rec
 
     @staticmethod

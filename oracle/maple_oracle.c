@@ -1001,6 +1001,16 @@ void or_shorten_slots(const OrModel *m, int64_t n, uint32_t *key, double *pay, c
     }
 }
 
+/* n > 0: use n OpenMP threads from now on, whatever OMP_NUM_THREADS said at start-up (torchrun exports
+ * OMP_NUM_THREADS=1 to its workers, which is not what a CPU baseline "on all host cores" means). */
+void or_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int or_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

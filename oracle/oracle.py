@@ -95,6 +95,9 @@ def declare(L):
     L.or_search_batch.restype = None
     L.or_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     L.or_num_threads.restype = C.c_int
+    if hasattr(L, "or_set_num_threads"):  # the oracle's own library; stand-ins that reuse this table (tests/hostsim) lack it
+        L.or_set_num_threads.restype = None
+        L.or_set_num_threads.argtypes = [C.c_int]
     L.or_shorten_slots.restype = None
     L.or_shorten_slots.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
     L.or_is_minor.restype = C.c_int
@@ -327,3 +330,14 @@ class Oracle:
 
     def num_threads(self):
         return int(self.L.or_num_threads())
+
+    def use_all_cores(self) -> int:
+        """One OpenMP thread per core this process may run on (its affinity mask), regardless of OMP_NUM_THREADS --
+        torchrun sets that to 1 for its workers.  Returns the thread count now in effect."""
+        import os
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        self.L.or_set_num_threads(int(n))
+        return self.num_threads()

@@ -12,13 +12,9 @@ def golden_names():
     return sorted(os.path.basename(p)[:-len(".json.gz")] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.json.gz")))
 
 
-# fixtures added after the last hardware run of round 1: their device tests live in tests/test_zz*_gpu_*.py (collected last), so that
-# a surprise there cannot stop the device tests that have already run on a B200
-NOT_YET_ON_HARDWARE = ("ay_unrest_1000",)
-
-
 def hw_names():
-    return [n for n in golden_names() if n not in NOT_YET_ON_HARDWARE]
+    """Fixtures the device tests run on (all of them; kept as a function because the tests parametrize over it)."""
+    return golden_names()
 
 
 def _as_tuples(gl):

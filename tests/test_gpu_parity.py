@@ -179,9 +179,23 @@ def test_prob_root_vs_golden_and_oracle(env):
     idx = np.array([c["v"] for c in calls], np.int32)
     got = eng.prob_root_batch(idx).cpu().numpy()
     for c, x in zip(calls, got):
-        assert abs(x - c["out"]) <= 1e-6 * max(1.0, abs(c["out"]) * 1e-4), (c, x)  # same bar as the oracle's own pin
+        assert abs(x - c["out"]) <= 1e-6, (c, x)  # north star: 1e-6 absolute on log-likelihoods
         assert abs(x - orc_r.prob_root(g["lists"][c["v"]])) <= LK_TOL * max(1.0, abs(c["out"]) * 1e-3)
     assert abs(eng.findProbRoot(g["lists"][calls[0]["v"]]) - got[0]) == 0.0
+
+
+def test_root_vector_vs_golden(env):
+    """maple_root_vector_batch against every rootVector call the reference recorded (:4916-4996): lists bit-identical."""
+    g, eng, packed, orc = env
+    calls = g["calls"]["rootVector"]
+    assert calls
+    r = eng.root_vector_batch([c["v"] for c in calls], [float(c["bLen"]) if c["bLen"] else 0.0 for c in calls],
+                              [1 if c["isFromTip"] else 0 for c in calls])
+    for got, c in zip(r.to_lists(), calls):
+        assert lists_equal(got, g["lists"][c["out"]]), c
+        assert lists_equal(got, orc.shorten(orc.root_vector(g["lists"][c["v"]], c["bLen"], c["isFromTip"]))), c
+    c = calls[0]
+    assert lists_equal(eng.rootVector(g["lists"][c["v"]], c["bLen"], c["isFromTip"]), g["lists"][c["out"]])
 
 
 def test_pass_branch_vs_golden(env):

@@ -103,7 +103,7 @@ def test_prob_root(fx):
     assert calls
     for c in calls:
         got = orc.prob_root(L[c["v"]])
-        assert abs(got - c["out"]) <= LK_TOL * max(1.0, abs(c["out"]) * 1e-4), (c, got)
+        assert abs(got - c["out"]) <= 1e-6, (c, got)  # north star: 1e-6 absolute on log-likelihoods
 
 
 def test_tree_likelihood_from_parts(fx):
