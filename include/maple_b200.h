@@ -221,9 +221,11 @@ int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, co
 int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant);
 
 /* Which search kernel maple_spr_search_batch launches: 0 (default) = one search per lane as a warp-converged state
- * machine, with subtrees whose lists are all stored ones scanned by the whole warp; 1 = the straight-line
- * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = warp scans with the queued-site form of appendProbNode and the node-by-node window replay
- * (1-3: kept for A/B measurements and to test the alternative paths; same results). */
+ * machine, with subtrees whose lists are all stored ones scanned by the whole warp over scan-format copies of the stored
+ * lists (scan2.cuh: bulk-copy staging, precomputed site factors, prefix-form replay); 1 = the straight-line
+ * one-search-per-thread kernel; 2 = the state machine without warp scans; 3 = the first form of the warp scans with the
+ * queued-site form of appendProbNode and the node-by-node window replay; 4 = the first form of the warp scans (arena lists
+ * staged per lane, pointer-jumping replay)  (1-4: kept for A/B measurements and to test the alternative paths; same results). */
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
 
 /* Subtrees of at least minNodes nodes are scanned by the whole warp (default 8; 0 = never).  Tuning only: results do not

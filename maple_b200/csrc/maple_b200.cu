@@ -17,6 +17,7 @@
 #include "search_fsm.cuh"
 #include "place.cuh"
 #include "place_scan.cuh"
+#include "scan2.cuh"
 
 using namespace maple;
 
@@ -45,6 +46,12 @@ struct maple_ctx {
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
     int fsmMinBlocks = 7;            // __launch_bounds__ minimum CTAs per SM of the state-machine kernel (7 -> 128 registers, 6 -> 168)
     int scanMinSize = 8;             // subtrees of at least this many nodes are scanned by the whole warp (0 = never)
+    // second form of the scans (scan2.cuh): per-position sizes / offsets of the scan-format lists (computed at maple_tree_bind), the
+    // arena that holds them and the per-position records (both rewritten before every search launch); owned
+    bool scan2Ok = false, scanOld = false, scanOldEnv = false;  // scanOld: A/B switch back to the first form (MAPLE_SCAN_OLD=1 or search variant 4)
+    uint32_t *scanUnits = nullptr, *scanOffsets = nullptr;
+    uint4* scanArena = nullptr;
+    ScanRec* scanRecs = nullptr;
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
@@ -257,6 +264,28 @@ __global__ void __launch_bounds__(256) k_scan_prepare(const __grid_constant__ De
     out[i] = make_scan_node(T, eff, i);
 }
 
+// ---- scan-format copies of the probVectTotUp lists (scan2.cuh), one thread per pre-order position
+// sizes, at maple_tree_bind: 16-byte units of the copy of the list at each position (0 = no list / too large to stage)
+__global__ void __launch_bounds__(256) k_scan_count(const __grid_constant__ DevTree T, uint32_t* __restrict__ units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T.nNodes) units[i] = scan_count_units(T, i);
+}
+
+// per launch: the copies themselves (they hold Q * siteRate, so they follow the model) and the records
+__global__ void __launch_bounds__(128) k_scan_build(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T, double eff,
+                                                    const uint32_t* __restrict__ units, uint4* __restrict__ arena, ScanRec* __restrict__ recs) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T.nNodes) recs[i] = scan_build_rec(sm, T, eff, i, units[i], arena);
+}
+
+// nearest scored proper ancestor of every position (what a node inherits only changes at scored nodes)
+__global__ void __launch_bounds__(256) k_scan_nsa(const __grid_constant__ DevTree T, ScanRec* __restrict__ recs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T.nNodes) scan_fill_nsa(T, recs, i);
+}
+
 // one SPR search per thread; threads pull the next pruned node from a global counter (searches differ ~10x in length)
 __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                const __grid_constant__ SearchParams sp, int64_t n,
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
 // The same searches as k_spr_search, one per lane, but as resumable state machines (search_fsm.cuh): every loop
 // iteration each lane advances its control code to the next co-walk request, then the warp runs each kind of
 // co-walk once for all lanes that requested it.
-template <int MINB>
+template <int MINB, bool SCAN2>
 __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                    const __grid_constant__ SearchParams sp, int64_t n,
                                                                    const int32_t* __restrict__ nodes, SearchResult* __restrict__ out,
@@ -303,14 +332,20 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
         st = wst[threadIdx.x >> 5];
         __syncthreads();
     }
-    const bool l0 = (threadIdx.x & 31) == 0;
     extern __shared__ uint4 dynSmem[];
-    const int warpSmem = int(sizeof(ScanSmem) - sizeof(uint4)) + poolBytes;
-    ScanSmem& W = *reinterpret_cast<ScanSmem*>(reinterpret_cast<char*>(dynSmem) + (threadIdx.x >> 5) * warpSmem);
+    const int warpSmem = int((SCAN2 ? sizeof(Scan2Smem) : sizeof(ScanSmem)) - sizeof(uint4)) + poolBytes;
+    char* const warpBase = reinterpret_cast<char*>(dynSmem) + (threadIdx.x >> 5) * warpSmem;
+    ScanSmem& W = *reinterpret_cast<ScanSmem*>(warpBase);
+    Scan2Smem& W2 = *reinterpret_cast<Scan2Smem*>(warpBase);
+    uint32_t mbarParity = 0;
+    if (SCAN2) {
+#ifdef __CUDA_ARCH__
+        if ((threadIdx.x & 31) == 0) mbar_init(&W2.mbar);
+#endif
+        __syncwarp();
+    }
+    (void)W;
     if (nDev) n = (int64_t)min((unsigned long long)n, *nDev);  // retry launch: the list length lives on the device
-    long long tk = clock64();
-#define STAT_T(i) do { if (st) { const long long now_ = clock64(); if (l0) st[i] += (unsigned long long)(now_ - tk); tk = now_; } } while (0)
-#define STAT_N(i, v) do { if (st && l0) st[i] += (unsigned long long)(v); } while (0)
     stage_model(sm, gm);
     // scratch is laid out for the lanes that own searches only
     const int lane_ = int(threadIdx.x & 31);
@@ -321,101 +356,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     s.ais = scrAis + tid * capA;
     s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
     StackE* stack = scrStack + tid * (size_t)stackCap;
-    Fsm f;
-    f.op = OP_NONE;
-    f.pc = 0;
-    // lanes beyond lanesPerWarp own no search: they only lend a hand in the whole-warp subtree scans (fewer searches per warp =
-    // a long search shares its warp's time with fewer others)
-    int stage = (int(threadIdx.x & 31) < lanesPerWarp) ? 0 : 3;  // 0 idle, 1 current-placement append pending, 2 search running, 3 no more work
-    unsigned long long i = 0;
-    int node = -1;
-    double bestCurrentLK = 0.0;
-    long long c0 = 0;
-    SearchResult r;
-    for (;;) {
-        // ---------------- control (divergent, cheap)
-        if (stage == 2) {
-            fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
-        } else if (stage == 1) {
-            bestCurrentLK = f.resD;
-            r.bestCurrentLK = bestCurrentLK;
-            if (!(bestCurrentLK < sp.thresholdTopologyPlacement || T.dist[node] != 0.0)) {  // :9674
-                f.rc = 1;
-                f.op = OP_DONE;
-            } else {
-                const int parent = T.up[node];
-                f.pc = 0;
-                f.parent = parent;
-                f.child = (T.child0[parent] == node) ? 0 : 1;
-                f.bestLKdiff = bestCurrentLK;
-                f.removedBLen = T.dist[node];
-                f.phase1 = 0;
-                f.rc = 0;
-                s.topK = s.topP = 0;
-                stage = 2;
-                fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
-            }
-        }
-        while (stage != 3 && (stage == 0 || f.op == OP_DONE)) {
-            if (stage != 0) {  // a search (or its pre-check) just ended
-                if (stage == 2) fsm_finish(f, T, sp, node, bestCurrentLK, r);
-                else r.status = f.rc;
-                out[outIndex ? outIndex[i] : i] = r;
-                if (outCycles) outCycles[i] = clock64() - c0;
-                stage = 0;
-            }
-            i = atomicAdd(counter, 1ULL);
-            if (i >= (unsigned long long)n) { stage = 3; f.op = OP_NONE; break; }
-            node = nodes[i];
-            c0 = clock64();
-            r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
-            r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
-            f.op = OP_NONE;
-            if (T.up[node] < 0) { out[outIndex ? outIndex[i] : i] = r; continue; }
-            s.topK = s.topP = 0;
-            s.err = 0;
-            const int parent = T.up[node];
-            LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
-            if (n_mut(T, node)) vectUp = s_pass(sm, T, s, vectUp, node, false);
-            const LRef own = tree_list(T, 0, node);
-            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[outIndex ? outIndex[i] : i] = r; continue; }
-            f.a1 = vectUp; f.a2 = own; f.at1 = T.isTip[node] != 0; f.ab1 = T.dist[node];
-            f.op = OP_APPEND;
-            stage = 1;
-        }
-        // ---------------- co-walks, one kind at a time, lanes converged
-        __syncwarp();
-        STAT_T(0);
-        if (stats) {
-            const unsigned b1 = __ballot_sync(0xffffffffu, f.op == OP_APPEND), b2 = __ballot_sync(0xffffffffu, f.op == OP_MERGE),
-                           b3 = __ballot_sync(0xffffffffu, f.op == OP_BLEN), b4 = __ballot_sync(0xffffffffu, f.op == OP_DIFFER);
-            STAT_N(8, __popc(b1)); STAT_N(9, __popc(b2)); STAT_N(10, __popc(b3)); STAT_N(11, __popc(b4));
-            STAT_N(12, b1 != 0); STAT_N(13, b2 != 0); STAT_N(14, b3 != 0); STAT_N(15, b4 != 0); STAT_N(16, 1);
-            tk = clock64();
-        }
-        if (f.op == OP_APPEND) f.resD = f_append(sm, f.a1, f.a2, f.at1 != 0, f.ab1);
-        __syncwarp();
-        STAT_T(1);
-        if (f.op == OP_MERGE) {
-            Writer w;
-            w.init(s.key + s.topK, s.pay + s.topP);
-            if (f_merge(sm, f.a1, f.ab1, f.at1 != 0, f.a2, f.ab2, f.at2 != 0, f.aflags, w) == 0) f.resL = sc_commit(s, w.nk, w.np);
-            else f.resL = lnull();
-        }
-        __syncwarp();
-        STAT_T(2);
-        if (f.op == OP_BLEN) f.resD = f_blen(sm, f.a1, f.a2, f.at1 != 0, s.ais);
-        __syncwarp();
-        STAT_T(3);
-        if (f.op == OP_DIFFER) f.resB = f_differ(sm, f.a1, f.a2) ? 1 : 0;
-        __syncwarp();
-        STAT_T(4);
-        // ---------------- subtree scans: the whole warp works for one lane's search at a time
-        for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1)
-            warp_scan_job(__ffs(pending) - 1, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags, st);
-        STAT_T(5);
-        if (__all_sync(0xffffffffu, stage == 3)) break;
-    }
+    fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
+                         lanesPerWarp, W, W2, mbarParity);
     if (stats) {
         __syncthreads();
         for (int i = threadIdx.x; i < kNumSearchStats; i += blockDim.x) {
@@ -424,8 +366,6 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
             if (v) atomicAdd(stats + i, v);
         }
     }
-#undef STAT_T
-#undef STAT_N
 }
 
 // one new-sample placement per thread (place.cuh); threads pull samples from a global counter
@@ -572,6 +512,8 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     maple_ctx* ctx = new maple_ctx();
     ctx->device = device;
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
+    if (const char* e = getenv("MAPLE_SCAN_OLD")) ctx->scanOldEnv = atoi(e) != 0;
+    ctx->scanOld = ctx->scanOldEnv;
     if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 0 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 0; }
     if (const char* e = getenv("MAPLE_SCAN_REPLAY")) ctx->scanReplaySequential = strcmp(e, "sequential") == 0;
     if (const char* e = getenv("MAPLE_SCAN_APPEND")) ctx->scanAppendSitewise = strcmp(e, "q4") != 0;
@@ -607,6 +549,9 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->retryCounters);
     cudaFree(ctx->treeDerived);
     cudaFree(ctx->searchStats);
+    cudaFree(ctx->scanUnits);
+    cudaFree(ctx->scanArena);
+    cudaFree(ctx->scanRecs);
     delete ctx;
     return MAPLE_OK;
 }
@@ -919,6 +864,33 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
     ctx->treeHeight = height;
     ctx->treeHasMut = mutStart && (mutBelow[root] || hMs[root + 1] > hMs[root]);
     ctx->haveTree = true;
+    // second form of the scans: where the scan-format copy of each probVectTotUp list goes (dense, in pre-order)
+    ctx->scan2Ok = false;
+    cudaFree(ctx->scanUnits); cudaFree(ctx->scanArena); cudaFree(ctx->scanRecs);
+    ctx->scanUnits = nullptr; ctx->scanOffsets = nullptr; ctx->scanArena = nullptr; ctx->scanRecs = nullptr;
+    t.scan2 = nullptr; t.scanArena = nullptr; t.scanOff = nullptr;
+    if (height < 65535) {
+        CK(cudaMalloc((void**)&ctx->scanUnits, 2 * n * sizeof(uint32_t)));
+        ctx->scanOffsets = ctx->scanUnits + n;
+        DevTree T = t;
+        T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
+        k_scan_count<<<(unsigned)((n + 255) / 256), 256>>>(T, ctx->scanUnits);
+        ctx->launches++;
+        std::vector<uint32_t> hu(n), ho(n);
+        CK(cudaMemcpy(hu.data(), ctx->scanUnits, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        uint64_t tot = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t u = (hu[i] & 0xffffu) + (hu[i] >> 16);
+            if (u == 0 || tot + u >= 0xffffffffull) { ho[i] = ~0u; continue; }
+            ho[i] = (uint32_t)tot;
+            tot += u;
+        }
+        CK(cudaMemcpy(ctx->scanOffsets, ho.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMalloc((void**)&ctx->scanArena, (size_t)(tot + 4) * sizeof(uint4)));
+        CK(cudaMalloc((void**)&ctx->scanRecs, n * sizeof(ScanRec)));
+        t.scan2 = ctx->scanRecs; t.scanArena = ctx->scanArena; t.scanOff = ctx->scanOffsets;
+        ctx->scan2Ok = true;
+    }
     return MAPLE_OK;
 }
 
@@ -946,10 +918,11 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocksPerSM = 0;
     if (ctx->searchVariant == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_spr_search, kSearchThreads, 0));
     // shared memory: a fixed part per warp plus as much list pool as the targeted CTAs per SM leave (227 KB per SM, 1 KB reserved per CTA)
+    const bool scan2 = ctx->searchVariant == 0 && ctx->scan2Ok && !ctx->scanOld && T.order && ctx->scanMinSize > 0;
     const int ctasWanted = ctx->fsmMinBlocks == 6 ? 6 : 8;
-    const int fixedPerWarp = int(sizeof(ScanSmem) - sizeof(uint4));
+    const int fixedPerWarp = int((scan2 ? sizeof(Scan2Smem) : sizeof(ScanSmem)) - sizeof(uint4));
     int poolBytes = ((227 * 1024 / ctasWanted - 2048) / (kSearchThreads / 32) - fixedPerWarp) & ~15;
-    if (poolBytes > 12288) poolBytes = 12288;
+    if (poolBytes > (scan2 ? 16384 : 12288)) poolBytes = scan2 ? 16384 : 12288;
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
@@ -960,9 +933,14 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     // touchy: check `-Xptxas -v` after changing it -- a 128-register build with ~2 kB of spills is as slow as 168 registers.)
     // Keep the three instantiations: with only <6> and <7> present the same <7> comes out with 2 kB of spills.  96-register builds
     // (<9>, <10>: 10 CTAs per SM, half the list pool) were measured too: 5.5 s against 3.1-3.4 s.
-    FsmKernel fsmKernel = k_spr_search_fsm<6>;
-    if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8>;
-    if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7>;
+    FsmKernel fsmKernel = k_spr_search_fsm<6, false>;
+    if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8, false>;
+    if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7, false>;
+    if (scan2) {
+        fsmKernel = k_spr_search_fsm<6, true>;
+        if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8, true>;
+        if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7, true>;
+    }
     if (ctx->searchVariant != 1) {
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1004,7 +982,12 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     double* scrAis = (double*)(base + owners * capP * 8);
     StackE* scrStack = (StackE*)(base + owners * (capP + capA) * 8);
     uint32_t* scrKey = (uint32_t*)(base + owners * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
-    if ((ctx->searchVariant == 0 || ctx->searchVariant == 3) && T.order && ctx->scanMinSize > 0) {
+    if (scan2) {
+        k_scan_build<<<(T.nNodes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->model, T, sp.effectivelyNon0BLen, ctx->scanUnits, ctx->scanArena,
+                                                                              ctx->scanRecs);
+        k_scan_nsa<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, ctx->scanRecs);
+        ctx->launches += 2;
+    } else if ((ctx->searchVariant == 0 || ctx->searchVariant == 3) && T.order && ctx->scanMinSize > 0) {
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, sp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
     }
@@ -1153,8 +1136,9 @@ int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant) {
 }
 
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
-    if (!ctx || variant < 0 || variant > 3) return MAPLE_E_ARG;
-    ctx->searchVariant = variant;
+    if (!ctx || variant < 0 || variant > 4) return MAPLE_E_ARG;
+    ctx->searchVariant = variant == 4 ? 0 : variant;
+    ctx->scanOld = variant == 4 ? true : ctx->scanOldEnv;
     return MAPLE_OK;
 }
 

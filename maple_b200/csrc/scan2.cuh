@@ -1,0 +1,696 @@
+// Subtree scans of the SPR search, second form: scan-format lists, bulk-copy staging, prefix-form replay.
+//
+// What a scan job is, and why its results equal the reference's walk (MAPLEv0.7.5.4.py:6975-7170), is described above
+// warp_scan_job in search_fsm.cuh; this file keeps that contract (same visited set, same counts, same phase-2 queue in
+// discovery order, same per-depth hand-down) and changes how the work is laid out:
+//
+//  * SCAN-FORMAT LISTS.  Once per launch k_scan_build rewrites every stored probVectTotUp list into a walk-friendly
+//    copy in a dense arena ordered by pre-order position: 8-byte entries {key, aux} followed by the payload.  aux
+//    carries the entry's payload index and a few class bits, and the payload of a nucleotide entry carries
+//    mutMatrices[pos][nuc][ref] (Q * siteRate, :6367) so that the commonest site -- a certain nucleotide of the candidate
+//    branch against a reference run of the removed subtree, :6729-6742 -- costs one shared-memory load and two multiplies.
+//    The removed list (the same for every candidate of a job) gets the same treatment once per job, and there the whole
+//    factor min(0.25, Q[ref][c]*rate*(bLen+len)) of a nucleotide against a plain reference run of the candidate (:6657-6663)
+//    is precomputed.  One AND of the two aux words classifies a segment: nothing to do / one of the two precomputed cases /
+//    general site (the unchanged append_site code, run with the lanes converged).  Same factors, same order of
+//    multiplications, same carry-over rule as dev_append: the scores are bit-identical to the lane path's.
+//  * STAGING.  The lists of a window's candidates are neighbours in the scan arena, so one cp.async.bulk (UBLKCP) per
+//    window brings them to shared memory, completion on an mbarrier; no registers, no per-lane copy loops.
+//  * REPLAY.  What a node hands to its children only changes at SCORED nodes, so every node carries the position of its
+//    nearest scored proper ancestor (static per tree; k_scan_build).  With it the bookkeeping of a window is: running best =
+//    prefix maximum over the (at most 32) scored nodes; failedPasses = one pointer-jumping pass over those <= 32 lanes in
+//    registers; stop rule per node; "reached" = no earlier node of the window that does not descend covers me, i.e. an
+//    exclusive prefix maximum of (w + size[w]) over non-descending nodes.  The prefix maximum of the scores includes nodes the
+//    stop rule prunes; that is exact unless a pruned node holds a new best, which is checked -- such a window is replayed node
+//    by node like the reference does.
+#pragma once
+#include "search.cuh"
+
+namespace maple {
+
+// ---------------------------------------------------------------------------------------------------------------
+// scan-format lists
+// entry.x = the arena key (type | nLens<<3 | flag<<5 | nuc<<6 | end<<8); entry.y = aux:
+//   bits 0-15  index (in doubles, from the list's payload base) of the entry's payload: [len0][len1] then, for a
+//              nucleotide entry, [g] (candidate side) or, for an O entry, the 4-vector.  On the removed-list side a
+//              nucleotide entry is laid out [f][len0][g] with the index pointing at len0, so f sits at index-1.
+//   bits 16-22 candidate side: one-hot of the entry type; removed side: types of the OTHER list this entry is informative
+//              against (append_informative) -- the AND of both is non-zero exactly at the informative segments
+//   bit 31     candidate side: plain reference run (type R, no lengths); removed side: nucleotide with at most one length
+//   bit 30     candidate side: plain nucleotide (no lengths); removed side: plain reference run (and bLen != 0)
+//   (bits 30/31 are only set without the error model: with it every site takes the general code)
+constexpr uint32_t SA_IDX = 0xffffu, SA_TYPES = 0x7f0000u, SA_FAST_C = 0x80000000u, SA_FAST_P = 0x40000000u;
+
+struct ScanRec {  // one per pre-order position, 32 bytes
+    int32_t node;
+    int32_t size;     // nodes in the subtree
+    int32_t nsa;      // pre-order position of the nearest SCORED proper ancestor, -1 if there is none
+    uint32_t depths;  // depth | depth of that ancestor << 16
+    uint32_t off;     // scan-format list: offset in the scan arena, 16-byte units (valid with SR_STAGED)
+    uint32_t cnt;     // 16-byte units: entries | payload << 16
+    uint32_t flags;   // SN_ELIG | SN_TOT | SN_PUSHED | SN_INNER as in ScanNode, plus:
+    uint32_t pad;
+};
+constexpr uint32_t SR_STAGED = 16;  // a scan-format copy of probVectTotUp exists
+constexpr uint32_t SR_SCORED = 64;  // SN_ELIG && SN_TOT && SN_PUSHED: the walk scores this node when it reaches it
+
+// upper bound of the scan-format size of a list with nk entries and np payload doubles, in 16-byte units
+__host__ __device__ inline uint32_t scan_list_units(int nk, int np) { return uint32_t((nk + 1) >> 1) + uint32_t((np + nk + 1) >> 1); }
+
+// Candidate-side copy of one stored list.  Returns the payload doubles written.
+__device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const double* p, int nk, uint2* outE, double* outP) {
+    int np = 0, ip = 0;
+    for (int i = 0; i < nk; i++) {
+        const uint32_t key = __ldg(k + i);
+        const int type = int(key & 7u), nl = int((key >> 3) & 3u), nuc = int((key >> 6) & 3u), end = int(key >> 8);
+        uint32_t aux = uint32_t(np) | (1u << (16 + type));
+        if (!m.U) {
+            if (type == T_R && nl == 0) aux |= SA_FAST_C;
+            if (type < 4 && nl == 0) aux |= SA_FAST_P;
+        }
+        for (int q = 0; q < nl; q++) outP[np++] = __ldg(p + ip + q);
+        ip += nl;
+        if (type < 4) {
+            const SiteQ q(m, end - 1);
+            outP[np++] = q.at(type, nuc);  // mutMatrices[pos][nuc of the entry][reference nuc]
+        } else if (type == T_O) {
+            for (int q = 0; q < 4; q++) outP[np++] = __ldg(p + ip + q);
+            ip += 4;
+        }
+        outE[i] = make_uint2(key, aux);
+    }
+    if (nk & 1) outE[nk] = make_uint2(0u, 0u);
+    return np;
+}
+
+// Removed-side copy (one per job, shared memory).  Returns the payload doubles written, or -1 if it does not fit.
+__device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const double* p, double bLen, uint2* outE, int capE, double* outP, int capP) {
+    constexpr unsigned long long INF = append_informative_mask();
+    int np = 0, ip = 0;
+    for (int i = 0;; i++) {
+        if (i >= capE) return -1;
+        const uint32_t key = k[i];
+        const int type = int(key & 7u), nl = int((key >> 3) & 3u), nuc = int((key >> 6) & 3u), end = int(key >> 8);
+        if (np + 8 > capP || np + 8 > int(SA_IDX)) return -1;
+        uint32_t row = 0;
+        for (int t1 = 0; t1 < 7; t1++) row |= uint32_t((INF >> (t1 * 8 + type)) & 1ull) << t1;
+        const bool fastNuc = !m.U && type < 4 && nl <= 1;
+        uint32_t aux = (row << 16) | uint32_t(np + (type < 4 ? 1 : 0));
+        if (fastNuc) aux |= SA_FAST_C;
+        if (!m.U && type == T_R && nl == 0 && bLen != 0.0) aux |= SA_FAST_P;
+        if (type < 4) {
+            const SiteQ q(m, end - 1);
+            const double g = q.at(nuc, type);  // mutMatrices[pos][reference nuc][nuc of the entry]
+            double contrib = bLen;
+            if (nl == 1) contrib += p[ip];
+            // the whole factor against a plain reference run of the candidate (:6657-6663); -1 marks "the reference returns -inf"
+            outP[np++] = (contrib == 0.0) ? -1.0 : fmin(0.25, g * contrib);
+            for (int q2 = 0; q2 < nl; q2++) outP[np++] = p[ip + q2];
+            ip += nl;
+            outP[np++] = g;
+        } else {
+            for (int q2 = 0; q2 < nl; q2++) outP[np++] = p[ip + q2];
+            ip += nl;
+            if (type == T_O) {
+                for (int q2 = 0; q2 < 4; q2++) outP[np++] = p[ip + q2];
+                ip += 4;
+            }
+        }
+        outE[i] = make_uint2(key, aux);
+        if (end == m.lRef) return np;
+    }
+}
+
+__device__ __noinline__ double scan_site_general(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
+                                                 double bLen, bool isTipC, double F) {
+    return append_site_ref(m, k1, pay1, k2, pay2, pos, bLen, isTipC, F);
+}
+
+// appendProbNode(candidate list, removed list, isTipC, bLen) over the scan-format copies: the arithmetic and its order are
+// dev_append's (:6505-6785).  pCm1 = removed-side payload base minus one double.
+__device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, const double* pP, const uint2* eC, const double* pC, bool isTipC,
+                                            double bLen) {
+    const int lRef = m.lRef;
+    const double* pCm1 = pC - 1;
+    uint2 a = eP[0], b = eC[0];
+    double F = 1.0;
+    double Lk = bLen * (-(double)lRef);
+    if (m.U && isTipC) Lk += m.totError;
+    for (;;) {
+        bool general = false;
+        int np;
+        for (;;) {
+            const uint32_t mm = a.y & b.y;
+            const int e1 = int(a.x >> 8), e2 = int(b.x >> 8);
+            np = min(e1, e2);
+            if (mm & (SA_FAST_C | SA_FAST_P | SA_TYPES)) {
+                if (mm & (SA_FAST_C | SA_FAST_P)) {
+                    const double f = (mm & SA_FAST_C) ? pCm1[b.y & SA_IDX] : fmin(0.25, pP[a.y & SA_IDX] * bLen);
+                    F *= f;
+                    if (F <= kMinCarryOver && np != lRef) {  // :6772-6783 (also catches the -1 marker)
+                        if (F < DBL_MIN) return -INFINITY;
+                        Lk += log(F);
+                        F = 1.0;
+                    }
+                } else {
+                    general = true;
+                    break;
+                }
+            }
+            if (np == lRef) break;
+            if (e1 == np) a = *++eP;
+            if (e2 == np) b = *++eC;
+        }
+        if (!general) break;
+        F = scan_site_general(m, a.x, pP + (a.y & SA_IDX), b.x, pC + (b.y & SA_IDX), np - 1, bLen, isTipC, F);
+        if (F < 0.0) return -INFINITY;
+        if (np == lRef) break;
+        if (F <= kMinCarryOver) {
+            if (F < DBL_MIN) return -INFINITY;
+            Lk += log(F);
+            F = 1.0;
+        }
+        if (int(a.x >> 8) == np) a = *++eP;
+        if (int(b.x >> 8) == np) b = *++eC;
+    }
+    if (!(F > 0.0)) return -INFINITY;
+    return Lk + log(F);
+}
+
+// The record of pre-order position i (k_scan_build, one thread per position).  nsaOf[] = nearest scored ancestor-or-self per
+// position, filled top-down by the caller (see scan_build_all).
+__device__ inline uint32_t scan_static_flags(const DevTree& T, double eff, int node) {
+    const int up = T.up[node];
+    const int64_t nN = T.nNodes;
+    uint32_t fl = 0;
+    if (up >= 0 && (T.dist[node] > eff || T.up[up] < 0)) fl |= SN_ELIG;
+    if (up >= 0 && T.keyStart[(T.child0[up] == node ? 1 : 2) * nN + up] >= 0) fl |= SN_PUSHED;
+    if (T.child0[node] >= 0) fl |= SN_INNER;
+    if (T.keyStart[3 * nN + node] >= 0) fl |= SN_TOT;
+    if ((fl & (SN_ELIG | SN_TOT | SN_PUSHED)) == (SN_ELIG | SN_TOT | SN_PUSHED)) fl |= SR_SCORED;
+    return fl;
+}
+
+// 16-byte units of the scan-format copy of the probVectTotUp list at pre-order position i: entries | payload << 16
+// (0 = no list, or too large to stage).  maple_tree_bind turns these into offsets.
+__device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
+    const int node = T.order[i];
+    if (node < 0 || T.pre[node] != i) return 0;
+    const int64_t id = 3 * (int64_t)T.nNodes + node, ks = T.keyStart[id];
+    if (ks < 0) return 0;
+    const int nk = T.nkeys[id];
+    int np = 0;
+    for (int q = 0; q < nk; q++) {
+        const uint32_t key = __ldg(T.key + ks + q);
+        const int type = int(key & 7u);
+        np += int((key >> 3) & 3u) + (type == T_O ? 4 : 0) + (type < 4 ? 1 : 0);
+    }
+    const uint32_t ue = uint32_t(nk + 1) >> 1, up = uint32_t(np + 1) >> 1;
+    return (nk > 0 && ue < 65536u && up < 65536u && np < 65536) ? (ue | (up << 16)) : 0u;
+}
+
+// The record of pre-order position i and, where there is one, the scan-format copy of its list (nsa is filled by scan_fill_nsa
+// once every record exists).
+__device__ inline ScanRec scan_build_rec(const DevModel& m, const DevTree& T, double eff, int i, uint32_t units, uint4* arena) {
+    ScanRec r;
+    const int node = T.order[i];
+    r.node = node; r.size = 1; r.nsa = -1; r.depths = 0; r.off = 0; r.cnt = 0; r.flags = 0; r.pad = 0;
+    if (node < 0 || T.pre[node] != i) {  // positions past the reachable nodes
+        r.node = -1;
+        return r;
+    }
+    r.size = T.size[node];
+    r.depths = uint32_t(T.depth[node]) & 0xffffu;
+    r.flags = scan_static_flags(T, eff, node);
+    const uint32_t off = T.scanOff[i];
+    if (off != ~0u && units) {
+        const int64_t id = 3 * (int64_t)T.nNodes + node;
+        uint4* dst = arena + off;
+        scan_build_p(m, T.key + T.keyStart[id], T.pay + T.payStart[id], T.nkeys[id], reinterpret_cast<uint2*>(dst),
+                     reinterpret_cast<double*>(dst + (units & 0xffffu)));
+        r.off = off;
+        r.cnt = units;
+        r.flags |= SR_STAGED;
+    }
+    return r;
+}
+
+__device__ inline void scan_fill_nsa(const DevTree& T, ScanRec* recs, int i) {
+    const int node = recs[i].node;
+    if (node < 0) return;
+    int a = T.up[node];
+    while (a >= 0) {
+        const int pa = T.pre[a];
+        if (recs[pa].flags & SR_SCORED) {
+            recs[i].nsa = pa;
+            recs[i].depths |= (uint32_t(T.depth[a]) & 0xffffu) << 16;
+            return;
+        }
+        a = T.up[a];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the job
+constexpr int kWin2 = 96;    // pre-order positions per window
+constexpr int kPath2 = 40;   // per-depth states kept in shared memory (deeper ones in global scratch)
+
+struct PathE2 {  // what a node hands to its children: midProb and failedPasses (:7090-7106)
+    double lk;
+    int failed, pad;
+};
+
+struct ScanJob {  // filled by the lane that owns the search
+    int R, pruned, sibling, failed0;
+    double best, lastLK0, removedBLen;
+    int isRemovedTip, pathCap, qCap, pad;
+    const uint32_t* remK;
+    const double* remP;
+    PathE2* gpath;
+    uint32_t* qTop;
+    // results
+    double bestOut;
+    int phase1, qN, newBest, err;
+};
+
+struct Scan2Smem {
+    double scoreS[32];  // by rank k: score of the k-th scored node of the window
+    double bbS[32];     // running best after the k-th scored node
+    PathE2 path[kPath2];
+    uint32_t info[kWin2];  // by window position: record flags | number of scored nodes before it << 8 | depth below the job's root << 16
+    int size[kWin2];
+    int failS[32];    // by rank: failedPasses handed down
+    uint32_t offS[32], cntS[32];
+    short nsa[kWin2];  // window position of the nearest scored proper ancestor, or -(path index)-1
+    unsigned char slotS[32];  // by rank: window position
+    unsigned long long mbar;
+    ScanJob job;
+    uint4 pool[1];  // the removed list's scan-format copy (for the whole job), then the window's lists
+};
+
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(b)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one lane: arm the barrier with the byte count and start the bulk copy global -> shared
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
+__device__ __forceinline__ double warp_max_incl_d(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double x = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = fmax(v, x);
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_max_incl_i(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = max(v, x);
+    }
+    return v;
+}
+
+__device__ __noinline__ double scan_append_generic(const DevModel& m, const uint32_t* kP, const double* pP, const uint32_t* kC, const double* pC,
+                                                   bool isTipC, double bLen) {
+    return dev_append_sitewise<true>(m, kP, pP, kC, pC, isTipC, bLen);
+}
+
+// W.job holds the request (written by the owning lane, visible to the warp); the results are left in W.job.
+// mbarParity: phase parity of W.mbar, kept by the caller across jobs.  st: optional profiling counters (lane 0 adds).
+__device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const SearchParams& sp, Scan2Smem& W, int poolBytes, int scanFlags /* 2: every window replayed node by node */,
+                               uint32_t& mbarParity, unsigned long long* st) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = int(threadIdx.x & 31);
+    const unsigned ltMask = (1u << lane) - 1u;
+    const ScanJob J = W.job;
+    const int R = J.R;
+    double best = J.best;
+    const bool isRemovedTip = J.isRemovedTip != 0;
+    const double removedBLen = J.removedBLen;
+    PathE2* const gpath = J.gpath;
+    const int pathCap = J.pathCap, qCap = J.qCap;
+    uint32_t* const qTop = J.qTop;
+    int phase1 = 0, qN = 0, newBest = 0, err = 0;
+    int pos = t.pre[R];
+    const int end = pos + t.size[R], d0 = t.depth[R];
+    long long tk = st ? clock64() : 0;
+    if (st && lane == 0) { st[17] += 1; st[18] += (unsigned long long)(end - pos); }
+    // ---- the removed list in scan format, at the front of the pool: the same for every candidate of the job
+    int cEntUnits = 0, cUnits = 0;  // 16-byte units of its entries / of the whole copy; cUnits == 0: it does not fit (at most half the pool)
+    if (lane == 0) {
+        int nkC = 0;
+        const int capE = poolBytes >> 4;  // half the pool at 8 bytes per entry
+        while (nkC < capE && int(J.remK[nkC] >> 8) != m.lRef) nkC++;
+        nkC++;
+        cEntUnits = (nkC + 1) >> 1;
+        const int capP = ((poolBytes >> 1) - 16 * cEntUnits) >> 3;
+        if (nkC <= capE && capP >= 8) {
+            const int npC = scan_build_c(m, J.remK, J.remP, removedBLen, reinterpret_cast<uint2*>(W.pool), nkC,
+                                         reinterpret_cast<double*>(W.pool + cEntUnits), capP);
+            if (npC >= 0) cUnits = cEntUnits + ((npC + 1) >> 1);
+        }
+        if (pathCap < 2) err = 3;
+        else W.path[0] = PathE2{J.lastLK0, J.failed0, 0};
+    }
+    cEntUnits = __shfl_sync(FULL, cEntUnits, 0);
+    cUnits = __shfl_sync(FULL, cUnits, 0);
+    const bool cOk = cUnits > 0;
+    err = __shfl_sync(FULL, err, 0);
+    __syncwarp();
+    const uint4* const arena = t.scanArena;
+    const int poolUnits = (poolBytes >> 4) - cUnits;
+    uint4* const winPool = W.pool + cUnits;
+    const uint2* const cEnt = reinterpret_cast<const uint2*>(W.pool);
+    const double* const cPay = reinterpret_cast<const double*>(W.pool + cEntUnits);
+    while (pos < end && !err) {
+        // ---- window: positions pos .. pos+nWin-1, at most 32 of them scored, their lists within the pool
+        int nWin = 0, nScore = 0;
+        bool generic = !cOk;  // some list has no scan-format copy: the whole window is scored from the arena lists
+        bool dyn = false;
+        for (int sweep = 0; sweep < kWin2 / 32 && pos + nWin < end && nScore < 32; sweep++) {
+            const int w = nWin + lane, idx = pos + w;
+            uint32_t flags = 0, off = 0, cnt = 0;
+            int size = 1, nsaCode = -1, rel = 0;
+            if (idx < end) {
+                const uint4* src4 = reinterpret_cast<const uint4*>(t.scan2 + idx);
+                const uint4 a4 = __ldg(src4), b4 = __ldg(src4 + 1);
+                const int node = int(a4.x), nsa = int(a4.z);
+                size = int(a4.y);
+                const int depth = int(a4.w & 0xffffu), nsaDepth = int(a4.w >> 16);
+                off = b4.x; cnt = b4.y; flags = b4.z;
+                // Two per-search exceptions to the static flags.  Neither occurs on the walks the state machine hands over (the
+                // children of the pruned node's parent are never inside a scanned subtree, and a job's root was pushed through an
+                // existing upper list), but if one did, the static ancestor links would be off: such a window is replayed node by node.
+                if (node == J.pruned || node == J.sibling) {  // children of the pruned node's parent are not scored (:6978)
+                    if (flags & SR_SCORED) dyn = true;
+                    flags &= ~(SN_ELIG | SR_SCORED);
+                }
+                if (node == R && !(flags & SN_PUSHED)) {
+                    flags |= SN_PUSHED;
+                    if ((flags & (SN_ELIG | SN_TOT)) == (SN_ELIG | SN_TOT)) { flags |= SR_SCORED; dyn = true; }
+                }
+                rel = depth - d0;
+                if (nsa >= pos) nsaCode = nsa - pos;
+                else {
+                    const int pi = (nsa >= 0 && nsaDepth >= d0) ? nsaDepth - d0 + 1 : 0;
+                    nsaCode = -pi - 1;
+                }
+            }
+            const unsigned need = __ballot_sync(FULL, (flags & SR_SCORED) != 0);
+            const int room = 32 - nScore;
+            int take = min(32, end - pos - nWin);
+            if (__popc(need) > room) take = __fns(need, 0, room) + 1;  // cut right after the node that fills the last lane
+            const unsigned mine = need & (take >= 32 ? FULL : ((1u << take) - 1u));
+            const int rank = nScore + __popc(mine & ltMask);
+            if (lane < take) {
+                W.info[w] = (flags & 0xffu) | (uint32_t(rank) << 8) | (uint32_t(rel) << 16);
+                W.size[w] = size;
+                W.nsa[w] = short(nsaCode);
+                if (flags & SR_SCORED) {
+                    W.slotS[rank] = (unsigned char)w;
+                    W.offS[rank] = off;
+                    W.cntS[rank] = cnt;
+                }
+            }
+            if (__any_sync(FULL, lane < take && (flags & SR_SCORED) && !(flags & SR_STAGED))) generic = true;
+            nScore += __popc(mine);
+            nWin += take;
+        }
+        __syncwarp();
+        // cut the window where its lists stop fitting the pool
+        uint32_t myOff = 0, myCnt = 0, off0 = 0;
+        if (!generic && nScore > 0) {
+            if (lane < nScore) { myOff = W.offS[lane]; myCnt = W.cntS[lane]; }
+            off0 = __shfl_sync(FULL, myOff, 0);
+            const uint32_t myEnd = myOff + (myCnt & 0xffffu) + (myCnt >> 16) - off0;
+            const unsigned fits = __ballot_sync(FULL, lane < nScore && myEnd <= uint32_t(poolUnits));
+            const int nFit = fits == FULL ? 32 : __ffs(~fits) - 1;  // leading run of lists that fit (offsets grow with the position)
+            if (nFit == 0) generic = true;
+            else if (nFit < nScore) {
+                nWin = W.slotS[nFit];
+                nScore = nFit;
+            }
+        }
+        // ---- stage the lists: one bulk copy, completion on the mbarrier
+        double sc = -INFINITY;
+#ifdef __CUDA_ARCH__
+        if (!generic && nScore > 0) {
+            const uint32_t endLast = __shfl_sync(FULL, myOff + (myCnt & 0xffffu) + (myCnt >> 16), nScore - 1);
+            if (lane == 0) bulk_load(winPool, arena + off0, (endLast - off0) << 4, &W.mbar);
+            mbar_wait(&W.mbar, mbarParity);
+            mbarParity ^= 1u;
+        }
+#endif
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) { st[23] += (unsigned long long)(now - tk); st[19] += 1; st[20] += nScore; st[24] += nWin; }
+            tk = now;
+        }
+        if (lane < nScore) {
+            if (!generic) {
+#ifdef __CUDA_ARCH__
+                const uint4* base = winPool + (myOff - off0);
+#else
+                const uint4* base = arena + myOff;
+#endif
+                const uint2* eP = reinterpret_cast<const uint2*>(base);
+                const double* pP = reinterpret_cast<const double*>(base + (myCnt & 0xffffu));
+                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen);
+            } else {
+                const int64_t id = 3 * (int64_t)t.nNodes + __ldg(&t.scan2[pos + W.slotS[lane]].node);
+                sc = scan_append_generic(m, t.key + t.keyStart[id], t.pay + t.payStart[id], J.remK, J.remP, isRemovedTip, removedBLen);
+            }
+        }
+        __syncwarp();
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) st[6] += (unsigned long long)(now - tk);
+            tk = now;
+        }
+        // ---- replay of the reference's bookkeeping over the window, prefix form
+        // running best after each scored node (lane k = k-th scored node)
+        const double bbIn = fmax(best, warp_max_incl_d(sc, lane));
+        double bbEx = __shfl_up_sync(FULL, bbIn, 1);
+        if (lane == 0) bbEx = best;
+        // failedPasses handed down by each scored node: SET 0 on a new best, else inherited + (1 on a consecutive worsening)
+        int fval = 0, ptr = -1;
+        {
+            double lkIn = 0.0;
+            int code = -1;
+            if (lane < nScore) code = W.nsa[W.slotS[lane]];
+            const int anc = code >= 0 ? (W.info[code] >> 8) & 0xff : 0;  // rank of the scored ancestor inside the window
+            const double ancScore = __shfl_sync(FULL, sc, anc);
+            if (lane < nScore) {
+                int failedIn = 0;
+                if (code >= 0) lkIn = ancScore;
+                else {
+                    const int pi = -code - 1;
+                    const PathE2 pe = pi < kPath2 ? W.path[pi] : gpath[pi];
+                    lkIn = pe.lk;
+                    failedIn = pe.failed;
+                }
+                const bool nb = sc > bbEx;
+                if (!nb) {
+                    fval = (sc < (lkIn - sp.thresholdLogLKconsecutivePlacement)) ? 1 : 0;
+                    if (code >= 0) ptr = anc;
+                    else fval += failedIn;
+                }
+            }
+            while (__any_sync(FULL, ptr >= 0)) {
+                const int q = ptr >= 0 ? ptr : 0;
+                const int pv = __shfl_sync(FULL, fval, q), pp = __shfl_sync(FULL, ptr, q);
+                if (ptr >= 0) { fval += pv; ptr = pp; }
+            }
+        }
+        if (lane < nScore) { W.scoreS[lane] = sc; W.bbS[lane] = bbIn; W.failS[lane] = fval; }
+        __syncwarp();
+        // stop rule of every node as if it were reached; a node that does not descend hides the rest of its subtree
+        constexpr int NC = kWin2 / 32;
+        double midc[NC];
+        int failc[NC], skipc[NC];
+        uint32_t infc[NC];
+        bool scoredc[NC], nbc[NC], quec[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const int w = c * 32 + lane;
+            midc[c] = 0.0; failc[c] = 0; infc[c] = 0; skipc[c] = 0;
+            scoredc[c] = nbc[c] = quec[c] = false;
+            if (w < nWin) {
+                const uint32_t inf = W.info[w];
+                infc[c] = inf;
+                const int r = int((inf >> 8) & 0xffu);
+                const double before = r == 0 ? best : W.bbS[r - 1];
+                const bool scored = (inf & SR_SCORED) != 0;
+                double bestAfter = before;
+                if (scored) {
+                    midc[c] = W.scoreS[r];
+                    failc[c] = W.failS[r];
+                    bestAfter = W.bbS[r];
+                    nbc[c] = midc[c] > before;
+                    quec[c] = midc[c] > before - sp.thresholdLogLKoptimizationTopology;  // :7071
+                } else {
+                    const int code = W.nsa[w];
+                    if (code >= 0) {
+                        const int q = (W.info[code] >> 8) & 0xff;
+                        midc[c] = W.scoreS[q];
+                        failc[c] = W.failS[q];
+                    } else {
+                        const int pi = -code - 1;
+                        const PathE2 pe = pi < kPath2 ? W.path[pi] : gpath[pi];
+                        midc[c] = pe.lk;
+                        failc[c] = pe.failed;
+                    }
+                }
+                scoredc[c] = scored;
+                const bool within = midc[c] > (bestAfter - sp.thresholdLogLKtopology);
+                const bool rule = sp.strictTopologyStopRules ? (failc[c] <= sp.allowedFailsTopology && within)
+                                                             : (failc[c] <= sp.allowedFailsTopology || within);
+                const bool dead = (inf & (SN_ELIG | SN_TOT)) == SN_ELIG;  // eligible but no probVectTotUp: the walk moves on (:6999)
+                const bool descend = (inf & SN_PUSHED) && !dead && (inf & SN_INNER) && rule;
+                skipc[c] = descend ? 0 : w + W.size[w];
+            }
+        }
+        // reached = no earlier node of the window that does not descend covers me
+        int maxTarget = 0, nCounted = 0;
+        bool bad = false, anyNb = false;
+        {
+            int carry = 0;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                const int incl = max(carry, warp_max_incl_i(skipc[c], lane));
+                int excl = __shfl_up_sync(FULL, incl, 1);
+                if (lane == 0) excl = carry;
+                carry = __shfl_sync(FULL, incl, 31);
+                const bool reached = w < nWin && excl <= w;
+                if (w < nWin) {
+                    if (reached) {
+                        maxTarget = max(maxTarget, skipc[c] ? skipc[c] : w + 1);
+                        if (scoredc[c]) { nCounted++; anyNb |= nbc[c]; }
+                    } else {
+                        if (scoredc[c] && nbc[c]) bad = true;  // a pruned node would have raised the prefix maximum
+                        quec[c] = false;
+                        skipc[c] = -1;  // not reached
+                    }
+                }
+            }
+        }
+        int j = 0;
+        if (!__any_sync(FULL, bad || dyn) && !(scanFlags & 2)) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                maxTarget = max(maxTarget, __shfl_xor_sync(FULL, maxTarget, o));
+                nCounted += __shfl_xor_sync(FULL, nCounted, o);
+            }
+            j = maxTarget;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int w = c * 32 + lane;
+                const unsigned qm = __ballot_sync(FULL, quec[c]);
+                if (quec[c]) {
+                    const int at = qN + __popc(qm & ltMask);
+                    if (at < qCap) qTop[-1 - at] = uint32_t(__ldg(&t.scan2[pos + w].node));
+                }
+                qN += __popc(qm);
+                // a reached node that descends and whose subtree goes on past this window leaves its hand-down for the windows
+                // that follow (one such node per depth: they are the ancestors of the next window's first node)
+                if (w < nWin && skipc[c] == 0 && w + W.size[w] > j) {
+                    const int rel1 = int(infc[c] >> 16) + 1;
+                    if (rel1 >= pathCap) err = 3;
+                    else if (rel1 < kPath2) W.path[rel1] = PathE2{midc[c], failc[c], 0};
+                    else gpath[rel1] = PathE2{midc[c], failc[c], 0};
+                }
+            }
+            if (qN > qCap) err = 3;
+            err = __any_sync(FULL, err == 3) ? 3 : err;
+            if (__any_sync(FULL, anyNb)) newBest = 1;
+            if (nScore > 0) best = __shfl_sync(FULL, bbIn, nScore - 1);
+            phase1 += nCounted;
+        } else {
+            // node-by-node replay, as the reference walks (every lane runs it redundantly on the shared arrays)
+            if (st && lane == 0) st[25] += 1;
+            while (j < nWin) {
+                const uint32_t inf = W.info[j];
+                const int rel = int(inf >> 16), sz = W.size[j];
+                const bool scored = (inf & SR_SCORED) != 0;
+                PathE2 pe;
+                if (rel < kPath2) pe = W.path[rel];
+                else pe = gpath[rel];
+                double midProb = pe.lk;
+                int failed = pe.failed;
+                bool alive = true, descend = false;
+                if (inf & SN_PUSHED) {
+                    if (inf & SN_ELIG) {
+                        if (!(inf & SN_TOT)) alive = false;
+                        else if (scored) {
+                            midProb = W.scoreS[(inf >> 8) & 0xff];
+                            phase1++;
+                            if (midProb > best - sp.thresholdLogLKoptimizationTopology) {  // :7071
+                                if (qN >= qCap) err = 3;
+                                else if (lane == 0) qTop[-1 - qN] = uint32_t(__ldg(&t.scan2[pos + j].node));
+                                qN++;
+                            }
+                            if (midProb > best) { best = midProb; failed = 0; newBest = 1; }
+                            else if (midProb < (pe.lk - sp.thresholdLogLKconsecutivePlacement)) failed++;
+                        }
+                    }
+                    if (alive && (inf & SN_INNER)) {
+                        if (sp.strictTopologyStopRules) descend = failed <= sp.allowedFailsTopology && midProb > (best - sp.thresholdLogLKtopology);
+                        else descend = failed <= sp.allowedFailsTopology || midProb > (best - sp.thresholdLogLKtopology);
+                        if (descend) {
+                            if (rel + 1 >= pathCap) { err = 3; descend = false; }
+                            else if (rel + 1 < kPath2) { if (lane == 0) W.path[rel + 1] = PathE2{midProb, failed, 0}; }
+                            else if (lane == 0) gpath[rel + 1] = PathE2{midProb, failed, 0};
+                        }
+                    }
+                }
+                __syncwarp();
+                j += descend ? 1 : sz;
+                if (err) break;
+            }
+        }
+        pos += j;
+        __syncwarp();
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) st[7] += (unsigned long long)(now - tk);
+            tk = now;
+        }
+    }
+    __syncwarp();
+    if (st && lane == 0) { st[21] += (unsigned long long)phase1; st[22] += (unsigned long long)qN; }
+    if (lane == 0) {
+        W.job.bestOut = best;
+        W.job.phase1 = phase1;
+        W.job.qN = qN;
+        W.job.newBest = newBest;
+        W.job.err = err;
+    }
+    __syncwarp();
+}
+
+}  // namespace maple

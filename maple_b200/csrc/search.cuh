@@ -40,6 +40,11 @@ struct DevTree {
     const int32_t* depth;     // edges between the root and a node
     const uint8_t* mutBelow;  // some node strictly below carries MAT mutations
     const struct ScanNode* scan;  // [nNodes] per pre-order position, refreshed by k_scan_prepare before every search launch
+    // second form of the subtree scans (scan2.cuh): records and scan-format copies of the probVectTotUp lists, rebuilt by
+    // k_scan_build before every search launch; scan2 == nullptr disables it
+    const struct ScanRec* scan2;
+    const uint4* scanArena;
+    const uint32_t* scanOff;      // [nNodes] per pre-order position: offset of the list's copy in scanArena (16-byte units), ~0u = none
 };
 
 // Everything a subtree scan needs to know about the node at one pre-order position, in one 32-byte record (two 16-byte loads,

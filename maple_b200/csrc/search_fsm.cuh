@@ -12,6 +12,7 @@
 // state that lives across a co-walk sits in the Fsm struct, and YIELD_* are the suspension points.
 #pragma once
 #include "search.cuh"
+#include "scan2.cuh"
 
 namespace maple {
 
@@ -945,6 +946,146 @@ __device__ void fsm_finish(const Fsm& f, const DevTree& t, const SearchParams& s
             r.placement = f.ph.bestNode;
         }
     }
+}
+
+// The warp's main loop of k_spr_search_fsm: every iteration each lane advances its control code to the next co-walk request,
+// then the warp runs each kind of co-walk once for all lanes that requested it, then the pending subtree scans one after the
+// other with the whole warp.  Lanes pull searches from the global counter.  SCAN2 selects the second form of the scans
+// (scan2.cuh).  A function of its own so that tests/hostsim can run the very same loop with the lanes emulated.
+template <bool SCAN2>
+__device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree& T, const SearchParams& sp, int64_t n, const int32_t* __restrict__ nodes,
+                                              SearchResult* __restrict__ out, ScratchD s, StackE* stack, int stackCap, unsigned long long* counter,
+                                              long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
+                                              const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity) {
+    const int lane_ = int(threadIdx.x & 31);
+    const bool l0 = lane_ == 0;
+    const bool stats = st != nullptr;
+    long long tk = clock64();
+#define STAT_T(i) do { if (st) { const long long now_ = clock64(); if (l0) st[i] += (unsigned long long)(now_ - tk); tk = now_; } } while (0)
+#define STAT_N(i, v) do { if (st && l0) st[i] += (unsigned long long)(v); } while (0)
+    Fsm f;
+    f.op = OP_NONE;
+    f.pc = 0;
+    // lanes beyond lanesPerWarp own no search: they only lend a hand in the whole-warp subtree scans (fewer searches per warp =
+    // a long search shares its warp's time with fewer others)
+    int stage = (int(threadIdx.x & 31) < lanesPerWarp) ? 0 : 3;  // 0 idle, 1 current-placement append pending, 2 search running, 3 no more work
+    unsigned long long i = 0;
+    int node = -1;
+    double bestCurrentLK = 0.0;
+    long long c0 = 0;
+    SearchResult r;
+    for (;;) {
+        // ---------------- control (divergent, cheap)
+        if (stage == 2) {
+            fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
+        } else if (stage == 1) {
+            bestCurrentLK = f.resD;
+            r.bestCurrentLK = bestCurrentLK;
+            if (!(bestCurrentLK < sp.thresholdTopologyPlacement || T.dist[node] != 0.0)) {  // :9674
+                f.rc = 1;
+                f.op = OP_DONE;
+            } else {
+                const int parent = T.up[node];
+                f.pc = 0;
+                f.parent = parent;
+                f.child = (T.child0[parent] == node) ? 0 : 1;
+                f.bestLKdiff = bestCurrentLK;
+                f.removedBLen = T.dist[node];
+                f.phase1 = 0;
+                f.rc = 0;
+                s.topK = s.topP = 0;
+                stage = 2;
+                fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
+            }
+        }
+        while (stage != 3 && (stage == 0 || f.op == OP_DONE)) {
+            if (stage != 0) {  // a search (or its pre-check) just ended
+                if (stage == 2) fsm_finish(f, T, sp, node, bestCurrentLK, r);
+                else r.status = f.rc;
+                out[outIndex ? outIndex[i] : i] = r;
+                if (outCycles) outCycles[i] = clock64() - c0;
+                stage = 0;
+            }
+            i = atomicAdd(counter, 1ULL);
+            if (i >= (unsigned long long)n) { stage = 3; f.op = OP_NONE; break; }
+            node = nodes[i];
+            c0 = clock64();
+            r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
+            r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
+            f.op = OP_NONE;
+            if (T.up[node] < 0) { out[outIndex ? outIndex[i] : i] = r; continue; }
+            s.topK = s.topP = 0;
+            s.err = 0;
+            const int parent = T.up[node];
+            LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
+            if (n_mut(T, node)) vectUp = s_pass(sm, T, s, vectUp, node, false);
+            const LRef own = tree_list(T, 0, node);
+            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[outIndex ? outIndex[i] : i] = r; continue; }
+            f.a1 = vectUp; f.a2 = own; f.at1 = T.isTip[node] != 0; f.ab1 = T.dist[node];
+            f.op = OP_APPEND;
+            stage = 1;
+        }
+        // ---------------- co-walks, one kind at a time, lanes converged
+        __syncwarp();
+        STAT_T(0);
+        if (stats) {
+            const unsigned b1 = __ballot_sync(0xffffffffu, f.op == OP_APPEND), b2 = __ballot_sync(0xffffffffu, f.op == OP_MERGE),
+                           b3 = __ballot_sync(0xffffffffu, f.op == OP_BLEN), b4 = __ballot_sync(0xffffffffu, f.op == OP_DIFFER);
+            STAT_N(8, __popc(b1)); STAT_N(9, __popc(b2)); STAT_N(10, __popc(b3)); STAT_N(11, __popc(b4));
+            STAT_N(12, b1 != 0); STAT_N(13, b2 != 0); STAT_N(14, b3 != 0); STAT_N(15, b4 != 0); STAT_N(16, 1);
+            tk = clock64();
+        }
+        if (f.op == OP_APPEND) f.resD = f_append(sm, f.a1, f.a2, f.at1 != 0, f.ab1);
+        __syncwarp();
+        STAT_T(1);
+        if (f.op == OP_MERGE) {
+            Writer w;
+            w.init(s.key + s.topK, s.pay + s.topP);
+            if (f_merge(sm, f.a1, f.ab1, f.at1 != 0, f.a2, f.ab2, f.at2 != 0, f.aflags, w) == 0) f.resL = sc_commit(s, w.nk, w.np);
+            else f.resL = lnull();
+        }
+        __syncwarp();
+        STAT_T(2);
+        if (f.op == OP_BLEN) f.resD = f_blen(sm, f.a1, f.a2, f.at1 != 0, s.ais);
+        __syncwarp();
+        STAT_T(3);
+        if (f.op == OP_DIFFER) f.resB = f_differ(sm, f.a1, f.a2) ? 1 : 0;
+        __syncwarp();
+        STAT_T(4);
+        // ---------------- subtree scans: the whole warp works for one lane's search at a time
+        for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1) {
+            const int src = __ffs(pending) - 1;
+            if (SCAN2) {
+                if (lane_ == src) {  // the request, for the whole warp to read
+                    ScanJob& J = W2.job;
+                    J.R = f.t1; J.pruned = f.pruned; J.sibling = f.sibling; J.failed0 = f.failedPasses;
+                    J.best = f.bestLKdiff; J.lastLK0 = f.lastLK; J.removedBLen = f.removedBLen;
+                    J.isRemovedTip = f.isRemovedTip;
+                    J.remK = f.removed.k; J.remP = f.removed.p;
+                    // deep per-depth state lives in the unused part of the DFS stack; the phase-2 queue grows down from the top of the key scratch
+                    J.gpath = reinterpret_cast<PathE2*>(stack + f.spN);
+                    J.pathCap = int((size_t)(stackCap - f.spN) * sizeof(StackE) / sizeof(PathE2));
+                    J.qTop = s.key + s.capK;
+                    J.qCap = int(s.capK - s.topK) - 8;
+                }
+                __syncwarp();
+                warp_scan_job2(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st);
+                if (lane_ == src) {
+                    const ScanJob& J = W2.job;
+                    f.bestLKdiff = J.bestOut;
+                    f.phase1 += J.phase1;
+                    f.qN = J.qN;
+                    f.scanNewBest = J.newBest;
+                    if (J.err) s.err = J.err;
+                }
+                __syncwarp();
+            } else warp_scan_job(src, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags, st);
+        }
+        STAT_T(5);
+        if (__all_sync(0xffffffffu, stage == 3)) break;
+    }
+#undef STAT_T
+#undef STAT_N
 }
 
 }  // namespace maple

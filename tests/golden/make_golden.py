@@ -50,6 +50,11 @@ CONFIGS = {
     "ay_unrest_1000": (EX + "sameRef_AY.4.2.2.maple.gz", 1000, ["--model", "UNREST", "--rateVariation"], 40),
     "ay_unrest_deep_200": (EX + "sameRef_AY.4.2.2.maple.gz", 200,
                            ["--model", "UNREST", "--deeperSearchForLongBranches"], 100),
+    # alignments written by the bench's own generator (maple_b200/synthetic.py: "synthetic:<nSeq>[:rv][:err][:sse]"), so that the
+    # reference pins the device on the kind of data bench.py measures, with and without the error model
+    "syn_unrest_rv_2000": ("synthetic:2000:rv", None, ["--model", "UNREST", "--rateVariation"], 40),
+    "syn_unrest_rv_sse_1500": ("synthetic:1500:rv:err:sse", None,
+                               ["--model", "UNREST", "--rateVariation", "--estimateSiteSpecificErrorRate"], 40),
 }
 
 FUNCS = ["appendProbNode", "mergeVectors", "estimateBranchLengthWithDerivative", "areVectorsDifferent",
@@ -57,6 +62,14 @@ FUNCS = ["appendProbNode", "mergeVectors", "estimateBranchLengthWithDerivative",
 
 
 def truncate_input(path, max_seqs, out):
+    if path.startswith("synthetic:"):  # the bench's generator, seed 1 (the tree it simulates is not used: the reference infers its own)
+        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+        from maple_b200.synthetic import generate, write_maple_file
+        opts = path.split(":")[1:]
+        d = generate(int(opts[0]), rate_variation="rv" in opts, error_model="err" in opts, site_specific_errors="sse" in opts, seed=1,
+                     ml_like_blens=True)
+        write_maple_file(d, out)
+        return out
     op = gzip.open if path.endswith(".gz") else open
     n = -1  # the reference record counts as the first '>'
     with op(path, "rt") as f, open(out, "w") as g:

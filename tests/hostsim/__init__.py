@@ -75,3 +75,59 @@ class KernelSourceOnHost(Oracle):
         out = np.zeros(len(nodes), dtype=SEARCH_RESULT_DTYPE)
         self.L.hs_search_batch_fsm(self.mp, C.addressof(t), C.addressof(sp), len(nodes), _p(nodes), int(scratch_keys), _p(out))
         return out
+
+
+# ---- the warp-level code with its 32 lanes emulated (hostwarp.cpp, shim_warp/cuda_runtime.h)
+WARP_LIB = os.path.join(HERE, "libhostwarp.so")
+WARP_SOURCES = [os.path.join(HERE, "hostwarp.cpp"), os.path.join(HERE, "shim_warp", "cuda_runtime.h")] + [
+    os.path.join(CSRC, f) for f in ("glist.cuh", "likelihood.cuh", "search.cuh", "search_fsm.cuh", "scan2.cuh")]
+_warp_lib = None
+
+
+def build_warp(force: bool = False) -> str:
+    if force or not os.path.isfile(WARP_LIB) or any(os.path.getmtime(s) > os.path.getmtime(WARP_LIB) for s in WARP_SOURCES):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                               "-I", os.path.join(HERE, "shim_warp"), "-I", CSRC, WARP_SOURCES[0], "-o", WARP_LIB])
+    return WARP_LIB
+
+
+def warp_lib():
+    global _warp_lib
+    if _warp_lib is None:
+        L = C.CDLL(build_warp())
+        L.hw_search_batch.restype = C.c_int
+        L.hw_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.hw_scan_append.restype = C.c_double
+        L.hw_scan_append.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        _warp_lib = L
+    return _warp_lib
+
+
+class WarpKernelOnHost(Oracle):
+    """The body of k_spr_search_fsm (state machines + warp-cooperative subtree scans) run on the host, lanes emulated."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.W = warp_lib()
+
+    def search_batch_warp(self, tree: dict, lists, params: dict, nodes, scan_form: int = 2, scan_min_size: int = 8, lanes_per_warp: int = 3,
+                          pool_bytes: int = 10240, scan_flags: int = 0, scratch_keys: int = 8192, stats=None):
+        """scan_form: 0 no scans, 1 first form (search_fsm.cuh: warp_scan_job), 2 second form (scan2.cuh: warp_scan_job2)."""
+        t, keep = self._tree_struct(tree, lists)
+        sp = OrSearchParams()
+        for k, v in params.items():
+            setattr(sp, k, v)
+        nodes = np.ascontiguousarray(nodes, np.int32)
+        out = np.zeros(len(nodes), dtype=SEARCH_RESULT_DTYPE)
+        npay = np.ascontiguousarray(lists.npay, np.int32)
+        rc = self.W.hw_search_batch(self.mp, C.addressof(t), C.addressof(sp), len(nodes), _p(nodes), int(scratch_keys), _p(npay), int(scan_form),
+                                    int(scan_min_size), int(lanes_per_warp), int(pool_bytes), int(scan_flags), _p(out), _p(stats))
+        if rc != 0:
+            raise RuntimeError("hw_search_batch: scan form %d not available for this tree" % scan_form)
+        return out
+
+    def scan_append(self, P, C_, isTipC, bLen):
+        """appendProbNode through the scan-format copies of both lists (scan2.cuh)."""
+        a, b = self._one(P), self._one(C_)
+        return self.W.hw_scan_append(self.mp, _p(a.key), _p(a.pay), int(a.nkeys[0]), _p(b.key), _p(b.pay), int(bool(isTipC)), float(bLen))

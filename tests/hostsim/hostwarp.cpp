@@ -1,0 +1,136 @@
+// TEST INFRASTRUCTURE: the WARP-level device code of the search kernel -- fsm_warp_loop, i.e. the whole body of
+// k_spr_search_fsm with its subtree scans (warp_scan_job of search_fsm.cuh, warp_scan_job2 of scan2.cuh) -- compiled for the host
+// behind shim_warp/cuda_runtime.h, which emulates the 32 lanes of a warp as coroutines that meet at the *_sync intrinsics.
+// The driver below does on the host what maple_tree_bind, k_scan_prepare / k_scan_count / k_scan_build / k_scan_nsa and the
+// kernel's prologue do on the device, with the same device functions.  Never loaded by anything under maple_b200/.
+#include "cuda_runtime.h"
+
+#include "search_fsm.cuh"
+
+#include <vector>
+
+using namespace maple;
+
+struct OrTree {  // oracle/oracle.py: OrTree
+    int32_t nNodes, root;
+    const int32_t *up, *child0, *child1;
+    const double* dist;
+    const uint8_t* isTip;
+    const int32_t *mutStart, *mut;
+    const uint32_t* key;
+    const double* pay;
+    const int64_t *keyStart, *payStart;
+    const int32_t* nkeys;
+};
+
+extern "C" {
+
+// scanForm: 0 = no warp scans, 1 = first form (warp_scan_job), 2 = second form (warp_scan_job2).
+// stats: optional 32 counters (as maple_search_stats).  Returns 0, or -1 if the second form is not available for this tree.
+int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, int64_t n, const int32_t* nodes, int64_t scratchKeys,
+                    const int32_t* npay, int32_t scanForm, int32_t scanMinSize, int32_t lanesPerWarp, int32_t poolBytes, int32_t scanFlags,
+                    SearchResult* out, unsigned long long* stats) {
+    DevTree T;
+    memset(&T, 0, sizeof T);
+    T.nNodes = t->nNodes; T.root = t->root;
+    T.up = t->up; T.child0 = t->child0; T.child1 = t->child1; T.dist = t->dist; T.isTip = t->isTip;
+    T.mutStart = t->mutStart; T.mut = t->mut;
+    T.key = t->key; T.pay = t->pay; T.keyStart = t->keyStart; T.payStart = t->payStart; T.nkeys = t->nkeys;
+    T.npay = npay;
+    const size_t N = (size_t)t->nNodes;
+    // what maple_tree_bind derives
+    std::vector<int32_t> order(N, -1), pre(N, -1), size(N, 1), depth(N, 0), st{t->root};
+    std::vector<uint8_t> mutBelow(N, 0);
+    size_t cnt = 0;
+    int height = 0;
+    while (!st.empty()) {
+        const int v = st.back();
+        st.pop_back();
+        pre[v] = (int32_t)cnt;
+        order[cnt++] = v;
+        if (depth[v] > height) height = depth[v];
+        if (t->child0[v] >= 0) {
+            depth[t->child0[v]] = depth[t->child1[v]] = depth[v] + 1;
+            st.push_back(t->child0[v]);
+            st.push_back(t->child1[v]);
+        }
+    }
+    for (size_t i = cnt; i-- > 1;) {
+        const int v = order[i], p = t->up[v];
+        size[p] += size[v];
+        if (mutBelow[v] || (t->mutStart && t->mutStart[v + 1] > t->mutStart[v])) mutBelow[p] = 1;
+    }
+    T.order = order.data(); T.pre = pre.data(); T.size = size.data(); T.depth = depth.data(); T.mutBelow = mutBelow.data();
+    std::vector<ScanNode> scan(N);
+    std::vector<ScanRec> recs(N);
+    std::vector<uint32_t> units(N), offs(N);
+    std::vector<uint4> arena;
+    if (scanForm == 1) {
+        T.scan = scan.data();
+        for (size_t i = 0; i < N; i++) scan[i] = make_scan_node(T, sp->effectivelyNon0BLen, (int)i);
+    } else if (scanForm == 2) {
+        if (height >= 65535) return -1;
+        uint64_t tot = 0;
+        for (size_t i = 0; i < N; i++) {
+            units[i] = scan_count_units(T, (int)i);
+            const uint64_t u = (units[i] & 0xffffu) + (units[i] >> 16);
+            if (u == 0) { offs[i] = ~0u; continue; }
+            offs[i] = (uint32_t)tot;
+            tot += u;
+        }
+        arena.assign(tot + 4, uint4{0, 0, 0, 0});
+        T.scanOff = offs.data();
+        for (size_t i = 0; i < N; i++) recs[i] = scan_build_rec(*m, T, sp->effectivelyNon0BLen, (int)i, units[i], arena.data());
+        for (size_t i = 0; i < N; i++) scan_fill_nsa(T, recs.data(), (int)i);
+        T.scan2 = recs.data();
+        T.scanArena = arena.data();
+    }
+    // what maple_spr_search_batch sizes
+    const unsigned capK = ((unsigned)scratchKeys + 3u) & ~3u, capP = 2 * capK + 6 * 1024, capA = capK / 4 > 2048 ? capK / 4 : 2048;
+    const int stackCap = (2 * height + 32 + 63) & ~63;
+    if (lanesPerWarp < 1) lanesPerWarp = 1;
+    if (lanesPerWarp > 32) lanesPerWarp = 32;
+    std::vector<uint32_t> key((size_t)lanesPerWarp * capK + 64);
+    std::vector<double> pay((size_t)lanesPerWarp * capP + 64), ais((size_t)lanesPerWarp * capA);
+    std::vector<StackE> stack((size_t)lanesPerWarp * stackCap);
+    const size_t fixed = scanForm == 2 ? sizeof(Scan2Smem) : sizeof(ScanSmem);
+    std::vector<uint4> smem((fixed + (size_t)poolBytes + 64) / 16);
+    ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data());
+    Scan2Smem& W2 = *reinterpret_cast<Scan2Smem*>(smem.data());
+    unsigned long long counter = 0;
+    unsigned long long wst[kNumSearchStats] = {0};
+    hostwarp::run_warp([&]() {
+        const int lane = int(threadIdx.x & 31);
+        const size_t tid = (size_t)(lane < lanesPerWarp ? lane : 0);
+        ScratchD s;
+        s.key = key.data() + tid * capK;
+        s.pay = pay.data() + tid * capP;
+        s.ais = ais.data() + tid * capA;
+        s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
+        StackE* stk = stack.data() + tid * (size_t)stackCap;
+        uint32_t parity = 0;
+        if (scanForm == 2)
+            fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity);
+        else
+            fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
+                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity);
+    });
+    if (stats)
+        for (int i = 0; i < kNumSearchStats; i++) stats[i] += wst[i];
+    return 0;
+}
+
+// appendProbNode through the scan-format copies (scan2.cuh: scan_build_p, scan_build_c, scan_walk), one pair.
+// Returns NaN if the removed-side copy does not fit its shared-memory slots.
+double hw_scan_append(const DevModel* m, const uint32_t* kP, const double* pP, int nkP, const uint32_t* kC, const double* pC, int isTipC,
+                      double bLen) {
+    const int capE = 1 << 16;
+    std::vector<uint2> eP(nkP + 2), eC(capE);
+    std::vector<double> yP(8 * (size_t)nkP + 8), yC(8 * (size_t)capE);
+    scan_build_p(*m, kP, pP, nkP, eP.data(), yP.data());
+    if (scan_build_c(*m, kC, pC, bLen, eC.data(), capE, yC.data(), 8 * capE) < 0) return NAN;
+    return scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen);
+}
+
+}  // extern "C"

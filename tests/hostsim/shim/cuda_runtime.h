@@ -32,6 +32,11 @@ static inline double max(double a, double b) { return std::fmax(a, b); }
 // on the host (the state machine is driven with scanMinSize = 0, i.e. search variant 2); they only let the file compile so that
 // its lane-level state machine (fsm_step, fsm_finish) can run.
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline int __all_sync(unsigned, int p) { return p != 0; }
+#define __restrict__
 struct HostIdx { unsigned x = 0, y = 0, z = 0; };
 static const HostIdx threadIdx, blockIdx;
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }

@@ -33,7 +33,7 @@ def _compare(rec, ref, nodes):
         assert np.max(np.abs(a[fin] - b[fin]), initial=0.0) <= 1e-9, f
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("name", golden_names())
 def test_search_vs_reference_goldens(name, variant):
     from maple_b200.engine import MapleEngine
@@ -61,7 +61,7 @@ def test_search_vs_reference_goldens(name, variant):
     compare_with_reference_searches(g, nodes, rec, lazy, ref)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("rv,err,strict,ml", [(False, False, True, False), (True, False, False, True), (True, True, False, False)])
 def test_search_vs_oracle_synthetic(rv, err, strict, ml, variant):
     import math

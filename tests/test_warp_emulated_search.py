@@ -1,0 +1,113 @@
+"""The body of the default search kernel (k_spr_search_fsm: per-lane state machines + warp-cooperative subtree scans) run on the
+host with its 32 lanes emulated as coroutines that meet at the *_sync intrinsics (tests/hostsim/hostwarp.cpp,
+shim_warp/cuda_runtime.h).  Both forms of the scans -- warp_scan_job (search_fsm.cuh) and warp_scan_job2 (scan2.cuh: scan-format
+lists, prefix-form replay) -- must give the records of the straight-line search of the same source, bit for bit (same libm),
+on every fixture and on the rounds recorded under the other stop rules; and they must equal the reference's own record of every
+search whose outcome does not depend on the order in which the reference fills probVectTotUp of zero-length children of the root.
+Shapes the default sizing does not produce are forced: tiny pools (windows cut by capacity, windows scored from the arena lists),
+one and many searches per warp, every subtree scanned (scan_min_size 1)."""
+import numpy as np
+import pytest
+
+from golden_io import golden_names, load_golden
+from hostsim import KernelSourceOnHost, WarpKernelOnHost
+from maple_b200.model import MapleModel
+from oracle.oracle import Oracle
+from test_kernel_source_host import _prefilled_lists
+from test_search_rounds_golden import ROUNDS, round_shim
+from tree_fixture import compare_with_reference_searches, search_params, searched_nodes, tree_arrays, tree_lists
+
+FIELDS = ("status", "placement", "bestNode", "phase1", "bLenTop", "bLenBottom", "bLenAppend", "bestCurrentLK", "bestScore", "improvement")
+
+
+def _same(a, b):
+    for f in FIELDS:
+        x, y = a[f], b[f]
+        assert np.array_equal(x, y) or np.all((x == y) | ((x != x) & (y != y))), f
+
+
+@pytest.mark.parametrize("form", [1, 2])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "ay_unrest_1000"])
+def test_warp_body_equals_straight_line_search(name, form):
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs, hw = KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
+    lists = _prefilled_lists(g, Oracle(model))
+    want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
+    st = np.zeros(32, np.uint64)
+    got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=form, stats=st)
+    _same(got, want)
+    if not g["env"]["deeperSearchForLongBranches"]:  # (that option keeps every node on the lane path)
+        assert st[17] > 0 and st[21] > 0  # scan jobs ran and counted candidates
+
+
+@pytest.mark.parametrize("rnd", ROUNDS)
+@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_rv_sse", "ay_unrest_deep_200"])
+def test_second_form_on_the_other_rounds(name, rnd):
+    g, s = round_shim(name, rnd)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    orc, hs, hw = Oracle(model), KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(s), np.array(searched_nodes(s), np.int32)
+    lists = _prefilled_lists(s, orc)
+    want = hs.search_batch(ta, lists, search_params(s), nodes, scratch_keys=1 << 17)
+    got = hw.search_batch_warp(ta, lists, search_params(s), nodes, scan_form=2, scratch_keys=1 << 15)
+    _same(got, want)
+    ref = orc.search_batch(ta, lists, search_params(s), nodes, lazy_mode=1)
+    lazy = orc.search_batch(ta, tree_lists(s), search_params(s), nodes, lazy_mode=0)
+    compare_with_reference_searches(s, nodes, got, lazy, ref)
+
+
+@pytest.mark.parametrize("shape", [dict(pool_bytes=1024, lanes_per_warp=1), dict(pool_bytes=256, lanes_per_warp=32),
+                                   dict(pool_bytes=4096, scan_min_size=1, lanes_per_warp=7), dict(pool_bytes=0, lanes_per_warp=2),
+                                   dict(scan_flags=2, lanes_per_warp=4)])
+@pytest.mark.parametrize("name", ["ex_unrest_rv", "ay_unrest_300"])
+def test_second_form_forced_shapes(name, shape):
+    """Pools of 256 - 4096 bytes cut most windows short (a 256-byte pool holds about one list; with none at all every window is
+    scored from the arena lists); scan_flags=2 replays every window node by node, the path a window takes when the stop rule
+    prunes a node that holds a new best; the records must not change."""
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs, hw = KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
+    lists = _prefilled_lists(g, Oracle(model))
+    want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
+    _same(hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, **shape), want)
+
+
+def test_second_form_big_fixture_deep_round():
+    """1 000 sequences, deep stop rules: long scan jobs, deep paths."""
+    g, s = round_shim("ay_unrest_1000", "frozen_deep")
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    orc, hs, hw = Oracle(model), KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(s), np.array(searched_nodes(s), np.int32)[::6]
+    lists = _prefilled_lists(s, orc)
+    want = hs.search_batch(ta, lists, search_params(s), nodes, scratch_keys=1 << 17)
+    st = np.zeros(32, np.uint64)
+    got = hw.search_batch_warp(ta, lists, search_params(s), nodes, scan_form=2, scratch_keys=1 << 15, stats=st)
+    _same(got, want)
+    assert st[21] > 10000
+
+
+@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_err", "ex_unrest_rv_sse", "ay_unrest_300"])
+def test_scan_format_append_equals_dev_append(name):
+    """appendProbNode through the scan-format copies (precomputed Q*rate, precomputed removed-side factors) against dev_append of
+    the same source: recorded calls and random pairs of the fixture's lists with branch lengths from the corners; bit for bit."""
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs, hw = KernelSourceOnHost(model), WarpKernelOnHost(model)
+    L = g["lists"]
+    for c in g["calls"]["appendProbNode"]:
+        a = hw.scan_append(L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"])
+        b = hs.append(L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"])
+        assert a == b, c
+        assert a == c["out"] or abs(a - c["out"]) <= 1e-9
+    rng = np.random.default_rng(11)
+    lower = [i for i in set(g["tree"]["probVect"]) if i is not None]
+    cand = [i for i in set(g["tree"]["probVectTotUp"]) if i is not None]
+    blens = [0.0, 1e-9, 0.3 / model.lRef, 1.0 / model.lRef, 3.3 / model.lRef, 0.1]
+    for _ in range(1500):
+        P, Cc = L[cand[rng.integers(len(cand))]], L[lower[rng.integers(len(lower))]]
+        tip, bl = bool(rng.integers(2)), blens[rng.integers(len(blens))]
+        a, b = hw.scan_append(P, Cc, tip, bl), hs.append(P, Cc, tip, bl)
+        assert a == b, (P, Cc, tip, bl, a, b)

@@ -15,7 +15,7 @@ from tree_fixture import compare_with_reference_searches, search_params, searche
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("variant", [0, 2, 4])
 @pytest.mark.parametrize("rnd", ROUNDS)
 @pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_rv_sse", "ay_unrest_300", "ay_unrest_deep_200"])
 def test_device_reproduces_the_reference_round(name, rnd, variant):

@@ -30,7 +30,7 @@ def _tree(g, s):
     return model, eng, tree, ta, lists
 
 
-@pytest.mark.parametrize("variant,rnd", [(0, "main"), (1, "main"), (2, "main"), (3, "main"), (0, "frozen_deep"), (0, "perturbed_deep"),
+@pytest.mark.parametrize("variant,rnd", [(0, "main"), (1, "main"), (2, "main"), (3, "main"), (4, "main"), (4, "frozen_deep"), (0, "frozen_deep"), (0, "perturbed_deep"),
                                          (0, "perturbed_fast")])
 def test_searches_on_the_big_tree(variant, rnd):
     from oracle.oracle import Oracle
