@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
                                                                    unsigned capK, unsigned capP, unsigned capA, int stackCap,
                                                                    unsigned long long* counter, long long* outCycles, int scanMinSize,
                                                                    int scanFlags, int poolBytes, unsigned long long* stats,
-                                                                   const unsigned long long* nDev, const int32_t* outIndex, int lanesPerWarp) {
+                                                                   const unsigned long long* nDev, const int32_t* outIndex, int lanesPerWarp,
+                                                                   const __grid_constant__ BigScratch big) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
     StackE* stack = scrStack + tid * (size_t)stackCap;
     fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
-                         lanesPerWarp, W, W2, mbarParity);
+                         lanesPerWarp, W, W2, mbarParity, big);
     if (stats) {
         __syncthreads();
         for (int i = threadIdx.x; i < kNumSearchStats; i += blockDim.x) {
@@ -926,7 +927,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
-                               const unsigned long long*, const int32_t*, int);
+                               const unsigned long long*, const int32_t*, int, const BigScratch);
     // Register budget = resident warps.  __launch_bounds__(64, 7) makes ptxas settle on 128 registers with few spills, which lets
     // 8 CTAs (16 warps) share an SM: 3.1 s for the deep round at 100 k sequences against 4.4 s for the 168-register build
     // (12 warps) on the same box.  MAPLE_FSM_MINB=6 selects the latter for A/B runs.  (Register allocation of this kernel is
@@ -982,6 +983,37 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     double* scrAis = (double*)(base + owners * capP * 8);
     StackE* scrStack = (StackE*)(base + owners * (capP + capA) * 8);
     uint32_t* scrKey = (uint32_t*)(base + owners * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+    // A few slots with 8x the scratch, shared by the launch: a search that exhausts its lane's scratch takes one and starts over
+    // inside the same launch (fsm_warp_loop), so the rare long search does not cost a serial launch of its own afterwards.
+    constexpr int kBigSlots = kSearchThreads;  // 64
+    BigScratch big{};
+    const int retryCap = (int)(n < 65536 ? n : 65536);
+    int32_t *retryNodes = nullptr, *retryIdx = nullptr;
+    if (ctx->searchVariant != 1) {
+        const unsigned capK2 = capK * 8, capP2 = 2 * capK2 + 6 * 1024, capA2 = capA * 8;
+        const size_t per2 = (size_t)capK2 * 4 + (size_t)capP2 * 8 + (size_t)capA2 * 8 + (size_t)stackCap * sizeof(StackE);
+        const size_t need2 = per2 * kBigSlots + 256 + (size_t)65536 * 8 + 64;
+        if (need2 > ctx->retryScratchBytes) {
+            cudaFree(ctx->retryScratch);
+            ctx->retryScratch = nullptr;
+            ctx->retryScratchBytes = 0;
+            CK(cudaMalloc(&ctx->retryScratch, need2));
+            ctx->retryScratchBytes = need2;
+        }
+        if (!ctx->retryCounters) CK(cudaMalloc((void**)&ctx->retryCounters, 4 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->retryCounters, 0, 4 * sizeof(unsigned long long), (cudaStream_t)stream));
+        char* b2 = (char*)ctx->retryScratch;
+        retryNodes = (int32_t*)b2;
+        retryIdx = retryNodes + 65536;
+        char* s2 = b2 + (size_t)65536 * 8 + 64;
+        big.pay = (double*)s2;
+        big.ais = (double*)(s2 + (size_t)kBigSlots * capP2 * 8);
+        big.stack = (StackE*)(s2 + (size_t)kBigSlots * (capP2 + capA2) * 8);
+        big.key = (uint32_t*)(s2 + (size_t)kBigSlots * ((size_t)(capP2 + capA2) * 8 + (size_t)stackCap * sizeof(StackE)));
+        big.capK = capK2; big.capP = capP2; big.capA = capA2;
+        big.nSlots = kBigSlots;
+        big.counter = ctx->retryCounters + 2;
+    }
     if (scan2) {
         k_scan_build<<<(T.nNodes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->model, T, sp.effectivelyNon0BLen, ctx->scanUnits, ctx->scanArena,
                                                                               ctx->scanRecs);
@@ -1001,39 +1033,19 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw);
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big);
     ctx->launches++;
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
-        // second chance on the device for searches that exhausted their scratch: 128 lanes with 8x the entries
-        const int retryCap = (int)(n < 65536 ? n : 65536);
-        const int lanes2 = 2 * kSearchThreads;
-        const unsigned capK2 = capK * 8, capP2 = 2 * capK2 + 6 * 1024, capA2 = capA * 8;
-        const size_t per2 = (size_t)capK2 * 4 + (size_t)capP2 * 8 + (size_t)capA2 * 8 + (size_t)stackCap * sizeof(StackE);
-        const size_t need2 = per2 * lanes2 + 256 + (size_t)retryCap * 8 + 64;
-        if (need2 > ctx->retryScratchBytes) {
-            cudaFree(ctx->retryScratch);
-            ctx->retryScratch = nullptr;
-            ctx->retryScratchBytes = 0;
-            CK(cudaMalloc(&ctx->retryScratch, need2));
-            ctx->retryScratchBytes = need2;
-        }
-        if (!ctx->retryCounters) CK(cudaMalloc((void**)&ctx->retryCounters, 2 * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(ctx->retryCounters, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
-        char* b2 = (char*)ctx->retryScratch;
-        int32_t* retryNodes = (int32_t*)b2;
-        int32_t* retryIdx = retryNodes + retryCap;
-        char* s2 = b2 + (((size_t)retryCap * 8 + 63) & ~size_t(63));
-        double* pay2 = (double*)s2;
-        double* ais2 = (double*)(s2 + (size_t)lanes2 * capP2 * 8);
-        StackE* stack2 = (StackE*)(s2 + (size_t)lanes2 * (capP2 + capA2) * 8);
-        uint32_t* key2 = (uint32_t*)(s2 + (size_t)lanes2 * ((size_t)(capP2 + capA2) * 8 + (size_t)stackCap * sizeof(StackE)));
+        // safety net: searches that found no large slot free are collected and re-run by one CTA that uses the same slots (free
+        // again by then).  With none to re-run the two launches return at once.
         k_collect_overflow<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, (const SearchResult*)out, nodes, retryNodes, retryIdx,
                                                                                          ctx->retryCounters, retryCap);
-        fsmKernel<<<lanes2 / kSearchThreads, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(
-            ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, key2, pay2, ais2, stack2, capK2, capP2, capA2, stackCap,
-            ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
+        BigScratch none{};
+        fsmKernel<<<kBigSlots / kSearchThreads, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(
+            ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, big.key, big.pay, big.ais, big.stack, big.capK, big.capP, big.capA,
+            stackCap, ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
-            ctx->retryCounters, retryIdx, 32);
+            ctx->retryCounters, retryIdx, 32, none);
         ctx->launches += 2;
     }
     CK(cudaGetLastError());

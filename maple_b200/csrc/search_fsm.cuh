@@ -952,11 +952,27 @@ __device__ void fsm_finish(const Fsm& f, const DevTree& t, const SearchParams& s
 // then the warp runs each kind of co-walk once for all lanes that requested it, then the pending subtree scans one after the
 // other with the whole warp.  Lanes pull searches from the global counter.  SCAN2 selects the second form of the scans
 // (scan2.cuh).  A function of its own so that tests/hostsim can run the very same loop with the lanes emulated.
+// A few large scratch slots shared by the whole launch: a search that exhausts its lane's scratch takes one (while there are
+// any) and starts over inside the same launch, concurrently with everybody else, instead of waiting for a second launch.
+struct BigScratch {
+    uint32_t* key;
+    double* pay;
+    double* ais;
+    StackE* stack;
+    unsigned capK, capP, capA;
+    int nSlots;
+    unsigned long long* counter;  // slots handed out so far
+};
+
 template <bool SCAN2>
 __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree& T, const SearchParams& sp, int64_t n, const int32_t* __restrict__ nodes,
                                               SearchResult* __restrict__ out, ScratchD s, StackE* stack, int stackCap, unsigned long long* counter,
                                               long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
-                                              const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity) {
+                                              const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity,
+                                              const BigScratch& big) {
+    const ScratchD sOwn = s;
+    StackE* const stackOwn = stack;
+    bool usingBig = false;
     const int lane_ = int(threadIdx.x & 31);
     const bool l0 = lane_ == 0;
     const bool stats = st != nullptr;
@@ -1000,6 +1016,28 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
         }
         while (stage != 3 && (stage == 0 || f.op == OP_DONE)) {
             if (stage != 0) {  // a search (or its pre-check) just ended
+                if (stage == 2 && f.rc == 3 && !usingBig && big.nSlots > 0) {  // scratch exhausted: once more with a large slot
+                    const unsigned long long slot = atomicAdd(big.counter, 1ULL);
+                    if (slot < (unsigned long long)big.nSlots) {
+                        usingBig = true;
+                        s.key = big.key + slot * big.capK;
+                        s.pay = big.pay + slot * big.capP;
+                        s.ais = big.ais + slot * big.capA;
+                        s.capK = big.capK; s.capP = big.capP; s.capA = big.capA; s.topK = s.topP = 0; s.err = 0;
+                        stack = big.stack + slot * (size_t)stackCap;
+                        f.pc = 0; f.op = OP_NONE;
+                        f.bestLKdiff = bestCurrentLK;
+                        f.removedBLen = T.dist[node];
+                        f.phase1 = 0; f.rc = 0;
+                        fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
+                        continue;
+                    }
+                }
+                if (usingBig) {
+                    usingBig = false;
+                    s = sOwn;
+                    stack = stackOwn;
+                }
                 if (stage == 2) fsm_finish(f, T, sp, node, bestCurrentLK, r);
                 else r.status = f.rc;
                 out[outIndex ? outIndex[i] : i] = r;

@@ -453,17 +453,43 @@ class DeviceTree:
         capi.check(eng.ctx, rc, "maple_tree_bind")
         self._bound_epoch = A.epoch
 
-    def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0, cycles=None):
-        """Run the searches of the listed nodes; returns a device tensor of raw records [n, 64 bytes] viewed as uint8
-        and a helper to read it as a numpy record array."""
+    def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0, cycles=None,
+                   schedule: bool = True):
+        """Run the searches of the listed nodes; returns a device tensor of raw records [n, 64 bytes] viewed as uint8 (in the
+        order of `nodes`) -- search_records() reads it as a numpy record array.
+
+        schedule: searches differ by orders of magnitude in length and the kernel's lanes pull them from the list in order, so
+        the list is handed over longest-first, using the SM cycles each node's search took the last time it ran on this tree
+        (kept on the device in self.search_cost; nodes never searched before go first).  The tree hardly changes between the
+        rounds of a run, so this is the LPT rule with last round's lengths.  Results do not depend on the order."""
         eng, dev = self.eng, self.eng.device
         if getattr(self, "_bound_epoch", None) != self.arena.epoch:
             self.prepare_search()  # never bound, or the arena's tables moved since (temporary lists added / released)
         nodes = torch.as_tensor(nodes, dtype=torch.int32, device=dev).contiguous()
-        out = torch.zeros((nodes.numel(), 64), dtype=torch.uint8, device=dev)
-        rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), nodes.numel(), _dp(nodes), _dp(out), int(scratch_keys),
-                                            int(max_concurrent), _dp(cycles), eng._stream())
+        n = nodes.numel()
+        cost = getattr(self, "search_cost", None)
+        if cost is None or cost.numel() != self.n:
+            cost = self.search_cost = torch.full((self.n,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+        perm = None
+        if schedule and n > 1:
+            perm = torch.argsort(cost[nodes.long()], descending=True, stable=True)
+            run_nodes = nodes[perm].contiguous()
+        else:
+            run_nodes = nodes
+        out = torch.zeros((n, 64), dtype=torch.uint8, device=dev)
+        cyc = torch.zeros(n, dtype=torch.int64, device=dev)
+        rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), n, _dp(run_nodes), _dp(out), int(scratch_keys),
+                                            int(max_concurrent), _dp(cyc), eng._stream())
         capi.check(eng.ctx, rc, "maple_spr_search_batch")
+        cost[run_nodes.long()] = cyc
+        if perm is not None:
+            back = torch.empty_like(out)
+            back[perm] = out
+            out = back
+            if cycles is not None:
+                cycles[perm] = cyc
+        elif cycles is not None:
+            cycles.copy_(cyc)
         return out
 
     # ------------------------------------------------------------------ findBestParentForNewSample for a batch (:7912, :11190-11287)

@@ -44,6 +44,7 @@ for variant in variants:
     if variant != 1:
         S = eng.search_stats(False, True)
         wc = float(sum(S[0:6])) or 1.0
+        print("   total warp time in the loop: %.1f warp-seconds @1.9GHz = %.0f%% of 2368 warps x %.1f ms" % (wc / 1.9e9, 100 * wc / 1.9e9 / (2368 * ms / 1e3), ms), flush=True)
         print("   warp cycles: control %.1f%% append %.1f%% merge %.1f%% blen %.1f%% differ %.1f%% scan %.1f%% (scan: window+stage %.1f%% score %.1f%% replay %.1f%%) | "
               "iterations %.3g; lanes/op-iteration: append %.1f merge %.1f blen %.1f differ %.1f | op counts a %.3g m %.3g b %.3g d %.3g" % (
                   100 * S[0] / wc, 100 * S[1] / wc, 100 * S[2] / wc, 100 * S[3] / wc, 100 * S[4] / wc, 100 * S[5] / wc, 100 * S[23] / wc, 100 * S[6] / wc, 100 * S[7] / wc,

@@ -29,7 +29,8 @@ extern "C" {
 // stats: optional 32 counters (as maple_search_stats).  Returns 0, or -1 if the second form is not available for this tree.
 int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, int64_t n, const int32_t* nodes, int64_t scratchKeys,
                     const int32_t* npay, int32_t scanForm, int32_t scanMinSize, int32_t lanesPerWarp, int32_t poolBytes, int32_t scanFlags,
-                    SearchResult* out, unsigned long long* stats) {
+                    int32_t bigSlots /* large scratch slots (8x) for searches that exhaust theirs, 0 = none */, SearchResult* out,
+                    unsigned long long* stats) {
     DevTree T;
     memset(&T, 0, sizeof T);
     T.nNodes = t->nNodes; T.root = t->root;
@@ -97,8 +98,16 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
     std::vector<uint4> smem((fixed + (size_t)poolBytes + 64) / 16);
     ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data());
     Scan2Smem& W2 = *reinterpret_cast<Scan2Smem*>(smem.data());
-    unsigned long long counter = 0;
+    unsigned long long counter = 0, bigCounter = 0;
     unsigned long long wst[kNumSearchStats] = {0};
+    BigScratch big;
+    memset(&big, 0, sizeof big);
+    big.capK = capK * 8; big.capP = 2 * big.capK + 6 * 1024; big.capA = capA * 8;
+    std::vector<uint32_t> bkey((size_t)bigSlots * big.capK + 64);
+    std::vector<double> bpay((size_t)bigSlots * big.capP + 64), bais((size_t)bigSlots * big.capA + 1);
+    std::vector<StackE> bstack((size_t)bigSlots * stackCap + 1);
+    big.key = bkey.data(); big.pay = bpay.data(); big.ais = bais.data(); big.stack = bstack.data();
+    big.nSlots = bigSlots; big.counter = &bigCounter;
     hostwarp::run_warp([&]() {
         const int lane = int(threadIdx.x & 31);
         const size_t tid = (size_t)(lane < lanesPerWarp ? lane : 0);
@@ -111,13 +120,15 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         uint32_t parity = 0;
         if (scanForm == 2)
             fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
-                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity);
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big);
         else
             fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
-                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity);
+                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big);
     });
-    if (stats)
+    if (stats) {
         for (int i = 0; i < kNumSearchStats; i++) stats[i] += wst[i];
+        stats[31] += bigCounter;  // requests for a large slot
+    }
     return 0;
 }
 

@@ -61,6 +61,13 @@ def _worker(rank, world, port, q):
         raw = torch.from_numpy(np.ascontiguousarray(rec).view(np.uint8).reshape(len(mine), 64).copy())
         allrec = gather_records(raw, len(nodes), rank, world)
         moves = moves_from_records(nodes, allrec)
+        # second round on the same tree: cost-balanced shards from what the first round measured (here the candidate counts)
+        cost = allrec["phase1"].astype(np.float64)
+        mine2 = shard_nodes(nodes, rank, world, cost)
+        rec2 = Oracle(model).search_batch(ta, packed, params, mine2, lazy_mode=1)
+        raw2 = torch.from_numpy(np.ascontiguousarray(rec2).view(np.uint8).reshape(len(mine2), 64).copy())
+        allrec2 = gather_records(raw2, len(nodes), rank, world, cost=cost)
+        assert allrec2.tobytes() == allrec.tobytes()
         q.put((rank, moves, allrec.tobytes()))
     finally:
         dist.destroy_process_group()
@@ -147,6 +154,22 @@ def test_placement_batch_two_ranks_agree_with_one():
     one = Oracle(model).place_batch(ta, packed, pp, pack_lists(samples, model.lRef, model.usingErrorRate))
     assert got[0][1] == got[1][1] == np.ascontiguousarray(one).tobytes()
     assert (one["status"] == 0).sum() > 10 and (one["status"] == 1).sum() > 5 and (one["phase1"][one["status"] == 0] > 0).all()
+
+
+def test_cost_balanced_shards():
+    rng = np.random.default_rng(3)
+    nodes = rng.permutation(1000).astype(np.int32)
+    cost = rng.pareto(1.2, 1000) * 1e6  # heavy tail, like search lengths
+    for world in (1, 2, 4, 8):
+        parts = [shard_nodes(nodes, r, world, cost) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == sorted(nodes.tolist())
+        c = dict(zip(nodes.tolist(), cost.tolist()))
+        sums = [sum(c[int(x)] for x in p) for p in parts]
+        # the single longest search bounds what any deal can do; beyond it the shares are within a few per cent
+        assert max(sums) <= max(cost.max(), 1.02 * sum(sums) / world), (world, sums)
+        for p in parts:  # longest first inside a shard
+            cc = [c[int(x)] for x in p]
+            assert cc == sorted(cc, reverse=True)
 
 
 def test_shard_nodes_is_the_round_robin_partition():

@@ -75,6 +75,25 @@ def test_second_form_forced_shapes(name, shape):
     _same(hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, **shape), want)
 
 
+def test_search_that_exhausts_its_scratch_starts_over_in_a_large_slot():
+    """With 512 entries of scratch per lane many searches of this tree run out; each takes one of the launch's large slots (8x)
+    and starts over inside the same launch.  Records as with ample scratch; with too few slots the rest report status 3."""
+    g = load_golden("ex_unrest")
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs, hw = KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
+    lists = _prefilled_lists(g, Oracle(model))
+    want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
+    st = np.zeros(32, np.uint64)
+    got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, scratch_keys=512, big_slots=256, stats=st, lanes_per_warp=5)
+    assert 0 < st[31] <= 256, st[31]
+    _same(got, want)
+    few = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, scratch_keys=512, big_slots=2, lanes_per_warp=5)
+    over = few["status"] == 3
+    assert over.sum() == st[31] - 2
+    _same(few[~over], want[~over])
+
+
 def test_second_form_big_fixture_deep_round():
     """1 000 sequences, deep stop rules: long scan jobs, deep paths."""
     g, s = round_shim("ay_unrest_1000", "frozen_deep")
