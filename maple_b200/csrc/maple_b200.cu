@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
     StackE* stack = scrStack + tid * (size_t)stackCap;
     fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
-                         lanesPerWarp, W, W2, mbarParity, big);
+                         lanesPerWarp, W, W2, mbarParity, big, int((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5),
+                         nDev ? 0 : int(gridDim.x * (blockDim.x >> 5)));
     if (stats) {
         __syncthreads();
         for (int i = threadIdx.x; i < kNumSearchStats; i += blockDim.x) {
@@ -977,7 +978,10 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         ctx->searchScratchBytes = need;
     }
     if (!ctx->searchCounter) CK(cudaMalloc((void**)&ctx->searchCounter, sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->searchCounter, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    {   // the state-machine kernel hands the first `owners` entries out statically (fsm_warp_loop), the counter serves the rest
+        const unsigned long long first = ctx->searchVariant != 1 ? (unsigned long long)owners : 0ULL;
+        CK(cudaMemcpyAsync(ctx->searchCounter, &first, sizeof first, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    }
     char* base = (char*)ctx->searchScratch;
     double* scrPay = (double*)base;
     double* scrAis = (double*)(base + owners * capP * 8);

@@ -37,9 +37,17 @@ namespace maple {
 //   bits 16-22 candidate side: one-hot of the entry type; removed side: types of the OTHER list this entry is informative
 //              against (append_informative) -- the AND of both is non-zero exactly at the informative segments
 //   bit 31     candidate side: plain reference run (type R, no lengths); removed side: nucleotide with at most one length
+//              -> the factor is the removed side's precomputed [f]
 //   bit 30     candidate side: plain nucleotide (no lengths); removed side: plain reference run (and bLen != 0)
-//   (bits 30/31 are only set without the error model: with it every site takes the general code)
-constexpr uint32_t SA_IDX = 0xffffu, SA_TYPES = 0x7f0000u, SA_FAST_C = 0x80000000u, SA_FAST_P = 0x40000000u;
+//              -> the factor is min(0.25, [g] * bLen) with the candidate side's [g]
+//   bit 29     candidate side: O entry whose probability of the reference nucleotide exceeds 0.02 (the shortcut of :6692);
+//              removed side: any reference run -> the factor is that probability, stored as [a] in front of the entry's payload
+//   bit 28     candidate side: any reference run; removed side: O entry whose probability of ITS reference nucleotide exceeds
+//              0.02 (:6615) -> the factor is that probability, stored as [a] in front of the entry's payload
+//   (bits 30/31 are only set without the error model: with it those sites take the general code; 28/29 hold with it too)
+// An entry with an [f] or [a] slot has it at index-1, so three of the four cases are one load from "payload base - 1".
+constexpr uint32_t SA_IDX = 0xffffu, SA_TYPES = 0x7f0000u, SA_FAST_C = 0x80000000u, SA_FAST_P = 0x40000000u, SA_FAST_PO = 0x20000000u,
+                   SA_FAST_CO = 0x10000000u, SA_FAST = 0xf0000000u;
 
 struct ScanRec {  // one per pre-order position, 32 bytes
     int32_t node;
@@ -63,11 +71,20 @@ __device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const d
     for (int i = 0; i < nk; i++) {
         const uint32_t key = __ldg(k + i);
         const int type = int(key & 7u), nl = int((key >> 3) & 3u), nuc = int((key >> 6) & 3u), end = int(key >> 8);
-        uint32_t aux = uint32_t(np) | (1u << (16 + type));
+        uint32_t aux = 1u << (16 + type);
+        if (type == T_R) aux |= SA_FAST_CO;
         if (!m.U) {
             if (type == T_R && nl == 0) aux |= SA_FAST_C;
             if (type < 4 && nl == 0) aux |= SA_FAST_P;
         }
+        if (type == T_O) {
+            const double a = __ldg(p + ip + nl + nuc);
+            if (a > 0.02) {
+                aux |= SA_FAST_PO;
+                outP[np++] = a;
+            }
+        }
+        aux |= uint32_t(np);
         for (int q = 0; q < nl; q++) outP[np++] = __ldg(p + ip + q);
         ip += nl;
         if (type < 4) {
@@ -95,9 +112,18 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
         uint32_t row = 0;
         for (int t1 = 0; t1 < 7; t1++) row |= uint32_t((INF >> (t1 * 8 + type)) & 1ull) << t1;
         const bool fastNuc = !m.U && type < 4 && nl <= 1;
-        uint32_t aux = (row << 16) | uint32_t(np + (type < 4 ? 1 : 0));
+        uint32_t aux = row << 16;
         if (fastNuc) aux |= SA_FAST_C;
+        if (type == T_R) aux |= SA_FAST_PO;
         if (!m.U && type == T_R && nl == 0 && bLen != 0.0) aux |= SA_FAST_P;
+        if (type == T_O) {
+            const double a = p[ip + nl + nuc];
+            if (a > 0.02) {
+                aux |= SA_FAST_CO;
+                outP[np++] = a;
+            }
+        }
+        aux |= uint32_t(np + (type < 4 ? 1 : 0));
         if (type < 4) {
             const SiteQ q(m, end - 1);
             const double g = q.at(nuc, type);  // mutMatrices[pos][reference nuc][nuc of the entry]
@@ -127,53 +153,69 @@ __device__ __noinline__ double scan_site_general(const DevModel& m, uint32_t k1,
 }
 
 // appendProbNode(candidate list, removed list, isTipC, bLen) over the scan-format copies: the arithmetic and its order are
-// dev_append's (:6505-6785).  pCm1 = removed-side payload base minus one double.
+// dev_append's (:6505-6785).  `mask` = the lanes of the warp that call this together (one candidate each): they meet before
+// every general site so that the long site code runs for all lanes that have one pending, not lane by lane.
+// The segment loop is written without branches around its loads: a precomputed factor is fetched (or 1.0 taken) and multiplied
+// in every iteration -- x * 1.0 == x exactly -- and a cursor that does not advance re-reads its entry.
 __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, const double* pP, const uint2* eC, const double* pC, bool isTipC,
-                                            double bLen) {
+                                            double bLen, unsigned mask) {
     const int lRef = m.lRef;
     const double* pCm1 = pC - 1;
+    const double* pPm1 = pP - 1;
     uint2 a = eP[0], b = eC[0];
     double F = 1.0;
     double Lk = bLen * (-(double)lRef);
     if (m.U && isTipC) Lk += m.totError;
+    bool finished = false, dead = false;
     for (;;) {
         bool general = false;
-        int np;
-        for (;;) {
-            const uint32_t mm = a.y & b.y;
-            const int e1 = int(a.x >> 8), e2 = int(b.x >> 8);
-            np = min(e1, e2);
-            if (mm & (SA_FAST_C | SA_FAST_P | SA_TYPES)) {
-                if (mm & (SA_FAST_C | SA_FAST_P)) {
-                    const double f = (mm & SA_FAST_C) ? pCm1[b.y & SA_IDX] : fmin(0.25, pP[a.y & SA_IDX] * bLen);
-                    F *= f;
-                    if (F <= kMinCarryOver && np != lRef) {  // :6772-6783 (also catches the -1 marker)
-                        if (F < DBL_MIN) return -INFINITY;
-                        Lk += log(F);
-                        F = 1.0;
-                    }
-                } else {
+        int np = 0;
+        if (!finished) {
+            for (;;) {
+                const uint32_t mm = a.y & b.y;
+                const int e1 = int(a.x >> 8), e2 = int(b.x >> 8);
+                np = min(e1, e2);
+                if ((mm & (SA_FAST | SA_TYPES)) && !(mm & SA_FAST)) {  // an informative site without a precomputed factor
                     general = true;
                     break;
                 }
+                // where the factor lies, if there is one: removed side [f]/[a] (bits 31, 28), candidate side [a] (29) or [g] (30)
+                const bool fromC = (mm & (SA_FAST_C | SA_FAST_CO)) != 0;
+                const double* src = fromC ? pCm1 + (b.y & SA_IDX) : ((mm & SA_FAST_PO) ? pPm1 : pP) + (a.y & SA_IDX);
+                double f = 1.0;
+                if (mm & SA_FAST) f = *src;
+                if ((mm & (SA_FAST_C | SA_FAST_CO | SA_FAST_PO | SA_FAST_P)) == SA_FAST_P) f = fmin(0.25, f * bLen);
+                F *= f;
+                if (np == lRef) { finished = true; break; }
+                if (F <= kMinCarryOver) {  // :6772-6783 (also catches the -1 marker of an impossible site)
+                    if (F < DBL_MIN) { dead = finished = true; break; }
+                    Lk += log(F);
+                    F = 1.0;
+                }
+                eP += (e1 == np);
+                eC += (e2 == np);
+                a = *eP;
+                b = *eC;
             }
-            if (np == lRef) break;
-            if (e1 == np) a = *++eP;
-            if (e2 == np) b = *++eC;
         }
-        if (!general) break;
-        F = scan_site_general(m, a.x, pP + (a.y & SA_IDX), b.x, pC + (b.y & SA_IDX), np - 1, bLen, isTipC, F);
-        if (F < 0.0) return -INFINITY;
-        if (np == lRef) break;
-        if (F <= kMinCarryOver) {
-            if (F < DBL_MIN) return -INFINITY;
-            Lk += log(F);
-            F = 1.0;
+        if (__ballot_sync(mask, general) == 0u) break;  // every lane is through its lists
+        if (general) {
+            F = scan_site_general(m, a.x, pP + (a.y & SA_IDX), b.x, pC + (b.y & SA_IDX), np - 1, bLen, isTipC, F);
+            if (F < 0.0) dead = finished = true;
+            else if (np == lRef) finished = true;
+            else {
+                if (F <= kMinCarryOver) {
+                    if (F < DBL_MIN) dead = finished = true;
+                    else { Lk += log(F); F = 1.0; }
+                }
+                eP += (int(a.x >> 8) == np);
+                eC += (int(b.x >> 8) == np);
+                a = *eP;
+                b = *eC;
+            }
         }
-        if (int(a.x >> 8) == np) a = *++eP;
-        if (int(b.x >> 8) == np) b = *++eC;
     }
-    if (!(F > 0.0)) return -INFINITY;
+    if (dead || !(F > 0.0)) return -INFINITY;
     return Lk + log(F);
 }
 
@@ -199,11 +241,18 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
     const int64_t id = 3 * (int64_t)T.nNodes + node, ks = T.keyStart[id];
     if (ks < 0) return 0;
     const int nk = T.nkeys[id];
-    int np = 0;
+    int np = 0, ip = 0;
     for (int q = 0; q < nk; q++) {
         const uint32_t key = __ldg(T.key + ks + q);
         const int type = int(key & 7u);
-        np += int((key >> 3) & 3u) + (type == T_O ? 4 : 0) + (type < 4 ? 1 : 0);
+        const int nl = int((key >> 3) & 3u);
+        np += nl + (type < 4 ? 1 : 0);
+        if (type == T_O) {
+            np += 4;
+            if (__ldg(T.pay + T.payStart[id] + ip + nl + int((key >> 6) & 3u)) > 0.02) np++;
+            ip += 4;
+        }
+        ip += nl;
     }
     const uint32_t ue = uint32_t(nk + 1) >> 1, up = uint32_t(np + 1) >> 1;
     return (nk > 0 && ue < 65536u && up < 65536u && np < 65536) ? (ue | (up << 16)) : 0u;
@@ -479,7 +528,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
 #endif
                 const uint2* eP = reinterpret_cast<const uint2*>(base);
                 const double* pP = reinterpret_cast<const double*>(base + (myCnt & 0xffffu));
-                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen);
+                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen, nScore >= 32 ? FULL : ((1u << nScore) - 1u));
             } else {
                 const int64_t id = 3 * (int64_t)t.nNodes + __ldg(&t.scan2[pos + W.slotS[lane]].node);
                 sc = scan_append_generic(m, t.key + t.keyStart[id], t.pay + t.payStart[id], J.remK, J.remP, isRemovedTip, removedBLen);

@@ -969,7 +969,11 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                                               SearchResult* __restrict__ out, ScratchD s, StackE* stack, int stackCap, unsigned long long* counter,
                                               long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
                                               const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity,
-                                              const BigScratch& big) {
+                                              const BigScratch& big, int warpId, int totalWarps) {
+    // First search of every owning lane: entry lane * totalWarps + warpId of the list, so that neighbours in the list -- the
+    // longest searches when the list is sorted longest-first -- start in different warps (the lanes of a warp share its time).
+    // The counter then starts behind those entries (the host sets it).  totalWarps == 0: everything comes from the counter.
+    bool firstPull = totalWarps > 0;
     const ScratchD sOwn = s;
     StackE* const stackOwn = stack;
     bool usingBig = false;
@@ -1044,7 +1048,10 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                 if (outCycles) outCycles[i] = clock64() - c0;
                 stage = 0;
             }
-            i = atomicAdd(counter, 1ULL);
+            if (firstPull) {
+                firstPull = false;
+                i = (unsigned long long)lane_ * (unsigned long long)totalWarps + (unsigned long long)warpId;
+            } else i = atomicAdd(counter, 1ULL);
             if (i >= (unsigned long long)n) { stage = 3; f.op = OP_NONE; break; }
             node = nodes[i];
             c0 = clock64();

@@ -98,7 +98,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
     std::vector<uint4> smem((fixed + (size_t)poolBytes + 64) / 16);
     ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data());
     Scan2Smem& W2 = *reinterpret_cast<Scan2Smem*>(smem.data());
-    unsigned long long counter = 0, bigCounter = 0;
+    unsigned long long counter = (unsigned long long)lanesPerWarp, bigCounter = 0;  // one warp: lane k starts with entry k (fsm_warp_loop)
     unsigned long long wst[kNumSearchStats] = {0};
     BigScratch big;
     memset(&big, 0, sizeof big);
@@ -120,10 +120,10 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         uint32_t parity = 0;
         if (scanForm == 2)
             fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
-                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big);
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1);
         else
             fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
-                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big);
+                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1);
     });
     if (stats) {
         for (int i = 0; i < kNumSearchStats; i++) stats[i] += wst[i];
@@ -141,7 +141,9 @@ double hw_scan_append(const DevModel* m, const uint32_t* kP, const double* pP, i
     std::vector<double> yP(8 * (size_t)nkP + 8), yC(8 * (size_t)capE);
     scan_build_p(*m, kP, pP, nkP, eP.data(), yP.data());
     if (scan_build_c(*m, kC, pC, bLen, eC.data(), capE, yC.data(), 8 * capE) < 0) return NAN;
-    return scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen);
+    double r = 0.0;
+    hostwarp::run_warp([&]() { if ((threadIdx.x & 31) == 0) r = scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen, 1u); });
+    return r;
 }
 
 }  // extern "C"
