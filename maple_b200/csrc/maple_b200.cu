@@ -52,6 +52,13 @@ struct maple_ctx {
     uint32_t *scanUnits = nullptr, *scanOffsets = nullptr;
     uint4* scanArena = nullptr;
     ScanRec* scanRecs = nullptr;
+    uint32_t scanMaxUnits = 0;    // largest scan-format list, 16-byte units
+    bool scanAllStaged = false;   // every probVectTotUp list has a scan-format copy
+    // scan service (scan2.cuh: ScanQueue): SMs whose CTAs own the searches; the CTAs of all other SMs only serve subtree scans.
+    // -1 = chosen per launch from the stop rules, 0 = off (every warp scans for its own lanes)
+    int fsmSMs = -1;
+    void* queueMem = nullptr;
+    size_t queueBytes = 0;
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
@@ -324,7 +331,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
                                                                    unsigned long long* counter, long long* outCycles, int scanMinSize,
                                                                    int scanFlags, int poolBytes, unsigned long long* stats,
                                                                    const unsigned long long* nDev, const int32_t* outIndex, int lanesPerWarp,
-                                                                   const __grid_constant__ BigScratch big) {
+                                                                   const __grid_constant__ BigScratch big, const __grid_constant__ ScanQueue sq,
+                                                                   int fsmSMs) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -348,9 +356,31 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     (void)W;
     if (nDev) n = (int64_t)min((unsigned long long)n, *nDev);  // retry launch: the list length lives on the device
     stage_model(sm, gm);
-    // scratch is laid out for the lanes that own searches only
     const int lane_ = int(threadIdx.x & 31);
-    const size_t tid = ((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * (size_t)lanesPerWarp + (lane_ < lanesPerWarp ? lane_ : 0);
+    size_t tid;
+    int ownerBase = 0;
+    if (SCAN2 && sq.cap != 0) {
+        // Scan service: the CTAs on the first fsmSMs SMs (and CTA 0, so that somebody owns the searches wherever the CTAs land) run
+        // the searches' state machines, 32 to a warp, and post their subtree scans; every other CTA only serves scans.  The split
+        // is by SM so that an SM's instruction cache holds one of the two code paths, not both.
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        bool owns = int(smid) < fsmSMs || blockIdx.x == 0;
+        if (owns) {
+            if (lane_ == 0) ownerBase = int(atomicAdd(sq.ownerCounter, (unsigned long long)lanesPerWarp));
+            ownerBase = __shfl_sync(0xffffffffu, ownerBase, 0);
+            if (ownerBase + lanesPerWarp > sq.maxOwners) owns = false;  // more owning warps than the host sized scratch for
+        }
+        if (!owns) {
+            scan_server_loop(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st, sq, n);
+            goto flush;
+        }
+        tid = (size_t)ownerBase + (lane_ < lanesPerWarp ? lane_ : 0);
+    } else {
+        // scratch is laid out for the lanes that own searches only
+        tid = ((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * (size_t)lanesPerWarp + (lane_ < lanesPerWarp ? lane_ : 0);
+    }
+    {
     ScratchD s;
     s.key = scrKey + tid * capK;
     s.pay = scrPay + tid * capP;
@@ -359,7 +389,9 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     StackE* stack = scrStack + tid * (size_t)stackCap;
     fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
                          lanesPerWarp, W, W2, mbarParity, big, int((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5),
-                         nDev ? 0 : int(gridDim.x * (blockDim.x >> 5)));
+                         (nDev || sq.cap != 0) ? 0 : int(gridDim.x * (blockDim.x >> 5)), sq, ownerBase);
+    }
+flush:
     if (stats) {
         __syncthreads();
         for (int i = threadIdx.x; i < kNumSearchStats; i += blockDim.x) {
@@ -515,6 +547,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     ctx->device = device;
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
     if (const char* e = getenv("MAPLE_SCAN_OLD")) ctx->scanOldEnv = atoi(e) != 0;
+    if (const char* e = getenv("MAPLE_FSM_SMS")) ctx->fsmSMs = atoi(e);
     ctx->scanOld = ctx->scanOldEnv;
     if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 0 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 0; }
     if (const char* e = getenv("MAPLE_SCAN_REPLAY")) ctx->scanReplaySequential = strcmp(e, "sequential") == 0;
@@ -554,6 +587,7 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->scanUnits);
     cudaFree(ctx->scanArena);
     cudaFree(ctx->scanRecs);
+    cudaFree(ctx->queueMem);
     delete ctx;
     return MAPLE_OK;
 }
@@ -881,12 +915,22 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
         std::vector<uint32_t> hu(n), ho(n);
         CK(cudaMemcpy(hu.data(), ctx->scanUnits, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         uint64_t tot = 0;
+        ctx->scanMaxUnits = 0;
+        ctx->scanAllStaged = true;
+        bool fixUnits = false;
         for (size_t i = 0; i < n; i++) {
+            if (hu[i] == ~0u) { hu[i] = 0; ctx->scanAllStaged = false; fixUnits = true; }  // a list too large for a scan-format copy
             const uint64_t u = (hu[i] & 0xffffu) + (hu[i] >> 16);
-            if (u == 0 || tot + u >= 0xffffffffull) { ho[i] = ~0u; continue; }
+            if (u == 0 || tot + u >= 0xffffffffull) {
+                if (u) ctx->scanAllStaged = false;
+                ho[i] = ~0u;
+                continue;
+            }
             ho[i] = (uint32_t)tot;
             tot += u;
+            if (u > ctx->scanMaxUnits) ctx->scanMaxUnits = (uint32_t)u;
         }
+        if (fixUnits) CK(cudaMemcpy(ctx->scanUnits, hu.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->scanOffsets, ho.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CK(cudaMalloc((void**)&ctx->scanArena, (size_t)(tot + 4) * sizeof(uint4)));
         CK(cudaMalloc((void**)&ctx->scanRecs, n * sizeof(ScanRec)));
@@ -928,7 +972,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
-                               const unsigned long long*, const int32_t*, int, const BigScratch);
+                               const unsigned long long*, const int32_t*, int, const BigScratch, const ScanQueue, int);
     // Register budget = resident warps.  __launch_bounds__(64, 7) makes ptxas settle on 128 registers with few spills, which lets
     // 8 CTAs (16 warps) share an SM: 3.1 s for the deep round at 100 k sequences against 4.4 s for the 168-register build
     // (12 warps) on the same box.  MAPLE_FSM_MINB=6 selects the latter for A/B runs.  (Register allocation of this kernel is
@@ -955,8 +999,25 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     // has to be kept busy is the warp, not the lane: every resident warp should own searches, and each owning lane should get
     // a few searches in turn (dynamic balance) rather than one.  With few searches (a shard of a multi-GPU round) this spreads
     // them over all warps instead of packing 32 into each of a few.
+    // Scan service: searches owned by the CTAs of fsmSMs SMs (32 to a warp), subtree scans served by all other CTAs.  Needs the
+    // whole grid resident (it is: sized from the occupancy query) and every list to fit a server's pool next to the removed list.
+    int fsmSMs = 0;
+    if (scan2 && ctx->scanAllStaged && (size_t)ctx->scanMaxUnits * 16 + 64 <= (size_t)poolBytes / 2 && max_concurrent_searches == 0 &&
+        ctx->numSMs >= 8 && ctx->lanesPerWarp <= 0) {
+        fsmSMs = ctx->fsmSMs;
+        // the strict rules of the fast round leave little to scan (most of the work is on the lanes), the deep rounds are nearly all scans
+        if (fsmSMs < 0) fsmSMs = sp.strictTopologyStopRules ? ctx->numSMs / 2 : ctx->numSMs / 6;
+        if (fsmSMs > ctx->numSMs - 4) fsmSMs = ctx->numSMs - 4;
+        // few searches: no more owning warps than searches / 8
+        const int64_t wantWarps = (n + 255) / 256;
+        const int warpsPerSM = blocksPerSM * (kSearchThreads / 32);
+        if ((int64_t)fsmSMs * warpsPerSM > wantWarps) fsmSMs = (int)((wantWarps + warpsPerSM - 1) / warpsPerSM);
+        if (fsmSMs < 1) fsmSMs = 1;
+    }
     int lpw = 32;
-    if (ctx->searchVariant != 1) {
+    if (fsmSMs > 0) {
+        lpw = 32;
+    } else if (ctx->searchVariant != 1) {
         lpw = ctx->lanesPerWarp;
         if (lpw <= 0) {
             const int64_t warps = threads / 32;
@@ -968,7 +1029,8 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     int blocks = (int)((threads + kSearchThreads - 1) / kSearchThreads);
     threads = (int64_t)blocks * kSearchThreads;
     const size_t perThread = (size_t)capK * 4 + (size_t)capP * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
-    const size_t owners = (size_t)threads / 32 * lpw;  // lanes that own a search (and scratch)
+    // lanes that own a search (and scratch); with the scan service: the warps of fsmSMs SMs and of CTA 0
+    const size_t owners = fsmSMs > 0 ? ((size_t)fsmSMs * blocksPerSM + 1) * (kSearchThreads / 32) * 32 : (size_t)threads / 32 * lpw;
     const size_t need = perThread * owners + 256;
     if (need > ctx->searchScratchBytes) {
         cudaFree(ctx->searchScratch);
@@ -979,7 +1041,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     }
     if (!ctx->searchCounter) CK(cudaMalloc((void**)&ctx->searchCounter, sizeof(unsigned long long)));
     {   // the state-machine kernel hands the first `owners` entries out statically (fsm_warp_loop), the counter serves the rest
-        const unsigned long long first = ctx->searchVariant != 1 ? (unsigned long long)owners : 0ULL;
+        const unsigned long long first = (ctx->searchVariant != 1 && fsmSMs == 0) ? (unsigned long long)owners : 0ULL;
         CK(cudaMemcpyAsync(ctx->searchCounter, &first, sizeof first, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     }
     char* base = (char*)ctx->searchScratch;
@@ -1018,6 +1080,29 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         big.nSlots = kBigSlots;
         big.counter = ctx->retryCounters + 2;
     }
+    ScanQueue sq{};
+    if (fsmSMs > 0) {
+        unsigned cap = 1024;
+        while (cap < 4 * owners) cap <<= 1;
+        const size_t bytes = 64 + (size_t)cap * 8 + owners * sizeof(ScanJob);
+        if (bytes > ctx->queueBytes) {
+            cudaFree(ctx->queueMem);
+            ctx->queueMem = nullptr;
+            ctx->queueBytes = 0;
+            CK(cudaMalloc(&ctx->queueMem, bytes));
+            ctx->queueBytes = bytes;
+        }
+        CK(cudaMemsetAsync(ctx->queueMem, 0, bytes, (cudaStream_t)stream));
+        char* q = (char*)ctx->queueMem;
+        sq.head = (unsigned long long*)q;
+        sq.tail = sq.head + 1;
+        sq.doneSearches = sq.head + 2;
+        sq.ownerCounter = sq.head + 3;
+        sq.ring = (unsigned long long*)(q + 64);
+        sq.jobs = (ScanJob*)(q + 64 + (size_t)cap * 8);
+        sq.cap = cap;
+        sq.maxOwners = (int)owners;
+    }
     if (scan2) {
         k_scan_build<<<(T.nNodes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->model, T, sp.effectivelyNon0BLen, ctx->scanUnits, ctx->scanArena,
                                                                               ctx->scanRecs);
@@ -1037,7 +1122,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big);
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs);
     ctx->launches++;
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
         // safety net: searches that found no large slot free are collected and re-run by one CTA that uses the same slots (free
@@ -1049,7 +1134,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
             ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, big.key, big.pay, big.ais, big.stack, big.capK, big.capP, big.capA,
             stackCap, ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
-            ctx->retryCounters, retryIdx, 32, none);
+            ctx->retryCounters, retryIdx, 32, none, ScanQueue{}, 0);
         ctx->launches += 2;
     }
     CK(cudaGetLastError());
@@ -1155,6 +1240,12 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
     if (!ctx || variant < 0 || variant > 4) return MAPLE_E_ARG;
     ctx->searchVariant = variant == 4 ? 0 : variant;
     ctx->scanOld = variant == 4 ? true : ctx->scanOldEnv;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs) {
+    if (!ctx || fsmSMs < -1) return MAPLE_E_ARG;
+    ctx->fsmSMs = fsmSMs;
     return MAPLE_OK;
 }
 

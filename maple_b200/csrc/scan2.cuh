@@ -28,6 +28,32 @@
 
 namespace maple {
 
+// loads that other SMs' stores must be visible to (scan service): volatile / L1-bypassing on the device
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+__device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void spin_pause(unsigned ns) { __nanosleep(ns); }
+template <class T>
+__device__ __forceinline__ T ld_cg(const T* p) {  // ld.global.cg of a 4- or 8-byte object
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "ld_cg: 4 or 8 bytes");
+    T v;
+    if (sizeof(T) == 4) {
+        const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(p));
+        memcpy(&v, &u, sizeof v);
+    } else {
+        const unsigned long long u = __ldcg(reinterpret_cast<const unsigned long long*>(p));
+        memcpy(&v, &u, sizeof v);
+    }
+    return v;
+}
+#else
+inline unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+inline int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+inline void spin_pause(unsigned) { host_yield(); }  // the emulated lane lets the others run
+template <class T>
+inline T ld_cg(const T* p) { return *p; }
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // scan-format lists
 // entry.x = the arena key (type | nLens<<3 | flag<<5 | nuc<<6 | end<<8); entry.y = aux:
@@ -106,7 +132,7 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
     int np = 0, ip = 0;
     for (int i = 0;; i++) {
         if (i >= capE) return -1;
-        const uint32_t key = k[i];
+        const uint32_t key = ld_cg(k + i);
         const int type = int(key & 7u), nl = int((key >> 3) & 3u), nuc = int((key >> 6) & 3u), end = int(key >> 8);
         if (np + 8 > capP || np + 8 > int(SA_IDX)) return -1;
         uint32_t row = 0;
@@ -117,7 +143,7 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
         if (type == T_R) aux |= SA_FAST_PO;
         if (!m.U && type == T_R && nl == 0 && bLen != 0.0) aux |= SA_FAST_P;
         if (type == T_O) {
-            const double a = p[ip + nl + nuc];
+            const double a = ld_cg(p + ip + nl + nuc);
             if (a > 0.02) {
                 aux |= SA_FAST_CO;
                 outP[np++] = a;
@@ -128,17 +154,17 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
             const SiteQ q(m, end - 1);
             const double g = q.at(nuc, type);  // mutMatrices[pos][reference nuc][nuc of the entry]
             double contrib = bLen;
-            if (nl == 1) contrib += p[ip];
+            if (nl == 1) contrib += ld_cg(p + ip);
             // the whole factor against a plain reference run of the candidate (:6657-6663); -1 marks "the reference returns -inf"
             outP[np++] = (contrib == 0.0) ? -1.0 : fmin(0.25, g * contrib);
-            for (int q2 = 0; q2 < nl; q2++) outP[np++] = p[ip + q2];
+            for (int q2 = 0; q2 < nl; q2++) outP[np++] = ld_cg(p + ip + q2);
             ip += nl;
             outP[np++] = g;
         } else {
-            for (int q2 = 0; q2 < nl; q2++) outP[np++] = p[ip + q2];
+            for (int q2 = 0; q2 < nl; q2++) outP[np++] = ld_cg(p + ip + q2);
             ip += nl;
             if (type == T_O) {
-                for (int q2 = 0; q2 < 4; q2++) outP[np++] = p[ip + q2];
+                for (int q2 = 0; q2 < 4; q2++) outP[np++] = ld_cg(p + ip + q2);
                 ip += 4;
             }
         }
@@ -255,7 +281,8 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
         ip += nl;
     }
     const uint32_t ue = uint32_t(nk + 1) >> 1, up = uint32_t(np + 1) >> 1;
-    return (nk > 0 && ue < 65536u && up < 65536u && np < 65536) ? (ue | (up << 16)) : 0u;
+    if (nk <= 0) return 0u;
+    return (ue < 65536u && up < 65536u && np < 65536) ? (ue | (up << 16)) : ~0u;  // ~0u: too large for a scan-format copy
 }
 
 // The record of pre-order position i and, where there is one, the scan-format copy of its list (nsa is filled by scan_fill_nsa
@@ -320,7 +347,27 @@ struct ScanJob {  // filled by the lane that owns the search
     // results
     double bestOut;
     int phase1, qN, newBest, err;
+    int state, pad2;  // scan service (below): 0 none, 1 posted, 2 served, 3 declined -- the owner's warp runs it itself
 };
+
+// ---- scan service: jobs handed from the warps that own searches to warps (on other SMs) that do nothing but scans.
+// One slot per owning lane in global memory; a ring of tickets says which slots are waiting.  Producer: fill the slot,
+// __threadfence, take a ticket (atomicAdd on tail), publish (ticket+1)<<32 | owner in ring[ticket % cap].  Consumer: take a
+// ticket below tail (CAS on head), wait for its ring entry, read the slot with L1-bypassing loads, run the job, write the
+// results, __threadfence, state = 2.  Every owner has at most one job outstanding and cap >= 4 * owners, so a ring entry is
+// never overwritten before its consumer has read it.
+struct ScanQueue {
+    unsigned long long* ring;
+    unsigned long long* head;
+    unsigned long long* tail;
+    unsigned long long* doneSearches;  // searches completed by the warps that own them; servers leave when it reaches n
+    unsigned long long* ownerCounter;  // owner ids handed to the owning warps
+    ScanJob* jobs;
+    unsigned cap;       // power of two; 0 = no service: every warp scans for its own lanes
+    int maxOwners;
+};
+
+
 
 struct Scan2Smem {
     double scoreS[32];  // by rank k: score of the k-th scored node of the window
@@ -390,8 +437,10 @@ __device__ __noinline__ double scan_append_generic(const DevModel& m, const uint
 
 // W.job holds the request (written by the owning lane, visible to the warp); the results are left in W.job.
 // mbarParity: phase parity of W.mbar, kept by the caller across jobs.  st: optional profiling counters (lane 0 adds).
+// remote: the job belongs to a lane of another warp (scan service): if the removed list's copy does not fit the pool the job is
+// declined (W.job.err = 4) instead of being scored from the arena lists, whose stale copies this SM's L1 might hold.
 __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const SearchParams& sp, Scan2Smem& W, int poolBytes, int scanFlags /* 2: every window replayed node by node */,
-                               uint32_t& mbarParity, unsigned long long* st) {
+                               uint32_t& mbarParity, unsigned long long* st, bool remote) {
     const unsigned FULL = 0xffffffffu;
     const int lane = int(threadIdx.x & 31);
     const unsigned ltMask = (1u << lane) - 1u;
@@ -413,7 +462,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
     if (lane == 0) {
         int nkC = 0;
         const int capE = poolBytes >> 4;  // half the pool at 8 bytes per entry
-        while (nkC < capE && int(J.remK[nkC] >> 8) != m.lRef) nkC++;
+        while (nkC < capE && int(ld_cg(J.remK + nkC) >> 8) != m.lRef) nkC++;
         nkC++;
         cEntUnits = (nkC + 1) >> 1;
         const int capP = ((poolBytes >> 1) - 16 * cEntUnits) >> 3;
@@ -429,6 +478,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
     cUnits = __shfl_sync(FULL, cUnits, 0);
     const bool cOk = cUnits > 0;
     err = __shfl_sync(FULL, err, 0);
+    if (remote && !cOk && !err) err = 4;
     __syncwarp();
     const uint4* const arena = t.scanArena;
     const int poolUnits = (poolBytes >> 4) - cUnits;
@@ -740,6 +790,51 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         W.job.err = err;
     }
     __syncwarp();
+}
+
+// The loop of a serving warp: take a posted job, run it, hand the results back; leave when every search of the launch has been
+// completed by the warp that owns it (then nothing can be posted any more) and the ring is empty.
+__device__ void scan_server_loop(const DevModel& m, const DevTree& t, const SearchParams& sp, Scan2Smem& W, int poolBytes, int scanFlags,
+                                 uint32_t& mbarParity, unsigned long long* st, const ScanQueue& sq, int64_t n) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = int(threadIdx.x & 31);
+    for (;;) {
+        long long owner = -1;
+        if (lane == 0) {
+            const unsigned long long h = ld_volatile_u64(sq.head), tl = ld_volatile_u64(sq.tail);
+            if (h < tl) {
+                if (atomicCAS(sq.head, h, h + 1ULL) == h) {
+                    const unsigned long long* slot = sq.ring + (h & (sq.cap - 1));
+                    unsigned long long v;
+                    while (((v = ld_volatile_u64(slot)) >> 32) != h + 1ULL) spin_pause(20);
+                    owner = (long long)(v & 0xffffffffULL);
+                }
+            } else if (ld_volatile_u64(sq.doneSearches) >= (unsigned long long)n) owner = -2;
+        }
+        owner = __shfl_sync(FULL, owner, 0);
+        if (owner == -2) break;
+        if (owner < 0) { spin_pause(300); continue; }
+        ScanJob* J = sq.jobs + owner;
+        __threadfence();
+        if (lane == 0) {  // the request, read past this SM's L1
+            ScanJob& L = W.job;
+            L.R = ld_cg(&J->R); L.pruned = ld_cg(&J->pruned); L.sibling = ld_cg(&J->sibling); L.failed0 = ld_cg(&J->failed0);
+            L.best = ld_cg(&J->best); L.lastLK0 = ld_cg(&J->lastLK0); L.removedBLen = ld_cg(&J->removedBLen);
+            L.isRemovedTip = ld_cg(&J->isRemovedTip); L.pathCap = ld_cg(&J->pathCap); L.qCap = ld_cg(&J->qCap);
+            L.remK = ld_cg(&J->remK); L.remP = ld_cg(&J->remP); L.gpath = ld_cg(&J->gpath); L.qTop = ld_cg(&J->qTop);
+        }
+        __syncwarp();
+        warp_scan_job2(m, t, sp, W, poolBytes, scanFlags, mbarParity, st, true);
+        if (lane == 0) {
+            const ScanJob& L = W.job;
+            const bool declined = L.err == 4;
+            J->bestOut = L.bestOut; J->phase1 = L.phase1; J->qN = L.qN; J->newBest = L.newBest; J->err = declined ? 0 : L.err;
+            __threadfence();
+            *reinterpret_cast<volatile int*>(&J->state) = declined ? 3 : 2;
+            if (st) st[27] += 1;
+        }
+        __syncwarp();
+    }
 }
 
 }  // namespace maple

@@ -196,7 +196,7 @@ __device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const Sear
                 f.qRes = (unsigned(f.qN) + 3u) & ~3u;
                 s.capK -= f.qRes;  // the queue sits at the top end of the key scratch
                 for (f.qi = 0; f.qi < f.qN; f.qi++) {
-                    f.t1 = int(s.key[s.capK + f.qRes - 1u - unsigned(f.qi)]);
+                    f.t1 = int(ld_cg(s.key + (s.capK + f.qRes - 1u - unsigned(f.qi))));  // may have been written by a serving warp on another SM
                     f.eUp = up_list_for(m, t, s, f.t1); f.eDist = dist[f.t1]; f.eMidTot = tree_list(t, 3, f.t1);
                     f.eDown = tree_list(t, 0, f.t1);
                     f.eFromTip1 = t.isTip[f.t1] != 0; f.evalRet = 5;
@@ -969,7 +969,12 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                                               SearchResult* __restrict__ out, ScratchD s, StackE* stack, int stackCap, unsigned long long* counter,
                                               long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
                                               const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity,
-                                              const BigScratch& big, int warpId, int totalWarps) {
+                                              const BigScratch& big, int warpId, int totalWarps, const ScanQueue& sq, int ownerBase) {
+    // Scan service (sq.cap != 0, SCAN2 only): a lane that needs a subtree scan posts the job in its slot sq.jobs[ownerBase + lane]
+    // and waits for a warp of the serving SMs to run it; meanwhile the other lanes of this warp go on with their co-walks.
+    const bool service = SCAN2 && sq.cap != 0;
+    bool waitScan = false, localScan = false;
+    unsigned long long nCompleted = 0;
     // First search of every owning lane: entry lane * totalWarps + warpId of the list, so that neighbours in the list -- the
     // longest searches when the list is sorted longest-first -- start in different warps (the lanes of a warp share its time).
     // The counter then starts behind those entries (the host sets it).  totalWarps == 0: everything comes from the counter.
@@ -996,7 +1001,24 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
     SearchResult r;
     for (;;) {
         // ---------------- control (divergent, cheap)
-        if (stage == 2) {
+        if (waitScan) {  // my posted scan: served yet?
+            ScanJob* J = sq.jobs + ownerBase + lane_;
+            const int state = ld_volatile_i32(&J->state);
+            if (state == 2) {
+                __threadfence();
+                f.bestLKdiff = ld_cg(&J->bestOut);
+                f.phase1 += ld_cg(&J->phase1);
+                f.qN = ld_cg(&J->qN);
+                f.scanNewBest = ld_cg(&J->newBest);
+                const int e = ld_cg(&J->err);
+                if (e) s.err = e;
+                waitScan = false;
+            } else if (state == 3) {  // declined (the removed list does not fit a server's pool): this warp runs it itself
+                waitScan = false;
+                localScan = true;
+            }
+        }
+        if (stage == 2 && !waitScan && !localScan) {
             fsm_step(f, sm, T, sp, s, stack, stackCap, scanMinSize);
         } else if (stage == 1) {
             bestCurrentLK = f.resD;
@@ -1047,6 +1069,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                 out[outIndex ? outIndex[i] : i] = r;
                 if (outCycles) outCycles[i] = clock64() - c0;
                 stage = 0;
+                nCompleted++;
             }
             if (firstPull) {
                 firstPull = false;
@@ -1058,14 +1081,14 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
             r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
             r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
             f.op = OP_NONE;
-            if (T.up[node] < 0) { out[outIndex ? outIndex[i] : i] = r; continue; }
+            if (T.up[node] < 0) { out[outIndex ? outIndex[i] : i] = r; nCompleted++; continue; }
             s.topK = s.topP = 0;
             s.err = 0;
             const int parent = T.up[node];
             LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
             if (n_mut(T, node)) vectUp = s_pass(sm, T, s, vectUp, node, false);
             const LRef own = tree_list(T, 0, node);
-            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[outIndex ? outIndex[i] : i] = r; continue; }
+            if (!vectUp.k || !own.k) { r.status = s.err ? s.err : 2; out[outIndex ? outIndex[i] : i] = r; nCompleted++; continue; }
             f.a1 = vectUp; f.a2 = own; f.at1 = T.isTip[node] != 0; f.ab1 = T.dist[node];
             f.op = OP_APPEND;
             stage = 1;
@@ -1097,8 +1120,32 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
         if (f.op == OP_DIFFER) f.resB = f_differ(sm, f.a1, f.a2) ? 1 : 0;
         __syncwarp();
         STAT_T(4);
-        // ---------------- subtree scans: the whole warp works for one lane's search at a time
-        for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN); pending; pending &= pending - 1) {
+        // ---------------- subtree scans
+        if (service) {
+            // post the new requests; the serving warps take them from the ring
+            if (f.op == OP_SCAN && !waitScan && !localScan) {
+                ScanJob* J = sq.jobs + ownerBase + lane_;
+                J->R = f.t1; J->pruned = f.pruned; J->sibling = f.sibling; J->failed0 = f.failedPasses;
+                J->best = f.bestLKdiff; J->lastLK0 = f.lastLK; J->removedBLen = f.removedBLen;
+                J->isRemovedTip = f.isRemovedTip;
+                J->remK = f.removed.k; J->remP = f.removed.p;
+                J->gpath = reinterpret_cast<PathE2*>(stack + f.spN);
+                J->pathCap = int((size_t)(stackCap - f.spN) * sizeof(StackE) / sizeof(PathE2));
+                J->qTop = s.key + s.capK;
+                J->qCap = int(s.capK - s.topK) - 8;
+                J->state = 1;
+                __threadfence();
+                const unsigned long long ticket = atomicAdd(sq.tail, 1ULL);
+                *reinterpret_cast<volatile unsigned long long*>(sq.ring + (ticket & (sq.cap - 1))) =
+                    ((ticket + 1ULL) << 32) | (unsigned long long)(ownerBase + lane_);
+                waitScan = true;
+                STAT_N(26, 1);
+            }
+            // nothing to do for anybody until a scan comes back: do not hammer the slots
+            if (__all_sync(0xffffffffu, stage == 3 || waitScan)) spin_pause(400);
+        }
+        // scans this warp runs itself (no service, or declined by it): the whole warp works for one lane's search at a time
+        for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_SCAN && (!service || localScan)); pending; pending &= pending - 1) {
             const int src = __ffs(pending) - 1;
             if (SCAN2) {
                 if (lane_ == src) {  // the request, for the whole warp to read
@@ -1114,7 +1161,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                     J.qCap = int(s.capK - s.topK) - 8;
                 }
                 __syncwarp();
-                warp_scan_job2(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st);
+                warp_scan_job2(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st, false);
                 if (lane_ == src) {
                     const ScanJob& J = W2.job;
                     f.bestLKdiff = J.bestOut;
@@ -1122,12 +1169,19 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                     f.qN = J.qN;
                     f.scanNewBest = J.newBest;
                     if (J.err) s.err = J.err;
+                    localScan = false;
                 }
                 __syncwarp();
             } else warp_scan_job(src, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags, st);
         }
         STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
+    }
+    if (service) {  // this warp's searches are over: tell the servers, then help them until everybody is through
+        for (int o = 16; o; o >>= 1) nCompleted += __shfl_xor_sync(0xffffffffu, nCompleted, o);
+        if (l0 && nCompleted) atomicAdd(sq.doneSearches, nCompleted);
+        __syncwarp();
+        scan_server_loop(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st, sq, n);
     }
 #undef STAT_T
 #undef STAT_N

@@ -142,6 +142,10 @@ class MapleEngine:
     def set_scan_min_size(self, n: int):
         capi.check(self.ctx, self.lib.maple_ctx_set_scan_min_size(self.ctx, int(n)), "maple_ctx_set_scan_min_size")
 
+    def set_scan_service(self, fsm_sms: int):
+        """SMs whose CTAs own the searches while all others only serve subtree scans (-1 = chosen per launch, 0 = off)."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_scan_service(self.ctx, int(fsm_sms)), "maple_ctx_set_scan_service")
+
     def search_stats(self, enable: bool = True, read: bool = True):
         """Profiling counters of the search kernel (see scripts/time_search.py for their meaning)."""
         out = (C.c_uint64 * 32)() if read else None

@@ -16,6 +16,8 @@ scratch_keys = int(sys.argv[5]) if len(sys.argv) > 5 else 16384
 d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=True)
 eng = MapleEngine(d.model, 0)
 eng.set_search_variant(variant)
+if len(sys.argv) > 6:
+    eng.set_scan_service(int(sys.argv[6]))
 tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
 tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, 0))
 nodes = dirty_nodes(tree)

@@ -143,6 +143,9 @@ class FakeLib:
         self.search_variant = variant
         return 0
 
+    def maple_ctx_set_scan_service(self, ctx, n):
+        return 0
+
     def maple_ctx_set_scan_min_size(self, ctx, n):
         return 0
 

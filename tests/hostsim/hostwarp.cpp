@@ -29,8 +29,9 @@ extern "C" {
 // stats: optional 32 counters (as maple_search_stats).  Returns 0, or -1 if the second form is not available for this tree.
 int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, int64_t n, const int32_t* nodes, int64_t scratchKeys,
                     const int32_t* npay, int32_t scanForm, int32_t scanMinSize, int32_t lanesPerWarp, int32_t poolBytes, int32_t scanFlags,
-                    int32_t bigSlots /* large scratch slots (8x) for searches that exhaust theirs, 0 = none */, SearchResult* out,
-                    unsigned long long* stats) {
+                    int32_t bigSlots /* large scratch slots (8x) for searches that exhaust theirs, 0 = none */,
+                    int32_t ownerWarps /* scan service: warps that own searches ... */, int32_t serverWarps /* ... and warps that only serve scans; 0 = no service */,
+                    SearchResult* out, unsigned long long* stats) {
     DevTree T;
     memset(&T, 0, sizeof T);
     T.nNodes = t->nNodes; T.root = t->root;
@@ -74,6 +75,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         uint64_t tot = 0;
         for (size_t i = 0; i < N; i++) {
             units[i] = scan_count_units(T, (int)i);
+            if (units[i] == ~0u) units[i] = 0;
             const uint64_t u = (units[i] & 0xffffu) + (units[i] >> 16);
             if (u == 0) { offs[i] = ~0u; continue; }
             offs[i] = (uint32_t)tot;
@@ -91,14 +93,19 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
     const int stackCap = (2 * height + 32 + 63) & ~63;
     if (lanesPerWarp < 1) lanesPerWarp = 1;
     if (lanesPerWarp > 32) lanesPerWarp = 32;
-    std::vector<uint32_t> key((size_t)lanesPerWarp * capK + 64);
-    std::vector<double> pay((size_t)lanesPerWarp * capP + 64), ais((size_t)lanesPerWarp * capA);
-    std::vector<StackE> stack((size_t)lanesPerWarp * stackCap);
+    const bool service = scanForm == 2 && serverWarps > 0;
+    if (!service) ownerWarps = 1;
+    if (ownerWarps < 1) ownerWarps = 1;
+    const size_t owners = (size_t)ownerWarps * lanesPerWarp;
+    std::vector<uint32_t> key(owners * capK + 64);
+    std::vector<double> pay(owners * capP + 64), ais(owners * capA);
+    std::vector<StackE> stack(owners * stackCap);
     const size_t fixed = scanForm == 2 ? sizeof(Scan2Smem) : sizeof(ScanSmem);
-    std::vector<uint4> smem((fixed + (size_t)poolBytes + 64) / 16);
-    ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data());
-    Scan2Smem& W2 = *reinterpret_cast<Scan2Smem*>(smem.data());
-    unsigned long long counter = (unsigned long long)lanesPerWarp, bigCounter = 0;  // one warp: lane k starts with entry k (fsm_warp_loop)
+    const int nWarps = service ? ownerWarps + serverWarps : 1;
+    const size_t warpSmem = (fixed + (size_t)poolBytes + 64) / 16;
+    std::vector<uint4> smem(warpSmem * nWarps);
+    // one warp without the service: lane k starts with entry k (fsm_warp_loop); with it everything comes from the counter
+    unsigned long long counter = service ? 0ULL : (unsigned long long)lanesPerWarp, bigCounter = 0;
     unsigned long long wst[kNumSearchStats] = {0};
     BigScratch big;
     memset(&big, 0, sizeof big);
@@ -108,22 +115,41 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
     std::vector<StackE> bstack((size_t)bigSlots * stackCap + 1);
     big.key = bkey.data(); big.pay = bpay.data(); big.ais = bais.data(); big.stack = bstack.data();
     big.nSlots = bigSlots; big.counter = &bigCounter;
-    hostwarp::run_warp([&]() {
+    ScanQueue sq;
+    memset(&sq, 0, sizeof sq);
+    unsigned long long qctl[4] = {0, 0, 0, 0};
+    unsigned cap = 1024;
+    while (cap < 4 * owners) cap <<= 1;
+    std::vector<unsigned long long> ring(cap, 0ULL);
+    std::vector<ScanJob> jobs(owners);
+    memset(jobs.data(), 0, owners * sizeof(ScanJob));
+    if (service) {
+        sq.head = &qctl[0]; sq.tail = &qctl[1]; sq.doneSearches = &qctl[2]; sq.ownerCounter = &qctl[3];
+        sq.ring = ring.data(); sq.jobs = jobs.data(); sq.cap = cap; sq.maxOwners = (int)owners;
+    }
+    hostwarp::run_warps(nWarps, [&](int w) {
         const int lane = int(threadIdx.x & 31);
-        const size_t tid = (size_t)(lane < lanesPerWarp ? lane : 0);
+        ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data() + warpSmem * w);
+        Scan2Smem& W2 = *reinterpret_cast<Scan2Smem*>(smem.data() + warpSmem * w);
+        uint32_t parity = 0;
+        if (service && w >= ownerWarps) {
+            scan_server_loop(*m, T, *sp, W2, poolBytes, scanFlags, parity, stats ? wst : nullptr, sq, n);
+            return;
+        }
+        const int ownerBase = w * lanesPerWarp;
+        const size_t tid = (size_t)ownerBase + (size_t)(lane < lanesPerWarp ? lane : 0);
         ScratchD s;
         s.key = key.data() + tid * capK;
         s.pay = pay.data() + tid * capP;
         s.ais = ais.data() + tid * capA;
         s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
         StackE* stk = stack.data() + tid * (size_t)stackCap;
-        uint32_t parity = 0;
         if (scanForm == 2)
             fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
-                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1);
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase);
         else
             fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
-                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1);
+                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, 0);
     });
     if (stats) {
         for (int i = 0; i < kNumSearchStats; i++) stats[i] += wst[i];

@@ -37,6 +37,9 @@ static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline int __all_sync(unsigned, int p) { return p != 0; }
 #define __restrict__
+static inline void host_yield() {}
+static inline void __threadfence() {}
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { const unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 struct HostIdx { unsigned x = 0, y = 0, z = 0; };
 static const HostIdx threadIdx, blockIdx;
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }

@@ -16,6 +16,7 @@
 #include <functional>
 #include <math.h>
 #include <ucontext.h>
+#include <vector>
 
 #define MAPLE_HOST_WARP 1
 #define __device__
@@ -46,14 +47,18 @@ struct Lane {
 
 struct Warp {
     Lane lane[32];
-    ucontext_t sched;
-    int cur = 0;
-    std::function<void()> body;
 };
 
-inline Warp*& current() {
-    static thread_local Warp* w = nullptr;
-    return w;
+struct Grid {
+    std::vector<Warp> warps;
+    ucontext_t sched;
+    int curWarp = 0, cur = 0;
+    std::function<void(int)> body;  // body(warp index), run once per lane
+};
+
+inline Grid*& current() {
+    static thread_local Grid* g = nullptr;
+    return g;
 }
 
 inline void complete(Warp& W, unsigned mask, int op) {
@@ -82,8 +87,9 @@ inline void complete(Warp& W, unsigned mask, int op) {
 }
 
 inline uint64_t collective(int op, unsigned mask, uint64_t val, int aux) {
-    Warp& W = *current();
-    const int me = W.cur;
+    Grid& G = *current();
+    Warp& W = G.warps[G.curWarp];
+    const int me = G.cur;
     Lane& L = W.lane[me];
     if (!((mask >> me) & 1u)) { fprintf(stderr, "hostwarp: lane %d calls a *_sync intrinsic with mask %08x that excludes it\n", me, mask); abort(); }
     L.waiting = true; L.mask = mask; L.op = op; L.val = val; L.aux = aux;
@@ -98,61 +104,78 @@ inline uint64_t collective(int op, unsigned mask, uint64_t val, int aux) {
                 else if (o.op != op) { fprintf(stderr, "hostwarp: lanes %d and %d meet at different intrinsics (%d vs %d)\n", me, l, op, o.op); abort(); }
             }
         if (all) { complete(W, mask, op); continue; }
-        swapcontext(&L.ctx, &W.sched);
+        swapcontext(&L.ctx, &G.sched);
     }
+}
+
+// a spinning lane (waiting for another warp through memory) lets everybody else run
+inline void yield() {
+    Grid& G = *current();
+    swapcontext(&G.warps[G.curWarp].lane[G.cur].ctx, &G.sched);
 }
 
 inline void trampoline() {
-    Warp& W = *current();
-    W.body();
-    W.lane[W.cur].done = true;
-    swapcontext(&W.lane[W.cur].ctx, &W.sched);
+    Grid& G = *current();
+    G.body(G.curWarp);
+    Lane& L = G.warps[G.curWarp].lane[G.cur];
+    L.done = true;
+    swapcontext(&L.ctx, &G.sched);
 }
 
-// runs body() once per lane, the 32 lanes interleaved at the warp intrinsics
-inline void run_warp(const std::function<void()>& body) {
-    static thread_local Warp* W = nullptr;
+// runs body(w) once per lane of each of nWarps warps, all lanes interleaved at the warp intrinsics and at spin_pause()
+inline void run_warps(int nWarps, const std::function<void(int)>& body) {
     constexpr size_t kStack = 1 << 20;
-    if (!W) {
-        W = new Warp;
-        for (auto& L : W->lane) L.stack = (char*)malloc(kStack);
-    }
-    Warp* prev = current();
-    current() = W;
-    W->body = body;
-    for (int l = 0; l < 32; l++) {
-        Lane& L = W->lane[l];
-        getcontext(&L.ctx);
-        L.ctx.uc_stack.ss_sp = L.stack;
-        L.ctx.uc_stack.ss_size = kStack;
-        L.ctx.uc_link = nullptr;
-        L.done = false; L.waiting = false;
-        makecontext(&L.ctx, (void (*)())trampoline, 0);
-    }
+    Grid* G = new Grid;
+    G->warps.resize(nWarps);
+    for (auto& W : G->warps)
+        for (auto& L : W.lane) L.stack = (char*)malloc(kStack);
+    Grid* prev = current();
+    current() = G;
+    G->body = body;
+    for (int w = 0; w < nWarps; w++)
+        for (int l = 0; l < 32; l++) {
+            Lane& L = G->warps[w].lane[l];
+            getcontext(&L.ctx);
+            L.ctx.uc_stack.ss_sp = L.stack;
+            L.ctx.uc_stack.ss_size = kStack;
+            L.ctx.uc_link = nullptr;
+            L.done = false; L.waiting = false;
+            makecontext(&L.ctx, (void (*)())trampoline, 0);
+        }
+    unsigned long long idlePasses = 0;
     for (;;) {
         bool anyLeft = false, progressed = false;
-        for (int l = 0; l < 32; l++) {
-            Lane& L = W->lane[l];
-            if (L.done) continue;
-            anyLeft = true;
-            if (L.waiting) {  // runnable only once its group is complete: let it re-check
-                bool all = true;
-                for (int q = 0; q < 32 && all; q++)
-                    if ((L.mask >> q) & 1u) all = W->lane[q].waiting && W->lane[q].mask == L.mask;
-                if (!all) continue;
+        for (int w = 0; w < nWarps; w++)
+            for (int l = 0; l < 32; l++) {
+                Lane& L = G->warps[w].lane[l];
+                if (L.done) continue;
+                anyLeft = true;
+                if (L.waiting) {  // runnable only once its group is complete: let it re-check
+                    bool all = true;
+                    for (int q = 0; q < 32 && all; q++)
+                        if ((L.mask >> q) & 1u) all = G->warps[w].lane[q].waiting && G->warps[w].lane[q].mask == L.mask;
+                    if (!all) continue;
+                }
+                G->curWarp = w;
+                G->cur = l;
+                swapcontext(&G->sched, &L.ctx);
+                progressed = true;
             }
-            W->cur = l;
-            swapcontext(&W->sched, &L.ctx);
-            progressed = true;
-        }
         if (!anyLeft) break;
         if (!progressed) { fprintf(stderr, "hostwarp: dead-lock, every live lane waits for a lane that is not coming\n"); abort(); }
+        if (++idlePasses > 400000000ull) { fprintf(stderr, "hostwarp: gave up after 4e8 scheduler passes (live-lock between warps?)\n"); abort(); }
     }
+    for (auto& W : G->warps)
+        for (auto& L : W.lane) free(L.stack);
     current() = prev;
+    delete G;
 }
+
+inline void run_warp(const std::function<void()>& body) { run_warps(1, [&](int) { body(); }); }
 
 struct Idx { unsigned x, y, z; };
 inline Idx tidx() { return Idx{current() ? (unsigned)current()->cur : 0u, 0u, 0u}; }
+inline int warp_index() { return current() ? current()->curWarp : 0; }
 
 template <class T>
 inline uint64_t bits(T v) { uint64_t u = 0; memcpy(&u, &v, sizeof v); return u; }
@@ -187,6 +210,9 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline long long clock64() { return 0; }
+static inline void host_yield() { hostwarp::yield(); }
+static inline void __threadfence() {}
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { const unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

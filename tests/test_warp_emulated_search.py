@@ -77,6 +77,27 @@ def test_second_form_forced_shapes(name, shape):
     _same(hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, **shape), want)
 
 
+@pytest.mark.parametrize("shape", [dict(owner_warps=1, server_warps=1, lanes_per_warp=32), dict(owner_warps=2, server_warps=3, lanes_per_warp=32),
+                                   dict(owner_warps=3, server_warps=1, lanes_per_warp=5, scan_min_size=1),
+                                   dict(owner_warps=1, server_warps=2, lanes_per_warp=32, pool_bytes=192)])
+@pytest.mark.parametrize("name", ["ex_unrest_rv", "ay_unrest_300"])
+def test_scan_service(name, shape):
+    """The scan service: the warps that own the searches post their subtree scans in global-memory slots, other warps take them
+    from a ticket ring, run them and hand the results back (scan2.cuh: ScanQueue, scan_server_loop; fsm_warp_loop).  All warps are
+    emulated together, a spinning lane lets the others run.  With a 192-byte pool the removed list's copy fits no server: every
+    job is declined and run by the warp that owns it.  Records as without the service."""
+    g = load_golden(name)
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs, hw = KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
+    lists = _prefilled_lists(g, Oracle(model))
+    want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
+    st = np.zeros(32, np.uint64)
+    got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, big_slots=64, stats=st, **shape)
+    _same(got, want)
+    assert st[27] > 0  # jobs went through the servers
+
+
 def test_search_that_exhausts_its_scratch_starts_over_in_a_large_slot():
     """With 512 entries of scratch per lane many searches of this tree run out; each takes one of the launch's large slots (8x)
     and starts over inside the same launch.  Records as with ample scratch; with too few slots the rest report status 3."""
