@@ -41,7 +41,12 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nseq", type=int, default=int(os.environ.get("MAPLE_BENCH_NSEQ", 100000)))
     ap.add_argument("--round", default=os.environ.get("MAPLE_BENCH_ROUND", "deep"), choices=["fast", "deep"])
+    ap.add_argument("--workload", default=os.environ.get("MAPLE_BENCH_WORKLOAD", "search"), choices=["search", "place"],
+                    help="search: one SPR search round (the headline); place: one batch of new samples placed on the frozen tree "
+                         "(findBestParentForNewSample, BASELINE.json config 5 shape)")
+    ap.add_argument("--new-samples", type=int, default=int(os.environ.get("MAPLE_BENCH_NEW_SAMPLES", 50000)), help="--workload place: samples per batch")
     ap.add_argument("--cpu-searches", type=int, default=1500, help="searches in the CPU sample")
+    ap.add_argument("--cpu-samples", type=int, default=400, help="--workload place: samples in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed side measurements reported under 'extra'")
     return ap.parse_args()
@@ -213,6 +218,25 @@ def callers_extra(args, d, eng, tree, d_nodes):
         rec = tree.search_records(o)
         out["search_round_" + other] = {"placements": int(rec["phase1"].sum()), "seconds": dt, "placements_per_s": float(rec["phase1"].sum()) / dt,
                                         "searched": int((rec["status"] == 0).sum()), "proposals": int((rec["placement"] >= 0).sum())}
+        # the CPU port on the same stop rules, same bounded sample as the headline's cpu_baseline
+        from oracle.oracle import Oracle
+        import numpy as np
+        orc = Oracle(d.model)
+        cores = orc.use_all_cores()
+        nodes_all = d_nodes.cpu().numpy()
+        sample = cpu_sample(nodes_all, args.cpu_searches)
+        host = tree.arena.to_host()
+        ta, pd = oracle_tree(d, tree), params_dict(p2)
+        orc.search_batch(ta, host, pd, sample[:64], lazy_mode=1)
+        t0 = time.perf_counter()
+        ref = orc.search_batch(ta, host, pd, sample, lazy_mode=1)
+        cdt = time.perf_counter() - t0
+        pos = {int(nd): i for i, nd in enumerate(nodes_all)}
+        got = rec[[pos[int(nd)] for nd in sample]]
+        same = all(np.array_equal(got[f], ref[f]) for f in ("placement", "bestNode", "status", "phase1", "bLenTop", "bLenBottom", "bLenAppend"))
+        out["search_round_" + other]["cpu_baseline"] = {"value": float(ref["phase1"].sum()) / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                                                        "sample": "%d of the %d searches (evenly spread)" % (len(sample), len(nodes_all)),
+                                                        "gpu_matches_oracle_on_sample": bool(same)}
     except Exception as e:
         out["search_round_error"] = repr(e)[:300]
     try:
@@ -238,23 +262,237 @@ def callers_extra(args, d, eng, tree, d_nodes):
 
 
 def placement_extra(args):
-    """Side measurement, outside every timed region and in its own processes (a failure there cannot take the headline down):
-    maple_place_batch (findBestParentForNewSample for a batch of new samples on the same frozen tree) with the
-    one-sample-per-thread kernel and the one-sample-per-warp kernels, records compared.  scripts/time_place.py does the work."""
-    out = {}
-    for key, variants in (("thread_vs_warp", "0,1"), ("thread_vs_warp_parallel_replay", "0,3")):
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "time_place.py"), str(args.nseq), "4000", variants],
-                               capture_output=True, text=True, timeout=240, cwd=ROOT)
-            got = [ln for ln in r.stdout.splitlines() if ln.startswith("PLACE_JSON ")]
-            out[key] = json.loads(got[-1][len("PLACE_JSON "):]) if got else {"error": (r.stderr or r.stdout)[-400:]}
-        except Exception as e:  # timeout included
-            out[key] = {"error": repr(e)[:400]}
+    """Side measurement, outside every timed region and in its own process (a failure there cannot take the headline down): the
+    placement workload of this file (`--workload place`: maple_place_batch = findBestParentForNewSample for a batch of new samples
+    on the same frozen tree) with a smaller batch; its JSON line is embedded as it is."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "place", "--nseq", str(args.nseq), "--new-samples", "20000",
+                            "--steps", "2", "--warmup", "1", "--cpu-samples", "200"], capture_output=True, text=True, timeout=400, cwd=ROOT)
+        got = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        return json.loads(got[-1]) if got else {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # timeout included
+        return {"error": repr(e)[:400]}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# --workload place: a batch of new samples placed on the frozen tree (findBestParentForNewSample, :7912; the reference's own
+# batch form is process_chunk under joblib, :11190-11287)
+PLACE_METRIC = "new_sample_candidate_placements_per_sec"
+
+
+def place_workload_name(args):
+    return ("synthetic 29903-bp, frozen tree of %d seqs (UNREST+rateVariation), %d new samples (tips with one extra substitution) placed "
+            "with findBestParentForNewSample, non-strict stop rules" % (args.nseq, args.new_samples))
+
+
+def new_samples(d, k, seed=3):
+    """k new samples: existing tips with one extra substitution in their first long reference run (so that they are not simply
+    absorbed as minor sequences)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in rng.choice(len(d.tip_lists), min(k, len(d.tip_lists)), replace=False):
+        gl, new, pos, done = d.tip_lists[i], [], 0, False
+        for e in gl:
+            end = e[1] if e[0] in (4, 5) else pos + 1
+            if not done and e[0] == 4 and end - pos > 40:
+                mid = pos + 20
+                ref = int(d.model.refIdx[mid])
+                new += [(4, mid), ((ref + 1 + int(rng.integers(3))) % 4, ref), (4, end)]
+                done = True
+            else:
+                new.append(e)
+            pos = end
+        out.append(new)
     return out
+
+
+def place_params_dict(lRef):
+    L = math.log(lRef)
+    return {"strictStopRules": 0, "allowedFails": 5, "deeperSearchForLongBranches": 0, "onlyFindIdentical": 0,
+            "thresholdLogLK": 18.0 * L, "thresholdLogLKoptimization": 1.0 * L, "thresholdLogLKconsecutivePlacement": 1.0,
+            "effectivelyNon0BLen": 1.0 / (10 * lRef), "BLenThresholdDeeperSearch": (L + 5) / lRef, "oneMutBLen": 1.0 / lRef}
+
+
+def run_place_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from maple_b200.genome_list import pack_lists
+    d, orc, ta, host, nodes, setup_s = build_problem_cpu(args)
+    cores = orc.use_all_cores()
+    samples = new_samples(d, args.new_samples)
+    sub = samples[:: max(1, len(samples) // args.cpu_samples)][: args.cpu_samples]
+    packed = pack_lists(sub, d.model.lRef, d.model.usingErrorRate)
+    pd = place_params_dict(d.model.lRef)
+    orc.place_batch(ta, host, pd, pack_lists(sub[:16], d.model.lRef, d.model.usingErrorRate))
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        rec = orc.place_batch(ta, host, pd, packed)
+        tot += int(rec["phase1"].sum())
+    dt = time.perf_counter() - t0
+    val = tot / dt
+    print(json.dumps({
+        "impl": "reference", "metric": PLACE_METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": place_workload_name(args), "nseq": args.nseq, "samples_per_step": len(sub), "placements_per_step": tot // args.steps,
+                   "samples_per_s": len(sub) * args.steps / dt, "setup_s": setup_s},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d of the %d new samples, oracle/maple_oracle.c placement (C, OpenMP on %d threads)" % (len(sub), len(samples), cores)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_place(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from maple_b200 import capi
+    from maple_b200.genome_list import pack_lists
+    from maple_b200.sharding import all_gather_raw
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: maple_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d, eng, tree, nodes, setup_s = build_problem(args, local)
+    dev = eng.device
+    samples = new_samples(d, args.new_samples)
+    mine = samples[rank::world]  # strong scaling: the tree on every GPU, the samples dealt round-robin (the reference's joblib chunks, :11280)
+    packed = pack_lists(mine, d.model.lRef, d.model.usingErrorRate)
+    pp = capi.PlaceParams()
+    for k, v in place_params_dict(d.model.lRef).items():
+        setattr(pp, k, v)
+    n_total = len(samples)
+
+    def gather(out):
+        if world > 1:
+            all_gather_raw(out, n_total, world)
+
+    ids, mark = tree.stage_samples(packed)
+    for _ in range(args.warmup):
+        out = tree.place_staged(ids, pp)
+        gather(out)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:
+            time.sleep(0.05)
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = eng.launches
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        out = tree.place_staged(ids, pp)
+        ev[k][1].record()
+        gather(out)
+        ev[k][2].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launches - l0
+    step_ms = sum(a.elapsed_time(z) for a, _, z in ev)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / args.steps
+    rec = tree.place_records(out)
+    tree.release_samples(mark)
+    cand = torch.tensor([int(rec["phase1"].sum()), int((rec["status"] == 0).sum()), int((rec["status"] == 1).sum()), int((rec["status"] >= 2).sum())],
+                        dtype=torch.int64, device=dev)
+    tmax = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cand)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    cand_total, placed, absorbed, failed = (int(x) for x in cand.tolist())
+    total_ms = float(tmax.item())
+    value = cand_total * args.steps / (total_ms / 1e3)
+    # ---- e2e: the packed sample lists come from host memory every step, the records go back to the host
+    h_out = torch.empty((len(mine), 48), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ids2, mark2 = tree.stage_samples(packed)
+        o = tree.place_staged(ids2, pp)
+        gather(o)
+        h_out.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+        _ = int(h_out[0, 0])
+        tree.release_samples(mark2)
+    e2e_dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    A, n = tree.arena, tree.n
+    tot_lists = slice(3 * n, 4 * n)
+    have = A.key_start[tot_lists] >= 0
+    mean_tot_bytes = float((A.nkeys[tot_lists][have].double() * 4 + A.npay[tot_lists][have].double() * 8).mean().item()) + 16
+    sample_bytes = float(packed.nkeys.mean() * 4 + packed.npay.mean() * 8) + 16
+    alg_bytes = cand_total / world * mean_tot_bytes + len(mine) * (sample_bytes + 48)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    h2d = int(packed.key.nbytes + packed.pay.nbytes + packed.key_start.nbytes * 2 + packed.nkeys.nbytes * 2)
+    line = {
+        "metric": PLACE_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": place_workload_name(args), "nseq": args.nseq, "nodes": tree.n, "samples_per_step": n_total,
+                   "placements_per_step": cand_total, "samples_per_s": n_total * args.steps / (total_ms / 1e3), "placed": placed,
+                   "absorbed_as_minor": absorbed, "failed": failed, "setup_s": setup_s, "l2": "flushed between timed iterations (160 MB memset)",
+                   "kernel_variant": capi.DEFAULT_PLACE_VARIANT,
+                   "parallelism": "whole tree on every GPU; samples dealt round-robin to %d GPU(s); one NCCL all-gather of the 48-byte records" % world},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": cand_total / float(e2e_dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(len(mine) * 48),
+                "samples_per_s": n_total / float(e2e_dt.item()), "note": "packed sample lists from host memory, staged in the arena, records out, per rank"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "k_place_samples_warp_mat", "kernel_ms": kern_ms, "alg_bytes_per_launch": int(alg_bytes),
+                     "mean_mid_branch_list_bytes": round(mean_tot_bytes, 1),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle.oracle import Oracle
+        host = tree.arena.to_host()
+        orc = Oracle(d.model)
+        cores = orc.use_all_cores()
+        step_ = max(1, len(samples) // args.cpu_samples)
+        sub = samples[::step_][: args.cpu_samples]
+        sp_ = pack_lists(sub, d.model.lRef, d.model.usingErrorRate)
+        ta, pd = oracle_tree(d, tree), place_params_dict(d.model.lRef)
+        orc.place_batch(ta, host, pd, pack_lists(sub[:16], d.model.lRef, d.model.usingErrorRate))
+        t0 = time.perf_counter()
+        ref = orc.place_batch(ta, host, pd, sp_)
+        cdt = time.perf_counter() - t0
+        got = rec[::step_][: args.cpu_samples]
+        same = all(np.array_equal(got[f], ref[f]) for f in ("bestNode", "status", "phase1", "missedMinors", "bLenTop", "bLenBottom", "bLenAppend"))
+        with np.errstate(invalid="ignore"):
+            diff = np.nanmax(np.abs(got["bestScore"] - ref["bestScore"]))
+        line["cpu_baseline"] = {"value": float(ref["phase1"].sum()) / cdt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "samples_per_s": len(sub) / cdt,
+                                "sample": "%d of the %d new samples (evenly spread), %d candidate branches, oracle/maple_oracle.c placement "
+                                          "(C, OpenMP)" % (len(sub), len(samples), int(ref["phase1"].sum())),
+                                "gpu_matches_oracle_on_sample": bool(same), "max_abs_score_diff": float(diff)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    if args.workload == "place":
+        return run_place_reference(args) if args.impl == "reference" else run_place(args)
     if args.impl == "reference":
         return run_reference(args)
     import numpy as np

@@ -210,12 +210,11 @@ typedef struct {
 int maple_place_batch(maple_ctx* ctx, const maple_place_params* p, int64_t n, const int32_t* sampleLists, maple_place_result* out,
                       int32_t scratch_keys_per_sample, void* stream);
 
-/* Which kernel maple_place_batch launches: 0 (default) = one sample per thread, the straight-line walk; 1 = one sample per
+/* Which kernel maple_place_batch launches (default 3): 0 = one sample per thread, the straight-line walk; 1 = one sample per
  * warp: windows of the pre-order scored one node per lane, leaf comparisons one per lane, refinement entries one per lane
  * (a few rare shapes run the straight-line walk inside that kernel; batches on trees with MAT mutations or with
  * --deeperSearchForLongBranches are launched on variant 0, which is the faster one for them); 2 = variant 1 with MAT trees
- * covered: lane 0 walks the part of the tree above mutation-carrying nodes, every mutation-free subtree is scanned by the warp
- * (checked against the reference's recorded placements with its lanes emulated on the host; not yet run on hardware);
+ * covered: lane 0 walks the part of the tree above mutation-carrying nodes, every mutation-free subtree is scanned by the warp;
  * 3 = variant 2 with the window bookkeeping in parallel form (prefix maximum + three pointer-jumping passes instead of the
  * one-lane replay; same checks, same status).  Same results; a sample that exhausts its scratch reports status 3 in every variant. */
 int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant);

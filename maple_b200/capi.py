@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAPLE_B200_LIB") or os.path.join(HERE, "libmaple_b200.so")
 
 MAPLE_F_USING_ERROR_RATE, MAPLE_F_ERROR_SITE_SPECIFIC, MAPLE_F_RATE_VARIATION = 1, 2, 4
+DEFAULT_PLACE_VARIANT = 3  # maple_place_batch: one sample per warp, MAT trees covered, parallel window replay
 MAPLE_MERGE_UPDOWN, MAPLE_MERGE_RETURN_LK = 1, 2
 
 _P, _I64, _I32, _D = C.c_void_p, C.c_int64, C.c_int32, C.c_double

@@ -68,7 +68,7 @@ struct maple_ctx {
     void* retryScratch = nullptr;  // node list + scratch of the on-device retry of overflowed searches
     size_t retryScratchBytes = 0;
     unsigned long long* retryCounters = nullptr;  // [0] overflowed searches, [1] work counter of the retry launch
-    int placeVariant = 0;   // 0 = one sample per thread (place.cuh), 1 = one sample per warp with windowed scans (place_scan.cuh)
+    int placeVariant = 3;   // 0 = one sample per thread (place.cuh), 1 = one sample per warp with windowed scans (place_scan.cuh), 2 = + MAT trees, 3 (default) = 2 with the parallel window replay
     int searchVariant = 0;  // 0 = state machine + warp-cooperative subtree scans (default), 1 = straight-line kernel, 2 = state machine only, 3 = scans with the queued-site appendProbNode and the node-by-node replay
     // device staging for the host-buffer entry point
     void* devStage = nullptr;
@@ -1005,6 +1005,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     if (scan2 && ctx->scanAllStaged && (size_t)ctx->scanMaxUnits * 16 + 64 <= (size_t)poolBytes / 2 && max_concurrent_searches == 0 &&
         ctx->numSMs >= 8 && ctx->lanesPerWarp <= 0) {
         fsmSMs = ctx->fsmSMs;
+        if (fsmSMs == 0) goto noService;
         // the strict rules of the fast round leave little to scan (most of the work is on the lanes), the deep rounds are nearly all scans
         if (fsmSMs < 0) fsmSMs = sp.strictTopologyStopRules ? ctx->numSMs / 2 : ctx->numSMs / 6;
         if (fsmSMs > ctx->numSMs - 4) fsmSMs = ctx->numSMs - 4;
@@ -1014,6 +1015,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         if ((int64_t)fsmSMs * warpsPerSM > wantWarps) fsmSMs = (int)((wantWarps + warpsPerSM - 1) / warpsPerSM);
         if (fsmSMs < 1) fsmSMs = 1;
     }
+noService:
     int lpw = 32;
     if (fsmSMs > 0) {
         lpw = 32;
@@ -1084,7 +1086,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     if (fsmSMs > 0) {
         unsigned cap = 1024;
         while (cap < 4 * owners) cap <<= 1;
-        const size_t bytes = 64 + (size_t)cap * 8 + owners * sizeof(ScanJob);
+        const size_t bytes = 1024 + (size_t)cap * 8 + owners * sizeof(ScanJob);
         if (bytes > ctx->queueBytes) {
             cudaFree(ctx->queueMem);
             ctx->queueMem = nullptr;
@@ -1094,12 +1096,12 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         }
         CK(cudaMemsetAsync(ctx->queueMem, 0, bytes, (cudaStream_t)stream));
         char* q = (char*)ctx->queueMem;
-        sq.head = (unsigned long long*)q;
-        sq.tail = sq.head + 1;
-        sq.doneSearches = sq.head + 2;
-        sq.ownerCounter = sq.head + 3;
-        sq.ring = (unsigned long long*)(q + 64);
-        sq.jobs = (ScanJob*)(q + 64 + (size_t)cap * 8);
+        sq.head = (unsigned long long*)q;  // every control word on a 256-byte line of its own: the servers poll head / tail
+        sq.tail = (unsigned long long*)(q + 256);
+        sq.doneSearches = (unsigned long long*)(q + 512);
+        sq.ownerCounter = (unsigned long long*)(q + 768);
+        sq.ring = (unsigned long long*)(q + 1024);
+        sq.jobs = (ScanJob*)(q + 1024 + (size_t)cap * 8);
         sq.cap = cap;
         sq.maxOwners = (int)owners;
     }

@@ -798,6 +798,8 @@ __device__ void scan_server_loop(const DevModel& m, const DevTree& t, const Sear
                                  uint32_t& mbarParity, unsigned long long* st, const ScanQueue& sq, int64_t n) {
     const unsigned FULL = 0xffffffffu;
     const int lane = int(threadIdx.x & 31);
+    unsigned idleNs = 500;  // an idle server backs off (up to 8 us between looks at the ring): thousands of warps poll two words
+    long long tk = st ? clock64() : 0;
     for (;;) {
         long long owner = -1;
         if (lane == 0) {
@@ -813,7 +815,17 @@ __device__ void scan_server_loop(const DevModel& m, const DevTree& t, const Sear
         }
         owner = __shfl_sync(FULL, owner, 0);
         if (owner == -2) break;
-        if (owner < 0) { spin_pause(300); continue; }
+        if (owner < 0) {
+            spin_pause(idleNs);
+            if (idleNs < 8000) idleNs <<= 1;
+            continue;
+        }
+        idleNs = 500;
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) st[29] += (unsigned long long)(now - tk);  // idle
+            tk = now;
+        }
         ScanJob* J = sq.jobs + owner;
         __threadfence();
         if (lane == 0) {  // the request, read past this SM's L1
@@ -834,6 +846,11 @@ __device__ void scan_server_loop(const DevModel& m, const DevTree& t, const Sear
             if (st) st[27] += 1;
         }
         __syncwarp();
+        if (st) {
+            const long long now = clock64();
+            if (lane == 0) st[28] += (unsigned long long)(now - tk);  // serving
+            tk = now;
+        }
     }
 }
 

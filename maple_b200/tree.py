@@ -493,33 +493,49 @@ class DeviceTree:
         return out
 
     # ------------------------------------------------------------------ findBestParentForNewSample for a batch (:7912, :11190-11287)
+    def stage_samples(self, samples: PackedLists):
+        """Append the tip genome lists of new samples to the arena as temporaries and bind the tree again (the arena's tables
+        moved).  Returns (device int32 ids, mark); give the mark to release_samples() when the batch is done."""
+        A, dev = self.arena, self.eng.device
+        n = len(samples)
+        mark = A.mark()
+        first = A.add_ids(n)
+        A.store_packed(np.arange(first, first + n, dtype=np.int64), samples)
+        self.prepare_search()
+        return torch.arange(first, first + n, dtype=torch.int32, device=dev), mark
+
+    def release_samples(self, mark):
+        self.arena.release(mark)
+        if getattr(self, "_bound_epoch", None) != self.arena.epoch:
+            self.prepare_search()
+
+    def place_staged(self, ids: torch.Tensor, params: "capi.PlaceParams", scratch_keys: int = 0) -> torch.Tensor:
+        """maple_place_batch on staged samples: raw records [n, 48 bytes] on the device (asynchronous)."""
+        eng, dev = self.eng, self.eng.device
+        out = torch.zeros((ids.numel(), 48), dtype=torch.uint8, device=dev)
+        rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), ids.numel(), _dp(ids), _dp(out), int(scratch_keys), eng._stream())
+        capi.check(eng.ctx, rc, "maple_place_batch")
+        return out
+
+    @staticmethod
+    def place_records(out: torch.Tensor) -> np.ndarray:
+        return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
+
     def place_samples(self, samples: PackedLists, params: "capi.PlaceParams", scratch_keys: int = 0) -> np.ndarray:
         """Place every tip genome list of `samples` (probVectTerminalNode output) on the frozen tree; returns records
-        (capi.PLACE_RESULT_FIELDS).  The tree is not modified; prepare_search() must have bound it."""
-        eng, dev, A = self.eng, self.eng.device, self.arena
-        n = len(samples)
-        mark = A.mark()  # the sample lists are temporaries of this batch: ids and storage are given back below
+        (capi.PLACE_RESULT_FIELDS).  The tree is not modified and the arena is left as it was found."""
+        eng, dev = self.eng, self.eng.device
+        ids, mark = self.stage_samples(samples)
         try:
-            first = A.add_ids(n)
-            A.store_packed(np.arange(first, first + n, dtype=np.int64), samples)
-            self.prepare_search()  # the arena's tables moved: bind again
-            ids = torch.arange(first, first + n, dtype=torch.int32, device=dev)
-
-            def run(which: torch.Tensor, keys: int) -> np.ndarray:
-                out = torch.zeros((which.numel(), 48), dtype=torch.uint8, device=dev)
-                rc = eng.lib.maple_place_batch(eng.ctx, C.byref(params), which.numel(), _dp(which), _dp(out), int(keys), eng._stream())
-                capi.check(eng.ctx, rc, "maple_place_batch")
-                return out.cpu().numpy().view(np.dtype(capi.PLACE_RESULT_FIELDS)).reshape(-1)
-
-            rec = run(ids, scratch_keys)
+            rec = self.place_records(self.place_staged(ids, params, scratch_keys))
             retry, keys = np.nonzero(rec["status"] == 3)[0], max(int(scratch_keys), 4096)
-            variant = getattr(eng, "place_variant", 0)
+            variant = getattr(eng, "place_variant", capi.DEFAULT_PLACE_VARIANT)
             try:
                 while retry.size and keys < (1 << 22):  # per-sample scratch (lists or the bestNodes table) exhausted: again with 8x
                     keys *= 8
                     if variant != 0:  # the retries go through the one-sample-per-thread kernel, whose whole scratch scales with `keys`
                         eng.set_place_variant(0)
-                    again = run(ids[torch.as_tensor(retry, device=dev)].contiguous(), keys)
+                    again = self.place_records(self.place_staged(ids[torch.as_tensor(retry, device=dev)].contiguous(), params, keys))
                     rec[retry] = again
                     retry = retry[again["status"] == 3]
             finally:
@@ -528,9 +544,7 @@ class DeviceTree:
             if retry.size:
                 raise capi.MapleError("%d samples still exhaust their scratch with %d entries (first: sample %d)" % (retry.size, keys, int(retry[0])))
         finally:
-            A.release(mark)
-            if getattr(self, "_bound_epoch", None) != A.epoch:
-                self.prepare_search()
+            self.release_samples(mark)
         return rec
 
     @staticmethod

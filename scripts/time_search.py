@@ -21,6 +21,8 @@ nodes = dirty_nodes(tree)
 tree.prepare_search()
 L = math.log(d.model.lRef)
 variants = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
+if len(sys.argv) > 5:
+    eng.set_scan_service(int(sys.argv[5]))
 rounds = sys.argv[4].split(",") if len(sys.argv) > 4 else ["fast", "deep"]
 for variant in variants:
   eng.set_search_variant(variant)
@@ -51,6 +53,8 @@ for variant in variants:
                   S[16], S[8] / max(S[12], 1), S[9] / max(S[13], 1), S[10] / max(S[14], 1), S[11] / max(S[15], 1), S[8], S[9], S[10], S[11]), flush=True)
         print("   scan jobs %d, nodes in their ranges %.3g, batches %.3g, lanes scored %.3g (%.1f / batch, window %.1f nodes), counted %.3g, phase-2 entries queued %d, windows replayed node by node %d" % (
             S[17], S[18], S[19], S[20], S[20] / max(S[19], 1), S[24] / max(S[19], 1), S[21], S[22], S[25]), flush=True)
+    if variant != 1 and S[27]:
+        print("   scan service: jobs posted (lane 0 only) %d, served %d, server warps serving %.1f warp-s, idle %.1f warp-s" % (S[26], S[27], S[28] / 1.9e9, S[29] / 1.9e9), flush=True)
     st = np.bincount(rec["status"], minlength=4)
     ph = rec["phase1"].sum()
     print("%s: %.1f ms, searches %d, status %s, phase1 %d (%.1f/search, max %d), %.3g cand/s, proposals %d" % (

@@ -129,7 +129,7 @@ class FakeLib:
         sks, sps, snk = np.ascontiguousarray(ks[ids]), np.ascontiguousarray(ps[ids]), np.ascontiguousarray(nkeys_all[ids])
         t = self._or_tree()
         keys = scratch_keys if scratch_keys > 0 else 4096
-        variant = getattr(self, "place_variant", 0)
+        variant = getattr(self, "place_variant", 3)  # the device default
         has_mut = self.tree[7] is not None and int(_arr(self.tree[7], self.tree[0] + 1, np.int32)[-1]) > 0
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         if variant == 0 or (variant == 1 and has_mut):

@@ -133,6 +133,9 @@ void or_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp,
 
 // One lane of k_spr_search_fsm (the default search kernel) with the warp scans switched off (search variant 2): the per-lane
 // control code (fsm_step, fsm_finish) and the co-walk service loop of the kernel, one search after the other.
+static long long* g_opCounts = nullptr;  // optional [n][5]: append, merge, blen, differ co-walks and control steps per search
+void hs_set_op_counts(long long* p) { g_opCounts = p; }
+
 void hs_search_batch_fsm(const DevModel* m, const OrTree* t, const SearchParams* sp, int64_t n, const int32_t* nodes, int64_t scratchKeys,
                          SearchResult* out) {
     const DevTree T = dev_tree(t);
@@ -172,6 +175,7 @@ void hs_search_batch_fsm(const DevModel* m, const OrTree* t, const SearchParams*
         s.topK = s.topP = 0;
         for (;;) {
             fsm_step(f, *m, T, *sp, s, stack.data(), stackCap, 0 /* no warp scans */);
+            if (g_opCounts) { g_opCounts[5 * i + 4]++; if (f.op >= OP_APPEND && f.op <= OP_DIFFER) g_opCounts[5 * i + f.op - 1]++; }
             if (f.op == OP_DONE) break;
             if (f.op == OP_APPEND) f.resD = f_append(*m, f.a1, f.a2, f.at1 != 0, f.ab1);
             else if (f.op == OP_MERGE) {
