@@ -510,19 +510,40 @@ def main():
     d, eng, tree, nodes, setup_s = build_problem(args, local)
     dev = eng.device
     p = round_params(args, d.model.lRef)
-    # strong scaling: every rank holds the whole tree; searches are dealt round-robin like coreNum[node]==corNum (:9619)
-    from maple_b200.sharding import all_gather_raw, shard_nodes
+    # strong scaling: every rank holds the whole tree.  First warm-up round: searches dealt round-robin like
+    # coreNum[node]==corNum (:9619).  From then on the deal follows what the previous round measured (per-search SM cycles,
+    # all-gathered once): cost-balanced shards, longest search first inside every shard (sharding.shard_nodes, DeviceTree.spr_search)
+    # -- a run has tens of rounds on a tree that hardly changes, so "the previous round" always exists after the first.
+    from maple_b200.sharding import all_gather_raw, shard_nodes, shard_positions
     mine = shard_nodes(nodes, rank, world)
     d_nodes = torch.as_tensor(mine, dtype=torch.int32, device=dev)
 
     def step(src_nodes):
         out = tree.spr_search(src_nodes, p)
         if world > 1:  # one collective per round: everybody gets every proposal
-            all_gather_raw(out, len(nodes), world)
+            all_gather_raw(out, len(nodes), world, per_rank)
         return out
 
-    for _ in range(args.warmup):
+    per_rank = (len(nodes) + world - 1) // world
+    cost = None
+    for w in range(max(args.warmup, 1)):
         out = step(d_nodes)
+        if w == 0 and world > 1:  # re-deal by measured cost
+            cyc = tree.search_cost[d_nodes.long()].clone()
+            pad = torch.zeros(per_rank, dtype=torch.int64, device=dev)
+            pad[: cyc.numel()] = cyc
+            allc = torch.empty(world * per_rank, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, pad)
+            allc = allc.cpu().numpy().reshape(world, per_rank)
+            cost = np.zeros(len(nodes), np.float64)
+            for r in range(world):
+                pos = shard_positions(len(nodes), r, world)
+                cost[pos] = allc[r, : len(pos)]
+            tree.search_cost[torch.as_tensor(nodes, dtype=torch.int64, device=dev)] = torch.as_tensor(cost, dtype=torch.int64, device=dev)
+            mine = shard_nodes(nodes, rank, world, cost)
+            d_nodes = torch.as_tensor(mine, dtype=torch.int32, device=dev)
+            from maple_b200.sharding import shard_sizes
+            per_rank = int(shard_sizes(len(nodes), world, cost).max())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -543,7 +564,7 @@ def main():
         out = tree.spr_search(d_nodes, p)
         ev[k][1].record()
         if world > 1:
-            all_gather_raw(out, len(nodes), world)
+            all_gather_raw(out, len(nodes), world, per_rank)
         ev[k][2].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -617,13 +638,13 @@ def main():
                    "searches_per_step": searched, "placements_per_step": cand_total, "proposals": proposals,
                    "scratch_overflows": overflowed, "arena_MB": round(tree.arena.used_bytes() / 1e6, 1), "setup_s": setup_s,
                    "l2": "flushed between timed iterations (160 MB memset)",
-                   "parallelism": "whole tree on every GPU; searches dealt round-robin to %d GPU(s); one NCCL all-gather of the "
-                                  "64-byte result records per round" % world},
+                   "parallelism": "whole tree on every GPU; searches dealt to %d GPU(s) in cost-balanced shards (the previous round's per-search "
+                                  "cycles), longest first inside a shard; one NCCL all-gather of the 64-byte result records per round" % world},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(len(mine) * 4), "d2h_bytes_per_step": int(len(mine) * 64),
                 "note": "pinned host node ids in, result records out, per rank"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_spr_search_fsm", "kernel_ms": kern_ms, "alg_bytes_per_launch": int(alg_bytes),
+                     "kernel": "k_spr_search_fsm<7,true>", "kernel_ms": kern_ms, "alg_bytes_per_launch": int(alg_bytes),
                      "mean_mid_branch_list_bytes": round(mean_tot_bytes, 1),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
     }

@@ -229,9 +229,9 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
 
 /* How maple_spr_search_batch (variant 0) divides the GPU: the CTAs on the first fsmSMs SMs own the searches (one per lane, their
  * merges / branch lengths / candidate scores near the pruning point run there) and post every subtree scan in a global-memory
- * slot; the CTAs of all other SMs do nothing but take scans from a ticket ring, run them and hand the results back.  -1 (default)
- * = chosen per launch from the stop rules (strict rules: half the SMs own, else a sixth), 0 = off: every warp scans for its own
- * lanes.  Tuning only: results do not depend on it. */
+ * slot; the CTAs of all other SMs do nothing but take scans from a ticket ring, run them and hand the results back.  0 (default)
+ * = off: every warp scans for its own lanes; -1 = chosen per launch from the stop rules (strict rules: half the SMs own, else a
+ * sixth).  Experimental (slower than the default on the measured rounds); results do not depend on it. */
 int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs);
 
 /* Subtrees of at least minNodes nodes are scanned by the whole warp (default 8; 0 = never).  Tuning only: results do not

@@ -151,6 +151,17 @@ def test_records_do_not_depend_on_the_batch():
     rec = tree.search_records(tree.spr_search(nodes[sub], p))
     eng.set_search_variant(0)
     assert rec.tobytes() == full[sub].tobytes()
+    # the scan service (searches owned by the CTAs of a few SMs, subtree scans served by all others), both stop-rule settings,
+    # and a second pass in the longest-first order the first pass measured
+    for fsm_sms in (12, -1):
+        eng.set_scan_service(fsm_sms)
+        for _ in range(2):
+            assert tree.search_records(tree.spr_search(nodes, p)).tobytes() == full.tobytes()
+    p_fast = search_params(d.model.lRef, True, 2, 6.0 * math.log(d.model.lRef))
+    with_service = tree.search_records(tree.spr_search(nodes, p_fast))
+    eng.set_scan_service(0)
+    assert tree.search_records(tree.spr_search(nodes, p_fast)).tobytes() == with_service.tobytes()
+    assert tree.search_records(tree.spr_search(nodes, p, schedule=False)).tobytes() == full.tobytes()
     # the proposals of a round can be applied in the reference's order: ascending improvement (:12312)
     from maple_b200.sharding import moves_from_records
     moves = moves_from_records(nodes, full)
