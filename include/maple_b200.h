@@ -234,6 +234,17 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
  * sixth).  Experimental (slower than the default on the measured rounds); results do not depend on it. */
 int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs);
 
+/* Dense scoring pass of maple_spr_search_batch (variant 0).  What a candidate branch scores against a pruned subtree
+ * (appendProbNode(probVectTotUp[node], removedPartials, ...), :7011/:7223) does not depend on the state of the walk, only whether
+ * the walk visits it does; and in a deep round a search visits most of the tree.  So before the searches run, one regular kernel
+ * scores every scorable node against the removed list of every search of the batch into a [searches x nodes] matrix of doubles
+ * in HBM, and the subtree scans of those searches only do the reference's bookkeeping on scores they read.  Same arithmetic, same
+ * bits.  Applies to trees without MAT mutations (the removed list is then the same for a whole search).
+ * mode: -1 (default) = when it applies and the stop rules are the non-strict ones of the deep rounds; 0 = never; 1 = whenever it
+ * applies.  maxBytes: HBM the matrix may take (0 = keep; default 64 GiB, and never more than half of what is free at the first
+ * allocation); searches beyond it scan the usual way.  Results do not depend on either. */
+int maple_ctx_set_dense_scoring(maple_ctx* ctx, int32_t mode, int64_t maxBytes);
+
 /* Subtrees of at least minNodes nodes are scanned by the whole warp (default 8; 0 = never).  Tuning only: results do not
  * depend on it. */
 int maple_ctx_set_scan_min_size(maple_ctx* ctx, int32_t minNodes);

@@ -39,6 +39,7 @@ SIGNATURES = {
     "maple_ctx_set_search_variant": (C.c_int, [_P, _I32]),
     "maple_ctx_set_scan_min_size": (C.c_int, [_P, _I32]),
     "maple_ctx_set_scan_service": (C.c_int, [_P, _I32]),
+    "maple_ctx_set_dense_scoring": (C.c_int, [_P, _I32, _I64]),
     "maple_search_stats": (C.c_int, [_P, _I32, _P]),
     "maple_launch_count": (_I64, [_P]),
 }

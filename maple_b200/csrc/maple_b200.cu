@@ -53,6 +53,7 @@ struct maple_ctx {
     uint4* scanArena = nullptr;
     ScanRec* scanRecs = nullptr;
     uint32_t scanMaxUnits = 0;    // largest scan-format list, 16-byte units
+    size_t scanNumLists = 0;      // lists that have a scan-format copy
     bool scanAllStaged = false;   // every probVectTotUp list has a scan-format copy
     // scan service (scan2.cuh: ScanQueue): SMs whose CTAs own the searches; the CTAs of all other SMs only serve subtree scans.
     // -1 = chosen per launch from the stop rules, 0 = off (every warp scans for its own lanes: the default -- measured on the
@@ -60,6 +61,12 @@ struct maple_ctx {
     int fsmSMs = 0;
     void* queueMem = nullptr;
     size_t queueBytes = 0;
+    // dense scoring pass (scan2.cuh: DenseScores): -1 = whenever it applies and the stop rules are the non-strict ones, 0 = never,
+    // 1 = whenever it applies.  The score matrix takes at most denseBudget bytes of HBM; searches beyond it scan the usual way.
+    int denseMode = -1;
+    size_t denseBudget = (size_t)64 << 30;
+    void* denseMem = nullptr;     // scores | removed-list copies | row tables | column table | counters
+    size_t denseBytes = 0;
     // per-thread scratch of the search kernel (owned by the context)
     void* searchScratch = nullptr;
     size_t searchScratchBytes = 0;
@@ -294,6 +301,77 @@ __global__ void __launch_bounds__(256) k_scan_nsa(const __grid_constant__ DevTre
     if (i < T.nNodes) scan_fill_nsa(T, recs, i);
 }
 
+// ---- dense scoring pass (scan2.cuh)
+// columns: compact index of the positions whose node is scored and has a scan-format copy.  One block; positions in chunks.
+__global__ void __launch_bounds__(1024) k_dense_cols(int nNodes, ScanRec* __restrict__ recs, int32_t* __restrict__ colPos, int32_t* __restrict__ nCols) {
+    __shared__ int warpSum[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int start = 0; start < nNodes; start += 1024) {
+        const int i = start + threadIdx.x;
+        const bool has = i < nNodes && (recs[i].flags & (SR_SCORED | SR_STAGED)) == (SR_SCORED | SR_STAGED);
+        const unsigned b = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) warpSum[wid] = __popc(b);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < wid; w++) before += warpSum[w];
+        int total = 0;
+        for (int w = 0; w < 32; w++) total += warpSum[w];
+        const int col = base + before + __popc(b & ((1u << lane) - 1u));
+        if (i < nNodes) recs[i].col = has ? col : -1;
+        if (has) colPos[col] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nCols = base;
+}
+
+__global__ void __launch_bounds__(128) k_dense_prepare(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
+                                                       const __grid_constant__ SearchParams sp, int64_t n, const int32_t* __restrict__ nodes,
+                                                       int maxRows, unsigned long long* rowCounter, int32_t* __restrict__ rowOf,
+                                                       int32_t* __restrict__ rowEntry, uint4* __restrict__ cArena, double* __restrict__ rowBLen) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dense_prepare_entry(sm, T, sp, i, nodes, maxRows, rowCounter, rowOf, rowEntry, cArena, rowBLen);
+}
+
+constexpr int kDenseThreads = 128;
+// persistent: every warp pulls (tile of 32 columns, block of kDenseCBlock rows) tasks; the numbers of rows and columns live on the device
+__global__ void __launch_bounds__(kDenseThreads, 3) k_dense_score(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T, int poolBytes,
+                                                                  const int32_t* __restrict__ nColsDev, const int32_t* __restrict__ colPos,
+                                                                  const unsigned long long* __restrict__ rowCounter, int maxRows,
+                                                                  const uint4* __restrict__ cArena, const double* __restrict__ rowBLen,
+                                                                  double* __restrict__ scores, long long stride, unsigned long long* taskCounter) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    extern __shared__ uint4 dynSmem[];
+    const int warpSmem = int(sizeof(DenseSmem) - sizeof(uint4)) + poolBytes;
+    DenseSmem& W = *reinterpret_cast<DenseSmem*>(reinterpret_cast<char*>(dynSmem) + (threadIdx.x >> 5) * warpSmem);
+    uint32_t parity = 0;
+#ifdef __CUDA_ARCH__
+    if ((threadIdx.x & 31) == 0) mbar_init(&W.mbar);
+#endif
+    __syncwarp();
+    const int nCols = *nColsDev;
+    const int nRows = (int)min((unsigned long long)maxRows, *rowCounter);
+    const long long nTiles = (nCols + 31) / 32, nBlocks = (nRows + kDenseCBlock - 1) / kDenseCBlock;
+    const long long nTasks = nTiles * nBlocks;
+    for (;;) {
+        long long task = 0;
+        if ((threadIdx.x & 31) == 0) task = (long long)atomicAdd(taskCounter, 1ULL);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= nTasks) break;
+        // consecutive tasks share the block of removed lists (L2) and take neighbouring tiles
+        const int blk = int(task / nTiles), tile = int(task % nTiles);
+        const int row0 = blk * kDenseCBlock, row1 = min(nRows, row0 + kDenseCBlock);
+        dense_score_task(sm, T, W, poolBytes, parity, tile, nCols, colPos, row0, row1, cArena, rowBLen, scores, stride);
+    }
+}
+
 // one SPR search per thread; threads pull the next pruned node from a global counter (searches differ ~10x in length)
 __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                const __grid_constant__ SearchParams sp, int64_t n,
@@ -333,7 +411,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
                                                                    int scanFlags, int poolBytes, unsigned long long* stats,
                                                                    const unsigned long long* nDev, const int32_t* outIndex, int lanesPerWarp,
                                                                    const __grid_constant__ BigScratch big, const __grid_constant__ ScanQueue sq,
-                                                                   int fsmSMs) {
+                                                                   int fsmSMs, const __grid_constant__ DenseScores ds) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -390,7 +468,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     StackE* stack = scrStack + tid * (size_t)stackCap;
     fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
                          lanesPerWarp, W, W2, mbarParity, big, int((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5),
-                         (nDev || sq.cap != 0) ? 0 : int(gridDim.x * (blockDim.x >> 5)), sq, ownerBase);
+                         (nDev || sq.cap != 0) ? 0 : int(gridDim.x * (blockDim.x >> 5)), sq, ownerBase, ds);
     }
 flush:
     if (stats) {
@@ -549,6 +627,8 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     if (const char* e = getenv("MAPLE_FSM_MINB")) ctx->fsmMinBlocks = atoi(e);
     if (const char* e = getenv("MAPLE_SCAN_OLD")) ctx->scanOldEnv = atoi(e) != 0;
     if (const char* e = getenv("MAPLE_FSM_SMS")) ctx->fsmSMs = atoi(e);
+    if (const char* e = getenv("MAPLE_DENSE")) ctx->denseMode = atoi(e);
+    if (const char* e = getenv("MAPLE_DENSE_GB")) ctx->denseBudget = (size_t)atoll(e) << 30;
     ctx->scanOld = ctx->scanOldEnv;
     if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 0 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 0; }
     if (const char* e = getenv("MAPLE_SCAN_REPLAY")) ctx->scanReplaySequential = strcmp(e, "sequential") == 0;
@@ -589,6 +669,7 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->scanArena);
     cudaFree(ctx->scanRecs);
     cudaFree(ctx->queueMem);
+    cudaFree(ctx->denseMem);
     delete ctx;
     return MAPLE_OK;
 }
@@ -917,6 +998,7 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
         CK(cudaMemcpy(hu.data(), ctx->scanUnits, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         uint64_t tot = 0;
         ctx->scanMaxUnits = 0;
+        ctx->scanNumLists = 0;
         ctx->scanAllStaged = true;
         bool fixUnits = false;
         for (size_t i = 0; i < n; i++) {
@@ -929,6 +1011,7 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
             }
             ho[i] = (uint32_t)tot;
             tot += u;
+            ctx->scanNumLists++;
             if (u > ctx->scanMaxUnits) ctx->scanMaxUnits = (uint32_t)u;
         }
         if (fixUnits) CK(cudaMemcpy(ctx->scanUnits, hu.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -973,7 +1056,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
-                               const unsigned long long*, const int32_t*, int, const BigScratch, const ScanQueue, int);
+                               const unsigned long long*, const int32_t*, int, const BigScratch, const ScanQueue, int, const DenseScores);
     // Register budget = resident warps.  __launch_bounds__(64, 7) makes ptxas settle on 128 registers with few spills, which lets
     // 8 CTAs (16 warps) share an SM: 3.1 s for the deep round at 100 k sequences against 4.4 s for the 168-register build
     // (12 warps) on the same box.  MAPLE_FSM_MINB=6 selects the latter for A/B runs.  (Register allocation of this kernel is
@@ -1084,6 +1167,7 @@ noService:
         big.counter = ctx->retryCounters + 2;
     }
     ScanQueue sq{};
+    DenseScores ds{};
     if (fsmSMs > 0) {
         unsigned cap = 1024;
         while (cap < 4 * owners) cap <<= 1;
@@ -1111,6 +1195,60 @@ noService:
                                                                               ctx->scanRecs);
         k_scan_nsa<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, ctx->scanRecs);
         ctx->launches += 2;
+        // ---- dense scoring pass: every scorable node against the removed list of every search that will run
+        const bool denseOn = (ctx->denseMode == 1 || (ctx->denseMode < 0 && !sp.strictTopologyStopRules)) && !ctx->treeHasMut &&
+                             !sp.deeperSearchForLongBranches && ctx->scanAllStaged;
+        if (denseOn) {
+            const size_t nN = (size_t)T.nNodes;
+            const long long stride = (long long)((ctx->scanNumLists + 31) & ~size_t(31));  // columns <= lists with a copy
+            size_t freeB = 0, totalB = 0;
+            CK(cudaMemGetInfo(&freeB, &totalB));
+            size_t budget = ctx->denseBudget;
+            if (ctx->denseBytes == 0 && budget > freeB / 2) budget = freeB / 2;  // first allocation: leave half of what is free
+            long long maxRows = stride > 0 ? (long long)(budget / ((size_t)stride * 8)) : 0;
+            if (maxRows > n) maxRows = n;
+            if (maxRows > 0) {
+                const size_t scoresB = ((size_t)maxRows * (size_t)stride * 8 + 255) & ~size_t(255);
+                const size_t cB = ((size_t)maxRows * kDenseCUnits * 16 + 255) & ~size_t(255);
+                const size_t tabB = (((size_t)n * 4 + (size_t)maxRows * 4 + (size_t)maxRows * 8 + nN * 4) + 255) & ~size_t(255);
+                const size_t need = scoresB + cB + tabB + 256;
+                if (need > ctx->denseBytes) {
+                    cudaFree(ctx->denseMem);
+                    ctx->denseMem = nullptr;
+                    ctx->denseBytes = 0;
+                    if (cudaMalloc(&ctx->denseMem, need) == cudaSuccess) ctx->denseBytes = need;
+                    else { ctx->denseMem = nullptr; (void)cudaGetLastError(); }
+                }
+                if (ctx->denseMem) {
+                    char* b = (char*)ctx->denseMem;
+                    double* scores = (double*)b;
+                    uint4* cArena = (uint4*)(b + scoresB);
+                    char* tb = b + scoresB + cB;
+                    double* rowBLen = (double*)tb;
+                    int32_t* rowOf = (int32_t*)(tb + (size_t)maxRows * 8);
+                    int32_t* rowEntry = rowOf + n;
+                    int32_t* colPos = rowEntry + maxRows;
+                    unsigned long long* counters = (unsigned long long*)(b + scoresB + cB + tabB);  // [0] rows, [1] tasks, [2] (int) columns
+                    CK(cudaMemsetAsync(counters, 0, 32, (cudaStream_t)stream));
+                    k_dense_cols<<<1, 1024, 0, (cudaStream_t)stream>>>(T.nNodes, ctx->scanRecs, colPos, (int32_t*)(counters + 2));
+                    k_dense_prepare<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (int)maxRows, counters, rowOf,
+                                                                                                 rowEntry, cArena, rowBLen);
+                    int densePerSM = 0;
+                    const int densePool = 14 * 1024;
+                    const size_t denseSmem = (kDenseThreads / 32) * (sizeof(DenseSmem) - sizeof(uint4) + densePool);
+                    CK(cudaFuncSetAttribute(k_dense_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)denseSmem));
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&densePerSM, k_dense_score, kDenseThreads, denseSmem));
+                    if (densePerSM < 1) densePerSM = 1;
+                    k_dense_score<<<ctx->numSMs * densePerSM, kDenseThreads, denseSmem, (cudaStream_t)stream>>>(
+                        ctx->model, T, densePool, (const int32_t*)(counters + 2), colPos, counters, (int)maxRows, cArena, rowBLen, scores, stride,
+                        counters + 1);
+                    ctx->launches += 3;
+                    ds.scores = scores;
+                    ds.rowOf = rowOf;
+                    ds.stride = stride;
+                }
+            }
+        }
     } else if ((ctx->searchVariant == 0 || ctx->searchVariant == 3) && T.order && ctx->scanMinSize > 0) {
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, sp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
@@ -1125,7 +1263,7 @@ noService:
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs);
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs, ds);
     ctx->launches++;
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
         // safety net: searches that found no large slot free are collected and re-run by one CTA that uses the same slots (free
@@ -1137,7 +1275,7 @@ noService:
             ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, big.key, big.pay, big.ais, big.stack, big.capK, big.capP, big.capA,
             stackCap, ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
-            ctx->retryCounters, retryIdx, 32, none, ScanQueue{}, 0);
+            ctx->retryCounters, retryIdx, 32, none, ScanQueue{}, 0, DenseScores{});
         ctx->launches += 2;
     }
     CK(cudaGetLastError());
@@ -1249,6 +1387,13 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
 int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs) {
     if (!ctx || fsmSMs < -1) return MAPLE_E_ARG;
     ctx->fsmSMs = fsmSMs;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_dense_scoring(maple_ctx* ctx, int32_t mode, int64_t maxBytes) {
+    if (!ctx || mode < -1 || mode > 1 || maxBytes < 0) return MAPLE_E_ARG;
+    ctx->denseMode = mode;
+    if (maxBytes > 0) ctx->denseBudget = (size_t)maxBytes;
     return MAPLE_OK;
 }
 

@@ -83,7 +83,7 @@ struct ScanRec {  // one per pre-order position, 32 bytes
     uint32_t off;     // scan-format list: offset in the scan arena, 16-byte units (valid with SR_STAGED)
     uint32_t cnt;     // 16-byte units: entries | payload << 16
     uint32_t flags;   // SN_ELIG | SN_TOT | SN_PUSHED | SN_INNER as in ScanNode, plus:
-    uint32_t pad;
+    int32_t col;      // dense scoring pass: column of this node's score in a search's row, -1 = none (not scored, or no copy)
 };
 constexpr uint32_t SR_STAGED = 16;  // a scan-format copy of probVectTotUp exists
 constexpr uint32_t SR_SCORED = 64;  // SN_ELIG && SN_TOT && SN_PUSHED: the walk scores this node when it reaches it
@@ -290,7 +290,7 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
 __device__ inline ScanRec scan_build_rec(const DevModel& m, const DevTree& T, double eff, int i, uint32_t units, uint4* arena) {
     ScanRec r;
     const int node = T.order[i];
-    r.node = node; r.size = 1; r.nsa = -1; r.depths = 0; r.off = 0; r.cnt = 0; r.flags = 0; r.pad = 0;
+    r.node = node; r.size = 1; r.nsa = -1; r.depths = 0; r.off = 0; r.cnt = 0; r.flags = 0; r.col = -1;
     if (node < 0 || T.pre[node] != i) {  // positions past the reachable nodes
         r.node = -1;
         return r;
@@ -344,6 +344,7 @@ struct ScanJob {  // filled by the lane that owns the search
     const double* remP;
     PathE2* gpath;
     uint32_t* qTop;
+    const double* scoreRow;  // dense scoring pass: the search's row of precomputed candidate scores, or nullptr
     // results
     double bestOut;
     int phase1, qN, newBest, err;
@@ -377,6 +378,7 @@ struct Scan2Smem {
     int size[kWin2];
     int failS[32];    // by rank: failedPasses handed down
     uint32_t offS[32], cntS[32];
+    int colS[32];     // by rank: column of the node's precomputed score (dense scoring pass), -1 = none
     short nsa[kWin2];  // window position of the nearest scored proper ancestor, or -(path index)-1
     unsigned char slotS[32];  // by rank: window position
     unsigned long long mbar;
@@ -412,6 +414,119 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
         : "memory");
 }
 #endif
+
+// ---- dense scoring pass -------------------------------------------------------------------------------------------------
+// In a deep round a search visits most of the tree (61 % of all (search, node) pairs at 100 000 sequences), and what a candidate
+// scores does not depend on the state of the walk -- only whether it is visited does.  So before the searches run, one regular
+// kernel scores EVERY scorable node against the removed list of EVERY search that will run (k_dense_score: each warp keeps 32
+// candidate lists in shared memory and sweeps a block of removed lists over them; same scan_walk, so the same bits), into a
+// [searches x nodes] matrix of doubles in HBM (43 GB at 100 000 sequences; searches beyond the memory budget simply do not get
+// a row).  The subtree scans of a search with a row then only do the bookkeeping: a window's scores are one coalesced read.
+// Applies when no list is re-referenced on the way (no MAT mutations), i.e. the removed list is the same for the whole search.
+struct DenseScores {
+    const double* scores;   // [maxRows][stride]
+    const int32_t* rowOf;   // per entry of the node list: its row, -1 = none
+    long long stride;       // doubles per row (columns rounded up to 32)
+};
+
+constexpr int kDenseCUnits = 64;  // 16-byte units reserved per removed-list copy (1 KB): entry units | total units in the first word pair
+
+struct DenseRowHeader {  // first 16 bytes of a removed-list copy
+    int32_t entUnits, units, isTip, pad;
+};
+
+// Per entry i of the node list: would startTopologyUpdatesParallel search it (:9646-9674)?  If so, and its removed list has a copy
+// that fits, it gets a row: the copy is built at cArena + row * kDenseCUnits.  One thread per entry (k_dense_prepare).
+__device__ inline void dense_prepare_entry(const DevModel& m, const DevTree& T, const SearchParams& sp, int64_t i, const int32_t* nodes, int maxRows,
+                                           unsigned long long* rowCounter, int32_t* rowOf, int32_t* rowEntry, uint4* cArena, double* rowBLen) {
+    rowOf[i] = -1;
+    const int node = nodes[i];
+    if (T.up[node] < 0) return;
+    const int parent = T.up[node];
+    const LRef vectUp = (T.child0[parent] == node) ? tree_list(T, 1, parent) : tree_list(T, 2, parent);
+    const LRef own = tree_list(T, 0, node);
+    if (!vectUp.k || !own.k) return;
+    const double bestCurrentLK = dev_append<true>(m, vectUp.k, vectUp.p, own.k, own.p, T.isTip[node] != 0, T.dist[node]);
+    if (!(bestCurrentLK < sp.thresholdTopologyPlacement || T.dist[node] != 0.0)) return;  // :9674
+    if (own.nk > 2 * (kDenseCUnits - 1) - 8) return;  // too long for the 1 KB slot: this search scans the usual way
+    const unsigned long long row = atomicAdd(rowCounter, 1ULL);
+    if (row >= (unsigned long long)maxRows) return;
+    uint4* slot = cArena + row * (size_t)kDenseCUnits;
+    const int entUnits = (own.nk + 1) >> 1;
+    const int capP = (kDenseCUnits - 1 - entUnits) * 2;
+    const int npC = scan_build_c(m, own.k, own.p, T.dist[node], reinterpret_cast<uint2*>(slot + 1), own.nk,
+                                 reinterpret_cast<double*>(slot + 1 + entUnits), capP);
+    DenseRowHeader h;
+    h.entUnits = entUnits; h.units = npC < 0 ? 0 : entUnits + ((npC + 1) >> 1); h.isTip = T.isTip[node] != 0; h.pad = 0;
+    *reinterpret_cast<DenseRowHeader*>(slot) = h;
+    rowBLen[row] = T.dist[node];
+    rowEntry[row] = int32_t(i);
+    if (npC >= 0) rowOf[i] = int32_t(row);  // (a copy that does not fit leaves its row unused)
+}
+
+constexpr int kDenseCBlock = 128;  // removed lists swept over a tile of candidates per task
+
+struct DenseSmem {          // per warp
+    uint4 cBuf[2][kDenseCUnits];
+    unsigned long long mbar;
+    uint32_t pad[2];
+    uint4 pool[1];          // the tile's candidate lists
+};
+
+// One task of k_dense_score: tile `tile` (32 consecutive columns) against rows [row0, row1).  colPos[c] = pre-order position of
+// column c.  Whole warp.
+__device__ inline void dense_score_task(const DevModel& m, const DevTree& t, DenseSmem& W, int poolBytes, uint32_t& mbarParity, int tile, int nCols,
+                                        const int32_t* colPos, int row0, int row1, const uint4* cArena, const double* rowBLen, double* scores,
+                                        long long stride) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = int(threadIdx.x & 31);
+    const int col = tile * 32 + lane;
+    const bool have = col < nCols;
+    uint32_t off = 0, cnt = 0;
+    if (have) {
+        const ScanRec* r = t.scan2 + colPos[col];
+        off = r->off;
+        cnt = r->cnt;
+    }
+    // stage the tile's lists: they are neighbours in the arena; what does not fit the pool is read where it lies
+    const uint32_t off0 = __shfl_sync(FULL, off, 0);
+    const uint32_t myEnd = off + (cnt & 0xffffu) + (cnt >> 16) - off0;
+    const unsigned fits = __ballot_sync(FULL, have && myEnd <= uint32_t(poolBytes >> 4));
+    const int nFit = fits == FULL ? 32 : __ffs(~fits) - 1;
+    const uint4* base = t.scanArena + off;
+    __syncwarp();
+#ifdef __CUDA_ARCH__
+    if (nFit > 0) {
+        const uint32_t endLast = __shfl_sync(FULL, off + (cnt & 0xffffu) + (cnt >> 16), nFit - 1);
+        if (lane == 0) bulk_load(W.pool, t.scanArena + off0, (endLast - off0) << 4, &W.mbar);
+        mbar_wait(&W.mbar, mbarParity);
+        mbarParity ^= 1u;
+        if (lane < nFit) base = W.pool + (off - off0);
+    }
+#endif
+    const uint2* eP = reinterpret_cast<const uint2*>(base);
+    const double* pP = reinterpret_cast<const double*>(base + (cnt & 0xffffu));
+    const unsigned mask = __ballot_sync(FULL, have);
+    // sweep the block of removed lists: copy k+1 lands in the other buffer while copy k is walked
+    auto load_c = [&](int row, int b) {
+        const uint4* src = cArena + (size_t)row * kDenseCUnits;
+        for (int u = lane; u < kDenseCUnits; u += 32) W.cBuf[b][u] = src[u];  // (a 1 KB slot: two 16-byte loads per lane)
+    };
+    load_c(row0, 0);
+    __syncwarp();
+    for (int row = row0; row < row1; row++) {
+        const int b = (row - row0) & 1;
+        if (row + 1 < row1) load_c(row + 1, b ^ 1);
+        const DenseRowHeader h = *reinterpret_cast<const DenseRowHeader*>(&W.cBuf[b][0]);
+        if (h.units > 0 && have) {
+            const uint2* eC = reinterpret_cast<const uint2*>(&W.cBuf[b][1]);
+            const double* pC = reinterpret_cast<const double*>(&W.cBuf[b][1 + h.entUnits]);
+            const double sc = scan_walk(m, eP, pP, eC, pC, h.isTip != 0, rowBLen[row], mask);
+            scores[(size_t)row * stride + col] = sc;
+        }
+        __syncwarp();
+    }
+}
 
 __device__ __forceinline__ double warp_max_incl_d(double v, int lane) {
 #pragma unroll
@@ -458,8 +573,9 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
     long long tk = st ? clock64() : 0;
     if (st && lane == 0) { st[17] += 1; st[18] += (unsigned long long)(end - pos); }
     // ---- the removed list in scan format, at the front of the pool: the same for every candidate of the job
+    const double* const scoreRow = J.scoreRow;  // dense scoring pass: the scores are there already, this job only keeps the books
     int cEntUnits = 0, cUnits = 0;  // 16-byte units of its entries / of the whole copy; cUnits == 0: it does not fit (at most half the pool)
-    if (lane == 0) {
+    if (lane == 0 && !scoreRow) {
         int nkC = 0;
         const int capE = poolBytes >> 4;  // half the pool at 8 bytes per entry
         while (nkC < capE && int(ld_cg(J.remK + nkC) >> 8) != m.lRef) nkC++;
@@ -471,6 +587,8 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
                                          reinterpret_cast<double*>(W.pool + cEntUnits), capP);
             if (npC >= 0) cUnits = cEntUnits + ((npC + 1) >> 1);
         }
+    }
+    if (lane == 0) {
         if (pathCap < 2) err = 3;
         else W.path[0] = PathE2{J.lastLK0, J.failed0, 0};
     }
@@ -478,7 +596,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
     cUnits = __shfl_sync(FULL, cUnits, 0);
     const bool cOk = cUnits > 0;
     err = __shfl_sync(FULL, err, 0);
-    if (remote && !cOk && !err) err = 4;
+    if (remote && !cOk && !scoreRow && !err) err = 4;
     __syncwarp();
     const uint4* const arena = t.scanArena;
     const int poolUnits = (poolBytes >> 4) - cUnits;
@@ -489,18 +607,19 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         // ---- window: positions pos .. pos+nWin-1, at most 32 of them scored, their lists within the pool
         int nWin = 0, nScore = 0;
         bool generic = !cOk;  // some list has no scan-format copy: the whole window is scored from the arena lists
+        const bool dense = scoreRow != nullptr;  // scores read from the search's row; a node without a column is scored from the arena lists
         bool dyn = false;
         for (int sweep = 0; sweep < kWin2 / 32 && pos + nWin < end && nScore < 32; sweep++) {
             const int w = nWin + lane, idx = pos + w;
             uint32_t flags = 0, off = 0, cnt = 0;
-            int size = 1, nsaCode = -1, rel = 0;
+            int size = 1, nsaCode = -1, rel = 0, col = -1;
             if (idx < end) {
                 const uint4* src4 = reinterpret_cast<const uint4*>(t.scan2 + idx);
                 const uint4 a4 = __ldg(src4), b4 = __ldg(src4 + 1);
                 const int node = int(a4.x), nsa = int(a4.z);
                 size = int(a4.y);
                 const int depth = int(a4.w & 0xffffu), nsaDepth = int(a4.w >> 16);
-                off = b4.x; cnt = b4.y; flags = b4.z;
+                off = b4.x; cnt = b4.y; flags = b4.z; col = int(b4.w);
                 // Two per-search exceptions to the static flags.  Neither occurs on the walks the state machine hands over (the
                 // children of the pruned node's parent are never inside a scanned subtree, and a job's root was pushed through an
                 // existing upper list), but if one did, the static ancestor links would be off: such a window is replayed node by node.
@@ -533,6 +652,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
                     W.slotS[rank] = (unsigned char)w;
                     W.offS[rank] = off;
                     W.cntS[rank] = cnt;
+                    W.colS[rank] = col;
                 }
             }
             if (__any_sync(FULL, lane < take && (flags & SR_SCORED) && !(flags & SR_STAGED))) generic = true;
@@ -542,7 +662,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         __syncwarp();
         // cut the window where its lists stop fitting the pool
         uint32_t myOff = 0, myCnt = 0, off0 = 0;
-        if (!generic && nScore > 0) {
+        if (!dense && !generic && nScore > 0) {
             if (lane < nScore) { myOff = W.offS[lane]; myCnt = W.cntS[lane]; }
             off0 = __shfl_sync(FULL, myOff, 0);
             const uint32_t myEnd = myOff + (myCnt & 0xffffu) + (myCnt >> 16) - off0;
@@ -557,7 +677,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         // ---- stage the lists: one bulk copy, completion on the mbarrier
         double sc = -INFINITY;
 #ifdef __CUDA_ARCH__
-        if (!generic && nScore > 0) {
+        if (!dense && !generic && nScore > 0) {
             const uint32_t endLast = __shfl_sync(FULL, myOff + (myCnt & 0xffffu) + (myCnt >> 16), nScore - 1);
             if (lane == 0) bulk_load(winPool, arena + off0, (endLast - off0) << 4, &W.mbar);
             mbar_wait(&W.mbar, mbarParity);
@@ -569,8 +689,9 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
             if (lane == 0) { st[23] += (unsigned long long)(now - tk); st[19] += 1; st[20] += nScore; st[24] += nWin; }
             tk = now;
         }
-        if (lane < nScore) {
-            if (!generic) {
+        if (lane < nScore && dense && W.colS[lane] >= 0) sc = __ldg(scoreRow + W.colS[lane]);
+        else if (lane < nScore) {
+            if (!generic && !dense) {
 #ifdef __CUDA_ARCH__
                 const uint4* base = winPool + (myOff - off0);
 #else
@@ -834,6 +955,7 @@ __device__ void scan_server_loop(const DevModel& m, const DevTree& t, const Sear
             L.best = ld_cg(&J->best); L.lastLK0 = ld_cg(&J->lastLK0); L.removedBLen = ld_cg(&J->removedBLen);
             L.isRemovedTip = ld_cg(&J->isRemovedTip); L.pathCap = ld_cg(&J->pathCap); L.qCap = ld_cg(&J->qCap);
             L.remK = ld_cg(&J->remK); L.remP = ld_cg(&J->remP); L.gpath = ld_cg(&J->gpath); L.qTop = ld_cg(&J->qTop);
+            L.scoreRow = ld_cg(&J->scoreRow);
         }
         __syncwarp();
         warp_scan_job2(m, t, sp, W, poolBytes, scanFlags, mbarParity, st, true);

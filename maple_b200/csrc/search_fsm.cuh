@@ -969,7 +969,9 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                                               SearchResult* __restrict__ out, ScratchD s, StackE* stack, int stackCap, unsigned long long* counter,
                                               long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
                                               const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity,
-                                              const BigScratch& big, int warpId, int totalWarps, const ScanQueue& sq, int ownerBase) {
+                                              const BigScratch& big, int warpId, int totalWarps, const ScanQueue& sq, int ownerBase,
+                                              const DenseScores& ds) {
+    const double* myRow = nullptr;  // dense scoring pass: the current search's row of precomputed candidate scores
     // Scan service (sq.cap != 0, SCAN2 only): a lane that needs a subtree scan posts the job in its slot sq.jobs[ownerBase + lane]
     // and waits for a warp of the serving SMs to run it; meanwhile the other lanes of this warp go on with their co-walks.
     const bool service = SCAN2 && sq.cap != 0;
@@ -1077,6 +1079,11 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
             } else i = atomicAdd(counter, 1ULL);
             if (i >= (unsigned long long)n) { stage = 3; f.op = OP_NONE; break; }
             node = nodes[i];
+            myRow = nullptr;
+            if (ds.rowOf) {
+                const int row = ds.rowOf[i];
+                if (row >= 0) myRow = ds.scores + (size_t)row * (size_t)ds.stride;
+            }
             c0 = clock64();
             r.placement = -1; r.bestNode = -1; r.status = 1; r.phase1 = 0;
             r.improvement = r.bestCurrentLK = r.bestScore = r.bLenTop = r.bLenBottom = r.bLenAppend = 0.0;
@@ -1133,6 +1140,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                 J->pathCap = int((size_t)(stackCap - f.spN) * sizeof(StackE) / sizeof(PathE2));
                 J->qTop = s.key + s.capK;
                 J->qCap = int(s.capK - s.topK) - 8;
+                J->scoreRow = myRow;
                 J->state = 1;
                 __threadfence();
                 const unsigned long long ticket = atomicAdd(sq.tail, 1ULL);
@@ -1159,6 +1167,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                     J.pathCap = int((size_t)(stackCap - f.spN) * sizeof(StackE) / sizeof(PathE2));
                     J.qTop = s.key + s.capK;
                     J.qCap = int(s.capK - s.topK) - 8;
+                    J.scoreRow = myRow;
                 }
                 __syncwarp();
                 warp_scan_job2(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st, false);

@@ -146,6 +146,11 @@ class MapleEngine:
         """SMs whose CTAs own the searches while all others only serve subtree scans (-1 = chosen per launch, 0 = off)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_scan_service(self.ctx, int(fsm_sms)), "maple_ctx_set_scan_service")
 
+    def set_dense_scoring(self, mode: int, max_bytes: int = 0):
+        """The dense scoring pass of the search (-1 = in deep rounds when it applies, 0 = never, 1 = whenever it applies) and the
+        HBM its score matrix may take (0 = keep the current limit)."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_dense_scoring(self.ctx, int(mode), int(max_bytes)), "maple_ctx_set_dense_scoring")
+
     def search_stats(self, enable: bool = True, read: bool = True):
         """Profiling counters of the search kernel (see scripts/time_search.py for their meaning)."""
         out = (C.c_uint64 * 32)() if read else None

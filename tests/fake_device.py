@@ -146,6 +146,9 @@ class FakeLib:
     def maple_ctx_set_scan_service(self, ctx, n):
         return 0
 
+    def maple_ctx_set_dense_scoring(self, ctx, mode, max_bytes):
+        return 0
+
     def maple_ctx_set_scan_min_size(self, ctx, n):
         return 0
 

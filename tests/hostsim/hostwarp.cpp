@@ -7,6 +7,7 @@
 
 #include "search_fsm.cuh"
 
+#include <algorithm>
 #include <vector>
 
 using namespace maple;
@@ -31,6 +32,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
                     const int32_t* npay, int32_t scanForm, int32_t scanMinSize, int32_t lanesPerWarp, int32_t poolBytes, int32_t scanFlags,
                     int32_t bigSlots /* large scratch slots (8x) for searches that exhaust theirs, 0 = none */,
                     int32_t ownerWarps /* scan service: warps that own searches ... */, int32_t serverWarps /* ... and warps that only serve scans; 0 = no service */,
+                    int32_t denseRows /* dense scoring pass: rows of the score matrix (searches that get one), 0 = off */,
                     SearchResult* out, unsigned long long* stats) {
     DevTree T;
     memset(&T, 0, sizeof T);
@@ -127,6 +129,41 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         sq.head = &qctl[0]; sq.tail = &qctl[1]; sq.doneSearches = &qctl[2]; sq.ownerCounter = &qctl[3];
         sq.ring = ring.data(); sq.jobs = jobs.data(); sq.cap = cap; sq.maxOwners = (int)owners;
     }
+    // dense scoring pass: what k_dense_cols, k_dense_prepare and k_dense_score do
+    DenseScores ds;
+    memset(&ds, 0, sizeof ds);
+    std::vector<int32_t> colPos(N), rowOf((size_t)n, -1), rowEntry((size_t)(denseRows > 0 ? denseRows : 1));
+    std::vector<double> rowBLen((size_t)(denseRows > 0 ? denseRows : 1)), scores;
+    std::vector<uint4> cArena((size_t)(denseRows > 0 ? denseRows : 1) * kDenseCUnits);
+    if (scanForm == 2 && denseRows > 0) {
+        int nCols = 0;
+        for (size_t i = 0; i < N; i++) {
+            const bool has = (recs[i].flags & (SR_SCORED | SR_STAGED)) == (SR_SCORED | SR_STAGED);
+            recs[i].col = has ? nCols : -1;
+            if (has) colPos[nCols++] = (int32_t)i;
+        }
+        unsigned long long rowCounter = 0;
+        for (int64_t i = 0; i < n; i++)
+            dense_prepare_entry(*m, T, *sp, i, nodes, denseRows, &rowCounter, rowOf.data(), rowEntry.data(), cArena.data(), rowBLen.data());
+        const int nRows = (int)std::min<unsigned long long>(rowCounter, (unsigned long long)denseRows);
+        const long long stride = (nCols + 31) & ~31;
+        scores.assign((size_t)nRows * stride + 1, NAN);
+        const int densePool = poolBytes > 2048 ? poolBytes : 2048;
+        std::vector<uint4> dsm((sizeof(DenseSmem) + (size_t)densePool + 64) / 16);
+        DenseSmem& DW = *reinterpret_cast<DenseSmem*>(dsm.data());
+        const int nTiles = (nCols + 31) / 32;
+        hostwarp::run_warps(1, [&](int) {
+            uint32_t parity = 0;
+            for (int row0 = 0; row0 < nRows; row0 += kDenseCBlock)
+                for (int tile = 0; tile < nTiles; tile++)
+                    dense_score_task(*m, T, DW, densePool, parity, tile, nCols, colPos.data(), row0, std::min(nRows, row0 + kDenseCBlock), cArena.data(),
+                                     rowBLen.data(), scores.data(), stride);
+        });
+        ds.scores = scores.data();
+        ds.rowOf = rowOf.data();
+        ds.stride = stride;
+        if (stats) stats[30] += (unsigned long long)nRows;
+    }
     hostwarp::run_warps(nWarps, [&](int w) {
         const int lane = int(threadIdx.x & 31);
         ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data() + warpSmem * w);
@@ -146,10 +183,10 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         StackE* stk = stack.data() + tid * (size_t)stackCap;
         if (scanForm == 2)
             fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
-                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase);
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase, ds);
         else
             fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
-                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, 0);
+                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, 0, ds);
     });
     if (stats) {
         for (int i = 0; i < kNumSearchStats; i++) stats[i] += wst[i];

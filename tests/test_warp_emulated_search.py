@@ -102,6 +102,35 @@ def test_scan_service(name, shape):
     assert st[27] > 0  # jobs went through the servers
 
 
+@pytest.mark.parametrize("rows", [100000, 37])
+@pytest.mark.parametrize("rv,err,strict,ml", [(True, False, False, True), (True, True, False, False), (False, False, True, False)])
+def test_dense_scoring_pass(rv, err, strict, ml, rows):
+    """The dense scoring pass (scan2.cuh: DenseScores): every scorable node scored against the removed list of every search that
+    will run, before the searches; their subtree scans then only read.  With room for 37 rows the other searches scan as usual.
+    Records as the straight-line search.  Synthetic trees (rate variation, site-specific error model, both stop-rule settings): the
+    pass applies to trees without MAT mutations, and the reference's own trees carry them."""
+    import math
+    from maple_b200.synthetic import generate
+    from oracle.host_tree import build_tree_lists
+    d = generate(400, lRef=4000, mean_diffs=8.0, rate_variation=rv, error_model=err, site_specific_errors=err, seed=5, ml_like_blens=ml)
+    model = d.model
+    orc, hs, hw = Oracle(model), KernelSourceOnHost(model), WarpKernelOnHost(model)
+    lists, dist, isTip = build_tree_lists(orc, d.up, d.child0, d.child1, d.dist, d.root, d.tip_nodes, d.tip_lists, model.lRef,
+                                          int(model.usingErrorRate))
+    ta = {"up": d.up, "child0": d.child0, "child1": d.child1, "dist": dist, "isTip": isTip, "root": d.root}
+    L = math.log(model.lRef)
+    sp = {"strictTopologyStopRules": int(strict), "allowedFailsTopology": 2 if strict else 4, "deeperSearchForLongBranches": 0,
+          "thresholdLogLKtopology": (2.0 if strict else 14.0) * L, "thresholdTopologyPlacement": -0.1,
+          "thresholdLogLKoptimizationTopology": L, "thresholdLogLKconsecutivePlacement": 1.0,
+          "effectivelyNon0BLen": 1.0 / (10 * model.lRef), "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "defaultBLen": 0.000033}
+    nodes = np.array([i for i in range(len(d.up)) if d.up[i] >= 0], np.int32)[::3]
+    want = hs.search_batch(ta, lists, sp, nodes, scratch_keys=1 << 15)
+    st = np.zeros(32, np.uint64)
+    got = hw.search_batch_warp(ta, lists, sp, nodes, scan_form=2, big_slots=64, stats=st, dense_rows=rows, lanes_per_warp=6)
+    _same(got, want)
+    assert 0 < st[30] <= rows and st[21] > 1000
+
+
 def test_search_that_exhausts_its_scratch_starts_over_in_a_large_slot():
     """With 512 entries of scratch per lane many searches of this tree run out; each takes one of the launch's large slots (8x)
     and starts over inside the same launch.  Records as with ample scratch; with too few slots the rest report status 3."""
