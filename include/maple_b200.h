@@ -240,8 +240,8 @@ int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs);
  * scores every scorable node against the removed list of every search of the batch into a [searches x nodes] matrix of doubles
  * in HBM, and the subtree scans of those searches only do the reference's bookkeeping on scores they read.  Same arithmetic, same
  * bits.  Applies to trees without MAT mutations (the removed list is then the same for a whole search).
- * mode: -1 (default) = when it applies and the stop rules are the non-strict ones of the deep rounds; 0 = never; 1 = whenever it
- * applies.  maxBytes: HBM the matrix may take (0 = keep; default 64 GiB, and never more than half of what is free at the first
+ * mode: 0 (default) = never; -1 = when it applies and the stop rules are the non-strict ones of the deep rounds; 1 = whenever it
+ * applies.  Experimental: measured slower than scoring in place.  maxBytes: HBM the matrix may take (0 = keep; default 64 GiB, and never more than half of what is free at the first
  * allocation); searches beyond it scan the usual way.  Results do not depend on either. */
 int maple_ctx_set_dense_scoring(maple_ctx* ctx, int32_t mode, int64_t maxBytes);
 

@@ -61,9 +61,11 @@ struct maple_ctx {
     int fsmSMs = 0;
     void* queueMem = nullptr;
     size_t queueBytes = 0;
-    // dense scoring pass (scan2.cuh: DenseScores): -1 = whenever it applies and the stop rules are the non-strict ones, 0 = never,
-    // 1 = whenever it applies.  The score matrix takes at most denseBudget bytes of HBM; searches beyond it scan the usual way.
-    int denseMode = -1;
+    // dense scoring pass (scan2.cuh: DenseScores): -1 = whenever it applies and the stop rules are the non-strict ones, 0 = never
+    // (the default: at 100 000 sequences the pass takes 1.86 s and the searches that read it 0.9 s, against 2.2 s for searches that
+    // score in place -- see DESIGN.md), 1 = whenever it applies.  The score matrix takes at most denseBudget bytes of HBM;
+    // searches beyond it scan the usual way.
+    int denseMode = 0;
     size_t denseBudget = (size_t)64 << 30;
     void* denseMem = nullptr;     // scores | removed-list copies | row tables | column table | counters
     size_t denseBytes = 0;
@@ -96,6 +98,33 @@ static thread_local std::string g_err;
     } while (0)
 
 constexpr int kThreads = 128;
+
+// MAPLE_TIME_KERNELS=1: device time of the phases of maple_spr_search_batch, printed to stderr (synchronises; diagnostics only)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    PhaseTimer(cudaStream_t s) : on(getenv("MAPLE_TIME_KERNELS") != nullptr), st(s) { mark("start"); }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back({name, e});
+    }
+    void report() {
+        if (!on) return;
+        cudaEventSynchronize(ev.back().second);
+        fprintf(stderr, "[maple_b200]");
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            fprintf(stderr, " %s %.2f ms |", ev[i].first, ms);
+        }
+        fprintf(stderr, "\n");
+        for (auto& e : ev) cudaEventDestroy(e.second);
+    }
+};
 
 struct Arena {
     const uint32_t* key;
@@ -1168,6 +1197,7 @@ noService:
     }
     ScanQueue sq{};
     DenseScores ds{};
+    PhaseTimer timer((cudaStream_t)stream);
     if (fsmSMs > 0) {
         unsigned cap = 1024;
         while (cap < 4 * owners) cap <<= 1;
@@ -1195,6 +1225,7 @@ noService:
                                                                               ctx->scanRecs);
         k_scan_nsa<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, ctx->scanRecs);
         ctx->launches += 2;
+        timer.mark("scan-format copies");
         // ---- dense scoring pass: every scorable node against the removed list of every search that will run
         const bool denseOn = (ctx->denseMode == 1 || (ctx->denseMode < 0 && !sp.strictTopologyStopRules)) && !ctx->treeHasMut &&
                              !sp.deeperSearchForLongBranches && ctx->scanAllStaged;
@@ -1233,6 +1264,7 @@ noService:
                     k_dense_cols<<<1, 1024, 0, (cudaStream_t)stream>>>(T.nNodes, ctx->scanRecs, colPos, (int32_t*)(counters + 2));
                     k_dense_prepare<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (int)maxRows, counters, rowOf,
                                                                                                  rowEntry, cArena, rowBLen);
+                    timer.mark("dense columns + rows");
                     int densePerSM = 0;
                     const int densePool = 14 * 1024;
                     const size_t denseSmem = (kDenseThreads / 32) * (sizeof(DenseSmem) - sizeof(uint4) + densePool);
@@ -1243,6 +1275,7 @@ noService:
                         ctx->model, T, densePool, (const int32_t*)(counters + 2), colPos, counters, (int)maxRows, cArena, rowBLen, scores, stride,
                         counters + 1);
                     ctx->launches += 3;
+                    timer.mark("dense scoring");
                     ds.scores = scores;
                     ds.rowOf = rowOf;
                     ds.stride = stride;
@@ -1265,6 +1298,7 @@ noService:
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
                                                                              ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs, ds);
     ctx->launches++;
+    timer.mark("searches");
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
         // safety net: searches that found no large slot free are collected and re-run by one CTA that uses the same slots (free
         // again by then).  With none to re-run the two launches return at once.
@@ -1277,7 +1311,9 @@ noService:
             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
             ctx->retryCounters, retryIdx, 32, none, ScanQueue{}, 0, DenseScores{});
         ctx->launches += 2;
+        timer.mark("retry net");
     }
+    timer.report();
     CK(cudaGetLastError());
     return MAPLE_OK;
 }

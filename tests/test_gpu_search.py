@@ -151,12 +151,12 @@ def test_records_do_not_depend_on_the_batch():
     rec = tree.search_records(tree.spr_search(nodes[sub], p))
     eng.set_search_variant(0)
     assert rec.tobytes() == full[sub].tobytes()
-    # the dense scoring pass (on by default under these rules): off, then on with a matrix that only has room for some searches
-    eng.set_dense_scoring(0)
+    # the dense scoring pass: on, then on with a matrix that only has room for some of the searches
+    eng.set_dense_scoring(1)
     assert tree.search_records(tree.spr_search(nodes, p)).tobytes() == full.tobytes()
     eng.set_dense_scoring(1, 64 << 20)
     assert tree.search_records(tree.spr_search(nodes, p)).tobytes() == full.tobytes()
-    eng.set_dense_scoring(-1, 64 << 30)
+    eng.set_dense_scoring(0, 64 << 30)
     # the scan service (searches owned by the CTAs of a few SMs, subtree scans served by all others), both stop-rule settings,
     # and a second pass in the longest-first order the first pass measured
     for fsm_sms in (12, -1):
@@ -169,7 +169,7 @@ def test_records_do_not_depend_on_the_batch():
     assert tree.search_records(tree.spr_search(nodes, p_fast)).tobytes() == with_service.tobytes()
     eng.set_dense_scoring(1)  # the strict rules with the dense pass forced on
     assert tree.search_records(tree.spr_search(nodes, p_fast)).tobytes() == with_service.tobytes()
-    eng.set_dense_scoring(-1)
+    eng.set_dense_scoring(0)
     assert tree.search_records(tree.spr_search(nodes, p, schedule=False)).tobytes() == full.tobytes()
     # the proposals of a round can be applied in the reference's order: ascending improvement (:12312)
     from maple_b200.sharding import moves_from_records

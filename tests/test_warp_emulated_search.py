@@ -102,8 +102,7 @@ def test_scan_service(name, shape):
     assert st[27] > 0  # jobs went through the servers
 
 
-@pytest.mark.parametrize("rows", [100000, 37])
-@pytest.mark.parametrize("rv,err,strict,ml", [(True, False, False, True), (True, True, False, False), (False, False, True, False)])
+@pytest.mark.parametrize("rv,err,strict,ml,rows", [(True, False, False, True, 100000), (True, True, False, False, 37), (False, False, True, False, 100000)])
 def test_dense_scoring_pass(rv, err, strict, ml, rows):
     """The dense scoring pass (scan2.cuh: DenseScores): every scorable node scored against the removed list of every search that
     will run, before the searches; their subtree scans then only read.  With room for 37 rows the other searches scan as usual.
@@ -123,7 +122,7 @@ def test_dense_scoring_pass(rv, err, strict, ml, rows):
           "thresholdLogLKtopology": (2.0 if strict else 14.0) * L, "thresholdTopologyPlacement": -0.1,
           "thresholdLogLKoptimizationTopology": L, "thresholdLogLKconsecutivePlacement": 1.0,
           "effectivelyNon0BLen": 1.0 / (10 * model.lRef), "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "defaultBLen": 0.000033}
-    nodes = np.array([i for i in range(len(d.up)) if d.up[i] >= 0], np.int32)[::3]
+    nodes = np.array([i for i in range(len(d.up)) if d.up[i] >= 0], np.int32)[::5]
     want = hs.search_batch(ta, lists, sp, nodes, scratch_keys=1 << 15)
     st = np.zeros(32, np.uint64)
     got = hw.search_batch_warp(ta, lists, sp, nodes, scan_form=2, big_slots=64, stats=st, dense_rows=rows, lanes_per_warp=6)
