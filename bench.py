@@ -258,6 +258,24 @@ def callers_extra(args, d, eng, tree, d_nodes):
         out["fast_branch_length_sweep"]["logLK_after_sweep_and_rebuild"] = lk2
     except Exception as e:
         out["branch_length_sweep_error"] = repr(e)[:300]
+    try:  # the reference's default mode: one branch at a time, updatePartials after every change, all on the device (one lane)
+        tree.dist[:] = dist0
+        tree.d_dist.copy_(torch.from_numpy(tree.dist))
+        tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        upd, dirty = tree.optimize_branch_lengths_sequential(1.0 / (10 * d.model.lRef))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out["sequential_branch_length_sweep"] = {"branches": int(tree.n - 3), "updated": int(upd), "seconds": dt,
+                                                 "logLK_after_sweep": tree.tree_likelihood(),
+                                                 "note": "traverseTreeToOptimizeBranchLengths(fastPass=False) + updatePartials after every change, "
+                                                         "device-resident, sequential by definition"}
+        tree.dist[:] = dist0
+        tree.d_dist.copy_(torch.from_numpy(tree.dist))
+        tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
+    except Exception as e:
+        out["sequential_sweep_error"] = repr(e)[:300]
     return out
 
 

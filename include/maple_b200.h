@@ -234,6 +234,41 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
  * sixth).  Experimental (slower than the default on the measured rounds); results do not depend on it. */
 int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs);
 
+/* ---- lists that follow an edit of the tree -----------------------------------------------------------------------------
+ * The bound tree and arena, writable: the same DEVICE memory maple_lists_bind / maple_tree_bind were given (key, pay and the four
+ * per-list tables, dist), plus tails[2] = entries used in key / doubles used in pay (DEVICE; new lists are appended there and the
+ * tables re-pointed, the old lists stay where they are), the capacities of key and pay, and dirty[nNodes] (uint8, DEVICE; the
+ * reference's tree.dirty). */
+typedef struct {
+    uint32_t* key;
+    double* pay;
+    int64_t* key_start;
+    int64_t* pay_start;
+    int32_t* nkeys;
+    int32_t* npay;
+    int64_t* tails;
+    int64_t cap_keys, cap_pay;
+    double* dist;
+    uint8_t* dirty;
+} maple_tree_rw;
+
+/* updatePartials(tree, nodeList) (:5479-5815): nodeDirection = HOST int32 pairs (node, direction) in the order of the python
+ * list (the LAST pair is taken first, like nodeList.pop()); direction 2 = the change comes from the parent, 0 / 1 = from that
+ * child.  Runs the reference's work list as the reference does -- one lane, the same order, updateBLen (:5385) on an
+ * inconsistent zero-length branch included -- so the lists, lengths and dirty flags come out as the reference's.
+ * out_status (HOST): 0 done; 2 the reference would raise; 3 arena capacity (or scratch) exhausted: restore the tables, dist and
+ * tails from a copy taken before the call, grow the arena and call again.  Synchronises.  After it the tree must be bound again
+ * (maple_tree_bind) before maple_spr_search_batch / maple_place_batch. */
+int maple_update_partials(maple_ctx* ctx, const maple_tree_rw* rw, int32_t nEntries, const int32_t* nodeDirection, int32_t* out_status,
+                          void* stream);
+
+/* The loop of traverseTreeToOptimizeBranchLengths(tree, root, fastPass=False) (:8815-8886) below the root's children: every dirty
+ * branch re-estimated in the reference's visiting order, each accepted change followed by updatePartials before the next
+ * estimate (the reference's default, sequential mode).  The caller does the scan of the root's own two branches first
+ * (:8745-8814: maple_merge_batch(returnLK) + maple_prob_root_batch, then maple_update_partials twice).  out_updates (HOST) =
+ * lengths changed.  Status and re-binding as for maple_update_partials. */
+int maple_blen_sweep_sequential(maple_ctx* ctx, const maple_tree_rw* rw, int32_t* out_updates, int32_t* out_status, void* stream);
+
 /* Dense scoring pass of maple_spr_search_batch (variant 0).  What a candidate branch scores against a pruned subtree
  * (appendProbNode(probVectTotUp[node], removedPartials, ...), :7011/:7223) does not depend on the state of the walk, only whether
  * the walk visits it does; and in a deep round a search visits most of the tree.  So before the searches run, one regular kernel

@@ -40,6 +40,8 @@ SIGNATURES = {
     "maple_ctx_set_scan_min_size": (C.c_int, [_P, _I32]),
     "maple_ctx_set_scan_service": (C.c_int, [_P, _I32]),
     "maple_ctx_set_dense_scoring": (C.c_int, [_P, _I32, _I64]),
+    "maple_update_partials": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
+    "maple_blen_sweep_sequential": (C.c_int, [_P, _P, _P, _P, _P]),
     "maple_search_stats": (C.c_int, [_P, _I32, _P]),
     "maple_launch_count": (_I64, [_P]),
 }
@@ -50,6 +52,12 @@ class SearchParams(C.Structure):
                 ("reserved", _I32), ("thresholdLogLKtopology", _D), ("thresholdTopologyPlacement", _D),
                 ("thresholdLogLKoptimizationTopology", _D), ("thresholdLogLKconsecutivePlacement", _D),
                 ("effectivelyNon0BLen", _D), ("BLenThresholdDeeperSearch", _D), ("defaultBLen", _D)]
+
+
+class TreeRW(C.Structure):
+    """maple_tree_rw (include/maple_b200.h): the bound tree and arena, writable."""
+    _fields_ = [("key", _P), ("pay", _P), ("key_start", _P), ("pay_start", _P), ("nkeys", _P), ("npay", _P), ("tails", _P),
+                ("cap_keys", _I64), ("cap_pay", _I64), ("dist", _P), ("dirty", _P)]
 
 
 class PlaceParams(C.Structure):

@@ -18,6 +18,7 @@
 #include "place.cuh"
 #include "place_scan.cuh"
 #include "scan2.cuh"
+#include "update.cuh"
 
 using namespace maple;
 
@@ -67,6 +68,8 @@ struct maple_ctx {
     // searches beyond it scan the usual way.
     int denseMode = 0;
     size_t denseBudget = (size_t)64 << 30;
+    void* updateMem = nullptr;    // scratch of k_update_partials
+    size_t updateBytes = 0;
     void* denseMem = nullptr;     // scores | removed-list copies | row tables | column table | counters
     size_t denseBytes = 0;
     // per-thread scratch of the search kernel (owned by the context)
@@ -328,6 +331,27 @@ __global__ void __launch_bounds__(128) k_scan_build(const __grid_constant__ DevM
 __global__ void __launch_bounds__(256) k_scan_nsa(const __grid_constant__ DevTree T, ScanRec* __restrict__ recs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < T.nNodes) scan_fill_nsa(T, recs, i);
+}
+
+// updatePartials / the sequential branch-length sweep (update.cuh): one lane, the reference's order
+__global__ void __launch_bounds__(32) k_update_partials(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T, ArenaW a, double* dist,
+                                                        uint8_t* dirty, uint32_t* scrKey, double* scrPay, double* scrAis, unsigned capK, unsigned capP,
+                                                        unsigned capA, int32_t* work, int workCap, int32_t* walk, int walkCap,
+                                                        const int32_t* __restrict__ entries, int nEntries, int mode, int32_t* result) {
+    __shared__ DevModel sm;
+    stage_model(sm, gm);
+    if (threadIdx.x != 0) return;
+    UpdateState u;
+    u.m = &sm; u.t = T; u.a = a; u.dist = dist; u.dirty = dirty;
+    u.s.key = scrKey; u.s.pay = scrPay; u.s.ais = scrAis; u.s.capK = capK; u.s.capP = capP; u.s.capA = capA; u.s.topK = u.s.topP = 0; u.s.err = 0;
+    u.work = work; u.workCap = workCap; u.nWork = 0; u.err = 0;
+    int updates = 0;
+    if (mode == 0) {
+        for (int i = 0; i < nEntries; i++) up_push(u, entries[2 * i], entries[2 * i + 1]);
+        dev_update_partials(u);
+    } else updates = dev_sweep_sequential(u, walk, walkCap);
+    result[0] = u.err;
+    result[1] = updates;
 }
 
 // ---- dense scoring pass (scan2.cuh)
@@ -699,6 +723,7 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->scanRecs);
     cudaFree(ctx->queueMem);
     cudaFree(ctx->denseMem);
+    cudaFree(ctx->updateMem);
     delete ctx;
     return MAPLE_OK;
 }
@@ -1424,6 +1449,61 @@ int maple_ctx_set_scan_service(maple_ctx* ctx, int32_t fsmSMs) {
     if (!ctx || fsmSMs < -1) return MAPLE_E_ARG;
     ctx->fsmSMs = fsmSMs;
     return MAPLE_OK;
+}
+
+static int run_update(maple_ctx* ctx, const maple_tree_rw* rw, int mode, int32_t nEntries, const int32_t* entries, int32_t* out_updates,
+                      int32_t* out_status, void* stream) {
+    int rc = ready(ctx);
+    if (rc) return rc;
+    if (!ctx->haveTree) { ctx->err = "maple_update_partials: no tree bound (maple_tree_bind)"; return MAPLE_E_STATE; }
+    if (!rw || !rw->key || !rw->pay || !rw->key_start || !rw->pay_start || !rw->nkeys || !rw->npay || !rw->tails || !rw->dist || !rw->dirty ||
+        !out_status || nEntries < 0 || (nEntries > 0 && !entries))
+        return MAPLE_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DevTree T = ctx->tree;
+    T.key = rw->key; T.pay = rw->pay; T.keyStart = rw->key_start; T.payStart = rw->pay_start; T.nkeys = rw->nkeys; T.npay = rw->npay;
+    T.dist = rw->dist;
+    const size_t nN = (size_t)T.nNodes;
+    const unsigned capK = 1u << 16, capP = 6u << 16, capA = 1u << 16;
+    const int workCap = (int)(4 * nN + 64), walkCap = (int)(nN + 8);
+    const size_t need = (size_t)capP * 8 + (size_t)capA * 8 + (size_t)capK * 4 + (size_t)workCap * 8 + (size_t)walkCap * 4 + (size_t)nEntries * 8 + 256;
+    if (need > ctx->updateBytes) {
+        cudaFree(ctx->updateMem);
+        ctx->updateMem = nullptr;
+        ctx->updateBytes = 0;
+        CK(cudaMalloc(&ctx->updateMem, need));
+        ctx->updateBytes = need;
+    }
+    char* b = (char*)ctx->updateMem;
+    double* scrPay = (double*)b;
+    double* scrAis = scrPay + capP;
+    uint32_t* scrKey = (uint32_t*)(scrAis + capA);
+    int32_t* work = (int32_t*)(scrKey + capK);
+    int32_t* walk = work + 2 * (size_t)workCap;
+    int32_t* dEntries = walk + walkCap;
+    int32_t* result = dEntries + 2 * (size_t)nEntries + 2;
+    if (nEntries) CK(cudaMemcpyAsync(dEntries, entries, (size_t)nEntries * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    ArenaW a;
+    a.key = rw->key; a.pay = rw->pay; a.keyStart = rw->key_start; a.payStart = rw->pay_start; a.nkeys = rw->nkeys; a.npay = rw->npay;
+    a.tails = (long long*)rw->tails; a.capK = rw->cap_keys; a.capP = rw->cap_pay;
+    k_update_partials<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->model, T, a, rw->dist, rw->dirty, scrKey, scrPay, scrAis, capK, capP, capA, work, workCap,
+                                                          walk, walkCap, dEntries, nEntries, mode, result);
+    ctx->launches++;
+    int32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, result, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    *out_status = h[0];
+    if (out_updates) *out_updates = h[1];
+    ctx->scan2Ok = false;  // the lists changed: the scan-format copies are sized at maple_tree_bind -- bind again before searching
+    return MAPLE_OK;
+}
+
+int maple_update_partials(maple_ctx* ctx, const maple_tree_rw* rw, int32_t nEntries, const int32_t* nodeDirection, int32_t* out_status, void* stream) {
+    return run_update(ctx, rw, 0, nEntries, nodeDirection, nullptr, out_status, stream);
+}
+
+int maple_blen_sweep_sequential(maple_ctx* ctx, const maple_tree_rw* rw, int32_t* out_updates, int32_t* out_status, void* stream) {
+    return run_update(ctx, rw, 1, 0, nullptr, out_updates, out_status, stream);
 }
 
 int maple_ctx_set_dense_scoring(maple_ctx* ctx, int32_t mode, int64_t maxBytes) {

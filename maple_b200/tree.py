@@ -408,6 +408,108 @@ class DeviceTree:
             A.release(mark)
         return updates, dirty
 
+    # ------------------------------------------------------------------ updatePartials (:5479) and the sequential sweep (:8727)
+    def _run_rw(self, call, slack_keys: int = 1 << 18):
+        """Common part of the calls that edit the lists on the device (maple_tree_rw): room behind the arena's tails, a copy of
+        the tables and lengths to come back to if the room runs out (then the arena grows and the call is repeated), and the
+        bookkeeping afterwards (tails, epoch, host copy of dist)."""
+        eng, dev, A = self.eng, self.eng.device, self.arena
+        if getattr(self, "_bound_epoch", None) is None:
+            self.prepare_search()  # these calls read the tree arrays of the binding; the lists come with the call
+        if not hasattr(self, "d_dirty") or self.d_dirty.numel() != self.n:
+            self.d_dirty = torch.ones(self.n, dtype=torch.uint8, device=dev)
+        while True:
+            A._reserve(slack_keys, 6 * slack_keys)
+            keep = (A.key_start.clone(), A.pay_start.clone(), A.nkeys.clone(), A.npay.clone(), self.d_dist.clone(), self.d_dirty.clone())
+            tails = torch.tensor([A.key_tail, A.pay_tail], dtype=torch.int64, device=dev)
+            rw = capi.TreeRW(_dp(A.key), _dp(A.pay), _dp(A.key_start), _dp(A.pay_start), _dp(A.nkeys), _dp(A.npay), _dp(tails),
+                             int(A.key.numel()), int(A.pay.numel()), _dp(self.d_dist), _dp(self.d_dirty))
+            status, result = call(rw)
+            if status == 3:  # out of room: back to the state before the call, twice the room
+                A.key_start.copy_(keep[0]); A.pay_start.copy_(keep[1]); A.nkeys.copy_(keep[2]); A.npay.copy_(keep[3])
+                self.d_dist.copy_(keep[4]); self.d_dirty.copy_(keep[5])
+                slack_keys *= 4
+                if slack_keys > (1 << 28):
+                    raise capi.MapleError("updatePartials keeps running out of arena room")
+                continue
+            if status != 0:
+                raise capi.MapleError("the reference would raise inside updatePartials (inconsistent lists), status %d" % status)
+            t = tails.cpu().numpy()
+            A.key_tail, A.pay_tail = int(t[0]), int(t[1])
+            A.epoch = next(_EPOCH)  # the lists changed: whoever holds sizes derived from them (maple_tree_bind) must bind again
+            self.dist = self.d_dist.cpu().numpy().copy()
+            return result
+
+    def update_partials(self, node_list):
+        """updatePartials(tree, nodeList) (:5479): node_list = [(node, direction), ...] as the reference builds it (the last entry
+        is processed first); direction 2 = the change comes from the parent, 0 / 1 = from that child.  The lists are re-derived on
+        the device, in the reference's order; self.d_dirty (uint8 per node) receives the reference's dirty marks."""
+        eng = self.eng
+        ent = np.ascontiguousarray(np.array([(int(a), int(b)) for a, b in node_list], np.int32).reshape(-1))
+
+        def call(rw):
+            st = C.c_int32(0)
+            rc = eng.lib.maple_update_partials(eng.ctx, C.byref(rw), len(ent) // 2, ent.ctypes.data_as(C.c_void_p), C.byref(st), eng._stream())
+            capi.check(eng.ctx, rc, "maple_update_partials")
+            return int(st.value), None
+
+        return self._run_rw(call)
+
+    def optimize_branch_lengths_sequential(self, effectivelyNon0BLen: float, dirty=None):
+        """traverseTreeToOptimizeBranchLengths(tree, root, fastPass=False) (:8727), the reference's default mode: the root's two
+        branches by the scan of their split followed by updatePartials for each (:8745-8814), then every dirty branch in the
+        reference's visiting order, each accepted change followed by updatePartials before the next estimate -- the loop runs on
+        the device (maple_blen_sweep_sequential).  Lengths, dirty flags and the update count equal the reference's.
+        Returns (number of updated branches, dirty flags after the sweep)."""
+        from . import blen_sweep
+        eng, n, dev, A = self.eng, self.n, self.eng.device, self.arena
+        t64 = lambda a: torch.as_tensor(a, dtype=torch.int64, device=dev)  # noqa: E731
+        root = self.root
+        self.d_dirty = torch.ones(n, dtype=torch.uint8, device=dev) if dirty is None else torch.as_tensor(np.array(dirty, np.uint8), device=dev)
+        mutStart = getattr(self, "mutStart", None)
+        nmut = np.zeros(n, np.int64) if mutStart is None else np.diff(mutStart).astype(np.int64)
+        if self.child0[root] >= 0:
+            c = np.array([self.child0[root], self.child1[root]], np.int64)
+            cand = blen_sweep.root_split_candidates(float(self.dist[c[0]]), float(self.dist[c[1]]), eng.model.lRef, effectivelyNon0BLen)
+            if cand is not None:
+                mark = A.mark()
+                try:
+                    low = t64(c) + FAM_LOWER * n
+                    hit = np.nonzero(nmut[c] > 0)[0]
+                    if mutStart is not None:
+                        d_ms = torch.from_numpy(mutStart).to(dev)
+                        d_mu = torch.from_numpy(np.ascontiguousarray(self.mut.reshape(-1))).to(dev)
+                    if hit.size:
+                        low = low.clone()
+                        low[t64(hit)] = A.add_lists(eng.pass_branch_batch(low[t64(hit)], c[hit], np.ones(hit.size, np.uint8), d_ms, d_mu))
+                    k = len(cand[0])
+                    tips = self.d_isTip[t64(c)]
+                    r = eng.merge_batch(low[0].expand(k).int().contiguous(), torch.from_numpy(cand[0]).to(dev), tips[0].expand(k).contiguous(),
+                                        low[1].expand(k).int().contiguous(), torch.from_numpy(cand[1]).to(dev), tips[1].expand(k).contiguous(),
+                                        torch.full((k,), capi.MAPLE_MERGE_RETURN_LK, dtype=torch.uint8, device=dev))
+                    if bool((r.status != 0).any().item()):
+                        raise capi.MapleError("inconsistent root vector while scanning the root's branch lengths (the reference fails too, :8768)")
+                    trial = A.add_lists(r)
+                    if nmut[root] > 0:
+                        trial = A.add_lists(eng.pass_branch_batch(trial, np.full(k, root, np.int64), np.ones(k, np.uint8), d_ms, d_mu))
+                    cost = (r.lk + eng.prob_root_batch(trial.int())).cpu().numpy()
+                    b1, b2 = blen_sweep.choose_root_split(cost, cand[0], float(self.dist[c[0]]), float(self.dist[c[1]]))
+                finally:
+                    A.release(mark)
+                for child, new in ((int(c[0]), b1), (int(c[1]), b2)):  # :8788-8797 (both work lists name (root, 0), as the reference's do)
+                    self.dist[child] = new
+                    self.d_dist.copy_(torch.from_numpy(self.dist))
+                    self.update_partials([(child, 2), (root, 0)])
+
+        def call(rw):
+            st, upd = C.c_int32(0), C.c_int32(0)
+            rc = eng.lib.maple_blen_sweep_sequential(eng.ctx, C.byref(rw), C.byref(upd), C.byref(st), eng._stream())
+            capi.check(eng.ctx, rc, "maple_blen_sweep_sequential")
+            return int(st.value), int(upd.value)
+
+        updates = self._run_rw(call)
+        return updates, self.d_dirty.cpu().numpy().astype(bool)
+
     # ------------------------------------------------------------------ construction from existing lists
     @classmethod
     def from_lists(cls, engine: MapleEngine, up, child0, child1, dist, root, isTip, lists: PackedLists, mutStart=None, mut=None,

@@ -117,6 +117,28 @@ class FakeLib:
         from hostsim import lib
         return lib()
 
+    # ---- updatePartials / the sequential sweep: update.cuh on the host (tests/hostsim: hs_update)
+    def _update(self, rw_ref, mode, n_entries, entries, out_updates, out_status):
+        self.launches += 1
+        rw = rw_ref._obj
+        t = self._or_tree()
+        f = self._hs().hs_update
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 9 + [C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        upd = C.c_int32(0)
+        st = f(self.mp, C.addressof(t), rw.key, rw.pay, rw.key_start, rw.pay_start, rw.nkeys, rw.npay, rw.tails, rw.cap_keys, rw.cap_pay, rw.dist,
+               rw.dirty, mode, n_entries, entries, C.addressof(upd))
+        out_status._obj.value = st
+        if out_updates is not None:
+            out_updates._obj.value = upd.value
+        return 0
+
+    def maple_update_partials(self, ctx, rw, n_entries, entries, out_status, stream):
+        return self._update(rw, 0, n_entries, entries, None, out_status)
+
+    def maple_blen_sweep_sequential(self, ctx, rw, out_updates, out_status, stream):
+        return self._update(rw, 1, 0, None, out_updates, out_status)
+
     def maple_ctx_set_place_variant(self, ctx, variant):
         self.place_variant = variant
         return 0

@@ -7,6 +7,7 @@
 
 #include "place_scan.cuh"
 #include "search_fsm.cuh"
+#include "update.cuh"
 
 #include <vector>
 
@@ -320,6 +321,36 @@ void hs_place_batch_scan(const DevModel* m, const OrTree* t, const PlaceParams* 
         else if (matVariant) place_sample_warp_mat<false>(*m, T, *pp, in, X, ws, out[i]);
         else place_sample_warp(*m, T, *pp, in, X.w, ws, out[i]);
     }
+}
+
+// updatePartials (mode 0: the work list `entries`, pairs (node, direction), last pair first) or the sequential branch-length sweep
+// (mode 1) of update.cuh on host arrays: the arena is writable and has room behind its tails.  Returns the status (0 ok, 2 the
+// reference would raise, 3 capacity); *updates = lengths changed by the sweep.
+int hs_update(const DevModel* m, const OrTree* t, uint32_t* key, double* pay, int64_t* keyStart, int64_t* payStart, int32_t* nkeys, int32_t* npay,
+              long long* tails, long long capK, long long capP, double* dist, uint8_t* dirty, int mode, int nEntries, const int32_t* entries,
+              int32_t* updates) {
+    DevTree T = dev_tree(t);
+    T.key = key; T.pay = pay; T.keyStart = keyStart; T.payStart = payStart; T.nkeys = nkeys; T.dist = dist;
+    std::vector<int32_t> npay_(4 * (size_t)t->nNodes + 8, 0);
+    T.npay = npay ? npay : npay_.data();
+    UpdateState u;
+    u.m = m; u.t = T;
+    u.a.key = key; u.a.pay = pay; u.a.keyStart = keyStart; u.a.payStart = payStart; u.a.nkeys = nkeys; u.a.npay = const_cast<int32_t*>(T.npay);
+    u.a.tails = tails; u.a.capK = capK; u.a.capP = capP;
+    u.dist = dist; u.dirty = dirty;
+    const unsigned sK = 1u << 16, sP = 6u << 16, sA = 1u << 16;
+    std::vector<uint32_t> sk(sK + 64);
+    std::vector<double> sp(sP + 64), sa(sA);
+    u.s.key = sk.data(); u.s.pay = sp.data(); u.s.ais = sa.data(); u.s.capK = sK; u.s.capP = sP; u.s.capA = sA; u.s.topK = u.s.topP = 0; u.s.err = 0;
+    std::vector<int32_t> work(8 * (size_t)t->nNodes + 128), walk((size_t)t->nNodes + 8);
+    u.work = work.data(); u.workCap = (int)(work.size() / 2); u.nWork = 0; u.err = 0;
+    int n = 0;
+    if (mode == 0) {
+        for (int i = 0; i < nEntries; i++) up_push(u, entries[2 * i], entries[2 * i + 1]);
+        dev_update_partials(u);
+    } else n = dev_sweep_sequential(u, walk.data(), (int)walk.size());
+    if (updates) *updates = n;
+    return u.err;
 }
 
 int or_num_threads(void) { return 1; }
