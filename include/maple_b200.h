@@ -227,6 +227,11 @@ int maple_ctx_set_place_variant(maple_ctx* ctx, int32_t variant);
  * staged per lane, pointer-jumping replay)  (1-4: kept for A/B measurements and to test the alternative paths; same results). */
 int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
 
+/* Searches a warp of maple_spr_search_batch (variant 0) runs at a time: that many of its lanes own a search each, the subtree scans
+ * of all of them are executed by the whole warp one after the other.  0 (default) = chosen per launch from the number of
+ * searches (few searches -> few per warp, so that a long search does not share its warp).  Tuning only. */
+int maple_ctx_set_lanes_per_warp(maple_ctx* ctx, int32_t lanes);
+
 /* How maple_spr_search_batch (variant 0) divides the GPU: the CTAs on the first fsmSMs SMs own the searches (one per lane, their
  * merges / branch lengths / candidate scores near the pruning point run there) and post every subtree scan in a global-memory
  * slot; the CTAs of all other SMs do nothing but take scans from a ticket ring, run them and hand the results back.  0 (default)
@@ -284,7 +289,7 @@ int maple_ctx_set_dense_scoring(maple_ctx* ctx, int32_t mode, int64_t maxBytes);
  * depend on it. */
 int maple_ctx_set_scan_min_size(maple_ctx* ctx, int32_t minNodes);
 
-/* Profiling counters of the search kernel (32 uint64, meaning in DESIGN.md / scripts/time_search.py): enable != 0
+/* Profiling counters of the search kernel (40 uint64, meaning in DESIGN.md / scripts/time_search.py): enable != 0
  * switches collection on for later launches; out != NULL receives and resets the counters (synchronises). */
 int maple_search_stats(maple_ctx* ctx, int32_t enable, uint64_t* out);
 

@@ -68,6 +68,9 @@ struct maple_ctx {
     // searches beyond it scan the usual way.
     int denseMode = 0;
     size_t denseBudget = (size_t)64 << 30;
+    void* evalMem = nullptr;      // per-lane scratch slices of warp_eval_queue (search_fsm.cuh)
+    size_t evalBytes = 0;
+    bool evalQueueWarp = true;    // MAPLE_EVALQ=0: the owning lane evaluates its queued phase-2 entries itself (A/B)
     void* updateMem = nullptr;    // scratch of k_update_partials
     size_t updateBytes = 0;
     void* denseMem = nullptr;     // scores | removed-list copies | row tables | column table | counters
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
                                                                    int scanFlags, int poolBytes, unsigned long long* stats,
                                                                    const unsigned long long* nDev, const int32_t* outIndex, int lanesPerWarp,
                                                                    const __grid_constant__ BigScratch big, const __grid_constant__ ScanQueue sq,
-                                                                   int fsmSMs, const __grid_constant__ DenseScores ds) {
+                                                                   int fsmSMs, const __grid_constant__ DenseScores ds, const __grid_constant__ EvalScratch es) {
     __shared__ DevModel sm;
     __shared__ unsigned long long wst[kSearchThreads / 32][kNumSearchStats];
     unsigned long long* st = nullptr;  // per-warp counters (lane 0 adds), flushed to `stats` at the end
@@ -521,7 +524,8 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     StackE* stack = scrStack + tid * (size_t)stackCap;
     fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
                          lanesPerWarp, W, W2, mbarParity, big, int((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5),
-                         (nDev || sq.cap != 0) ? 0 : int(gridDim.x * (blockDim.x >> 5)), sq, ownerBase, ds);
+                         (nDev || sq.cap != 0) ? 0 : int(gridDim.x * (blockDim.x >> 5)), sq, ownerBase, ds, es,
+                         blockIdx.x * (size_t)blockDim.x + threadIdx.x);
     }
 flush:
     if (stats) {
@@ -681,6 +685,7 @@ int maple_ctx_create(maple_ctx** out, int device, int32_t lRef, const double roo
     if (const char* e = getenv("MAPLE_SCAN_OLD")) ctx->scanOldEnv = atoi(e) != 0;
     if (const char* e = getenv("MAPLE_FSM_SMS")) ctx->fsmSMs = atoi(e);
     if (const char* e = getenv("MAPLE_DENSE")) ctx->denseMode = atoi(e);
+    if (const char* e = getenv("MAPLE_EVALQ")) ctx->evalQueueWarp = atoi(e) != 0;
     if (const char* e = getenv("MAPLE_DENSE_GB")) ctx->denseBudget = (size_t)atoll(e) << 30;
     ctx->scanOld = ctx->scanOldEnv;
     if (const char* e = getenv("MAPLE_LANES_PER_WARP")) { ctx->lanesPerWarp = atoi(e); if (ctx->lanesPerWarp < 0 || ctx->lanesPerWarp > 32) ctx->lanesPerWarp = 0; }
@@ -724,6 +729,7 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->queueMem);
     cudaFree(ctx->denseMem);
     cudaFree(ctx->updateMem);
+    cudaFree(ctx->evalMem);
     delete ctx;
     return MAPLE_OK;
 }
@@ -1110,7 +1116,7 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     const size_t fsmSmem = (kSearchThreads / 32) * (size_t)(fixedPerWarp + poolBytes);
     using FsmKernel = void (*)(const DevModel, const DevTree, const SearchParams, int64_t, const int32_t*, SearchResult*, uint32_t*, double*, double*,
                                StackE*, unsigned, unsigned, unsigned, int, unsigned long long*, long long*, int, int, int, unsigned long long*,
-                               const unsigned long long*, const int32_t*, int, const BigScratch, const ScanQueue, int, const DenseScores);
+                               const unsigned long long*, const int32_t*, int, const BigScratch, const ScanQueue, int, const DenseScores, const EvalScratch);
     // Register budget = resident warps.  __launch_bounds__(64, 7) makes ptxas settle on 128 registers with few spills, which lets
     // 8 CTAs (16 warps) share an SM: 3.1 s for the deep round at 100 k sequences against 4.4 s for the 168-register build
     // (12 warps) on the same box.  MAPLE_FSM_MINB=6 selects the latter for A/B runs.  (Register allocation of this kernel is
@@ -1222,7 +1228,27 @@ noService:
     }
     ScanQueue sq{};
     DenseScores ds{};
+    EvalScratch es{};
     PhaseTimer timer((cudaStream_t)stream);
+    if (ctx->searchVariant != 1 && ctx->evalQueueWarp) {
+        // a slice per lane of the launch for the warp-wide evaluation of queued phase-2 entries: four merged lists of an
+        // evaluatePlacement (a few hundred entries) fit; an entry that does not is evaluated by the owning lane in its own scratch
+        es.capK = 1024; es.capP = 6 * 1024; es.capA = 1024;
+        const size_t perLane = (size_t)es.capK * 4 + (size_t)es.capP * 8 + (size_t)es.capA * 8;
+        const size_t needE = perLane * (size_t)threads + 256;
+        if (needE > ctx->evalBytes) {
+            cudaFree(ctx->evalMem);
+            ctx->evalMem = nullptr;
+            ctx->evalBytes = 0;
+            if (cudaMalloc(&ctx->evalMem, needE) == cudaSuccess) ctx->evalBytes = needE;
+            else { ctx->evalMem = nullptr; (void)cudaGetLastError(); }
+        }
+        if (ctx->evalMem) {
+            es.pay = (double*)ctx->evalMem;
+            es.ais = es.pay + (size_t)threads * es.capP;
+            es.key = (uint32_t*)(es.ais + (size_t)threads * es.capA);
+        }
+    }
     if (fsmSMs > 0) {
         unsigned cap = 1024;
         while (cap < 4 * owners) cap <<= 1;
@@ -1321,7 +1347,7 @@ noService:
                                                                              (long long*)out_cycles,
                                                                              (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
                                                                              ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs, ds);
+                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs, ds, es);
     ctx->launches++;
     timer.mark("searches");
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
@@ -1334,7 +1360,7 @@ noService:
             ctx->model, T, sp, (int64_t)retryCap, retryNodes, (SearchResult*)out, big.key, big.pay, big.ais, big.stack, big.capK, big.capP, big.capA,
             stackCap, ctx->retryCounters + 1, nullptr, (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes, nullptr,
-            ctx->retryCounters, retryIdx, 32, none, ScanQueue{}, 0, DenseScores{});
+            ctx->retryCounters, retryIdx, 32, none, ScanQueue{}, 0, DenseScores{}, EvalScratch{});
         ctx->launches += 2;
         timer.mark("retry net");
     }
@@ -1442,6 +1468,12 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
     if (!ctx || variant < 0 || variant > 4) return MAPLE_E_ARG;
     ctx->searchVariant = variant == 4 ? 0 : variant;
     ctx->scanOld = variant == 4 ? true : ctx->scanOldEnv;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_lanes_per_warp(maple_ctx* ctx, int32_t lanes) {
+    if (!ctx || lanes < 0 || lanes > 32) return MAPLE_E_ARG;
+    ctx->lanesPerWarp = lanes;
     return MAPLE_OK;
 }
 

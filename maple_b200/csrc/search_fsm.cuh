@@ -16,9 +16,9 @@
 
 namespace maple {
 
-constexpr int kNumSearchStats = 32;
+constexpr int kNumSearchStats = 40;
 
-enum FsmOp { OP_NONE = 0, OP_APPEND = 1, OP_MERGE = 2, OP_BLEN = 3, OP_DIFFER = 4, OP_DONE = 5, OP_SCAN = 6 };
+enum FsmOp { OP_NONE = 0, OP_APPEND = 1, OP_MERGE = 2, OP_BLEN = 3, OP_DIFFER = 4, OP_DONE = 5, OP_SCAN = 6, OP_EVALQ = 7 };
 
 struct Fsm {
     int pc, op;
@@ -43,6 +43,7 @@ struct Fsm {
     // subtree scan (warp_scan_job): phase-2 entries it found, waiting to be evaluated
     int qN, qi, scanNewBest;
     unsigned qRes;
+    int evalqDone;  // the queued entries were evaluated by the whole warp (warp_eval_queue)
 };
 
 struct PathE {  // per-depth state of a subtree scan: what a node hands to its children (lastLK, failedPasses)
@@ -195,7 +196,17 @@ __device__ void fsm_step(Fsm& f, const DevModel& m, const DevTree& t, const Sear
                 if (f.scanNewBest) f_shorten_inplace(m, f.removed);  // :7087
                 f.qRes = (unsigned(f.qN) + 3u) & ~3u;
                 s.capK -= f.qRes;  // the queue sits at the top end of the key scratch
-                for (f.qi = 0; f.qi < f.qN; f.qi++) {
+                // The entries are independent of one another (stored lists + the removed list in, a score and three lengths out) and
+                // only folded into the best placement in order: the whole warp takes them one per lane (warp_eval_queue); what it
+                // cannot do (no per-lane scratch in this launch, or an entry that does not fit its slice) is done here, in turn.
+                f.evalqDone = 0;
+                if (f.qN >= 2) {
+                    f.op = OP_EVALQ;
+                    f.pc = 31;
+                    return;
+                    case 31:;
+                }
+                for (f.qi = f.evalqDone ? f.qN : 0; f.qi < f.qN; f.qi++) {
                     f.t1 = int(ld_cg(s.key + (s.capK + f.qRes - 1u - unsigned(f.qi))));  // may have been written by a serving warp on another SM
                     f.eUp = up_list_for(m, t, s, f.t1); f.eDist = dist[f.t1]; f.eMidTot = tree_list(t, 3, f.t1);
                     f.eDown = tree_list(t, 0, f.t1);
@@ -922,6 +933,90 @@ __device__ void warp_scan_job(int src, Fsm& f, const DevModel& m, const DevTree&
     }
 }
 
+// Per-lane scratch slices for warp_eval_queue: one ScratchD worth of room per lane of every warp of the launch.
+struct EvalScratch {
+    uint32_t* key;
+    double* pay;
+    double* ais;
+    unsigned capK, capP, capA;  // per lane; key == nullptr: none (the owning lane evaluates its queue itself)
+};
+
+// The phase-2 entries a subtree scan queued for lane src's search (:7460-7639 for the entries found below a converged node),
+// one entry per lane: evaluatePlacement (:6790) + the two appendProbNode calls of :7510-7511, with the lanes converged inside each
+// co-walk; then folded into the search's best placement as the reference's loop does in order -- an entry replaces the best when
+// its score is >= it (:7635), so the final best is the LAST entry that attains the maximum, if that maximum reaches the old best.
+// On any failure (a slice too small, a None list) nothing is folded and the owning lane goes through the queue itself.
+__device__ void warp_eval_queue(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, const EvalScratch& es,
+                                size_t laneSlot, unsigned long long* st) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = int(threadIdx.x & 31);
+    const int qN = __shfl_sync(FULL, f.qN, src);
+    const uint32_t* qTop = reinterpret_cast<const uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(s.key + s.capK + f.qRes), src));
+    LRef removed;
+    removed.k = reinterpret_cast<const uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(f.removed.k), src));
+    removed.p = reinterpret_cast<const double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(f.removed.p), src));
+    removed.nk = __shfl_sync(FULL, f.removed.nk, src);
+    const bool isRemovedTip = __shfl_sync(FULL, f.isRemovedTip, src) != 0;
+    double best = __shfl_sync(FULL, f.ph.bestScore, src);
+    int bestNode = -1;
+    double bT = 0.0, bB = 0.0, bA = 0.0;
+    bool ok = es.key != nullptr;
+    ScratchD ls;
+    ls.key = es.key + laneSlot * es.capK;
+    ls.pay = es.pay + laneSlot * es.capP;
+    ls.ais = es.ais + laneSlot * es.capA;
+    ls.capK = es.capK; ls.capP = es.capP; ls.capA = es.capA; ls.err = 0;
+    __syncwarp();
+    for (int base = 0; base < qN && ok; base += 32) {
+        const int e = base + lane;
+        const bool have = e < qN;
+        double score = -INFINITY, cT = 0.0, cB = 0.0, cA = 0.0;
+        int t1 = -1;
+        bool bad = false;
+        if (have) {
+            t1 = int(ld_cg(qTop - 1 - e));
+            ls.topK = ls.topP = 0;
+            ls.err = 0;
+            const LRef eUp = up_list_for(m, t, ls, t1), eDown = tree_list(t, 0, t1), eMidTot = tree_list(t, 3, t1);
+            const bool fromTip1 = t.isTip[t1] != 0;
+            const double eDist = t.dist[t1];
+            double cost = 0.0;
+            if (eval_placement(m, sp, ls, eMidTot, eDown, eUp, eDist, removed, isRemovedTip, fromTip1, cost, cB, cT, cA)) bad = true;
+            else {
+                const double initialCost = f_append(m, eUp, eDown, fromTip1, eDist);
+                const double newPartialCost = f_append(m, eUp, eDown, fromTip1, cB + cT);
+                score = cost + newPartialCost - initialCost;
+            }
+        }
+        if (__any_sync(FULL, bad)) { ok = false; break; }
+        // fold this batch: the maximum, and the last lane that holds it
+        double mx = score;  // (a NaN score never replaces anything in the reference's `>=` either: fmax drops it)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+        const unsigned at = __ballot_sync(FULL, have && score == mx);
+        if (at && mx >= best) {
+            const int w = 31 - __clz(at);
+            best = mx;
+            bestNode = __shfl_sync(FULL, t1, w);
+            bT = __shfl_sync(FULL, cT, w);
+            bB = __shfl_sync(FULL, cB, w);
+            bA = __shfl_sync(FULL, cA, w);
+        }
+    }
+    if (st && lane == 0) { st[ok ? 32 : 33] += (unsigned long long)qN; }
+    if (lane == src) {
+        f.evalqDone = ok ? 1 : 0;
+        if (ok && bestNode >= 0) {
+            f.ph.bestNode = bestNode;
+            f.ph.bestScore = best;
+            f.ph.bTop = bT;
+            f.ph.bBottom = bB;
+            f.ph.bAppend = bA;
+        }
+    }
+    __syncwarp();
+}
+
 // After a search finished: startTopologyUpdatesParallel's acceptance logic (:9681-9702)
 __device__ void fsm_finish(const Fsm& f, const DevTree& t, const SearchParams& sp, int node, double bestCurrentLK, SearchResult& r) {
     r.phase1 = f.phase1;
@@ -970,7 +1065,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                                               long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
                                               const int32_t* outIndex, int lanesPerWarp, ScanSmem& W, Scan2Smem& W2, uint32_t& mbarParity,
                                               const BigScratch& big, int warpId, int totalWarps, const ScanQueue& sq, int ownerBase,
-                                              const DenseScores& ds) {
+                                              const DenseScores& ds, const EvalScratch& es, size_t evalSlot) {
     const double* myRow = nullptr;  // dense scoring pass: the current search's row of precomputed candidate scores
     // Scan service (sq.cap != 0, SCAN2 only): a lane that needs a subtree scan posts the job in its slot sq.jobs[ownerBase + lane]
     // and waits for a warp of the serving SMs to run it; meanwhile the other lanes of this warp go on with their co-walks.
@@ -1183,6 +1278,9 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                 __syncwarp();
             } else warp_scan_job(src, f, sm, T, sp, s, stack, stackCap, W, poolBytes, scanFlags, st);
         }
+        // ---------------- queued phase-2 entries: one per lane
+        for (unsigned pending = __ballot_sync(0xffffffffu, f.op == OP_EVALQ); pending; pending &= pending - 1)
+            warp_eval_queue(__ffs(pending) - 1, f, sm, T, sp, s, es, evalSlot, st);
         STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
     }

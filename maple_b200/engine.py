@@ -142,6 +142,10 @@ class MapleEngine:
     def set_scan_min_size(self, n: int):
         capi.check(self.ctx, self.lib.maple_ctx_set_scan_min_size(self.ctx, int(n)), "maple_ctx_set_scan_min_size")
 
+    def set_lanes_per_warp(self, lanes: int):
+        """Searches a warp of the search kernel runs at a time (0 = chosen per launch)."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_lanes_per_warp(self.ctx, int(lanes)), "maple_ctx_set_lanes_per_warp")
+
     def set_scan_service(self, fsm_sms: int):
         """SMs whose CTAs own the searches while all others only serve subtree scans (-1 = chosen per launch, 0 = off)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_scan_service(self.ctx, int(fsm_sms)), "maple_ctx_set_scan_service")
@@ -153,7 +157,7 @@ class MapleEngine:
 
     def search_stats(self, enable: bool = True, read: bool = True):
         """Profiling counters of the search kernel (see scripts/time_search.py for their meaning)."""
-        out = (C.c_uint64 * 32)() if read else None
+        out = (C.c_uint64 * 40)() if read else None
         capi.check(self.ctx, self.lib.maple_search_stats(self.ctx, 1 if enable else 0, out), "maple_search_stats")
         return None if out is None else list(out)
 

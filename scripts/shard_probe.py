@@ -1,0 +1,43 @@
+"""Ad-hoc: what one GPU of an N-GPU round sees -- a cost-balanced 1/N shard of the searches -- timed for several settings of
+searches per warp."""
+import math, sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+from maple_b200.engine import MapleEngine
+from maple_b200.genome_list import pack_lists
+from maple_b200.search import dirty_nodes, search_params
+from maple_b200.sharding import shard_nodes
+from maple_b200.synthetic import generate
+from maple_b200.tree import DeviceTree
+
+nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+lanes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 4, 8]
+d = generate(nseq, rate_variation=True, seed=1, ml_like_blens=True)
+eng = MapleEngine(d.model, 0)
+tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
+tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, 0))
+nodes = dirty_nodes(tree)
+tree.prepare_search()
+L = math.log(d.model.lRef)
+p = search_params(d.model.lRef, False, 4, 14.0 * L)
+cyc = torch.zeros(len(nodes), dtype=torch.int64, device=eng.device)
+full = tree.search_records(tree.spr_search(nodes, p, cycles=cyc))
+cost = cyc.cpu().numpy().astype(np.float64)
+mine = shard_nodes(nodes, 0, world, cost)
+print("full round: %d searches; shard 0 of %d: %d nodes, %d real searches, cost share %.3f" % (
+    (full["status"] == 0).sum(), world, len(mine), (full["status"][np.isin(nodes, mine)] == 0).sum(), cost[np.isin(nodes, mine)].sum() / cost.sum()), flush=True)
+for l in lanes:
+    eng.set_lanes_per_warp(l)
+    ts = []
+    for rep in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c2 = torch.zeros(len(mine), dtype=torch.int64, device=eng.device)
+        a.record()
+        out = tree.spr_search(mine, p, cycles=c2)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    c = c2.cpu().numpy()
+    print("lanes/warp %2d: %s ms | longest search %.1f ms, p99 %.1f ms, sum of search times / 2368 warps = %.1f ms" % (
+        l, " ".join("%.1f" % t for t in ts), c.max() / 1.965e6, np.percentile(c, 99) / 1.965e6, c.sum() / 1.965e6 / 2368), flush=True)

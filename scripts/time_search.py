@@ -53,6 +53,8 @@ for variant in variants:
                   S[16], S[8] / max(S[12], 1), S[9] / max(S[13], 1), S[10] / max(S[14], 1), S[11] / max(S[15], 1), S[8], S[9], S[10], S[11]), flush=True)
         print("   scan jobs %d, nodes in their ranges %.3g, batches %.3g, lanes scored %.3g (%.1f / batch, window %.1f nodes), counted %.3g, phase-2 entries queued %d, windows replayed node by node %d" % (
             S[17], S[18], S[19], S[20], S[20] / max(S[19], 1), S[24] / max(S[19], 1), S[21], S[22], S[25]), flush=True)
+    if variant != 1 and len(S) > 33:
+        print("   queued phase-2 entries evaluated by the warp: %d, left to the owning lane: %d" % (S[32], S[33]), flush=True)
     if variant != 1 and S[27]:
         print("   scan service: jobs posted (lane 0 only) %d, served %d, server warps serving %.1f warp-s, idle %.1f warp-s" % (S[26], S[27], S[28] / 1.9e9, S[29] / 1.9e9), flush=True)
     st = np.bincount(rec["status"], minlength=4)

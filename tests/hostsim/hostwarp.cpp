@@ -33,6 +33,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
                     int32_t bigSlots /* large scratch slots (8x) for searches that exhaust theirs, 0 = none */,
                     int32_t ownerWarps /* scan service: warps that own searches ... */, int32_t serverWarps /* ... and warps that only serve scans; 0 = no service */,
                     int32_t denseRows /* dense scoring pass: rows of the score matrix (searches that get one), 0 = off */,
+                    int32_t evalSlice /* warp-wide evaluation of queued phase-2 entries: scratch entries per lane, 0 = the owning lane does it */,
                     SearchResult* out, unsigned long long* stats) {
     DevTree T;
     memset(&T, 0, sizeof T);
@@ -164,6 +165,18 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         ds.stride = stride;
         if (stats) stats[30] += (unsigned long long)nRows;
     }
+    // per-lane slices for the warp-wide evaluation of queued phase-2 entries (evalSlice = entries per slice, 0 = none)
+    EvalScratch es;
+    memset(&es, 0, sizeof es);
+    std::vector<uint32_t> ek;
+    std::vector<double> ep, ea;
+    if (evalSlice > 0) {
+        es.capK = (unsigned)evalSlice; es.capP = 6u * (unsigned)evalSlice; es.capA = (unsigned)evalSlice;
+        ek.resize((size_t)nWarps * 32 * es.capK + 64);
+        ep.resize((size_t)nWarps * 32 * es.capP + 64);
+        ea.resize((size_t)nWarps * 32 * es.capA + 64);
+        es.key = ek.data(); es.pay = ep.data(); es.ais = ea.data();
+    }
     hostwarp::run_warps(nWarps, [&](int w) {
         const int lane = int(threadIdx.x & 31);
         ScanSmem& W = *reinterpret_cast<ScanSmem*>(smem.data() + warpSmem * w);
@@ -183,10 +196,10 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         StackE* stk = stack.data() + tid * (size_t)stackCap;
         if (scanForm == 2)
             fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
-                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase, ds);
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase, ds, es, (size_t)w * 32 + (size_t)lane);
         else
             fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
-                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, 0, ds);
+                                 poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, 0, ds, es, (size_t)w * 32 + (size_t)lane);
     });
     if (stats) {
         for (int i = 0; i < kNumSearchStats; i++) stats[i] += wst[i];

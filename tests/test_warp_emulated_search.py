@@ -37,7 +37,7 @@ def test_warp_body_equals_straight_line_search(name, form):
         nodes = nodes[::7]
     lists = _prefilled_lists(g, Oracle(model))
     want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
-    st = np.zeros(32, np.uint64)
+    st = np.zeros(40, np.uint64)
     got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=form, stats=st, big_slots=64)
     _same(got, want)
     if not g["env"]["deeperSearchForLongBranches"]:  # (that option keeps every node on the lane path)
@@ -96,7 +96,7 @@ def test_scan_service(name, shape):
         nodes = nodes[::2]
     lists = _prefilled_lists(g, Oracle(model))
     want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
-    st = np.zeros(32, np.uint64)
+    st = np.zeros(40, np.uint64)
     got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, big_slots=64, stats=st, **shape)
     _same(got, want)
     assert st[27] > 0  # jobs went through the servers
@@ -124,10 +124,32 @@ def test_dense_scoring_pass(rv, err, strict, ml, rows):
           "effectivelyNon0BLen": 1.0 / (10 * model.lRef), "BLenThresholdDeeperSearch": (L + 5) / model.lRef, "defaultBLen": 0.000033}
     nodes = np.array([i for i in range(len(d.up)) if d.up[i] >= 0], np.int32)[::5]
     want = hs.search_batch(ta, lists, sp, nodes, scratch_keys=1 << 15)
-    st = np.zeros(32, np.uint64)
+    st = np.zeros(40, np.uint64)
     got = hw.search_batch_warp(ta, lists, sp, nodes, scan_form=2, big_slots=64, stats=st, dense_rows=rows, lanes_per_warp=6)
     _same(got, want)
     assert 0 < st[30] <= rows and st[21] > 1000
+
+
+@pytest.mark.parametrize("eval_slice", [1024, 96, 0])
+def test_queued_phase2_entries_evaluated_by_the_warp(eval_slice):
+    """The phase-2 entries a subtree scan queues are evaluated one per lane (search_fsm.cuh: warp_eval_queue) and folded in the
+    reference's order; with 96 scratch entries per lane most batches do not fit and the owning lane goes through its queue
+    itself, with none it always does.  Deep rules on a perturbed tree (queues of many entries).  Records as the straight-line search."""
+    g, s = round_shim("ex_unrest_rv", "perturbed_deep")
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    orc, hs, hw = Oracle(model), KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(s), np.array(searched_nodes(s), np.int32)[::2]
+    lists = _prefilled_lists(s, orc)
+    want = hs.search_batch(ta, lists, search_params(s), nodes, scratch_keys=1 << 17)
+    st = np.zeros(40, np.uint64)
+    got = hw.search_batch_warp(ta, lists, search_params(s), nodes, scan_form=2, scratch_keys=1 << 15, stats=st, eval_slice=eval_slice, lanes_per_warp=4)
+    _same(got, want)
+    if eval_slice == 1024:
+        assert st[32] > 20 and st[33] == 0, (st[32], st[33])
+    elif eval_slice == 96:
+        assert st[33] > 0
+    else:
+        assert st[32] == 0
 
 
 def test_search_that_exhausts_its_scratch_starts_over_in_a_large_slot():
@@ -139,7 +161,7 @@ def test_search_that_exhausts_its_scratch_starts_over_in_a_large_slot():
     ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)
     lists = _prefilled_lists(g, Oracle(model))
     want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
-    st = np.zeros(32, np.uint64)
+    st = np.zeros(40, np.uint64)
     got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, scratch_keys=512, big_slots=256, stats=st, lanes_per_warp=5)
     assert 0 < st[31] <= 256, st[31]
     _same(got, want)
@@ -157,7 +179,7 @@ def test_second_form_big_fixture_deep_round():
     ta, nodes = tree_arrays(s), np.array(searched_nodes(s), np.int32)[::6]
     lists = _prefilled_lists(s, orc)
     want = hs.search_batch(ta, lists, search_params(s), nodes, scratch_keys=1 << 17)
-    st = np.zeros(32, np.uint64)
+    st = np.zeros(40, np.uint64)
     got = hw.search_batch_warp(ta, lists, search_params(s), nodes, scan_form=2, scratch_keys=1 << 15, stats=st)
     _same(got, want)
     assert st[21] > 10000
