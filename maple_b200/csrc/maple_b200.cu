@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
 // The same searches as k_spr_search, one per lane, but as resumable state machines (search_fsm.cuh): every loop
 // iteration each lane advances its control code to the next co-walk request, then the warp runs each kind of
 // co-walk once for all lanes that requested it.
-template <int MINB, bool SCAN2>
+template <int MINB, bool SCAN2, bool EXTRAS>
 __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const __grid_constant__ DevModel gm, const __grid_constant__ DevTree T,
                                                                    const __grid_constant__ SearchParams sp, int64_t n,
                                                                    const int32_t* __restrict__ nodes, SearchResult* __restrict__ out,
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     const int lane_ = int(threadIdx.x & 31);
     size_t tid;
     int ownerBase = 0;
-    if (SCAN2 && sq.cap != 0) {
+    if (EXTRAS && SCAN2 && sq.cap != 0) {
         // Scan service: the CTAs on the first fsmSMs SMs (and CTA 0, so that somebody owns the searches wherever the CTAs land) run
         // the searches' state machines, 32 to a warp, and post their subtree scans; every other CTA only serves scans.  The split
         // is by SM so that an SM's instruction cache holds one of the two code paths, not both.
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
     s.ais = scrAis + tid * capA;
     s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
     StackE* stack = scrStack + tid * (size_t)stackCap;
-    fsm_warp_loop<SCAN2>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
+    fsm_warp_loop<SCAN2, EXTRAS>(sm, T, sp, n, nodes, out, s, stack, stackCap, counter, outCycles, scanMinSize, scanFlags, poolBytes, st, outIndex,
                          lanesPerWarp, W, W2, mbarParity, big, int((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5),
                          (nDev || sq.cap != 0) ? 0 : int(gridDim.x * (blockDim.x >> 5)), sq, ownerBase, ds, es,
                          blockIdx.x * (size_t)blockDim.x + threadIdx.x);
@@ -1123,14 +1123,18 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     // touchy: check `-Xptxas -v` after changing it -- a 128-register build with ~2 kB of spills is as slow as 168 registers.)
     // Keep the three instantiations: with only <6> and <7> present the same <7> comes out with 2 kB of spills.  96-register builds
     // (<9>, <10>: 10 CTAs per SM, half the list pool) were measured too: 5.5 s against 3.1-3.4 s.
-    FsmKernel fsmKernel = k_spr_search_fsm<6, false>;
-    if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8, false>;
-    if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7, false>;
+    // <.., SCAN2 = second form of the subtree scans, EXTRAS = scan service + dense scoring pass compiled in (chosen below, once it
+    // is known whether either is on for this launch)>
+    FsmKernel fsmKernel = k_spr_search_fsm<6, false, false>;
+    if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8, false, false>;
+    if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7, false, false>;
     if (scan2) {
-        fsmKernel = k_spr_search_fsm<6, true>;
-        if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8, true>;
-        if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7, true>;
+        fsmKernel = k_spr_search_fsm<6, true, false>;
+        if (ctx->fsmMinBlocks == 8) fsmKernel = k_spr_search_fsm<8, true, false>;
+        if (ctx->fsmMinBlocks == 7) fsmKernel = k_spr_search_fsm<7, true, false>;
     }
+    if (scan2 && (ctx->fsmSMs != 0 || ctx->denseMode != 0))
+        fsmKernel = ctx->fsmMinBlocks == 6 ? k_spr_search_fsm<6, true, true> : k_spr_search_fsm<7, true, true>;
     if (ctx->searchVariant != 1) {
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -554,8 +554,12 @@ __device__ __noinline__ double scan_append_generic(const DevModel& m, const uint
 // mbarParity: phase parity of W.mbar, kept by the caller across jobs.  st: optional profiling counters (lane 0 adds).
 // remote: the job belongs to a lane of another warp (scan service): if the removed list's copy does not fit the pool the job is
 // declined (W.job.err = 4) instead of being scored from the arena lists, whose stale copies this SM's L1 might hold.
+// EXTRAS = false compiles the scan service and the dense scoring pass out (the default kernel: they are off by default, and their
+// code costs the hot paths registers).
+template <bool EXTRAS>
 __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const SearchParams& sp, Scan2Smem& W, int poolBytes, int scanFlags /* 2: every window replayed node by node */,
-                               uint32_t& mbarParity, unsigned long long* st, bool remote) {
+                               uint32_t& mbarParity, unsigned long long* st, bool remoteArg) {
+    const bool remote = EXTRAS && remoteArg;
     const unsigned FULL = 0xffffffffu;
     const int lane = int(threadIdx.x & 31);
     const unsigned ltMask = (1u << lane) - 1u;
@@ -573,7 +577,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
     long long tk = st ? clock64() : 0;
     if (st && lane == 0) { st[17] += 1; st[18] += (unsigned long long)(end - pos); }
     // ---- the removed list in scan format, at the front of the pool: the same for every candidate of the job
-    const double* const scoreRow = J.scoreRow;  // dense scoring pass: the scores are there already, this job only keeps the books
+    const double* const scoreRow = EXTRAS ? J.scoreRow : nullptr;  // dense scoring pass: the scores are there already, this job only keeps the books
     int cEntUnits = 0, cUnits = 0;  // 16-byte units of its entries / of the whole copy; cUnits == 0: it does not fit (at most half the pool)
     if (lane == 0 && !scoreRow) {
         int nkC = 0;
@@ -958,7 +962,7 @@ __device__ void scan_server_loop(const DevModel& m, const DevTree& t, const Sear
             L.scoreRow = ld_cg(&J->scoreRow);
         }
         __syncwarp();
-        warp_scan_job2(m, t, sp, W, poolBytes, scanFlags, mbarParity, st, true);
+        warp_scan_job2<true>(m, t, sp, W, poolBytes, scanFlags, mbarParity, st, true);
         if (lane == 0) {
             const ScanJob& L = W.job;
             const bool declined = L.err == 4;

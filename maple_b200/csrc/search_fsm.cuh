@@ -946,7 +946,7 @@ struct EvalScratch {
 // co-walk; then folded into the search's best placement as the reference's loop does in order -- an entry replaces the best when
 // its score is >= it (:7635), so the final best is the LAST entry that attains the maximum, if that maximum reaches the old best.
 // On any failure (a slice too small, a None list) nothing is folded and the owning lane goes through the queue itself.
-__device__ void warp_eval_queue(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, const EvalScratch& es,
+__device__ __noinline__ void warp_eval_queue(int src, Fsm& f, const DevModel& m, const DevTree& t, const SearchParams& sp, ScratchD& s, const EvalScratch& es,
                                 size_t laneSlot, unsigned long long* st) {
     const unsigned FULL = 0xffffffffu;
     const int lane = int(threadIdx.x & 31);
@@ -1059,7 +1059,7 @@ struct BigScratch {
     unsigned long long* counter;  // slots handed out so far
 };
 
-template <bool SCAN2>
+template <bool SCAN2, bool EXTRAS>
 __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree& T, const SearchParams& sp, int64_t n, const int32_t* __restrict__ nodes,
                                               SearchResult* __restrict__ out, ScratchD s, StackE* stack, int stackCap, unsigned long long* counter,
                                               long long* outCycles, int scanMinSize, int scanFlags, int poolBytes, unsigned long long* st,
@@ -1069,7 +1069,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
     const double* myRow = nullptr;  // dense scoring pass: the current search's row of precomputed candidate scores
     // Scan service (sq.cap != 0, SCAN2 only): a lane that needs a subtree scan posts the job in its slot sq.jobs[ownerBase + lane]
     // and waits for a warp of the serving SMs to run it; meanwhile the other lanes of this warp go on with their co-walks.
-    const bool service = SCAN2 && sq.cap != 0;
+    const bool service = EXTRAS && SCAN2 && sq.cap != 0;
     bool waitScan = false, localScan = false;
     unsigned long long nCompleted = 0;
     // First search of every owning lane: entry lane * totalWarps + warpId of the list, so that neighbours in the list -- the
@@ -1175,7 +1175,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
             if (i >= (unsigned long long)n) { stage = 3; f.op = OP_NONE; break; }
             node = nodes[i];
             myRow = nullptr;
-            if (ds.rowOf) {
+            if (EXTRAS && ds.rowOf) {
                 const int row = ds.rowOf[i];
                 if (row >= 0) myRow = ds.scores + (size_t)row * (size_t)ds.stride;
             }
@@ -1265,7 +1265,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                     J.scoreRow = myRow;
                 }
                 __syncwarp();
-                warp_scan_job2(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st, false);
+                warp_scan_job2<EXTRAS>(sm, T, sp, W2, poolBytes, scanFlags, mbarParity, st, false);
                 if (lane_ == src) {
                     const ScanJob& J = W2.job;
                     f.bestLKdiff = J.bestOut;
@@ -1284,7 +1284,7 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
         STAT_T(5);
         if (__all_sync(0xffffffffu, stage == 3)) break;
     }
-    if (service) {  // this warp's searches are over: tell the servers, then help them until everybody is through
+    if (EXTRAS && service) {  // this warp's searches are over: tell the servers, then help them until everybody is through
         for (int o = 16; o; o >>= 1) nCompleted += __shfl_xor_sync(0xffffffffu, nCompleted, o);
         if (l0 && nCompleted) atomicAdd(sq.doneSearches, nCompleted);
         __syncwarp();

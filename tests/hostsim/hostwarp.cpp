@@ -195,10 +195,10 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
         StackE* stk = stack.data() + tid * (size_t)stackCap;
         if (scanForm == 2)
-            fsm_warp_loop<true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
+            fsm_warp_loop<true, true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
                                 stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase, ds, es, (size_t)w * 32 + (size_t)lane);
         else
-            fsm_warp_loop<false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
+            fsm_warp_loop<false, false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanForm == 1 ? scanMinSize : 0, scanFlags,
                                  poolBytes, stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, 0, ds, es, (size_t)w * 32 + (size_t)lane);
     });
     if (stats) {
