@@ -1047,57 +1047,6 @@ __device__ void fsm_finish(const Fsm& f, const DevTree& t, const SearchParams& s
 // then the warp runs each kind of co-walk once for all lanes that requested it, then the pending subtree scans one after the
 // other with the whole warp.  Lanes pull searches from the global counter.  SCAN2 selects the second form of the scans
 // (scan2.cuh).  A function of its own so that tests/hostsim can run the very same loop with the lanes emulated.
-// Operands of the lane-level co-walks into shared memory.  A lane that merges (compares, scores ...) two lists on its own walks
-// them entry by entry through dependent loads; from HBM / L2 that is several hundred cycles per entry and the other lanes of the
-// warp mostly have nothing to do (2-3 lanes request the same kind of co-walk at a time).  So before the lanes of `req` run a
-// co-walk, the whole warp copies their two operand lists into the warp's pool with coalesced loads, as many lanes' worth as fit
-// (lists of a few hundred entries: a few KB); those lanes then walk shared memory.  The lists are not changed: same results.
-// Returns the lanes whose operands were staged; for them s1 / s2 replace a1 / a2.
-__device__ __forceinline__ unsigned warp_stage_operands(unsigned req, const LRef& a1, const LRef& a2, uint4* pool, int poolBytes, LRef& s1, LRef& s2) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = int(threadIdx.x & 31);
-    unsigned done = 0;
-    int used = 0;
-    s1 = a1;
-    s2 = a2;
-    for (unsigned mleft = req; mleft; mleft &= mleft - 1) {
-        const int r = __ffs(mleft) - 1;
-        const uint32_t* k1 = reinterpret_cast<const uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(a1.k), r));
-        const uint32_t* k2 = reinterpret_cast<const uint32_t*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(a2.k), r));
-        const double* p1 = reinterpret_cast<const double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(a1.p), r));
-        const double* p2 = reinterpret_cast<const double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(a2.p), r));
-        const int nk1 = __shfl_sync(FULL, a1.nk, r), nk2 = __shfl_sync(FULL, a2.nk, r);
-        if (!k1 || !k2 || nk1 <= 0 || nk2 <= 0) continue;
-        const int kb1 = (4 * nk1 + 4 + 15) & ~15, kb2 = (4 * nk2 + 4 + 15) & ~15;  // (+1 entry: a cursor may decode the key after the last)
-        if (used + kb1 + kb2 > poolBytes) break;
-        // payload doubles of each list = sum over its entries of nLens + (O ? 4 : 0)
-        int c1 = 0, c2 = 0;
-        for (int i = lane; i < nk1; i += 32) { const uint32_t k = k1[i]; c1 += int((k >> 3) & 3u) + ((k & 7u) == 6u ? 4 : 0); }
-        for (int i = lane; i < nk2; i += 32) { const uint32_t k = k2[i]; c2 += int((k >> 3) & 3u) + ((k & 7u) == 6u ? 4 : 0); }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { c1 += __shfl_xor_sync(FULL, c1, o); c2 += __shfl_xor_sync(FULL, c2, o); }
-        const int pb1 = (8 * c1 + 8 + 15) & ~15, pb2 = (8 * c2 + 8 + 15) & ~15;
-        if (used + kb1 + kb2 + pb1 + pb2 > poolBytes) break;
-        char* base = reinterpret_cast<char*>(pool) + used;
-        uint32_t* sk1 = reinterpret_cast<uint32_t*>(base);
-        uint32_t* sk2 = reinterpret_cast<uint32_t*>(base + kb1);
-        double* sp1 = reinterpret_cast<double*>(base + kb1 + kb2);
-        double* sp2 = reinterpret_cast<double*>(base + kb1 + kb2 + pb1);
-        for (int i = lane; i <= nk1; i += 32) sk1[i] = i < nk1 ? k1[i] : 0u;
-        for (int i = lane; i <= nk2; i += 32) sk2[i] = i < nk2 ? k2[i] : 0u;
-        for (int i = lane; i <= c1; i += 32) sp1[i] = i < c1 ? p1[i] : 0.0;
-        for (int i = lane; i <= c2; i += 32) sp2[i] = i < c2 ? p2[i] : 0.0;
-        if (lane == r) {
-            s1 = LRef{sk1, sp1, nk1};
-            s2 = LRef{sk2, sp2, nk2};
-        }
-        used += kb1 + kb2 + pb1 + pb2;
-        done |= 1u << r;
-    }
-    __syncwarp();
-    return done;
-}
-
 // A few large scratch slots shared by the whole launch: a search that exhausts its lane's scratch takes one (while there are
 // any) and starts over inside the same launch, concurrently with everybody else, instead of waiting for a second launch.
 struct BigScratch {
@@ -1256,39 +1205,21 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
             STAT_N(12, b1 != 0); STAT_N(13, b2 != 0); STAT_N(14, b3 != 0); STAT_N(15, b4 != 0); STAT_N(16, 1);
             tk = clock64();
         }
-        // (SCAN2: the operands of the requesting lanes are first copied to shared memory by the whole warp, warp_stage_operands)
-        LRef o1 = f.a1, o2 = f.a2;
-        {
-            const unsigned req = __ballot_sync(0xffffffffu, f.op == OP_APPEND);
-            if (SCAN2 && req) warp_stage_operands(req, f.a1, f.a2, W2.pool, poolBytes, o1, o2);
-            if (f.op == OP_APPEND) f.resD = f_append(sm, o1, o2, f.at1 != 0, f.ab1);
-        }
+        if (f.op == OP_APPEND) f.resD = f_append(sm, f.a1, f.a2, f.at1 != 0, f.ab1);
         __syncwarp();
         STAT_T(1);
-        {
-            const unsigned req = __ballot_sync(0xffffffffu, f.op == OP_MERGE);
-            if (SCAN2 && req) warp_stage_operands(req, f.a1, f.a2, W2.pool, poolBytes, o1, o2);
-            if (f.op == OP_MERGE) {
-                Writer w;
-                w.init(s.key + s.topK, s.pay + s.topP);
-                if (f_merge(sm, o1, f.ab1, f.at1 != 0, o2, f.ab2, f.at2 != 0, f.aflags, w) == 0) f.resL = sc_commit(s, w.nk, w.np);
-                else f.resL = lnull();
-            }
+        if (f.op == OP_MERGE) {
+            Writer w;
+            w.init(s.key + s.topK, s.pay + s.topP);
+            if (f_merge(sm, f.a1, f.ab1, f.at1 != 0, f.a2, f.ab2, f.at2 != 0, f.aflags, w) == 0) f.resL = sc_commit(s, w.nk, w.np);
+            else f.resL = lnull();
         }
         __syncwarp();
         STAT_T(2);
-        {
-            const unsigned req = __ballot_sync(0xffffffffu, f.op == OP_BLEN);
-            if (SCAN2 && req) warp_stage_operands(req, f.a1, f.a2, W2.pool, poolBytes, o1, o2);
-            if (f.op == OP_BLEN) f.resD = f_blen(sm, o1, o2, f.at1 != 0, s.ais);
-        }
+        if (f.op == OP_BLEN) f.resD = f_blen(sm, f.a1, f.a2, f.at1 != 0, s.ais);
         __syncwarp();
         STAT_T(3);
-        {
-            const unsigned req = __ballot_sync(0xffffffffu, f.op == OP_DIFFER);
-            if (SCAN2 && req) warp_stage_operands(req, f.a1, f.a2, W2.pool, poolBytes, o1, o2);
-            if (f.op == OP_DIFFER) f.resB = f_differ(sm, o1, o2) ? 1 : 0;
-        }
+        if (f.op == OP_DIFFER) f.resB = f_differ(sm, f.a1, f.a2) ? 1 : 0;
         __syncwarp();
         STAT_T(4);
         // ---------------- subtree scans

@@ -41,20 +41,3 @@ for l in lanes:
     c = c2.cpu().numpy()
     print("lanes/warp %2d: %s ms | longest search %.1f ms, p99 %.1f ms, sum of search times / 2368 warps = %.1f ms" % (
         l, " ".join("%.1f" % t for t in ts), c.max() / 1.965e6, np.percentile(c, 99) / 1.965e6, c.sum() / 1.965e6 / 2368), flush=True)
-# the longest search of the shard, alone on the GPU, with the kernel's counters on
-worst = int(mine[int(np.argmax(c))])
-eng.set_lanes_per_warp(1)
-eng.search_stats(True, True)
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-out = tree.spr_search(np.array([worst], np.int32), p, schedule=False)
-b.record()
-torch.cuda.synchronize()
-S = eng.search_stats(False, True)
-r = tree.search_records(out)[0]
-wc = float(sum(S[0:6])) or 1.0
-print("longest search alone (node %d): %.1f ms, %d candidates | warp cycles: control %.1f%% append %.1f%% merge %.1f%% blen %.1f%% differ %.1f%% scan+evalq %.1f%% "
-      "(window+stage %.1f%% score %.1f%% replay %.1f%%) | iterations %d, ops a %d m %d b %d d %d | scan jobs %d windows %d scored %d counted %d queued %d | "
-      "evalq by warp %d by lane %d" % (worst, a.elapsed_time(b), r["phase1"], 100 * S[0] / wc, 100 * S[1] / wc, 100 * S[2] / wc, 100 * S[3] / wc,
-                                        100 * S[4] / wc, 100 * S[5] / wc, 100 * S[23] / wc, 100 * S[6] / wc, 100 * S[7] / wc, S[16], S[8], S[9], S[10], S[11],
-                                        S[17], S[19], S[20], S[21], S[22], S[32], S[33]), flush=True)
