@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--new-samples", type=int, default=int(os.environ.get("MAPLE_BENCH_NEW_SAMPLES", 50000)), help="--workload place: samples per batch")
     ap.add_argument("--cpu-searches", type=int, default=1500, help="searches in the CPU sample")
     ap.add_argument("--cpu-samples", type=int, default=400, help="--workload place: samples in the CPU sample")
+    ap.add_argument("--error-model", action="store_true", default=bool(int(os.environ.get("MAPLE_BENCH_ERROR_MODEL", "0"))),
+                    help="site-specific sequencing-error rates on (the reference's --estimateSiteSpecificErrorRate shape, BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the untimed side measurements reported under 'extra'")
     return ap.parse_args()
@@ -97,8 +99,9 @@ def round_params(args, lRef):
 
 
 def workload_name(args):
-    return ("synthetic 29903-bp, %d seqs ~10 diffs, UNREST+rateVariation, MAPLE-like branch lengths; one full SPR search round "
-            "(%s stop rules) over every non-root node of the frozen tree" % (args.nseq, args.round))
+    return ("synthetic 29903-bp, %d seqs ~10 diffs, UNREST+rateVariation%s, MAPLE-like branch lengths; one full SPR search round "
+            "(%s stop rules) over every non-root node of the frozen tree"
+            % (args.nseq, "+site-specific error rates" if args.error_model else "", args.round))
 
 
 def build_problem(args, device_index):
@@ -109,7 +112,8 @@ def build_problem(args, device_index):
     from maple_b200.synthetic import generate
     from maple_b200.tree import DeviceTree
     t0 = time.time()
-    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, seed=1, ml_like_blens=True)
+    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, error_model=args.error_model,
+                 site_specific_errors=args.error_model, seed=1, ml_like_blens=True)
     eng = MapleEngine(d.model, device_index)
     tree = DeviceTree(eng, d.up, d.child0, d.child1, d.dist, d.root)
     tree.recalculate_all_lists(d.tip_nodes, pack_lists(d.tip_lists, d.model.lRef, d.model.usingErrorRate))
@@ -143,7 +147,8 @@ def build_problem_cpu(args):
     from oracle.host_tree import build_tree_lists
     from oracle.oracle import Oracle
     t0 = time.time()
-    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, seed=1, ml_like_blens=True)
+    d = generate(args.nseq, lRef=29903, mean_diffs=10.0, rate_variation=True, error_model=args.error_model,
+                 site_specific_errors=args.error_model, seed=1, ml_like_blens=True)
     orc = Oracle(d.model)
     lists, dist, isTip = build_tree_lists(orc, d.up, d.child0, d.child1, d.dist, d.root, d.tip_nodes, d.tip_lists, d.model.lRef,
                                           d.model.usingErrorRate)

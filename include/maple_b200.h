@@ -232,6 +232,14 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant);
  * searches (few searches -> few per warp, so that a long search does not share its warp).  Tuning only. */
 int maple_ctx_set_lanes_per_warp(maple_ctx* ctx, int32_t lanes);
 
+/* Searches that get an SM each.  A round ends with its longest search, and one search is a dependent chain that runs about 1.6x
+ * faster on an SM it does not share (instruction cache, issue slots).  count > 0: the FIRST count entries of the node list of
+ * every following maple_spr_search_batch (the caller sorts the list longest-first, e.g. by out_cycles of the previous round) are
+ * run by a launch of their own -- one single-warp CTA each that takes a whole SM's shared memory -- next to the usual launch,
+ * which gets the other SMs.  Worth it when the longest searches are a large part of the round (a shard of a multi-GPU round);
+ * at most half the SMs; ignored when the batch has fewer than 4 * count searches.  0 (default) = off.  Same results. */
+int maple_ctx_set_critical_searches(maple_ctx* ctx, int32_t count);
+
 /* How maple_spr_search_batch (variant 0) divides the GPU: the CTAs on the first fsmSMs SMs own the searches (one per lane, their
  * merges / branch lengths / candidate scores near the pruning point run there) and post every subtree scan in a global-memory
  * slot; the CTAs of all other SMs do nothing but take scans from a ticket ring, run them and hand the results back.  0 (default)

@@ -91,7 +91,9 @@ __device__ __forceinline__ void gv_vec(const SiteQ& q, double t, const double* v
 }
 
 // getPartialVec for a single nucleotide x (:4110-4141); `flag` already includes usingErrorRate
-__device__ __forceinline__ void gv_nuc(const SiteQ& q, double eps, int x, double t, bool up, bool flag, double* o) {
+// (QT: SiteQ, or anything with the same at(i, j))
+template <class QT>
+__device__ __forceinline__ void gv_nuc(const QT& q, double eps, int x, double t, bool up, bool flag, double* o) {
     if (flag) {
         double nv[4];
         const double e3 = eps * 0.33333;

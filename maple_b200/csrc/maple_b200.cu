@@ -43,6 +43,10 @@ struct maple_ctx {
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
     int lanesPerWarp = 0;               // searches per warp (1..32); 0 = chosen per launch from the number of searches
+    int criticalSearches = 0;           // the first so many entries of a batch run on an SM of their own each (maple_ctx_set_critical_searches)
+    cudaStream_t criticalStream = nullptr;
+    cudaEvent_t criticalEvA = nullptr, criticalEvB = nullptr;
+    unsigned long long* criticalCounter = nullptr;
     bool scanReplaySequential = false;  // A/B: node-by-node window replay instead of the pointer-jumping one
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
     int fsmMinBlocks = 7;            // __launch_bounds__ minimum CTAs per SM of the state-machine kernel (7 -> 128 registers, 6 -> 168)
@@ -454,6 +458,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
     }
 }
 
+// Holds the stream until `want` CTAs of a launch on another stream have started (BigScratch::started), or ~2 ms have passed:
+// the launch that follows then finds those CTAs resident and is scheduled around them.
+__global__ void k_wait_started(const unsigned long long* started, unsigned long long want) {
+    const long long t0 = clock64();
+    while (ld_volatile_u64(started) < want && clock64() - t0 < 4000000LL) spin_pause(200);
+}
+
 // The same searches as k_spr_search, one per lane, but as resumable state machines (search_fsm.cuh): every loop
 // iteration each lane advances its control code to the next co-walk request, then the warp runs each kind of
 // co-walk once for all lanes that requested it.
@@ -489,6 +500,7 @@ __global__ void __launch_bounds__(kSearchThreads, MINB) k_spr_search_fsm(const _
         __syncwarp();
     }
     (void)W;
+    if (big.started && threadIdx.x == 0) atomicAdd(big.started, 1ULL);
     if (nDev) n = (int64_t)min((unsigned long long)n, *nDev);  // retry launch: the list length lives on the device
     stage_model(sm, gm);
     const int lane_ = int(threadIdx.x & 31);
@@ -718,6 +730,10 @@ int maple_ctx_destroy(maple_ctx* ctx) {
     cudaFree(ctx->devStage);
     cudaFree(ctx->searchScratch);
     cudaFree(ctx->searchCounter);
+    cudaFree(ctx->criticalCounter);
+    if (ctx->criticalStream) cudaStreamDestroy(ctx->criticalStream);
+    if (ctx->criticalEvA) cudaEventDestroy(ctx->criticalEvA);
+    if (ctx->criticalEvB) cudaEventDestroy(ctx->criticalEvB);
     cudaFree(ctx->retryScratch);
     cudaFree(ctx->placeScratch);
     cudaFree(ctx->retryCounters);
@@ -1164,6 +1180,22 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
         if (fsmSMs < 1) fsmSMs = 1;
     }
 noService:
+    // Searches that run on an SM of their own (maple_ctx_set_critical_searches): the first nCrit entries of the list go to a launch
+    // of their own -- one single-warp CTA each, which asks for a whole SM's shared memory so that nothing else is scheduled next
+    // to it -- and the rest of the list to the usual launch on the remaining SMs.
+    int nCrit = 0;
+    if (scan2 && fsmSMs == 0 && ctx->criticalSearches > 0 && ctx->denseMode == 0 && max_concurrent_searches == 0 && ctx->searchVariant == 0) {
+        nCrit = ctx->criticalSearches;
+        if (nCrit > ctx->numSMs / 2) nCrit = ctx->numSMs / 2;
+        if ((int64_t)nCrit * 4 > n) nCrit = 0;
+    }
+    const int32_t* const nodesAll = nodes;
+    const int64_t nAll = n;
+    if (nCrit) {
+        nodes += nCrit;
+        n -= nCrit;
+        threads = (int64_t)(ctx->numSMs - nCrit) * blocksPerSM * kSearchThreads;
+    }
     int lpw = 32;
     if (fsmSMs > 0) {
         lpw = 32;
@@ -1181,7 +1213,8 @@ noService:
     const size_t perThread = (size_t)capK * 4 + (size_t)capP * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
     // lanes that own a search (and scratch); with the scan service: the warps of fsmSMs SMs and of CTA 0
     const size_t owners = fsmSMs > 0 ? ((size_t)fsmSMs * blocksPerSM + 1) * (kSearchThreads / 32) * 32 : (size_t)threads / 32 * lpw;
-    const size_t need = perThread * owners + 256;
+    const size_t mainBytes = (perThread * owners + 255) & ~size_t(255);
+    const size_t need = mainBytes + perThread * (size_t)nCrit + 256;
     if (need > ctx->searchScratchBytes) {
         cudaFree(ctx->searchScratch);
         ctx->searchScratch = nullptr;
@@ -1239,7 +1272,7 @@ noService:
         // evaluatePlacement (a few hundred entries) fit; an entry that does not is evaluated by the owning lane in its own scratch
         es.capK = 1024; es.capP = 6 * 1024; es.capA = 1024;
         const size_t perLane = (size_t)es.capK * 4 + (size_t)es.capP * 8 + (size_t)es.capA * 8;
-        const size_t needE = perLane * (size_t)threads + 256;
+        const size_t needE = perLane * ((size_t)threads + (size_t)nCrit * 32) + 256;
         if (needE > ctx->evalBytes) {
             cudaFree(ctx->evalMem);
             ctx->evalMem = nullptr;
@@ -1248,9 +1281,10 @@ noService:
             else { ctx->evalMem = nullptr; (void)cudaGetLastError(); }
         }
         if (ctx->evalMem) {
+            const size_t lanes = (size_t)threads + (size_t)nCrit * 32;
             es.pay = (double*)ctx->evalMem;
-            es.ais = es.pay + (size_t)threads * es.capP;
-            es.key = (uint32_t*)(es.ais + (size_t)threads * es.capA);
+            es.ais = es.pay + lanes * es.capP;
+            es.key = (uint32_t*)(es.ais + lanes * es.capA);
         }
     }
     if (fsmSMs > 0) {
@@ -1341,17 +1375,59 @@ noService:
         k_scan_prepare<<<(T.nNodes + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, sp.effectivelyNon0BLen, const_cast<ScanNode*>(T.scan));
         ctx->launches++;
     }
+    const int scanMin = (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0;
+    const int scanFlags = ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0));
+    SearchResult* outMain = (SearchResult*)out + nCrit;
+    long long* cyclesMain = out_cycles ? (long long*)out_cycles + nCrit : nullptr;
+    if (nCrit) {
+        // The critical launch goes first, on a stream of its own; a one-thread gate holds this stream until its CTAs are resident.
+        if (!ctx->criticalStream) {
+            CK(cudaStreamCreateWithFlags(&ctx->criticalStream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->criticalEvA, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->criticalEvB, cudaEventDisableTiming));
+            CK(cudaMalloc((void**)&ctx->criticalCounter, sizeof(unsigned long long)));
+        }
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, fsmKernel));
+        int maxOptin = 0;
+        CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        const size_t hogSmem = (size_t)maxOptin - fa.sharedSizeBytes;  // a whole SM's shared memory: nothing else fits next to this CTA
+        CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hogSmem));
+        const unsigned long long firstC = (unsigned long long)nCrit;  // one search per CTA, handed out statically; the counter has nothing more
+        CK(cudaMemcpyAsync(ctx->criticalCounter, &firstC, sizeof firstC, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        char* base2 = base + mainBytes;
+        const size_t o2 = (size_t)nCrit;
+        double* pay2 = (double*)base2;
+        double* ais2 = (double*)(base2 + o2 * capP * 8);
+        StackE* stack2 = (StackE*)(base2 + o2 * (capP + capA) * 8);
+        uint32_t* key2 = (uint32_t*)(base2 + o2 * ((size_t)(capP + capA) * 8 + (size_t)stackCap * sizeof(StackE)));
+        BigScratch big2 = big;
+        big2.started = ctx->retryCounters + 3;
+        EvalScratch es2 = es;
+        if (es.key) { es2.pay += (size_t)threads * es.capP; es2.ais += (size_t)threads * es.capA; es2.key += (size_t)threads * es.capK; }
+        CK(cudaEventRecord(ctx->criticalEvA, (cudaStream_t)stream));
+        CK(cudaStreamWaitEvent(ctx->criticalStream, ctx->criticalEvA, 0));
+        fsmKernel<<<nCrit, 32, hogSmem, ctx->criticalStream>>>(ctx->model, T, sp, (int64_t)nCrit, nodesAll, (SearchResult*)out, key2, pay2, ais2, stack2, capK,
+                                                                 capP, capA, stackCap, ctx->criticalCounter, (long long*)out_cycles, scanMin, scanFlags,
+                                                                 poolBytes, ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, 1, big2, sq, 0, ds, es2);
+        CK(cudaEventRecord(ctx->criticalEvB, ctx->criticalStream));
+        k_wait_started<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->retryCounters + 3, (unsigned long long)nCrit);
+        ctx->launches += 2;
+    }
     if (ctx->searchVariant == 1)
         k_spr_search<<<blocks, kSearchThreads, 0, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
                                                                          scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
                                                                          (long long*)out_cycles);
     else
-        fsmKernel<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, (SearchResult*)out, scrKey, scrPay,
-                                                                             scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
-                                                                             (long long*)out_cycles,
-                                                                             (T.order && (ctx->searchVariant == 0 || ctx->searchVariant == 3)) ? ctx->scanMinSize : 0,
-                                                                             ctx->searchVariant == 3 ? 3 : ((ctx->scanAppendSitewise ? 0 : 1) | (ctx->scanReplaySequential ? 2 : 0)), poolBytes,
-                                                                             ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw, big, sq, fsmSMs, ds, es);
+        fsmKernel<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, outMain, scrKey, scrPay, scrAis, scrStack, capK,
+                                                                             capP, capA, stackCap, ctx->searchCounter, cyclesMain, scanMin, scanFlags,
+                                                                             poolBytes, ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw,
+                                                                             big, sq, fsmSMs, ds, es);
+    if (nCrit) {
+        CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->criticalEvB, 0));
+        nodes = nodesAll;
+        n = nAll;
+    }
     ctx->launches++;
     timer.mark("searches");
     if (ctx->searchVariant != 1 && n < (int64_t(1) << 31)) {
@@ -1478,6 +1554,12 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
 int maple_ctx_set_lanes_per_warp(maple_ctx* ctx, int32_t lanes) {
     if (!ctx || lanes < 0 || lanes > 32) return MAPLE_E_ARG;
     ctx->lanesPerWarp = lanes;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_critical_searches(maple_ctx* ctx, int32_t count) {
+    if (!ctx || count < 0) return MAPLE_E_ARG;
+    ctx->criticalSearches = count;
     return MAPLE_OK;
 }
 

@@ -57,23 +57,28 @@ inline T ld_cg(const T* p) { return *p; }
 // ---------------------------------------------------------------------------------------------------------------
 // scan-format lists
 // entry.x = the arena key (type | nLens<<3 | flag<<5 | nuc<<6 | end<<8); entry.y = aux:
-//   bits 0-15  index (in doubles, from the list's payload base) of the entry's payload: [len0][len1] then, for a
-//              nucleotide entry, [g] (candidate side) or, for an O entry, the 4-vector.  On the removed-list side a
-//              nucleotide entry is laid out [f][len0][g] with the index pointing at len0, so f sits at index-1.
+//   bits 0-15  byte offset (from the list's payload base) of the entry's payload [len0][len1](4-vector of an O entry).  An
+//              informative entry has one more slot IN FRONT of that, at offset - 8: the candidate side's [g] of a nucleotide
+//              entry (mutMatrices[pos][nuc][ref]) or [a] of an O entry; the removed side's [f] of a nucleotide entry or [a] of
+//              an O entry -- so every precomputed factor is one load from "payload base - 8 + offset".  A candidate-side O
+//              entry below the 0.02 shortcut also carries [q0..q3] = mutMatrices[pos][.][ref] behind its vector (scan_convert_slow_o).
 //   bits 16-22 candidate side: one-hot of the entry type; removed side: types of the OTHER list this entry is informative
 //              against (append_informative) -- the AND of both is non-zero exactly at the informative segments
 //   bit 31     candidate side: plain reference run (type R, no lengths); removed side: nucleotide with at most one length
 //              -> the factor is the removed side's precomputed [f]
-//   bit 30     candidate side: plain nucleotide (no lengths); removed side: plain reference run (and bLen != 0)
+//   bit 30     candidate side: plain nucleotide (no lengths); removed side: plain reference run
 //              -> the factor is min(0.25, [g] * bLen) with the candidate side's [g]
 //   bit 29     candidate side: O entry whose probability of the reference nucleotide exceeds 0.02 (the shortcut of :6692);
-//              removed side: any reference run -> the factor is that probability, stored as [a] in front of the entry's payload
+//              removed side: any reference run -> the factor is that probability, the candidate side's [a]
 //   bit 28     candidate side: any reference run; removed side: O entry whose probability of ITS reference nucleotide exceeds
-//              0.02 (:6615) -> the factor is that probability, stored as [a] in front of the entry's payload
-//   (bits 30/31 are only set without the error model: with it those sites take the general code; 28/29 hold with it too)
-// An entry with an [f] or [a] slot has it at index-1, so three of the four cases are one load from "payload base - 1".
-constexpr uint32_t SA_IDX = 0xffffu, SA_TYPES = 0x7f0000u, SA_FAST_C = 0x80000000u, SA_FAST_P = 0x40000000u, SA_FAST_PO = 0x20000000u,
-                   SA_FAST_CO = 0x10000000u, SA_FAST = 0xf0000000u;
+//              0.02 (:6615) -> the factor is that probability, the removed side's [a]
+//   bit 27     candidate side: O entry below that shortcut whose [a] slot the job has overwritten with its whole factor against a
+//              plain reference run (scan_convert_slow_o, on the job's own staged copy); removed side: plain reference run
+//              (type R, no lengths) -> the factor is that slot
+//   (bits 27/30/31 are only set without the error model: with it those sites take the general code; 28/29 hold with it too)
+constexpr int kMinCarryOverHi = 0x0a711b0e;  // high word of kMinCarryOver = DBL_MIN * 1e50 (checked in scan_walk's host build)
+constexpr uint32_t SA_OFF = 0xffffu /* bytes */, SA_TYPES = 0x7f0000u, SA_FAST_C = 0x80000000u, SA_FAST_P = 0x40000000u, SA_FAST_PO = 0x20000000u,
+                   SA_FAST_CO = 0x10000000u, SA_FAST_PS = 0x08000000u, SA_FAST = 0xf8000000u;
 
 struct ScanRec {  // one per pre-order position, 32 bytes
     int32_t node;
@@ -83,47 +88,80 @@ struct ScanRec {  // one per pre-order position, 32 bytes
     uint32_t off;     // scan-format list: offset in the scan arena, 16-byte units (valid with SR_STAGED)
     uint32_t cnt;     // 16-byte units: entries | payload << 16
     uint32_t flags;   // SN_ELIG | SN_TOT | SN_PUSHED | SN_INNER as in ScanNode, plus:
-    int32_t col;      // dense scoring pass: column of this node's score in a search's row, -1 = none (not scored, or no copy)
+    int32_t col;      // dense scoring pass (k_dense_cols): column of this node's score in a search's row, -1 = none (not scored, or no
+                      // copy); otherwise, as k_scan_build leaves it: the list's O entries below the 0.02 shortcut -- their number
+                      // (bits 30-31, 3 = three or more) and the entry indices of the first three (10 bits each, 1023 = beyond)
 };
 constexpr uint32_t SR_STAGED = 16;  // a scan-format copy of probVectTotUp exists
 constexpr uint32_t SR_SCORED = 64;  // SN_ELIG && SN_TOT && SN_PUSHED: the walk scores this node when it reaches it
 
-// upper bound of the scan-format size of a list with nk entries and np payload doubles, in 16-byte units
-__host__ __device__ inline uint32_t scan_list_units(int nk, int np) { return uint32_t((nk + 1) >> 1) + uint32_t((np + nk + 1) >> 1); }
-
-// Candidate-side copy of one stored list.  Returns the payload doubles written.
-__device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const double* p, int nk, uint2* outE, double* outP) {
+// Candidate-side copy of one stored list.  Returns the payload doubles written.  slowInfo: the list's O entries below the 0.02
+// shortcut (without the error model) -- their number in bits 30-31 (3 = more than two) and the entry indices of the first two
+// (15 bits each, 0x7fff = beyond).
+__device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const double* p, int nk, uint2* outE, double* outP,
+                                   uint32_t* slowInfo = nullptr) {
     int np = 0, ip = 0;
+    uint32_t slow = 0, nSlow = 0;
     for (int i = 0; i < nk; i++) {
         const uint32_t key = __ldg(k + i);
         const int type = int(key & 7u), nl = int((key >> 3) & 3u), nuc = int((key >> 6) & 3u), end = int(key >> 8);
         uint32_t aux = 1u << (16 + type);
+        bool slowO = false;
         if (type == T_R) aux |= SA_FAST_CO;
         if (!m.U) {
             if (type == T_R && nl == 0) aux |= SA_FAST_C;
             if (type < 4 && nl == 0) aux |= SA_FAST_P;
         }
-        if (type == T_O) {
-            const double a = __ldg(p + ip + nl + nuc);
-            if (a > 0.02) {
-                aux |= SA_FAST_PO;
-                outP[np++] = a;
-            }
-        }
-        aux |= uint32_t(np);
-        for (int q = 0; q < nl; q++) outP[np++] = __ldg(p + ip + q);
-        ip += nl;
         if (type < 4) {
             const SiteQ q(m, end - 1);
-            outP[np++] = q.at(type, nuc);  // mutMatrices[pos][nuc of the entry][reference nuc]
-        } else if (type == T_O) {
+            outP[np++] = q.at(type, nuc);  // [g] = mutMatrices[pos][nuc of the entry][reference nuc]
+        } else if (type == T_O) {  // [a]: the shortcut's probability, or room for the job's own factor (bit 27)
+            const double a = __ldg(p + ip + nl + nuc);
+            if (a > 0.02) aux |= SA_FAST_PO;
+            else if (!m.U) {
+                slowO = true;
+                if (nSlow < 2) slow |= uint32_t(i < 0x7fff ? i : 0x7fff) << (15 * nSlow);
+                nSlow++;
+            }
+            outP[np++] = a;
+        }
+        aux |= uint32_t(np) << 3;
+        for (int q = 0; q < nl; q++) outP[np++] = __ldg(p + ip + q);
+        ip += nl;
+        if (type == T_O) {
             for (int q = 0; q < 4; q++) outP[np++] = __ldg(p + ip + q);
             ip += 4;
+            if (slowO) {
+                const SiteQ q(m, end - 1);
+                for (int j = 0; j < 4; j++) outP[np++] = q.at(j, nuc);  // what getPartialVec reads for the reference nucleotide (:4110-4141)
+            }
         }
         outE[i] = make_uint2(key, aux);
     }
     if (nk & 1) outE[nk] = make_uint2(0u, 0u);
+    if (slowInfo) *slowInfo = slow | ((nSlow < 3 ? nSlow : 3u) << 30);
     return np;
+}
+
+// The whole factor of a candidate-side O entry below the 0.02 shortcut against a plain reference run of the removed list
+// (:6692-6703; the same getPartialVec and the same sum as append_site): it depends on the job only through bLen.
+// pay = the entry's payload in the scan format: [len0][len1] [vector] [q0..q3].
+struct SlotQ {
+    const double* g;
+    __device__ __forceinline__ double at(int i, int) const { return g[i]; }
+};
+__device__ __forceinline__ double scan_slow_o_factor(uint32_t key, const double* pay, double bLen) {
+    const int nl = int((key >> 3) & 3u), x = int((key >> 6) & 3u);
+    double contrib = bLen;
+    if (nl == 1) contrib += pay[0];
+    const double* a = pay + nl;
+    const SlotQ q{pay + nl + 4};
+    double t3[4];
+    gv_nuc(q, 0.0, x, contrib, false, false, t3);
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) tot += a[j] * t3[j];
+    return tot;
 }
 
 // Removed-side copy (one per job, shared memory).  Returns the payload doubles written, or -1 if it does not fit.
@@ -134,14 +172,15 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
         if (i >= capE) return -1;
         const uint32_t key = ld_cg(k + i);
         const int type = int(key & 7u), nl = int((key >> 3) & 3u), nuc = int((key >> 6) & 3u), end = int(key >> 8);
-        if (np + 8 > capP || np + 8 > int(SA_IDX)) return -1;
+        if (np + 8 > capP || (np + 8) * 8 > int(SA_OFF)) return -1;
         uint32_t row = 0;
         for (int t1 = 0; t1 < 7; t1++) row |= uint32_t((INF >> (t1 * 8 + type)) & 1ull) << t1;
         const bool fastNuc = !m.U && type < 4 && nl <= 1;
         uint32_t aux = row << 16;
         if (fastNuc) aux |= SA_FAST_C;
         if (type == T_R) aux |= SA_FAST_PO;
-        if (!m.U && type == T_R && nl == 0 && bLen != 0.0) aux |= SA_FAST_P;
+        // (bLen == 0 included: the factor min(0.25, g * 0) = 0 makes the walk return -inf there, as the reference does, :6663)
+        if (!m.U && type == T_R && nl == 0) aux |= SA_FAST_P | SA_FAST_PS;
         if (type == T_O) {
             const double a = ld_cg(p + ip + nl + nuc);
             if (a > 0.02) {
@@ -149,7 +188,7 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
                 outP[np++] = a;
             }
         }
-        aux |= uint32_t(np + (type < 4 ? 1 : 0));
+        aux |= uint32_t(np + (type < 4 ? 1 : 0)) << 3;
         if (type < 4) {
             const SiteQ q(m, end - 1);
             const double g = q.at(nuc, type);  // mutMatrices[pos][reference nuc][nuc of the entry]
@@ -173,75 +212,75 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
     }
 }
 
+// Host builds with -DMAPLE_HOST_STATS (ad-hoc analysis, tests/hostsim): which sites take the general code.
+#if defined(MAPLE_HOST_STATS) && !defined(__CUDACC__)
+extern "C" { unsigned long long g_scan_hist[16]; }
+#define SCAN_HIST(i) (g_scan_hist[i]++)
+#else
+#define SCAN_HIST(i) ((void)0)
+#endif
+
 __device__ __noinline__ double scan_site_general(const DevModel& m, uint32_t k1, const double* pay1, uint32_t k2, const double* pay2, int pos,
                                                  double bLen, bool isTipC, double F) {
+#if defined(MAPLE_HOST_STATS) && !defined(__CUDACC__)
+    {
+        const int t1 = int(k1 & 7u), t2 = int(k2 & 7u), nl1 = int((k1 >> 3) & 3u), nl2 = int((k2 >> 3) & 3u);
+        SCAN_HIST(nl1 == 2 ? 6 : (t1 < 4 && t2 < 4) ? 0 : (t1 < 4 && t2 == T_O) ? 1 : (t1 == T_O && t2 < 4) ? 2 : (t1 == T_O && t2 == T_O) ? 3
+                  : (t1 == T_R && t2 == T_O) ? 4 : (t1 == T_O && t2 == T_R) ? (nl2 ? 10 : 5) : (t1 == T_R && t2 < 4) ? (nl1 ? 11 : 12)
+                  : (t1 < 4 && t2 == T_R) ? (nl2 ? 13 : nl1 ? 14 : 15) : 7);
+    }
+#endif
     return append_site_ref(m, k1, pay1, k2, pay2, pos, bLen, isTipC, F);
 }
 
 // appendProbNode(candidate list, removed list, isTipC, bLen) over the scan-format copies: the arithmetic and its order are
-// dev_append's (:6505-6785).  `mask` = the lanes of the warp that call this together (one candidate each): they meet before
-// every general site so that the long site code runs for all lanes that have one pending, not lane by lane.
+// dev_append's (:6505-6785).  Called by the lanes of a warp together, one candidate each.
 // The segment loop is written without branches around its loads: a precomputed factor is fetched (or 1.0 taken) and multiplied
-// in every iteration -- x * 1.0 == x exactly -- and a cursor that does not advance re-reads its entry.
+// in every iteration -- x * 1.0 == x exactly -- and a cursor that does not advance re-reads its entry.  A site without a
+// precomputed factor takes the general code then and there (a call inside the iteration, after which the lanes go on together:
+// a lane that stopped to wait for the others would have to run the rest of its lists on its own afterwards).
 __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, const double* pP, const uint2* eC, const double* pC, bool isTipC,
-                                            double bLen, unsigned mask) {
+                                            double bLen, const double* one /* a 1.0 next to the lists (same memory space) */) {
     const int lRef = m.lRef;
-    const double* pCm1 = pC - 1;
-    const double* pPm1 = pP - 1;
+    const char* const fC = reinterpret_cast<const char*>(pC - 1);  // factor slots: payload base - 8 + offset
+    const char* const fP = reinterpret_cast<const char*>(pP - 1);
     uint2 a = eP[0], b = eC[0];
     double F = 1.0;
     double Lk = bLen * (-(double)lRef);
     if (m.U && isTipC) Lk += m.totError;
-    bool finished = false, dead = false;
+    SCAN_HIST(9);
     for (;;) {
-        bool general = false;
-        int np = 0;
-        if (!finished) {
-            for (;;) {
-                const uint32_t mm = a.y & b.y;
-                const int e1 = int(a.x >> 8), e2 = int(b.x >> 8);
-                np = min(e1, e2);
-                if ((mm & (SA_FAST | SA_TYPES)) && !(mm & SA_FAST)) {  // an informative site without a precomputed factor
-                    general = true;
-                    break;
-                }
-                // where the factor lies, if there is one: removed side [f]/[a] (bits 31, 28), candidate side [a] (29) or [g] (30)
-                const bool fromC = (mm & (SA_FAST_C | SA_FAST_CO)) != 0;
-                const double* src = fromC ? pCm1 + (b.y & SA_IDX) : ((mm & SA_FAST_PO) ? pPm1 : pP) + (a.y & SA_IDX);
-                double f = 1.0;
-                if (mm & SA_FAST) f = *src;
-                if ((mm & (SA_FAST_C | SA_FAST_CO | SA_FAST_PO | SA_FAST_P)) == SA_FAST_P) f = fmin(0.25, f * bLen);
-                F *= f;
-                if (np == lRef) { finished = true; break; }
-                if (F <= kMinCarryOver) {  // :6772-6783 (also catches the -1 marker of an impossible site)
-                    if (F < DBL_MIN) { dead = finished = true; break; }
-                    Lk += log(F);
-                    F = 1.0;
-                }
-                eP += (e1 == np);
-                eC += (e2 == np);
-                a = *eP;
-                b = *eC;
+        SCAN_HIST(8);
+        const uint32_t mm = a.y & b.y;
+        const int e1 = int(a.x >> 8), e2 = int(b.x >> 8);
+        const int np = min(e1, e2);
+        if ((mm & (SA_FAST | SA_TYPES)) && !(mm & SA_FAST)) {  // an informative site without a precomputed factor
+            F = scan_site_general(m, a.x, pP + ((a.y & SA_OFF) >> 3), b.x, pC + ((b.y & SA_OFF) >> 3), np - 1, bLen, isTipC, F);
+        } else {
+            // the factor, if there is one: the removed side's slot (bits 31, 28) or the candidate side's (30, 29, 27)
+            const bool fromC = (mm & (SA_FAST_C | SA_FAST_CO)) != 0;
+            const char* src = (fromC ? fC : fP) + ((fromC ? b.y : a.y) & SA_OFF);
+            if (!(mm & SA_FAST)) src = reinterpret_cast<const char*>(one);
+            double f = *reinterpret_cast<const double*>(src);
+            if ((mm & SA_FAST) == SA_FAST_P) {  // min(0.25, [g] * bLen); the cap hardly ever applies, and neither is ever a NaN
+                f *= bLen;
+                if (__double2hiint(f) >= 0x3fd00000) f = fmin(0.25, f);
             }
+            F *= f;
         }
-        if (__ballot_sync(mask, general) == 0u) break;  // every lane is through its lists
-        if (general) {
-            F = scan_site_general(m, a.x, pP + (a.y & SA_IDX), b.x, pC + (b.y & SA_IDX), np - 1, bLen, isTipC, F);
-            if (F < 0.0) dead = finished = true;
-            else if (np == lRef) finished = true;
-            else {
-                if (F <= kMinCarryOver) {
-                    if (F < DBL_MIN) dead = finished = true;
-                    else { Lk += log(F); F = 1.0; }
-                }
-                eP += (int(a.x >> 8) == np);
-                eC += (int(b.x >> 8) == np);
-                a = *eP;
-                b = *eC;
-            }
+        if (np == lRef) break;
+        // F <= minimumCarryOver (:6772-6783; also catches the -1 marker of an impossible site), screened by the high word first
+        if (__double2hiint(F) <= kMinCarryOverHi && F <= kMinCarryOver) {
+            if (F < DBL_MIN) return -INFINITY;
+            Lk += log(F);
+            F = 1.0;
         }
+        eP += (e1 == np);
+        eC += (e2 == np);
+        a = *eP;
+        b = *eC;
     }
-    if (dead || !(F > 0.0)) return -INFINITY;
+    if (!(F > 0.0)) return -INFINITY;
     return Lk + log(F);
 }
 
@@ -273,16 +312,16 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
         const int type = int(key & 7u);
         const int nl = int((key >> 3) & 3u);
         np += nl + (type < 4 ? 1 : 0);
-        if (type == T_O) {
-            np += 4;
-            if (__ldg(T.pay + T.payStart[id] + ip + nl + int((key >> 6) & 3u)) > 0.02) np++;
+        if (type == T_O) {  // [a], the vector and, below the 0.02 shortcut, [q0..q3] (sized as without the error model)
+            np += 5;
+            if (!(__ldg(T.pay + T.payStart[id] + ip + nl + int((key >> 6) & 3u)) > 0.02)) np += 4;
             ip += 4;
         }
         ip += nl;
     }
     const uint32_t ue = uint32_t(nk + 1) >> 1, up = uint32_t(np + 1) >> 1;
     if (nk <= 0) return 0u;
-    return (ue < 65536u && up < 65536u && np < 65536) ? (ue | (up << 16)) : ~0u;  // ~0u: too large for a scan-format copy
+    return (ue < 65536u && up < 65536u && np < 8192) ? (ue | (up << 16)) : ~0u;  // ~0u: too large for a scan-format copy (16-bit byte offsets)
 }
 
 // The record of pre-order position i and, where there is one, the scan-format copy of its list (nsa is filled by scan_fill_nsa
@@ -290,7 +329,7 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
 __device__ inline ScanRec scan_build_rec(const DevModel& m, const DevTree& T, double eff, int i, uint32_t units, uint4* arena) {
     ScanRec r;
     const int node = T.order[i];
-    r.node = node; r.size = 1; r.nsa = -1; r.depths = 0; r.off = 0; r.cnt = 0; r.flags = 0; r.col = -1;
+    r.node = node; r.size = 1; r.nsa = -1; r.depths = 0; r.off = 0; r.cnt = 0; r.flags = 0; r.col = 0;
     if (node < 0 || T.pre[node] != i) {  // positions past the reachable nodes
         r.node = -1;
         return r;
@@ -302,8 +341,10 @@ __device__ inline ScanRec scan_build_rec(const DevModel& m, const DevTree& T, do
     if (off != ~0u && units) {
         const int64_t id = 3 * (int64_t)T.nNodes + node;
         uint4* dst = arena + off;
+        uint32_t slow = 0;
         scan_build_p(m, T.key + T.keyStart[id], T.pay + T.payStart[id], T.nkeys[id], reinterpret_cast<uint2*>(dst),
-                     reinterpret_cast<double*>(dst + (units & 0xffffu)));
+                     reinterpret_cast<double*>(dst + (units & 0xffffu)), &slow);
+        r.col = int32_t(slow);
         r.off = off;
         r.cnt = units;
         r.flags |= SR_STAGED;
@@ -382,6 +423,7 @@ struct Scan2Smem {
     short nsa[kWin2];  // window position of the nearest scored proper ancestor, or -(path index)-1
     unsigned char slotS[32];  // by rank: window position
     unsigned long long mbar;
+    double one;     // 1.0: what scan_walk multiplies by where there is no factor
     ScanJob job;
     uint4 pool[1];  // the removed list's scan-format copy (for the whole job), then the window's lists
 };
@@ -469,7 +511,7 @@ constexpr int kDenseCBlock = 128;  // removed lists swept over a tile of candida
 struct DenseSmem {          // per warp
     uint4 cBuf[2][kDenseCUnits];
     unsigned long long mbar;
-    uint32_t pad[2];
+    double one;             // 1.0 (scan_walk)
     uint4 pool[1];          // the tile's candidate lists
 };
 
@@ -506,7 +548,7 @@ __device__ inline void dense_score_task(const DevModel& m, const DevTree& t, Den
 #endif
     const uint2* eP = reinterpret_cast<const uint2*>(base);
     const double* pP = reinterpret_cast<const double*>(base + (cnt & 0xffffu));
-    const unsigned mask = __ballot_sync(FULL, have);
+    if (lane == 0) W.one = 1.0;
     // sweep the block of removed lists: copy k+1 lands in the other buffer while copy k is walked
     auto load_c = [&](int row, int b) {
         const uint4* src = cArena + (size_t)row * kDenseCUnits;
@@ -521,7 +563,7 @@ __device__ inline void dense_score_task(const DevModel& m, const DevTree& t, Den
         if (h.units > 0 && have) {
             const uint2* eC = reinterpret_cast<const uint2*>(&W.cBuf[b][1]);
             const double* pC = reinterpret_cast<const double*>(&W.cBuf[b][1 + h.entUnits]);
-            const double sc = scan_walk(m, eP, pP, eC, pC, h.isTip != 0, rowBLen[row], mask);
+            const double sc = scan_walk(m, eP, pP, eC, pC, h.isTip != 0, rowBLen[row], &W.one);
             scores[(size_t)row * stride + col] = sc;
         }
         __syncwarp();
@@ -593,6 +635,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         }
     }
     if (lane == 0) {
+        W.one = 1.0;
         if (pathCap < 2) err = 3;
         else W.path[0] = PathE2{J.lastLK0, J.failed0, 0};
     }
@@ -680,14 +723,54 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         }
         // ---- stage the lists: one bulk copy, completion on the mbarrier
         double sc = -INFINITY;
-#ifdef __CUDA_ARCH__
         if (!dense && !generic && nScore > 0) {
             const uint32_t endLast = __shfl_sync(FULL, myOff + (myCnt & 0xffffu) + (myCnt >> 16), nScore - 1);
+#ifdef __CUDA_ARCH__
             if (lane == 0) bulk_load(winPool, arena + off0, (endLast - off0) << 4, &W.mbar);
             mbar_wait(&W.mbar, mbarParity);
             mbarParity ^= 1u;
-        }
+#else
+            if (lane == 0)
+                for (uint32_t u = 0; u < endLast - off0; u++) winPool[u] = arena[off0 + u];
+            __syncwarp();
 #endif
+            // The staged copies are this job's own: the O entries of the candidates that are below the 0.02 shortcut (the first
+            // two of a list) get their whole factor against a plain reference run of the removed list written into their [a]
+            // slot (bit 27), so that the walk below finds a precomputed factor there as well -- most of the sites that would
+            // take the general code are of this kind.  One entry per lane, whichever candidate it belongs to.
+            if (!EXTRAS && !m.U) {
+                const uint32_t slow = lane < nScore ? uint32_t(W.colS[lane]) : 0u;
+                const int nSlow = min(int(slow >> 30), 2);
+                int before = nSlow;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int x = __shfl_up_sync(FULL, before, o);
+                    if (lane >= o) before += x;
+                }
+                const int total = __shfl_sync(FULL, before, 31);
+                if (total > 0) {
+                    before -= nSlow;
+                    uint32_t* const work = reinterpret_cast<uint32_t*>(W.scoreS);  // (free until this window's scores are in) 64 items
+                    const uint32_t listOff = (myOff - off0) << 4, payOff = listOff + ((myCnt & 0xffffu) << 4);  // bytes from winPool
+                    for (int r = 0; r < nSlow; r++) {
+                        const uint32_t idx = (slow >> (15 * r)) & 0x7fffu;
+                        work[before + r] = idx == 0x7fffu ? ~0u : ((listOff + idx * 8u) | (payOff << 16));
+                    }
+                    __syncwarp();
+                    char* const wp = reinterpret_cast<char*>(winPool);
+                    for (int t = lane; t < total; t += 32) {
+                        const uint32_t it = work[t];
+                        if (it == ~0u) continue;
+                        uint2* const e = reinterpret_cast<uint2*>(wp + (it & 0xffffu));
+                        const uint2 ev = *e;
+                        double* const pay = reinterpret_cast<double*>(wp + (it >> 16) + (ev.y & SA_OFF));
+                        pay[-1] = scan_slow_o_factor(ev.x, pay, removedBLen);
+                        e->y = ev.y | SA_FAST_PS;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
         if (st) {
             const long long now = clock64();
             if (lane == 0) { st[23] += (unsigned long long)(now - tk); st[19] += 1; st[20] += nScore; st[24] += nWin; }
@@ -696,14 +779,10 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         if (lane < nScore && dense && W.colS[lane] >= 0) sc = __ldg(scoreRow + W.colS[lane]);
         else if (lane < nScore) {
             if (!generic && !dense) {
-#ifdef __CUDA_ARCH__
                 const uint4* base = winPool + (myOff - off0);
-#else
-                const uint4* base = arena + myOff;
-#endif
                 const uint2* eP = reinterpret_cast<const uint2*>(base);
                 const double* pP = reinterpret_cast<const double*>(base + (myCnt & 0xffffu));
-                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen, nScore >= 32 ? FULL : ((1u << nScore) - 1u));
+                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen, &W.one);
             } else {
                 const int64_t id = 3 * (int64_t)t.nNodes + __ldg(&t.scan2[pos + W.slotS[lane]].node);
                 sc = scan_append_generic(m, t.key + t.keyStart[id], t.pay + t.payStart[id], J.remK, J.remP, isRemovedTip, removedBLen);

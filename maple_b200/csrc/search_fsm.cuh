@@ -1057,6 +1057,7 @@ struct BigScratch {
     unsigned capK, capP, capA;
     int nSlots;
     unsigned long long* counter;  // slots handed out so far
+    unsigned long long* started;  // not null: every CTA of the launch counts itself here when it starts (see k_wait_started)
 };
 
 template <bool SCAN2, bool EXTRAS>

@@ -74,6 +74,10 @@ class MapleEngine:
         rc = self.lib.maple_ctx_create(C.byref(ctx), device, model.lRef, pi, flags)
         capi.check(None, rc, "maple_ctx_create")
         self.ctx = ctx
+        try:
+            self.num_sms = int(torch.cuda.get_device_properties(self.device).multi_processor_count)
+        except Exception:
+            self.num_sms = 148
         self.lists: Optional[DeviceLists] = None
         self.update_model()
 
@@ -145,6 +149,10 @@ class MapleEngine:
     def set_lanes_per_warp(self, lanes: int):
         """Searches a warp of the search kernel runs at a time (0 = chosen per launch)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_lanes_per_warp(self.ctx, int(lanes)), "maple_ctx_set_lanes_per_warp")
+
+    def set_critical_searches(self, count: int):
+        """The first `count` entries of every following search batch run on an SM of their own each (0 = off)."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_critical_searches(self.ctx, int(count)), "maple_ctx_set_critical_searches")
 
     def set_scan_service(self, fsm_sms: int):
         """SMs whose CTAs own the searches while all others only serve subtree scans (-1 = chosen per launch, 0 = off)."""

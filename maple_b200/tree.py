@@ -555,15 +555,22 @@ class DeviceTree:
         capi.check(eng.ctx, rc, "maple_tree_bind")
         self._bound_epoch = A.epoch
 
+    # what a search that had an SM to itself would have taken next to the others: the cycles kept in search_cost are the busy kind
+    ALONE_TO_BUSY = 1.6
+
     def spr_search(self, nodes, params: "capi.SearchParams", scratch_keys: int = 0, max_concurrent: int = 0, cycles=None,
-                   schedule: bool = True):
+                   schedule: bool = True, critical=None):
         """Run the searches of the listed nodes; returns a device tensor of raw records [n, 64 bytes] viewed as uint8 (in the
         order of `nodes`) -- search_records() reads it as a numpy record array.
 
         schedule: searches differ by orders of magnitude in length and the kernel's lanes pull them from the list in order, so
         the list is handed over longest-first, using the SM cycles each node's search took the last time it ran on this tree
         (kept on the device in self.search_cost; nodes never searched before go first).  The tree hardly changes between the
-        rounds of a run, so this is the LPT rule with last round's lengths.  Results do not depend on the order."""
+        rounds of a run, so this is the LPT rule with last round's lengths.  Results do not depend on the order.
+
+        critical: how many of the longest searches get an SM each (maple_ctx_set_critical_searches); None = decided from
+        last round's lengths: when the longest search alone is longer than the whole batch would take at full throughput (a
+        shard of a multi-GPU round), every search longer than the time the batch is then expected to take."""
         eng, dev = self.eng, self.eng.device
         if getattr(self, "_bound_epoch", None) != self.arena.epoch:
             self.prepare_search()  # never bound, or the arena's tables moved since (temporary lists added / released)
@@ -573,17 +580,26 @@ class DeviceTree:
         if cost is None or cost.numel() != self.n:
             cost = self.search_cost = torch.full((self.n,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
         perm = None
+        k = 0
         if schedule and n > 1:
-            perm = torch.argsort(cost[nodes.long()], descending=True, stable=True)
+            mine = cost[nodes.long()]
+            perm = torch.argsort(mine, descending=True, stable=True)
             run_nodes = nodes[perm].contiguous()
+            k = self._critical_count(mine[perm], n) if critical is None else int(critical)
         else:
             run_nodes = nodes
+        k = max(0, min(k, n // 4))
+        if k != getattr(self, "_critical_set", 0):
+            eng.set_critical_searches(k)
+            self._critical_set = k
         out = torch.zeros((n, 64), dtype=torch.uint8, device=dev)
         cyc = torch.zeros(n, dtype=torch.int64, device=dev)
         rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), n, _dp(run_nodes), _dp(out), int(scratch_keys),
                                             int(max_concurrent), _dp(cyc), eng._stream())
         capi.check(eng.ctx, rc, "maple_spr_search_batch")
         cost[run_nodes.long()] = cyc
+        if k:
+            cost[run_nodes[:k].long()] = (cyc[:k].double() * self.ALONE_TO_BUSY).long()
         if perm is not None:
             back = torch.empty_like(out)
             back[perm] = out
@@ -593,6 +609,25 @@ class DeviceTree:
         elif cycles is not None:
             cycles.copy_(cyc)
         return out
+
+    def _critical_count(self, sorted_cost: torch.Tensor, n: int) -> int:
+        """See spr_search.  sorted_cost: last round's cycles of this batch's searches, longest first (device)."""
+        sms = int(getattr(self.eng, "num_sms", 148))
+        cap = max(1, sms // 9)
+        if n < 64 or cap < 1:
+            return 0
+        warps = sms * 16
+        lpw = min(32, max(2, -(-n // (warps * 3))))  # searches per warp as maple_spr_search_batch chooses them
+        head = sorted_cost[:cap + 1]
+        stats = torch.cat([head.double(), sorted_cost.double().sum().reshape(1)]).cpu().numpy()
+        c, total = stats[:-1], stats[-1]
+        if c[0] >= float(torch.iinfo(torch.int64).max) / 2 or total <= 0:  # searches with no recorded length yet
+            return 0
+        t_full = total / (warps * lpw)  # cycles the batch takes when every lane is busy all the time
+        if c[0] < 1.1 * t_full:
+            return 0
+        target = max(1.15 * t_full, c[0] / self.ALONE_TO_BUSY)
+        return int(min(cap, (c[:cap] > target).sum()))
 
     # ------------------------------------------------------------------ findBestParentForNewSample for a batch (:7912, :11190-11287)
     def stage_samples(self, samples: PackedLists):

@@ -41,3 +41,22 @@ for l in lanes:
     c = c2.cpu().numpy()
     print("lanes/warp %2d: %s ms | longest search %.1f ms, p99 %.1f ms, sum of search times / 2368 warps = %.1f ms" % (
         l, " ".join("%.1f" % t for t in ts), c.max() / 1.965e6, np.percentile(c, 99) / 1.965e6, c.sum() / 1.965e6 / 2368), flush=True)
+# the longest searches on SMs of their own (maple_ctx_set_critical_searches): explicit counts, then the automatic choice
+eng.set_lanes_per_warp(0)
+for k in ([int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 4, 8, 16, 32, -1]):
+    ts = []
+    for rep in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c2 = torch.zeros(len(mine), dtype=torch.int64, device=eng.device)
+        a.record()
+        out = tree.spr_search(mine, p, cycles=c2, critical=None if k < 0 else k)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    rec = tree.search_records(out)
+    pos = {int(nd): i for i, nd in enumerate(nodes)}
+    sel = np.array([pos[int(nd)] for nd in mine])
+    same = all(np.array_equal(rec[f], full[f][sel]) for f in ("status", "placement", "phase1", "bLenAppend"))
+    c = c2.cpu().numpy()
+    print("critical %3s (set %d): %s ms | longest search %.1f ms | records equal to the full round's: %s" % (
+        "auto" if k < 0 else k, getattr(tree, "_critical_set", 0), " ".join("%.1f" % t for t in ts), c.max() / 1.965e6, same), flush=True)

@@ -99,7 +99,7 @@ def warp_lib():
         L.hw_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.hw_scan_append.restype = C.c_double
-        L.hw_scan_append.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.hw_scan_append.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
         _warp_lib = L
     return _warp_lib
 
@@ -133,7 +133,10 @@ class WarpKernelOnHost(Oracle):
             raise RuntimeError("hw_search_batch: scan form %d not available for this tree" % scan_form)
         return out
 
-    def scan_append(self, P, C_, isTipC, bLen):
-        """appendProbNode through the scan-format copies of both lists (scan2.cuh)."""
+    def scan_append(self, P, C_, isTipC, bLen, convert_slow=False):
+        """appendProbNode through the scan-format copies of both lists (scan2.cuh).  convert_slow: with the candidate side's O
+        entries below the 0.02 shortcut given their factor against a plain reference run first, as a scan job does to its
+        staged copies (bit 27 of the scan format)."""
         a, b = self._one(P), self._one(C_)
-        return self.W.hw_scan_append(self.mp, _p(a.key), _p(a.pay), int(a.nkeys[0]), _p(b.key), _p(b.pay), int(bool(isTipC)), float(bLen))
+        return self.W.hw_scan_append(self.mp, _p(a.key), _p(a.pay), int(a.nkeys[0]), _p(b.key), _p(b.pay), int(bool(isTipC)), float(bLen),
+                                     int(bool(convert_slow)))

@@ -194,7 +194,10 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         s.ais = ais.data() + tid * capA;
         s.capK = capK; s.capP = capP; s.capA = capA; s.topK = 0; s.topP = 0; s.err = 0;
         StackE* stk = stack.data() + tid * (size_t)stackCap;
-        if (scanForm == 2)
+        if (scanForm == 2 && !service && !ds.rowOf)  // the default kernel's instantiation (scan service and dense pass compiled out)
+            fsm_warp_loop<true, false>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
+                                stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, 1, sq, ownerBase, ds, es, (size_t)w * 32 + (size_t)lane);
+        else if (scanForm == 2)
             fsm_warp_loop<true, true>(*m, T, *sp, n, nodes, out, s, stk, stackCap, &counter, nullptr, scanMinSize, scanFlags, poolBytes,
                                 stats ? wst : nullptr, nullptr, lanesPerWarp, W, W2, parity, big, 0, service ? 0 : 1, sq, ownerBase, ds, es, (size_t)w * 32 + (size_t)lane);
         else
@@ -211,14 +214,25 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
 // appendProbNode through the scan-format copies (scan2.cuh: scan_build_p, scan_build_c, scan_walk), one pair.
 // Returns NaN if the removed-side copy does not fit its shared-memory slots.
 double hw_scan_append(const DevModel* m, const uint32_t* kP, const double* pP, int nkP, const uint32_t* kC, const double* pC, int isTipC,
-                      double bLen) {
+                      double bLen, int convertSlow) {
     const int capE = 1 << 16;
     std::vector<uint2> eP(nkP + 2), eC(capE);
-    std::vector<double> yP(8 * (size_t)nkP + 8), yC(8 * (size_t)capE);
-    scan_build_p(*m, kP, pP, nkP, eP.data(), yP.data());
+    std::vector<double> yP(12 * (size_t)nkP + 8), yC(8 * (size_t)capE);
+    uint32_t slow = 0;
+    scan_build_p(*m, kP, pP, nkP, eP.data(), yP.data(), &slow);
     if (scan_build_c(*m, kC, pC, bLen, eC.data(), capE, yC.data(), 8 * capE) < 0) return NAN;
+    if (convertSlow && !m->U)  // what a job does to its staged copy (warp_scan_job2): the factors of the O entries below the shortcut
+        for (int r = 0; r < std::min(int(slow >> 30), 2); r++) {
+            const uint32_t idx = (slow >> (15 * r)) & 0x7fffu;
+            if (idx == 0x7fffu) continue;
+            double* pay = yP.data() + ((eP[idx].y & SA_OFF) >> 3);
+            pay[-1] = scan_slow_o_factor(eP[idx].x, pay, bLen);
+            eP[idx].y |= SA_FAST_PS;
+        }
+    const double one = 1.0;
+    if (__double2hiint(kMinCarryOver) != kMinCarryOverHi) return NAN;  // scan_walk's screen of the carry-over test
     double r = 0.0;
-    hostwarp::run_warp([&]() { if ((threadIdx.x & 31) == 0) r = scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen, 1u); });
+    hostwarp::run_warp([&]() { if ((threadIdx.x & 31) == 0) r = scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen, &one); });
     return r;
 }
 

@@ -19,6 +19,7 @@
 
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+static inline int __double2hiint(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(u >> 32); }
 static inline unsigned __activemask() { return 1u; }
 static inline void __syncwarp(unsigned = 1u) {}
 static inline int __any_sync(unsigned, int p) { return p != 0; }

@@ -190,6 +190,7 @@ inline T unbits(uint64_t u) { T v; memcpy(&v, &u, sizeof v); return v; }
 
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+static inline int __double2hiint(double x) { unsigned long long u; memcpy(&u, &x, 8); return (int)(u >> 32); }
 static inline unsigned __activemask() { return 0xffffffffu; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { hostwarp::collective(hostwarp::OP_SYNC, mask, 0, 0); }
 static inline int __any_sync(unsigned mask, int p) { return hostwarp::collective(hostwarp::OP_BALLOT, mask, p != 0, 0) != 0; }

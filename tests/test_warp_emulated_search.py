@@ -185,7 +185,7 @@ def test_second_form_big_fixture_deep_round():
     assert st[21] > 10000
 
 
-@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_err", "ex_unrest_rv_sse", "ay_unrest_300"])
+@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_err", "ex_unrest_rv_sse", "ay_unrest_300", "syn_unrest_rv_2000"])
 def test_scan_format_append_equals_dev_append(name):
     """appendProbNode through the scan-format copies (precomputed Q*rate, precomputed removed-side factors) against dev_append of
     the same source: recorded calls and random pairs of the fixture's lists with branch lengths from the corners; bit for bit."""
@@ -198,6 +198,7 @@ def test_scan_format_append_equals_dev_append(name):
         b = hs.append(L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"])
         assert a == b, c
         assert a == c["out"] or abs(a - c["out"]) <= 1e-9
+        assert hw.scan_append(L[c["P"]], L[c["C"]], c["isTipC"], c["bLen"], convert_slow=True) == b, c
     rng = np.random.default_rng(11)
     lower = [i for i in set(g["tree"]["probVect"]) if i is not None]
     cand = [i for i in set(g["tree"]["probVectTotUp"]) if i is not None]
@@ -206,4 +207,6 @@ def test_scan_format_append_equals_dev_append(name):
         P, Cc = L[cand[rng.integers(len(cand))]], L[lower[rng.integers(len(lower))]]
         tip, bl = bool(rng.integers(2)), blens[rng.integers(len(blens))]
         a, b = hw.scan_append(P, Cc, tip, bl), hs.append(P, Cc, tip, bl)
+        assert a == b, (P, Cc, tip, bl, a, b)
+        a = hw.scan_append(P, Cc, tip, bl, convert_slow=True)  # the job's own factors for the O entries below the shortcut
         assert a == b, (P, Cc, tip, bl, a, b)
