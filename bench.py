@@ -660,6 +660,7 @@ def main():
         "config": {"workload": workload_name(args), "nseq": args.nseq, "round": args.round, "nodes": tree.n,
                    "searches_per_step": searched, "placements_per_step": cand_total, "proposals": proposals,
                    "scratch_overflows": overflowed, "arena_MB": round(tree.arena.used_bytes() / 1e6, 1), "setup_s": setup_s,
+                   "critical_searches": int(getattr(tree, "_critical_set", 0)),  # searches given an SM each (rank 0's choice)
                    "l2": "flushed between timed iterations (160 MB memset)",
                    "parallelism": "whole tree on every GPU; searches dealt to %d GPU(s) in cost-balanced shards (the previous round's per-search "
                                   "cycles), longest first inside a shard; one NCCL all-gather of the 64-byte result records per round" % world},

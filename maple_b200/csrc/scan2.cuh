@@ -129,7 +129,10 @@ __device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const d
         for (int q = 0; q < nl; q++) outP[np++] = __ldg(p + ip + q);
         ip += nl;
         if (type == T_O) {
-            for (int q = 0; q < 4; q++) outP[np++] = __ldg(p + ip + q);
+            // the vector only where the walk itself may need it: an entry above the shortcut is [a] against every reference run,
+            // and the rare site where it meets something else reads the vector from the stored list (scan_orig_payload)
+            if (!(aux & SA_FAST_PO))
+                for (int q = 0; q < 4; q++) outP[np++] = __ldg(p + ip + q);
             ip += 4;
             if (slowO) {
                 const SiteQ q(m, end - 1);
@@ -141,6 +144,20 @@ __device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const d
     if (nk & 1) outE[nk] = make_uint2(0u, 0u);
     if (slowInfo) *slowInfo = slow | ((nSlow < 3 ? nSlow : 3u) << 30);
     return np;
+}
+
+// Payload of entry idx of a stored (arena) list: [len0][len1][4-vector].
+struct ScanOrig {
+    const uint32_t* k;
+    const double* p;
+};
+__device__ __noinline__ const double* scan_orig_payload(ScanOrig o, int idx) {
+    int ip = 0;
+    for (int i = 0; i < idx; i++) {
+        const uint32_t key = __ldg(o.k + i);
+        ip += int((key >> 3) & 3u) + ((key & 7u) == uint32_t(T_O) ? 4 : 0);
+    }
+    return o.p + ip;
 }
 
 // The whole factor of a candidate-side O entry below the 0.02 shortcut against a plain reference run of the removed list
@@ -239,8 +256,11 @@ __device__ __noinline__ double scan_site_general(const DevModel& m, uint32_t k1,
 // in every iteration -- x * 1.0 == x exactly -- and a cursor that does not advance re-reads its entry.  A site without a
 // precomputed factor takes the general code then and there (a call inside the iteration, after which the lanes go on together:
 // a lane that stopped to wait for the others would have to run the rest of its lists on its own afterwards).
+template <class GetOrig>
 __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, const double* pP, const uint2* eC, const double* pC, bool isTipC,
-                                            double bLen, const double* one /* a 1.0 next to the lists (same memory space) */) {
+                                            double bLen, const double* one /* a 1.0 next to the lists (same memory space) */,
+                                            GetOrig getOrig /* () -> ScanOrig: the stored list the candidate side was copied from */) {
+    const uint2* const eP0 = eP;
     const int lRef = m.lRef;
     const char* const fC = reinterpret_cast<const char*>(pC - 1);  // factor slots: payload base - 8 + offset
     const char* const fP = reinterpret_cast<const char*>(pP - 1);
@@ -255,7 +275,9 @@ __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, 
         const int e1 = int(a.x >> 8), e2 = int(b.x >> 8);
         const int np = min(e1, e2);
         if ((mm & (SA_FAST | SA_TYPES)) && !(mm & SA_FAST)) {  // an informative site without a precomputed factor
-            F = scan_site_general(m, a.x, pP + ((a.y & SA_OFF) >> 3), b.x, pC + ((b.y & SA_OFF) >> 3), np - 1, bLen, isTipC, F);
+            const double* pay1 = pP + ((a.y & SA_OFF) >> 3);
+            if (a.y & SA_FAST_PO) pay1 = scan_orig_payload(getOrig(), int(eP - eP0));  // an O entry copied without its vector
+            F = scan_site_general(m, a.x, pay1, b.x, pC + ((b.y & SA_OFF) >> 3), np - 1, bLen, isTipC, F);
         } else {
             // the factor, if there is one: the removed side's slot (bits 31, 28) or the candidate side's (30, 29, 27)
             const bool fromC = (mm & (SA_FAST_C | SA_FAST_CO)) != 0;
@@ -312,9 +334,9 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
         const int type = int(key & 7u);
         const int nl = int((key >> 3) & 3u);
         np += nl + (type < 4 ? 1 : 0);
-        if (type == T_O) {  // [a], the vector and, below the 0.02 shortcut, [q0..q3] (sized as without the error model)
-            np += 5;
-            if (!(__ldg(T.pay + T.payStart[id] + ip + nl + int((key >> 6) & 3u)) > 0.02)) np += 4;
+        if (type == T_O) {  // [a] and, below the 0.02 shortcut, the vector and [q0..q3] (sized as without the error model)
+            np += 1;
+            if (!(__ldg(T.pay + T.payStart[id] + ip + nl + int((key >> 6) & 3u)) > 0.02)) np += 8;
             ip += 4;
         }
         ip += nl;
@@ -563,7 +585,10 @@ __device__ inline void dense_score_task(const DevModel& m, const DevTree& t, Den
         if (h.units > 0 && have) {
             const uint2* eC = reinterpret_cast<const uint2*>(&W.cBuf[b][1]);
             const double* pC = reinterpret_cast<const double*>(&W.cBuf[b][1 + h.entUnits]);
-            const double sc = scan_walk(m, eP, pP, eC, pC, h.isTip != 0, rowBLen[row], &W.one);
+            const double sc = scan_walk(m, eP, pP, eC, pC, h.isTip != 0, rowBLen[row], &W.one, [&]() {
+                const int64_t id = 3 * (int64_t)t.nNodes + __ldg(&t.scan2[colPos[col]].node);
+                return ScanOrig{t.key + t.keyStart[id], t.pay + t.payStart[id]};
+            });
             scores[(size_t)row * stride + col] = sc;
         }
         __syncwarp();
@@ -782,7 +807,10 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
                 const uint4* base = winPool + (myOff - off0);
                 const uint2* eP = reinterpret_cast<const uint2*>(base);
                 const double* pP = reinterpret_cast<const double*>(base + (myCnt & 0xffffu));
-                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen, &W.one);
+                sc = scan_walk(m, eP, pP, cEnt, cPay, isRemovedTip, removedBLen, &W.one, [&]() {
+                    const int64_t id = 3 * (int64_t)t.nNodes + __ldg(&t.scan2[pos + W.slotS[lane]].node);
+                    return ScanOrig{t.key + t.keyStart[id], t.pay + t.payStart[id]};
+                });
             } else {
                 const int64_t id = 3 * (int64_t)t.nNodes + __ldg(&t.scan2[pos + W.slotS[lane]].node);
                 sc = scan_append_generic(m, t.key + t.keyStart[id], t.pay + t.payStart[id], J.remK, J.remP, isRemovedTip, removedBLen);

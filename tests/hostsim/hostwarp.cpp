@@ -232,7 +232,7 @@ double hw_scan_append(const DevModel* m, const uint32_t* kP, const double* pP, i
     const double one = 1.0;
     if (__double2hiint(kMinCarryOver) != kMinCarryOverHi) return NAN;  // scan_walk's screen of the carry-over test
     double r = 0.0;
-    hostwarp::run_warp([&]() { if ((threadIdx.x & 31) == 0) r = scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen, &one); });
+    hostwarp::run_warp([&]() { if ((threadIdx.x & 31) == 0) r = scan_walk(*m, eP.data(), yP.data(), eC.data(), yC.data(), isTipC != 0, bLen, &one, [&]() { return ScanOrig{kP, pP}; }); });
     return r;
 }
 
