@@ -552,17 +552,22 @@ def main():
     for w in range(max(args.warmup, 1)):
         out = step(d_nodes)
         if w == 0 and world > 1:  # re-deal by measured cost
-            cyc = tree.search_cost[d_nodes.long()].clone()
-            pad = torch.zeros(per_rank, dtype=torch.int64, device=dev)
-            pad[: cyc.numel()] = cyc
-            allc = torch.empty(world * per_rank, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allc, pad)
-            allc = allc.cpu().numpy().reshape(world, per_rank)
+            # two measures per search, all-gathered: the cycles it took (they order a shard and pick the searches that get an SM
+            # each, DeviceTree.spr_search) and the candidates it scored -- the cycles of a search include waiting for the
+            # lanes it shares its warp with, so shards of equal summed cycles are not shards of equal work; candidates are
+            both = torch.zeros((per_rank, 2), dtype=torch.int64, device=dev)
+            both[: d_nodes.numel(), 0] = tree.search_cost[d_nodes.long()]
+            both[: d_nodes.numel(), 1] = torch.from_numpy(tree.search_records(out)["phase1"].astype(np.int64)).to(dev)
+            allc = torch.empty((world * per_rank, 2), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allc, both)
+            allc = allc.cpu().numpy().reshape(world, per_rank, 2)
+            cyc_all = np.zeros(len(nodes), np.float64)
             cost = np.zeros(len(nodes), np.float64)
             for r in range(world):
                 pos = shard_positions(len(nodes), r, world)
-                cost[pos] = allc[r, : len(pos)]
-            tree.search_cost[torch.as_tensor(nodes, dtype=torch.int64, device=dev)] = torch.as_tensor(cost, dtype=torch.int64, device=dev)
+                cyc_all[pos] = allc[r, : len(pos), 0]
+                cost[pos] = allc[r, : len(pos), 1] + 500.0  # + the search's own merges and branch lengths, in candidates' worth
+            tree.search_cost[torch.as_tensor(nodes, dtype=torch.int64, device=dev)] = torch.as_tensor(cyc_all, dtype=torch.int64, device=dev)
             mine = shard_nodes(nodes, rank, world, cost)
             d_nodes = torch.as_tensor(mine, dtype=torch.int32, device=dev)
             from maple_b200.sharding import shard_sizes
@@ -599,9 +604,13 @@ def main():
     cand = torch.tensor([int(rec["phase1"].sum()), int((rec["status"] == 0).sum()), int((rec["status"] == 3).sum()),
                          int((rec["placement"] >= 0).sum())], dtype=torch.int64, device=dev)
     tmax = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    kern_all = [kern_ms]
     if world > 1:
         dist.all_reduce(cand)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        kt = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(kt, torch.tensor([kern_ms], dtype=torch.float64, device=dev))
+        kern_all = [round(float(x), 1) for x in kt.tolist()]
     cand_total, searched, overflowed, proposals = (int(x) for x in cand.tolist())
     total_ms = float(tmax.item())
     value = cand_total * args.steps / (total_ms / 1e3)
@@ -668,7 +677,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(len(mine) * 4), "d2h_bytes_per_step": int(len(mine) * 64),
                 "note": "pinned host node ids in, result records out, per rank"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "k_spr_search_fsm<7,true>", "kernel_ms": kern_ms, "alg_bytes_per_launch": int(alg_bytes),
+                     "kernel": "k_spr_search_fsm<7,true,false>", "kernel_ms": kern_ms, "kernel_ms_per_rank": kern_all, "alg_bytes_per_launch": int(alg_bytes),
                      "mean_mid_branch_list_bytes": round(mean_tot_bytes, 1),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
     }

@@ -256,14 +256,28 @@ __device__ __noinline__ double scan_site_general(const DevModel& m, uint32_t k1,
 // in every iteration -- x * 1.0 == x exactly -- and a cursor that does not advance re-reads its entry.  A site without a
 // precomputed factor takes the general code then and there (a call inside the iteration, after which the lanes go on together:
 // a lane that stopped to wait for the others would have to run the rest of its lists on its own afterwards).
+// :6772-6783, out of line (it is rare): F has fallen to minimumCarryOver or below.  Returns (F, Lk) after the carry-over; F = -1:
+// the reference returns -inf.  (By value: arguments by reference would pin the walk's accumulators in local memory.)
+struct ScanCarry {
+    double F, Lk;
+};
+__device__ __noinline__ ScanCarry scan_carry_over(double F, double Lk) {
+    if (F <= kMinCarryOver) {
+        if (F < DBL_MIN) return ScanCarry{-1.0, Lk};
+        Lk += log(F);
+        F = 1.0;
+    }
+    return ScanCarry{F, Lk};
+}
+
 template <class GetOrig>
 __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, const double* pP, const uint2* eC, const double* pC, bool isTipC,
                                             double bLen, const double* one /* a 1.0 next to the lists (same memory space) */,
                                             GetOrig getOrig /* () -> ScanOrig: the stored list the candidate side was copied from */) {
-    const uint2* const eP0 = eP;
     const int lRef = m.lRef;
     const char* const fC = reinterpret_cast<const char*>(pC - 1);  // factor slots: payload base - 8 + offset
     const char* const fP = reinterpret_cast<const char*>(pP - 1);
+    int iP = 0, iC = 0;
     uint2 a = eP[0], b = eC[0];
     double F = 1.0;
     double Lk = bLen * (-(double)lRef);
@@ -276,7 +290,7 @@ __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, 
         const int np = min(e1, e2);
         if ((mm & (SA_FAST | SA_TYPES)) && !(mm & SA_FAST)) {  // an informative site without a precomputed factor
             const double* pay1 = pP + ((a.y & SA_OFF) >> 3);
-            if (a.y & SA_FAST_PO) pay1 = scan_orig_payload(getOrig(), int(eP - eP0));  // an O entry copied without its vector
+            if (a.y & SA_FAST_PO) pay1 = scan_orig_payload(getOrig(), iP);  // an O entry copied without its vector
             F = scan_site_general(m, a.x, pay1, b.x, pC + ((b.y & SA_OFF) >> 3), np - 1, bLen, isTipC, F);
         } else {
             // the factor, if there is one: the removed side's slot (bits 31, 28) or the candidate side's (30, 29, 27)
@@ -284,23 +298,24 @@ __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, 
             const char* src = (fromC ? fC : fP) + ((fromC ? b.y : a.y) & SA_OFF);
             if (!(mm & SA_FAST)) src = reinterpret_cast<const char*>(one);
             double f = *reinterpret_cast<const double*>(src);
-            if ((mm & SA_FAST) == SA_FAST_P) {  // min(0.25, [g] * bLen); the cap hardly ever applies, and neither is ever a NaN
+            if ((mm & SA_FAST) == SA_FAST_P) {  // min(0.25, [g] * bLen): neither is ever a NaN, so the cap applies from 0.25 up
                 f *= bLen;
-                if (__double2hiint(f) >= 0x3fd00000) f = fmin(0.25, f);
+                if (__double2hiint(f) >= 0x3fd00000) f = 0.25;
             }
             F *= f;
         }
         if (np == lRef) break;
-        // F <= minimumCarryOver (:6772-6783; also catches the -1 marker of an impossible site), screened by the high word first
-        if (__double2hiint(F) <= kMinCarryOverHi && F <= kMinCarryOver) {
-            if (F < DBL_MIN) return -INFINITY;
-            Lk += log(F);
-            F = 1.0;
+        // F <= minimumCarryOver (also catches the -1 marker of an impossible site): screened by the high word
+        if (__double2hiint(F) <= kMinCarryOverHi) {
+            const ScanCarry c = scan_carry_over(F, Lk);
+            if (c.F < 0.0) return -INFINITY;
+            F = c.F;
+            Lk = c.Lk;
         }
-        eP += (e1 == np);
-        eC += (e2 == np);
-        a = *eP;
-        b = *eC;
+        iP += (e1 == np);
+        iC += (e2 == np);
+        a = eP[iP];
+        b = eC[iC];
     }
     if (!(F > 0.0)) return -INFINITY;
     return Lk + log(F);
