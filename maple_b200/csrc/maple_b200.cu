@@ -47,6 +47,7 @@ struct maple_ctx {
     cudaStream_t criticalStream = nullptr;
     cudaEvent_t criticalEvA = nullptr, criticalEvB = nullptr;
     unsigned long long* criticalCounter = nullptr;
+    size_t criticalHogSmem = 0;
     bool scanReplaySequential = false;  // A/B: node-by-node window replay instead of the pointer-jumping one
     bool scanAppendSitewise = true;   // A/B: break-at-every-site appendProbNode in the scans instead of the queued one
     int fsmMinBlocks = 7;            // __launch_bounds__ minimum CTAs per SM of the state-machine kernel (7 -> 128 registers, 6 -> 168)
@@ -458,11 +459,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_spr_search(const __grid_cons
     }
 }
 
-// Holds the stream until `want` CTAs of a launch on another stream have started (BigScratch::started), or ~2 ms have passed:
-// the launch that follows then finds those CTAs resident and is scheduled around them.
+// Holds the stream until `want` CTAs of a launch on another stream have started (BigScratch::started), or ~0.1 s have passed:
+// the launch that follows then finds those CTAs resident and is scheduled around them.  (Without it the launch that follows
+// may take every SM first, and CTAs that need a whole SM each then wait for it to end.  The first such launch of a process has
+// been seen to take well over 2 ms to start.)
 __global__ void k_wait_started(const unsigned long long* started, unsigned long long want) {
     const long long t0 = clock64();
-    while (ld_volatile_u64(started) < want && clock64() - t0 < 4000000LL) spin_pause(200);
+    while (ld_volatile_u64(started) < want && clock64() - t0 < 200000000LL) spin_pause(500);
 }
 
 // The same searches as k_spr_search, one per lane, but as resumable state machines (search_fsm.cuh): every loop
@@ -1151,8 +1154,23 @@ int maple_spr_search_batch(maple_ctx* ctx, const maple_search_params* p, int64_t
     }
     if (scan2 && (ctx->fsmSMs != 0 || ctx->denseMode != 0))
         fsmKernel = ctx->fsmMinBlocks == 6 ? k_spr_search_fsm<6, true, true> : k_spr_search_fsm<7, true, true>;
+    if (scan2 && !ctx->criticalStream) {
+        // what a launch with critical searches needs, set up with the first batch of a context whether or not it has any: the
+        // first use must not cost more than the later ones (callers compare the two launch shapes by their time)
+        CK(cudaStreamCreateWithFlags(&ctx->criticalStream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->criticalEvA, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->criticalEvB, cudaEventDisableTiming));
+        CK(cudaMalloc((void**)&ctx->criticalCounter, sizeof(unsigned long long)));
+        int maxOptin = 0;
+        CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, k_spr_search_fsm<7, true, false>));
+        ctx->criticalHogSmem = (size_t)maxOptin - fa.sharedSizeBytes;
+        CK(cudaFuncGetAttributes(&fa, k_wait_started));  // (loads it)
+    }
     if (ctx->searchVariant != 1) {
-        CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmSmem));
+        CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(scan2 && ctx->criticalHogSmem > fsmSmem ? ctx->criticalHogSmem : fsmSmem)));
         CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, fsmKernel, kSearchThreads, fsmSmem));
     }
@@ -1214,7 +1232,8 @@ noService:
     // lanes that own a search (and scratch); with the scan service: the warps of fsmSMs SMs and of CTA 0
     const size_t owners = fsmSMs > 0 ? ((size_t)fsmSMs * blocksPerSM + 1) * (kSearchThreads / 32) * 32 : (size_t)threads / 32 * lpw;
     const size_t mainBytes = (perThread * owners + 255) & ~size_t(255);
-    const size_t need = mainBytes + perThread * (size_t)nCrit + 256;
+    // (room for the searches of a critical launch always: switching it on must not cost a reallocation)
+    const size_t need = mainBytes + perThread * (size_t)(ctx->numSMs / 2) + 256;
     if (need > ctx->searchScratchBytes) {
         cudaFree(ctx->searchScratch);
         ctx->searchScratch = nullptr;
@@ -1272,7 +1291,7 @@ noService:
         // evaluatePlacement (a few hundred entries) fit; an entry that does not is evaluated by the owning lane in its own scratch
         es.capK = 1024; es.capP = 6 * 1024; es.capA = 1024;
         const size_t perLane = (size_t)es.capK * 4 + (size_t)es.capP * 8 + (size_t)es.capA * 8;
-        const size_t needE = perLane * ((size_t)threads + (size_t)nCrit * 32) + 256;
+        const size_t needE = perLane * ((size_t)threads + (size_t)(ctx->numSMs / 2) * 32) + 256;
         if (needE > ctx->evalBytes) {
             cudaFree(ctx->evalMem);
             ctx->evalMem = nullptr;
@@ -1381,18 +1400,7 @@ noService:
     long long* cyclesMain = out_cycles ? (long long*)out_cycles + nCrit : nullptr;
     if (nCrit) {
         // The critical launch goes first, on a stream of its own; a one-thread gate holds this stream until its CTAs are resident.
-        if (!ctx->criticalStream) {
-            CK(cudaStreamCreateWithFlags(&ctx->criticalStream, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&ctx->criticalEvA, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ctx->criticalEvB, cudaEventDisableTiming));
-            CK(cudaMalloc((void**)&ctx->criticalCounter, sizeof(unsigned long long)));
-        }
-        cudaFuncAttributes fa;
-        CK(cudaFuncGetAttributes(&fa, fsmKernel));
-        int maxOptin = 0;
-        CK(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-        const size_t hogSmem = (size_t)maxOptin - fa.sharedSizeBytes;  // a whole SM's shared memory: nothing else fits next to this CTA
-        CK(cudaFuncSetAttribute(fsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hogSmem));
+        const size_t hogSmem = ctx->criticalHogSmem;  // a whole SM's shared memory: nothing else fits next to this CTA
         const unsigned long long firstC = (unsigned long long)nCrit;  // one search per CTA, handed out statically; the counter has nothing more
         CK(cudaMemcpyAsync(ctx->criticalCounter, &firstC, sizeof firstC, cudaMemcpyHostToDevice, (cudaStream_t)stream));
         char* base2 = base + mainBytes;

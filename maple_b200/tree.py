@@ -568,9 +568,11 @@ class DeviceTree:
         (kept on the device in self.search_cost; nodes never searched before go first).  The tree hardly changes between the
         rounds of a run, so this is the LPT rule with last round's lengths.  Results do not depend on the order.
 
-        critical: how many of the longest searches get an SM each (maple_ctx_set_critical_searches); None = decided from
-        last round's lengths: when the longest search alone is longer than the whole batch would take at full throughput (a
-        shard of a multi-GPU round), every search longer than the time the batch is then expected to take."""
+        critical: how many of the longest searches get an SM each (maple_ctx_set_critical_searches).  None = found out by
+        measurement: a run repeats rounds of about the same size on a tree that hardly changes, so the first sorted round of a
+        size runs without, the next with the longest searches (_critical_count) on SMs of their own, and the faster of the two
+        shapes -- device time of the launch -- is kept for that size.  (On a whole 100 000-sequence round the plain launch
+        wins; on an eighth of it, one GPU's share of an 8-GPU round, the other one does by a third.)"""
         eng, dev = self.eng, self.eng.device
         if getattr(self, "_bound_epoch", None) != self.arena.epoch:
             self.prepare_search()  # never bound, or the arena's tables moved since (temporary lists added / released)
@@ -581,11 +583,15 @@ class DeviceTree:
             cost = self.search_cost = torch.full((self.n,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
         perm = None
         k = 0
+        trial = None
         if schedule and n > 1:
             mine = cost[nodes.long()]
             perm = torch.argsort(mine, descending=True, stable=True)
             run_nodes = nodes[perm].contiguous()
-            k = self._critical_count(mine[perm], n) if critical is None else int(critical)
+            if critical is None:
+                k, trial = self._critical_auto(mine[perm], n)
+            else:
+                k = int(critical)
         else:
             run_nodes = nodes
         k = max(0, min(k, n // 4))
@@ -594,9 +600,14 @@ class DeviceTree:
             self._critical_set = k
         out = torch.zeros((n, 64), dtype=torch.uint8, device=dev)
         cyc = torch.zeros(n, dtype=torch.int64, device=dev)
+        if trial is not None:
+            trial["ev"] = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            trial["ev"][0].record()
         rc = eng.lib.maple_spr_search_batch(eng.ctx, C.byref(params), n, _dp(run_nodes), _dp(out), int(scratch_keys),
                                             int(max_concurrent), _dp(cyc), eng._stream())
         capi.check(eng.ctx, rc, "maple_spr_search_batch")
+        if trial is not None:
+            trial["ev"][1].record()
         cost[run_nodes.long()] = cyc
         if k:
             cost[run_nodes[:k].long()] = (cyc[:k].double() * self.ALONE_TO_BUSY).long()
@@ -610,24 +621,52 @@ class DeviceTree:
             cycles.copy_(cyc)
         return out
 
+    def _critical_auto(self, sorted_cost: torch.Tensor, n: int):
+        """The number of searches to give an SM each in this round, and (while the two launch shapes are still being compared
+        for this batch size) the record in which spr_search leaves the events that time the launch.  See spr_search."""
+        if not torch.cuda.is_available():
+            return 0, None
+        st = getattr(self, "_critical_state", None)
+        if st is None or abs(n - st["n"]) > 0.2 * st["n"]:
+            st = self._critical_state = {"n": n, "ms": {}, "pending": None, "k": 0, "choice": None}
+        if st["pending"] is not None:  # the launch timed last time
+            which, rec = st["pending"]
+            st["pending"] = None
+            try:
+                rec["ev"][1].synchronize()
+                st["ms"][which] = float(rec["ev"][0].elapsed_time(rec["ev"][1]))
+            except Exception:
+                st["ms"][which] = float("inf")
+        if st["choice"] is not None:
+            return (st["k"] if st["choice"] == "on" else 0), None
+        if "off" not in st["ms"]:
+            if float(sorted_cost[0].item()) >= float(torch.iinfo(torch.int64).max) / 2:
+                return 0, None  # searches with no recorded length yet: this round only measures them
+            rec = {}
+            st["pending"] = ("off", rec)
+            return 0, rec
+        if "on" not in st["ms"]:
+            st["k"] = self._critical_count(sorted_cost, n)
+            if st["k"] == 0:
+                st["choice"] = "off"
+                return 0, None
+            rec = {}
+            st["pending"] = ("on", rec)
+            return st["k"], rec
+        st["choice"] = "on" if st["ms"]["on"] < 0.97 * st["ms"]["off"] else "off"
+        return (st["k"] if st["choice"] == "on" else 0), None
+
     def _critical_count(self, sorted_cost: torch.Tensor, n: int) -> int:
-        """See spr_search.  sorted_cost: last round's cycles of this batch's searches, longest first (device)."""
+        """How many of the longest searches would get an SM each: those that took at least half as long as the longest one, at
+        most a ninth of the SMs.  sorted_cost: last round's cycles of this batch's searches, longest first (device)."""
         sms = int(getattr(self.eng, "num_sms", 148))
         cap = max(1, sms // 9)
-        if n < 64 or cap < 1:
+        if n < 64:
             return 0
-        warps = sms * 16
-        lpw = min(32, max(2, -(-n // (warps * 3))))  # searches per warp as maple_spr_search_batch chooses them
-        head = sorted_cost[:cap + 1]
-        stats = torch.cat([head.double(), sorted_cost.double().sum().reshape(1)]).cpu().numpy()
-        c, total = stats[:-1], stats[-1]
-        if c[0] >= float(torch.iinfo(torch.int64).max) / 2 or total <= 0:  # searches with no recorded length yet
+        c = sorted_cost[:cap].double().cpu().numpy()
+        if c[0] <= 0 or c[0] >= float(torch.iinfo(torch.int64).max) / 2:
             return 0
-        t_full = total / (warps * lpw)  # cycles the batch takes when every lane is busy all the time
-        if c[0] < 1.1 * t_full:
-            return 0
-        target = max(1.15 * t_full, c[0] / self.ALONE_TO_BUSY)
-        return int(min(cap, (c[:cap] > target).sum()))
+        return int(max(4, min(cap, (c >= 0.5 * c[0]).sum())))
 
     # ------------------------------------------------------------------ findBestParentForNewSample for a batch (:7912, :11190-11287)
     def stage_samples(self, samples: PackedLists):
