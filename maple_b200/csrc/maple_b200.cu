@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(256) k_scan_prepare(const __grid_constant__ De
 
 // ---- scan-format copies of the probVectTotUp lists (scan2.cuh), one thread per pre-order position
 // sizes, at maple_tree_bind: 16-byte units of the copy of the list at each position (0 = no list / too large to stage)
-__global__ void __launch_bounds__(256) k_scan_count(const __grid_constant__ DevTree T, uint32_t* __restrict__ units) {
+__global__ void __launch_bounds__(256) k_scan_count(const __grid_constant__ DevTree T, uint32_t* __restrict__ units, bool U) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < T.nNodes) units[i] = scan_count_units(T, i);
+    if (i < T.nNodes) units[i] = scan_count_units(T, i, U);
 }
 
 // per launch: the copies themselves (they hold Q * siteRate, so they follow the model) and the records
@@ -1071,7 +1071,7 @@ int maple_tree_bind(maple_ctx* ctx, int32_t nNodes, int32_t root, const int32_t*
         ctx->scanOffsets = ctx->scanUnits + n;
         DevTree T = t;
         T.key = ctx->key; T.pay = ctx->pay; T.keyStart = ctx->keyStart; T.payStart = ctx->payStart;
-        k_scan_count<<<(unsigned)((n + 255) / 256), 256>>>(T, ctx->scanUnits);
+        k_scan_count<<<(unsigned)((n + 255) / 256), 256>>>(T, ctx->scanUnits, ctx->model.U != 0);
         ctx->launches++;
         std::vector<uint32_t> hu(n), ho(n);
         CK(cudaMemcpy(hu.data(), ctx->scanUnits, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));

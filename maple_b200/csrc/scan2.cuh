@@ -75,7 +75,9 @@ inline T ld_cg(const T* p) { return *p; }
 //   bit 27     candidate side: O entry below that shortcut whose [a] slot the job has overwritten with its whole factor against a
 //              plain reference run (scan_convert_slow_o, on the job's own staged copy); removed side: plain reference run
 //              (type R, no lengths) -> the factor is that slot
-//   (bits 27/30/31 are only set without the error model: with it those sites take the general code; 28/29 hold with it too)
+//   (under the error model the removed side's [f] carries the error term of :6657 where there is one, a candidate-side
+//   nucleotide entry has [e] = 0.33333 * error rate of the site in front of its [g], which the walk adds to the factor of bit 30
+//   when the removed node is a tip (:6742), and bit 27 is not set on the removed side then -- those sites take the general code)
 constexpr int kMinCarryOverHi = 0x0a711b0e;  // high word of kMinCarryOver = DBL_MIN * 1e50 (checked in scan_walk's host build)
 constexpr uint32_t SA_OFF = 0xffffu /* bytes */, SA_TYPES = 0x7f0000u, SA_FAST_C = 0x80000000u, SA_FAST_P = 0x40000000u, SA_FAST_PO = 0x20000000u,
                    SA_FAST_CO = 0x10000000u, SA_FAST_PS = 0x08000000u, SA_FAST = 0xf8000000u;
@@ -108,17 +110,17 @@ __device__ inline int scan_build_p(const DevModel& m, const uint32_t* k, const d
         uint32_t aux = 1u << (16 + type);
         bool slowO = false;
         if (type == T_R) aux |= SA_FAST_CO;
-        if (!m.U) {
-            if (type == T_R && nl == 0) aux |= SA_FAST_C;
-            if (type < 4 && nl == 0) aux |= SA_FAST_P;
-        }
+        if (type == T_R && nl == 0) aux |= SA_FAST_C;
+        if (type < 4 && nl == 0) aux |= SA_FAST_P;
         if (type < 4) {
             const SiteQ q(m, end - 1);
+            // under the error model, in front of [g]: the term a removed TIP adds to the factor min(0.25, [g] * bLen) (:6742)
+            if (m.U) outP[np++] = (double)(1) * 0.33333 * site_eps(m, end - 1);
             outP[np++] = q.at(type, nuc);  // [g] = mutMatrices[pos][nuc of the entry][reference nuc]
         } else if (type == T_O) {  // [a]: the shortcut's probability, or room for the job's own factor (bit 27)
             const double a = __ldg(p + ip + nl + nuc);
             if (a > 0.02) aux |= SA_FAST_PO;
-            else if (!m.U) {
+            else {
                 slowO = true;
                 if (nSlow < 2) slow |= uint32_t(i < 0x7fff ? i : 0x7fff) << (15 * nSlow);
                 nSlow++;
@@ -182,7 +184,8 @@ __device__ __forceinline__ double scan_slow_o_factor(uint32_t key, const double*
 }
 
 // Removed-side copy (one per job, shared memory).  Returns the payload doubles written, or -1 if it does not fit.
-__device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const double* p, double bLen, uint2* outE, int capE, double* outP, int capP) {
+__device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const double* p, double bLen, bool isTipC, uint2* outE, int capE, double* outP,
+                                   int capP) {
     constexpr unsigned long long INF = append_informative_mask();
     int np = 0, ip = 0;
     for (int i = 0;; i++) {
@@ -192,12 +195,14 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
         if (np + 8 > capP || (np + 8) * 8 > int(SA_OFF)) return -1;
         uint32_t row = 0;
         for (int t1 = 0; t1 < 7; t1++) row |= uint32_t((INF >> (t1 * 8 + type)) & 1ull) << t1;
-        const bool fastNuc = !m.U && type < 4 && nl <= 1;
+        const bool fastNuc = type < 4 && nl <= 1;
         uint32_t aux = row << 16;
         if (fastNuc) aux |= SA_FAST_C;
         if (type == T_R) aux |= SA_FAST_PO;
-        // (bLen == 0 included: the factor min(0.25, g * 0) = 0 makes the walk return -inf there, as the reference does, :6663)
-        if (!m.U && type == T_R && nl == 0) aux |= SA_FAST_P | SA_FAST_PS;
+        // (bLen == 0 included: the factor min(0.25, g * 0) = 0 makes the walk return -inf there, as the reference does, :6663.
+        //  Under the error model the candidate side's factors against a plain reference run pick up an error term when the
+        //  removed node is a tip (:6729-6742, :6696): the walk adds it for a nucleotide; an O entry takes the general code then.)
+        if (type == T_R && nl == 0) aux |= (m.U && isTipC) ? SA_FAST_P : (SA_FAST_P | SA_FAST_PS);
         if (type == T_O) {
             const double a = ld_cg(p + ip + nl + nuc);
             if (a > 0.02) {
@@ -211,8 +216,12 @@ __device__ inline int scan_build_c(const DevModel& m, const uint32_t* k, const d
             const double g = q.at(nuc, type);  // mutMatrices[pos][reference nuc][nuc of the entry]
             double contrib = bLen;
             if (nl == 1) contrib += ld_cg(p + ip);
-            // the whole factor against a plain reference run of the candidate (:6657-6663); -1 marks "the reference returns -inf"
-            outP[np++] = (contrib == 0.0) ? -1.0 : fmin(0.25, g * contrib);
+            // the whole factor against a plain reference run of the candidate (:6640-6663); -1 marks "the reference returns -inf"
+            const bool flag2 = m.U && (isTipC || (nl > 0 && ((key >> 5) & 1u)));
+            double f;
+            if (flag2) f = fmin(0.25, g * contrib) + site_eps(m, end - 1) * 0.33333;
+            else f = (contrib == 0.0) ? -1.0 : fmin(0.25, g * contrib);
+            outP[np++] = f;
             for (int q2 = 0; q2 < nl; q2++) outP[np++] = ld_cg(p + ip + q2);
             ip += nl;
             outP[np++] = g;
@@ -281,7 +290,8 @@ __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, 
     uint2 a = eP[0], b = eC[0];
     double F = 1.0;
     double Lk = bLen * (-(double)lRef);
-    if (m.U && isTipC) Lk += m.totError;
+    const bool uTip = m.U && isTipC;
+    if (uTip) Lk += m.totError;
     SCAN_HIST(9);
     for (;;) {
         SCAN_HIST(8);
@@ -301,6 +311,7 @@ __device__ __forceinline__ double scan_walk(const DevModel& m, const uint2* eP, 
             if ((mm & SA_FAST) == SA_FAST_P) {  // min(0.25, [g] * bLen): neither is ever a NaN, so the cap applies from 0.25 up
                 f *= bLen;
                 if (__double2hiint(f) >= 0x3fd00000) f = 0.25;
+                if (uTip) f += *reinterpret_cast<const double*>(src - 8);  // error model, removed tip: + [e]
             }
             F *= f;
         }
@@ -337,7 +348,7 @@ __device__ inline uint32_t scan_static_flags(const DevTree& T, double eff, int n
 
 // 16-byte units of the scan-format copy of the probVectTotUp list at pre-order position i: entries | payload << 16
 // (0 = no list, or too large to stage).  maple_tree_bind turns these into offsets.
-__device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
+__device__ inline uint32_t scan_count_units(const DevTree& T, int i, bool U /* error model: [e] slots */) {
     const int node = T.order[i];
     if (node < 0 || T.pre[node] != i) return 0;
     const int64_t id = 3 * (int64_t)T.nNodes + node, ks = T.keyStart[id];
@@ -348,7 +359,7 @@ __device__ inline uint32_t scan_count_units(const DevTree& T, int i) {
         const uint32_t key = __ldg(T.key + ks + q);
         const int type = int(key & 7u);
         const int nl = int((key >> 3) & 3u);
-        np += nl + (type < 4 ? 1 : 0);
+        np += nl + (type < 4 ? (U ? 2 : 1) : 0);
         if (type == T_O) {  // [a] and, below the 0.02 shortcut, the vector and [q0..q3] (sized as without the error model)
             np += 1;
             if (!(__ldg(T.pay + T.payStart[id] + ip + nl + int((key >> 6) & 3u)) > 0.02)) np += 8;
@@ -533,7 +544,7 @@ __device__ inline void dense_prepare_entry(const DevModel& m, const DevTree& T, 
     uint4* slot = cArena + row * (size_t)kDenseCUnits;
     const int entUnits = (own.nk + 1) >> 1;
     const int capP = (kDenseCUnits - 1 - entUnits) * 2;
-    const int npC = scan_build_c(m, own.k, own.p, T.dist[node], reinterpret_cast<uint2*>(slot + 1), own.nk,
+    const int npC = scan_build_c(m, own.k, own.p, T.dist[node], T.isTip[node] != 0, reinterpret_cast<uint2*>(slot + 1), own.nk,
                                  reinterpret_cast<double*>(slot + 1 + entUnits), capP);
     DenseRowHeader h;
     h.entUnits = entUnits; h.units = npC < 0 ? 0 : entUnits + ((npC + 1) >> 1); h.isTip = T.isTip[node] != 0; h.pad = 0;
@@ -669,7 +680,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
         cEntUnits = (nkC + 1) >> 1;
         const int capP = ((poolBytes >> 1) - 16 * cEntUnits) >> 3;
         if (nkC <= capE && capP >= 8) {
-            const int npC = scan_build_c(m, J.remK, J.remP, removedBLen, reinterpret_cast<uint2*>(W.pool), nkC,
+            const int npC = scan_build_c(m, J.remK, J.remP, removedBLen, isRemovedTip, reinterpret_cast<uint2*>(W.pool), nkC,
                                          reinterpret_cast<double*>(W.pool + cEntUnits), capP);
             if (npC >= 0) cUnits = cEntUnits + ((npC + 1) >> 1);
         }
@@ -778,7 +789,7 @@ __device__ void warp_scan_job2(const DevModel& m, const DevTree& t, const Search
             // two of a list) get their whole factor against a plain reference run of the removed list written into their [a]
             // slot (bit 27), so that the walk below finds a precomputed factor there as well -- most of the sites that would
             // take the general code are of this kind.  One entry per lane, whichever candidate it belongs to.
-            if (!EXTRAS && !m.U) {
+            if (!EXTRAS && !(m.U && isRemovedTip)) {
                 const uint32_t slow = lane < nScore ? uint32_t(W.colS[lane]) : 0u;
                 const int nSlow = min(int(slow >> 30), 2);
                 int before = nSlow;

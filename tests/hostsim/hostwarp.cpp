@@ -77,7 +77,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
         if (height >= 65535) return -1;
         uint64_t tot = 0;
         for (size_t i = 0; i < N; i++) {
-            units[i] = scan_count_units(T, (int)i);
+            units[i] = scan_count_units(T, (int)i, m->U != 0);
             if (units[i] == ~0u) units[i] = 0;
             const uint64_t u = (units[i] & 0xffffu) + (units[i] >> 16);
             if (u == 0) { offs[i] = ~0u; continue; }
@@ -220,8 +220,8 @@ double hw_scan_append(const DevModel* m, const uint32_t* kP, const double* pP, i
     std::vector<double> yP(12 * (size_t)nkP + 8), yC(8 * (size_t)capE);
     uint32_t slow = 0;
     scan_build_p(*m, kP, pP, nkP, eP.data(), yP.data(), &slow);
-    if (scan_build_c(*m, kC, pC, bLen, eC.data(), capE, yC.data(), 8 * capE) < 0) return NAN;
-    if (convertSlow && !m->U)  // what a job does to its staged copy (warp_scan_job2): the factors of the O entries below the shortcut
+    if (scan_build_c(*m, kC, pC, bLen, isTipC != 0, eC.data(), capE, yC.data(), 8 * capE) < 0) return NAN;
+    if (convertSlow && !(m->U && isTipC))  // what a job does to its staged copy (warp_scan_job2): the factors of the O entries below the shortcut
         for (int r = 0; r < std::min(int(slow >> 30), 2); r++) {
             const uint32_t idx = (slow >> (15 * r)) & 0x7fffu;
             if (idx == 0x7fffu) continue;

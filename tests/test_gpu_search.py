@@ -3,6 +3,7 @@
 
 Bar: identical best node, branch lengths, phase-1 candidate counts and proposed moves; scores within 1e-9."""
 import numpy as np
+import torch
 import pytest
 
 from golden_io import hw_names as golden_names, load_golden
@@ -151,6 +152,16 @@ def test_records_do_not_depend_on_the_batch():
     rec = tree.search_records(tree.spr_search(nodes[sub], p))
     eng.set_search_variant(0)
     assert rec.tobytes() == full[sub].tobytes()
+    # the longest searches on SMs of their own (a second launch next to the usual one): explicit counts, then the choice by
+    # measurement over four rounds (plain launch, critical launch, the faster of the two twice)
+    for k in (1, 7, 40, 0):
+        assert tree.search_records(tree.spr_search(nodes, p, critical=k)).tobytes() == full.tobytes()
+        assert getattr(tree, "_critical_set", 0) == k
+    for _ in range(4):
+        assert tree.search_records(tree.spr_search(nodes, p)).tobytes() == full.tobytes()
+    if torch.cuda.is_available():  # (the dry run of this file on the stand-in library has no launches to time)
+        assert tree._critical_state["choice"] in ("on", "off")
+    tree.spr_search(nodes, p, critical=0)
     # the dense scoring pass: on, then on with a matrix that only has room for some of the searches
     eng.set_dense_scoring(1)
     assert tree.search_records(tree.spr_search(nodes, p)).tobytes() == full.tobytes()

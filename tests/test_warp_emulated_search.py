@@ -185,7 +185,7 @@ def test_second_form_big_fixture_deep_round():
     assert st[21] > 10000
 
 
-@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_err", "ex_unrest_rv_sse", "ay_unrest_300", "syn_unrest_rv_2000"])
+@pytest.mark.parametrize("name", ["ex_unrest", "ex_unrest_err", "ex_unrest_rv_sse", "ay_unrest_300", "syn_unrest_rv_2000", "syn_unrest_rv_sse_1500"])
 def test_scan_format_append_equals_dev_append(name):
     """appendProbNode through the scan-format copies (precomputed Q*rate, precomputed removed-side factors) against dev_append of
     the same source: recorded calls and random pairs of the fixture's lists with branch lengths from the corners; bit for bit."""
