@@ -69,8 +69,15 @@ __device__ __forceinline__ double py_sum4(const double* v) {
 #endif
 }
 
+// (A/B: -DMAPLE_LEAN compiles the getPartialVec helpers and tree_list out of line -- one copy each instead of one per use)
+#ifdef MAPLE_LEAN
+#define MAPLE_HELPER_INLINE __noinline__
+#else
+#define MAPLE_HELPER_INLINE __forceinline__
+#endif
+
 // getPartialVec for an O vector (:4085-4109)
-__device__ __forceinline__ void gv_vec(const SiteQ& q, double t, const double* v, bool up, double* o) {
+__device__ MAPLE_HELPER_INLINE void gv_vec(const SiteQ& q, double t, const double* v, bool up, double* o) {
     if (t == 0.0) {
         o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
         return;
@@ -93,7 +100,7 @@ __device__ __forceinline__ void gv_vec(const SiteQ& q, double t, const double* v
 // getPartialVec for a single nucleotide x (:4110-4141); `flag` already includes usingErrorRate
 // (QT: SiteQ, or anything with the same at(i, j))
 template <class QT>
-__device__ __forceinline__ void gv_nuc(const QT& q, double eps, int x, double t, bool up, bool flag, double* o) {
+__device__ MAPLE_HELPER_INLINE void gv_nuc(const QT& q, double eps, int x, double t, bool up, bool flag, double* o) {
     if (flag) {
         double nv[4];
         const double e3 = eps * 0.33333;

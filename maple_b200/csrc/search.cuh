@@ -104,7 +104,7 @@ struct StackE {
 
 __device__ __forceinline__ LRef lnull() { return LRef{nullptr, nullptr, 0}; }
 
-__device__ __forceinline__ LRef tree_list(const DevTree& t, int fam, int node) {
+__device__ MAPLE_HELPER_INLINE LRef tree_list(const DevTree& t, int fam, int node) {
     const int64_t id = (int64_t)fam * t.nNodes + node;
     const int64_t ks = t.keyStart[id];
     if (ks < 0) return lnull();

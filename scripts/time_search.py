@@ -2,6 +2,10 @@
 import math, sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
+import os
+from maple_b200 import capi
+if os.environ.get('MAPLE_LIB'):  # A/B of two builds of the library in one job
+    capi.LIB_PATH = os.path.abspath(os.environ['MAPLE_LIB'])
 from maple_b200.engine import MapleEngine
 from maple_b200.genome_list import pack_lists
 from maple_b200.search import dirty_nodes, search_params
