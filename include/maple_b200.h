@@ -240,6 +240,14 @@ int maple_ctx_set_lanes_per_warp(maple_ctx* ctx, int32_t lanes);
  * at most half the SMs; ignored when the batch has fewer than 4 * count searches.  0 (default) = off.  Same results. */
 int maple_ctx_set_critical_searches(maple_ctx* ctx, int32_t count);
 
+/* Head of the list.  count > 0: the first count entries of the node list of every following maple_spr_search_batch (sorted
+ * longest-first by the caller) are handed out one per WARP -- lane 0 of every warp pulls them, the other lanes wait until they are
+ * gone -- so that each long search has a warp to itself while it runs and the warps share the long ones out one at a time;
+ * afterwards every lane pulls as usual.  (With 28 searches to a warp from the start, the long ones advance at a fraction of the
+ * warp's speed until the short ones are gone, and the round ends with whichever warp is left holding the most.)  0 (default) =
+ * off.  Same results. */
+int maple_ctx_set_head_searches(maple_ctx* ctx, int32_t count);
+
 /* How maple_spr_search_batch (variant 0) divides the GPU: the CTAs on the first fsmSMs SMs own the searches (one per lane, their
  * merges / branch lengths / candidate scores near the pruning point run there) and post every subtree scan in a global-memory
  * slot; the CTAs of all other SMs do nothing but take scans from a ticket ring, run them and hand the results back.  0 (default)

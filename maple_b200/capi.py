@@ -41,6 +41,7 @@ SIGNATURES = {
     "maple_ctx_set_scan_service": (C.c_int, [_P, _I32]),
     "maple_ctx_set_lanes_per_warp": (C.c_int, [_P, _I32]),
     "maple_ctx_set_critical_searches": (C.c_int, [_P, _I32]),
+    "maple_ctx_set_head_searches": (C.c_int, [_P, _I32]),
     "maple_ctx_set_dense_scoring": (C.c_int, [_P, _I32, _I64]),
     "maple_update_partials": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
     "maple_blen_sweep_sequential": (C.c_int, [_P, _P, _P, _P, _P]),

@@ -43,6 +43,7 @@ struct maple_ctx {
     unsigned long long* searchStats = nullptr;  // device counters of the search kernel (maple_search_stats)
     bool statsOn = false;
     int lanesPerWarp = 0;               // searches per warp (1..32); 0 = chosen per launch from the number of searches
+    int headSearches = 0;               // the first so many entries of a batch are run one per warp (maple_ctx_set_head_searches)
     int criticalSearches = 0;           // the first so many entries of a batch run on an SM of their own each (maple_ctx_set_critical_searches)
     cudaStream_t criticalStream = nullptr;
     cudaEvent_t criticalEvA = nullptr, criticalEvB = nullptr;
@@ -1228,6 +1229,13 @@ noService:
     } else if (threads > n) threads = n;
     int blocks = (int)((threads + kSearchThreads - 1) / kSearchThreads);
     threads = (int64_t)blocks * kSearchThreads;
+    // head of the list run one per warp (maple_ctx_set_head_searches): relative to the main launch's part of the list
+    unsigned long long headEnd = 0;
+    if (scan2 && fsmSMs == 0 && ctx->searchVariant == 0 && ctx->headSearches > nCrit && max_concurrent_searches == 0 && lpw > 1) {
+        headEnd = (unsigned long long)(ctx->headSearches - nCrit);
+        if ((int64_t)headEnd > n) headEnd = (unsigned long long)n;
+        if (headEnd < (unsigned long long)(threads / 32)) headEnd = 0;  // fewer than one per warp: the static first pull does the same
+    }
     const size_t perThread = (size_t)capK * 4 + (size_t)capP * 8 + (size_t)capA * 8 + (size_t)stackCap * sizeof(StackE);
     // lanes that own a search (and scratch); with the scan service: the warps of fsmSMs SMs and of CTA 0
     const size_t owners = fsmSMs > 0 ? ((size_t)fsmSMs * blocksPerSM + 1) * (kSearchThreads / 32) * 32 : (size_t)threads / 32 * lpw;
@@ -1243,7 +1251,8 @@ noService:
     }
     if (!ctx->searchCounter) CK(cudaMalloc((void**)&ctx->searchCounter, sizeof(unsigned long long)));
     {   // the state-machine kernel hands the first `owners` entries out statically (fsm_warp_loop), the counter serves the rest
-        const unsigned long long first = (ctx->searchVariant != 1 && fsmSMs == 0) ? (unsigned long long)owners : 0ULL;
+        // (with a head of the list run one per warp, only lane 0 of every warp has a static first entry)
+        const unsigned long long first = (ctx->searchVariant != 1 && fsmSMs == 0) ? (unsigned long long)(headEnd ? owners / lpw : owners) : 0ULL;
         CK(cudaMemcpyAsync(ctx->searchCounter, &first, sizeof first, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     }
     char* base = (char*)ctx->searchScratch;
@@ -1427,10 +1436,14 @@ noService:
                                                                          scrAis, scrStack, capK, capP, capA, stackCap, ctx->searchCounter,
                                                                          (long long*)out_cycles);
     else
+    {
+        BigScratch bigMain = big;
+        bigMain.headEnd = headEnd;
         fsmKernel<<<blocks, kSearchThreads, fsmSmem, (cudaStream_t)stream>>>(ctx->model, T, sp, n, nodes, outMain, scrKey, scrPay, scrAis, scrStack, capK,
                                                                              capP, capA, stackCap, ctx->searchCounter, cyclesMain, scanMin, scanFlags,
                                                                              poolBytes, ctx->statsOn ? ctx->searchStats : nullptr, nullptr, nullptr, lpw,
-                                                                             big, sq, fsmSMs, ds, es);
+                                                                             bigMain, sq, fsmSMs, ds, es);
+    }
     if (nCrit) {
         CK(cudaStreamWaitEvent((cudaStream_t)stream, ctx->criticalEvB, 0));
         nodes = nodesAll;
@@ -1562,6 +1575,12 @@ int maple_ctx_set_search_variant(maple_ctx* ctx, int32_t variant) {
 int maple_ctx_set_lanes_per_warp(maple_ctx* ctx, int32_t lanes) {
     if (!ctx || lanes < 0 || lanes > 32) return MAPLE_E_ARG;
     ctx->lanesPerWarp = lanes;
+    return MAPLE_OK;
+}
+
+int maple_ctx_set_head_searches(maple_ctx* ctx, int32_t count) {
+    if (!ctx || count < 0) return MAPLE_E_ARG;
+    ctx->headSearches = count;
     return MAPLE_OK;
 }
 

@@ -1058,6 +1058,7 @@ struct BigScratch {
     int nSlots;
     unsigned long long* counter;  // slots handed out so far
     unsigned long long* started;  // not null: every CTA of the launch counts itself here when it starts (see k_wait_started)
+    unsigned long long headEnd;   // > 0: the first so many entries of the list are run one per warp (maple_ctx_set_head_searches)
 };
 
 template <bool SCAN2, bool EXTRAS>
@@ -1077,6 +1078,11 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
     // longest searches when the list is sorted longest-first -- start in different warps (the lanes of a warp share its time).
     // The counter then starts behind those entries (the host sets it).  totalWarps == 0: everything comes from the counter.
     bool firstPull = totalWarps > 0;
+    // Head of the list (big.headEnd entries, the longest searches when the list is sorted): pulled by lane 0 of every warp only,
+    // so each of them has a warp to itself and the warps share them out one at a time; the other lanes wait until the counter
+    // has passed the head, then everybody pulls as usual.
+    bool headOpen = big.headEnd == 0;
+    unsigned waitTick = 0;
     const ScratchD sOwn = s;
     StackE* const stackOwn = stack;
     bool usingBig = false;
@@ -1168,6 +1174,11 @@ __device__ __forceinline__ void fsm_warp_loop(const DevModel& sm, const DevTree&
                 if (outCycles) outCycles[i] = clock64() - c0;
                 stage = 0;
                 nCompleted++;
+            }
+            if (!headOpen && lane_ != 0) {  // the head is still being handed out: not my turn yet (look again every 64 iterations)
+                firstPull = false;
+                if ((waitTick++ & 63u) == 0u && ld_volatile_u64(counter) >= big.headEnd) headOpen = true;
+                if (!headOpen) { f.op = OP_NONE; break; }
             }
             if (firstPull) {
                 firstPull = false;

@@ -154,6 +154,10 @@ class MapleEngine:
         """The first `count` entries of every following search batch run on an SM of their own each (0 = off)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_critical_searches(self.ctx, int(count)), "maple_ctx_set_critical_searches")
 
+    def set_head_searches(self, count: int):
+        """The first `count` entries of every following search batch are handed out one per warp before all lanes pull (0 = off)."""
+        capi.check(self.ctx, self.lib.maple_ctx_set_head_searches(self.ctx, int(count)), "maple_ctx_set_head_searches")
+
     def set_scan_service(self, fsm_sms: int):
         """SMs whose CTAs own the searches while all others only serve subtree scans (-1 = chosen per launch, 0 = off)."""
         capi.check(self.ctx, self.lib.maple_ctx_set_scan_service(self.ctx, int(fsm_sms)), "maple_ctx_set_scan_service")

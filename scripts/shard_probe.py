@@ -60,3 +60,21 @@ for k in ([int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0,
     c = c2.cpu().numpy()
     print("critical %3s (set %d): %s ms | longest search %.1f ms | records equal to the full round's: %s" % (
         "auto" if k < 0 else k, getattr(tree, "_critical_set", 0), " ".join("%.1f" % t for t in ts), c.max() / 1.965e6, same), flush=True)
+# head of the list handed out one per warp (maple_ctx_set_head_searches)
+for h in ([int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else []):
+    eng.set_head_searches(h)
+    ts = []
+    for rep in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c2 = torch.zeros(len(mine), dtype=torch.int64, device=eng.device)
+        a.record()
+        out = tree.spr_search(mine, p, cycles=c2, critical=0)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    rec = tree.search_records(out)
+    pos = {int(nd): i for i, nd in enumerate(nodes)}
+    sel = np.array([pos[int(nd)] for nd in mine])
+    same = all(np.array_equal(rec[f], full[f][sel]) for f in ("status", "placement", "phase1", "bLenAppend"))
+    print("head %6d: %s ms | records equal to the full round's: %s" % (h, " ".join("%.1f" % t for t in ts), same), flush=True)
+eng.set_head_searches(0)

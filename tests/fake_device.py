@@ -174,6 +174,9 @@ class FakeLib:
     def maple_ctx_set_critical_searches(self, ctx, n):
         return 0
 
+    def maple_ctx_set_head_searches(self, ctx, n):
+        return 0
+
     def maple_ctx_set_dense_scoring(self, ctx, mode, max_bytes):
         return 0
 

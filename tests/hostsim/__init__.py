@@ -113,7 +113,7 @@ class WarpKernelOnHost(Oracle):
 
     def search_batch_warp(self, tree: dict, lists, params: dict, nodes, scan_form: int = 2, scan_min_size: int = 8, lanes_per_warp: int = 3,
                           pool_bytes: int = 10240, scan_flags: int = 0, scratch_keys: int = 8192, stats=None, big_slots: int = 0,
-                          owner_warps: int = 1, server_warps: int = 0, dense_rows: int = 0, eval_slice: int = 1024):
+                          owner_warps: int = 1, server_warps: int = 0, dense_rows: int = 0, eval_slice: int = 1024, head_end: int = 0):
         """scan_form: 0 no scans, 1 first form (search_fsm.cuh: warp_scan_job), 2 second form (scan2.cuh: warp_scan_job2).
         server_warps > 0 (scan form 2): the scan service -- owner_warps warps own the searches and post their subtree scans, server_warps
         warps only serve them (scan2.cuh: ScanQueue, scan_server_loop), all emulated together.  dense_rows > 0 (scan form 2): the
@@ -128,7 +128,7 @@ class WarpKernelOnHost(Oracle):
         out = np.zeros(len(nodes), dtype=SEARCH_RESULT_DTYPE)
         npay = np.ascontiguousarray(lists.npay, np.int32)
         rc = self.W.hw_search_batch(self.mp, C.addressof(t), C.addressof(sp), len(nodes), _p(nodes), int(scratch_keys), _p(npay), int(scan_form),
-                                    int(scan_min_size), int(lanes_per_warp), int(pool_bytes), int(scan_flags), int(big_slots), int(owner_warps), int(server_warps), int(dense_rows), int(eval_slice), _p(out), _p(stats))
+                                    int(scan_min_size), int(lanes_per_warp), int(pool_bytes), int(scan_flags), int(big_slots), int(owner_warps), int(server_warps), int(dense_rows), int(eval_slice), int(head_end), _p(out), _p(stats))
         if rc != 0:
             raise RuntimeError("hw_search_batch: scan form %d not available for this tree" % scan_form)
         return out

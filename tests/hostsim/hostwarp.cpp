@@ -34,6 +34,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
                     int32_t ownerWarps /* scan service: warps that own searches ... */, int32_t serverWarps /* ... and warps that only serve scans; 0 = no service */,
                     int32_t denseRows /* dense scoring pass: rows of the score matrix (searches that get one), 0 = off */,
                     int32_t evalSlice /* warp-wide evaluation of queued phase-2 entries: scratch entries per lane, 0 = the owning lane does it */,
+                    int32_t headEnd /* head of the list handed out one per warp (BigScratch::headEnd), 0 = off */,
                     SearchResult* out, unsigned long long* stats) {
     DevTree T;
     memset(&T, 0, sizeof T);
@@ -108,7 +109,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
     const size_t warpSmem = (fixed + (size_t)poolBytes + 64) / 16;
     std::vector<uint4> smem(warpSmem * nWarps);
     // one warp without the service: lane k starts with entry k (fsm_warp_loop); with it everything comes from the counter
-    unsigned long long counter = service ? 0ULL : (unsigned long long)lanesPerWarp, bigCounter = 0;
+    unsigned long long counter = service ? 0ULL : (unsigned long long)(headEnd > 0 ? 1 : lanesPerWarp), bigCounter = 0;
     unsigned long long wst[kNumSearchStats] = {0};
     BigScratch big;
     memset(&big, 0, sizeof big);
@@ -118,6 +119,7 @@ int hw_search_batch(const DevModel* m, const OrTree* t, const SearchParams* sp, 
     std::vector<StackE> bstack((size_t)bigSlots * stackCap + 1);
     big.key = bkey.data(); big.pay = bpay.data(); big.ais = bais.data(); big.stack = bstack.data();
     big.nSlots = bigSlots; big.counter = &bigCounter;
+    big.headEnd = (!service && headEnd > 0) ? (unsigned long long)headEnd : 0ULL;
     ScanQueue sq;
     memset(&sq, 0, sizeof sq);
     unsigned long long qctl[4] = {0, 0, 0, 0};

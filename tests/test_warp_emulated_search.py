@@ -130,6 +130,20 @@ def test_dense_scoring_pass(rv, err, strict, ml, rows):
     assert 0 < st[30] <= rows and st[21] > 1000
 
 
+def test_head_of_the_list_one_search_per_warp():
+    """BigScratch::headEnd (maple_ctx_set_head_searches): the first entries of the list pulled by lane 0 only, the other lanes
+    waiting until they are gone -- every head length from 'one entry' to 'the whole list' gives the records of the plain run."""
+    g = load_golden("ay_unrest_300")
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    hs, hw = KernelSourceOnHost(model), WarpKernelOnHost(model)
+    ta, nodes = tree_arrays(g), np.array(searched_nodes(g), np.int32)[::3]
+    lists = _prefilled_lists(g, Oracle(model))
+    want = hs.search_batch(ta, lists, search_params(g), nodes, scratch_keys=1 << 15)
+    for head in (1, 7, len(nodes) // 2, len(nodes)):
+        got = hw.search_batch_warp(ta, lists, search_params(g), nodes, scan_form=2, lanes_per_warp=5, big_slots=8, head_end=head)
+        _same(got, want)
+
+
 @pytest.mark.parametrize("eval_slice", [1024, 96, 0])
 def test_queued_phase2_entries_evaluated_by_the_warp(eval_slice):
     """The phase-2 entries a subtree scan queues are evaluated one per lane (search_fsm.cuh: warp_eval_queue) and folded in the
