@@ -2,7 +2,7 @@
 
   cuobjdump -xelf all libmaple_b200.so; nvdisasm -g -c *.cubin > all.txt
   ncu -i rep.ncu-rep --page source --csv --print-source sass > sass.csv
-  python scripts/ncu_attr.py all.txt sass.csv '<mangled kernel prefix>' [top]
+  python scripts/ncu_attr.py all.txt sass.csv '<mangled kernel prefix>' [top [csrc dir of the profiled build]]
 
 Prints, per source function (found by line ranges in the files under maple_b200/csrc), the warp instructions executed, the
 average active threads, the stall samples and the share of 'no instruction' samples; then the hottest source lines."""
@@ -10,6 +10,7 @@ import collections, csv, re, sys
 
 dis, sass, prefix = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+csrc = sys.argv[5] if len(sys.argv) > 5 else None  # the sources the profiled library was built from, if not the current ones
 # offset -> (file, line)
 loc = {}
 cur = None
@@ -31,7 +32,7 @@ for ln in open(dis, errors="replace"):
 # function line ranges
 funcs = {}
 import glob, os
-for f in glob.glob(os.path.join(os.path.dirname(__file__), "..", "maple_b200", "csrc", "*")):
+for f in glob.glob(os.path.join(csrc or os.path.join(os.path.dirname(__file__), "..", "maple_b200", "csrc"), "*")):
     starts = []
     for i, ln in enumerate(open(f, errors="replace"), 1):
         m = re.match(r"^(?:template\s*<[^>]*>\s*)?(?:static\s+)?(?:__device__|__global__|__host__|inline|__forceinline__|__noinline__|\s)+[\w:<>\*&\s]+?\b(\w+)\s*\(", ln)
