@@ -140,3 +140,46 @@ def test_search_seam_wrapper_on_reference_trees(name):
     assert moves == sorted(moves, key=lambda m: m[2])
     assert sorted(m[:2] for m in moves) == sorted((m[0], m[1]) for core in g["proposed"] for m in core)  # the reference's own proposedMoves
     assert (rec["status"] == 0).sum() > 50
+
+
+def test_launch_shape_is_chosen_by_measurement(monkeypatch):
+    """DeviceTree._critical_auto (tree.py): for a batch size the first sorted round runs plain and is timed, the next runs with the
+    longest searches on SMs of their own and is timed, the faster shape is kept; a batch of another size starts over; searches
+    without a recorded length only get measured.  The timers are stubbed -- the decision logic is what is tested here."""
+    import torch
+    g = load_golden("ex_unrest")
+    model = MapleModel.from_reference_snapshot(g["env"], g["model"])
+    a = tree_arrays(g)
+    tree = DeviceTree.from_lists(FakeEngine(model), a["up"], a["child0"], a["child1"], a["dist"], a["root"], a["isTip"], tree_lists(g),
+                                 mutStart=a["mutStart"], mut=a["mut"], numMinor=a["numMinor"])
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+
+    class Ev:
+        def __init__(self, ms):
+            self.ms = ms
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return other.ms
+
+    def run(n, cost, ms):
+        k, rec = tree._critical_auto(torch.tensor(cost, dtype=torch.int64), n)
+        if rec is not None:
+            rec["ev"] = (Ev(0.0), Ev(ms))  # what spr_search records around the launch
+        return k, rec is not None
+
+    big = torch.iinfo(torch.int64).max
+    n = 1000
+    cost = [900, 800, 500, 460, 300] + [10] * (n - 5)
+    assert run(n, [big] * n, 0.0) == (0, False)            # nothing measured yet: plain, untimed
+    assert run(n, cost, 400.0) == (0, True)                # plain, timed
+    k, timed = run(n, cost, 300.0)                         # critical, timed: the searches at least half as long as the longest
+    assert (k, timed) == (4, True)
+    assert run(n, cost, 0.0) == (4, False) and tree._critical_state["choice"] == "on"   # 300 < 0.97 * 400: kept
+    assert run(n, cost, 0.0) == (4, False)
+    assert run(2 * n, cost + [10] * n, 500.0) == (0, True)  # another batch size: start over
+    assert run(2 * n, cost + [10] * n, 499.0)[1] is True
+    assert run(2 * n, cost + [10] * n, 0.0) == (0, False) and tree._critical_state["choice"] == "off"  # 499 is not < 0.97 * 500
+    assert tree._critical_count(torch.tensor([5] * 10, dtype=torch.int64), 10) == 0  # too few searches for a second launch
